@@ -1,0 +1,235 @@
+"""Generate the golden vectors under tests/golden/ from the REAL reference.  TEST INFRASTRUCTURE.
+
+Runs only in the build container (needs the read-only checkout at /root/reference, imported
+through ``oracle/refshim`` + ``oracle/refshim_orch``).  The outputs
+are small ``.npz`` files that travel to the GPU box, where the reference does not exist.
+
+    python oracle/make_golden.py            # rewrites tests/golden/*.npz
+
+Two kinds of fixture:
+
+* ``calls_*.npz``  -- seeded synthetic inputs pushed through every hot-path method of the
+  reference's ``DefaultInference`` (per-call isolation parity);
+* ``tape_*.npz``   -- every ``Inference`` call (inputs AND outputs) the reference's own
+  ``DeseqDataSet.deseq2()`` + ``DeseqStats.summary()`` make on the datasets shipped with the
+  reference, plus the final LFC/dispersion/p-value tables and the stored R DESeq2 results
+  (``tests/data/**/r_test_res.csv``) for those datasets.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for d in ("refshim", "refshim_orch"):
+    sys.path.insert(0, os.path.join(HERE, d))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import pandas as pd  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def synth(N, G, design, seed=0):
+    """SURVEY.md §8(d) generator (DESeq2 makeExampleDESeqDataSet-like)."""
+    from pydeseq2_b200.synth import make_counts
+
+    return make_counts(N, G, design, seed)
+
+
+def ref_inference():
+    from pydeseq2.default_inference import DefaultInference
+
+    class FloatFlags(DefaultInference):
+        """pandas-3 compatibility: converged as float."""
+
+        def irls(self, *a, **k):
+            b, m, h, c = super().irls(*a, **k)
+            return b, m, h, np.asarray(c, dtype=float)
+
+        def alpha_mle(self, *a, **k):
+            d, c = super().alpha_mle(*a, **k)
+            return d, np.asarray(c, dtype=float)
+
+    return FloatFlags(n_cpus=1)
+
+
+def gen_calls(name, N, G, design_kind, seed):
+    from pydeseq2.preprocessing import deseq2_norm
+
+    inf = ref_inference()
+    counts, X, _truth = synth(N, G, design_kind, seed)
+    # drop all-zero genes like dds.py:729-731
+    counts = counts[:, ~(counts == 0).all(0)]
+    normed, sf = deseq2_norm(counts)
+    p = X.shape[1]
+    out = dict(counts=counts, X=X, sf=sf, normed=normed)
+    out["rough"] = inf.fit_rough_dispersions(normed, pd.DataFrame(X))
+    out["moments"] = inf.fit_moments_dispersions(normed, sf)
+    max_disp = max(10.0, N)
+    mom = np.clip(np.minimum(out["rough"], out["moments"]), 1e-8, max_disp)
+    out["mom"] = mom
+    out["lin_mu"] = inf.lin_reg_mu(counts, sf, X, 0.5)
+    b, m, h, c = inf.irls(counts, sf, X, mom, 0.5, 1e-8)
+    out.update(irls0_beta=b, irls0_mu=np.ascontiguousarray(m), irls0_hat=np.ascontiguousarray(h), irls0_conv=c)
+    mu_hat = np.ascontiguousarray(out["lin_mu"] if design_kind == "two_level" else m)
+    out["mu_hat"] = mu_hat
+    a, c = inf.alpha_mle(counts, X, mu_hat, mom, 1e-8, max_disp)
+    out.update(gw_alpha=a, gw_conv=c)
+    gw = np.clip(a, 1e-8, max_disp)
+    # a synthetic "trend" for the MAP stage (any positive vector is a valid alpha_hat)
+    rng = np.random.default_rng(seed + 1)
+    trend = gw * np.exp(rng.normal(0, 0.3, gw.shape))
+    out["trend"] = trend
+    out["prior_var"] = np.float64(0.6)
+    a, c = inf.alpha_mle(counts, X, mu_hat, trend, 1e-8, max_disp, prior_disp_var=0.6, cr_reg=True, prior_reg=True)
+    out.update(map_alpha=a, map_conv=c)
+    disp = np.clip(a, 1e-8, max_disp)
+    out["disp"] = disp
+    b, m, h, c = inf.irls(counts, sf, X, disp, 0.5, 1e-8)
+    out.update(lfc_beta=b, lfc_mu=np.ascontiguousarray(m), lfc_hat=np.ascontiguousarray(h), lfc_conv=c)
+    contrast = np.zeros(p)
+    contrast[1] = 1.0
+    ridge = np.diag(np.repeat(1e-6, p))
+    out.update(contrast=contrast, ridge=ridge)
+    mu_w = np.ascontiguousarray(m)
+    for alt, null in ((None, 0.0), ("greater", 0.3), ("less", 0.3), ("greaterAbs", 0.3), ("lessAbs", 0.3)):
+        pv, st, se = inf.wald_test(X, disp, b, mu_w, ridge, contrast, null, alt)
+        tag = alt or "two_sided"
+        out[f"wald_{tag}_p"], out[f"wald_{tag}_stat"], out[f"wald_{tag}_se"] = pv, st, se
+    coeffs, pred, ok = inf.dispersion_trend_gamma_glm(pd.Series(1.0 / normed.mean(0)), pd.Series(gw))
+    out.update(trend_coeffs=coeffs, trend_pred=pred, trend_ok=np.float64(ok))
+    np.savez_compressed(os.path.join(OUT, f"calls_{name}.npz"), **out)
+    print(f"calls_{name}: N={N} G={counts.shape[1]} p={p}")
+
+
+class Tape:
+    """Wraps an Inference and records every hot-path call."""
+
+    def __init__(self, inner):
+        self._inner = inner
+        self.calls = []
+
+    n_cpus = property(lambda s: s._inner.n_cpus, lambda s, v: setattr(s._inner, "n_cpus", v))
+
+    def __getattr__(self, name):
+        fn = getattr(self._inner, name)
+        if name not in ("lin_reg_mu", "irls", "alpha_mle", "wald_test", "fit_rough_dispersions",
+                        "fit_moments_dispersions", "dispersion_trend_gamma_glm"):
+            return fn
+
+        def rec(*a, **k):
+            res = fn(*a, **k)
+            self.calls.append((name, a, k, res))
+            return res
+
+        return rec
+
+
+def _arr(v):
+    if isinstance(v, (pd.Series, pd.DataFrame)):
+        v = v.values
+    if v is None:
+        return np.array(np.nan)
+    return np.ascontiguousarray(np.asarray(v, dtype=float) if not isinstance(v, str) else np.array(v))
+
+
+def gen_tape(name, counts_df, metadata, design_df, contrast, r_res_csv, r_disp_csv=None, **dds_kwargs):
+    from pydeseq2.dds import DeseqDataSet
+    from pydeseq2.ds import DeseqStats
+
+    tape = Tape(ref_inference())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dds = DeseqDataSet(counts=counts_df, metadata=metadata, design=design_df, inference=tape, quiet=True,
+                           **dds_kwargs)
+        dds.deseq2()
+        ds = DeseqStats(dds, contrast=np.asarray(contrast, dtype=float), inference=tape, quiet=True)
+        ds.summary()
+    out = {}
+    for i, (meth, a, k, res) in enumerate(tape.calls):
+        pre = f"c{i:02d}_{meth}"
+        assert not a or meth in ("fit_rough_dispersions", "fit_moments_dispersions", "dispersion_trend_gamma_glm")
+        for j, v in enumerate(a):
+            out[f"{pre}__arg{j}"] = _arr(v)
+        for kk, v in k.items():
+            if kk == "alt_hypothesis":
+                out[f"{pre}__{kk}"] = np.array("" if v is None else v)
+            elif kk in ("cr_reg", "prior_reg"):
+                out[f"{pre}__{kk}"] = np.array(float(v))
+            else:
+                out[f"{pre}__{kk}"] = _arr(v)
+        res = res if isinstance(res, tuple) else (res,)
+        for j, v in enumerate(res):
+            out[f"{pre}__out{j}"] = _arr(v)
+    out["n_calls"] = np.array(len(tape.calls))
+    out["final_LFC"] = dds.varm["LFC"].values
+    out["final_dispersions"] = dds.var["dispersions"].values
+    out["final_genewise"] = dds.var["genewise_dispersions"].values
+    out["final_size_factors"] = dds.obs["size_factors"].values
+    out["final_pvalues"] = ds.p_values.values
+    out["final_stat"] = ds.statistics.values
+    out["final_se"] = ds.SE.values
+    out["final_padj"] = ds.padj.values
+    out["counts"] = counts_df.values.astype(np.int64)
+    out["design"] = design_df.values.astype(float)
+    out["contrast"] = np.asarray(contrast, dtype=float)
+    r = pd.read_csv(r_res_csv, index_col=0)
+    out["r_log2FoldChange"] = r["log2FoldChange"].values
+    out["r_pvalue"] = r["pvalue"].values
+    out["r_lfcSE"] = r["lfcSE"].values
+    out["r_stat"] = r["stat"].values
+    if r_disp_csv:
+        out["r_dispersions"] = pd.read_csv(r_disp_csv, index_col=0).squeeze().values
+    np.savez_compressed(os.path.join(OUT, f"tape_{name}.npz"), **out)
+    # sanity: reference vs R at the reference's own tolerance (tests/test_pydeseq2.py:932-942)
+    rel = np.nanmax(np.abs(r["log2FoldChange"].values - ds.results_df["log2FoldChange"].values)
+                    / np.abs(r["log2FoldChange"].values))
+    print(f"tape_{name}: {len(tape.calls)} calls, max rel LFC diff vs R = {rel:.2e}")
+
+
+def indicator(series, level):
+    return (series == level).astype(float)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    gen_calls("two_level_n24", 24, 40, "two_level", 0)
+    gen_calls("factorial_n30", 30, 40, "factorial", 1)
+    gen_calls("continuous_n40", 40, 40, "continuous", 2)
+    gen_calls("two_level_n200", 200, 64, "two_level", 3)
+
+    # shipped 100 x 10 synthetic dataset
+    counts = pd.read_csv(f"{REF}/datasets/synthetic/test_counts.csv", index_col=0).T
+    meta = pd.read_csv(f"{REF}/datasets/synthetic/test_metadata.csv", index_col=0)
+    d1 = pd.DataFrame({"Intercept": 1.0, "condition[T.B]": indicator(meta["condition"], "B")}, index=meta.index)
+    gen_tape("single_factor", counts, meta, d1, [0, 1], f"{REF}/tests/data/single_factor/r_test_res.csv",
+             f"{REF}/tests/data/single_factor/r_test_dispersions.csv")
+    d2 = pd.DataFrame({"Intercept": 1.0, "group[T.Y]": indicator(meta["group"], "Y"),
+                       "condition[T.B]": indicator(meta["condition"], "B")}, index=meta.index)
+    gen_tape("multi_factor", counts, meta, d2, [0, 0, 1], f"{REF}/tests/data/multi_factor/r_test_res.csv",
+             f"{REF}/tests/data/multi_factor/r_test_dispersions.csv")
+    # continuous covariate dataset
+    cc = pd.read_csv(f"{REF}/tests/data/continuous/test_counts.csv", index_col=0).T
+    cm = pd.read_csv(f"{REF}/tests/data/continuous/test_metadata.csv", index_col=0)
+    print("continuous metadata columns:", list(cm.columns))
+    d3 = pd.DataFrame({"Intercept": 1.0, "group[T.Y]": indicator(cm["group"], "Y"),
+                       "condition[T.B]": indicator(cm["condition"], "B"),
+                       "measurement": cm["measurement"].astype(float)}, index=cm.index)
+    gen_tape("continuous", cc, cm, d3, [0, 0, 0, 1], f"{REF}/tests/data/continuous/r_test_res.csv")
+    # wide dataset (more genes than samples)
+    wc = pd.read_csv(f"{REF}/tests/data/wide/test_counts.csv", index_col=0).T
+    wm = pd.read_csv(f"{REF}/tests/data/wide/test_metadata.csv", index_col=0)
+    print("wide metadata columns:", list(wm.columns), wc.shape)
+    d4 = pd.DataFrame({"Intercept": 1.0, "group[T.Y]": indicator(wm["group"], "Y"),
+                       "condition[T.B]": indicator(wm["condition"], "B")}, index=wm.index)
+    gen_tape("wide", wc, wm, d4, [0, 0, 1], f"{REF}/tests/data/wide/r_test_res.csv",
+             f"{REF}/tests/data/wide/r_test_dispersions.csv")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,51 @@
+"""Synthetic negative-binomial count generator.
+
+Modelled on DESeq2's ``makeExampleDESeqDataSet`` (which the reference's shipped
+``datasets/synthetic`` also derives from, ``/root/reference/datasets/README.md:6-8``):
+per gene ``beta0/ln2 ~ N(4, 2)``, other coefficients ``/ln2 ~ N(0, 0.5)``,
+``alpha_g = 4/exp(beta0) + 0.1``, ``sf_i = exp(N(0, 0.2))``, ``y ~ NB(mean=sf_i*exp(x_i.beta_g),
+size=1/alpha_g)`` as int64 in the reference's native layout: (N samples, G genes), C-contiguous,
+gene index fastest-varying (``dds.py:245-249``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+LN2 = np.log(2.0)
+
+DESIGNS = ("two_level", "factorial", "continuous")
+
+
+def design_matrix(N: int, kind: str, seed: int = 0) -> np.ndarray:
+    """The three design shapes BASELINE.json's configs name."""
+    i = np.arange(N)
+    cond = (i >= N // 2).astype(float)
+    if kind == "two_level":  # C2 / C5: p=2, lin_reg_mu branch of dds.py:747-756
+        cols = [np.ones(N), cond]
+    elif kind == "factorial":  # C3: p=3, four unique rows -> IRLS-initialised mu_hat (dds.py:757-765)
+        cols = [np.ones(N), cond, (i % 2).astype(float)]
+    elif kind == "continuous":  # C4: p=3 with a continuous covariate
+        z = np.random.default_rng(seed + 7919).normal(0.0, 1.0, N)
+        cols = [np.ones(N), cond, z]
+    else:
+        raise ValueError(f"unknown design kind {kind!r}; expected one of {DESIGNS}")
+    return np.ascontiguousarray(np.stack(cols, axis=1))
+
+
+def make_counts(N: int, G: int, kind: str = "two_level", seed: int = 0, chunk: int = 1 << 16):
+    """Return ``(counts int64 (N, G), X float64 (N, p), truth dict)``."""
+    rng = np.random.default_rng(seed)
+    X = design_matrix(N, kind, seed)
+    p = X.shape[1]
+    sf = np.exp(rng.normal(0.0, 0.2, N))
+    beta = np.empty((G, p))
+    beta[:, 0] = rng.normal(4.0, 2.0, G) * LN2
+    beta[:, 1:] = rng.normal(0.0, 0.5, (G, p - 1)) * LN2
+    alpha = 4.0 / np.exp(beta[:, 0]) + 0.1
+    counts = np.empty((N, G), dtype=np.int64)
+    for g0 in range(0, G, chunk):  # bounded temporaries for the 10^6-gene config
+        g1 = min(G, g0 + chunk)
+        mu = sf[:, None] * np.exp(X @ beta[g0:g1].T)
+        size = 1.0 / alpha[g0:g1]
+        counts[:, g0:g1] = rng.negative_binomial(size[None, :], size[None, :] / (size[None, :] + mu))
+    return counts, X, {"beta": beta, "alpha": alpha, "sf": sf}
