@@ -1,0 +1,162 @@
+/*
+ * pydeseq2_b200 -- C ABI of the B200 (sm_100a) backend for PyDESeq2's per-gene NB-GLM hot path.
+ *
+ * Every `pdq_*` compute entry point replaces one method of the reference's plugin interface
+ * `pydeseq2.inference.Inference` (reference file:line cited per function).  The reference binds
+ * to it with the ctypes stub shown in INTEGRATION.md (`pydeseq2_b200/_lib.py` is that stub).
+ *
+ * Conventions
+ *   - extern "C", plain pointers + sizes, caller-allocated outputs, no ownership crosses the ABI.
+ *   - Every function returns 0 on success or a negative `pdq_status`; `pdq_last_error(ctx)` gives text.
+ *   - (N, G) arrays are the reference's native layout: C-contiguous, sample-major, the gene index
+ *     is the fastest-varying one (`dds.py:752,759,779,902,954`: `self.X[:, self.non_zero_idx]`).
+ *     `ld` arguments are the row pitch in ELEMENTS (ld == G for a contiguous array).
+ *   - counts are int64, everything else float64 (`dds.py:245-249`); `converged` flags are returned
+ *     as float64 0/1 (the caller stores them in a NaN-initialised float column, `dds.py:796-797`).
+ *   - Two flavours of each hot call: `pdq_<op>` takes HOST buffers (the drop-in boundary: copies
+ *     in, launches, copies out, synchronises) and `pdq_<op>_dev` takes DEVICE buffers allocated
+ *     with `pdq_malloc` (resident pipeline; asynchronous on the context's stream).
+ *   - One context per backend object, not re-entrant (the reference's caller is single-threaded).
+ */
+#ifndef PYDESEQ2_B200_H
+#define PYDESEQ2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pdq_ctx pdq_ctx;       /* device, stream, scratch, NCCL communicator */
+typedef struct pdq_design pdq_design; /* device-resident design pack: X (N x p), size factors, (XtX)^+ */
+
+typedef enum pdq_status {
+    PDQ_OK = 0,
+    PDQ_ERR_CUDA = -1,        /* a CUDA runtime call failed */
+    PDQ_ERR_INVALID = -2,     /* bad argument (null pointer, N<=0, p<1, ld<G, ...) */
+    PDQ_ERR_UNSUPPORTED = -3, /* p > PDQ_MAX_P, or the design pack exceeds shared memory */
+    PDQ_ERR_NCCL = -4,        /* NCCL missing or a collective failed */
+    PDQ_ERR_NO_DEVICE = -5    /* no CUDA device / not an sm_100 part */
+} pdq_status;
+
+#define PDQ_MAX_P 8 /* design columns supported by the register-resident p x p solvers */
+
+/* alt_hypothesis codes of Inference.wald_test (utils.py:778-806) */
+#define PDQ_ALT_NONE 0
+#define PDQ_ALT_GREATER_ABS 1
+#define PDQ_ALT_LESS_ABS 2
+#define PDQ_ALT_GREATER 3
+#define PDQ_ALT_LESS 4
+
+/* ----------------------------------------------------------------- context / memory */
+int pdq_ctx_create(int device, pdq_ctx** out);
+void pdq_ctx_destroy(pdq_ctx* ctx);
+const char* pdq_last_error(const pdq_ctx* ctx);
+const char* pdq_version(void);
+int pdq_device_count(void);
+/* name, SM count, global memory bytes of the context's device */
+int pdq_device_info(const pdq_ctx* ctx, char* name, size_t name_len, int* sm_count, size_t* mem_bytes);
+/* lanes cooperating on one gene (1,2,4,8,16,32); 0 = choose from G (default) */
+int pdq_set_lanes_per_gene(pdq_ctx* ctx, int lanes);
+/* number of kernel launches issued through this context so far (bench.py `gpu_launches`) */
+int64_t pdq_launch_count(const pdq_ctx* ctx);
+
+int pdq_malloc(pdq_ctx* ctx, size_t bytes, void** dptr);
+int pdq_free(pdq_ctx* ctx, void* dptr);
+int pdq_host_alloc(pdq_ctx* ctx, size_t bytes, void** hptr); /* pinned host memory */
+int pdq_host_free(pdq_ctx* ctx, void* hptr);
+int pdq_memcpy_h2d(pdq_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
+int pdq_memcpy_d2h(pdq_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
+int pdq_memset(pdq_ctx* ctx, void* dst, int value, size_t bytes);
+int pdq_sync(pdq_ctx* ctx);
+/* CUDA-event timing on the context's stream (bench.py): record slot 0/1, elapsed ms between them */
+int pdq_event_record(pdq_ctx* ctx, int slot);
+int pdq_event_elapsed_ms(pdq_ctx* ctx, int slot_start, int slot_stop, float* ms);
+
+/* Design pack.  X is (N x p) row-major as the reference passes `design_matrix`
+ * (`dds.py:740`), size_factors (N,) may be NULL for calls that take none (alpha_mle, wald_test). */
+int pdq_design_create(pdq_ctx* ctx, const double* X, const double* size_factors, int N, int p,
+                      pdq_design** out);
+void pdq_design_destroy(pdq_ctx* ctx, pdq_design* d);
+
+/* ----------------------------------------------------------------- hot path, host buffers
+ * Inference.lin_reg_mu  (inference.py:12-43; default_inference.py:58-81; utils.py:682-715) */
+int pdq_lin_reg_mu(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N, int G,
+                   const double* size_factors, const double* X, int p, double min_mu,
+                   double* mu_out /* (N,G) ld=G */);
+
+/* Inference.irls  (inference.py:45-118; default_inference.py:83-124; utils.py:273-438).
+ * `mu_out` is the UNclamped mean, `hat_out` the hat-matrix diagonal, both (N,G) with ld=G.
+ * `n_fallback` (may be NULL) receives how many genes left the IRLS loop through the reference's
+ * optimiser branch (utils.py:374-413). */
+int pdq_irls(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N, int G,
+             const double* size_factors, const double* X, int p, const double* disp,
+             double min_mu, double beta_tol, double min_beta, double max_beta, int maxiter,
+             double* beta_out /* (G,p) */, double* mu_out, double* hat_out,
+             double* converged_out /* (G,) 0/1 */, int* n_fallback);
+
+/* Inference.alpha_mle  (inference.py:120-177; default_inference.py:126-161; utils.py:441-564;
+ * fallback grid_search.py:54-142).  `prior_disp_var` is ignored unless prior_reg != 0. */
+int pdq_alpha_mle(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N, int G,
+                  const double* X, int p, const double* mu, int64_t ld_mu,
+                  const double* alpha_hat, double min_disp, double max_disp,
+                  double prior_disp_var, int cr_reg, int prior_reg,
+                  double* alpha_out /* (G,) */, double* converged_out /* (G,) 0/1 */);
+
+/* Inference.wald_test  (inference.py:179-234; default_inference.py:163-198; utils.py:718-811).
+ * `ridge` is (p,p) row-major, `contrast` (p,), `lfc_null` in natural log, `alt` a PDQ_ALT_* code. */
+int pdq_wald_test(pdq_ctx* ctx, const double* X, int N, int p, const double* disp,
+                  const double* lfc /* (G,p) */, const double* mu, int64_t ld_mu, int G,
+                  const double* ridge, const double* contrast, double lfc_null, int alt,
+                  double* pvalue_out, double* stat_out, double* se_out);
+
+/* Inference.fit_rough_dispersions  (inference.py:236-258; utils.py:814-853) */
+int pdq_fit_rough_dispersions(pdq_ctx* ctx, const double* normed_counts, int64_t ld, int N, int G,
+                              const double* X, int p, double* alpha_out);
+/* Inference.fit_moments_dispersions  (inference.py:260-281; utils.py:856-885).  Computes every
+ * column; `all_zero_out[g]` = 1 marks the all-zero columns the reference drops (utils.py:878). */
+int pdq_fit_moments_dispersions(pdq_ctx* ctx, const double* normed_counts, int64_t ld, int N, int G,
+                                const double* size_factors, double* alpha_out, double* all_zero_out);
+
+/* ----------------------------------------------------------------- hot path, device-resident
+ * Same semantics; every pointer except `design` is device memory from pdq_malloc.  Asynchronous. */
+int pdq_lin_reg_mu_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld, int G,
+                       double min_mu, double* mu_out, int64_t ld_out);
+int pdq_irls_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld, int G,
+                 const double* disp, double min_mu, double beta_tol, double min_beta, double max_beta,
+                 int maxiter, double* beta_out, double* mu_out, double* hat_out, int64_t ld_out,
+                 double* converged_out, int* n_fallback_dev /* device int, may be NULL */);
+int pdq_alpha_mle_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld, int G,
+                      const double* mu, int64_t ld_mu, const double* alpha_hat, double min_disp,
+                      double max_disp, double prior_disp_var, int cr_reg, int prior_reg,
+                      double* alpha_out, double* converged_out);
+int pdq_wald_test_dev(pdq_ctx* ctx, const pdq_design* design, const double* disp, const double* lfc,
+                      const double* mu, int64_t ld_mu, int G, const double* ridge_host,
+                      const double* contrast_host, double lfc_null, int alt, double* pvalue_out,
+                      double* stat_out, double* se_out);
+/* Method-of-moments start values straight from raw counts (fuses `counts / size_factors`,
+ * fit_rough_dispersions, fit_moments_dispersions, the min() and clip of dds.py:1140-1162) and the
+ * per-gene normalised mean (`dds.py:708`).  Device-resident pipeline only. */
+int pdq_mom_dispersions_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld,
+                            int G, double min_disp, double max_disp, double* alpha_out,
+                            double* normed_mean_out);
+/* mu = size_factor * exp(X beta) for the Wald stage (ds.py:320-324), device-resident */
+int pdq_mu_from_lfc_dev(pdq_ctx* ctx, const pdq_design* design, const double* lfc, int G,
+                        double* mu_out, int64_t ld_out);
+
+/* ----------------------------------------------------------------- multi-GPU (gene shards)
+ * One process per GPU.  Rank 0 calls pdq_comm_unique_id and ships the 128 bytes to the other ranks
+ * (any out-of-band channel); every rank then calls pdq_comm_init.  The only exchange on the path is
+ * the all-gather of per-gene vectors (genewise dispersions + normalised means before the trend fit,
+ * final per-gene results at the end).  `count` doubles are contributed per rank. */
+#define PDQ_UNIQUE_ID_BYTES 128
+int pdq_comm_unique_id(pdq_ctx* ctx, void* id_out);
+int pdq_comm_init(pdq_ctx* ctx, const void* id, int world_size, int rank);
+int pdq_allgather_f64_dev(pdq_ctx* ctx, const double* send, double* recv, size_t count);
+int pdq_comm_destroy(pdq_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYDESEQ2_B200_H */

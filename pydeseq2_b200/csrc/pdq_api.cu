@@ -1,0 +1,602 @@
+// pdq_api.cu -- the C ABI declared in include/pydeseq2_b200.h (context, memory, host-buffer and
+// device-resident entry points, NCCL gene-shard exchange).  Host code only; kernels live in
+// pdq_kernels.cu.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "pdq_internal.h"
+#include "pdq_host_linalg.h"
+
+using namespace pdq;
+
+// --------------------------------------------------------------------------------------------- NCCL (dlopen)
+// NCCL is resolved at run time so that the library loads on boxes without it and never clashes with
+// the copy a host application (e.g. torch) already mapped: the soname lookup returns that same copy.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static const int kNcclFloat64 = 8;  // ncclDataType_t::ncclFloat64 (stable across NCCL 2.x)
+
+enum { kBufCounts, kBufA, kBufB, kBufC, kBufD, kBufE, kBufF, kBufG, kBufStatus, kBufMisc, kNumBufs };
+
+struct pdq_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaDeviceProp prop{};
+    int lanes_override = 0;
+    int64_t launches = 0;
+    std::string err;
+    void* buf[kNumBufs] = {};
+    size_t cap[kNumBufs] = {};
+    // cached design of the host-buffer entry points (keyed on the bytes of X and size factors)
+    pdq_design* cached = nullptr;
+    std::vector<double> cached_X, cached_sf;
+    NcclApi nccl;
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+};
+
+struct pdq_design {
+    DesignDev d;
+};
+
+static int fail(pdq_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        char tmp[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(tmp, sizeof tmp, fmt, ap);
+        va_end(ap);
+        c->err = tmp;
+    }
+    return code;
+}
+
+#define CU(c, call)                                                                                  \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(c, PDQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+static int ensure(pdq_ctx* c, int which, size_t bytes, void** out) {
+    if (bytes > c->cap[which]) {
+        if (c->buf[which]) CU(c, cudaFree(c->buf[which]));
+        c->buf[which] = nullptr;
+        c->cap[which] = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        CU(c, cudaMalloc(&c->buf[which], want));
+        c->cap[which] = want;
+    }
+    *out = c->buf[which];
+    return 0;
+}
+
+static int pick_lgT(const pdq_ctx* c, int G, int N) {
+    int T;
+    if (c->lanes_override) {
+        T = c->lanes_override;
+    } else {
+        // fill ~1024 resident threads per SM: T = smallest power of two with G*T >= SMs*1024, capped by 32
+        const double want = (double)c->prop.multiProcessorCount * 1024.0 / (double)(G > 0 ? G : 1);
+        T = 1;
+        while (T < 32 && (double)T < want) T <<= 1;
+    }
+    while (T > 1 && T > N) T >>= 1;  // never more lanes than samples
+    int lg = 0;
+    while ((1 << lg) < T) ++lg;
+    return lg;
+}
+
+static LaunchCfg cfg(const pdq_ctx* c, int G, int N) { return LaunchCfg{c->stream, pick_lgT(c, G, N), c->prop.multiProcessorCount}; }
+
+// --------------------------------------------------------------------------------------------- context
+extern "C" const char* pdq_version(void) { return "pydeseq2_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int pdq_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int pdq_ctx_create(int device, pdq_ctx** out) {
+    if (!out) return PDQ_ERR_INVALID;
+    *out = nullptr;
+    int n = pdq_device_count();
+    if (n <= 0 || device < 0 || device >= n) return PDQ_ERR_NO_DEVICE;
+    pdq_ctx* c = new pdq_ctx();
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&c->prop, device) != cudaSuccess) {
+        delete c;
+        return PDQ_ERR_NO_DEVICE;
+    }
+    if (c->prop.major < 10) {  // the fatbin holds sm_100a SASS only
+        delete c;
+        return PDQ_ERR_NO_DEVICE;
+    }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return PDQ_ERR_CUDA;
+    }
+    for (auto& e : c->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) {
+            delete c;
+            return PDQ_ERR_CUDA;
+        }
+    *out = c;
+    return PDQ_OK;
+}
+
+extern "C" void pdq_ctx_destroy(pdq_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
+    if (c->cached) pdq_design_destroy(c, c->cached);
+    for (auto& b : c->buf)
+        if (b) cudaFree(b);
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" const char* pdq_last_error(const pdq_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+extern "C" int pdq_device_info(const pdq_ctx* c, char* name, size_t name_len, int* sm_count, size_t* mem_bytes) {
+    if (!c) return PDQ_ERR_INVALID;
+    if (name && name_len) {
+        strncpy(name, c->prop.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = c->prop.multiProcessorCount;
+    if (mem_bytes) *mem_bytes = c->prop.totalGlobalMem;
+    return PDQ_OK;
+}
+
+extern "C" int pdq_set_lanes_per_gene(pdq_ctx* c, int lanes) {
+    if (!c) return PDQ_ERR_INVALID;
+    if (lanes != 0 && (lanes < 1 || lanes > 32 || (lanes & (lanes - 1)))) return fail(c, PDQ_ERR_INVALID, "lanes per gene must be 0 or a power of two <= 32");
+    c->lanes_override = lanes;
+    return PDQ_OK;
+}
+
+extern "C" int64_t pdq_launch_count(const pdq_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int pdq_malloc(pdq_ctx* c, size_t bytes, void** dptr) {
+    if (!c || !dptr) return PDQ_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMalloc(dptr, bytes ? bytes : 1));
+    return PDQ_OK;
+}
+extern "C" int pdq_free(pdq_ctx* c, void* dptr) {
+    if (!c) return PDQ_ERR_INVALID;
+    if (dptr) CU(c, cudaFree(dptr));
+    return PDQ_OK;
+}
+extern "C" int pdq_host_alloc(pdq_ctx* c, size_t bytes, void** hptr) {
+    if (!c || !hptr) return PDQ_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return PDQ_OK;
+}
+extern "C" int pdq_host_free(pdq_ctx* c, void* hptr) {
+    if (!c) return PDQ_ERR_INVALID;
+    if (hptr) CU(c, cudaFreeHost(hptr));
+    return PDQ_OK;
+}
+extern "C" int pdq_memcpy_h2d(pdq_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c) return PDQ_ERR_INVALID;
+    CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return PDQ_OK;
+}
+extern "C" int pdq_memcpy_d2h(pdq_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c) return PDQ_ERR_INVALID;
+    CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return PDQ_OK;
+}
+extern "C" int pdq_memset(pdq_ctx* c, void* dst, int value, size_t bytes) {
+    if (!c) return PDQ_ERR_INVALID;
+    CU(c, cudaMemsetAsync(dst, value, bytes, c->stream));
+    return PDQ_OK;
+}
+extern "C" int pdq_sync(pdq_ctx* c) {
+    if (!c) return PDQ_ERR_INVALID;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return PDQ_OK;
+}
+extern "C" int pdq_event_record(pdq_ctx* c, int slot) {
+    if (!c || slot < 0 || slot >= 4) return PDQ_ERR_INVALID;
+    CU(c, cudaEventRecord(c->ev[slot], c->stream));
+    return PDQ_OK;
+}
+extern "C" int pdq_event_elapsed_ms(pdq_ctx* c, int a, int b, float* ms) {
+    if (!c || !ms || a < 0 || a >= 4 || b < 0 || b >= 4) return PDQ_ERR_INVALID;
+    CU(c, cudaEventSynchronize(c->ev[b]));
+    CU(c, cudaEventElapsedTime(ms, c->ev[a], c->ev[b]));
+    return PDQ_OK;
+}
+
+// --------------------------------------------------------------------------------------------- design pack
+extern "C" int pdq_design_create(pdq_ctx* c, const double* X, const double* sf, int N, int p, pdq_design** out) {
+    if (!c || !X || !out || N <= 0 || p < 1) return fail(c, PDQ_ERR_INVALID, "pdq_design_create: bad arguments");
+    if (p > PDQ_MAX_P) return fail(c, PDQ_ERR_UNSUPPORTED, "design has %d columns; this build supports p <= %d", p, PDQ_MAX_P);
+    CU(c, cudaSetDevice(c->device));
+    pdq_design* d = new pdq_design();
+    DesignDev& dd = d->d;
+    dd.N = N;
+    dd.p = p;
+    dd.Npad = (N + 1) & ~1;
+    dd.smem_bytes = (size_t)(p + 2) * dd.Npad * 8 + 16;
+    if (dd.smem_bytes > kMaxDynSmem) {
+        delete d;
+        return fail(c, PDQ_ERR_UNSUPPORTED, "design pack (%d samples x %d columns = %zu bytes) exceeds the %zu-byte shared-memory stage", N, p,
+                    dd.smem_bytes, kMaxDynSmem);
+    }
+    design_linear_algebra(X, N, p, dd.pinv, &dd.full_rank);
+    std::vector<double> pack((size_t)(p + 2) * dd.Npad, 0.0);
+    double inv_sum = 0.0;
+    for (int n = 0; n < N; ++n) {
+        for (int j = 0; j < p; ++j) pack[(size_t)j * dd.Npad + n] = X[(size_t)n * p + j];
+        const double s = sf ? sf[n] : 1.0;
+        pack[(size_t)p * dd.Npad + n] = s;
+        pack[(size_t)(p + 1) * dd.Npad + n] = log(s);
+        inv_sum += 1.0 / s;
+    }
+    for (int n = N; n < dd.Npad; ++n) pack[(size_t)p * dd.Npad + n] = 1.0;
+    dd.s_mean_inv = inv_sum / N;
+    if (cudaMalloc((void**)&dd.pack, pack.size() * 8) != cudaSuccess) {
+        delete d;
+        return fail(c, PDQ_ERR_CUDA, "cudaMalloc(design pack) failed");
+    }
+    // synchronous copy: `pack` is a temporary
+    if (cudaMemcpy(dd.pack, pack.data(), pack.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(dd.pack);
+        delete d;
+        return fail(c, PDQ_ERR_CUDA, "cudaMemcpy(design pack) failed");
+    }
+    *out = d;
+    return PDQ_OK;
+}
+
+extern "C" void pdq_design_destroy(pdq_ctx* c, pdq_design* d) {
+    if (!d) return;
+    if (c) cudaSetDevice(c->device);
+    if (c && c->cached == d) c->cached = nullptr;
+    if (d->d.pack) cudaFree(d->d.pack);
+    delete d;
+}
+
+// design cache for the host-buffer entry points: deseq2() passes the same X (and size factors) to every call
+static int cached_design(pdq_ctx* c, const double* X, const double* sf, int N, int p, pdq_design** out) {
+    const size_t nx = (size_t)N * p;
+    bool hit = c->cached && c->cached->d.N == N && c->cached->d.p == p && c->cached_X.size() == nx &&
+               memcmp(c->cached_X.data(), X, nx * 8) == 0 && ((sf == nullptr) == c->cached_sf.empty()) &&
+               (!sf || memcmp(c->cached_sf.data(), sf, (size_t)N * 8) == 0);
+    if (!hit) {
+        if (c->cached) pdq_design_destroy(c, c->cached);
+        c->cached = nullptr;
+        pdq_design* d = nullptr;
+        if (int e = pdq_design_create(c, X, sf, N, p, &d)) return e;
+        c->cached = d;
+        c->cached_X.assign(X, X + nx);
+        if (sf) c->cached_sf.assign(sf, sf + N); else c->cached_sf.clear();
+    }
+    *out = c->cached;
+    return PDQ_OK;
+}
+
+// --------------------------------------------------------------------------------------------- device-resident ops
+#define CHECK_CTX(c) \
+    if (!(c)) return PDQ_ERR_INVALID; \
+    CU(c, cudaSetDevice((c)->device))
+
+static int done(pdq_ctx* c, int rc, const char* what) {
+    if (rc < 0) {
+        if (rc == PDQ_ERR_UNSUPPORTED) return fail(c, rc, "%s: unsupported design (p=%d..%d, shared-memory stage <= %zu bytes)", what, 1, PDQ_MAX_P, kMaxDynSmem);
+        return fail(c, rc, "%s: kernel launch failed: %s", what, cudaGetErrorString(cudaGetLastError()));
+    }
+    c->launches += rc;
+    return PDQ_OK;
+}
+
+extern "C" int pdq_lin_reg_mu_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, double min_mu,
+                                  double* mu_out, int64_t ld_out) {
+    CHECK_CTX(c);
+    if (!d || !counts || !mu_out || G <= 0 || ld < G || ld_out < G) return fail(c, PDQ_ERR_INVALID, "pdq_lin_reg_mu_dev: bad arguments");
+    return done(c, launch_lin_reg_mu(cfg(c, G, d->d.N), d->d, counts, ld, G, min_mu, mu_out, ld_out), "lin_reg_mu");
+}
+
+extern "C" int pdq_irls_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, const double* disp,
+                            double min_mu, double beta_tol, double min_beta, double max_beta, int maxiter, double* beta,
+                            double* mu, double* hat, int64_t ld_out, double* conv, int* n_fallback_dev) {
+    CHECK_CTX(c);
+    if (!d || !counts || !disp || !beta || !mu || !hat || !conv || G <= 0 || ld < G || ld_out < G)
+        return fail(c, PDQ_ERR_INVALID, "pdq_irls_dev: bad arguments");
+    void* status;
+    if (int e = ensure(c, kBufStatus, (size_t)G * sizeof(int), &status)) return e;
+    IrlsHost h{min_mu, beta_tol, min_beta, max_beta, maxiter};
+    return done(c, launch_irls(cfg(c, G, d->d.N), d->d, counts, ld, G, disp, h, beta, mu, hat, ld_out, conv, (int*)status, n_fallback_dev), "irls");
+}
+
+extern "C" int pdq_alpha_mle_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, const double* mu,
+                                 int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp, double prior_disp_var,
+                                 int cr_reg, int prior_reg, double* alpha, double* conv) {
+    CHECK_CTX(c);
+    if (!d || !counts || !mu || !alpha_hat || !alpha || !conv || G <= 0 || ld < G || ld_mu < G)
+        return fail(c, PDQ_ERR_INVALID, "pdq_alpha_mle_dev: bad arguments");
+    if (prior_reg && !(prior_disp_var > 0.0)) return fail(c, PDQ_ERR_INVALID, "alpha_mle: prior_reg needs prior_disp_var > 0");
+    void* status;
+    if (int e = ensure(c, kBufStatus, (size_t)G * sizeof(int), &status)) return e;
+    return done(c, launch_alpha_mle(cfg(c, G, d->d.N), d->d, counts, ld, G, mu, ld_mu, alpha_hat, min_disp, max_disp, prior_disp_var,
+                                    cr_reg, prior_reg, alpha, conv, (int*)status), "alpha_mle");
+}
+
+extern "C" int pdq_wald_test_dev(pdq_ctx* c, const pdq_design* d, const double* disp, const double* lfc, const double* mu,
+                                 int64_t ld_mu, int G, const double* ridge, const double* contrast, double lfc_null, int alt,
+                                 double* pv, double* stat, double* se) {
+    CHECK_CTX(c);
+    if (!d || !disp || !lfc || !mu || !ridge || !contrast || !pv || !stat || !se || G <= 0 || ld_mu < G || alt < 0 || alt > 4)
+        return fail(c, PDQ_ERR_INVALID, "pdq_wald_test_dev: bad arguments");
+    return done(c, launch_wald(cfg(c, G, d->d.N), d->d, disp, lfc, mu, ld_mu, G, ridge, contrast, lfc_null, alt, pv, stat, se), "wald_test");
+}
+
+extern "C" int pdq_mom_dispersions_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, double min_disp,
+                                       double max_disp, double* alpha, double* normed_mean) {
+    CHECK_CTX(c);
+    if (!d || !counts || !alpha || !normed_mean || G <= 0 || ld < G) return fail(c, PDQ_ERR_INVALID, "pdq_mom_dispersions_dev: bad arguments");
+    if (d->d.N == d->d.p) return fail(c, PDQ_ERR_INVALID, "The number of samples and the number of design variables are equal");
+    return done(c, launch_mom_from_counts(cfg(c, G, d->d.N), d->d, counts, ld, G, min_disp, max_disp, alpha, normed_mean), "mom_dispersions");
+}
+
+extern "C" int pdq_mu_from_lfc_dev(pdq_ctx* c, const pdq_design* d, const double* lfc, int G, double* mu, int64_t ld_out) {
+    CHECK_CTX(c);
+    if (!d || !lfc || !mu || G <= 0 || ld_out < G) return fail(c, PDQ_ERR_INVALID, "pdq_mu_from_lfc_dev: bad arguments");
+    return done(c, launch_mu_from_lfc(cfg(c, G, d->d.N), d->d, lfc, G, mu, ld_out), "mu_from_lfc");
+}
+
+// --------------------------------------------------------------------------------------------- host-buffer ops
+static int h2d_2d(pdq_ctx* c, void* dst, const void* src, int64_t ld, int N, int G, size_t elem) {
+    if (ld == G) {
+        CU(c, cudaMemcpyAsync(dst, src, (size_t)N * G * elem, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        CU(c, cudaMemcpy2DAsync(dst, (size_t)G * elem, src, (size_t)ld * elem, (size_t)G * elem, N, cudaMemcpyHostToDevice, c->stream));
+    }
+    return 0;
+}
+
+extern "C" int pdq_lin_reg_mu(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, const double* sf, const double* X, int p,
+                              double min_mu, double* mu_out) {
+    CHECK_CTX(c);
+    if (!counts || !sf || !X || !mu_out || N <= 0 || G <= 0 || ld < G) return fail(c, PDQ_ERR_INVALID, "pdq_lin_reg_mu: bad arguments");
+    pdq_design* d;
+    if (int e = cached_design(c, X, sf, N, p, &d)) return e;
+    void *dc, *dm;
+    const size_t ng = (size_t)N * G;
+    if (int e = ensure(c, kBufCounts, ng * 8, &dc)) return e;
+    if (int e = ensure(c, kBufA, ng * 8, &dm)) return e;
+    if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
+    if (int e = pdq_lin_reg_mu_dev(c, d, (const int64_t*)dc, G, G, min_mu, (double*)dm, G)) return e;
+    CU(c, cudaMemcpyAsync(mu_out, dm, ng * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return PDQ_OK;
+}
+
+extern "C" int pdq_irls(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, const double* sf, const double* X, int p,
+                        const double* disp, double min_mu, double beta_tol, double min_beta, double max_beta, int maxiter,
+                        double* beta_out, double* mu_out, double* hat_out, double* conv_out, int* n_fallback) {
+    CHECK_CTX(c);
+    if (!counts || !sf || !X || !disp || !beta_out || !mu_out || !hat_out || !conv_out || N <= 0 || G <= 0 || ld < G)
+        return fail(c, PDQ_ERR_INVALID, "pdq_irls: bad arguments");
+    pdq_design* d;
+    if (int e = cached_design(c, X, sf, N, p, &d)) return e;
+    const size_t ng = (size_t)N * G;
+    void *dc, *dmu, *dhat, *ddisp, *dbeta, *dconv, *dmisc;
+    if (int e = ensure(c, kBufCounts, ng * 8, &dc)) return e;
+    if (int e = ensure(c, kBufA, ng * 8, &dmu)) return e;
+    if (int e = ensure(c, kBufB, ng * 8, &dhat)) return e;
+    if (int e = ensure(c, kBufC, (size_t)G * 8, &ddisp)) return e;
+    if (int e = ensure(c, kBufD, (size_t)G * p * 8, &dbeta)) return e;
+    if (int e = ensure(c, kBufE, (size_t)G * 8, &dconv)) return e;
+    if (int e = ensure(c, kBufMisc, 64, &dmisc)) return e;
+    if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
+    CU(c, cudaMemcpyAsync(ddisp, disp, (size_t)G * 8, cudaMemcpyHostToDevice, c->stream));
+    if (int e = pdq_irls_dev(c, d, (const int64_t*)dc, G, G, (const double*)ddisp, min_mu, beta_tol, min_beta, max_beta, maxiter,
+                             (double*)dbeta, (double*)dmu, (double*)dhat, G, (double*)dconv, (int*)dmisc))
+        return e;
+    CU(c, cudaMemcpyAsync(beta_out, dbeta, (size_t)G * p * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(conv_out, dconv, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(mu_out, dmu, ng * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(hat_out, dhat, ng * 8, cudaMemcpyDeviceToHost, c->stream));
+    int nfb = 0;
+    CU(c, cudaMemcpyAsync(&nfb, dmisc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (n_fallback) *n_fallback = nfb;
+    return PDQ_OK;
+}
+
+extern "C" int pdq_alpha_mle(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, const double* X, int p, const double* mu,
+                             int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp, double prior_disp_var,
+                             int cr_reg, int prior_reg, double* alpha_out, double* conv_out) {
+    CHECK_CTX(c);
+    if (!counts || !X || !mu || !alpha_hat || !alpha_out || !conv_out || N <= 0 || G <= 0 || ld < G || ld_mu < G)
+        return fail(c, PDQ_ERR_INVALID, "pdq_alpha_mle: bad arguments");
+    pdq_design* d;
+    if (int e = cached_design(c, X, nullptr, N, p, &d)) return e;
+    const size_t ng = (size_t)N * G;
+    void *dc, *dmu, *dah, *dal, *dconv;
+    if (int e = ensure(c, kBufCounts, ng * 8, &dc)) return e;
+    if (int e = ensure(c, kBufA, ng * 8, &dmu)) return e;
+    if (int e = ensure(c, kBufC, (size_t)G * 8, &dah)) return e;
+    if (int e = ensure(c, kBufD, (size_t)G * 8, &dal)) return e;
+    if (int e = ensure(c, kBufE, (size_t)G * 8, &dconv)) return e;
+    if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
+    if (int e = h2d_2d(c, dmu, mu, ld_mu, N, G, 8)) return e;
+    CU(c, cudaMemcpyAsync(dah, alpha_hat, (size_t)G * 8, cudaMemcpyHostToDevice, c->stream));
+    if (int e = pdq_alpha_mle_dev(c, d, (const int64_t*)dc, G, G, (const double*)dmu, G, (const double*)dah, min_disp, max_disp,
+                                  prior_disp_var, cr_reg, prior_reg, (double*)dal, (double*)dconv))
+        return e;
+    CU(c, cudaMemcpyAsync(alpha_out, dal, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(conv_out, dconv, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return PDQ_OK;
+}
+
+extern "C" int pdq_wald_test(pdq_ctx* c, const double* X, int N, int p, const double* disp, const double* lfc, const double* mu,
+                             int64_t ld_mu, int G, const double* ridge, const double* contrast, double lfc_null, int alt,
+                             double* pv_out, double* stat_out, double* se_out) {
+    CHECK_CTX(c);
+    if (!X || !disp || !lfc || !mu || !ridge || !contrast || !pv_out || !stat_out || !se_out || N <= 0 || G <= 0 || ld_mu < G)
+        return fail(c, PDQ_ERR_INVALID, "pdq_wald_test: bad arguments");
+    pdq_design* d;
+    if (int e = cached_design(c, X, nullptr, N, p, &d)) return e;
+    const size_t ng = (size_t)N * G;
+    void *dmu, *ddisp, *dlfc, *dp, *ds, *dse;
+    if (int e = ensure(c, kBufA, ng * 8, &dmu)) return e;
+    if (int e = ensure(c, kBufC, (size_t)G * 8, &ddisp)) return e;
+    if (int e = ensure(c, kBufD, (size_t)G * p * 8, &dlfc)) return e;
+    if (int e = ensure(c, kBufE, (size_t)G * 8, &dp)) return e;
+    if (int e = ensure(c, kBufF, (size_t)G * 8, &ds)) return e;
+    if (int e = ensure(c, kBufG, (size_t)G * 8, &dse)) return e;
+    if (int e = h2d_2d(c, dmu, mu, ld_mu, N, G, 8)) return e;
+    CU(c, cudaMemcpyAsync(ddisp, disp, (size_t)G * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dlfc, lfc, (size_t)G * p * 8, cudaMemcpyHostToDevice, c->stream));
+    if (int e = pdq_wald_test_dev(c, d, (const double*)ddisp, (const double*)dlfc, (const double*)dmu, G, G, ridge, contrast, lfc_null,
+                                  alt, (double*)dp, (double*)ds, (double*)dse))
+        return e;
+    CU(c, cudaMemcpyAsync(pv_out, dp, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(stat_out, ds, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(se_out, dse, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return PDQ_OK;
+}
+
+extern "C" int pdq_fit_rough_dispersions(pdq_ctx* c, const double* normed, int64_t ld, int N, int G, const double* X, int p,
+                                         double* alpha_out) {
+    CHECK_CTX(c);
+    if (!normed || !X || !alpha_out || N <= 0 || G <= 0 || ld < G) return fail(c, PDQ_ERR_INVALID, "pdq_fit_rough_dispersions: bad arguments");
+    if (N == p) return fail(c, PDQ_ERR_INVALID, "The number of samples and the number of design variables are equal");
+    pdq_design* d;
+    if (int e = cached_design(c, X, nullptr, N, p, &d)) return e;
+    const size_t ng = (size_t)N * G;
+    void *dn, *da;
+    if (int e = ensure(c, kBufA, ng * 8, &dn)) return e;
+    if (int e = ensure(c, kBufC, (size_t)G * 8, &da)) return e;
+    if (int e = h2d_2d(c, dn, normed, ld, N, G, 8)) return e;
+    if (int e = done(c, launch_rough(cfg(c, G, N), d->d, (const double*)dn, G, G, (double*)da), "fit_rough_dispersions")) return e;
+    CU(c, cudaMemcpyAsync(alpha_out, da, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return PDQ_OK;
+}
+
+extern "C" int pdq_fit_moments_dispersions(pdq_ctx* c, const double* normed, int64_t ld, int N, int G, const double* sf,
+                                           double* alpha_out, double* all_zero_out) {
+    CHECK_CTX(c);
+    if (!normed || !sf || !alpha_out || !all_zero_out || N <= 0 || G <= 0 || ld < G)
+        return fail(c, PDQ_ERR_INVALID, "pdq_fit_moments_dispersions: bad arguments");
+    // a one-column design carries the size factors (the moments estimator does not use X)
+    std::vector<double> ones((size_t)N, 1.0);
+    pdq_design* d;
+    if (int e = cached_design(c, ones.data(), sf, N, 1, &d)) return e;
+    const size_t ng = (size_t)N * G;
+    void *dn, *da, *dz;
+    if (int e = ensure(c, kBufA, ng * 8, &dn)) return e;
+    if (int e = ensure(c, kBufC, (size_t)G * 8, &da)) return e;
+    if (int e = ensure(c, kBufE, (size_t)G * 8, &dz)) return e;
+    if (int e = h2d_2d(c, dn, normed, ld, N, G, 8)) return e;
+    if (int e = done(c, launch_moments(cfg(c, G, N), d->d, (const double*)dn, G, G, (double*)da, (double*)dz), "fit_moments_dispersions")) return e;
+    CU(c, cudaMemcpyAsync(alpha_out, da, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(all_zero_out, dz, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return PDQ_OK;
+}
+
+// --------------------------------------------------------------------------------------------- NCCL gene-shard exchange
+static int nccl_load(pdq_ctx* c) {
+    if (c->nccl.handle) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        c->nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (c->nccl.handle) break;
+    }
+    if (!c->nccl.handle) return fail(c, PDQ_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    auto sym = [&](const char* s) { return dlsym(c->nccl.handle, s); };
+    c->nccl.GetUniqueId = (decltype(c->nccl.GetUniqueId))sym("ncclGetUniqueId");
+    c->nccl.CommInitRank = (decltype(c->nccl.CommInitRank))sym("ncclCommInitRank");
+    c->nccl.AllGather = (decltype(c->nccl.AllGather))sym("ncclAllGather");
+    c->nccl.CommDestroy = (decltype(c->nccl.CommDestroy))sym("ncclCommDestroy");
+    c->nccl.GetErrorString = (decltype(c->nccl.GetErrorString))sym("ncclGetErrorString");
+    if (!c->nccl.GetUniqueId || !c->nccl.CommInitRank || !c->nccl.AllGather || !c->nccl.CommDestroy)
+        return fail(c, PDQ_ERR_NCCL, "libnccl is missing a required symbol");
+    return 0;
+}
+
+static int nccl_fail(pdq_ctx* c, ncclResult_t r, const char* what) {
+    return fail(c, PDQ_ERR_NCCL, "%s failed: %s", what, c->nccl.GetErrorString ? c->nccl.GetErrorString(r) : "nccl error");
+}
+
+extern "C" int pdq_comm_unique_id(pdq_ctx* c, void* id_out) {
+    CHECK_CTX(c);
+    if (!id_out) return PDQ_ERR_INVALID;
+    if (int e = nccl_load(c)) return e;
+    ncclUniqueId id;
+    ncclResult_t r = c->nccl.GetUniqueId(&id);
+    if (r != 0) return nccl_fail(c, r, "ncclGetUniqueId");
+    static_assert(sizeof(id) == PDQ_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    memcpy(id_out, &id, sizeof id);
+    return PDQ_OK;
+}
+
+extern "C" int pdq_comm_init(pdq_ctx* c, const void* id, int world, int rank) {
+    CHECK_CTX(c);
+    if (!id || world < 1 || rank < 0 || rank >= world) return fail(c, PDQ_ERR_INVALID, "pdq_comm_init: bad arguments");
+    if (int e = nccl_load(c)) return e;
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    ncclResult_t r = c->nccl.CommInitRank(&c->comm, world, uid, rank);
+    if (r != 0) return nccl_fail(c, r, "ncclCommInitRank");
+    c->world = world;
+    c->rank = rank;
+    return PDQ_OK;
+}
+
+extern "C" int pdq_allgather_f64_dev(pdq_ctx* c, const double* send, double* recv, size_t count) {
+    CHECK_CTX(c);
+    if (!send || !recv) return PDQ_ERR_INVALID;
+    if (!c->comm) {  // single rank: the gather is a copy
+        if (send != recv) CU(c, cudaMemcpyAsync(recv, send, count * 8, cudaMemcpyDeviceToDevice, c->stream));
+        return PDQ_OK;
+    }
+    ncclResult_t r = c->nccl.AllGather(send, recv, count, kNcclFloat64, c->comm, c->stream);
+    if (r != 0) return nccl_fail(c, r, "ncclAllGather");
+    return PDQ_OK;
+}
+
+extern "C" int pdq_comm_destroy(pdq_ctx* c) {
+    CHECK_CTX(c);
+    if (c->comm) {
+        c->nccl.CommDestroy(c->comm);
+        c->comm = nullptr;
+    }
+    c->world = 1;
+    c->rank = 0;
+    return PDQ_OK;
+}

@@ -1,0 +1,859 @@
+// pdq_gene.cuh -- the per-gene routines of the hot path, one cooperative lane-group per gene.
+//
+// Work decomposition: a group of T = 1,2,4,...,32 lanes of one warp owns one gene;
+// lane `si` of the group walks samples si, si+T, si+2T, ... so that, with 32/T adjacent genes per warp,
+// every warp-wide load of the (N, G) sample-major arrays touches T rows x (32/T) contiguous genes.
+// Per-gene sums (X^T W X, X^T W z, deviance, score terms) are butterfly-reduced across the group
+// with warp shuffles; after the butterfly every lane of the group holds bit-identical totals, so the
+// p x p Cholesky work and all control flow are replicated per lane without further communication.
+//
+// The same source is compiled for the device and for the host emulator (Group::sum is the identity
+// there, T = 1), see pdq_math.cuh.
+#pragma once
+
+#include "pdq_math.cuh"
+
+namespace pdq {
+
+struct Group {
+    int si;   // this lane's first sample
+    int T;    // lanes per gene (sample stride)
+    int gpw;  // genes per warp = 32 / T
+    PDQ_HD double sum(double v) const {
+#if defined(__CUDA_ARCH__)
+        for (int off = 16; off >= gpw; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+#endif
+        return v;
+    }
+    PDQ_HD bool any(bool p) const {
+#if defined(__CUDA_ARCH__)
+        return __any_sync(0xffffffffu, p) != 0;
+#else
+        return p;
+#endif
+    }
+};
+
+// staged design pack (shared memory on the device): X column-major [P][Npad], sf, log sf
+struct DesignS {
+    const double* X;
+    const double* sf;
+    const double* lsf;
+    int N;
+    int Npad;
+};
+
+template <int P>
+struct SmallMat {
+    double v[P * P];
+};
+
+template <int P>
+PDQ_HD void load_x(const DesignS& d, int n, double (&x)[P]) {
+#pragma unroll
+    for (int j = 0; j < P; ++j) x[j] = d.X[j * d.Npad + n];
+}
+
+template <int P>
+PDQ_HD void group_sum_sym(const Group& g, Sym<P>& s) {
+#pragma unroll
+    for (int k = 0; k < P * (P + 1) / 2; ++k) s.a[k] = g.sum(s.a[k]);
+}
+
+template <int P>
+PDQ_HD void group_sum_vec(const Group& g, double (&v)[P]) {
+#pragma unroll
+    for (int k = 0; k < P; ++k) v[k] = g.sum(v[k]);
+}
+
+// =============================================================================================
+// (a4) lin_reg_mu -- utils.py:682-715.  OLS of counts/sf on X, mu = max(sf * X beta, min_mu).
+// `pinv` = (X^T X)^+ (host, from the SVD of X) so beta = pinv X^T (y / sf) is the least-squares
+// (minimum-norm if rank deficient) solution sklearn's LinearRegression returns.
+// =============================================================================================
+template <int P>
+PDQ_HD void linmu_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pinv, const int64_t* y,
+                       int64_t ld, double min_mu, double* mu_out, int64_t ld_out, bool valid) {
+    double v[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) v[j] = 0.0;
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        double x[P];
+        load_x<P>(d, n, x);
+        const double t = (double)y[n * ld] / d.sf[n];
+#pragma unroll
+        for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
+    }
+    group_sum_vec<P>(grp, v);
+    double beta[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) s = fma(pinv.v[i * P + j], v[j], s);
+        beta[i] = s;
+    }
+    if (!valid) return;
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        double x[P];
+        load_x<P>(d, n, x);
+        double e = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) e = fma(x[j], beta[j], e);
+        const double m = d.sf[n] * e;
+        mu_out[n * ld_out] = (m < min_mu) ? min_mu : m;  // np.maximum (NaN propagates)
+    }
+}
+
+// =============================================================================================
+// (a1) irls -- utils.py:273-438.
+// =============================================================================================
+struct IrlsParams {
+    double min_mu, beta_tol, min_beta, max_beta;
+    int maxiter;
+    int full_rank;
+};
+
+// one fused sweep over the gene's samples at coefficient vector `beta`:
+//   A = X^T W X, b = X^T W z  (utils.py:368-371, W and z from the CLAMPED mu)
+//   S = sum (y + r) log(r + mu) - y log(mu)  -- the mu-dependent part of nb_nll (utils.py:220-234)
+template <int P>
+PDQ_HD void irls_sweep(const Group& grp, const DesignS& d, const int64_t* y, int64_t ld, const double (&beta)[P],
+                       double alpha, double r, double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P],
+                       double& S) {
+    sym_zero<P>(A);
+#pragma unroll
+    for (int j = 0; j < P; ++j) b[j] = 0.0;
+    S = 0.0;
+#pragma unroll 2
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        double x[P];
+        load_x<P>(d, n, x);
+        const double yv = (double)y[n * ld];
+        double eta = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
+        const double mu_raw = d.sf[n] * exp(eta);
+        const bool cl = mu_raw < min_mu;
+        const double mu = cl ? min_mu : mu_raw;                        // np.maximum(sf*exp(X b), min_mu)
+        const double lmu_sf = cl ? (log_min_mu - d.lsf[n]) : eta;      // log(mu / sf)
+        const double lmu = cl ? log_min_mu : (eta + d.lsf[n]);         // log(mu)
+        const double den = fma(mu, alpha, 1.0);
+        const double q = 1.0 / (mu * den);
+        const double W = mu * mu * q;                                  // mu / (1 + mu alpha)
+        const double z = fma(yv - mu, den * q, lmu_sf);                // log(mu/sf) + (y - mu)/mu
+        sym_rank1<P>(A, W, x);
+        const double Wz = W * z;
+#pragma unroll
+        for (int j = 0; j < P; ++j) b[j] = fma(Wz, x[j], b[j]);
+        S += fma(yv + r, log(r + mu), -yv * lmu);
+    }
+    group_sum_sym<P>(grp, A);
+    group_sum_vec<P>(grp, b);
+    S = grp.sum(S);
+}
+
+// status codes written per gene
+constexpr int kIrlsOk = 0;
+constexpr int kIrlsNeedsOptimizer = 1;  // left through utils.py:374 (|beta|>max_beta or i>=maxiter)
+
+template <int P>
+PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pinv, const IrlsParams& prm,
+                      const int64_t* y, int64_t ld, double alpha, double* beta_out, double* mu_out,
+                      double* hat_out, int64_t ld_out, double* conv_out, int* status_out, bool valid) {
+    const double r = 1.0 / alpha;
+    const double Nd = (double)d.N;
+    const double log_min_mu = log(prm.min_mu);
+
+    // ---- start value (utils.py:349-357) and the mu-independent part of nb_nll ----------------
+    double v[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) v[j] = 0.0;
+    double lgsum = 0.0, logmean = 0.0;
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        double x[P];
+        load_x<P>(d, n, x);
+        const double yv = (double)y[n * ld];
+        const double q = yv / d.sf[n];
+        if (prm.full_rank) {
+            const double t = log(q + 0.1);
+#pragma unroll
+            for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
+        } else {
+            logmean += log(q);
+        }
+        lgsum += lgamma_pos(yv + 1.0) - lgamma_pos(yv + r);
+    }
+    group_sum_vec<P>(grp, v);
+    lgsum = grp.sum(lgsum);
+    double beta[P];
+    if (prm.full_rank) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < P; ++j) s = fma(pinv.v[i * P + j], v[j], s);
+            beta[i] = s;
+        }
+    } else {
+        logmean = grp.sum(logmean);
+#pragma unroll
+        for (int i = 0; i < P; ++i) beta[i] = 0.0;
+        beta[0] = logmean / Nd;
+    }
+    // nb_nll = C + S(mu):  C = N r log(alpha) + N lgamma(r) + sum lgamma(y+1) - lgamma(y+r)
+    const double C = Nd * r * log(alpha) + Nd * lgamma_pos(r) + lgsum;
+
+    // ---- IRLS loop (utils.py:359-421) ---------------------------------------------------------
+    Sym<P> A;
+    double b[P], S;
+    irls_sweep<P>(grp, d, y, ld, beta, alpha, r, prm.min_mu, log_min_mu, A, b, S);
+    double dev = 1000.0, ratio = 1.0;
+    int it = 0, status = kIrlsOk;
+    bool active = true;
+    for (;;) {
+        if (active && !(ratio > prm.beta_tol)) active = false;  // `while dev_ratio > beta_tol` (NaN exits)
+        if (!grp.any(active)) break;
+        Sym<P> L = A;
+#pragma unroll
+        for (int i = 0; i < P; ++i) L.a[tri(i, i)] += kRidge;
+        chol<P>(L);
+        double bh[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) bh[j] = b[j];
+        chol_solve<P>(L, bh);
+        if (active) {
+            ++it;
+            bool div = it >= prm.maxiter;
+#pragma unroll
+            for (int j = 0; j < P; ++j) div = div || (fabs(bh[j]) > prm.max_beta);
+            if (div) {
+                status = kIrlsNeedsOptimizer;
+                active = false;
+            } else {
+#pragma unroll
+                for (int j = 0; j < P; ++j) beta[j] = bh[j];
+            }
+        }
+        // frozen groups recompute the same sums (keeps the warp's shuffles uniform)
+        irls_sweep<P>(grp, d, y, ld, beta, alpha, r, prm.min_mu, log_min_mu, A, b, S);
+        if (active) {
+            const double old = dev;
+            dev = -2.0 * (C + S);
+            ratio = fabs(dev - old) / (fabs(dev) + 0.1);
+        }
+    }
+
+    // ---- outputs: hat diagonal from the clamped mu, mu itself unclamped (utils.py:423-438) -----
+    Sym<P> Hinv;
+    {
+        Sym<P> L = A;
+#pragma unroll
+        for (int i = 0; i < P; ++i) L.a[tri(i, i)] += kRidge;
+        chol<P>(L);
+        chol_inverse<P>(L, Hinv);
+    }
+    if (!valid) return;
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        double x[P];
+        load_x<P>(d, n, x);
+        double eta = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
+        const double mu_raw = d.sf[n] * exp(eta);
+        const double mu = (mu_raw < prm.min_mu) ? prm.min_mu : mu_raw;
+        const double W = mu / fma(mu, alpha, 1.0);
+        mu_out[n * ld_out] = mu_raw;
+        hat_out[n * ld_out] = W * sym_quad<P>(Hinv, x);
+    }
+    if (grp.si == 0) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) beta_out[j] = beta[j];
+        *conv_out = 1.0;  // IRLS exits are "converged" (utils.py:365); the optimiser branch overwrites
+        *status_out = status;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Optimiser branch of irls (utils.py:374-413): minimise f(beta) = nb_nll(y, max(sf e^{X beta}, min_mu), disp)
+// + 0.5 * 1e-6 |beta|^2 over the box [min_beta, max_beta]^p, started from the IRLS start value.
+// The reference uses scipy L-BFGS-B; f is convex in X beta wherever the clamp is inactive, so any
+// descent method reaches the same minimiser: here a projected Newton iteration with the exact
+// Hessian and Armijo backtracking.  Called for the (rare) genes flagged kIrlsNeedsOptimizer.
+// =============================================================================================
+template <int P>
+PDQ_HD void irls_obj_sweep(const Group& grp, const DesignS& d, const int64_t* y, int64_t ld, const double (&beta)[P],
+                           double alpha, double r, double min_mu, double log_min_mu, double& f, double (&g)[P],
+                           Sym<P>& H) {
+    sym_zero<P>(H);
+#pragma unroll
+    for (int j = 0; j < P; ++j) g[j] = 0.0;
+    f = 0.0;
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        double x[P];
+        load_x<P>(d, n, x);
+        const double yv = (double)y[n * ld];
+        double eta = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
+        const double mu_raw = d.sf[n] * exp(eta);
+        const bool cl = mu_raw < min_mu;
+        const double mu = cl ? min_mu : mu_raw;
+        const double lmu = cl ? log_min_mu : (eta + d.lsf[n]);
+        f += fma(yv + r, log(r + mu), -yv * lmu);
+        // df of the reference: -X^T y + ((r + y) mu / (r + mu)) X  (treats d mu / d eta = mu everywhere)
+        const double t = (r + yv) * mu / (r + mu);
+        const double gi = t - yv;
+        const double hi = t * r / (r + mu);  // d t / d eta where the clamp is inactive
+#pragma unroll
+        for (int j = 0; j < P; ++j) g[j] = fma(gi, x[j], g[j]);
+        sym_rank1<P>(H, hi, x);
+    }
+    f = grp.sum(f);
+    group_sum_vec<P>(grp, g);
+    group_sum_sym<P>(grp, H);
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        f = fma(0.5 * kRidge * beta[j], beta[j], f);
+        g[j] = fma(kRidge, beta[j], g[j]);
+        H.a[tri(j, j)] += kRidge;
+    }
+}
+
+template <int P>
+PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pinv, const IrlsParams& prm,
+                                const int64_t* y, int64_t ld, double alpha, double* beta_out, double* mu_out,
+                                double* hat_out, int64_t ld_out, double* conv_out, bool valid) {
+    const double r = 1.0 / alpha;
+    const double log_min_mu = log(prm.min_mu);
+    // start value: same as irls_gene (utils.py:349-357, `beta_init`)
+    double v[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) v[j] = 0.0;
+    double logmean = 0.0;
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        double x[P];
+        load_x<P>(d, n, x);
+        const double q = (double)y[n * ld] / d.sf[n];
+        if (prm.full_rank) {
+            const double t = log(q + 0.1);
+#pragma unroll
+            for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
+        } else {
+            logmean += log(q);
+        }
+    }
+    group_sum_vec<P>(grp, v);
+    double beta[P];
+    if (prm.full_rank) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < P; ++j) s = fma(pinv.v[i * P + j], v[j], s);
+            beta[i] = s;
+        }
+    } else {
+        logmean = grp.sum(logmean);
+#pragma unroll
+        for (int i = 0; i < P; ++i) beta[i] = 0.0;
+        beta[0] = logmean / (double)d.N;
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) beta[j] = fmin(fmax(beta[j], prm.min_beta), prm.max_beta);
+
+    double f, g[P];
+    Sym<P> H;
+    irls_obj_sweep<P>(grp, d, y, ld, beta, alpha, r, prm.min_mu, log_min_mu, f, g, H);
+    bool ok = false, active = valid;  // `valid` = this gene was flagged and is in range
+    for (int it = 0; it < 100; ++it) {
+        // projected-gradient norm (free variables only)
+        double pg = 0.0;
+        bool fixed[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            fixed[j] = (beta[j] <= prm.min_beta && g[j] > 0.0) || (beta[j] >= prm.max_beta && g[j] < 0.0);
+            if (!fixed[j]) pg = fmax(pg, fabs(g[j]));
+        }
+        if (active && (pg <= 1e-9 * (1.0 + fabs(f)) || !(pg == pg))) {
+            ok = (pg == pg);
+            active = false;
+        }
+        if (!grp.any(active)) break;
+        // Newton direction on the free set
+        Sym<P> L = H;
+        double dir[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            dir[i] = fixed[i] ? 0.0 : -g[i];
+            if (fixed[i]) {
+#pragma unroll
+                for (int j = 0; j < P; ++j)
+                    if (j != i) L.a[j <= i ? tri(i, j) : tri(j, i)] = 0.0;
+                L.a[tri(i, i)] = 1.0;
+            }
+        }
+        chol<P>(L);
+        chol_solve<P>(L, dir);
+        double slope = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) slope = fma(g[j], dir[j], slope);
+        if (!(slope < 0.0)) {  // not a descent direction (indefinite/NaN): steepest descent on the free set
+            slope = 0.0;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                dir[j] = fixed[j] ? 0.0 : -g[j];
+                slope = fma(g[j], dir[j], slope);
+            }
+        }
+        // backtracking line search with projection onto the box
+        double step = 1.0, fn = f, gn[P], bn[P];
+        Sym<P> Hn = H;
+        bool accepted = false;
+#pragma unroll
+        for (int j = 0; j < P; ++j) { gn[j] = g[j]; bn[j] = beta[j]; }
+        for (int ls = 0; ls < 30; ++ls) {
+            double bt[P], dec = 0.0;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                bt[j] = fmin(fmax(fma(step, dir[j], beta[j]), prm.min_beta), prm.max_beta);
+                dec = fma(g[j], bt[j] - beta[j], dec);
+            }
+            double ft, gt[P];
+            Sym<P> Ht;
+            irls_obj_sweep<P>(grp, d, y, ld, bt, alpha, r, prm.min_mu, log_min_mu, ft, gt, Ht);
+            const bool good = ft <= f + 1e-4 * dec;
+            if (active && !accepted && good) {
+                accepted = true;
+                fn = ft;
+                Hn = Ht;
+#pragma unroll
+                for (int j = 0; j < P; ++j) { gn[j] = gt[j]; bn[j] = bt[j]; }
+            }
+            if (!grp.any(active && !accepted)) break;
+            step *= 0.5;
+        }
+        if (active) {
+            if (!accepted) {  // line search failed: declare failure like res.success == False
+                active = false;
+                ok = false;
+            } else {
+                const double df = f - fn;
+                f = fn;
+                H = Hn;
+#pragma unroll
+                for (int j = 0; j < P; ++j) { g[j] = gn[j]; beta[j] = bn[j]; }
+                if (df <= 1e-15 * (1.0 + fabs(f))) {  // no further decrease possible in FP64
+                    active = false;
+                    ok = true;
+                }
+            }
+        }
+    }
+    // outputs exactly like the tail of irls_solver: W from clamped mu, ridge 1e-6, mu unclamped
+    Sym<P> A;
+    sym_zero<P>(A);
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        double x[P];
+        load_x<P>(d, n, x);
+        double eta = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
+        const double mu_raw = d.sf[n] * exp(eta);
+        const double mu = (mu_raw < prm.min_mu) ? prm.min_mu : mu_raw;
+        sym_rank1<P>(A, mu / fma(mu, alpha, 1.0), x);
+    }
+    group_sum_sym<P>(grp, A);
+    Sym<P> Hinv;
+#pragma unroll
+    for (int i = 0; i < P; ++i) A.a[tri(i, i)] += kRidge;
+    chol<P>(A);
+    chol_inverse<P>(A, Hinv);
+    if (!valid) return;
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        double x[P];
+        load_x<P>(d, n, x);
+        double eta = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
+        const double mu_raw = d.sf[n] * exp(eta);
+        const double mu = (mu_raw < prm.min_mu) ? prm.min_mu : mu_raw;
+        mu_out[n * ld_out] = mu_raw;
+        hat_out[n * ld_out] = mu / fma(mu, alpha, 1.0) * sym_quad<P>(Hinv, x);
+    }
+    if (grp.si == 0) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) beta_out[j] = beta[j];
+        *conv_out = ok ? 1.0 : 0.0;
+    }
+}
+
+// =============================================================================================
+// (a2) alpha_mle -- utils.py:441-564.
+// The objective in x = log(alpha) (utils.py:509-520) and its derivative (utils.py:522-544):
+//   loss  = nb_nll(y, mu, a) + [cr] 0.5 logdet(X^T W X) + [prior] (x - xhat)^2 / (2 var),   W = mu/(1+mu a)
+//   dloss = a dnb_nll + [cr] -0.5 a tr((X^T W X)^-1 X^T W^2 X) + [prior] (x - xhat)/var
+// =============================================================================================
+struct AlphaParams {
+    double lo, hi;  // log(min_disp), log(max_disp)
+    double prior_var;
+    int cr_reg, prior_reg;
+};
+
+// derivative only (the minimiser is located as a root of dloss)
+template <int P>
+PDQ_HD double alpha_dloss(const Group& grp, const DesignS& d, const AlphaParams& prm, const int64_t* y, int64_t ld,
+                          const double* mu, int64_t ld_mu, double x, double xhat) {
+    const double a = exp(x), r = 1.0 / a, Nd = (double)d.N;
+    double Sg = 0.0;
+    Sym<P> A, B;
+    sym_zero<P>(A);
+    sym_zero<P>(B);
+#pragma unroll 2
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        const double yv = (double)y[n * ld];
+        const double m = mu[n * ld_mu];
+        const double rm = r + m;
+        const double inv = 1.0 / rm;
+        Sg += log(rm) - digamma_pos(yv + r) + (yv - m) * inv;
+        if (prm.cr_reg) {
+            double xv[P];
+            load_x<P>(d, n, xv);
+            const double W = m * r * inv;
+            sym_rank1<P>(A, W, xv);
+            sym_rank1<P>(B, W * W, xv);
+        }
+    }
+    Sg = grp.sum(Sg);
+    // a * dnb_nll = -r * sum[psi(r) - psi(y+r) + log(1 + mu a) + (y - mu)/(mu + r)],  log(1+mu a) = x + log(r+mu)
+    double g = -r * (Nd * (digamma_pos(r) + x) + Sg);
+    if (prm.cr_reg) {
+        group_sum_sym<P>(grp, A);
+        group_sum_sym<P>(grp, B);
+        Sym<P> Ainv;
+        chol<P>(A);
+        chol_inverse<P>(A, Ainv);
+        g -= 0.5 * a * sym_dot<P>(Ainv, B);
+    }
+    if (prm.prior_reg) g += (x - xhat) / prm.prior_var;
+    return g;
+}
+
+// loss value up to the alpha-independent constant  sum lgamma(y+1) - y log(mu)  (irrelevant to argmin)
+template <int P>
+PDQ_HD double alpha_loss(const Group& grp, const DesignS& d, int cr_reg, int prior_reg, double prior_var,
+                         const int64_t* y, int64_t ld, const double* mu, int64_t ld_mu, double x, double xhat) {
+    const double a = exp(x), r = 1.0 / a, Nd = (double)d.N;
+    double Sf = 0.0;
+    Sym<P> A;
+    sym_zero<P>(A);
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        const double yv = (double)y[n * ld];
+        const double m = mu[n * ld_mu];
+        const double rm = r + m;
+        Sf += fma(yv + r, log(rm), -lgamma_pos(yv + r));
+        if (cr_reg) {
+            double xv[P];
+            load_x<P>(d, n, xv);
+            sym_rank1<P>(A, m * r / rm, xv);
+        }
+    }
+    Sf = grp.sum(Sf);
+    double f = Nd * (r * x + lgamma_pos(r)) + Sf;
+    if (cr_reg) {
+        group_sum_sym<P>(grp, A);
+        chol<P>(A);
+        f += 0.5 * chol_logdet<P>(A);
+    }
+    if (prior_reg) f += (x - xhat) * (x - xhat) / (2.0 * prior_var);
+    return f;
+}
+
+constexpr int kAlphaOk = 0;
+constexpr int kAlphaNeedsGrid = 1;  // the reference's `res.success == False` branch (utils.py:556-564)
+
+// Bounded root search on dloss, shaped after what 1-D L-BFGS-B does from the same start: project x0 into
+// the box, take a unit step against the gradient, then secant (= 1-D BFGS) steps; once the root is
+// bracketed the secant point is safeguarded by the bracket (bisection when it leaves it or stalls).
+template <int P>
+PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& prm, const int64_t* y, int64_t ld,
+                       const double* mu, int64_t ld_mu, double alpha_hat, double* alpha_out, double* conv_out,
+                       int* status_out, bool valid) {
+    const double xhat = log(alpha_hat);
+    const double tolx = 1e-5;   // last secant step is taken unevaluated: final error << tolx
+    double xb = fmin(fmax(xhat, prm.lo), prm.hi);
+    double gb = alpha_dloss<P>(grp, d, prm, y, ld, mu, ld_mu, xb, xhat);
+    double xa = xb, ga = gb;
+    double bl = prm.lo, br = prm.hi;  // bracket ends (valid when have_br)
+    bool have_br = false, active = true, fail = false;
+    double xres = xb, xt = xb;
+    int stall = 0;
+    // decide the first trial point
+    if (!(gb == gb)) {
+        fail = true;
+        active = false;
+    } else if (gb == 0.0 || (gb > 0.0 && xb <= prm.lo) || (gb < 0.0 && xb >= prm.hi)) {
+        active = false;  // stationary, or the projected gradient vanishes at a bound
+    } else {
+        xt = fmin(fmax(xb - sgn(gb) * 1.0, prm.lo), prm.hi);
+    }
+    for (int ev = 0; ev < 60; ++ev) {
+        if (!grp.any(active)) break;
+        const double gt = alpha_dloss<P>(grp, d, prm, y, ld, mu, ld_mu, xt, xhat);
+        if (!active) continue;
+        if (!(gt == gt)) {
+            fail = true;
+            active = false;
+            continue;
+        }
+        // bracket bookkeeping: the minimum lies where dloss goes from - (left end) to + (right end)
+        if (have_br) {
+            if (gt < 0.0) bl = xt; else br = xt;
+        } else if ((gt < 0.0) != (gb < 0.0) && gt != 0.0) {
+            have_br = true;
+            bl = (gt < 0.0) ? xt : xb;
+            br = (gt < 0.0) ? xb : xt;
+        }
+        const double prev_step = fabs(xb - xa);
+        xa = xb; ga = gb;
+        xb = xt; gb = gt;
+        xres = xb;
+        if (gt == 0.0) { active = false; continue; }
+        if (!have_br && ((gb > 0.0 && xb <= prm.lo) || (gb < 0.0 && xb >= prm.hi))) {
+            active = false;  // pushed against a bound: L-BFGS-B stops with zero projected gradient
+            continue;
+        }
+        // next point
+        const double dx = xb - xa, dg = gb - ga;
+        double xn;
+        if (have_br) {
+            xn = xb - gb * dx / dg;
+            // Brent-style safeguard: fall back to bisection when the secant point leaves the bracket or
+            // the steps have not been shrinking for two evaluations in a row
+            if (ev > 0 && fabs(dx) > 0.5 * prev_step) ++stall; else stall = 0;
+            const bool inside = (xn > bl) && (xn < br);
+            if (!inside || !(dg != 0.0) || stall >= 2) {
+                xn = 0.5 * (bl + br);
+                stall = 0;
+            }
+            if (br - bl <= tolx) {  // bracket already tight: finish at the interpolated point
+                xres = xn;
+                active = false;
+                continue;
+            }
+        } else {
+            if (dg * dx > 0.0) {
+                xn = xb - gb * dx / dg;                      // secant = 1-D BFGS step
+                const double cap = 8.0 * fabs(dx);           // keep extrapolation bounded
+                if (fabs(xn - xb) > cap) xn = xb - sgn(gb) * cap;
+            } else {
+                xn = xb - sgn(gb) * 2.0 * fabs(dx);          // non-convex stretch: keep walking downhill
+            }
+            xn = fmin(fmax(xn, prm.lo), prm.hi);
+        }
+        if (fabs(xn - xb) <= tolx) {
+            xres = xn;
+            active = false;
+            continue;
+        }
+        xt = xn;
+    }
+    if (active) fail = true;  // evaluation budget exhausted
+    if (valid && grp.si == 0) {
+        *alpha_out = exp(xres);
+        *conv_out = fail ? 0.0 : 1.0;
+        *status_out = fail ? kAlphaNeedsGrid : kAlphaOk;
+    }
+}
+
+// grid fallback (grid_search.py:54-142): 100-point grid on [lo, hi], then 100 points on +-1 cell around the
+// best; always cr_reg=True, prior_reg=False because the reference's call drops those flags (utils.py:558-562).
+template <int P>
+PDQ_HD void alpha_grid_gene(const Group& grp, const DesignS& d, double lo, double hi, const int64_t* y, int64_t ld,
+                            const double* mu, int64_t ld_mu, double* alpha_out, bool valid) {
+    const int K = 100;
+    const double delta = (hi - lo) / (double)(K - 1);
+    double best = 0.0, bestx = lo;
+    for (int k = 0; k < K; ++k) {
+        const double x = (k == K - 1) ? hi : fma((double)k, delta, lo);
+        const double f = alpha_loss<P>(grp, d, 1, 0, 1.0, y, ld, mu, ld_mu, x, 0.0);
+        if (k == 0 || f < best) { best = f; bestx = x; }  // np.argmin: first minimum, NaN-free case
+    }
+    const double flo = bestx - delta, fhi = bestx + delta;
+    const double fd = (fhi - flo) / (double)(K - 1);
+    double bestf = flo;
+    for (int k = 0; k < K; ++k) {
+        const double x = (k == K - 1) ? fhi : fma((double)k, fd, flo);
+        const double f = alpha_loss<P>(grp, d, 1, 0, 1.0, y, ld, mu, ld_mu, x, 0.0);
+        if (k == 0 || f < best) { best = f; bestf = x; }
+    }
+    if (valid && grp.si == 0) *alpha_out = exp(bestf);
+}
+
+// =============================================================================================
+// (a3) wald_test -- utils.py:718-811.
+// =============================================================================================
+template <int P>
+struct WaldParams {
+    double ridge[P * P];
+    double contrast[P];
+    double lfc_null;
+    int alt;
+};
+
+template <int P>
+PDQ_HD void wald_gene(const Group& grp, const DesignS& d, const WaldParams<P>& prm, double disp, const double* lfc,
+                      const double* mu, int64_t ld_mu, double* p_out, double* stat_out, double* se_out, bool valid) {
+    Sym<P> M;
+    sym_zero<P>(M);
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        double x[P];
+        load_x<P>(d, n, x);
+        const double m = mu[n * ld_mu];
+        sym_rank1<P>(M, m / fma(m, disp, 1.0), x);
+    }
+    group_sum_sym<P>(grp, M);
+    Sym<P> L = M, H;
+#pragma unroll
+    for (int i = 0; i < P; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L.a[tri(i, j)] += prm.ridge[i * P + j];
+    chol<P>(L);
+    chol_inverse<P>(L, H);
+    double Hc[P], MHc[P];
+    sym_matvec<P>(H, prm.contrast, Hc);
+    sym_matvec<P>(M, Hc, MHc);
+    double q = 0.0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) q = fma(Hc[j], MHc[j], q);
+    const double se = sqrt(q);
+    double b[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) b[j] = lfc[j];
+    const double t0 = prm.lfc_null;
+    double stat, pv;
+    // each variant applies the elementwise transform to every coefficient, then dots with the contrast
+    auto greater = [&](double t, double& s, double& p) {
+        s = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], fmax((b[j] - t) / se, 0.0), s);
+        p = norm_sf(s);
+    };
+    auto less = [&](double t, double& s, double& p) {
+        s = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], fmin((b[j] - t) / se, 0.0), s);
+        p = norm_sf(fabs(s));
+    };
+    if (prm.alt == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], b[j] - t0, s);
+        stat = s / se;
+        pv = 2.0 * norm_sf(fabs(stat));
+    } else if (prm.alt == 1) {  // greaterAbs
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], sgn(b[j]) * fmax((fabs(b[j]) - t0) / se, 0.0), s);
+        stat = s;
+        pv = 2.0 * norm_sf(fabs(s));
+    } else if (prm.alt == 2) {  // lessAbs
+        double sa, pa, sb, pb;
+        greater(-fabs(t0), sa, pa);
+        less(fabs(t0), sb, pb);
+        stat = (fabs(sb) < fabs(sa)) ? sb : sa;  // min(sa, sb, key=abs): first wins ties
+        pv = (pb > pa) ? pb : pa;                // max(pa, pb)
+    } else if (prm.alt == 3) {
+        greater(t0, stat, pv);
+    } else {
+        less(t0, stat, pv);
+    }
+    if (valid && grp.si == 0) {
+        *p_out = pv;
+        *stat_out = stat;
+        *se_out = se;
+    }
+}
+
+// =============================================================================================
+// (a5) fit_rough_dispersions (utils.py:814-853) / fit_moments_dispersions (utils.py:856-885)
+// `Y` abstracts where normalised counts come from: a float64 (N,G) array (the plugin call) or raw
+// int64 counts divided by the staged size factors on the fly (resident pipeline).
+// =============================================================================================
+struct NormedF64 {
+    const double* p;
+    int64_t ld;
+    PDQ_HD double at(const DesignS&, int n) const { return p[n * ld]; }
+};
+struct NormedFromCounts {
+    const int64_t* p;
+    int64_t ld;
+    PDQ_HD double at(const DesignS& d, int n) const { return (double)p[n * ld] / d.sf[n]; }
+};
+
+template <int P, class Y>
+PDQ_HD double rough_disp_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pinv, const Y& yy) {
+    double v[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) v[j] = 0.0;
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        double x[P];
+        load_x<P>(d, n, x);
+        const double t = yy.at(d, n);
+#pragma unroll
+        for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
+    }
+    group_sum_vec<P>(grp, v);
+    double beta[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) s = fma(pinv.v[i * P + j], v[j], s);
+        beta[i] = s;
+    }
+    double acc = 0.0;
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        double x[P];
+        load_x<P>(d, n, x);
+        double yh = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) yh = fma(x[j], beta[j], yh);
+        yh = (yh < 1.0) ? 1.0 : yh;  // np.maximum(y_hat, 1)
+        const double e = yy.at(d, n) - yh;
+        acc += (e * e - yh) / (yh * yh);
+    }
+    acc = grp.sum(acc) / (double)(d.N - P);
+    return (acc < 0.0) ? 0.0 : acc;  // np.maximum(alpha_rde, 0)
+}
+
+// returns the moments estimate; `mean_out` = per-gene mean of the normalised counts, `all_zero` flag
+template <class Y>
+PDQ_HD double moments_disp_gene(const Group& grp, const DesignS& d, const Y& yy, double s_mean_inv, double& mean_out,
+                                bool& all_zero) {
+    double s = 0.0;
+    bool nz = false;
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        const double t = yy.at(d, n);
+        s += t;
+        nz = nz || (t != 0.0);
+    }
+    s = grp.sum(s);
+    all_zero = !(grp.sum(nz ? 1.0 : 0.0) > 0.0);
+    const double m = s / (double)d.N;
+    double ss = 0.0;
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        const double e = yy.at(d, n) - m;
+        ss = fma(e, e, ss);
+    }
+    const double var = grp.sum(ss) / (double)(d.N - 1);  // ddof=1
+    mean_out = m;
+    double a = (var - s_mean_inv * m) / (m * m);
+    // np.nan_to_num: NaN -> 0, +-inf -> +-DBL_MAX
+    if (!(a == a)) a = 0.0;
+    else if (a > 1.7976931348623157e308) a = 1.7976931348623157e308;
+    else if (a < -1.7976931348623157e308) a = -1.7976931348623157e308;
+    return a;
+}
+
+}  // namespace pdq

@@ -1,0 +1,56 @@
+// pdq_internal.h -- host-side declarations shared by pdq_api.cu (C ABI) and pdq_kernels.cu (launchers).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pydeseq2_b200.h"
+
+namespace pdq {
+
+// Device-resident design pack:
+//   pack = [ X column-major (p x Npad) | sf (Npad) | log sf (Npad) ]  float64, Npad = N rounded up to 2
+// so that one `cp.async.bulk` (TMA 1-D bulk copy, 16-byte granularity) stages it into shared memory.
+struct DesignDev {
+    double* pack;       // device
+    int N, Npad, p;
+    int full_rank;      // np.linalg.matrix_rank(X) == p  (utils.py:349)
+    double pinv[PDQ_MAX_P * PDQ_MAX_P];  // (X^T X)^+ row-major p x p (host copy, passed by value to kernels)
+    double s_mean_inv;  // mean(1 / size_factors)  (utils.py:880)
+    size_t smem_bytes;  // dynamic shared memory the kernels need for this pack
+};
+
+struct LaunchCfg {
+    cudaStream_t stream;
+    int lgT;       // log2(lanes per gene)
+    int sm_count;
+};
+
+struct IrlsHost {
+    double min_mu, beta_tol, min_beta, max_beta;
+    int maxiter;
+};
+
+// launchers (pdq_kernels.cu); each returns the number of kernels launched or a negative pdq_status
+int launch_lin_reg_mu(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64_t ld, int G, double min_mu,
+                      double* mu_out, int64_t ld_out);
+int launch_irls(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64_t ld, int G, const double* disp,
+                const IrlsHost& prm, double* beta, double* mu, double* hat, int64_t ld_out, double* conv, int* status,
+                int* n_fallback);
+int launch_alpha_mle(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64_t ld, int G, const double* mu,
+                     int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp, double prior_var,
+                     int cr_reg, int prior_reg, double* alpha, double* conv, int* status);
+int launch_wald(const LaunchCfg&, const DesignDev&, const double* disp, const double* lfc, const double* mu,
+                int64_t ld_mu, int G, const double* ridge, const double* contrast, double lfc_null, int alt,
+                double* pv, double* stat, double* se);
+int launch_rough(const LaunchCfg&, const DesignDev&, const double* normed, int64_t ld, int G, double* alpha);
+int launch_moments(const LaunchCfg&, const DesignDev&, const double* normed, int64_t ld, int G, double* alpha,
+                   double* all_zero);
+int launch_mom_from_counts(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64_t ld, int G,
+                           double min_disp, double max_disp, double* alpha, double* normed_mean);
+int launch_mu_from_lfc(const LaunchCfg&, const DesignDev&, const double* lfc, int G, double* mu, int64_t ld_out);
+
+// largest dynamic shared memory a kernel of this library may ask for (B200: 227 KB per CTA)
+constexpr size_t kMaxDynSmem = 227 * 1024;
+
+}  // namespace pdq

@@ -1,0 +1,461 @@
+// pdq_kernels.cu -- sm_100a kernels of the per-gene NB-GLM hot path and their launchers.
+//
+// Every kernel has the same skeleton:
+//   1. one elected thread stages the design pack (X column-major, size factors, log size factors)
+//      from global into shared memory with ONE TMA bulk copy (`cp.async.bulk`, SASS UBLKCP) whose
+//      completion is signalled on an mbarrier; all threads wait on the barrier phase;
+//   2. each warp owns 32/T adjacent genes, T lanes per gene; lanes stream the gene's samples from
+//      the (N, G) sample-major arrays (coalesced across the adjacent genes of the warp, read-only
+//      path) and keep all per-gene state (X^T W X, beta, ...) in registers;
+//   3. cross-lane sums use xor-butterfly warp shuffles; p x p Cholesky solves run redundantly per lane.
+// Tensor cores are deliberately not used: p <= 8, the work is FP64 transcendental + HBM streaming.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pdq_gene.cuh"
+#include "pdq_internal.h"
+
+namespace pdq {
+namespace {
+
+constexpr int kBlock = 128;
+constexpr int kWarps = kBlock / 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- TMA 1-D bulk copy global -> shared, mbarrier completion --------------------------------------
+__device__ __forceinline__ DesignS stage_design(const double* __restrict__ pack, int N, int Npad, int P,
+                                                unsigned char* smem) {
+    double* s = reinterpret_cast<double*>(smem);
+    const uint32_t bytes = (uint32_t)((P + 2) * Npad) * 8u;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + bytes);
+    const uint32_t bar_a = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        // chunked so a single descriptor never exceeds 32 KB; all chunks complete on the same barrier
+        uint32_t off = 0;
+        while (off < bytes) {
+            const uint32_t n = (bytes - off > 32768u) ? 32768u : (bytes - off);
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    smem_u32(smem + off)),
+                "l"(reinterpret_cast<const unsigned char*>(pack) + off), "r"(n), "r"(bar_a)
+                : "memory");
+            off += n;
+        }
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar_a), "r"(0u)
+            : "memory");
+    }
+    DesignS d;
+    d.X = s;
+    d.sf = s + P * Npad;
+    d.lsf = s + (P + 1) * Npad;
+    d.N = N;
+    d.Npad = Npad;
+    return d;
+}
+
+__device__ __forceinline__ void map_lanes(int lgT, int G, Group& grp, int& gene, bool& valid) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    grp.T = 1 << lgT;
+    grp.gpw = 32 >> lgT;
+    grp.si = lane >> (5 - lgT);
+    const int gi = lane & (grp.gpw - 1);
+    const int gidx = (blockIdx.x * kWarps + warp) * grp.gpw + gi;
+    valid = gidx < G;
+    gene = valid ? gidx : (G - 1);
+}
+
+struct DesignView {
+    const double* pack;
+    int N, Npad;
+};
+
+// ---- kernels --------------------------------------------------------------------------------------
+template <int P>
+struct LinMuArgs {
+    DesignView dv;
+    SmallMat<P> pinv;
+    const int64_t* counts;
+    int64_t ld;
+    int G, lgT;
+    double min_mu;
+    double* mu;
+    int64_t ld_out;
+};
+
+template <int P>
+__global__ void __launch_bounds__(kBlock) k_lin_reg_mu(const __grid_constant__ LinMuArgs<P> a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(a.lgT, a.G, grp, g, valid);
+    linmu_gene<P>(grp, d, a.pinv, a.counts + g, a.ld, a.min_mu, a.mu + g, a.ld_out, valid);
+}
+
+template <int P>
+struct IrlsArgs {
+    DesignView dv;
+    SmallMat<P> pinv;
+    IrlsParams prm;
+    const int64_t* counts;
+    int64_t ld;
+    int G, lgT;
+    const double* disp;
+    double *beta, *mu, *hat, *conv;
+    int64_t ld_out;
+    int* status;
+    int* n_fallback;
+};
+
+template <int P>
+__global__ void __launch_bounds__(kBlock) k_irls(const __grid_constant__ IrlsArgs<P> a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(a.lgT, a.G, grp, g, valid);
+    int st = 0;
+    irls_gene<P>(grp, d, a.pinv, a.prm, a.counts + g, a.ld, a.disp[g], a.beta + (int64_t)g * P, a.mu + g, a.hat + g,
+                 a.ld_out, a.conv + g, &st, valid);
+    if (valid && grp.si == 0) {
+        a.status[g] = st;
+        if (st != kIrlsOk && a.n_fallback) atomicAdd(a.n_fallback, 1);
+    }
+}
+
+// optimiser branch for the genes k_irls flagged (utils.py:374-413); blocks without a flagged gene exit
+template <int P>
+__global__ void __launch_bounds__(kBlock) k_irls_optimizer(const __grid_constant__ IrlsArgs<P> a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(a.lgT, a.G, grp, g, valid);
+    const bool run = valid && a.status[g] == kIrlsNeedsOptimizer;
+    if (!__syncthreads_or(run)) return;
+    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    if (!__any_sync(0xffffffffu, run)) return;
+    irls_optimizer_gene<P>(grp, d, a.pinv, a.prm, a.counts + g, a.ld, a.disp[g], a.beta + (int64_t)g * P, a.mu + g,
+                           a.hat + g, a.ld_out, a.conv + g, run);
+}
+
+template <int P>
+struct AlphaArgs {
+    DesignView dv;
+    AlphaParams prm;
+    const int64_t* counts;
+    int64_t ld;
+    int G, lgT;
+    const double* mu;
+    int64_t ld_mu;
+    const double* alpha_hat;
+    double *alpha, *conv;
+    int* status;
+};
+
+template <int P>
+__global__ void __launch_bounds__(kBlock) k_alpha_mle(const __grid_constant__ AlphaArgs<P> a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(a.lgT, a.G, grp, g, valid);
+    alpha_gene<P>(grp, d, a.prm, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha_hat[g], a.alpha + g, a.conv + g,
+                  a.status + g, valid);
+}
+
+template <int P>
+__global__ void __launch_bounds__(kBlock) k_alpha_grid(const __grid_constant__ AlphaArgs<P> a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(a.lgT, a.G, grp, g, valid);
+    const bool run = valid && a.status[g] == kAlphaNeedsGrid;
+    if (!__syncthreads_or(run)) return;
+    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    if (!__any_sync(0xffffffffu, run)) return;
+    alpha_grid_gene<P>(grp, d, a.prm.lo, a.prm.hi, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha + g, run);
+}
+
+template <int P>
+struct WaldArgs {
+    DesignView dv;
+    WaldParams<P> prm;
+    const double *disp, *lfc, *mu;
+    int64_t ld_mu;
+    int G, lgT;
+    double *pv, *stat, *se;
+};
+
+template <int P>
+__global__ void __launch_bounds__(kBlock) k_wald(const __grid_constant__ WaldArgs<P> a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(a.lgT, a.G, grp, g, valid);
+    wald_gene<P>(grp, d, a.prm, a.disp[g], a.lfc + (int64_t)g * P, a.mu + g, a.ld_mu, a.pv + g, a.stat + g, a.se + g,
+                 valid);
+}
+
+template <int P>
+struct MomArgs {
+    DesignView dv;
+    SmallMat<P> pinv;
+    const double* normed;    // plugin calls
+    const int64_t* counts;   // resident pipeline
+    int64_t ld;
+    int G, lgT;
+    double s_mean_inv, min_disp, max_disp;
+    double *alpha, *aux;     // aux: all_zero flags (moments) or normalised means (fused)
+};
+
+template <int P>
+__global__ void __launch_bounds__(kBlock) k_rough(const __grid_constant__ MomArgs<P> a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(a.lgT, a.G, grp, g, valid);
+    const double r = rough_disp_gene<P>(grp, d, a.pinv, NormedF64{a.normed + g, a.ld});
+    if (valid && grp.si == 0) a.alpha[g] = r;
+}
+
+template <int P>
+__global__ void __launch_bounds__(kBlock) k_moments(const __grid_constant__ MomArgs<P> a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(a.lgT, a.G, grp, g, valid);
+    double mean;
+    bool az;
+    const double m = moments_disp_gene(grp, d, NormedF64{a.normed + g, a.ld}, a.s_mean_inv, mean, az);
+    if (valid && grp.si == 0) {
+        a.alpha[g] = m;
+        a.aux[g] = az ? 1.0 : 0.0;
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(kBlock) k_mom_from_counts(const __grid_constant__ MomArgs<P> a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(a.lgT, a.G, grp, g, valid);
+    const NormedFromCounts yy{a.counts + g, a.ld};
+    const double rde = rough_disp_gene<P>(grp, d, a.pinv, yy);
+    double mean;
+    bool az;
+    const double mde = moments_disp_gene(grp, d, yy, a.s_mean_inv, mean, az);
+    if (valid && grp.si == 0) {
+        double v = (mde < rde) ? mde : rde;                       // np.minimum (dds.py:1158)
+        v = (v < a.min_disp) ? a.min_disp : ((v > a.max_disp) ? a.max_disp : v);  // np.clip (dds.py:1161)
+        a.alpha[g] = v;
+        a.aux[g] = mean;
+    }
+}
+
+template <int P>
+struct MuLfcArgs {
+    DesignView dv;
+    const double* lfc;
+    int G, lgT;
+    double* mu;
+    int64_t ld_out;
+};
+
+template <int P>
+__global__ void __launch_bounds__(kBlock) k_mu_from_lfc(const __grid_constant__ MuLfcArgs<P> a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(a.lgT, a.G, grp, g, valid);
+    if (!valid) return;
+    double b[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) b[j] = a.lfc[(int64_t)g * P + j];
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        double x[P];
+        load_x<P>(d, n, x);
+        double eta = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) eta = fma(x[j], b[j], eta);
+        a.mu[n * a.ld_out + g] = d.sf[n] * exp(eta);  // ds.py:320-324
+    }
+}
+
+// ---- launch helpers ---------------------------------------------------------------------------------
+inline int grid_for(int G, int lgT) {
+    const int genes_per_block = kWarps * (32 >> lgT);
+    return (G + genes_per_block - 1) / genes_per_block;
+}
+
+template <class K>
+int prep(K kernel, size_t smem) {
+    if (smem > kMaxDynSmem) return PDQ_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return PDQ_ERR_CUDA;
+    }
+    return 0;
+}
+
+template <int P>
+SmallMat<P> pinv_of(const DesignDev& d) {
+    SmallMat<P> m;
+    for (int i = 0; i < P * P; ++i) m.v[i] = d.pinv[i];
+    return m;
+}
+
+#define PDQ_DISPATCH_P(p, ...)             \
+    switch (p) {                           \
+        case 1: { constexpr int P = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int P = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int P = 3; __VA_ARGS__; } break; \
+        case 4: { constexpr int P = 4; __VA_ARGS__; } break; \
+        case 5: { constexpr int P = 5; __VA_ARGS__; } break; \
+        case 6: { constexpr int P = 6; __VA_ARGS__; } break; \
+        case 7: { constexpr int P = 7; __VA_ARGS__; } break; \
+        case 8: { constexpr int P = 8; __VA_ARGS__; } break; \
+        default: return PDQ_ERR_UNSUPPORTED; \
+    }
+
+inline int check_launch() { return cudaGetLastError() == cudaSuccess ? 0 : PDQ_ERR_CUDA; }
+
+}  // namespace
+
+int launch_lin_reg_mu(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G, double min_mu,
+                      double* mu_out, int64_t ld_out) {
+    PDQ_DISPATCH_P(d.p, {
+        LinMuArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d), counts, ld, G, c.lgT, min_mu, mu_out, ld_out};
+        if (int e = prep(k_lin_reg_mu<P>, d.smem_bytes)) return e;
+        k_lin_reg_mu<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+    });
+    if (int e = check_launch()) return e;
+    return 1;
+}
+
+int launch_irls(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G, const double* disp,
+                const IrlsHost& h, double* beta, double* mu, double* hat, int64_t ld_out, double* conv, int* status,
+                int* n_fallback) {
+    if (n_fallback && cudaMemsetAsync(n_fallback, 0, sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;
+    PDQ_DISPATCH_P(d.p, {
+        IrlsArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d),
+                      IrlsParams{h.min_mu, h.beta_tol, h.min_beta, h.max_beta, h.maxiter, d.full_rank},
+                      counts, ld, G, c.lgT, disp, beta, mu, hat, conv, ld_out, status, n_fallback};
+        if (int e = prep(k_irls<P>, d.smem_bytes)) return e;
+        if (int e = prep(k_irls_optimizer<P>, d.smem_bytes)) return e;
+        k_irls<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+        k_irls_optimizer<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+    });
+    if (int e = check_launch()) return e;
+    return 2;
+}
+
+int launch_alpha_mle(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G,
+                     const double* mu, int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp,
+                     double prior_var, int cr_reg, int prior_reg, double* alpha, double* conv, int* status) {
+    PDQ_DISPATCH_P(d.p, {
+        AlphaArgs<P> a{{d.pack, d.N, d.Npad}, AlphaParams{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg},
+                       counts, ld, G, c.lgT, mu, ld_mu, alpha_hat, alpha, conv, status};
+        if (int e = prep(k_alpha_mle<P>, d.smem_bytes)) return e;
+        if (int e = prep(k_alpha_grid<P>, d.smem_bytes)) return e;
+        k_alpha_mle<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+        k_alpha_grid<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+    });
+    if (int e = check_launch()) return e;
+    return 2;
+}
+
+int launch_wald(const LaunchCfg& c, const DesignDev& d, const double* disp, const double* lfc, const double* mu,
+                int64_t ld_mu, int G, const double* ridge, const double* contrast, double lfc_null, int alt, double* pv,
+                double* stat, double* se) {
+    PDQ_DISPATCH_P(d.p, {
+        WaldArgs<P> a;
+        a.dv = DesignView{d.pack, d.N, d.Npad};
+        for (int i = 0; i < P * P; ++i) a.prm.ridge[i] = ridge[i];
+        for (int i = 0; i < P; ++i) a.prm.contrast[i] = contrast[i];
+        a.prm.lfc_null = lfc_null;
+        a.prm.alt = alt;
+        a.disp = disp; a.lfc = lfc; a.mu = mu; a.ld_mu = ld_mu; a.G = G; a.lgT = c.lgT;
+        a.pv = pv; a.stat = stat; a.se = se;
+        if (int e = prep(k_wald<P>, d.smem_bytes)) return e;
+        k_wald<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+    });
+    if (int e = check_launch()) return e;
+    return 1;
+}
+
+int launch_rough(const LaunchCfg& c, const DesignDev& d, const double* normed, int64_t ld, int G, double* alpha) {
+    PDQ_DISPATCH_P(d.p, {
+        MomArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d), normed, nullptr, ld, G, c.lgT, d.s_mean_inv, 0.0, 0.0, alpha,
+                     nullptr};
+        if (int e = prep(k_rough<P>, d.smem_bytes)) return e;
+        k_rough<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+    });
+    if (int e = check_launch()) return e;
+    return 1;
+}
+
+int launch_moments(const LaunchCfg& c, const DesignDev& d, const double* normed, int64_t ld, int G, double* alpha,
+                   double* all_zero) {
+    PDQ_DISPATCH_P(d.p, {
+        MomArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d), normed, nullptr, ld, G, c.lgT, d.s_mean_inv, 0.0, 0.0, alpha,
+                     all_zero};
+        if (int e = prep(k_moments<P>, d.smem_bytes)) return e;
+        k_moments<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+    });
+    if (int e = check_launch()) return e;
+    return 1;
+}
+
+int launch_mom_from_counts(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G,
+                           double min_disp, double max_disp, double* alpha, double* normed_mean) {
+    PDQ_DISPATCH_P(d.p, {
+        MomArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d), nullptr, counts, ld, G, c.lgT, d.s_mean_inv, min_disp,
+                     max_disp, alpha, normed_mean};
+        if (int e = prep(k_mom_from_counts<P>, d.smem_bytes)) return e;
+        k_mom_from_counts<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+    });
+    if (int e = check_launch()) return e;
+    return 1;
+}
+
+int launch_mu_from_lfc(const LaunchCfg& c, const DesignDev& d, const double* lfc, int G, double* mu, int64_t ld_out) {
+    PDQ_DISPATCH_P(d.p, {
+        MuLfcArgs<P> a{{d.pack, d.N, d.Npad}, lfc, G, c.lgT, mu, ld_out};
+        if (int e = prep(k_mu_from_lfc<P>, d.smem_bytes)) return e;
+        k_mu_from_lfc<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+    });
+    if (int e = check_launch()) return e;
+    return 1;
+}
+
+}  // namespace pdq

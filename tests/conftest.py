@@ -5,8 +5,9 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -44,8 +45,8 @@ def tape_calls(t):
                 kw[field] = str(v) or None
             elif field in ("cr_reg", "prior_reg"):
                 kw[field] = bool(v)
-            elif v.ndim == 0:
-                kw[field] = None if np.isnan(v) else float(v)
+            elif field in ("min_mu", "beta_tol", "min_disp", "max_disp", "prior_disp_var", "lfc_null"):
+                kw[field] = None if np.isnan(v).all() else float(np.ravel(v)[0])
             else:
                 kw[field] = v
         if "counts" in kw:

@@ -1,0 +1,75 @@
+"""ctypes front-end of the host emulator (tests/emu/pdq_emu.cpp) with the `_CudaOps` interface, so the
+CPU suite can push the *device* algorithms through `B200Inference`'s marshalling.  Test infrastructure."""
+import ctypes as C
+
+import numpy as np
+
+from . import build as _build
+
+f64p = C.POINTER(C.c_double)
+i64p = C.POINTER(C.c_int64)
+i32p = C.POINTER(C.c_int)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class EmuOps:
+    def __init__(self, force_optimizer=False, force_grid=False):
+        self.lib = C.CDLL(_build.build())
+        self.lib.emu_lgamma.restype = C.c_double
+        self.lib.emu_lgamma.argtypes = [C.c_double]
+        self.lib.emu_digamma.restype = C.c_double
+        self.lib.emu_digamma.argtypes = [C.c_double]
+        self.force_optimizer = int(force_optimizer)
+        self.force_grid = int(force_grid)
+        self.last_status = None
+
+    def empty(self, shape):
+        return np.empty(shape, dtype=np.float64)
+
+    def lin_reg_mu(self, counts, ld, N, G, sf, X, p, min_mu, mu):
+        rc = self.lib.emu_lin_reg_mu(_p(counts, i64p), C.c_int64(ld), N, G, _p(sf, f64p), _p(X, f64p), p, C.c_double(min_mu),
+                                     _p(mu, f64p))
+        assert rc == 0
+
+    def irls(self, counts, ld, N, G, sf, X, p, disp, min_mu, beta_tol, min_beta, max_beta, maxiter, beta, mu, hat, conv):
+        status = np.zeros(G, dtype=np.int32)
+        rc = self.lib.emu_irls(_p(counts, i64p), C.c_int64(ld), N, G, _p(sf, f64p), _p(X, f64p), p, _p(disp, f64p),
+                               C.c_double(min_mu), C.c_double(beta_tol), C.c_double(min_beta), C.c_double(max_beta),
+                               maxiter, _p(beta, f64p), _p(mu, f64p), _p(hat, f64p), _p(conv, f64p), _p(status, i32p),
+                               self.force_optimizer)
+        assert rc == 0
+        self.last_status = status
+        return int((status != 0).sum())
+
+    def alpha_mle(self, counts, ld, N, G, X, p, mu, ld_mu, alpha_hat, min_disp, max_disp, prior_var, cr_reg, prior_reg,
+                  alpha, conv):
+        status = np.zeros(G, dtype=np.int32)
+        rc = self.lib.emu_alpha_mle(_p(counts, i64p), C.c_int64(ld), N, G, _p(X, f64p), p, _p(mu, f64p), C.c_int64(ld_mu),
+                                    _p(alpha_hat, f64p), C.c_double(min_disp), C.c_double(max_disp), C.c_double(prior_var),
+                                    cr_reg, prior_reg, _p(alpha, f64p), _p(conv, f64p), _p(status, i32p), self.force_grid)
+        assert rc == 0
+        self.last_status = status
+
+    def wald_test(self, X, N, p, disp, lfc, mu, ld_mu, G, ridge, contrast, lfc_null, alt, pv, stat, se):
+        rc = self.lib.emu_wald_test(_p(X, f64p), N, p, _p(disp, f64p), _p(lfc, f64p), _p(mu, f64p), C.c_int64(ld_mu), G,
+                                    _p(ridge, f64p), _p(contrast, f64p), C.c_double(lfc_null), alt, _p(pv, f64p),
+                                    _p(stat, f64p), _p(se, f64p))
+        assert rc == 0
+
+    def rough(self, normed, ld, N, G, X, p, out):
+        assert self.lib.emu_rough(_p(normed, f64p), C.c_int64(ld), N, G, _p(X, f64p), p, _p(out, f64p)) == 0
+
+    def moments(self, normed, ld, N, G, sf, out, all_zero):
+        assert self.lib.emu_moments(_p(normed, f64p), C.c_int64(ld), N, G, _p(sf, f64p), _p(out, f64p), _p(all_zero, f64p)) == 0
+
+    def mom_from_counts(self, counts, sf, X, min_disp, max_disp):
+        N, G = counts.shape
+        a = np.empty(G)
+        m = np.empty(G)
+        rc = self.lib.emu_mom_from_counts(_p(counts, i64p), C.c_int64(G), N, G, _p(sf, f64p), _p(X, f64p), X.shape[1],
+                                          C.c_double(min_disp), C.c_double(max_disp), _p(a, f64p), _p(m, f64p))
+        assert rc == 0
+        return a, m

@@ -1,0 +1,183 @@
+// pdq_emu.cpp -- HOST EMULATOR of the device per-gene routines.  TEST INFRASTRUCTURE ONLY.
+//
+// Compiles pydeseq2_b200/csrc/pdq_gene.cuh (the exact source the sm_100a kernels are built from)
+// with g++, one "lane" per gene (T = 1, Group::sum is the identity), so that the CPU test-suite can
+// check the algorithmic content of the kernels -- IRLS control flow, the bounded root search for
+// the dispersion, Cholesky algebra, special functions -- against the oracle without a GPU.
+// It is built by tests/emu/build.py into tests/emu/_build/ and loaded only by tests/; the product
+// (pydeseq2_b200) never loads it and has no CPU fallback.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../pydeseq2_b200/csrc/pdq_gene.cuh"
+#include "../../pydeseq2_b200/csrc/pdq_host_linalg.h"
+
+using namespace pdq;
+
+namespace {
+
+struct Pack {
+    std::vector<double> buf;
+    DesignS d;
+    double pinv[PDQ_MAX_P * PDQ_MAX_P];
+    int full_rank;
+    double s_mean_inv;
+};
+
+Pack make_pack(const double* X, const double* sf, int N, int p) {
+    Pack k;
+    const int Npad = (N + 1) & ~1;
+    k.buf.assign((size_t)(p + 2) * Npad, 0.0);
+    double inv = 0;
+    for (int n = 0; n < N; ++n) {
+        for (int j = 0; j < p; ++j) k.buf[(size_t)j * Npad + n] = X[(size_t)n * p + j];
+        const double s = sf ? sf[n] : 1.0;
+        k.buf[(size_t)p * Npad + n] = s;
+        k.buf[(size_t)(p + 1) * Npad + n] = log(s);
+        inv += 1.0 / s;
+    }
+    k.s_mean_inv = inv / N;
+    k.d = DesignS{k.buf.data(), k.buf.data() + (size_t)p * Npad, k.buf.data() + (size_t)(p + 1) * Npad, N, Npad};
+    design_linear_algebra(X, N, p, k.pinv, &k.full_rank);
+    return k;
+}
+
+template <int P>
+SmallMat<P> pinv_of(const Pack& k) {
+    SmallMat<P> m;
+    for (int i = 0; i < P * P; ++i) m.v[i] = k.pinv[i];
+    return m;
+}
+
+const Group kOne{0, 1, 32};
+
+#define EMU_DISPATCH(p, ...)                               \
+    switch (p) {                                           \
+        case 1: { constexpr int P = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int P = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int P = 3; __VA_ARGS__; } break; \
+        case 4: { constexpr int P = 4; __VA_ARGS__; } break; \
+        case 5: { constexpr int P = 5; __VA_ARGS__; } break; \
+        case 6: { constexpr int P = 6; __VA_ARGS__; } break; \
+        case 7: { constexpr int P = 7; __VA_ARGS__; } break; \
+        case 8: { constexpr int P = 8; __VA_ARGS__; } break; \
+        default: return -3;                                \
+    }
+
+}  // namespace
+
+extern "C" {
+
+int emu_lin_reg_mu(const int64_t* counts, int64_t ld, int N, int G, const double* sf, const double* X, int p, double min_mu,
+                   double* mu) {
+    Pack k = make_pack(X, sf, N, p);
+    EMU_DISPATCH(p, {
+        const SmallMat<P> pi = pinv_of<P>(k);
+        for (int g = 0; g < G; ++g) linmu_gene<P>(kOne, k.d, pi, counts + g, ld, min_mu, mu + g, G, true);
+    });
+    return 0;
+}
+
+int emu_irls(const int64_t* counts, int64_t ld, int N, int G, const double* sf, const double* X, int p, const double* disp,
+             double min_mu, double beta_tol, double min_beta, double max_beta, int maxiter, double* beta, double* mu,
+             double* hat, double* conv, int* status, int force_optimizer) {
+    Pack k = make_pack(X, sf, N, p);
+    EMU_DISPATCH(p, {
+        const SmallMat<P> pi = pinv_of<P>(k);
+        const IrlsParams prm{min_mu, beta_tol, min_beta, max_beta, maxiter, k.full_rank};
+        for (int g = 0; g < G; ++g) {
+            irls_gene<P>(kOne, k.d, pi, prm, counts + g, ld, disp[g], beta + (size_t)g * P, mu + g, hat + g, G, conv + g,
+                         status + g, true);
+            if (force_optimizer) status[g] = kIrlsNeedsOptimizer;
+            if (status[g] == kIrlsNeedsOptimizer)
+                irls_optimizer_gene<P>(kOne, k.d, pi, prm, counts + g, ld, disp[g], beta + (size_t)g * P, mu + g, hat + g,
+                                       G, conv + g, true);
+        }
+    });
+    return 0;
+}
+
+int emu_alpha_mle(const int64_t* counts, int64_t ld, int N, int G, const double* X, int p, const double* mu, int64_t ld_mu,
+                  const double* alpha_hat, double min_disp, double max_disp, double prior_var, int cr_reg, int prior_reg,
+                  double* alpha, double* conv, int* status, int force_grid) {
+    Pack k = make_pack(X, nullptr, N, p);
+    EMU_DISPATCH(p, {
+        const AlphaParams prm{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg};
+        for (int g = 0; g < G; ++g) {
+            alpha_gene<P>(kOne, k.d, prm, counts + g, ld, mu + g, ld_mu, alpha_hat[g], alpha + g, conv + g, status + g, true);
+            if (force_grid) status[g] = kAlphaNeedsGrid;
+            if (status[g] == kAlphaNeedsGrid)
+                alpha_grid_gene<P>(kOne, k.d, prm.lo, prm.hi, counts + g, ld, mu + g, ld_mu, alpha + g, true);
+        }
+    });
+    return 0;
+}
+
+int emu_wald_test(const double* X, int N, int p, const double* disp, const double* lfc, const double* mu, int64_t ld_mu, int G,
+                  const double* ridge, const double* contrast, double lfc_null, int alt, double* pv, double* stat,
+                  double* se) {
+    Pack k = make_pack(X, nullptr, N, p);
+    EMU_DISPATCH(p, {
+        WaldParams<P> prm;
+        for (int i = 0; i < P * P; ++i) prm.ridge[i] = ridge[i];
+        for (int i = 0; i < P; ++i) prm.contrast[i] = contrast[i];
+        prm.lfc_null = lfc_null;
+        prm.alt = alt;
+        for (int g = 0; g < G; ++g)
+            wald_gene<P>(kOne, k.d, prm, disp[g], lfc + (size_t)g * P, mu + g, ld_mu, pv + g, stat + g, se + g, true);
+    });
+    return 0;
+}
+
+int emu_rough(const double* normed, int64_t ld, int N, int G, const double* X, int p, double* alpha) {
+    Pack k = make_pack(X, nullptr, N, p);
+    EMU_DISPATCH(p, {
+        const SmallMat<P> pi = pinv_of<P>(k);
+        for (int g = 0; g < G; ++g) alpha[g] = rough_disp_gene<P>(kOne, k.d, pi, NormedF64{normed + g, ld});
+    });
+    return 0;
+}
+
+int emu_moments(const double* normed, int64_t ld, int N, int G, const double* sf, double* alpha, double* all_zero) {
+    std::vector<double> ones((size_t)N, 1.0);
+    Pack k = make_pack(ones.data(), sf, N, 1);
+    for (int g = 0; g < G; ++g) {
+        double mean;
+        bool az;
+        alpha[g] = moments_disp_gene(kOne, k.d, NormedF64{normed + g, ld}, k.s_mean_inv, mean, az);
+        all_zero[g] = az ? 1.0 : 0.0;
+    }
+    return 0;
+}
+
+int emu_mom_from_counts(const int64_t* counts, int64_t ld, int N, int G, const double* sf, const double* X, int p,
+                        double min_disp, double max_disp, double* alpha, double* normed_mean) {
+    Pack k = make_pack(X, sf, N, p);
+    EMU_DISPATCH(p, {
+        const SmallMat<P> pi = pinv_of<P>(k);
+        for (int g = 0; g < G; ++g) {
+            const NormedFromCounts yy{counts + g, ld};
+            const double rde = rough_disp_gene<P>(kOne, k.d, pi, yy);
+            double mean;
+            bool az;
+            const double mde = moments_disp_gene(kOne, k.d, yy, k.s_mean_inv, mean, az);
+            double v = (mde < rde) ? mde : rde;
+            v = (v < min_disp) ? min_disp : ((v > max_disp) ? max_disp : v);
+            alpha[g] = v;
+            normed_mean[g] = mean;
+        }
+    });
+    return 0;
+}
+
+double emu_lgamma(double x) { return lgamma_pos(x); }
+double emu_digamma(double x) { return digamma_pos(x); }
+int emu_design_rank_pinv(const double* X, int N, int p, double* pinv) {
+    int fr;
+    design_linear_algebra(X, N, p, pinv, &fr);
+    return fr;
+}
+
+}  // extern "C"
