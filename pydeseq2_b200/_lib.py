@@ -122,6 +122,7 @@ class Context:
                             "this backend needs an sm_100 (B200) GPU and has no CPU fallback")
         self.h = h
         self.device = int(device)
+        self._pin_pool = {}  # nbytes -> [addresses] of released page-locked blocks (cudaHostAlloc is expensive)
 
     def check(self, rc: int):
         if rc != 0:
@@ -130,6 +131,10 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for blocks in self._pin_pool.values():
+                for addr in blocks:
+                    self.lib.pdq_host_free(self.h, C.c_void_p(addr))
+            self._pin_pool = {}
             self.lib.pdq_ctx_destroy(self.h)
             self.h = None
 
@@ -187,16 +192,26 @@ class _Pinned:
     """Owner of one cudaHostAlloc block, exposed to numpy through ``__array_interface__``."""
 
     def __init__(self, ctx: Context, shape, dtype):
-        n = int(np.prod(shape)) * dtype.itemsize
-        p = C.c_void_p()
-        ctx.check(ctx.lib.pdq_host_alloc(ctx.h, max(n, 1), C.byref(p)))
+        n = max(int(np.prod(shape)) * dtype.itemsize, 1)
+        pool = ctx._pin_pool.get(n)
+        if pool:
+            addr = pool.pop()
+        else:
+            p = C.c_void_p()
+            ctx.check(ctx.lib.pdq_host_alloc(ctx.h, n, C.byref(p)))
+            addr = p.value
         self._ctx = ctx  # keeps the context alive for as long as the block is
-        self._addr = p.value
-        self.__array_interface__ = {"shape": shape, "typestr": dtype.str, "data": (p.value, False), "version": 3}
+        self._addr = addr
+        self._n = n
+        self.__array_interface__ = {"shape": shape, "typestr": dtype.str, "data": (addr, False), "version": 3}
 
     def __del__(self):  # pragma: no cover
         try:
             if self._addr and self._ctx.h:
-                self._ctx.lib.pdq_host_free(self._ctx.h, C.c_void_p(self._addr))
+                pool = self._ctx._pin_pool.setdefault(self._n, [])
+                if len(pool) < 6:
+                    pool.append(self._addr)  # recycled by the next pinned_empty of the same size
+                else:
+                    self._ctx.lib.pdq_host_free(self._ctx.h, C.c_void_p(self._addr))
         except Exception:
             pass

@@ -89,21 +89,33 @@ def _rows(a, dtype, name):
 class _CudaOps:
     """Raw ops on numpy buffers through the C ABI (host-buffer entry points)."""
 
-    def __init__(self, device=0, lanes_per_gene=0):
+    def __init__(self, device=0, lanes_per_gene=0, pinned_outputs=True):
         self.ctx = _lib.Context(device)
         self.lib = self.ctx.lib
+        self.pinned_outputs = pinned_outputs
+        self.h2d_bytes = 0  # bytes the calls below asked the library to copy in / out (bench.py `e2e`)
+        self.d2h_bytes = 0
         if lanes_per_gene:
             self.ctx.check(self.lib.pdq_set_lanes_per_gene(self.ctx.h, int(lanes_per_gene)))
 
     def empty(self, shape):
+        # large outputs land in recycled page-locked blocks: the D2H copy then runs at full PCIe rate
+        if self.pinned_outputs and int(np.prod(shape)) >= (1 << 16):
+            return self.ctx.pinned_empty(shape)
         return np.empty(shape, dtype=np.float64)
 
+    def _io(self, ins, outs):
+        self.h2d_bytes += sum(a.nbytes for a in ins)
+        self.d2h_bytes += sum(a.nbytes for a in outs)
+
     def lin_reg_mu(self, counts, ld, N, G, sf, X, p, min_mu, mu):
+        self._io((counts, sf, X), (mu,))
         self.ctx.check(self.lib.pdq_lin_reg_mu(self.ctx.h, as_i64p(counts), ld, N, G, as_f64p(sf), as_f64p(X), p, min_mu,
                                                as_f64p(mu)))
 
     def irls(self, counts, ld, N, G, sf, X, p, disp, min_mu, beta_tol, min_beta, max_beta, maxiter, beta, mu, hat, conv):
         nfb = C.c_int(0)
+        self._io((counts, sf, X, disp), (beta, mu, hat, conv))
         self.ctx.check(self.lib.pdq_irls(self.ctx.h, as_i64p(counts), ld, N, G, as_f64p(sf), as_f64p(X), p, as_f64p(disp),
                                          min_mu, beta_tol, min_beta, max_beta, maxiter, as_f64p(beta), as_f64p(mu),
                                          as_f64p(hat), as_f64p(conv), C.byref(nfb)))
@@ -111,19 +123,23 @@ class _CudaOps:
 
     def alpha_mle(self, counts, ld, N, G, X, p, mu, ld_mu, alpha_hat, min_disp, max_disp, prior_var, cr_reg, prior_reg,
                   alpha, conv):
+        self._io((counts, mu, X, alpha_hat), (alpha, conv))
         self.ctx.check(self.lib.pdq_alpha_mle(self.ctx.h, as_i64p(counts), ld, N, G, as_f64p(X), p, as_f64p(mu), ld_mu,
                                               as_f64p(alpha_hat), min_disp, max_disp, prior_var, cr_reg, prior_reg,
                                               as_f64p(alpha), as_f64p(conv)))
 
     def wald_test(self, X, N, p, disp, lfc, mu, ld_mu, G, ridge, contrast, lfc_null, alt, pv, stat, se):
+        self._io((X, disp, lfc, mu), (pv, stat, se))
         self.ctx.check(self.lib.pdq_wald_test(self.ctx.h, as_f64p(X), N, p, as_f64p(disp), as_f64p(lfc), as_f64p(mu), ld_mu,
                                               G, as_f64p(ridge), as_f64p(contrast), lfc_null, alt, as_f64p(pv),
                                               as_f64p(stat), as_f64p(se)))
 
     def rough(self, normed, ld, N, G, X, p, out):
+        self._io((normed, X), (out,))
         self.ctx.check(self.lib.pdq_fit_rough_dispersions(self.ctx.h, as_f64p(normed), ld, N, G, as_f64p(X), p, as_f64p(out)))
 
     def moments(self, normed, ld, N, G, sf, out, all_zero):
+        self._io((normed, sf), (out, all_zero))
         self.ctx.check(self.lib.pdq_fit_moments_dispersions(self.ctx.h, as_f64p(normed), ld, N, G, as_f64p(sf), as_f64p(out),
                                                             as_f64p(all_zero)))
 

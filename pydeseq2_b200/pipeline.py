@@ -1,0 +1,375 @@
+"""Hot-path drivers: the order in which ``DeseqDataSet.deseq2()`` + ``DeseqStats.run_wald_test()`` call the
+``Inference`` plugin (``/root/reference/pydeseq2/dds.py:516-562``, ``ds.py:303-360``), without the orchestrator's
+AnnData/pandas state and without the stages SURVEY.md §8 marks "next" (Cook's distances / outlier refit,
+independent filtering).
+
+Two drivers share the host glue (size factors, trend loop, dispersion prior -- global reductions over genes):
+
+* :func:`fit_host` -- takes ANY object with the reference's ``Inference`` methods (``B200Inference``, the oracle,
+  the reference's own ``DefaultInference``) and passes HOST numpy buffers, exactly like the orchestrator does.
+  This is the end-to-end (``e2e``) path of ``bench.py`` and what the parity tests chain.
+* :class:`ResidentFit` -- keeps counts and every (N, G) intermediate in HBM and chains the ``*_dev`` entry
+  points of the C ABI; only per-gene vectors cross PCIe.  This is the ``value`` path of ``bench.py``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+import warnings
+from dataclasses import dataclass, field
+
+import numpy as np
+from scipy.special import polygamma
+from scipy.stats import trim_mean
+
+LN2 = float(np.log(2.0))
+
+
+# --------------------------------------------------------------------------------------- host glue
+def median_of_ratios(counts: np.ndarray):
+    """Size factors by median of ratios (preprocessing.py:31-102). Returns (normed_counts, size_factors)."""
+    with np.errstate(divide="ignore"):
+        lc = np.log(counts)
+    lm = lc.mean(0)
+    keep = ~np.isinf(lm)
+    if not keep.any():
+        raise ValueError("Every gene contains at least one zero, cannot compute log geometric means.")
+    sf = np.exp(np.median(lc[:, keep] - lm[keep], axis=1))
+    return counts / sf[:, None], sf
+
+
+def lin_mu_branch(X: np.ndarray) -> bool:
+    """True when #unique design rows == #columns: mu_hat comes from ``lin_reg_mu`` (dds.py:747-756)."""
+    return len(np.unique(X, axis=0)) == X.shape[1]
+
+
+def mean_absolute_deviation(x: np.ndarray) -> float:
+    """utils.py:1210-1227 (scaled MAD)."""
+    from scipy.special import erfinv  # 1 / (sqrt(2) erfinv(0.5)) = 1.4826...
+
+    return float(np.median(np.abs(x - np.median(x))) / (np.sqrt(2.0) * erfinv(0.5)))
+
+
+@dataclass
+class TrendFit:
+    kind: str                 # "parametric" | "mean"
+    coeffs: np.ndarray        # (a0, a1) or (mean_disp, nan)
+    fitted: np.ndarray        # fitted dispersion per gene
+    n_iter: int = 0
+
+
+def fit_trend(inference, normed_means: np.ndarray, genewise: np.ndarray, min_disp: float, fit_type="parametric") -> TrendFit:
+    """Dispersion trend (dds.py:799-831): parametric gamma-GLM loop (:1199-1275) or trimmed mean (:1277-1299)."""
+    def mean_trend():
+        sel = genewise > 10 * min_disp
+        m = float(trim_mean(genewise[sel], proportiontocut=0.001))
+        return TrendFit("mean", np.array([m, np.nan]), np.full_like(genewise, m))
+
+    if fit_type == "mean":
+        return mean_trend()
+    with np.errstate(divide="ignore"):
+        cov = 1.0 / normed_means
+    ok = np.isfinite(cov)
+    idx = np.flatnonzero(ok)
+    old = np.array([0.1, 0.1])
+    coeffs = np.array([1.0, 1.0])
+    n_iter = 0
+    while (coeffs > 1e-10).all() and (np.log(np.abs(coeffs / old)) ** 2).sum() >= 1e-6:
+        old = coeffs
+        coeffs, pred, converged = inference.dispersion_trend_gamma_glm(cov[idx], genewise[idx])
+        coeffs = np.asarray(coeffs, dtype=float)
+        n_iter += 1
+        if not converged or (coeffs <= 1e-10).any():
+            warnings.warn("The dispersion trend curve fitting did not converge. Switching to a mean-based dispersion trend.",
+                          UserWarning, stacklevel=2)
+            return mean_trend()
+        ratio = genewise[idx] / np.asarray(pred, dtype=float)
+        idx = idx[~((ratio < 1e-4) | (ratio >= 15))]
+    fitted = coeffs[0] + coeffs[1] / normed_means
+    return TrendFit("parametric", coeffs, fitted, n_iter)
+
+
+def fit_prior_var(genewise: np.ndarray, fitted: np.ndarray, N: int, p: int, min_disp: float):
+    """dds.py:840-884: squared MAD of log residuals, minus trigamma((N-p)/2), floored at 0.25."""
+    res = np.log(genewise) - np.log(fitted)
+    above = genewise >= 100 * min_disp
+    sq = mean_absolute_deviation(res[above]) ** 2
+    return sq, float(np.maximum(sq - polygamma(1, (N - p) / 2), 0.25))
+
+
+@dataclass
+class FitResult:
+    size_factors: np.ndarray
+    non_zero: np.ndarray
+    mom: np.ndarray
+    genewise: np.ndarray
+    genewise_converged: np.ndarray
+    trend: TrendFit
+    prior_var: float
+    squared_logres: float
+    map: np.ndarray
+    map_converged: np.ndarray
+    dispersions: np.ndarray
+    lfc: np.ndarray            # (G, p), natural log scale
+    lfc_converged: np.ndarray
+    pvalue: np.ndarray
+    stat: np.ndarray
+    se: np.ndarray
+    timings: dict = field(default_factory=dict)
+
+
+def _expand(v, nz, G_all):
+    out = np.full((G_all,) + v.shape[1:], np.nan)
+    out[nz] = v
+    return out
+
+
+def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5, min_disp=1e-8, max_disp=10.0,
+             beta_tol=1e-8, fit_type="parametric", lfc_null=0.0, alt_hypothesis=None, timings=None, comm=None) -> FitResult:
+    """deseq2() + run_wald_test() hot path through the plugin API with host buffers.
+
+    ``comm`` (``sharding.NcclComm`` / ``TorchDistComm``): this process holds one gene shard; the genewise
+    dispersions and normalised means of all shards are gathered for the trend and prior (the only cross-gene
+    step).  ``size_factors`` must then be given (they are per sample, global over genes)."""
+    T = timings if timings is not None else {}
+
+    def timed(key, fn, *a, **k):
+        t0 = time.perf_counter()
+        r = fn(*a, **k)
+        T[key] = T.get(key, 0.0) + time.perf_counter() - t0
+        return r
+
+    counts = np.asarray(counts)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    N, G_all = counts.shape
+    p = X.shape[1]
+    max_disp = max(max_disp, N)  # dds.py:312
+    if contrast is None:
+        contrast = np.zeros(p)
+        contrast[-1] = 1.0
+    if size_factors is None:
+        normed, sf = timed("size_factors", median_of_ratios, counts)
+    else:
+        sf = np.asarray(size_factors, dtype=float)
+        normed = counts / sf[:, None]
+    nz = ~(counts == 0).all(axis=0)                      # dds.py:729-731
+    all_nz = bool(nz.all())
+    c = counts if all_nz else counts[:, nz]              # no copy when the caller already dropped all-zero genes
+    nn = normed if all_nz else normed[:, nz]
+    normed_means = normed.mean(0)[nz]                    # dds.py:708
+
+    rde = timed("fit_rough_dispersions", inference.fit_rough_dispersions, nn, X)       # dds.py:1150-1157
+    mde = timed("fit_moments_dispersions", inference.fit_moments_dispersions, nn, sf)
+    mom = np.clip(np.minimum(rde, mde), min_disp, max_disp)
+    if lin_mu_branch(X):                                 # dds.py:747-765
+        mu_hat = timed("lin_reg_mu", inference.lin_reg_mu, c, sf, X, min_mu)
+    else:
+        _, mu_hat, _, _ = timed("irls_init", inference.irls, c, sf, X, mom, min_mu, beta_tol)
+    mu_hat = np.ascontiguousarray(mu_hat)                # layers["_mu_hat"][:, non_zero_idx] is a fresh C array
+    gw, gw_conv = timed("alpha_mle_genewise", inference.alpha_mle, c, X, mu_hat, mom, min_disp, max_disp)
+    gw = np.clip(gw, min_disp, max_disp)                 # dds.py:792-794
+    if comm is None:
+        trend = timed("trend", fit_trend, inference, normed_means, gw, min_disp, fit_type)
+        sq, prior_var = timed("prior", fit_prior_var, gw, trend.fitted, N, p, min_disp)
+    else:
+        gw_all, means_all = timed("allgather", comm.allgather_pair, gw, normed_means)
+        trend = timed("trend", fit_trend, inference, means_all, gw_all, min_disp, fit_type)
+        sq, prior_var = timed("prior", fit_prior_var, gw_all, trend.fitted, N, p, min_disp)
+        local = (trend.coeffs[0] + trend.coeffs[1] / normed_means) if trend.kind == "parametric" else np.full_like(gw, trend.coeffs[0])
+        trend = TrendFit(trend.kind, trend.coeffs, local, trend.n_iter)
+    mp, mp_conv = timed("alpha_mle_map", inference.alpha_mle, c, X, mu_hat, trend.fitted, min_disp, max_disp,
+                        prior_disp_var=prior_var, cr_reg=True, prior_reg=True)
+    mp = np.clip(mp, min_disp, max_disp)
+    disp = mp.copy()
+    outlier = np.log(gw) > np.log(trend.fitted) + 2 * np.sqrt(sq)   # dds.py:926-932
+    disp[outlier] = gw[outlier]
+    lfc, mu_lfc, hat, lfc_conv = timed("irls_lfc", inference.irls, c, sf, X, disp, min_mu, beta_tol)
+
+    # Wald stage on ALL genes, all-zero genes carry NaN (ds.py:320-347)
+    lfc_all = _expand(np.asarray(lfc), nz, G_all)
+    disp_all = _expand(disp, nz, G_all)
+    t0 = time.perf_counter()
+    mu_w = np.exp(X @ lfc_all.T) * sf[:, None]
+    T["wald_mu_host"] = T.get("wald_mu_host", 0.0) + time.perf_counter() - t0
+    ridge = np.diag(np.repeat(1e-6, p))
+    pv, st, se = timed("wald_test", inference.wald_test, X, disp_all, lfc_all, mu_w, ridge, np.asarray(contrast, float),
+                       LN2 * lfc_null, alt_hypothesis)
+    return FitResult(sf, nz, mom, gw, np.asarray(gw_conv), trend, prior_var, sq, mp, np.asarray(mp_conv), disp_all,
+                     lfc_all, np.asarray(lfc_conv), np.asarray(pv), np.asarray(st), np.asarray(se), T)
+
+
+# --------------------------------------------------------------------------------------- resident driver
+class ResidentFit:
+    """Same sequence with counts and all (N, G) intermediates resident in HBM (C ABI ``*_dev`` entry points).
+
+    ``upload()`` places the shard's counts on the device; ``run()`` is one pass of the hot path: every kernel of
+    the chain plus the host trend/prior glue on per-gene vectors.  ``comm`` (optional, see ``sharding.py``)
+    gathers the per-gene vectors of all gene shards where the path needs them.
+    """
+
+    def __init__(self, ctx, X, size_factors, min_mu=0.5, min_disp=1e-8, max_disp=10.0, beta_tol=1e-8, comm=None):
+        from . import _lib
+
+        self._lib_mod = _lib
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.X = np.ascontiguousarray(X, dtype=np.float64)
+        self.sf = np.ascontiguousarray(size_factors, dtype=np.float64)
+        self.N, self.p = self.X.shape
+        self.min_mu, self.min_disp, self.beta_tol = min_mu, min_disp, beta_tol
+        self.max_disp = max(max_disp, self.N)
+        self.comm = comm
+        d = _lib.c_design()
+        ctx.check(self.lib.pdq_design_create(ctx.h, _lib.as_f64p(self.X), _lib.as_f64p(self.sf), self.N, self.p, C.byref(d)))
+        self.design = d
+        self.lin_branch = lin_mu_branch(self.X)
+        self.G = 0
+        self._bufs = {}
+        self.stage_ms = {}
+
+    # -- memory --------------------------------------------------------------------------------
+    def _dev(self, name, nbytes):
+        cur = self._bufs.get(name)
+        if cur is None or cur[1] < nbytes:
+            if cur is not None:
+                self.ctx.free(cur[0])
+            self._bufs[name] = (self.ctx.malloc(nbytes), nbytes)
+        return self._bufs[name][0]
+
+    def upload(self, counts: np.ndarray):
+        """H2D of this shard's counts (genes that are all-zero must already be dropped, dds.py:729-731)."""
+        counts = np.ascontiguousarray(counts, dtype=np.int64)
+        assert counts.shape[0] == self.N
+        self.G = counts.shape[1]
+        G, N, p = self.G, self.N, self.p
+        ng = N * G * 8
+        self.d_counts = self._dev("counts", ng)
+        self.d_mu_hat = self._dev("mu_hat", ng)
+        self.d_mu = self._dev("mu", ng)
+        self.d_hat = self._dev("hat", ng)
+        for name, n in (("mom", G), ("means", G), ("gw", G), ("gw_conv", G), ("fitted", G), ("map", G), ("map_conv", G),
+                        ("disp", G), ("beta", G * p), ("beta0", G * p), ("conv", G), ("pv", G), ("stat", G), ("se", G)):
+            setattr(self, "d_" + name, self._dev(name, n * 8))
+        self.d_nfb = self._dev("nfb", 64)
+        self.ctx.h2d(self.d_counts, counts)
+        self.ctx.sync()
+        self._h = {k: self.ctx.pinned_empty((G,)) for k in ("mom", "means", "gw", "gw_conv", "fitted", "map", "map_conv",
+                                                              "disp", "conv", "pv", "stat", "se")}
+        self._h["beta"] = self.ctx.pinned_empty((G, p))
+
+    def close(self):
+        for ptr, _ in self._bufs.values():
+            self.ctx.free(ptr)
+        self._bufs = {}
+        if self.design:
+            self.lib.pdq_design_destroy(self.ctx.h, self.design)
+            self.design = None
+
+    # -- one pass ----------------------------------------------------------------------------------
+    def run(self, contrast=None, lfc_null=0.0, alt_hypothesis=None, fit_type="parametric", trend_inference=None,
+            fetch_all=True, profile=False):
+        """One pass.  ``profile=True`` brackets every kernel stage with CUDA events on the context's stream
+        (``stage_ms``); it serialises the host against each stage, so never time a step with it."""
+        L, ctx, h, d, G = self.lib, self.ctx, self.ctx.h, self.design, self.G
+        stage = [None]
+
+        class _Check:  # ctx.check with optional per-stage event timing
+            def __call__(_, rc):
+                ctx.check(rc)
+                if profile and stage[0]:
+                    ctx.record(3)
+                    self.stage_ms[stage[0]] = ctx.elapsed_ms(2, 3)
+                    stage[0] = None
+
+        check = _Check()
+
+        def begin(name):
+            if profile:
+                stage[0] = name
+                ctx.sync()
+                ctx.record(2)
+        c_d = self._lib_mod.c_dptr
+        p = self.p
+        H = self._h
+        if contrast is None:
+            contrast = np.zeros(p)
+            contrast[-1] = 1.0
+        contrast = np.ascontiguousarray(contrast, dtype=np.float64)
+        ridge = np.ascontiguousarray(np.diag(np.repeat(1e-6, p)))
+        # 1. method-of-moments start values + normalised means (dds.py:1140-1162, :708)
+        begin("mom_dispersions")
+        check(L.pdq_mom_dispersions_dev(h, d, c_d(self.d_counts), G, G, self.min_disp, self.max_disp, c_d(self.d_mom),
+                                            c_d(self.d_means)))
+        # 2. initial mu_hat (dds.py:747-765)
+        if self.lin_branch:
+            begin("lin_reg_mu")
+            check(L.pdq_lin_reg_mu_dev(h, d, c_d(self.d_counts), G, G, self.min_mu, c_d(self.d_mu_hat), G))
+        else:
+            begin("irls_init")
+            check(L.pdq_irls_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mom), self.min_mu, self.beta_tol, -30.0, 30.0,
+                                     250, c_d(self.d_beta0), c_d(self.d_mu_hat), c_d(self.d_hat), G, c_d(self.d_conv),
+                                     c_d(self.d_nfb)))
+        # 3. genewise dispersions (dds.py:778-797)
+        begin("alpha_mle_genewise")
+        check(L.pdq_alpha_mle_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(self.d_mom), self.min_disp,
+                                      self.max_disp, 1.0, 1, 0, c_d(self.d_gw), c_d(self.d_gw_conv)))
+        ctx.d2h(H["gw"], self.d_gw)
+        ctx.d2h(H["means"], self.d_means)
+        ctx.d2h(H["gw_conv"], self.d_gw_conv)
+        ctx.sync()
+        gw = np.clip(H["gw"], self.min_disp, self.max_disp)
+        means = H["means"]
+        # 4. trend + prior: global over ALL genes of ALL shards (dds.py:799-884)
+        t0 = time.perf_counter()
+        if self.comm is not None:
+            gw_all, means_all = self.comm.allgather_pair(gw, means)
+        else:
+            gw_all, means_all = gw, means
+        trend = fit_trend(trend_inference or _HostTrend(), means_all, gw_all, self.min_disp, fit_type)
+        sq, prior_var = fit_prior_var(gw_all, trend.fitted, self.N, p, self.min_disp)
+        if trend.kind == "parametric":
+            fitted = trend.coeffs[0] + trend.coeffs[1] / means
+        else:
+            fitted = np.full_like(gw, trend.coeffs[0])
+        self.stage_ms["trend_prior_host"] = (time.perf_counter() - t0) * 1e3
+        H["fitted"][:] = fitted
+        ctx.h2d(self.d_fitted, H["fitted"])
+        # 5. MAP dispersions (dds.py:886-935)
+        begin("alpha_mle_map")
+        check(L.pdq_alpha_mle_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(self.d_fitted), self.min_disp,
+                                      self.max_disp, prior_var, 1, 1, c_d(self.d_map), c_d(self.d_map_conv)))
+        ctx.d2h(H["map"], self.d_map)
+        ctx.d2h(H["map_conv"], self.d_map_conv)
+        ctx.sync()
+        mp = np.clip(H["map"], self.min_disp, self.max_disp)
+        disp = mp.copy()
+        outlier = np.log(gw) > np.log(fitted) + 2 * np.sqrt(sq)
+        disp[outlier] = gw[outlier]
+        H["disp"][:] = disp
+        ctx.h2d(self.d_disp, H["disp"])
+        # 6. LFC fit (dds.py:937-984): beta, mu (unclamped), hat diagonal stay on the device
+        begin("irls_lfc")
+        check(L.pdq_irls_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_disp), self.min_mu, self.beta_tol, -30.0, 30.0, 250,
+                                 c_d(self.d_beta), c_d(self.d_mu), c_d(self.d_hat), G, c_d(self.d_conv), c_d(self.d_nfb)))
+        # 7. Wald (ds.py:303-360): mu = sf * exp(X beta) is exactly the mu the LFC fit just wrote (unclamped)
+        begin("wald_test")
+        check(L.pdq_wald_test_dev(h, d, c_d(self.d_disp), c_d(self.d_beta), c_d(self.d_mu), G, G,
+                                      self._lib_mod.as_f64p(ridge), self._lib_mod.as_f64p(contrast), LN2 * lfc_null,
+                                      self._lib_mod.ALT_CODES[alt_hypothesis], c_d(self.d_pv), c_d(self.d_stat), c_d(self.d_se)))
+        for k in ("pv", "stat", "se", "conv", "beta"):
+            ctx.d2h(H[k], getattr(self, "d_" + k))
+        if fetch_all:
+            ctx.d2h(H["mom"], self.d_mom)
+        ctx.sync()
+        return {"mom": H["mom"], "genewise": gw, "genewise_converged": H["gw_conv"], "trend": trend, "prior_var": prior_var,
+                "squared_logres": sq, "map": mp, "map_converged": H["map_conv"], "dispersions": disp, "lfc": H["beta"],
+                "lfc_converged": H["conv"], "pvalue": H["pv"], "stat": H["stat"], "se": H["se"], "normed_means": means}
+
+
+class _HostTrend:
+    """The trend GLM of B200Inference without needing a device context."""
+
+    def dispersion_trend_gamma_glm(self, covariates, targets):
+        from .inference import B200Inference
+
+        return B200Inference.dispersion_trend_gamma_glm(None, covariates, targets)

@@ -1,0 +1,118 @@
+"""Gene shards across GPUs: one process per GPU, contiguous gene blocks, the design matrix and
+size factors replicated.  Every hot-path method is independent per gene; the ONLY cross-gene dependency on
+the path is the dispersion trend + prior (``dds.py:799-884``), which need the genewise dispersions and
+normalised means of all genes -- one small all-gather of two float64 vectors.
+
+``NcclComm`` runs that all-gather with NCCL on device buffers through the C ABI (``pdq_allgather_f64_dev``);
+``TorchDistComm`` does the same through ``torch.distributed`` (used with the ``gloo`` backend by the CPU tests
+of the multi-rank host logic).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+
+def shard_bounds(G: int, world: int, rank: int):
+    """Contiguous block ``[lo, hi)`` of rank ``rank``: blocks of ceil(G / world) genes, the tail may be short."""
+    per = -(-G // world)
+    lo = min(G, rank * per)
+    return lo, min(G, lo + per)
+
+
+def shard_sizes(G: int, world: int):
+    return [shard_bounds(G, world, r)[1] - shard_bounds(G, world, r)[0] for r in range(world)]
+
+
+class _PaddedGather:
+    """All-gather of ragged per-rank vectors through an equal-count primitive (pad with NaN, strip after)."""
+
+    sizes: list
+
+    def _gather_equal(self, send: np.ndarray) -> np.ndarray:  # (world * len(send),)
+        raise NotImplementedError
+
+    def allgather(self, v: np.ndarray) -> np.ndarray:
+        m = max(self.sizes)
+        send = np.full(m, np.nan)
+        send[: len(v)] = v
+        out = self._gather_equal(send).reshape(len(self.sizes), m)
+        return np.concatenate([out[r, :n] for r, n in enumerate(self.sizes)])
+
+    def allgather_pair(self, a: np.ndarray, b: np.ndarray):
+        m = max(self.sizes)
+        send = np.full(2 * m, np.nan)
+        send[: len(a)] = a
+        send[m: m + len(b)] = b
+        out = self._gather_equal(send).reshape(len(self.sizes), 2, m)
+        return (np.concatenate([out[r, 0, :n] for r, n in enumerate(self.sizes)]),
+                np.concatenate([out[r, 1, :n] for r, n in enumerate(self.sizes)]))
+
+
+class TorchDistComm(_PaddedGather):
+    """torch.distributed flavour (gloo on CPU for tests; also works with nccl + cuda tensors)."""
+
+    def __init__(self, sizes, group=None, device="cpu"):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.sizes = list(sizes)
+        self.device = device
+
+    def _gather_equal(self, send):
+        import torch
+
+        t = torch.from_numpy(np.ascontiguousarray(send)).to(self.device)
+        outs = [torch.empty_like(t) for _ in self.sizes]
+        self.dist.all_gather(outs, t, group=self.group)
+        return np.concatenate([o.cpu().numpy() for o in outs])
+
+
+class NcclComm(_PaddedGather):
+    """NCCL all-gather on device buffers through the C ABI.  ``unique_id`` must be the same 128 bytes on all ranks
+    (rank 0: ``NcclComm.make_unique_id(ctx)``; ship it with any out-of-band channel, e.g. a torch.distributed
+    broadcast or a file)."""
+
+    def __init__(self, ctx, sizes, rank: int, unique_id: bytes):
+        from . import _lib
+
+        self.ctx = ctx
+        self.sizes = list(sizes)
+        self.rank = rank
+        self._c_dptr = _lib.c_dptr
+        buf = C.create_string_buffer(bytes(unique_id), _lib.UNIQUE_ID_BYTES)
+        ctx.check(ctx.lib.pdq_comm_init(ctx.h, buf, len(self.sizes), rank))
+        self._cap = 0
+        self._send = self._recv = None
+
+    @staticmethod
+    def make_unique_id(ctx) -> bytes:
+        from . import _lib
+
+        buf = C.create_string_buffer(_lib.UNIQUE_ID_BYTES)
+        ctx.check(ctx.lib.pdq_comm_unique_id(ctx.h, buf))
+        return buf.raw
+
+    def _gather_equal(self, send):
+        n = len(send)
+        world = len(self.sizes)
+        if n > self._cap:
+            if self._send:
+                self.ctx.free(self._send)
+                self.ctx.free(self._recv)
+            self._send = self.ctx.malloc(n * 8)
+            self._recv = self.ctx.malloc(n * 8 * world)
+            self._cap = n
+            self._hs = self.ctx.pinned_empty((n,))
+            self._hr = self.ctx.pinned_empty((n * world,))
+        self._hs[:] = send
+        self.ctx.h2d(self._send, self._hs)
+        self.ctx.check(self.ctx.lib.pdq_allgather_f64_dev(self.ctx.h, self._c_dptr(self._send), self._c_dptr(self._recv), n))
+        self.ctx.d2h(self._hr, self._recv)
+        self.ctx.sync()
+        return self._hr.copy()
+
+    def close(self):
+        self.ctx.check(self.ctx.lib.pdq_comm_destroy(self.ctx.h))

@@ -1,0 +1,136 @@
+"""GPU suite: chained-pipeline parity against the oracle on seeded inputs, the resident driver against the
+host-buffer driver, and size-independent properties at BASELINE.json's full single-GPU size."""
+import os
+
+import numpy as np
+import pytest
+
+from parity import rel_err
+
+pytestmark = pytest.mark.gpu
+
+# north star (BASELINE.json): LFCs, dispersions, Wald statistics / p-values within 1e-4 relative of the
+# reference CPU backend on the same counts/design
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def inf():
+    from pydeseq2_b200.inference import B200Inference
+
+    return B200Inference(device=0)
+
+
+def _data(N, G, kind, seed):
+    from pydeseq2_b200.pipeline import median_of_ratios
+    from pydeseq2_b200.synth import make_counts
+
+    counts, X, _ = make_counts(N, G, kind, seed)
+    counts = np.ascontiguousarray(counts[:, ~(counts == 0).all(0)])
+    return counts, X, median_of_ratios(counts)[1]
+
+
+def _frac_bad(got, want, rtol, atol=0.0, mask=None):
+    bad = ~np.isclose(got, want, rtol=rtol, atol=atol, equal_nan=True)
+    if mask is not None:
+        bad = bad[mask] if bad.ndim == 1 else bad[mask, :]
+    return float(bad.mean()), bad
+
+
+@pytest.mark.parametrize("N,G,kind,seed", [(200, 3000, "two_level", 0), (100, 1500, "factorial", 1), (120, 1500, "continuous", 2)])
+def test_chained_pipeline_matches_oracle(inf, N, G, kind, seed):
+    from oracle import nbglm
+    from pydeseq2_b200.pipeline import fit_host
+
+    counts, X, sf = _data(N, G, kind, seed)
+    ref = fit_host(counts, X, nbglm.OracleInference(n_cpus=os.cpu_count()), size_factors=sf)
+    got = fit_host(counts, X, inf, size_factors=sf)
+    # genes on which the reference itself trusts its fit (converged-mask aware comparison)
+    ok = (ref.genewise_converged == 1) & (ref.map_converged == 1) & (ref.lfc_converged == 1)
+    assert ok.mean() > 0.99
+    np.testing.assert_allclose(got.trend.coeffs, ref.trend.coeffs, rtol=1e-4)
+    assert got.prior_var == pytest.approx(ref.prior_var, rel=1e-4)
+    for name, a, b, atol in (("lfc", got.lfc, ref.lfc, 1e-8), ("dispersions", got.dispersions, ref.dispersions, 0.0),
+                             ("stat", got.stat, ref.stat, 1e-8), ("se", got.se, ref.se, 0.0)):
+        frac, bad = _frac_bad(a, b, RTOL, atol, ok)
+        assert frac == 0.0, f"{name}: {frac:.2%} of converged genes off by more than {RTOL}; worst {np.nanmax(rel_err(a, b)):.2e}"
+    big = ok & (ref.pvalue >= 1e-20)
+    frac, _ = _frac_bad(got.pvalue, ref.pvalue, 1e-3, 0.0, big)
+    assert frac == 0.0
+    # -log10 p agrees everywhere it is finite
+    with np.errstate(divide="ignore"):
+        lp_g, lp_r = -np.log10(got.pvalue[ok]), -np.log10(ref.pvalue[ok])
+    fin = np.isfinite(lp_r)
+    np.testing.assert_allclose(lp_g[fin], lp_r[fin], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("N,G,kind", [(200, 4000, "two_level"), (60, 1000, "factorial")])
+def test_resident_driver_equals_host_buffer_driver(inf, N, G, kind):
+    from pydeseq2_b200.pipeline import ResidentFit, fit_host
+
+    counts, X, sf = _data(N, G, kind, 4)
+    host = fit_host(counts, X, inf, size_factors=sf)
+    rf = ResidentFit(inf._ops.ctx, X, sf)
+    rf.upload(counts)
+    r = rf.run()
+    np.testing.assert_allclose(r["mom"], host.mom, rtol=1e-10)
+    np.testing.assert_allclose(r["genewise"], host.genewise, rtol=1e-9)
+    np.testing.assert_allclose(r["dispersions"], host.dispersions, rtol=1e-8)
+    np.testing.assert_allclose(r["lfc"], host.lfc, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(r["stat"], host.stat, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(r["pvalue"], host.pvalue, rtol=1e-7, atol=1e-300)
+    rf.close()
+
+
+def test_full_size_properties(inf):
+    """BASELINE.json configs[1] (20 000 genes x 200 samples): properties that need no CPU reference."""
+    counts, X, sf = _data(200, 20000, "two_level", 0)
+    N, G = counts.shape
+    rng = np.random.default_rng(0)
+    disp = np.exp(rng.normal(-1.5, 1.0, G))
+    beta, mu, hat, conv = inf.irls(counts, sf, X, disp, 0.5, 1e-8)
+    assert np.isfinite(beta).all() and (conv == 1).mean() > 0.999
+    # (1) genes are independent: any permutation / subset of genes gives bit-identical per-gene results
+    perm = rng.permutation(G)
+    b2, m2, h2, c2 = inf.irls(np.ascontiguousarray(counts[:, perm]), sf, X, disp[perm], 0.5, 1e-8)
+    np.testing.assert_array_equal(b2, beta[perm])
+    np.testing.assert_array_equal(m2, mu[:, perm])
+    np.testing.assert_array_equal(h2, hat[:, perm])
+    sub = slice(5000, 5321)
+    b3, m3, h3, c3 = inf.irls(counts[:, sub], sf, X, disp[sub], 0.5, 1e-8)
+    np.testing.assert_array_equal(b3, beta[sub])
+    # (2) mu is the unclamped sf * exp(X beta); the hat diagonal sums to p (trace of a projector, ridge 1e-6)
+    np.testing.assert_allclose(mu, sf[:, None] * np.exp(X @ beta.T), rtol=1e-12)
+    unclamped = (mu >= 0.5).all(0)
+    np.testing.assert_allclose(hat[:, unclamped].sum(0), X.shape[1], rtol=1e-4)
+    # (3) IRLS fixed point: the score X^T (y - mu) W/mu ... vanishes at the returned beta (unclamped genes)
+    W = mu / (1 + mu * disp)
+    score = np.einsum("np,ng->gp", X, (counts - mu) * W / mu)
+    scale = np.einsum("np,ng->gp", np.abs(X), np.abs(counts - mu) * W / mu) + 1e-12
+    assert np.percentile(np.abs(score[unclamped]) / scale[unclamped], 99) < 1e-3
+    # (4) Wald: swapping the sign of the contrast flips the statistic and keeps SE and p
+    ridge = np.diag(np.repeat(1e-6, 2))
+    p1, s1, e1 = inf.wald_test(X, disp, beta, mu, ridge, np.array([0.0, 1.0]), 0.0, None)
+    p2, s2, e2 = inf.wald_test(X, disp, beta, mu, ridge, np.array([0.0, -1.0]), 0.0, None)
+    np.testing.assert_array_equal(s1, -s2)
+    np.testing.assert_array_equal(p1, p2)
+    np.testing.assert_array_equal(e1, e2)
+    # (5) dispersion estimate is a stationary point of the reference objective (checked with the oracle's gradient on a sample)
+    from oracle import nbglm
+
+    alpha, aconv = inf.alpha_mle(counts, X, mu, disp, 1e-8, float(N))
+    assert (aconv == 1).mean() > 0.999
+    for g in rng.choice(G, 200, replace=False):
+        a = alpha[g]
+        if not (1e-6 < a < N * 0.99):
+            continue
+        y, m = counts[:, g], mu[:, g]
+
+        def dloss(la):
+            al = np.exp(la)
+            Wg = m / (1 + m * al)
+            return al * nbglm.dnb_nll(y, m, al) + 0.5 * al * (np.linalg.inv((X.T * Wg) @ X) * ((X.T * (-(Wg**2))) @ X)).sum()
+
+        h = 1e-4
+        curv = (dloss(np.log(a) + h) - dloss(np.log(a) - h)) / (2 * h)
+        assert abs(dloss(np.log(a)) / curv) < 1e-5, (g, a)  # Newton distance to the stationary point, in log alpha
