@@ -68,6 +68,7 @@ int pdq_host_alloc(pdq_ctx* ctx, size_t bytes, void** hptr); /* pinned host memo
 int pdq_host_free(pdq_ctx* ctx, void* hptr);
 int pdq_memcpy_h2d(pdq_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
 int pdq_memcpy_d2h(pdq_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
+int pdq_memcpy_d2d(pdq_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
 int pdq_memset(pdq_ctx* ctx, void* dst, int value, size_t bytes);
 int pdq_sync(pdq_ctx* ctx);
 /* CUDA-event timing on the context's stream (bench.py): record slot 0/1, elapsed ms between them */
@@ -119,6 +120,13 @@ int pdq_fit_rough_dispersions(pdq_ctx* ctx, const double* normed_counts, int64_t
 int pdq_fit_moments_dispersions(pdq_ctx* ctx, const double* normed_counts, int64_t ld, int N, int G,
                                 const double* size_factors, double* alpha_out, double* all_zero_out);
 
+/* Inference.dispersion_trend_gamma_glm  (inference.py:283-307; default_inference.py:200-230): ONE gamma-GLM
+ * fit  targets ~ c0 + c1 * covariates  (identity link) from (1, 1) under c >= 1e-12.  `coeffs_out` (2,),
+ * `pred_out` (n,) = c0 + c1 * covariates, `converged_out` 0/1.  The reference's scipy L-BFGS-B stops within
+ * ~4e-6 of the minimiser; this converges to the minimiser itself. */
+int pdq_dispersion_trend_gamma_glm(pdq_ctx* ctx, const double* covariates, const double* targets, size_t n,
+                                   double* coeffs_out, double* pred_out, int* converged_out);
+
 /* ----------------------------------------------------------------- hot path, device-resident
  * Same semantics; every pointer except `design` is device memory from pdq_malloc.  Asynchronous. */
 int pdq_lin_reg_mu_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld, int G,
@@ -141,6 +149,13 @@ int pdq_wald_test_dev(pdq_ctx* ctx, const pdq_design* design, const double* disp
 int pdq_mom_dispersions_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld,
                             int G, double min_disp, double max_disp, double* alpha_out,
                             double* normed_mean_out);
+/* Parametric dispersion trend INCLUDING the caller's outer loop (dds.py:1199-1275: fit, drop genes with
+ * genewise/fitted outside [1e-4, 15), refit until sum(log(c/c_old)^2) < 1e-6), entirely on the device.
+ * `normed_means`, `genewise` (n,) device; genewise is clipped to [min_disp, max_disp] on the fly (dds.py:792).
+ * `out8` (8 doubles, device): c0, c1, status (0 ok / 1 = fall back to the mean trend), outer rounds,
+ * genes used, inner iterations, loss, 0.  `fitted_out` (n,) device, may be NULL: c0 + c1 / mean. */
+int pdq_trend_fit_dev(pdq_ctx* ctx, const double* normed_means, const double* genewise, size_t n, double min_disp,
+                      double max_disp, double* out8, double* fitted_out);
 /* mu = size_factor * exp(X beta) for the Wald stage (ds.py:320-324), device-resident */
 int pdq_mu_from_lfc_dev(pdq_ctx* ctx, const pdq_design* design, const double* lfc, int G,
                         double* mu_out, int64_t ld_out);

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "pdq_host_free": (C.c_int, [c_ctx, C.c_void_p]),
     "pdq_memcpy_h2d": (C.c_int, [c_ctx, c_dptr, C.c_void_p, C.c_size_t]),
     "pdq_memcpy_d2h": (C.c_int, [c_ctx, C.c_void_p, c_dptr, C.c_size_t]),
+    "pdq_memcpy_d2d": (C.c_int, [c_ctx, c_dptr, c_dptr, C.c_size_t]),
     "pdq_memset": (C.c_int, [c_ctx, c_dptr, C.c_int, C.c_size_t]),
     "pdq_sync": (C.c_int, [c_ctx]),
     "pdq_event_record": (C.c_int, [c_ctx, C.c_int]),
@@ -71,6 +72,8 @@ _SIGNATURES = {
                                     C.c_int, c_dptr, c_dptr, c_dptr]),
     "pdq_mom_dispersions_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, C.c_double, C.c_double, c_dptr,
                                           c_dptr]),
+    "pdq_dispersion_trend_gamma_glm": (C.c_int, [c_ctx, f64p, f64p, C.c_size_t, f64p, f64p, C.POINTER(C.c_int)]),
+    "pdq_trend_fit_dev": (C.c_int, [c_ctx, c_dptr, c_dptr, C.c_size_t, C.c_double, C.c_double, c_dptr, c_dptr]),
     "pdq_mu_from_lfc_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int, c_dptr, C.c_int64]),
     "pdq_comm_unique_id": (C.c_int, [c_ctx, C.c_void_p]),
     "pdq_comm_init": (C.c_int, [c_ctx, C.c_void_p, C.c_int, C.c_int]),

@@ -32,7 +32,7 @@ struct NcclApi {
 };
 static const int kNcclFloat64 = 8;  // ncclDataType_t::ncclFloat64 (stable across NCCL 2.x)
 
-enum { kBufCounts, kBufA, kBufB, kBufC, kBufD, kBufE, kBufF, kBufG, kBufStatus, kBufMisc, kNumBufs };
+enum { kBufCounts, kBufA, kBufB, kBufC, kBufD, kBufE, kBufF, kBufG, kBufStatus, kBufMisc, kBufKeep, kNumBufs };
 
 struct pdq_ctx {
     int device = 0;
@@ -213,6 +213,11 @@ extern "C" int pdq_memcpy_d2h(pdq_ctx* c, void* dst, const void* src, size_t byt
     CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     return PDQ_OK;
 }
+extern "C" int pdq_memcpy_d2d(pdq_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c) return PDQ_ERR_INVALID;
+    CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return PDQ_OK;
+}
 extern "C" int pdq_memset(pdq_ctx* c, void* dst, int value, size_t bytes) {
     if (!c) return PDQ_ERR_INVALID;
     CU(c, cudaMemsetAsync(dst, value, bytes, c->stream));
@@ -373,6 +378,18 @@ extern "C" int pdq_mu_from_lfc_dev(pdq_ctx* c, const pdq_design* d, const double
     return done(c, launch_mu_from_lfc(cfg(c, G, d->d.N), d->d, lfc, G, mu, ld_out), "mu_from_lfc");
 }
 
+extern "C" int pdq_trend_fit_dev(pdq_ctx* c, const double* means, const double* genewise, size_t n, double min_disp, double max_disp,
+                                 double* out8, double* fitted) {
+    CHECK_CTX(c);
+    if (!means || !genewise || !out8 || n == 0) return fail(c, PDQ_ERR_INVALID, "pdq_trend_fit_dev: bad arguments");
+    void* keep;
+    if (int e = ensure(c, kBufKeep, n, &keep)) return e;
+    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount};
+    if (int e = done(c, launch_trend_fit(lc, means, genewise, (unsigned char*)keep, n, 1, min_disp, max_disp, 1, out8), "trend_fit")) return e;
+    if (fitted) return done(c, launch_trend_eval(lc, means, n, out8, fitted), "trend_eval");
+    return PDQ_OK;
+}
+
 // --------------------------------------------------------------------------------------------- host-buffer ops
 static int h2d_2d(pdq_ctx* c, void* dst, const void* src, int64_t ld, int N, int G, size_t elem) {
     if (ld == G) {
@@ -526,6 +543,33 @@ extern "C" int pdq_fit_moments_dispersions(pdq_ctx* c, const double* normed, int
     CU(c, cudaMemcpyAsync(alpha_out, da, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(all_zero_out, dz, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    return PDQ_OK;
+}
+
+extern "C" int pdq_dispersion_trend_gamma_glm(pdq_ctx* c, const double* cov, const double* targets, size_t n, double* coeffs_out,
+                                              double* pred_out, int* converged_out) {
+    CHECK_CTX(c);
+    if (!cov || !targets || !coeffs_out || !pred_out || !converged_out || n == 0)
+        return fail(c, PDQ_ERR_INVALID, "pdq_dispersion_trend_gamma_glm: bad arguments");
+    void *dx, *dt, *keep, *dout;
+    if (int e = ensure(c, kBufC, n * 8, &dx)) return e;
+    if (int e = ensure(c, kBufD, n * 8, &dt)) return e;
+    if (int e = ensure(c, kBufKeep, n, &keep)) return e;
+    if (int e = ensure(c, kBufMisc, 64, &dout)) return e;
+    CU(c, cudaMemcpyAsync(dx, cov, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dt, targets, n * 8, cudaMemcpyHostToDevice, c->stream));
+    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount};
+    const double inf = 1.0 / 0.0;
+    if (int e = done(c, launch_trend_fit(lc, (const double*)dx, (const double*)dt, (unsigned char*)keep, n, 0, -inf, inf, 0, (double*)dout),
+                     "dispersion_trend_gamma_glm"))
+        return e;
+    double out[8];
+    CU(c, cudaMemcpyAsync(out, dout, sizeof out, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    coeffs_out[0] = out[0];
+    coeffs_out[1] = out[1];
+    *converged_out = out[7] != 0.0;  // the reference's flag is L-BFGS-B's `success`; ours: the iteration converged
+    for (size_t i = 0; i < n; ++i) pred_out[i] = out[0] + out[1] * cov[i];
     return PDQ_OK;
 }
 

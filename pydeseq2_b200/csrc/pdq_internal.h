@@ -50,6 +50,10 @@ int launch_mom_from_counts(const LaunchCfg&, const DesignDev&, const int64_t* co
                            double min_disp, double max_disp, double* alpha, double* normed_mean);
 int launch_mu_from_lfc(const LaunchCfg&, const DesignDev&, const double* lfc, int G, double* mu, int64_t ld_out);
 
+int launch_trend_fit(const LaunchCfg&, const double* x, const double* t, unsigned char* keep, size_t n, int x_is_mean,
+                     double lo, double hi, int outer, double* out8);
+int launch_trend_eval(const LaunchCfg&, const double* means, size_t n, const double* out8, double* fitted);
+
 // largest dynamic shared memory a kernel of this library may ask for (B200: 227 KB per CTA)
 constexpr size_t kMaxDynSmem = 227 * 1024;
 

@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include "pdq_gene.cuh"
+#include "pdq_trend.cuh"
 #include "pdq_internal.h"
 
 namespace pdq {
@@ -311,6 +312,65 @@ __global__ void __launch_bounds__(kBlock) k_mu_from_lfc(const __grid_constant__ 
     }
 }
 
+
+// ---- dispersion trend: the whole gamma-GLM fit (all iterations, all outer rounds) in one cooperative block ----
+struct BlockReducer {
+    double* sm;  // 33 doubles of shared memory
+    __host__ __device__ int tid() const {
+#if defined(__CUDA_ARCH__)
+        return threadIdx.x;
+#else
+        return 0;
+#endif
+    }
+    __host__ __device__ int nthreads() const {
+#if defined(__CUDA_ARCH__)
+        return blockDim.x;
+#else
+        return 1;
+#endif
+    }
+    __host__ __device__ void sync() {
+#if defined(__CUDA_ARCH__)
+        __syncthreads();
+#endif
+    }
+    __host__ __device__ double sum(double v) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        __syncthreads();  // previous result fully consumed
+        if (lane == 0) sm[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            double w = (lane < (blockDim.x >> 5)) ? sm[lane] : 0.0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
+            if (lane == 0) sm[32] = w;
+        }
+        __syncthreads();
+        return sm[32];
+#else
+        return v;
+#endif
+    }
+};
+
+__global__ void __launch_bounds__(1024) k_trend_fit(const double* __restrict__ x, const double* __restrict__ t,
+                                                    unsigned char* keep, size_t n, int x_is_mean, double lo, double hi,
+                                                    int outer, TrendOut* out) {
+    __shared__ double sm[33];
+    BlockReducer red{sm};
+    trend_fit_outer(red, x, t, keep, n, x_is_mean != 0, lo, hi, outer != 0, out);
+}
+
+// fitted = c0 + c1 / mean (dds.py:1267-1275) from the device-resident coefficients
+__global__ void k_trend_eval(const double* __restrict__ means, size_t n, const TrendOut* __restrict__ c, double* fitted) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fitted[i] = c->c0 + c->c1 / means[i];
+}
+
 // ---- launch helpers ---------------------------------------------------------------------------------
 inline int grid_for(int G, int lgT) {
     const int genes_per_block = kWarps * (32 >> lgT);
@@ -454,6 +514,19 @@ int launch_mu_from_lfc(const LaunchCfg& c, const DesignDev& d, const double* lfc
         if (int e = prep(k_mu_from_lfc<P>, d.smem_bytes)) return e;
         k_mu_from_lfc<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });
+    if (int e = check_launch()) return e;
+    return 1;
+}
+
+int launch_trend_fit(const LaunchCfg& c, const double* x, const double* t, unsigned char* keep, size_t n, int x_is_mean,
+                     double lo, double hi, int outer, double* out8) {
+    k_trend_fit<<<1, 1024, 0, c.stream>>>(x, t, keep, n, x_is_mean, lo, hi, outer, reinterpret_cast<TrendOut*>(out8));
+    if (int e = check_launch()) return e;
+    return 1;
+}
+
+int launch_trend_eval(const LaunchCfg& c, const double* means, size_t n, const double* out8, double* fitted) {
+    k_trend_eval<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(means, n, reinterpret_cast<const TrendOut*>(out8), fitted);
     if (int e = check_launch()) return e;
     return 1;
 }

@@ -313,27 +313,58 @@ class ResidentFit:
         begin("alpha_mle_genewise")
         check(L.pdq_alpha_mle_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(self.d_mom), self.min_disp,
                                       self.max_disp, 1.0, 1, 0, c_d(self.d_gw), c_d(self.d_gw_conv)))
-        ctx.d2h(H["gw"], self.d_gw)
-        ctx.d2h(H["means"], self.d_means)
+        # 4. trend + prior: global over ALL genes of ALL shards (dds.py:799-884).  The gamma-GLM trend (all
+        #    iterations, all outer rounds) is one kernel launch on the device-resident vectors; with gene shards
+        #    the per-gene vectors are all-gathered over NCCL first, device to device.
+        W = self.comm.world if self.comm is not None else 1
+        rank = self.comm.rank if self.comm is not None else 0
+        m = self.comm.max_size if self.comm is not None else G
+        n_all = W * m
+        if self.comm is not None:
+            d_gw_all, d_means_all = self._dev("gw_all", n_all * 8), self._dev("means_all", n_all * 8)
+            begin("allgather")
+            self.comm.allgather_dev(self.d_gw, d_gw_all, self.d_means, d_means_all, G)
+            if profile:
+                check(0)
+        else:
+            d_gw_all, d_means_all = self.d_gw, self.d_means
+        d_fit_all = self._dev("fitted_all", n_all * 8)
+        d_t8 = self._dev("trend8", 64)
+        begin("trend_fit")
+        check(L.pdq_trend_fit_dev(h, c_d(d_means_all), c_d(d_gw_all), n_all, self.min_disp, self.max_disp, c_d(d_t8), c_d(d_fit_all)))
+        self.d_fitted = d_fit_all + rank * m * 8  # this shard's slice of the fitted curve
+        if "all" not in self._h or self._h["all"].shape[1] != n_all:
+            self._h["all"] = ctx.pinned_empty((3, n_all))
+            self._h["t8"] = ctx.pinned_empty((8,))
+        A = self._h["all"]
+        ctx.d2h(A[0], d_gw_all)
+        ctx.d2h(A[1], d_means_all)
+        ctx.d2h(A[2], d_fit_all)
+        ctx.d2h(self._h["t8"], d_t8)
         ctx.d2h(H["gw_conv"], self.d_gw_conv)
         ctx.sync()
-        gw = np.clip(H["gw"], self.min_disp, self.max_disp)
-        means = H["means"]
-        # 4. trend + prior: global over ALL genes of ALL shards (dds.py:799-884)
         t0 = time.perf_counter()
-        if self.comm is not None:
-            gw_all, means_all = self.comm.allgather_pair(gw, means)
-        else:
-            gw_all, means_all = gw, means
-        trend = fit_trend(trend_inference or _HostTrend(), means_all, gw_all, self.min_disp, fit_type)
+        valid = ~np.isnan(A[1])  # padding of ragged shards
+        gw_all = np.clip(A[0][valid], self.min_disp, self.max_disp)
+        means_all = A[1][valid]
+        lo = rank * m
+        gw = np.clip(A[0][lo:lo + G], self.min_disp, self.max_disp)
+        means = A[1][lo:lo + G].copy()
+        t8 = self._h["t8"]
+        if fit_type == "parametric" and t8[2] == 0.0:
+            trend = TrendFit("parametric", np.array([t8[0], t8[1]]), A[2][valid], int(t8[3]))
+            fitted = A[2][lo:lo + G].copy()
+        else:  # dds.py:1243-1252: mean-trend fallback
+            if fit_type == "parametric":
+                warnings.warn("The dispersion trend curve fitting did not converge. Switching to a mean-based dispersion trend.",
+                              UserWarning, stacklevel=2)
+            trend = fit_trend(None, means_all, gw_all, self.min_disp, "mean")
+            fitted = np.full(G, trend.coeffs[0])
+            H["fitted"][:] = fitted
+            self.d_fitted = self._dev("fitted", G * 8)
+            ctx.h2d(self.d_fitted, H["fitted"])
         sq, prior_var = fit_prior_var(gw_all, trend.fitted, self.N, p, self.min_disp)
-        if trend.kind == "parametric":
-            fitted = trend.coeffs[0] + trend.coeffs[1] / means
-        else:
-            fitted = np.full_like(gw, trend.coeffs[0])
-        self.stage_ms["trend_prior_host"] = (time.perf_counter() - t0) * 1e3
-        H["fitted"][:] = fitted
-        ctx.h2d(self.d_fitted, H["fitted"])
+        self.stage_ms["prior_host"] = (time.perf_counter() - t0) * 1e3
         # 5. MAP dispersions (dds.py:886-935)
         begin("alpha_mle_map")
         check(L.pdq_alpha_mle_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(self.d_fitted), self.min_disp,

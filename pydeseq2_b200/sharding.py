@@ -86,6 +86,9 @@ class NcclComm(_PaddedGather):
         ctx.check(ctx.lib.pdq_comm_init(ctx.h, buf, len(self.sizes), rank))
         self._cap = 0
         self._send = self._recv = None
+        self.world = len(self.sizes)
+        self.max_size = max(self.sizes)
+        self._pad = None
 
     @staticmethod
     def make_unique_id(ctx) -> bytes:
@@ -113,6 +116,22 @@ class NcclComm(_PaddedGather):
         self.ctx.d2h(self._hr, self._recv)
         self.ctx.sync()
         return self._hr.copy()
+
+    def allgather_dev(self, d_a, d_a_all, d_b, d_b_all, n_local):
+        """Device-to-device all-gather of two per-gene vectors (genewise dispersions, normalised means).  Ragged
+        shards are NaN-padded to the largest shard so that NCCL's equal-count all-gather applies."""
+        m = self.max_size
+        lib, h, cd = self.ctx.lib, self.ctx.h, self._c_dptr
+        for src, dst in ((d_a, d_a_all), (d_b, d_b_all)):
+            send = src
+            if n_local < m:  # stage a NaN-padded copy of the short shard
+                if self._pad is None:
+                    self._pad = self.ctx.malloc(m * 8)
+                    self._nan = np.full(m, np.nan)
+                self.ctx.h2d(self._pad, self._nan)
+                self.ctx.check(lib.pdq_memcpy_d2d(h, cd(self._pad), cd(src), n_local * 8))
+                send = self._pad
+            self.ctx.check(lib.pdq_allgather_f64_dev(h, cd(send), cd(dst), m))
 
     def close(self):
         self.ctx.check(self.ctx.lib.pdq_comm_destroy(self.ctx.h))

@@ -73,3 +73,16 @@ class EmuOps:
                                           C.c_double(min_disp), C.c_double(max_disp), _p(a, f64p), _p(m, f64p))
         assert rc == 0
         return a, m
+
+    def trend_glm(self, cov, targets):
+        out = np.zeros(8)
+        rc = self.lib.emu_trend_fit(_p(cov, f64p), _p(targets, f64p), C.c_size_t(len(cov)), 0, C.c_double(-np.inf),
+                                    C.c_double(np.inf), 0, _p(out, f64p))
+        assert rc == 0
+        return out[:2].copy(), out[0] + out[1] * cov, bool(out[7])
+
+    def trend_outer(self, means, gw, lo, hi):
+        out = np.zeros(8)
+        assert self.lib.emu_trend_fit(_p(means, f64p), _p(gw, f64p), C.c_size_t(len(gw)), 1, C.c_double(lo), C.c_double(hi), 1,
+                                      _p(out, f64p)) == 0
+        return out

@@ -13,6 +13,7 @@
 
 #include "../../pydeseq2_b200/csrc/pdq_gene.cuh"
 #include "../../pydeseq2_b200/csrc/pdq_host_linalg.h"
+#include "../../pydeseq2_b200/csrc/pdq_trend.cuh"
 
 using namespace pdq;
 
@@ -169,6 +170,13 @@ int emu_mom_from_counts(const int64_t* counts, int64_t ld, int N, int G, const d
             normed_mean[g] = mean;
         }
     });
+    return 0;
+}
+
+int emu_trend_fit(const double* x, const double* t, size_t n, int x_is_mean, double lo, double hi, int outer, double* out8) {
+    std::vector<unsigned char> keep(n);
+    SerialReducer red;
+    trend_fit_outer(red, x, t, keep.data(), n, x_is_mean != 0, lo, hi, outer != 0, reinterpret_cast<TrendOut*>(out8));
     return 0;
 }
 

@@ -98,7 +98,8 @@ def test_full_size_properties(inf):
     np.testing.assert_array_equal(h2, hat[:, perm])
     sub = slice(5000, 5321)
     b3, m3, h3, c3 = inf.irls(counts[:, sub], sf, X, disp[sub], 0.5, 1e-8)
-    np.testing.assert_array_equal(b3, beta[sub])
+    # a 321-gene call uses more lanes per gene than the 20 000-gene call: only the summation tree differs
+    np.testing.assert_allclose(b3, beta[sub], rtol=1e-10, atol=1e-13)
     # (2) mu is the unclamped sf * exp(X beta); the hat diagonal sums to p (trace of a projector, ridge 1e-6)
     np.testing.assert_allclose(mu, sf[:, None] * np.exp(X @ beta.T), rtol=1e-12)
     unclamped = (mu >= 0.5).all(0)
