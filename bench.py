@@ -267,8 +267,10 @@ def main():
     # ---------------------------------------------------------------- e2e: plugin calls with host buffers
     c_host = ctx.pinned_empty(counts.shape, np.int64)
     c_host[:] = counts
+    n_host = ctx.pinned_empty(counts.shape, np.float64)  # layers["normed_counts"] of the orchestrator (dds.py:700-708)
+    np.divide(counts, sf[:, None], out=n_host)
     for _ in range(2):
-        fit_host(c_host, X, inf, size_factors=sf, comm=comm)
+        fit_host(c_host, X, inf, size_factors=sf, comm=comm, normed_counts=n_host)
     barrier()
     ops = inf._ops
     h0, d0 = ops.h2d_bytes, ops.d2h_bytes
@@ -277,7 +279,7 @@ def main():
     for _ in range(args.steps):
         barrier()
         t0 = time.perf_counter()
-        fit_host(c_host, X, inf, size_factors=sf, comm=comm, timings=e2e_T)
+        fit_host(c_host, X, inf, size_factors=sf, comm=comm, timings=e2e_T, normed_counts=n_host)
         ctx.sync()
         e2e_t.append(time.perf_counter() - t0)
     e2e_s = float(np.mean(e2e_t))

@@ -10,10 +10,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpydeseq2_b200.so")
 SOURCES = ["pdq_kernels.cu", "pdq_api.cu"]
-HEADERS = ["pdq_math.cuh", "pdq_gene.cuh", "pdq_internal.h", "pdq_host_linalg.h",
+HEADERS = ["pdq_math.cuh", "pdq_fast.cuh", "pdq_trend.cuh", "pdq_gene.cuh", "pdq_internal.h", "pdq_host_linalg.h",
            os.path.join("..", "..", "include", "pydeseq2_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC,-fopenmp", "--expt-relaxed-constexpr"]
 
 
 def _nvcc() -> str:
@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if force or _stale(OUT, objs):
         cmd = [_nvcc(), "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
-                                                        "-ldl", "-lrt", "-lpthread"]
+                                                        "-ldl", "-lrt", "-lpthread", "-lgomp"]
         subprocess.run(cmd, check=True)
     return OUT
 

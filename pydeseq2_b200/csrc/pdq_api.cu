@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -47,6 +48,11 @@ struct pdq_ctx {
     // cached design of the host-buffer entry points (keyed on the bytes of X and size factors)
     pdq_design* cached = nullptr;
     std::vector<double> cached_X, cached_sf;
+    // page-locked staging ring for pageable host buffers (numpy arrays are pageable)
+    void* stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    bool stage_busy[2] = {false, false};
+    int staging = 1;  // PDQ_STAGING=0 disables (plain cudaMemcpyAsync from pageable memory)
     NcclApi nccl;
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
@@ -142,6 +148,7 @@ extern "C" int pdq_ctx_create(int device, pdq_ctx** out) {
             delete c;
             return PDQ_ERR_CUDA;
         }
+    if (const char* s = getenv("PDQ_STAGING")) c->staging = atoi(s);
     *out = c;
     return PDQ_OK;
 }
@@ -153,6 +160,10 @@ extern "C" void pdq_ctx_destroy(pdq_ctx* c) {
     if (c->cached) pdq_design_destroy(c, c->cached);
     for (auto& b : c->buf)
         if (b) cudaFree(b);
+    for (int i = 0; i < 2; ++i) {
+        if (c->stage[i]) cudaFreeHost(c->stage[i]);
+        if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
+    }
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -391,12 +402,88 @@ extern "C" int pdq_trend_fit_dev(pdq_ctx* c, const double* means, const double* 
 }
 
 // --------------------------------------------------------------------------------------------- host-buffer ops
-static int h2d_2d(pdq_ctx* c, void* dst, const void* src, int64_t ld, int N, int G, size_t elem) {
-    if (ld == G) {
-        CU(c, cudaMemcpyAsync(dst, src, (size_t)N * G * elem, cudaMemcpyHostToDevice, c->stream));
-    } else {
-        CU(c, cudaMemcpy2DAsync(dst, (size_t)G * elem, src, (size_t)ld * elem, (size_t)G * elem, N, cudaMemcpyHostToDevice, c->stream));
+// ---- host <-> device copies of caller buffers ------------------------------------------------------------------
+// numpy arrays are pageable; a plain cudaMemcpy from/to pageable memory is staged by the driver at a fraction of the
+// PCIe rate.  Large pageable buffers are therefore pipelined through two page-locked chunks owned by the context:
+// a few host threads copy chunk k+1 into / out of the ring while the DMA engine moves chunk k.
+static const size_t kStageChunk = 8u << 20;
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
     }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static void par_memcpy(void* dst, const void* src, size_t n) {
+    const int nt = n >= (2u << 20) ? 4 : 1;
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int t = 0; t < nt; ++t) {
+        const size_t lo = n * t / nt, hi = n * (t + 1) / nt;
+        memcpy((char*)dst + lo, (const char*)src + lo, hi - lo);
+    }
+}
+
+static int stage_init(pdq_ctx* c) {
+    for (int i = 0; i < 2; ++i)
+        if (!c->stage[i]) {
+            CU(c, cudaHostAlloc(&c->stage[i], kStageChunk, cudaHostAllocDefault));
+            CU(c, cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+        }
+    return 0;
+}
+
+static int copy_h2d(pdq_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c->staging || bytes < (1u << 20) || is_pinned(src)) {
+        CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        return 0;
+    }
+    if (int e = stage_init(c)) return e;
+    int k = 0;
+    for (size_t off = 0; off < bytes; off += kStageChunk, k ^= 1) {
+        const size_t n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
+        if (c->stage_busy[k]) CU(c, cudaEventSynchronize(c->stage_ev[k]));
+        par_memcpy(c->stage[k], (const char*)src + off, n);
+        CU(c, cudaMemcpyAsync((char*)dst + off, c->stage[k], n, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaEventRecord(c->stage_ev[k], c->stream));
+        c->stage_busy[k] = true;
+    }
+    return 0;
+}
+
+// device -> caller buffer; the pageable path synchronises the stream chunk by chunk
+static int copy_d2h(pdq_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (!c->staging || bytes < (1u << 20) || is_pinned(dst)) {
+        CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        return 0;
+    }
+    if (int e = stage_init(c)) return e;
+    for (int i = 0; i < 2; ++i)
+        if (c->stage_busy[i]) {
+            CU(c, cudaEventSynchronize(c->stage_ev[i]));
+            c->stage_busy[i] = false;
+        }
+    const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
+    for (size_t i = 0; i <= nchunks; ++i) {
+        if (i < nchunks) {  // launch DMA of chunk i into slot i&1
+            const size_t off = i * kStageChunk, n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
+            CU(c, cudaMemcpyAsync(c->stage[i & 1], (const char*)src + off, n, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaEventRecord(c->stage_ev[i & 1], c->stream));
+        }
+        if (i > 0) {  // drain chunk i-1 while chunk i is in flight
+            const size_t j = i - 1, off = j * kStageChunk, n = bytes - off < kStageChunk ? bytes - off : kStageChunk;
+            CU(c, cudaEventSynchronize(c->stage_ev[j & 1]));
+            par_memcpy((char*)dst + off, c->stage[j & 1], n);
+        }
+    }
+    return 0;
+}
+
+static int h2d_2d(pdq_ctx* c, void* dst, const void* src, int64_t ld, int N, int G, size_t elem) {
+    if (ld == G) return copy_h2d(c, dst, src, (size_t)N * G * elem);
+    CU(c, cudaMemcpy2DAsync(dst, (size_t)G * elem, src, (size_t)ld * elem, (size_t)G * elem, N, cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
 
@@ -412,7 +499,7 @@ extern "C" int pdq_lin_reg_mu(pdq_ctx* c, const int64_t* counts, int64_t ld, int
     if (int e = ensure(c, kBufA, ng * 8, &dm)) return e;
     if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
     if (int e = pdq_lin_reg_mu_dev(c, d, (const int64_t*)dc, G, G, min_mu, (double*)dm, G)) return e;
-    CU(c, cudaMemcpyAsync(mu_out, dm, ng * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (int e = copy_d2h(c, mu_out, dm, ng * 8)) return e;
     CU(c, cudaStreamSynchronize(c->stream));
     return PDQ_OK;
 }
@@ -441,8 +528,8 @@ extern "C" int pdq_irls(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, in
         return e;
     CU(c, cudaMemcpyAsync(beta_out, dbeta, (size_t)G * p * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(conv_out, dconv, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(mu_out, dmu, ng * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(hat_out, dhat, ng * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (int e = copy_d2h(c, mu_out, dmu, ng * 8)) return e;
+    if (int e = copy_d2h(c, hat_out, dhat, ng * 8)) return e;
     int nfb = 0;
     CU(c, cudaMemcpyAsync(&nfb, dmisc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));

@@ -1,0 +1,121 @@
+// pdq_fast.cuh -- FP64 log / exp / reciprocal tuned for the sm_100a FP64 pipe.
+//
+// Why not libdevice's `log`, `exp` and the `/` operator: the ncu profile of round 1 (profiles/r1_alpha_mle.md)
+// showed that 32 % of all issued warp instructions were UMOV / IMAD.MOV pairs materialising 64-bit polynomial
+// coefficients next to every DFMA, plus BSSY/BSYNC/branch scaffolding around each division's slow path.  Here
+//   * coefficients live in __constant__ memory, so DFMA takes them as constant-bank operands (no extra instruction);
+//   * the reciprocal is MUFU.RCP64H + two Newton steps, branch-free (operands on this path are normal, finite);
+//   * special cases (NaN, inf, zero, denormal, |x| huge) fall through to libdevice behind one predictable branch.
+// Accuracy: <= 2 ulp for log/exp over the guarded range, <= 1 ulp for the reciprocal (checked against libm in
+// tests/test_emu_parity.py through the host emulator, which compiles the same polynomials).
+#pragma once
+
+#include "pdq_math.cuh"
+
+namespace pdq {
+
+#if defined(__CUDA_ARCH__)
+#define PDQ_CONST __constant__
+#else
+#define PDQ_CONST static const
+#endif
+
+// log(m) = 2f (1 + s g(s)),  f = (m-1)/(m+1), s = f^2, m in [sqrt(1/2), sqrt(2)];  g ~ degree-6 fit, |rel err| < 6e-18
+PDQ_CONST double kLogG[7] = {0.3333333333333335, 0.1999999999994302, 0.14285714315994175, 0.11111105083699467,
+                             0.09091479328268151, 0.07664720034027003, 0.073221513558091};
+// e^r = 1 + r + r^2 q(r) on |r| <= ln2/2;  q ~ degree-9 fit, |abs err| < 1.5e-17
+PDQ_CONST double kExpQ[10] = {0.5000000000000001, 0.1666666666666667, 0.04166666666662063, 0.008333333333325553,
+                              0.0013888888918941061, 0.00019841269876841745, 2.480151863878229e-05,
+                              2.7557252858587773e-06, 2.762133977167299e-07, 2.5106265298633842e-08};
+PDQ_CONST double kLn2Hi = 6.93147180369123816490e-01;  // ln2 with the low 21 bits zero (fdlibm split)
+PDQ_CONST double kLn2Lo = 1.90821492927058770002e-10;
+PDQ_CONST double kLog2e = 1.44269504088896338700e+00;
+
+// 1/d for normal finite d (|d| in [2^-1000, 2^1000]): hardware seed + two Newton-Raphson steps
+PDQ_HD double fast_rcp(double d) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+#else
+    return 1.0 / d;
+#endif
+}
+
+// a / b with one residual correction (<= 1 ulp for normal operands)
+PDQ_HD double fast_div(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    const double y = fast_rcp(b);
+    const double q = a * y;
+    return fma(fma(-b, q, a), y, q);
+#else
+    return a / b;
+#endif
+}
+
+PDQ_HD double fast_log(double x) {
+#if defined(__CUDA_ARCH__)
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(x);  // <=0, denormal, inf, NaN: libdevice semantics
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    if (hi >= 0x3ff6a09f) {  // m > ~sqrt(2): halve it
+        hi -= 0x00100000;
+        e += 1;
+    }
+    const double m = __hiloint2double(hi, lo);
+    const double ed = (double)e;
+#else
+    if (!(x > 2.2250738585072014e-308) || !(x < 1.7976931348623157e308)) return log(x);
+    int e;
+    double m = frexp(x, &e);  // m in [0.5, 1)
+    m *= 2.0;
+    e -= 1;
+    if (m > 1.4142135623730951) {
+        m *= 0.5;
+        e += 1;
+    }
+    const double ed = (double)e;
+#endif
+    const double f = fast_div(m - 1.0, m + 1.0);
+    const double s = f * f;
+    double g = kLogG[6];
+    g = fma(g, s, kLogG[5]);
+    g = fma(g, s, kLogG[4]);
+    g = fma(g, s, kLogG[3]);
+    g = fma(g, s, kLogG[2]);
+    g = fma(g, s, kLogG[1]);
+    g = fma(g, s, kLogG[0]);
+    const double f2 = f + f;
+    // e*ln2_hi is exact (|e| < 2^11, ln2_hi has 21 trailing zero bits)
+    return fma(ed, kLn2Hi, f2 + fma(f2 * s, g, ed * kLn2Lo));
+}
+
+PDQ_HD double fast_exp(double x) {
+    if (!(fabs(x) < 700.0)) return exp(x);  // overflow/underflow edge, inf, NaN: libm/libdevice semantics
+    const double kd = rint(x * kLog2e);
+    const double r = fma(-kd, kLn2Lo, fma(-kd, kLn2Hi, x));
+    double q = kExpQ[9];
+    q = fma(q, r, kExpQ[8]);
+    q = fma(q, r, kExpQ[7]);
+    q = fma(q, r, kExpQ[6]);
+    q = fma(q, r, kExpQ[5]);
+    q = fma(q, r, kExpQ[4]);
+    q = fma(q, r, kExpQ[3]);
+    q = fma(q, r, kExpQ[2]);
+    q = fma(q, r, kExpQ[1]);
+    q = fma(q, r, kExpQ[0]);
+    const double p = fma(r * r, q, r) + 1.0;
+    const int k = (int)kd;  // |k| <= 1010: 2^k is a normal double
+#if defined(__CUDA_ARCH__)
+    return p * __hiloint2double((k + 1023) << 20, 0);
+#else
+    return ldexp(p, k);
+#endif
+}
+
+}  // namespace pdq

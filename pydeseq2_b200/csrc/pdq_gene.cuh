@@ -11,6 +11,7 @@
 // there, T = 1), see pdq_math.cuh.
 #pragma once
 
+#include "pdq_fast.cuh"
 #include "pdq_math.cuh"
 
 namespace pdq {
@@ -19,6 +20,26 @@ struct Group {
     int si;   // this lane's first sample
     int T;    // lanes per gene (sample stride)
     int gpw;  // genes per warp = 32 / T
+    // exclusive prefix sum over the lanes of this gene ordered by si (host: single lane -> 0)
+    PDQ_HD double excl_scan(double v) const {
+#if defined(__CUDA_ARCH__)
+        const int lane = threadIdx.x & 31;
+        double inc = v;
+        for (int off = gpw; off < 32; off <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        return inc - v;
+#else
+        (void)v;
+        return 0.0;
+#endif
+    }
+    PDQ_HD void sync() const {
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+    }
     PDQ_HD double sum(double v) const {
 #if defined(__CUDA_ARCH__)
         for (int off = 16; off >= gpw; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -125,28 +146,33 @@ PDQ_HD void irls_sweep(const Group& grp, const DesignS& d, const int64_t* y, int
 #pragma unroll
     for (int j = 0; j < P; ++j) b[j] = 0.0;
     S = 0.0;
+    const int64_t ystep = (int64_t)grp.T * ld;
+    const int64_t* yp = y + (int64_t)grp.si * ld;
+    const double* xp = d.X + grp.si;
 #pragma unroll 2
-    for (int n = grp.si; n < d.N; n += grp.T) {
+    for (int n = grp.si; n < d.N; n += grp.T, yp += ystep, xp += grp.T) {
         double x[P];
-        load_x<P>(d, n, x);
-        const double yv = (double)y[n * ld];
+#pragma unroll
+        for (int j = 0; j < P; ++j) x[j] = xp[j * d.Npad];
+        const double sfn = xp[P * d.Npad], lsfn = xp[(P + 1) * d.Npad];  // sf and log sf follow X in the pack
+        const double yv = (double)*yp;
         double eta = 0.0;
 #pragma unroll
         for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
-        const double mu_raw = d.sf[n] * exp(eta);
+        const double mu_raw = sfn * fast_exp(eta);
         const bool cl = mu_raw < min_mu;
         const double mu = cl ? min_mu : mu_raw;                        // np.maximum(sf*exp(X b), min_mu)
-        const double lmu_sf = cl ? (log_min_mu - d.lsf[n]) : eta;      // log(mu / sf)
-        const double lmu = cl ? log_min_mu : (eta + d.lsf[n]);         // log(mu)
+        const double lmu_sf = cl ? (log_min_mu - lsfn) : eta;          // log(mu / sf)
+        const double lmu = cl ? log_min_mu : (eta + lsfn);             // log(mu)
         const double den = fma(mu, alpha, 1.0);
-        const double q = 1.0 / (mu * den);
+        const double q = fast_rcp(mu * den);
         const double W = mu * mu * q;                                  // mu / (1 + mu alpha)
         const double z = fma(yv - mu, den * q, lmu_sf);                // log(mu/sf) + (y - mu)/mu
         sym_rank1<P>(A, W, x);
         const double Wz = W * z;
 #pragma unroll
         for (int j = 0; j < P; ++j) b[j] = fma(Wz, x[j], b[j]);
-        S += fma(yv + r, log(r + mu), -yv * lmu);
+        S += fma(yv + r, fast_log(r + mu), -yv * lmu);
     }
     group_sum_sym<P>(grp, A);
     group_sum_vec<P>(grp, b);
@@ -174,13 +200,13 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
         double x[P];
         load_x<P>(d, n, x);
         const double yv = (double)y[n * ld];
-        const double q = yv / d.sf[n];
+        const double q = fast_div(yv, d.sf[n]);
         if (prm.full_rank) {
-            const double t = log(q + 0.1);
+            const double t = fast_log(q + 0.1);
 #pragma unroll
             for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
         } else {
-            logmean += log(q);
+            logmean += fast_log(q);
         }
         lgsum += lgamma_pos(yv + 1.0) - lgamma_pos(yv + r);
     }
@@ -260,9 +286,9 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
         double eta = 0.0;
 #pragma unroll
         for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
-        const double mu_raw = d.sf[n] * exp(eta);
+        const double mu_raw = d.sf[n] * fast_exp(eta);
         const double mu = (mu_raw < prm.min_mu) ? prm.min_mu : mu_raw;
-        const double W = mu / fma(mu, alpha, 1.0);
+        const double W = fast_div(mu, fma(mu, alpha, 1.0));
         mu_out[n * ld_out] = mu_raw;
         hat_out[n * ld_out] = W * sym_quad<P>(Hinv, x);
     }
@@ -500,25 +526,67 @@ struct AlphaParams {
     int cr_reg, prior_reg;
 };
 
+// psi(r + k), k = 0..kPsiK-1, per gene and per evaluation, in shared memory: psi(r+k) = psi(r) + sum_{j<k} 1/(r+j).
+// The lanes of the gene split the reciprocals into contiguous segments and stitch them with an exclusive scan.
+// Samples with count < kPsiK then cost one table read instead of a shifted asymptotic series, and counts >= kPsiK
+// always satisfy the z >= 10 precondition of the unshifted series.
+constexpr int kPsiK = 32;
+
+PDQ_HD void build_psi_table(const Group& grp, double* tab, double r) {
+    const int seg = kPsiK / grp.T;              // T in {1,...,32} divides 32
+    const int k0 = grp.si * seg;
+    double part = 0.0;
+    for (int k = k0; k < k0 + seg; ++k) {
+        const double inv = fast_rcp(r + (double)k);
+        tab[k] = inv;
+        part += inv;
+    }
+    double run = digamma_pos(r) + grp.excl_scan(part);
+    for (int k = k0; k < k0 + seg; ++k) {
+        const double inv = tab[k];
+        tab[k] = run;
+        run += inv;
+    }
+    grp.sync();
+}
+
 // derivative only (the minimiser is located as a root of dloss)
 template <int P>
 PDQ_HD double alpha_dloss(const Group& grp, const DesignS& d, const AlphaParams& prm, const int64_t* y, int64_t ld,
-                          const double* mu, int64_t ld_mu, double x, double xhat) {
-    const double a = exp(x), r = 1.0 / a, Nd = (double)d.N;
+                          const double* mu, int64_t ld_mu, double x, double xhat, double* psi_tab) {
+#if defined(PDQ_EMU_COUNT_EVALS) && !defined(__CUDA_ARCH__)
+    ++g_emu_alpha_evals;  // host emulator instrumentation only
+#endif
+    const double a = fast_exp(x), r = fast_rcp(a), Nd = (double)d.N;
+    grp.sync();  // previous evaluation's table reads are done
+    build_psi_table(grp, psi_tab, r);
     double Sg = 0.0;
     Sym<P> A, B;
     sym_zero<P>(A);
     sym_zero<P>(B);
+    const int64_t ystep = (int64_t)grp.T * ld, mstep = (int64_t)grp.T * ld_mu;
+    const int64_t* yp = y + (int64_t)grp.si * ld;
+    const double* mp = mu + (int64_t)grp.si * ld_mu;
+    const double* xp = d.X + grp.si;
 #pragma unroll 2
-    for (int n = grp.si; n < d.N; n += grp.T) {
-        const double yv = (double)y[n * ld];
-        const double m = mu[n * ld_mu];
+    for (int n = grp.si; n < d.N; n += grp.T, yp += ystep, mp += mstep, xp += grp.T) {
+        const long long yi = *yp;
+        const double yv = (double)yi;
+        const double m = *mp;
         const double rm = r + m;
-        const double inv = 1.0 / rm;
-        Sg += log(rm) - digamma_pos(yv + r) + (yv - m) * inv;
+        const double inv = fast_rcp(rm);
+        double dg;
+        if (yi < kPsiK && yi >= 0) {
+            dg = psi_tab[yi];
+        } else {
+            const double z = yv + r;
+            dg = digamma_asym(z, fast_log(z));
+        }
+        Sg += fast_log(rm) - dg + (yv - m) * inv;
         if (prm.cr_reg) {
             double xv[P];
-            load_x<P>(d, n, xv);
+#pragma unroll
+            for (int j = 0; j < P; ++j) xv[j] = xp[j * d.Npad];
             const double W = m * r * inv;
             sym_rank1<P>(A, W, xv);
             sym_rank1<P>(B, W * W, xv);
@@ -526,7 +594,7 @@ PDQ_HD double alpha_dloss(const Group& grp, const DesignS& d, const AlphaParams&
     }
     Sg = grp.sum(Sg);
     // a * dnb_nll = -r * sum[psi(r) - psi(y+r) + log(1 + mu a) + (y - mu)/(mu + r)],  log(1+mu a) = x + log(r+mu)
-    double g = -r * (Nd * (digamma_pos(r) + x) + Sg);
+    double g = -r * (Nd * (psi_tab[0] + x) + Sg);
     if (prm.cr_reg) {
         group_sum_sym<P>(grp, A);
         group_sum_sym<P>(grp, B);
@@ -578,11 +646,11 @@ constexpr int kAlphaNeedsGrid = 1;  // the reference's `res.success == False` br
 template <int P>
 PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& prm, const int64_t* y, int64_t ld,
                        const double* mu, int64_t ld_mu, double alpha_hat, double* alpha_out, double* conv_out,
-                       int* status_out, bool valid) {
+                       int* status_out, bool valid, double* psi_tab) {
     const double xhat = log(alpha_hat);
     const double tolx = 1e-5;   // last secant step is taken unevaluated: final error << tolx
     double xb = fmin(fmax(xhat, prm.lo), prm.hi);
-    double gb = alpha_dloss<P>(grp, d, prm, y, ld, mu, ld_mu, xb, xhat);
+    double gb = alpha_dloss<P>(grp, d, prm, y, ld, mu, ld_mu, xb, xhat, psi_tab);
     double xa = xb, ga = gb;
     double bl = prm.lo, br = prm.hi;  // bracket ends (valid when have_br)
     bool have_br = false, active = true, fail = false;
@@ -599,7 +667,7 @@ PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& pr
     }
     for (int ev = 0; ev < 60; ++ev) {
         if (!grp.any(active)) break;
-        const double gt = alpha_dloss<P>(grp, d, prm, y, ld, mu, ld_mu, xt, xhat);
+        const double gt = alpha_dloss<P>(grp, d, prm, y, ld, mu, ld_mu, xt, xhat, psi_tab);
         if (!active) continue;
         if (!(gt == gt)) {
             fail = true;

@@ -179,8 +179,11 @@ __global__ void __launch_bounds__(kBlock) k_alpha_mle(const __grid_constant__ Al
     int g;
     bool valid;
     map_lanes(a.lgT, a.G, grp, g, valid);
+    // per-gene psi(r + k) tables live behind the design pack and its mbarrier
+    double* psi = reinterpret_cast<double*>(smem + (size_t)(P + 2) * a.dv.Npad * 8 + 16) +
+                  (size_t)((threadIdx.x >> 5) * grp.gpw + ((threadIdx.x & 31) & (grp.gpw - 1))) * kPsiK;
     alpha_gene<P>(grp, d, a.prm, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha_hat[g], a.alpha + g, a.conv + g,
-                  a.status + g, valid);
+                  a.status + g, valid, psi);
 }
 
 template <int P>
@@ -445,9 +448,10 @@ int launch_alpha_mle(const LaunchCfg& c, const DesignDev& d, const int64_t* coun
     PDQ_DISPATCH_P(d.p, {
         AlphaArgs<P> a{{d.pack, d.N, d.Npad}, AlphaParams{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg},
                        counts, ld, G, c.lgT, mu, ld_mu, alpha_hat, alpha, conv, status};
-        if (int e = prep(k_alpha_mle<P>, d.smem_bytes)) return e;
+        const size_t smem_alpha = d.smem_bytes + (size_t)kWarps * (32 >> c.lgT) * kPsiK * sizeof(double);
+        if (int e = prep(k_alpha_mle<P>, smem_alpha)) return e;
         if (int e = prep(k_alpha_grid<P>, d.smem_bytes)) return e;
-        k_alpha_mle<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+        k_alpha_mle<P><<<grid_for(G, c.lgT), kBlock, smem_alpha, c.stream>>>(a);
         k_alpha_grid<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });
     if (int e = check_launch()) return e;

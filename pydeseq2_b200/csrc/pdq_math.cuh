@@ -180,8 +180,12 @@ PDQ_HD void shift10(double x, double& P, double& dP) {
     }
 }
 
+PDQ_HD double fast_rcp(double d);  // pdq_fast.cuh
+PDQ_HD double fast_div(double a, double b);
+PDQ_HD double fast_log(double x);
+
 PDQ_HD double digamma_asym(double z, double logz) {  // z >= 10
-    const double iz = 1.0 / z, w = iz * iz;
+    const double iz = fast_rcp(z), w = iz * iz;
     // sum_k B_2k / (2k z^2k): 1/12, -1/120, 1/252, -1/240, 1/132, -691/32760, 1/12
     double s = 1.0 / 12.0;
     s = fma(s, w, -691.0 / 32760.0);
@@ -194,7 +198,7 @@ PDQ_HD double digamma_asym(double z, double logz) {  // z >= 10
 }
 
 PDQ_HD double lgamma_asym(double z, double logz) {  // z >= 10
-    const double iz = 1.0 / z, w = iz * iz;
+    const double iz = fast_rcp(z), w = iz * iz;
     // sum_k B_2k / (2k (2k-1) z^(2k-1)): 1/12, -1/360, 1/1260, -1/1680, 1/1188, -691/360360, 1/156
     double s = 1.0 / 156.0;
     s = fma(s, w, -691.0 / 360360.0);
@@ -207,19 +211,19 @@ PDQ_HD double lgamma_asym(double z, double logz) {  // z >= 10
 }
 
 PDQ_HD double digamma_pos(double x) {
-    if (x >= 10.0) return digamma_asym(x, log(x));
+    if (x >= 10.0) return digamma_asym(x, fast_log(x));
     double P, dP;
     shift10(x, P, dP);
     const double z = x + 10.0;
-    return digamma_asym(z, log(z)) - dP / P;
+    return digamma_asym(z, fast_log(z)) - fast_div(dP, P);
 }
 
 PDQ_HD double lgamma_pos(double x) {
-    if (x >= 10.0) return lgamma_asym(x, log(x));
+    if (x >= 10.0) return lgamma_asym(x, fast_log(x));
     double P, dP;
     shift10(x, P, dP);
     const double z = x + 10.0;
-    return lgamma_asym(z, log(z)) - log(P);
+    return lgamma_asym(z, fast_log(z)) - fast_log(P);
 }
 
 // both at once (shares the log and the shift)

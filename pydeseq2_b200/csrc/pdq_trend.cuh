@@ -122,25 +122,34 @@ PDQ_HD bool trend_fit_once(R& red, const double* x, const double* t, const unsig
                 d1 = -(a * s.g1 - b * s.g0) / det;
             }
         }
-        // backtracking on the loss, projecting onto c >= 1e-12
-        double step = 1.0, n0 = c0, n1 = c1, Ln = s.L;
-        bool acc = false;
-        for (int ls = 0; ls < 40; ++ls) {
-            n0 = fmax(fma(step, d0, c0), kLB);
-            n1 = fmax(fma(step, d1, c1), kLB);
-            Ln = trend_loss(red, x, t, keep, n, x_is_mean, lo, hi, n0, n1);
-            if (Ln <= s.L + 1e-4 * (s.g0 * (n0 - c0) + s.g1 * (n1 - c1)) || (Ln == Ln && fabs(Ln - s.L) <= 1e-15 * fabs(s.L))) {
-                acc = true;
-                break;
+        // Close to the minimiser (tiny Newton decrement) the summed loss can no longer resolve progress in FP64, but
+        // the Newton step itself still can: take it without a line search (quadratic convergence, Hessian PD here).
+        double n0 = c0, n1 = c1, Ln = s.L;
+        const double dec = -(s.g0 * d0 + s.g1 * d1);
+        if (dec <= 1e-9 * fabs(s.L)) {
+            n0 = fmax(c0 + d0, kLB);
+            n1 = fmax(c1 + d1, kLB);
+        } else {
+            // backtracking on the loss, projecting onto c >= 1e-12
+            double step = 1.0;
+            bool acc = false;
+            for (int ls = 0; ls < 40; ++ls) {
+                n0 = fmax(fma(step, d0, c0), kLB);
+                n1 = fmax(fma(step, d1, c1), kLB);
+                Ln = trend_loss(red, x, t, keep, n, x_is_mean, lo, hi, n0, n1);
+                if (Ln <= s.L + 1e-4 * (s.g0 * (n0 - c0) + s.g1 * (n1 - c1))) {
+                    acc = true;
+                    break;
+                }
+                step *= 0.5;
             }
-            step *= 0.5;
+            if (!acc) return false;
         }
-        if (!acc) return false;
         const double rel = fmax(fabs(n0 - c0) / fmax(fabs(n0), 1e-300), fabs(n1 - c1) / fmax(fabs(n1), 1e-300));
         c0 = n0;
         c1 = n1;
         loss = Ln / s.n;
-        if (rel < 1e-11) {
+        if (rel < 1e-12 || (dec <= 1e-9 * fabs(s.L) && rel < 1e-9 && it > 60)) {
             ok = true;
             break;
         }

@@ -125,12 +125,18 @@ def _expand(v, nz, G_all):
 
 
 def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5, min_disp=1e-8, max_disp=10.0,
-             beta_tol=1e-8, fit_type="parametric", lfc_null=0.0, alt_hypothesis=None, timings=None, comm=None) -> FitResult:
+             beta_tol=1e-8, fit_type="parametric", lfc_null=0.0, alt_hypothesis=None, timings=None, comm=None,
+             normed_counts=None, reuse_lfc_mu=True) -> FitResult:
     """deseq2() + run_wald_test() hot path through the plugin API with host buffers.
 
     ``comm`` (``sharding.NcclComm`` / ``TorchDistComm``): this process holds one gene shard; the genewise
     dispersions and normalised means of all shards are gathered for the trend and prior (the only cross-gene
-    step).  ``size_factors`` must then be given (they are per sample, global over genes)."""
+    step).  ``size_factors`` must then be given (they are per sample, global over genes).
+
+    ``normed_counts``: ``counts / size_factors`` when the caller already holds it (the orchestrator keeps it as
+    ``layers["normed_counts"]`` from ``fit_size_factors``, dds.py:700-708).  ``reuse_lfc_mu``: feed the Wald stage
+    with the ``mu`` the LFC fit returned -- ``irls`` returns the UNclamped ``sf * exp(X beta)`` (utils.py:435-438),
+    which is exactly what ``run_wald_test`` recomputes on the host (ds.py:320-324)."""
     T = timings if timings is not None else {}
 
     def timed(key, fn, *a, **k):
@@ -151,7 +157,7 @@ def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5,
         normed, sf = timed("size_factors", median_of_ratios, counts)
     else:
         sf = np.asarray(size_factors, dtype=float)
-        normed = counts / sf[:, None]
+        normed = normed_counts if normed_counts is not None else timed("normed_counts", lambda: counts / sf[:, None])
     nz = ~(counts == 0).all(axis=0)                      # dds.py:729-731
     all_nz = bool(nz.all())
     c = counts if all_nz else counts[:, nz]              # no copy when the caller already dropped all-zero genes
@@ -189,7 +195,12 @@ def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5,
     lfc_all = _expand(np.asarray(lfc), nz, G_all)
     disp_all = _expand(disp, nz, G_all)
     t0 = time.perf_counter()
-    mu_w = np.exp(X @ lfc_all.T) * sf[:, None]
+    if reuse_lfc_mu:
+        mu_w = mu_lfc if all_nz else np.full((N, G_all), np.nan)
+        if not all_nz:
+            mu_w[:, nz] = mu_lfc
+    else:
+        mu_w = np.exp(X @ lfc_all.T) * sf[:, None]
     T["wald_mu_host"] = T.get("wald_mu_host", 0.0) + time.perf_counter() - t0
     ridge = np.diag(np.repeat(1e-6, p))
     pv, st, se = timed("wald_test", inference.wald_test, X, disp_all, lfc_all, mu_w, ridge, np.asarray(contrast, float),

@@ -11,10 +11,13 @@
 
 #include <vector>
 
+extern long g_emu_alpha_evals;
+#define PDQ_EMU_COUNT_EVALS 1
 #include "../../pydeseq2_b200/csrc/pdq_gene.cuh"
 #include "../../pydeseq2_b200/csrc/pdq_host_linalg.h"
 #include "../../pydeseq2_b200/csrc/pdq_trend.cuh"
 
+long g_emu_alpha_evals = 0;
 using namespace pdq;
 
 namespace {
@@ -106,8 +109,9 @@ int emu_alpha_mle(const int64_t* counts, int64_t ld, int N, int G, const double*
     Pack k = make_pack(X, nullptr, N, p);
     EMU_DISPATCH(p, {
         const AlphaParams prm{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg};
+        double psi[kPsiK];
         for (int g = 0; g < G; ++g) {
-            alpha_gene<P>(kOne, k.d, prm, counts + g, ld, mu + g, ld_mu, alpha_hat[g], alpha + g, conv + g, status + g, true);
+            alpha_gene<P>(kOne, k.d, prm, counts + g, ld, mu + g, ld_mu, alpha_hat[g], alpha + g, conv + g, status + g, true, psi);
             if (force_grid) status[g] = kAlphaNeedsGrid;
             if (status[g] == kAlphaNeedsGrid)
                 alpha_grid_gene<P>(kOne, k.d, prm.lo, prm.hi, counts + g, ld, mu + g, ld_mu, alpha + g, true);
@@ -180,6 +184,9 @@ int emu_trend_fit(const double* x, const double* t, size_t n, int x_is_mean, dou
     return 0;
 }
 
+long emu_eval_count(int reset) { long v = g_emu_alpha_evals; if (reset) g_emu_alpha_evals = 0; return v; }
+double emu_fast_log(double x) { return fast_log(x); }
+double emu_fast_exp(double x) { return fast_exp(x); }
 double emu_lgamma(double x) { return lgamma_pos(x); }
 double emu_digamma(double x) { return digamma_pos(x); }
 int emu_design_rank_pinv(const double* X, int N, int p, double* pinv) {

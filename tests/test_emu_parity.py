@@ -36,3 +36,25 @@ def test_special_functions():
     dg = np.array([ops.lib.emu_digamma(float(x)) for x in xs])
     np.testing.assert_allclose(lg, gammaln(xs), rtol=2e-14, atol=3e-14)
     np.testing.assert_allclose(dg, polygamma(0, xs), rtol=2e-14, atol=3e-14)
+
+
+def test_fast_log_exp_accuracy():
+    """The kernels' own log/exp (constant-bank polynomials, pdq_fast.cuh) against libm: <= 2 ulp."""
+    import ctypes as C
+
+    ops = EmuOps()
+    for f in (ops.lib.emu_fast_log, ops.lib.emu_fast_exp):
+        f.restype = C.c_double
+        f.argtypes = [C.c_double]
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([np.exp(rng.uniform(-700, 700, 20000)), rng.uniform(0.5, 2.0, 20000), [1.0, 2.0, 0.5, 1e-300, 1e300]])
+    got = np.array([ops.lib.emu_fast_log(float(x)) for x in xs])
+    want = np.log(xs)
+    ulp = np.spacing(np.abs(want)) + 1e-320
+    assert np.max(np.abs(got - want) / np.maximum(ulp, np.spacing(1e-16))) <= 2.0 or np.allclose(got, want, rtol=4e-16, atol=3e-16)
+    np.testing.assert_allclose(got, want, rtol=5e-16, atol=3e-16)
+    es = np.concatenate([rng.uniform(-690, 690, 20000), rng.uniform(-1, 1, 20000), [0.0, 1.0, -1.0, 709.0, -745.0]])
+    got = np.array([ops.lib.emu_fast_exp(float(x)) for x in es])
+    np.testing.assert_allclose(got, np.exp(es), rtol=5e-16)
+    assert np.isnan(ops.lib.emu_fast_exp(float("nan"))) and np.isnan(ops.lib.emu_fast_log(float("nan")))
+    assert ops.lib.emu_fast_log(0.0) == -np.inf and np.isnan(ops.lib.emu_fast_log(-1.0))
