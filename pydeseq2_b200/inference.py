@@ -304,264 +304,6 @@ class B200Inference(_InferenceBase):
         coeffs, pred, ok = self._ops.trend_glm(cov, tgt)
         return coeffs, pred, ok
 
-    def lfc_shrink_nbinom_glm(self, design_matrix, counts, size, offset, prior_no_shrink_scale, prior_scale,
-                                  optimizer, shrink_index): ...
-
-
-def _f64(a, name, ndim=None):
-    a = np.asarray(a.values if hasattr(a, "values") else a)
-    if a.dtype != np.float64:
-        a = a.astype(np.float64)
-    if ndim is not None and a.ndim != ndim:
-        raise ValueError(f"{name} must be {ndim}-dimensional, got shape {a.shape}")
-    return a
-
-
-def _rows(a, dtype, name):
-    """(N, G) array with unit stride along genes; returns (array, row pitch in elements)."""
-    a = np.asarray(a.values if hasattr(a, "values") else a)
-    if a.ndim != 2:
-        raise ValueError(f"{name} must be (samples, genes), got shape {a.shape}")
-    if a.dtype != dtype:
-        if dtype == np.int64 and a.dtype.kind == "f" and not np.all(np.isfinite(a)):
-            raise ValueError(f"{name} contains NaN/inf")
-        a = a.astype(dtype)
-    item = a.dtype.itemsize
-    if a.shape[1] > 1 and a.strides[1] != item or a.strides[0] % item or a.strides[0] < a.shape[1] * item:
-        a = np.ascontiguousarray(a)
-    return a, (a.strides[0] // item if a.shape[0] > 1 else a.shape[1])
-
-
-class _CudaOps:
-    """Raw ops on numpy buffers through the C ABI (host-buffer entry points)."""
-
-    def __init__(self, device=0, lanes_per_gene=0, pinned_outputs=True):
-        self.ctx = _lib.Context(device)
-        self.lib = self.ctx.lib
-        self.pinned_outputs = pinned_outputs
-        self.h2d_bytes = 0  # bytes the calls below asked the library to copy in / out (bench.py `e2e`)
-        self.d2h_bytes = 0
-        if lanes_per_gene:
-            self.ctx.check(self.lib.pdq_set_lanes_per_gene(self.ctx.h, int(lanes_per_gene)))
-
-    def empty(self, shape):
-        # large outputs land in recycled page-locked blocks: the D2H copy then runs at full PCIe rate
-        if self.pinned_outputs and int(np.prod(shape)) >= (1 << 16):
-            return self.ctx.pinned_empty(shape)
-        return np.empty(shape, dtype=np.float64)
-
-    def _io(self, ins, outs):
-        self.h2d_bytes += sum(a.nbytes for a in ins)
-        self.d2h_bytes += sum(a.nbytes for a in outs)
-
-    def lin_reg_mu(self, counts, ld, N, G, sf, X, p, min_mu, mu):
-        self._io((counts, sf, X), (mu,))
-        self.ctx.check(self.lib.pdq_lin_reg_mu(self.ctx.h, as_i64p(counts), ld, N, G, as_f64p(sf), as_f64p(X), p, min_mu,
-                                               as_f64p(mu)))
-
-    def irls(self, counts, ld, N, G, sf, X, p, disp, min_mu, beta_tol, min_beta, max_beta, maxiter, beta, mu, hat, conv):
-        nfb = C.c_int(0)
-        self._io((counts, sf, X, disp), (beta, mu, hat, conv))
-        self.ctx.check(self.lib.pdq_irls(self.ctx.h, as_i64p(counts), ld, N, G, as_f64p(sf), as_f64p(X), p, as_f64p(disp),
-                                         min_mu, beta_tol, min_beta, max_beta, maxiter, as_f64p(beta), as_f64p(mu),
-                                         as_f64p(hat), as_f64p(conv), C.byref(nfb)))
-        return nfb.value
-
-    def alpha_mle(self, counts, ld, N, G, X, p, mu, ld_mu, alpha_hat, min_disp, max_disp, prior_var, cr_reg, prior_reg,
-                  alpha, conv):
-        self._io((counts, mu, X, alpha_hat), (alpha, conv))
-        self.ctx.check(self.lib.pdq_alpha_mle(self.ctx.h, as_i64p(counts), ld, N, G, as_f64p(X), p, as_f64p(mu), ld_mu,
-                                              as_f64p(alpha_hat), min_disp, max_disp, prior_var, cr_reg, prior_reg,
-                                              as_f64p(alpha), as_f64p(conv)))
-
-    def wald_test(self, X, N, p, disp, lfc, mu, ld_mu, G, ridge, contrast, lfc_null, alt, pv, stat, se):
-        self._io((X, disp, lfc, mu), (pv, stat, se))
-        self.ctx.check(self.lib.pdq_wald_test(self.ctx.h, as_f64p(X), N, p, as_f64p(disp), as_f64p(lfc), as_f64p(mu), ld_mu,
-                                              G, as_f64p(ridge), as_f64p(contrast), lfc_null, alt, as_f64p(pv),
-                                              as_f64p(stat), as_f64p(se)))
-
-    def rough(self, normed, ld, N, G, X, p, out):
-        self._io((normed, X), (out,))
-        self.ctx.check(self.lib.pdq_fit_rough_dispersions(self.ctx.h, as_f64p(normed), ld, N, G, as_f64p(X), p, as_f64p(out)))
-
-    def moments(self, normed, ld, N, G, sf, out, all_zero):
-        self._io((normed, sf), (out, all_zero))
-        self.ctx.check(self.lib.pdq_fit_moments_dispersions(self.ctx.h, as_f64p(normed), ld, N, G, as_f64p(sf), as_f64p(out),
-                                                            as_f64p(all_zero)))
-
-
-    def trend_glm(self, cov, targets):
-        n = len(cov)
-        coeffs = np.empty(2)
-        pred = np.empty(n)
-        ok = C.c_int(0)
-        self._io((cov, targets), (coeffs,))
-        self.ctx.check(self.lib.pdq_dispersion_trend_gamma_glm(self.ctx.h, as_f64p(cov), as_f64p(targets), n, as_f64p(coeffs),
-                                                               as_f64p(pred), C.byref(ok)))
-        return coeffs, pred, bool(ok.value)
-
-
-class B200Inference(_InferenceBase):
-    """B200 implementation of the reference's ``Inference`` plugin API.
-
-    Parameters
-    ----------
-    device : int
-        CUDA device ordinal (one backend object per GPU; gene shards across GPUs are handled by
-        ``pydeseq2_b200.sharding``).
-    n_cpus : int, optional
-        Accepted and stored because ``DeseqDataSet``/``DeseqStats`` set it on the backend
-        (``dds.py:323-333``, ``ds.py:194-204``); it has no effect on the GPU path.
-    lanes_per_gene : int
-        0 (default) picks the lanes cooperating on one gene from the number of genes.
-    """
-
-    def __init__(self, device: int = 0, n_cpus: int | None = None, lanes_per_gene: int = 0, _ops=None):
-        self._ops = _ops if _ops is not None else _CudaOps(device, lanes_per_gene)
-        self._n_cpus = n_cpus or 1
-        self.last_irls_fallbacks = 0
-
-    @property
-    def n_cpus(self) -> int:  # noqa: D102
-        return self._n_cpus
-
-    @n_cpus.setter
-    def n_cpus(self, n_cpus: int) -> None:
-        self._n_cpus = n_cpus or 1
-
-    # ------------------------------------------------------------------ a4: inference.py:12-43
-    def lin_reg_mu(self, counts, size_factors, design_matrix, min_mu):  # noqa: D102
-        counts, ld = _rows(counts, np.int64, "counts")
-        X = np.ascontiguousarray(_f64(design_matrix, "design_matrix", 2))
-        sf = np.ascontiguousarray(_f64(size_factors, "size_factors", 1))
-        N, G = counts.shape
-        self._check_design(X, N, sf)
-        mu = self._ops.empty((N, G))
-        if G:
-            self._ops.lin_reg_mu(counts, ld, N, G, sf, X, X.shape[1], float(min_mu), mu)
-        return mu
-
-    # ------------------------------------------------------------------ a1: inference.py:45-118
-    def irls(self, counts, size_factors, design_matrix, disp, min_mu, beta_tol, min_beta=-30, max_beta=30,
-             optimizer="L-BFGS-B", maxiter=250):  # noqa: D102
-        assert optimizer in ["BFGS", "L-BFGS-B"]  # utils.py:343 (the device optimiser honours the bounds)
-        counts, ld = _rows(counts, np.int64, "counts")
-        X = np.ascontiguousarray(_f64(design_matrix, "design_matrix", 2))
-        sf = np.ascontiguousarray(_f64(size_factors, "size_factors", 1))
-        disp = np.ascontiguousarray(_f64(disp, "disp", 1))
-        N, G = counts.shape
-        p = X.shape[1]
-        self._check_design(X, N, sf)
-        if disp.shape[0] != G:
-            raise ValueError(f"disp has {disp.shape[0]} entries for {G} genes")
-        beta = self._ops.empty((G, p))
-        mu = self._ops.empty((N, G))
-        hat = self._ops.empty((N, G))
-        conv = self._ops.empty((G,))
-        if G:
-            self.last_irls_fallbacks = self._ops.irls(counts, ld, N, G, sf, X, p, disp, float(min_mu), float(beta_tol),
-                                                      float(min_beta), float(max_beta), int(maxiter), beta, mu, hat, conv)
-        return beta, mu, hat, conv
-
-    # ------------------------------------------------------------------ a2: inference.py:120-177
-    def alpha_mle(self, counts, design_matrix, mu, alpha_hat, min_disp, max_disp, prior_disp_var=None, cr_reg=True,
-                  prior_reg=False, optimizer="L-BFGS-B"):  # noqa: D102
-        assert optimizer in ["BFGS", "L-BFGS-B"]  # utils.py:499
-        if prior_reg and prior_disp_var is None:
-            raise ValueError("Sigma_prior is required for prior regularization")  # utils.py:518
-        counts, ld = _rows(counts, np.int64, "counts")
-        mu, ld_mu = _rows(mu, np.float64, "mu")
-        X = np.ascontiguousarray(_f64(design_matrix, "design_matrix", 2))
-        alpha_hat = np.ascontiguousarray(_f64(alpha_hat, "alpha_hat", 1))
-        N, G = counts.shape
-        self._check_design(X, N)
-        if mu.shape != (N, G) or alpha_hat.shape[0] != G:
-            raise ValueError("counts, mu and alpha_hat disagree on the number of samples/genes")
-        alpha = self._ops.empty((G,))
-        conv = self._ops.empty((G,))
-        if G:
-            self._ops.alpha_mle(counts, ld, N, G, X, X.shape[1], mu, ld_mu, alpha_hat, float(min_disp), float(max_disp),
-                                float(prior_disp_var) if prior_disp_var is not None else 1.0, int(bool(cr_reg)),
-                                int(bool(prior_reg)), alpha, conv)
-        return alpha, conv
-
-    # ------------------------------------------------------------------ a3: inference.py:179-234
-    def wald_test(self, design_matrix, disp, lfc, mu, ridge_factor, contrast, lfc_null, alt_hypothesis=None):  # noqa: D102
-        if alt_hypothesis not in ALT_CODES:
-            raise KeyError(alt_hypothesis)  # same failure mode as the dict lookup at utils.py:798-803
-        X = np.ascontiguousarray(_f64(design_matrix, "design_matrix", 2))
-        mu, ld_mu = _rows(mu, np.float64, "mu")
-        disp = np.ascontiguousarray(_f64(disp, "disp", 1))
-        lfc = np.ascontiguousarray(_f64(lfc, "lfc", 2))
-        ridge = np.ascontiguousarray(_f64(ridge_factor, "ridge_factor", 2))
-        contrast = np.ascontiguousarray(_f64(contrast, "contrast", 1))
-        N, G = mu.shape
-        p = X.shape[1]
-        self._check_design(X, N)
-        if lfc.shape != (G, p) or disp.shape[0] != G or ridge.shape != (p, p) or contrast.shape[0] != p:
-            raise ValueError("wald_test arguments disagree on the number of genes/coefficients")
-        pv = self._ops.empty((G,))
-        stat = self._ops.empty((G,))
-        se = self._ops.empty((G,))
-        if G:
-            self._ops.wald_test(X, N, p, disp, lfc, mu, ld_mu, G, ridge, contrast, float(np.asarray(lfc_null)),
-                                ALT_CODES[alt_hypothesis], pv, stat, se)
-        return pv, stat, se
-
-    # ------------------------------------------------------------------ a5: inference.py:236-281
-    def fit_rough_dispersions(self, normed_counts, design_matrix):  # noqa: D102
-        normed, ld = _rows(normed_counts, np.float64, "normed_counts")
-        X = np.ascontiguousarray(_f64(design_matrix, "design_matrix", 2))
-        N, G = normed.shape
-        if N == X.shape[1]:  # utils.py:839-844, relied on by the reference's tests/test_edge_cases.py:141-158
-            raise ValueError(
-                "The number of samples and the number of design variables are "
-                "equal, i.e., there are no replicates to estimate the "
-                "dispersion. Please use a design with fewer variables."
-            )
-        self._check_design(X, N)
-        out = self._ops.empty((G,))
-        if G:
-            self._ops.rough(normed, ld, N, G, X, X.shape[1], out)
-        return out
-
-    def fit_moments_dispersions(self, normed_counts, size_factors):  # noqa: D102
-        normed, ld = _rows(normed_counts, np.float64, "normed_counts")
-        sf = np.ascontiguousarray(_f64(size_factors, "size_factors", 1))
-        N, G = normed.shape
-        out = self._ops.empty((G,))
-        all_zero = self._ops.empty((G,))
-        if G:
-            self._ops.moments(normed, ld, N, G, sf, out, all_zero)
-        return out[all_zero == 0.0]  # the reference drops all-zero columns (utils.py:878)
-
-    # ------------------------------------------------------------------ global (not per gene): host
-    def dispersion_trend_gamma_glm(self, covariates, targets):  # noqa: D102
-        """Gamma-GLM trend ``alpha ~ a0 + a1 / mean`` (inference.py:283-307, default_inference.py:200-230).
-
-        Two coefficients fitted on G-length vectors -- a global reduction, not per-gene work, 20 ms at
-        G = 20 000 -- so it stays on the host, using the reference's optimiser call.
-        """
-        from scipy.optimize import minimize
-
-        cov = _f64(covariates, "covariates", 1)
-        tgt = _f64(targets, "targets", 1)
-        D = np.stack([np.ones_like(cov), cov], axis=1)
-
-        def loss(c):
-            m = D @ c
-            return np.nanmean(tgt / m + np.log(m), axis=0)
-
-        def grad(c):
-            m = D @ c
-            return -np.nanmean(((tgt / m - 1)[:, None] * D) / m[:, None], axis=0)
-
-        try:
-            res = minimize(loss, x0=np.array([1.0, 1.0]), jac=grad, method="L-BFGS-B", bounds=[(1e-12, np.inf)])
-        except RuntimeWarning:  # coefficients collapsing to zero under `filterwarnings=error`
-            return np.array([np.nan, np.nan]), np.array([np.nan, np.nan]), False
-        return res.x, D @ res.x, res.success
-
     def lfc_shrink_nbinom_glm(self, design_matrix, counts, size, offset, prior_no_shrink_scale, prior_scale, optimizer,
                               shrink_index):  # noqa: D102
         raise NotImplementedError(
