@@ -137,8 +137,9 @@ int pdq_irls_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, 
                  double* converged_out, int* n_fallback_dev /* device int, may be NULL */);
 int pdq_alpha_mle_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld, int G,
                       const double* mu, int64_t ld_mu, const double* alpha_hat, double min_disp,
-                      double max_disp, double prior_disp_var, int cr_reg, int prior_reg,
-                      double* alpha_out, double* converged_out);
+                      double max_disp, double prior_disp_var,
+                      const double* prior_var_dev /* device double overriding prior_disp_var, may be NULL */,
+                      int cr_reg, int prior_reg, double* alpha_out, double* converged_out);
 int pdq_wald_test_dev(pdq_ctx* ctx, const pdq_design* design, const double* disp, const double* lfc,
                       const double* mu, int64_t ld_mu, int G, const double* ridge_host,
                       const double* contrast_host, double lfc_null, int alt, double* pvalue_out,
@@ -150,12 +151,21 @@ int pdq_mom_dispersions_dev(pdq_ctx* ctx, const pdq_design* design, const int64_
                             int G, double min_disp, double max_disp, double* alpha_out,
                             double* normed_mean_out);
 /* Parametric dispersion trend INCLUDING the caller's outer loop (dds.py:1199-1275: fit, drop genes with
- * genewise/fitted outside [1e-4, 15), refit until sum(log(c/c_old)^2) < 1e-6), entirely on the device.
- * `normed_means`, `genewise` (n,) device; genewise is clipped to [min_disp, max_disp] on the fly (dds.py:792).
- * `out8` (8 doubles, device): c0, c1, status (0 ok / 1 = fall back to the mean trend), outer rounds,
- * genes used, inner iterations, loss, 0.  `fitted_out` (n,) device, may be NULL: c0 + c1 / mean. */
+ * genewise/fitted outside [1e-4, 15), refit until sum(log(c/c_old)^2) < 1e-6) AND the dispersion prior
+ * (dds.py:840-884: squared scaled MAD of the log residuals, prior variance), entirely on the device in one launch of
+ * one thread-block cluster.  `normed_means`, `genewise` (n,) device; genewise is clipped to [min_disp, max_disp] on
+ * the fly (dds.py:792); NaN entries (padding of ragged gene shards) are ignored.  `trigamma_c` = polygamma(1, (N-p)/2).
+ * `out16` (16 doubles, device): c0, c1, status (0 ok / 1 = caller must fall back to the mean trend), outer rounds,
+ * genes used, inner iterations, loss, last fit converged, squared_logres, prior_var, genes above 100*min_disp, 0...
+ * `fitted_out` (n,) device, may be NULL: c0 + c1 / mean. */
 int pdq_trend_fit_dev(pdq_ctx* ctx, const double* normed_means, const double* genewise, size_t n, double min_disp,
-                      double max_disp, double* out8, double* fitted_out);
+                      double max_disp, double trigamma_c, double* out16, double* fitted_out);
+/* Final dispersions (dds.py:918-932): clip(MAP), except genes with log(genewise) > log(fitted) + 2 sqrt(squared_logres)
+ * which keep their clipped genewise value; `trend_out16` is the record written by pdq_trend_fit_dev.
+ * `outlier_out` (n,) 0/1 may be NULL. */
+int pdq_select_dispersions_dev(pdq_ctx* ctx, const double* genewise, const double* map, const double* fitted,
+                               const double* trend_out16, size_t n, double min_disp, double max_disp,
+                               double* disp_out, double* outlier_out);
 /* mu = size_factor * exp(X beta) for the Wald stage (ds.py:320-324), device-resident */
 int pdq_mu_from_lfc_dev(pdq_ctx* ctx, const pdq_design* design, const double* lfc, int G,
                         double* mu_out, int64_t ld_out);

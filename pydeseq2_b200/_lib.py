@@ -67,13 +67,15 @@ _SIGNATURES = {
     "pdq_irls_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, c_dptr, C.c_double, C.c_double, C.c_double,
                                C.c_double, C.c_int, c_dptr, c_dptr, c_dptr, C.c_int64, c_dptr, c_dptr]),
     "pdq_alpha_mle_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, c_dptr, C.c_int64, c_dptr, C.c_double,
-                                    C.c_double, C.c_double, C.c_int, C.c_int, c_dptr, c_dptr]),
+                                    C.c_double, C.c_double, c_dptr, C.c_int, C.c_int, c_dptr, c_dptr]),
     "pdq_wald_test_dev": (C.c_int, [c_ctx, c_design, c_dptr, c_dptr, c_dptr, C.c_int64, C.c_int, f64p, f64p, C.c_double,
                                     C.c_int, c_dptr, c_dptr, c_dptr]),
     "pdq_mom_dispersions_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, C.c_double, C.c_double, c_dptr,
                                           c_dptr]),
     "pdq_dispersion_trend_gamma_glm": (C.c_int, [c_ctx, f64p, f64p, C.c_size_t, f64p, f64p, C.POINTER(C.c_int)]),
-    "pdq_trend_fit_dev": (C.c_int, [c_ctx, c_dptr, c_dptr, C.c_size_t, C.c_double, C.c_double, c_dptr, c_dptr]),
+    "pdq_trend_fit_dev": (C.c_int, [c_ctx, c_dptr, c_dptr, C.c_size_t, C.c_double, C.c_double, C.c_double, c_dptr, c_dptr]),
+    "pdq_select_dispersions_dev": (C.c_int, [c_ctx, c_dptr, c_dptr, c_dptr, c_dptr, C.c_size_t, C.c_double, C.c_double, c_dptr,
+                                             c_dptr]),
     "pdq_mu_from_lfc_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int, c_dptr, C.c_int64]),
     "pdq_comm_unique_id": (C.c_int, [c_ctx, C.c_void_p]),
     "pdq_comm_init": (C.c_int, [c_ctx, C.c_void_p, C.c_int, C.c_int]),

@@ -33,7 +33,7 @@ struct NcclApi {
 };
 static const int kNcclFloat64 = 8;  // ncclDataType_t::ncclFloat64 (stable across NCCL 2.x)
 
-enum { kBufCounts, kBufA, kBufB, kBufC, kBufD, kBufE, kBufF, kBufG, kBufStatus, kBufMisc, kBufKeep, kNumBufs };
+enum { kBufCounts, kBufA, kBufB, kBufC, kBufD, kBufE, kBufF, kBufG, kBufStatus, kBufMisc, kBufKeep, kBufRes, kNumBufs };
 
 struct pdq_ctx {
     int device = 0;
@@ -355,15 +355,15 @@ extern "C" int pdq_irls_dev(pdq_ctx* c, const pdq_design* d, const int64_t* coun
 
 extern "C" int pdq_alpha_mle_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, const double* mu,
                                  int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp, double prior_disp_var,
-                                 int cr_reg, int prior_reg, double* alpha, double* conv) {
+                                 const double* prior_var_dev, int cr_reg, int prior_reg, double* alpha, double* conv) {
     CHECK_CTX(c);
     if (!d || !counts || !mu || !alpha_hat || !alpha || !conv || G <= 0 || ld < G || ld_mu < G)
         return fail(c, PDQ_ERR_INVALID, "pdq_alpha_mle_dev: bad arguments");
-    if (prior_reg && !(prior_disp_var > 0.0)) return fail(c, PDQ_ERR_INVALID, "alpha_mle: prior_reg needs prior_disp_var > 0");
+    if (prior_reg && !prior_var_dev && !(prior_disp_var > 0.0)) return fail(c, PDQ_ERR_INVALID, "alpha_mle: prior_reg needs prior_disp_var > 0");
     void* status;
     if (int e = ensure(c, kBufStatus, (size_t)G * sizeof(int), &status)) return e;
     return done(c, launch_alpha_mle(cfg(c, G, d->d.N), d->d, counts, ld, G, mu, ld_mu, alpha_hat, min_disp, max_disp, prior_disp_var,
-                                    cr_reg, prior_reg, alpha, conv, (int*)status), "alpha_mle");
+                                    prior_var_dev, cr_reg, prior_reg, alpha, conv, (int*)status), "alpha_mle");
 }
 
 extern "C" int pdq_wald_test_dev(pdq_ctx* c, const pdq_design* d, const double* disp, const double* lfc, const double* mu,
@@ -390,15 +390,28 @@ extern "C" int pdq_mu_from_lfc_dev(pdq_ctx* c, const pdq_design* d, const double
 }
 
 extern "C" int pdq_trend_fit_dev(pdq_ctx* c, const double* means, const double* genewise, size_t n, double min_disp, double max_disp,
-                                 double* out8, double* fitted) {
+                                 double trigamma_c, double* out16, double* fitted) {
     CHECK_CTX(c);
-    if (!means || !genewise || !out8 || n == 0) return fail(c, PDQ_ERR_INVALID, "pdq_trend_fit_dev: bad arguments");
-    void* keep;
+    if (!means || !genewise || !out16 || n == 0) return fail(c, PDQ_ERR_INVALID, "pdq_trend_fit_dev: bad arguments");
+    void *keep, *res;
     if (int e = ensure(c, kBufKeep, n, &keep)) return e;
+    if (int e = ensure(c, kBufRes, n * 8, &res)) return e;
     LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount};
-    if (int e = done(c, launch_trend_fit(lc, means, genewise, (unsigned char*)keep, n, 1, min_disp, max_disp, 1, out8), "trend_fit")) return e;
-    if (fitted) return done(c, launch_trend_eval(lc, means, n, out8, fitted), "trend_eval");
+    if (int e = done(c, launch_trend_fit(lc, means, genewise, (unsigned char*)keep, n, 1, min_disp, max_disp, 1, min_disp, trigamma_c, 1,
+                                         (double*)res, out16), "trend_fit"))
+        return e;
+    if (fitted) return done(c, launch_trend_eval(lc, means, n, out16, fitted), "trend_eval");
     return PDQ_OK;
+}
+
+extern "C" int pdq_select_dispersions_dev(pdq_ctx* c, const double* genewise, const double* map, const double* fitted,
+                                          const double* trend_out16, size_t n, double min_disp, double max_disp, double* disp_out,
+                                          double* outlier_out) {
+    CHECK_CTX(c);
+    if (!genewise || !map || !fitted || !trend_out16 || !disp_out || n == 0)
+        return fail(c, PDQ_ERR_INVALID, "pdq_select_dispersions_dev: bad arguments");
+    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount};
+    return done(c, launch_select_disp(lc, genewise, map, fitted, trend_out16, n, min_disp, max_disp, disp_out, outlier_out), "select_dispersions");
 }
 
 // --------------------------------------------------------------------------------------------- host-buffer ops
@@ -556,7 +569,7 @@ extern "C" int pdq_alpha_mle(pdq_ctx* c, const int64_t* counts, int64_t ld, int 
     if (int e = h2d_2d(c, dmu, mu, ld_mu, N, G, 8)) return e;
     CU(c, cudaMemcpyAsync(dah, alpha_hat, (size_t)G * 8, cudaMemcpyHostToDevice, c->stream));
     if (int e = pdq_alpha_mle_dev(c, d, (const int64_t*)dc, G, G, (const double*)dmu, G, (const double*)dah, min_disp, max_disp,
-                                  prior_disp_var, cr_reg, prior_reg, (double*)dal, (double*)dconv))
+                                  prior_disp_var, nullptr, cr_reg, prior_reg, (double*)dal, (double*)dconv))
         return e;
     CU(c, cudaMemcpyAsync(alpha_out, dal, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(conv_out, dconv, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -642,15 +655,16 @@ extern "C" int pdq_dispersion_trend_gamma_glm(pdq_ctx* c, const double* cov, con
     if (int e = ensure(c, kBufC, n * 8, &dx)) return e;
     if (int e = ensure(c, kBufD, n * 8, &dt)) return e;
     if (int e = ensure(c, kBufKeep, n, &keep)) return e;
-    if (int e = ensure(c, kBufMisc, 64, &dout)) return e;
+    if (int e = ensure(c, kBufMisc, 256, &dout)) return e;
     CU(c, cudaMemcpyAsync(dx, cov, n * 8, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(dt, targets, n * 8, cudaMemcpyHostToDevice, c->stream));
     LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount};
     const double inf = 1.0 / 0.0;
-    if (int e = done(c, launch_trend_fit(lc, (const double*)dx, (const double*)dt, (unsigned char*)keep, n, 0, -inf, inf, 0, (double*)dout),
+    if (int e = done(c, launch_trend_fit(lc, (const double*)dx, (const double*)dt, (unsigned char*)keep, n, 0, -inf, inf, 0, 0.0, 0.0, 0, nullptr,
+                                         (double*)dout),
                      "dispersion_trend_gamma_glm"))
         return e;
-    double out[8];
+    double out[16];
     CU(c, cudaMemcpyAsync(out, dout, sizeof out, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     coeffs_out[0] = out[0];

@@ -39,7 +39,7 @@ int launch_irls(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64
                 int* n_fallback);
 int launch_alpha_mle(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64_t ld, int G, const double* mu,
                      int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp, double prior_var,
-                     int cr_reg, int prior_reg, double* alpha, double* conv, int* status);
+                     const double* prior_var_dev, int cr_reg, int prior_reg, double* alpha, double* conv, int* status);
 int launch_wald(const LaunchCfg&, const DesignDev&, const double* disp, const double* lfc, const double* mu,
                 int64_t ld_mu, int G, const double* ridge, const double* contrast, double lfc_null, int alt,
                 double* pv, double* stat, double* se);
@@ -51,8 +51,11 @@ int launch_mom_from_counts(const LaunchCfg&, const DesignDev&, const int64_t* co
 int launch_mu_from_lfc(const LaunchCfg&, const DesignDev&, const double* lfc, int G, double* mu, int64_t ld_out);
 
 int launch_trend_fit(const LaunchCfg&, const double* x, const double* t, unsigned char* keep, size_t n, int x_is_mean,
-                     double lo, double hi, int outer, double* out8);
-int launch_trend_eval(const LaunchCfg&, const double* means, size_t n, const double* out8, double* fitted);
+                     double lo, double hi, int outer, double min_disp, double trigamma_c, int with_prior, double* res,
+                     double* out16);
+int launch_trend_eval(const LaunchCfg&, const double* means, size_t n, const double* out16, double* fitted);
+int launch_select_disp(const LaunchCfg&, const double* gw, const double* mp, const double* fitted, const double* out16,
+                       size_t n, double lo, double hi, double* disp, double* outlier);
 
 // largest dynamic shared memory a kernel of this library may ask for (B200: 227 KB per CTA)
 constexpr size_t kMaxDynSmem = 227 * 1024;

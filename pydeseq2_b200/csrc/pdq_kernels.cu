@@ -9,6 +9,7 @@
 //      path) and keep all per-gene state (X^T W X, beta, ...) in registers;
 //   3. cross-lane sums use xor-butterfly warp shuffles; p x p Cholesky solves run redundantly per lane.
 // Tensor cores are deliberately not used: p <= 8, the work is FP64 transcendental + HBM streaming.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -169,6 +170,7 @@ struct AlphaArgs {
     const double* alpha_hat;
     double *alpha, *conv;
     int* status;
+    const double* prior_var_dev;  // when set, overrides prm.prior_var (written by k_trend_prior on the same stream)
 };
 
 template <int P>
@@ -182,7 +184,9 @@ __global__ void __launch_bounds__(kBlock) k_alpha_mle(const __grid_constant__ Al
     // per-gene psi(r + k) tables live behind the design pack and its mbarrier
     double* psi = reinterpret_cast<double*>(smem + (size_t)(P + 2) * a.dv.Npad * 8 + 16) +
                   (size_t)((threadIdx.x >> 5) * grp.gpw + ((threadIdx.x & 31) & (grp.gpw - 1))) * kPsiK;
-    alpha_gene<P>(grp, d, a.prm, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha_hat[g], a.alpha + g, a.conv + g,
+    AlphaParams prm = a.prm;
+    if (a.prior_var_dev) prm.prior_var = *a.prior_var_dev;
+    alpha_gene<P>(grp, d, prm, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha_hat[g], a.alpha + g, a.conv + g,
                   a.status + g, valid, psi);
 }
 
@@ -316,62 +320,126 @@ __global__ void __launch_bounds__(kBlock) k_mu_from_lfc(const __grid_constant__ 
 }
 
 
-// ---- dispersion trend: the whole gamma-GLM fit (all iterations, all outer rounds) in one cooperative block ----
-struct BlockReducer {
-    double* sm;  // 33 doubles of shared memory
+// ---- dispersion trend + prior: the whole gamma-GLM fit (all iterations, all outer rounds) and the MAD-based prior
+// variance in ONE launch of one thread-block cluster.  Per iteration the blocks reduce their partial sums with warp
+// shuffles + shared memory, exchange the block totals through distributed shared memory (DSMEM stores into every
+// peer's slot table) and meet at one cluster barrier; all blocks then hold identical totals and take identical
+// decisions, so no further communication is needed.
+constexpr int kTrendK = 10;        // packed sums per reduction
+constexpr int kTrendMaxCluster = 16;
+
+struct ClusterReducer {
+    double* warp_part;  // [32][kTrendK]
+    double* slots;      // [2][kTrendMaxCluster][kTrendK], written by every block of the cluster (DSMEM)
+    unsigned rank, nblocks;
+    int parity;
     __host__ __device__ int tid() const {
 #if defined(__CUDA_ARCH__)
-        return threadIdx.x;
+        return rank * blockDim.x + threadIdx.x;
 #else
         return 0;
 #endif
     }
     __host__ __device__ int nthreads() const {
 #if defined(__CUDA_ARCH__)
+        return nblocks * blockDim.x;
+#else
+        return 1;
+#endif
+    }
+    __host__ __device__ int local_tid() const {
+#if defined(__CUDA_ARCH__)
+        return threadIdx.x;
+#else
+        return 0;
+#endif
+    }
+    __host__ __device__ int local_nthreads() const {
+#if defined(__CUDA_ARCH__)
         return blockDim.x;
 #else
         return 1;
 #endif
     }
-    __host__ __device__ void sync() {
+    __host__ __device__ void local_sync() {
 #if defined(__CUDA_ARCH__)
         __syncthreads();
 #endif
     }
-    __host__ __device__ double sum(double v) {
+    __host__ __device__ void sync() {
 #if defined(__CUDA_ARCH__)
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        cooperative_groups::this_cluster().sync();
+#endif
+    }
+    __host__ __device__ void sum_many(double* v, int k) {
+#if defined(__CUDA_ARCH__)
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        __syncthreads();  // previous result fully consumed
-        if (lane == 0) sm[warp] = v;
-        __syncthreads();
-        if (warp == 0) {
-            double w = (lane < (blockDim.x >> 5)) ? sm[lane] : 0.0;
+        for (int j = 0; j < k; ++j) {
+            double w = v[j];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
-            if (lane == 0) sm[32] = w;
+            if (lane == 0) warp_part[warp * kTrendK + j] = w;
         }
         __syncthreads();
-        return sm[32];
+        if ((int)threadIdx.x < k) {
+            double tot = 0.0;
+            const int nw = blockDim.x >> 5;
+            for (int w = 0; w < nw; ++w) tot += warp_part[w * kTrendK + threadIdx.x];
+            for (unsigned r = 0; r < nblocks; ++r) {
+                double* remote = cluster.map_shared_rank(slots, r);
+                remote[(parity * kTrendMaxCluster + rank) * kTrendK + threadIdx.x] = tot;
+            }
+        }
+        cluster.sync();  // release the DSMEM stores / acquire the peers'
+        for (int j = 0; j < k; ++j) {
+            double tot = 0.0;
+            for (unsigned r = 0; r < nblocks; ++r) tot += slots[(parity * kTrendMaxCluster + r) * kTrendK + j];
+            v[j] = tot;
+        }
+        parity ^= 1;
 #else
-        return v;
+        (void)v;
+        (void)k;
 #endif
     }
 };
 
-__global__ void __launch_bounds__(1024) k_trend_fit(const double* __restrict__ x, const double* __restrict__ t,
-                                                    unsigned char* keep, size_t n, int x_is_mean, double lo, double hi,
-                                                    int outer, TrendOut* out) {
-    __shared__ double sm[33];
-    BlockReducer red{sm};
-    trend_fit_outer(red, x, t, keep, n, x_is_mean != 0, lo, hi, outer != 0, out);
+__global__ void __launch_bounds__(1024) k_trend_prior(const double* __restrict__ x, const double* __restrict__ t,
+                                                      unsigned char* keep, size_t n, int x_is_mean, double lo, double hi,
+                                                      int outer, double min_disp, double trigamma_c, int with_prior,
+                                                      double* res, TrendOut* out) {
+    __shared__ double warp_part[32 * kTrendK];
+    __shared__ double slots[2 * kTrendMaxCluster * kTrendK];
+    __shared__ unsigned hist[256];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    ClusterReducer red{warp_part, slots, cluster.block_rank(), cluster.num_blocks(), 0};
+    TrendOut o = trend_fit_outer(red, x, t, keep, n, x_is_mean != 0, lo, hi, outer != 0);
+    if (with_prior && o.status == 0.0) trend_prior(red, x, t, n, lo, hi, min_disp, trigamma_c, res, hist, o);
+    if (red.tid() == 0) *out = o;
+    cluster.sync();  // no block may exit while peers can still address its shared memory
 }
 
 // fitted = c0 + c1 / mean (dds.py:1267-1275) from the device-resident coefficients
 __global__ void k_trend_eval(const double* __restrict__ means, size_t n, const TrendOut* __restrict__ c, double* fitted) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) fitted[i] = c->c0 + c->c1 / means[i];
+}
+
+// final dispersions (dds.py:918-932): clip the MAP estimate, but genes whose genewise estimate lies more than
+// 2 sd of the log residuals above the trend keep their (clipped) genewise value
+__global__ void k_select_disp(const double* __restrict__ gw, const double* __restrict__ mp, const double* __restrict__ fitted,
+                              const TrendOut* __restrict__ c, size_t n, double lo, double hi, double* disp, double* outlier) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double g = gw[i], m = mp[i];
+    g = (g < lo) ? lo : ((g > hi) ? hi : g);
+    m = (m < lo) ? lo : ((m > hi) ? hi : m);
+    const bool out = log(g) > log(fitted[i]) + 2.0 * sqrt(c->squared_logres);
+    disp[i] = out ? g : m;
+    if (outlier) outlier[i] = out ? 1.0 : 0.0;
 }
 
 // ---- launch helpers ---------------------------------------------------------------------------------
@@ -444,10 +512,11 @@ int launch_irls(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, i
 
 int launch_alpha_mle(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G,
                      const double* mu, int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp,
-                     double prior_var, int cr_reg, int prior_reg, double* alpha, double* conv, int* status) {
+                     double prior_var, const double* prior_var_dev, int cr_reg, int prior_reg, double* alpha, double* conv,
+                     int* status) {
     PDQ_DISPATCH_P(d.p, {
         AlphaArgs<P> a{{d.pack, d.N, d.Npad}, AlphaParams{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg},
-                       counts, ld, G, c.lgT, mu, ld_mu, alpha_hat, alpha, conv, status};
+                       counts, ld, G, c.lgT, mu, ld_mu, alpha_hat, alpha, conv, status, prior_var_dev};
         const size_t smem_alpha = d.smem_bytes + (size_t)kWarps * (32 >> c.lgT) * kPsiK * sizeof(double);
         if (int e = prep(k_alpha_mle<P>, smem_alpha)) return e;
         if (int e = prep(k_alpha_grid<P>, d.smem_bytes)) return e;
@@ -523,14 +592,40 @@ int launch_mu_from_lfc(const LaunchCfg& c, const DesignDev& d, const double* lfc
 }
 
 int launch_trend_fit(const LaunchCfg& c, const double* x, const double* t, unsigned char* keep, size_t n, int x_is_mean,
-                     double lo, double hi, int outer, double* out8) {
-    k_trend_fit<<<1, 1024, 0, c.stream>>>(x, t, keep, n, x_is_mean, lo, hi, outer, reinterpret_cast<TrendOut*>(out8));
+                     double lo, double hi, int outer, double min_disp, double trigamma_c, int with_prior, double* res,
+                     double* out16) {
+    // cluster size: enough blocks for ~4 elements per thread, at most 8 (portable) -- the vectors are G-length
+    unsigned nb = 1;
+    while (nb < 8 && (size_t)nb * 1024 * 4 < n) nb <<= 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nb, 1, 1);
+    cfg.blockDim = dim3(1024, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nb;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, k_trend_prior, x, t, keep, n, x_is_mean, lo, hi, outer, min_disp, trigamma_c, with_prior, res,
+                           reinterpret_cast<TrendOut*>(out16)) != cudaSuccess)
+        return PDQ_ERR_CUDA;
     if (int e = check_launch()) return e;
     return 1;
 }
 
-int launch_trend_eval(const LaunchCfg& c, const double* means, size_t n, const double* out8, double* fitted) {
-    k_trend_eval<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(means, n, reinterpret_cast<const TrendOut*>(out8), fitted);
+int launch_trend_eval(const LaunchCfg& c, const double* means, size_t n, const double* out16, double* fitted) {
+    k_trend_eval<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(means, n, reinterpret_cast<const TrendOut*>(out16), fitted);
+    if (int e = check_launch()) return e;
+    return 1;
+}
+
+int launch_select_disp(const LaunchCfg& c, const double* gw, const double* mp, const double* fitted, const double* out16,
+                       size_t n, double lo, double hi, double* disp, double* outlier) {
+    k_select_disp<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(gw, mp, fitted, reinterpret_cast<const TrendOut*>(out16), n,
+                                                                     lo, hi, disp, outlier);
     if (int e = check_launch()) return e;
     return 1;
 }

@@ -11,6 +11,8 @@
 // Compiled for the host emulator as well (one "thread").
 #pragma once
 
+#include <string.h>
+
 #include "pdq_math.cuh"
 
 namespace pdq {
@@ -23,6 +25,10 @@ struct TrendOut {
     double n_iter;   // inner iterations summed over rounds
     double loss;
     double last_converged;  // 1 when the most recent single fit converged (the reference's `res.success`)
+    // dispersion prior (dds.py:840-884), filled by trend_prior(): squared scaled MAD of the log residuals of the genes
+    // with genewise >= 100 * min_disp, the prior variance max(sq - trigamma((N-p)/2), 0.25), and the genes counted
+    double squared_logres, prior_var, n_above;
+    double pad[5];
 };
 
 // Reducer concept: tid(), nthreads(), sum(double) -> block-wide total visible to every thread, sync().
@@ -30,7 +36,12 @@ struct SerialReducer {
     PDQ_HD int tid() const { return 0; }
     PDQ_HD int nthreads() const { return 1; }
     PDQ_HD double sum(double v) { return v; }
+    PDQ_HD void sum_many(double*, int) {}  // in-place totals of k values, visible to every thread
     PDQ_HD void sync() {}
+    // thread-private in the emulator; block-shared scratch on the device
+    PDQ_HD int local_tid() const { return 0; }
+    PDQ_HD int local_nthreads() const { return 1; }
+    PDQ_HD void local_sync() {}
 };
 
 struct TrendSums {
@@ -65,11 +76,13 @@ PDQ_HD TrendSums trend_sums(R& red, const double* x, const double* t, const unsi
         f11 += fi * xv * xv;
         cnt += 1.0;
     }
+    double v[10] = {L, g0, g1, h00, h01, h11, f00, f01, f11, cnt};
+    red.sum_many(v, 10);  // one packed reduction round for all ten sums
     TrendSums s;
-    s.L = red.sum(L); s.g0 = red.sum(g0); s.g1 = red.sum(g1);
-    s.h00 = red.sum(h00); s.h01 = red.sum(h01); s.h11 = red.sum(h11);
-    s.f00 = red.sum(f00); s.f01 = red.sum(f01); s.f11 = red.sum(f11);
-    s.n = red.sum(cnt);
+    s.L = v[0]; s.g0 = v[1]; s.g1 = v[2];
+    s.h00 = v[3]; s.h01 = v[4]; s.h11 = v[5];
+    s.f00 = v[6]; s.f01 = v[7]; s.f11 = v[8];
+    s.n = v[9];
     return s;
 }
 
@@ -86,16 +99,18 @@ PDQ_HD double trend_loss(R& red, const double* x, const double* t, const unsigne
         const double m = fma(c1, xv, c0);
         L += tv / m + log(m);
     }
-    return red.sum(L);
+    red.sum_many(&L, 1);
+    return L;
 }
 
 // one GLM fit from (1, 1); returns true when converged
 template <class R>
 PDQ_HD bool trend_fit_once(R& red, const double* x, const double* t, const unsigned char* keep, size_t n, bool x_is_mean,
                            double lo, double hi, double& c0, double& c1, double& loss, int& iters) {
+    // Starts from the incoming (c0, c1): (1, 1) for the first round like the reference (default_inference.py:221);
+    // later rounds of the outer loop warm-start from the previous optimum -- the minimiser does not depend on the
+    // start, only the iteration count does.
     const double kLB = 1e-12;  // bounds=[(1e-12, inf)] (default_inference.py:224)
-    c0 = 1.0;
-    c1 = 1.0;
     bool ok = false;
     for (int it = 0; it < 200; ++it) {
         ++iters;
@@ -159,8 +174,8 @@ PDQ_HD bool trend_fit_once(R& red, const double* x, const double* t, const unsig
 
 // Full outer loop of dds.py:1199-1275.  `keep` (n bytes, scratch) holds the genes still in the fit.
 template <class R>
-PDQ_HD void trend_fit_outer(R& red, const double* x, const double* t, unsigned char* keep, size_t n, bool x_is_mean,
-                            double lo, double hi, bool outer, TrendOut* out) {
+PDQ_HD TrendOut trend_fit_outer(R& red, const double* x, const double* t, unsigned char* keep, size_t n, bool x_is_mean,
+                                double lo, double hi, bool outer) {
     for (size_t i = red.tid(); i < n; i += red.nthreads()) {
         const double xv = x_is_mean ? 1.0 / x[i] : x[i];
         keep[i] = (xv == xv) && (fabs(xv) <= 1.7976931348623157e308);  // drop inf / NaN covariates (dds.py:1225-1232)
@@ -195,17 +210,116 @@ PDQ_HD void trend_fit_outer(R& red, const double* x, const double* t, unsigned c
     }
     double used = 0.0;
     for (size_t i = red.tid(); i < n; i += red.nthreads()) used += keep[i] ? 1.0 : 0.0;
-    used = red.sum(used);
-    if (red.tid() == 0) {
-        out->c0 = c0;
-        out->c1 = c1;
-        out->status = failed ? 1.0 : 0.0;
-        out->n_outer = (double)rounds;
-        out->n_used = used;
-        out->n_iter = (double)iters;
-        out->loss = loss;
-        out->last_converged = last_conv ? 1.0 : 0.0;
+    red.sum_many(&used, 1);
+    TrendOut o;  // identical in every thread (all decisions were taken on block/cluster-wide sums)
+    o.c0 = c0;
+    o.c1 = c1;
+    o.status = failed ? 1.0 : 0.0;
+    o.n_outer = (double)rounds;
+    o.n_used = used;
+    o.n_iter = (double)iters;
+    o.loss = loss;
+    o.last_converged = last_conv ? 1.0 : 0.0;
+    o.squared_logres = o.prior_var = o.n_above = 0.0 / 0.0;
+    for (int i = 0; i < 5; ++i) o.pad[i] = 0.0;
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Dispersion prior (dds.py:840-884): residuals r = log(genewise) - log(fitted) over the genes with
+// genewise >= 100 * min_disp, squared scaled MAD (utils.py:1210-1227), prior_var = max(sq - trigamma((N-p)/2), 0.25).
+// The two medians are exact order statistics found by an MSB-first radix select (8-bit digits, 256-bin histogram
+// in block-shared memory) over an order-preserving integer image of the doubles; every block of the cluster runs
+// the selection redundantly on the full vector (no cross-block traffic, identical results everywhere).
+// ---------------------------------------------------------------------------------------------------------
+PDQ_HD uint64_t f64_key(double v) {
+    uint64_t u;
+#if defined(__CUDA_ARCH__)
+    u = (uint64_t)__double_as_longlong(v);
+#else
+    memcpy(&u, &v, 8);
+#endif
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+PDQ_HD double f64_from_key(uint64_t k) {
+    const uint64_t u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double v;
+    memcpy(&v, &u, 8);
+    return v;
+#endif
+}
+
+// k-th smallest (0-based) of { |res[i] - center| or res[i] } over the non-NaN entries
+template <class R>
+PDQ_HD double select_kth(R& red, const double* res, size_t n, bool absdev, double center, unsigned* hist, size_t k) {
+    uint64_t prefix = 0, mask = 0;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int b = red.local_tid(); b < 256; b += red.local_nthreads()) hist[b] = 0;
+        red.local_sync();
+        for (size_t i = red.local_tid(); i < n; i += red.local_nthreads()) {
+            const double r = res[i];
+            if (!(r == r)) continue;
+            const uint64_t key = f64_key(absdev ? fabs(r - center) : r);
+            if ((key & mask) == prefix) {
+#if defined(__CUDA_ARCH__)
+                atomicAdd(&hist[(key >> shift) & 0xff], 1u);
+#else
+                ++hist[(key >> shift) & 0xff];
+#endif
+            }
+        }
+        red.local_sync();
+        size_t cum = 0;
+        int d = 0;
+        for (; d < 256; ++d) {
+            const size_t c = hist[d];
+            if (cum + c > k) break;
+            cum += c;
+        }
+        k -= cum;
+        prefix |= (uint64_t)d << shift;
+        mask |= (uint64_t)0xff << shift;
+        red.local_sync();
     }
+    return f64_from_key(prefix);
+}
+
+template <class R>
+PDQ_HD double median_of(R& red, const double* res, size_t n, size_t cnt, bool absdev, double center, unsigned* hist) {
+    if (cnt == 0) return 0.0 / 0.0;  // np.median([]) = nan
+    const double hi = select_kth(red, res, n, absdev, center, hist, cnt / 2);
+    if (cnt & 1) return hi;
+    return 0.5 * (select_kth(red, res, n, absdev, center, hist, cnt / 2 - 1) + hi);
+}
+
+// `res` : n doubles of scratch; `hist`: 256 unsigned in block-shared memory; `trigamma_c` = polygamma(1, (N-p)/2)
+template <class R>
+PDQ_HD void trend_prior(R& red, const double* means, const double* t, size_t n, double lo, double hi, double min_disp,
+                        double trigamma_c, double* res, unsigned* hist, TrendOut& out) {
+    const double c0 = out.c0, c1 = out.c1;
+    double cnt = 0.0;
+    // every block fills the whole scratch vector (redundantly, same values) so that no cluster barrier is needed
+    for (size_t i = red.local_tid(); i < n; i += red.local_nthreads()) {
+        double tv = t[i];
+        tv = (tv < lo) ? lo : ((tv > hi) ? hi : tv);
+        const double fit = c0 + c1 / means[i];
+        const bool use = (tv >= 100.0 * min_disp) && (means[i] == means[i]);
+        res[i] = use ? (log(tv) - log(fit)) : (0.0 / 0.0);
+    }
+    red.local_sync();
+    for (size_t i = red.tid(); i < n; i += red.nthreads()) cnt += (res[i] == res[i]) ? 1.0 : 0.0;
+    red.sum_many(&cnt, 1);
+    const size_t m = (size_t)cnt;
+    const double med = median_of(red, res, n, m, false, 0.0, hist);
+    const double mad = median_of(red, res, n, m, true, med, hist) * 1.4826022185056018;  // / (sqrt(2) erfinv(1/2))
+    const double sq = mad * mad;
+    out.squared_logres = sq;
+    const double pv = sq - trigamma_c;
+    out.prior_var = (pv > 0.25 || pv != pv) ? pv : 0.25;  // np.maximum propagates NaN
+    out.n_above = cnt;
 }
 
 }  // namespace pdq

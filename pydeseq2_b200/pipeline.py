@@ -277,40 +277,40 @@ class ResidentFit:
             self.design = None
 
     # -- one pass ----------------------------------------------------------------------------------
-    def run(self, contrast=None, lfc_null=0.0, alt_hypothesis=None, fit_type="parametric", trend_inference=None,
-            fetch_all=True, profile=False):
-        """One pass.  ``profile=True`` brackets every kernel stage with CUDA events on the context's stream
-        (``stage_ms``); it serialises the host against each stage, so never time a step with it."""
+    def run(self, contrast=None, lfc_null=0.0, alt_hypothesis=None, fit_type="parametric", profile=False):
+        """One pass of the hot path.  Every stage is enqueued on the context's stream back to back -- the trend and
+        the dispersion prior run on the device too -- so the host synchronises exactly once, at the end.
+        ``profile=True`` brackets every stage with CUDA events (``stage_ms``); it serialises the host against each
+        stage, so never time a step with it."""
         L, ctx, h, d, G = self.lib, self.ctx, self.ctx.h, self.design, self.G
+        c_d = self._lib_mod.c_dptr
+        p, N = self.p, self.N
+        H = self._h
         stage = [None]
 
-        class _Check:  # ctx.check with optional per-stage event timing
-            def __call__(_, rc):
-                ctx.check(rc)
-                if profile and stage[0]:
-                    ctx.record(3)
-                    self.stage_ms[stage[0]] = ctx.elapsed_ms(2, 3)
-                    stage[0] = None
-
-        check = _Check()
+        def check(rc):  # ctx.check with optional per-stage event timing
+            ctx.check(rc)
+            if profile and stage[0]:
+                ctx.record(3)
+                self.stage_ms[stage[0]] = ctx.elapsed_ms(2, 3)
+                stage[0] = None
 
         def begin(name):
             if profile:
                 stage[0] = name
                 ctx.sync()
                 ctx.record(2)
-        c_d = self._lib_mod.c_dptr
-        p = self.p
-        H = self._h
+
         if contrast is None:
             contrast = np.zeros(p)
             contrast[-1] = 1.0
         contrast = np.ascontiguousarray(contrast, dtype=np.float64)
         ridge = np.ascontiguousarray(np.diag(np.repeat(1e-6, p)))
+        trigamma_c = float(polygamma(1, (N - p) / 2))
         # 1. method-of-moments start values + normalised means (dds.py:1140-1162, :708)
         begin("mom_dispersions")
         check(L.pdq_mom_dispersions_dev(h, d, c_d(self.d_counts), G, G, self.min_disp, self.max_disp, c_d(self.d_mom),
-                                            c_d(self.d_means)))
+                                        c_d(self.d_means)))
         # 2. initial mu_hat (dds.py:747-765)
         if self.lin_branch:
             begin("lin_reg_mu")
@@ -318,15 +318,14 @@ class ResidentFit:
         else:
             begin("irls_init")
             check(L.pdq_irls_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mom), self.min_mu, self.beta_tol, -30.0, 30.0,
-                                     250, c_d(self.d_beta0), c_d(self.d_mu_hat), c_d(self.d_hat), G, c_d(self.d_conv),
-                                     c_d(self.d_nfb)))
+                                 250, c_d(self.d_beta0), c_d(self.d_mu_hat), c_d(self.d_hat), G, c_d(self.d_conv),
+                                 c_d(self.d_nfb)))
         # 3. genewise dispersions (dds.py:778-797)
         begin("alpha_mle_genewise")
         check(L.pdq_alpha_mle_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(self.d_mom), self.min_disp,
-                                      self.max_disp, 1.0, 1, 0, c_d(self.d_gw), c_d(self.d_gw_conv)))
-        # 4. trend + prior: global over ALL genes of ALL shards (dds.py:799-884).  The gamma-GLM trend (all
-        #    iterations, all outer rounds) is one kernel launch on the device-resident vectors; with gene shards
-        #    the per-gene vectors are all-gathered over NCCL first, device to device.
+                                  self.max_disp, 1.0, None, 1, 0, c_d(self.d_gw), c_d(self.d_gw_conv)))
+        # 4. trend + prior: global over ALL genes of ALL shards (dds.py:799-884).  With gene shards the per-gene
+        #    vectors are all-gathered over NCCL first, device to device; the fit itself is one cluster launch.
         W = self.comm.world if self.comm is not None else 1
         rank = self.comm.rank if self.comm is not None else 0
         m = self.comm.max_size if self.comm is not None else G
@@ -340,73 +339,86 @@ class ResidentFit:
         else:
             d_gw_all, d_means_all = self.d_gw, self.d_means
         d_fit_all = self._dev("fitted_all", n_all * 8)
-        d_t8 = self._dev("trend8", 64)
-        begin("trend_fit")
-        check(L.pdq_trend_fit_dev(h, c_d(d_means_all), c_d(d_gw_all), n_all, self.min_disp, self.max_disp, c_d(d_t8), c_d(d_fit_all)))
-        self.d_fitted = d_fit_all + rank * m * 8  # this shard's slice of the fitted curve
-        if "all" not in self._h or self._h["all"].shape[1] != n_all:
-            self._h["all"] = ctx.pinned_empty((3, n_all))
-            self._h["t8"] = ctx.pinned_empty((8,))
-        A = self._h["all"]
-        ctx.d2h(A[0], d_gw_all)
-        ctx.d2h(A[1], d_means_all)
-        ctx.d2h(A[2], d_fit_all)
-        ctx.d2h(self._h["t8"], d_t8)
-        ctx.d2h(H["gw_conv"], self.d_gw_conv)
-        ctx.sync()
-        t0 = time.perf_counter()
-        valid = ~np.isnan(A[1])  # padding of ragged shards
-        gw_all = np.clip(A[0][valid], self.min_disp, self.max_disp)
-        means_all = A[1][valid]
-        lo = rank * m
-        gw = np.clip(A[0][lo:lo + G], self.min_disp, self.max_disp)
-        means = A[1][lo:lo + G].copy()
-        t8 = self._h["t8"]
-        if fit_type == "parametric" and t8[2] == 0.0:
-            trend = TrendFit("parametric", np.array([t8[0], t8[1]]), A[2][valid], int(t8[3]))
-            fitted = A[2][lo:lo + G].copy()
-        else:  # dds.py:1243-1252: mean-trend fallback
+        d_t16 = self._dev("trend16", 128)
+        d_fitted = d_fit_all + rank * m * 8  # this shard's slice of the fitted curve
+        if fit_type == "parametric":
+            begin("trend_prior")
+            check(L.pdq_trend_fit_dev(h, c_d(d_means_all), c_d(d_gw_all), n_all, self.min_disp, self.max_disp, trigamma_c,
+                                      c_d(d_t16), c_d(d_fit_all)))
+            self._tail(d_fitted, d_t16, d_t16 + 9 * 8, 0.0, contrast, ridge, lfc_null, alt_hypothesis, begin, check)
+        if "t16" not in H:
+            H["t16"] = ctx.pinned_empty((16,))
+        if fit_type == "parametric":
+            ctx.d2h(H["t16"], d_t16)
+        for k in ("gw", "gw_conv", "means"):
+            ctx.d2h(H[k], getattr(self, "d_" + k))
+        ctx.sync()  # the only host synchronisation of the pass
+        t16 = H["t16"]
+        if fit_type == "parametric" and t16[2] == 0.0:
+            trend = TrendFit("parametric", np.array([t16[0], t16[1]]), None, int(t16[3]))
+            sq, prior_var = float(t16[8]), float(t16[9])
+        else:
+            # dds.py:1243-1252 / fit_type="mean": trimmed-mean trend on the host (global, G-length), then the tail again
             if fit_type == "parametric":
                 warnings.warn("The dispersion trend curve fitting did not converge. Switching to a mean-based dispersion trend.",
                               UserWarning, stacklevel=2)
-            trend = fit_trend(None, means_all, gw_all, self.min_disp, "mean")
+            A = ctx.pinned_empty((2, n_all))
+            ctx.d2h(A[0], d_gw_all)
+            ctx.d2h(A[1], d_means_all)
+            ctx.sync()
+            valid = ~np.isnan(A[1])
+            gw_all = np.clip(A[0][valid], self.min_disp, self.max_disp)
+            trend = fit_trend(None, A[1][valid], gw_all, self.min_disp, "mean")
+            sq, prior_var = fit_prior_var(gw_all, trend.fitted, N, p, self.min_disp)
+            rec = ctx.pinned_empty((16,))
+            rec[:] = 0.0
+            rec[0], rec[2], rec[8], rec[9] = trend.coeffs[0], 0.0, sq, prior_var
+            fit_all = ctx.pinned_empty((n_all,))
+            fit_all[:] = trend.coeffs[0]
+            ctx.h2d(d_t16, rec)
+            ctx.h2d(d_fit_all, fit_all)
+            self._tail(d_fitted, d_t16, None, prior_var, contrast, ridge, lfc_null, alt_hypothesis, begin, check)
+            ctx.sync()
+        gw = np.clip(H["gw"], self.min_disp, self.max_disp)
+        means = H["means"]
+        if trend.kind == "parametric":
+            fitted = trend.coeffs[0] + trend.coeffs[1] / means
+            trend = TrendFit("parametric", trend.coeffs, fitted, trend.n_iter)
+        else:
             fitted = np.full(G, trend.coeffs[0])
-            H["fitted"][:] = fitted
-            self.d_fitted = self._dev("fitted", G * 8)
-            ctx.h2d(self.d_fitted, H["fitted"])
-        sq, prior_var = fit_prior_var(gw_all, trend.fitted, self.N, p, self.min_disp)
-        self.stage_ms["prior_host"] = (time.perf_counter() - t0) * 1e3
-        # 5. MAP dispersions (dds.py:886-935)
+        return {"mom": H["mom"], "genewise": gw, "genewise_converged": H["gw_conv"], "trend": trend, "prior_var": prior_var,
+                "squared_logres": sq, "map": np.clip(H["map"], self.min_disp, self.max_disp), "map_converged": H["map_conv"],
+                "dispersions": H["disp"], "lfc": H["beta"], "lfc_converged": H["conv"], "pvalue": H["pv"], "stat": H["stat"],
+                "se": H["se"], "normed_means": means, "fitted": fitted, "outlier": H["outlier"]}
+
+    def _tail(self, d_fitted, d_t16, d_prior_var, prior_var, contrast, ridge, lfc_null, alt_hypothesis, begin, check):
+        """MAP dispersions -> final dispersions -> LFC fit -> Wald, all enqueued without host synchronisation."""
+        L, ctx, h, d, G = self.lib, self.ctx, self.ctx.h, self.design, self.G
+        c_d = self._lib_mod.c_dptr
+        H = self._h
+        if "outlier" not in H:
+            H["outlier"] = ctx.pinned_empty((G,))
+            self.d_outlier = self._dev("outlier", G * 8)
+        # 5. MAP dispersions (dds.py:886-935); the prior variance is read from device memory (written by the trend kernel)
         begin("alpha_mle_map")
-        check(L.pdq_alpha_mle_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(self.d_fitted), self.min_disp,
-                                      self.max_disp, prior_var, 1, 1, c_d(self.d_map), c_d(self.d_map_conv)))
-        ctx.d2h(H["map"], self.d_map)
-        ctx.d2h(H["map_conv"], self.d_map_conv)
-        ctx.sync()
-        mp = np.clip(H["map"], self.min_disp, self.max_disp)
-        disp = mp.copy()
-        outlier = np.log(gw) > np.log(fitted) + 2 * np.sqrt(sq)
-        disp[outlier] = gw[outlier]
-        H["disp"][:] = disp
-        ctx.h2d(self.d_disp, H["disp"])
+        check(L.pdq_alpha_mle_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(d_fitted), self.min_disp,
+                                  self.max_disp, prior_var if d_prior_var is None else 1.0,
+                                  c_d(d_prior_var) if d_prior_var is not None else None, 1, 1, c_d(self.d_map), c_d(self.d_map_conv)))
+        # final dispersions: clip(MAP), outlier genes keep the genewise value (dds.py:918-932)
+        begin("select_dispersions")
+        check(L.pdq_select_dispersions_dev(h, c_d(self.d_gw), c_d(self.d_map), c_d(d_fitted), c_d(d_t16), G, self.min_disp,
+                                           self.max_disp, c_d(self.d_disp), c_d(self.d_outlier)))
         # 6. LFC fit (dds.py:937-984): beta, mu (unclamped), hat diagonal stay on the device
         begin("irls_lfc")
         check(L.pdq_irls_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_disp), self.min_mu, self.beta_tol, -30.0, 30.0, 250,
-                                 c_d(self.d_beta), c_d(self.d_mu), c_d(self.d_hat), G, c_d(self.d_conv), c_d(self.d_nfb)))
+                             c_d(self.d_beta), c_d(self.d_mu), c_d(self.d_hat), G, c_d(self.d_conv), c_d(self.d_nfb)))
         # 7. Wald (ds.py:303-360): mu = sf * exp(X beta) is exactly the mu the LFC fit just wrote (unclamped)
         begin("wald_test")
         check(L.pdq_wald_test_dev(h, d, c_d(self.d_disp), c_d(self.d_beta), c_d(self.d_mu), G, G,
-                                      self._lib_mod.as_f64p(ridge), self._lib_mod.as_f64p(contrast), LN2 * lfc_null,
-                                      self._lib_mod.ALT_CODES[alt_hypothesis], c_d(self.d_pv), c_d(self.d_stat), c_d(self.d_se)))
-        for k in ("pv", "stat", "se", "conv", "beta"):
+                                  self._lib_mod.as_f64p(ridge), self._lib_mod.as_f64p(contrast), LN2 * lfc_null,
+                                  self._lib_mod.ALT_CODES[alt_hypothesis], c_d(self.d_pv), c_d(self.d_stat), c_d(self.d_se)))
+        for k in ("map", "map_conv", "disp", "pv", "stat", "se", "conv", "beta", "mom", "outlier"):
             ctx.d2h(H[k], getattr(self, "d_" + k))
-        if fetch_all:
-            ctx.d2h(H["mom"], self.d_mom)
-        ctx.sync()
-        return {"mom": H["mom"], "genewise": gw, "genewise_converged": H["gw_conv"], "trend": trend, "prior_var": prior_var,
-                "squared_logres": sq, "map": mp, "map_converged": H["map_conv"], "dispersions": disp, "lfc": H["beta"],
-                "lfc_converged": H["conv"], "pvalue": H["pv"], "stat": H["stat"], "se": H["se"], "normed_means": means}
-
 
 class _HostTrend:
     """The trend GLM of B200Inference without needing a device context."""

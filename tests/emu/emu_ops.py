@@ -75,14 +75,14 @@ class EmuOps:
         return a, m
 
     def trend_glm(self, cov, targets):
-        out = np.zeros(8)
+        out = np.zeros(16)
         rc = self.lib.emu_trend_fit(_p(cov, f64p), _p(targets, f64p), C.c_size_t(len(cov)), 0, C.c_double(-np.inf),
-                                    C.c_double(np.inf), 0, _p(out, f64p))
+                                    C.c_double(np.inf), 0, C.c_double(0.0), C.c_double(0.0), 0, _p(out, f64p))
         assert rc == 0
         return out[:2].copy(), out[0] + out[1] * cov, bool(out[7])
 
-    def trend_outer(self, means, gw, lo, hi):
-        out = np.zeros(8)
+    def trend_outer(self, means, gw, lo, hi, min_disp=1e-8, trigamma_c=0.0, with_prior=True):
+        out = np.zeros(16)
         assert self.lib.emu_trend_fit(_p(means, f64p), _p(gw, f64p), C.c_size_t(len(gw)), 1, C.c_double(lo), C.c_double(hi), 1,
-                                      _p(out, f64p)) == 0
+                                      C.c_double(min_disp), C.c_double(trigamma_c), int(with_prior), _p(out, f64p)) == 0
         return out

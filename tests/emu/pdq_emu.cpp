@@ -177,14 +177,18 @@ int emu_mom_from_counts(const int64_t* counts, int64_t ld, int N, int G, const d
     return 0;
 }
 
-int emu_trend_fit(const double* x, const double* t, size_t n, int x_is_mean, double lo, double hi, int outer, double* out8) {
+int emu_trend_fit(const double* x, const double* t, size_t n, int x_is_mean, double lo, double hi, int outer, double min_disp,
+                  double trigamma_c, int with_prior, double* out16) {
     std::vector<unsigned char> keep(n);
+    std::vector<double> res(n);
+    unsigned hist[256];
     SerialReducer red;
-    trend_fit_outer(red, x, t, keep.data(), n, x_is_mean != 0, lo, hi, outer != 0, reinterpret_cast<TrendOut*>(out8));
+    TrendOut o = trend_fit_outer(red, x, t, keep.data(), n, x_is_mean != 0, lo, hi, outer != 0);
+    if (with_prior && o.status == 0.0) trend_prior(red, x, t, n, lo, hi, min_disp, trigamma_c, res.data(), hist, o);
+    memcpy(out16, &o, sizeof o);
     return 0;
 }
 
-long emu_eval_count(int reset) { long v = g_emu_alpha_evals; if (reset) g_emu_alpha_evals = 0; return v; }
 double emu_fast_log(double x) { return fast_log(x); }
 double emu_fast_exp(double x) { return fast_exp(x); }
 double emu_lgamma(double x) { return lgamma_pos(x); }

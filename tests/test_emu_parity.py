@@ -58,3 +58,38 @@ def test_fast_log_exp_accuracy():
     np.testing.assert_allclose(got, np.exp(es), rtol=5e-16)
     assert np.isnan(ops.lib.emu_fast_exp(float("nan"))) and np.isnan(ops.lib.emu_fast_log(float("nan")))
     assert ops.lib.emu_fast_log(0.0) == -np.inf and np.isnan(ops.lib.emu_fast_log(-1.0))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_device_trend_and_prior_match_host_glue(seed):
+    """The on-device trend (outer loop included) + MAD prior (radix-select medians) against the host glue that
+    reproduces dds.py:1199-1275 / 840-884 with the reference's scipy fit."""
+    from scipy.special import polygamma
+
+    from oracle import nbglm
+    from pydeseq2_b200.pipeline import fit_prior_var, fit_trend
+
+    class Ref:
+        dispersion_trend_gamma_glm = staticmethod(nbglm.dispersion_trend_gamma_glm)
+
+    ops = EmuOps()
+    rng = np.random.default_rng(seed)
+    G, N, p = [2001, 6000][seed % 2], 60, 3
+    means = np.exp(rng.normal(4, 2, G) * np.log(2))
+    gw = (4 / means + 0.1) * np.exp(rng.normal(0, [0.3, 0.8][seed // 2], G))
+    gw[rng.integers(0, G, 40)] = 1e-8          # collapsed estimates are excluded from the prior (dds.py:868-875)
+    gw[rng.integers(0, G, 10)] *= 100.0        # far above the curve: dropped by the outer loop
+    out = ops.trend_outer(means, gw, 1e-8, float(N), 1e-8, float(polygamma(1, (N - p) / 2)))
+    gwc = np.clip(gw, 1e-8, N)
+    tr = fit_trend(Ref(), means, gwc, 1e-8)
+    sq, pv = fit_prior_var(gwc, tr.fitted, N, p, 1e-8)
+    assert out[2] == 0.0 and int(out[3]) == tr.n_iter
+    np.testing.assert_allclose(out[:2], tr.coeffs, rtol=1e-4)   # L-BFGS-B's own slack
+    np.testing.assert_allclose(out[8], sq, rtol=2e-4)
+    np.testing.assert_allclose(out[9], pv, rtol=2e-4)
+    assert int(out[10]) == int((gwc >= 1e-6).sum())
+    # with the SAME coefficients the prior is exact: feed the device coefficients to the host formula
+    fitted = out[0] + out[1] / means
+    sq2, pv2 = fit_prior_var(gwc, fitted, N, p, 1e-8)
+    np.testing.assert_allclose(out[8], sq2, rtol=1e-12)
+    np.testing.assert_allclose(out[9], pv2, rtol=1e-12)
