@@ -221,12 +221,13 @@ def main():
         ctx.sync()
 
     # ---------------------------------------------------------------- value: device-resident
+    clk = ClockSampler(local).__enter__()  # sampled from the warm-up until the end of the e2e loop (steps last only ms)
     for _ in range(max(args.warmup, 3)):
         rf.run()
     barrier()
     launches0 = ctx.launches()
     step_ms = []
-    with ClockSampler(local) as clk:
+    if True:
         for _ in range(args.steps):
             flush_l2()
             barrier()
@@ -283,6 +284,8 @@ def main():
         ctx.sync()
         e2e_t.append(time.perf_counter() - t0)
     e2e_s = float(np.mean(e2e_t))
+    time.sleep(0.25)  # let nvidia-smi emit at least one more sample
+    clk.__exit__()
     if dist is not None:
         import torch
 

@@ -371,6 +371,43 @@ struct ClusterReducer {
         cooperative_groups::this_cluster().sync();
 #endif
     }
+    // warp 0 scans the 256-bin histogram (8 bins per lane + shuffle scan) and publishes digit / count-before in hist[256..257]
+    __host__ __device__ void find_bin(unsigned* hist, size_t k, int& d, size_t& cum) {
+#if defined(__CUDA_ARCH__)
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            unsigned c[8], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                c[j] = hist[lane * 8 + j];
+                tot += c[j];
+            }
+            unsigned inc = tot;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= off) inc += t;
+            }
+            const unsigned before = inc - tot;
+            const unsigned kk = (unsigned)k;
+            if (before <= kk && kk < inc) {  // exactly one lane owns the crossing
+                unsigned run = before;
+                int j = 0;
+                for (; j < 8; ++j) {
+                    if (run + c[j] > kk) break;
+                    run += c[j];
+                }
+                hist[256] = (unsigned)(lane * 8 + j);
+                hist[257] = run;
+            }
+        }
+        __syncthreads();
+        d = (int)hist[256];
+        cum = hist[257];
+#else
+        (void)hist; (void)k; (void)d; (void)cum;
+#endif
+    }
     __host__ __device__ void sum_many(double* v, int k) {
 #if defined(__CUDA_ARCH__)
         namespace cg = cooperative_groups;
@@ -412,7 +449,7 @@ __global__ void __launch_bounds__(1024) k_trend_prior(const double* __restrict__
                                                       double* res, TrendOut* out) {
     __shared__ double warp_part[32 * kTrendK];
     __shared__ double slots[2 * kTrendMaxCluster * kTrendK];
-    __shared__ unsigned hist[256];
+    __shared__ unsigned hist[258];
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     ClusterReducer red{warp_part, slots, cluster.block_rank(), cluster.num_blocks(), 0};

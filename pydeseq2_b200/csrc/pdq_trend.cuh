@@ -42,6 +42,14 @@ struct SerialReducer {
     PDQ_HD int local_tid() const { return 0; }
     PDQ_HD int local_nthreads() const { return 1; }
     PDQ_HD void local_sync() {}
+    PDQ_HD void find_bin(const unsigned* hist, size_t k, int& d, size_t& cum) {
+        cum = 0;
+        for (d = 0; d < 256; ++d) {
+            const size_t c = hist[d];
+            if (cum + c > k) break;
+            cum += c;
+        }
+    }
 };
 
 struct TrendSums {
@@ -274,11 +282,7 @@ PDQ_HD double select_kth(R& red, const double* res, size_t n, bool absdev, doubl
         red.local_sync();
         size_t cum = 0;
         int d = 0;
-        for (; d < 256; ++d) {
-            const size_t c = hist[d];
-            if (cum + c > k) break;
-            cum += c;
-        }
+        red.find_bin(hist, k, d, cum);  // first bin whose cumulative count exceeds k, and the count before it
         k -= cum;
         prefix |= (uint64_t)d << shift;
         mask |= (uint64_t)0xff << shift;
@@ -295,7 +299,7 @@ PDQ_HD double median_of(R& red, const double* res, size_t n, size_t cnt, bool ab
     return 0.5 * (select_kth(red, res, n, absdev, center, hist, cnt / 2 - 1) + hi);
 }
 
-// `res` : n doubles of scratch; `hist`: 256 unsigned in block-shared memory; `trigamma_c` = polygamma(1, (N-p)/2)
+// `res` : n doubles of scratch; `hist`: 256 (+2 result slots) unsigned in block-shared memory; `trigamma_c` = polygamma(1, (N-p)/2)
 template <class R>
 PDQ_HD void trend_prior(R& red, const double* means, const double* t, size_t n, double lo, double hi, double min_disp,
                         double trigamma_c, double* res, unsigned* hist, TrendOut& out) {

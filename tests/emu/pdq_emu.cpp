@@ -181,7 +181,7 @@ int emu_trend_fit(const double* x, const double* t, size_t n, int x_is_mean, dou
                   double trigamma_c, int with_prior, double* out16) {
     std::vector<unsigned char> keep(n);
     std::vector<double> res(n);
-    unsigned hist[256];
+    unsigned hist[258];
     SerialReducer red;
     TrendOut o = trend_fit_outer(red, x, t, keep.data(), n, x_is_mean != 0, lo, hi, outer != 0);
     if (with_prior && o.status == 0.0) trend_prior(red, x, t, n, lo, hi, min_disp, trigamma_c, res.data(), hist, o);
