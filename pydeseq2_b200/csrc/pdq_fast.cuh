@@ -95,6 +95,59 @@ PDQ_HD double fast_log(double x) {
     return fma(ed, kLn2Hi, f2 + fma(f2 * s, g, ed * kLn2Lo));
 }
 
+// Branch-free cores.  `fast_log_nb` needs a positive normal finite argument, `fast_exp_nb` needs |x| < 700; callers
+// track violations in a flag and redo the (rare) affected gene through the guarded versions, so that the hot loops stay
+// straight-line code in which the chains of two samples interleave.
+PDQ_HD double fast_exp(double x);
+
+PDQ_HD double fast_log_nb(double x) {
+#if defined(__CUDA_ARCH__)
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    const bool big = hi >= 0x3ff6a09f;
+    hi = big ? hi - 0x00100000 : hi;
+    e = big ? e + 1 : e;
+    const double m = __hiloint2double(hi, lo);
+    const double ed = (double)e;
+    const double f = fast_div(m - 1.0, m + 1.0);
+    const double s = f * f;
+    double g = kLogG[6];
+    g = fma(g, s, kLogG[5]);
+    g = fma(g, s, kLogG[4]);
+    g = fma(g, s, kLogG[3]);
+    g = fma(g, s, kLogG[2]);
+    g = fma(g, s, kLogG[1]);
+    g = fma(g, s, kLogG[0]);
+    const double f2 = f + f;
+    return fma(ed, kLn2Hi, f2 + fma(f2 * s, g, ed * kLn2Lo));
+#else
+    return fast_log(x);
+#endif
+}
+
+PDQ_HD double fast_exp_nb(double x) {
+#if defined(__CUDA_ARCH__)
+    const double kd = rint(x * kLog2e);
+    const double r = fma(-kd, kLn2Lo, fma(-kd, kLn2Hi, x));
+    double q = kExpQ[9];
+    q = fma(q, r, kExpQ[8]);
+    q = fma(q, r, kExpQ[7]);
+    q = fma(q, r, kExpQ[6]);
+    q = fma(q, r, kExpQ[5]);
+    q = fma(q, r, kExpQ[4]);
+    q = fma(q, r, kExpQ[3]);
+    q = fma(q, r, kExpQ[2]);
+    q = fma(q, r, kExpQ[1]);
+    q = fma(q, r, kExpQ[0]);
+    const double p = fma(r * r, q, r) + 1.0;
+    return p * __hiloint2double(((int)kd + 1023) << 20, 0);
+#else
+    return fast_exp(x);
+#endif
+}
+
 PDQ_HD double fast_exp(double x) {
     if (!(fabs(x) < 700.0)) return exp(x);  // overflow/underflow edge, inf, NaN: libm/libdevice semantics
     const double kd = rint(x * kLog2e);

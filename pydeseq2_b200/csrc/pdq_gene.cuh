@@ -138,42 +138,66 @@ struct IrlsParams {
 // one fused sweep over the gene's samples at coefficient vector `beta`:
 //   A = X^T W X, b = X^T W z  (utils.py:368-371, W and z from the CLAMPED mu)
 //   S = sum (y + r) log(r + mu) - y log(mu)  -- the mu-dependent part of nb_nll (utils.py:220-234)
-template <int P>
-PDQ_HD void irls_sweep(const Group& grp, const DesignS& d, const int64_t* y, int64_t ld, const double (&beta)[P],
-                       double alpha, double r, double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P],
-                       double& S) {
+// contribution of one sample to the sweep.  NB = branch-free math cores; arguments outside their domain raise `odd`
+template <int P, bool NB>
+PDQ_HD void irls_sample(const double* xp, int Npad, double yv, const double (&beta)[P], double alpha, double r,
+                        double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P], double& S, bool& odd) {
+    double x[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) x[j] = xp[j * Npad];
+    const double sfn = xp[P * Npad], lsfn = xp[(P + 1) * Npad];      // sf and log sf follow X in the pack
+    double eta = 0.0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
+    if (NB) odd = odd || !(fabs(eta) < 300.0);
+    const double mu_raw = sfn * (NB ? fast_exp_nb(eta) : fast_exp(eta));
+    const bool cl = mu_raw < min_mu;
+    const double mu = cl ? min_mu : mu_raw;                            // np.maximum(sf*exp(X b), min_mu)
+    const double lmu_sf = cl ? (log_min_mu - lsfn) : eta;              // log(mu / sf)
+    const double lmu = cl ? log_min_mu : (eta + lsfn);                 // log(mu)
+    const double den = fma(mu, alpha, 1.0);
+    const double q = NB ? fast_rcp(mu * den) : 1.0 / (mu * den);
+    const double W = mu * mu * q;                                      // mu / (1 + mu alpha)
+    const double z = fma(yv - mu, den * q, lmu_sf);                    // log(mu/sf) + (y - mu)/mu
+    sym_rank1<P>(A, W, x);
+    const double Wz = W * z;
+#pragma unroll
+    for (int j = 0; j < P; ++j) b[j] = fma(Wz, x[j], b[j]);
+    S += fma(yv + r, NB ? fast_log_nb(r + mu) : fast_log(r + mu), -yv * lmu);
+}
+
+template <int P, bool NB>
+PDQ_HD bool irls_sweep_t(const Group& grp, const DesignS& d, const int64_t* y, int64_t ld, const double (&beta)[P],
+                         double alpha, double r, double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P], double& S) {
     sym_zero<P>(A);
 #pragma unroll
     for (int j = 0; j < P; ++j) b[j] = 0.0;
     S = 0.0;
-    const int64_t ystep = (int64_t)grp.T * ld;
+    bool odd = false;
+    const int T = grp.T;
+    const int64_t ystep = (int64_t)T * ld;
     const int64_t* yp = y + (int64_t)grp.si * ld;
     const double* xp = d.X + grp.si;
-#pragma unroll 2
-    for (int n = grp.si; n < d.N; n += grp.T, yp += ystep, xp += grp.T) {
-        double x[P];
-#pragma unroll
-        for (int j = 0; j < P; ++j) x[j] = xp[j * d.Npad];
-        const double sfn = xp[P * d.Npad], lsfn = xp[(P + 1) * d.Npad];  // sf and log sf follow X in the pack
-        const double yv = (double)*yp;
-        double eta = 0.0;
-#pragma unroll
-        for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
-        const double mu_raw = sfn * fast_exp(eta);
-        const bool cl = mu_raw < min_mu;
-        const double mu = cl ? min_mu : mu_raw;                        // np.maximum(sf*exp(X b), min_mu)
-        const double lmu_sf = cl ? (log_min_mu - lsfn) : eta;          // log(mu / sf)
-        const double lmu = cl ? log_min_mu : (eta + lsfn);             // log(mu)
-        const double den = fma(mu, alpha, 1.0);
-        const double q = fast_rcp(mu * den);
-        const double W = mu * mu * q;                                  // mu / (1 + mu alpha)
-        const double z = fma(yv - mu, den * q, lmu_sf);                // log(mu/sf) + (y - mu)/mu
-        sym_rank1<P>(A, W, x);
-        const double Wz = W * z;
-#pragma unroll
-        for (int j = 0; j < P; ++j) b[j] = fma(Wz, x[j], b[j]);
-        S += fma(yv + r, fast_log(r + mu), -yv * lmu);
+    int n = grp.si;
+    // two samples per trip, straight-line: their exp / log / reciprocal chains interleave on the FP64 pipe
+    for (; n + T < d.N; n += 2 * T, yp += 2 * ystep, xp += 2 * T) {
+        const double y0 = (double)yp[0], y1 = (double)yp[ystep];
+        irls_sample<P, NB>(xp, d.Npad, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd);
+        irls_sample<P, NB>(xp + T, d.Npad, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd);
     }
+    if (n < d.N) irls_sample<P, NB>(xp, d.Npad, (double)yp[0], beta, alpha, r, min_mu, log_min_mu, A, b, S, odd);
+    return odd;
+}
+
+template <int P>
+PDQ_HD void irls_sweep(const Group& grp, const DesignS& d, const int64_t* y, int64_t ld, const double (&beta)[P],
+                       double alpha, double r, double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P],
+                       double& S) {
+    // the branch-free cores need r = 1/alpha positive finite and a positive clamp
+    bool odd = !(alpha > 0.0 && r > 0.0 && r < 1e300 && min_mu > 0.0);
+    if (!odd) odd = irls_sweep_t<P, true>(grp, d, y, ld, beta, alpha, r, min_mu, log_min_mu, A, b, S);
+    if (grp.any(odd))  // rare (diverging beta, NaN dispersion): guarded libdevice path, IEEE semantics of the reference
+        irls_sweep_t<P, false>(grp, d, y, ld, beta, alpha, r, min_mu, log_min_mu, A, b, S);
     group_sum_sym<P>(grp, A);
     group_sum_vec<P>(grp, b);
     S = grp.sum(S);
@@ -550,6 +574,69 @@ PDQ_HD void build_psi_table(const Group& grp, double* tab, double r) {
     grp.sync();
 }
 
+// contribution of two samples (or one, when !two) to the derivative sums; NB as in irls_sample
+template <int P, bool NB>
+PDQ_HD void alpha_pair(const Group& grp, const double* xp0, const double* xp1, int Npad, long long yi0, long long yi1,
+                       double m0, double m1, bool one, bool two, double r, bool cr_reg, const double* psi_tab, double& Sg,
+                       Sym<P>& A, Sym<P>& B, bool& odd) {
+    // `one` / `two`: which of the two samples exist for this lane (masked-out slots carry y = 0, mu = 1)
+    const double yv0 = (double)yi0, yv1 = (double)yi1;
+    const bool big0 = one && ((yi0 >= kPsiK) || (yi0 < 0)), big1 = two && ((yi1 >= kPsiK) || (yi1 < 0));
+    if (NB) odd = odd || !(m0 >= 0.0 && m0 < 1e300) || !(m1 >= 0.0 && m1 < 1e300);
+    const double rm0 = r + m0, rm1 = r + m1;
+    const double inv0 = NB ? fast_rcp(rm0) : 1.0 / rm0, inv1 = NB ? fast_rcp(rm1) : 1.0 / rm1;
+    const double lg0 = NB ? fast_log_nb(rm0) : fast_log(rm0), lg1 = NB ? fast_log_nb(rm1) : fast_log(rm1);
+    double dg0 = psi_tab[(int)(yi0 & (kPsiK - 1))], dg1 = psi_tab[(int)(yi1 & (kPsiK - 1))];
+    if (grp.any(big0 || big1)) {  // warp-uniform: the unshifted series only when some lane holds a count >= kPsiK
+        const double z0 = big0 ? yv0 + r : r + (double)kPsiK, z1 = big1 ? yv1 + r : r + (double)kPsiK;
+        const double a0 = digamma_asym(z0, NB ? fast_log_nb(z0) : fast_log(z0));
+        const double a1 = digamma_asym(z1, NB ? fast_log_nb(z1) : fast_log(z1));
+        dg0 = big0 ? a0 : dg0;
+        dg1 = big1 ? a1 : dg1;
+    }
+    const double t0 = lg0 - dg0 + (yv0 - m0) * inv0, t1 = lg1 - dg1 + (yv1 - m1) * inv1;
+    Sg += (one ? t0 : 0.0) + (two ? t1 : 0.0);
+    if (cr_reg) {
+        double xv[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) xv[j] = xp0[j * Npad];
+        const double W0 = one ? m0 * r * inv0 : 0.0;
+        sym_rank1<P>(A, W0, xv);
+        sym_rank1<P>(B, W0 * W0, xv);
+#pragma unroll
+        for (int j = 0; j < P; ++j) xv[j] = xp1[j * Npad];
+        const double W1 = two ? m1 * r * inv1 : 0.0;
+        sym_rank1<P>(A, W1, xv);
+        sym_rank1<P>(B, W1 * W1, xv);
+    }
+}
+
+template <int P, bool NB>
+PDQ_HD bool alpha_sweep_t(const Group& grp, const DesignS& d, bool cr_reg, const int64_t* y, int64_t ld, const double* mu,
+                          int64_t ld_mu, double r, const double* psi_tab, double& Sg, Sym<P>& A, Sym<P>& B) {
+    Sg = 0.0;
+    sym_zero<P>(A);
+    sym_zero<P>(B);
+    bool odd = false;
+    const int T = grp.T;
+    const int64_t ystep = (int64_t)T * ld, mstep = (int64_t)T * ld_mu;
+    const int64_t* yp = y + (int64_t)grp.si * ld;
+    const double* mp = mu + (int64_t)grp.si * ld_mu;
+    const double* xp = d.X + grp.si;
+    // the trip count is made uniform across the warp (lanes past N contribute a masked dummy) because alpha_pair votes
+    const int trips = (d.N + 2 * T - 1) / (2 * T);
+    int n = grp.si;
+    for (int it = 0; it < trips; ++it, n += 2 * T, yp += 2 * ystep, mp += 2 * mstep, xp += 2 * T) {
+        const bool v0 = n < d.N, v1 = n + T < d.N;
+        const long long yi0 = v0 ? yp[0] : 0, yi1 = v1 ? yp[ystep] : 0;
+        const double m0 = v0 ? mp[0] : 1.0, m1 = v1 ? mp[mstep] : 1.0;
+        // one call site: every lane of the warp reaches the vote inside alpha_pair together
+        alpha_pair<P, NB>(grp, v0 ? xp : d.X, v1 ? xp + T : d.X, d.Npad, yi0, yi1, m0, m1, v0, v1, r, cr_reg, psi_tab, Sg, A,
+                          B, odd);
+    }
+    return odd;
+}
+
 // derivative only (the minimiser is located as a root of dloss)
 template <int P>
 PDQ_HD double alpha_dloss(const Group& grp, const DesignS& d, const AlphaParams& prm, const int64_t* y, int64_t ld,
@@ -560,38 +647,11 @@ PDQ_HD double alpha_dloss(const Group& grp, const DesignS& d, const AlphaParams&
     const double a = fast_exp(x), r = fast_rcp(a), Nd = (double)d.N;
     grp.sync();  // previous evaluation's table reads are done
     build_psi_table(grp, psi_tab, r);
-    double Sg = 0.0;
+    double Sg;
     Sym<P> A, B;
-    sym_zero<P>(A);
-    sym_zero<P>(B);
-    const int64_t ystep = (int64_t)grp.T * ld, mstep = (int64_t)grp.T * ld_mu;
-    const int64_t* yp = y + (int64_t)grp.si * ld;
-    const double* mp = mu + (int64_t)grp.si * ld_mu;
-    const double* xp = d.X + grp.si;
-#pragma unroll 2
-    for (int n = grp.si; n < d.N; n += grp.T, yp += ystep, mp += mstep, xp += grp.T) {
-        const long long yi = *yp;
-        const double yv = (double)yi;
-        const double m = *mp;
-        const double rm = r + m;
-        const double inv = fast_rcp(rm);
-        double dg;
-        if (yi < kPsiK && yi >= 0) {
-            dg = psi_tab[yi];
-        } else {
-            const double z = yv + r;
-            dg = digamma_asym(z, fast_log(z));
-        }
-        Sg += fast_log(rm) - dg + (yv - m) * inv;
-        if (prm.cr_reg) {
-            double xv[P];
-#pragma unroll
-            for (int j = 0; j < P; ++j) xv[j] = xp[j * d.Npad];
-            const double W = m * r * inv;
-            sym_rank1<P>(A, W, xv);
-            sym_rank1<P>(B, W * W, xv);
-        }
-    }
+    bool odd = !(r > 0.0 && r < 1e300);
+    if (!odd) odd = alpha_sweep_t<P, true>(grp, d, prm.cr_reg != 0, y, ld, mu, ld_mu, r, psi_tab, Sg, A, B);
+    if (grp.any(odd)) alpha_sweep_t<P, false>(grp, d, prm.cr_reg != 0, y, ld, mu, ld_mu, r, psi_tab, Sg, A, B);
     Sg = grp.sum(Sg);
     // a * dnb_nll = -r * sum[psi(r) - psi(y+r) + log(1 + mu a) + (y - mu)/(mu + r)],  log(1+mu a) = x + log(r+mu)
     double g = -r * (Nd * (psi_tab[0] + x) + Sg);
