@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpydeseq2_b200.so")
+LIB_PATH = os.environ.get("PDQ_LIB") or os.path.join(_HERE, "libpydeseq2_b200.so")  # PDQ_LIB: tuning variants
 
 c_ctx = C.c_void_p
 c_design = C.c_void_p

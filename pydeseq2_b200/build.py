@@ -27,8 +27,12 @@ def _stale(target: str, deps) -> bool:
     return not os.path.exists(target) or any(os.path.getmtime(d) > os.path.getmtime(target) for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    objdir = os.path.join(HERE, "build")
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """`defines` / `out` build a tuning variant (e.g. ("-DPDQ_ALPHA_MINB=5",), "libpdq_a5.so") next to the default library."""
+    global OUT
+    tag = "".join(d.replace("-D", "_").replace("=", "") for d in defines)
+    objdir = os.path.join(HERE, "build" + tag)
+    target = os.path.join(HERE, out) if out else OUT
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     objs = []
@@ -38,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [_nvcc()] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, pr in procs:
         out, _ = pr.communicate()
@@ -46,11 +50,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if pr.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    if force or _stale(OUT, objs):
-        cmd = [_nvcc(), "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
+    if force or _stale(target, objs):
+        cmd = [_nvcc(), "-shared", "-o", target] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
                                                         "-ldl", "-lrt", "-lpthread", "-lgomp"]
         subprocess.run(cmd, check=True)
-    return OUT
+    return target
 
 
 if __name__ == "__main__":

@@ -53,6 +53,7 @@ struct pdq_ctx {
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     bool stage_busy[2] = {false, false};
     int staging = 1;  // PDQ_STAGING=0 disables (plain cudaMemcpyAsync from pageable memory)
+    int* tickets = nullptr;  // device ints for the persistent kernels' tile counters
     NcclApi nccl;
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
@@ -110,7 +111,7 @@ static int pick_lgT(const pdq_ctx* c, int G, int N) {
     return lg;
 }
 
-static LaunchCfg cfg(const pdq_ctx* c, int G, int N) { return LaunchCfg{c->stream, pick_lgT(c, G, N), c->prop.multiProcessorCount}; }
+static LaunchCfg cfg(const pdq_ctx* c, int G, int N) { return LaunchCfg{c->stream, pick_lgT(c, G, N), c->prop.multiProcessorCount, c->tickets}; }
 
 // --------------------------------------------------------------------------------------------- context
 extern "C" const char* pdq_version(void) { return "pydeseq2_b200 0.1.0 (sm_100a)"; }
@@ -149,6 +150,10 @@ extern "C" int pdq_ctx_create(int device, pdq_ctx** out) {
             return PDQ_ERR_CUDA;
         }
     if (const char* s = getenv("PDQ_STAGING")) c->staging = atoi(s);
+    if (cudaMalloc((void**)&c->tickets, 64) != cudaSuccess) {
+        delete c;
+        return PDQ_ERR_CUDA;
+    }
     *out = c;
     return PDQ_OK;
 }
@@ -160,6 +165,7 @@ extern "C" void pdq_ctx_destroy(pdq_ctx* c) {
     if (c->cached) pdq_design_destroy(c, c->cached);
     for (auto& b : c->buf)
         if (b) cudaFree(b);
+    if (c->tickets) cudaFree(c->tickets);
     for (int i = 0; i < 2; ++i) {
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
         if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
@@ -396,7 +402,7 @@ extern "C" int pdq_trend_fit_dev(pdq_ctx* c, const double* means, const double* 
     void *keep, *res;
     if (int e = ensure(c, kBufKeep, n, &keep)) return e;
     if (int e = ensure(c, kBufRes, n * 8, &res)) return e;
-    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount};
+    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets};
     if (int e = done(c, launch_trend_fit(lc, means, genewise, (unsigned char*)keep, n, 1, min_disp, max_disp, 1, min_disp, trigamma_c, 1,
                                          (double*)res, out16), "trend_fit"))
         return e;
@@ -410,7 +416,7 @@ extern "C" int pdq_select_dispersions_dev(pdq_ctx* c, const double* genewise, co
     CHECK_CTX(c);
     if (!genewise || !map || !fitted || !trend_out16 || !disp_out || n == 0)
         return fail(c, PDQ_ERR_INVALID, "pdq_select_dispersions_dev: bad arguments");
-    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount};
+    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets};
     return done(c, launch_select_disp(lc, genewise, map, fitted, trend_out16, n, min_disp, max_disp, disp_out, outlier_out), "select_dispersions");
 }
 
@@ -658,7 +664,7 @@ extern "C" int pdq_dispersion_trend_gamma_glm(pdq_ctx* c, const double* cov, con
     if (int e = ensure(c, kBufMisc, 256, &dout)) return e;
     CU(c, cudaMemcpyAsync(dx, cov, n * 8, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(dt, targets, n * 8, cudaMemcpyHostToDevice, c->stream));
-    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount};
+    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets};
     const double inf = 1.0 / 0.0;
     if (int e = done(c, launch_trend_fit(lc, (const double*)dx, (const double*)dt, (unsigned char*)keep, n, 0, -inf, inf, 0, 0.0, 0.0, 0, nullptr,
                                          (double*)dout),

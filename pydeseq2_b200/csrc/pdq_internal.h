@@ -24,6 +24,7 @@ struct LaunchCfg {
     cudaStream_t stream;
     int lgT;       // log2(lanes per gene)
     int sm_count;
+    int* tickets;  // device ints: tile counters of the persistent kernels
 };
 
 struct IrlsHost {

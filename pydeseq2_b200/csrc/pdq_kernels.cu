@@ -22,6 +22,13 @@ namespace {
 
 constexpr int kBlock = 128;
 constexpr int kWarps = kBlock / 32;
+// resident blocks per SM the two heavy kernels are compiled for (register cap = 65536 / (128 * blocks)); tuned on B200
+#ifndef PDQ_IRLS_MINB
+#define PDQ_IRLS_MINB 6
+#endif
+#ifndef PDQ_ALPHA_MINB
+#define PDQ_ALPHA_MINB 4
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -81,6 +88,25 @@ __device__ __forceinline__ void map_lanes(int lgT, int G, Group& grp, int& gene,
     gene = valid ? gidx : (G - 1);
 }
 
+// Persistent scheduling for the two heavy kernels: the grid holds as many blocks as fit on the machine and every WARP
+// draws gene tiles (32/T adjacent genes) from a global ticket counter until the tiles run out.  Genes differ in
+// iteration count, so a static assignment leaves SMs idle at the tail (20 % of the cycles in the first profile).
+__device__ __forceinline__ bool next_tile(int* ticket, int lgT, int G, Group& grp, int& gene, bool& valid) {
+    const int lane = threadIdx.x & 31;
+    grp.T = 1 << lgT;
+    grp.gpw = 32 >> lgT;
+    grp.si = lane >> (5 - lgT);
+    int tile = 0;
+    if (lane == 0) tile = atomicAdd(ticket, 1);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    const int ntiles = (G + grp.gpw - 1) >> (5 - lgT);
+    if (tile >= ntiles) return false;
+    const int gidx = tile * grp.gpw + (lane & (grp.gpw - 1));
+    valid = gidx < G;
+    gene = valid ? gidx : (G - 1);
+    return true;
+}
+
 struct DesignView {
     const double* pack;
     int N, Npad;
@@ -123,22 +149,24 @@ struct IrlsArgs {
     int64_t ld_out;
     int* status;
     int* n_fallback;
+    int* ticket;  // tile counter of the persistent scheduler (zeroed before the launch)
 };
 
 template <int P>
-__global__ void __launch_bounds__(kBlock) k_irls(const __grid_constant__ IrlsArgs<P> a) {
+__global__ void __launch_bounds__(kBlock, PDQ_IRLS_MINB) k_irls(const __grid_constant__ IrlsArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
     Group grp;
     int g;
     bool valid;
-    map_lanes(a.lgT, a.G, grp, g, valid);
-    int st = 0;
-    irls_gene<P>(grp, d, a.pinv, a.prm, a.counts + g, a.ld, a.disp[g], a.beta + (int64_t)g * P, a.mu + g, a.hat + g,
-                 a.ld_out, a.conv + g, &st, valid);
-    if (valid && grp.si == 0) {
-        a.status[g] = st;
-        if (st != kIrlsOk && a.n_fallback) atomicAdd(a.n_fallback, 1);
+    while (next_tile(a.ticket, a.lgT, a.G, grp, g, valid)) {
+        int st = 0;
+        irls_gene<P>(grp, d, a.pinv, a.prm, a.counts + g, a.ld, a.disp[g], a.beta + (int64_t)g * P, a.mu + g, a.hat + g,
+                     a.ld_out, a.conv + g, &st, valid);
+        if (valid && grp.si == 0) {
+            a.status[g] = st;
+            if (st != kIrlsOk && a.n_fallback) atomicAdd(a.n_fallback, 1);
+        }
     }
 }
 
@@ -171,23 +199,25 @@ struct AlphaArgs {
     double *alpha, *conv;
     int* status;
     const double* prior_var_dev;  // when set, overrides prm.prior_var (written by k_trend_prior on the same stream)
+    int* ticket;                  // tile counter of the persistent scheduler (zeroed before the launch)
 };
 
 template <int P>
-__global__ void __launch_bounds__(kBlock) k_alpha_mle(const __grid_constant__ AlphaArgs<P> a) {
+__global__ void __launch_bounds__(kBlock, PDQ_ALPHA_MINB) k_alpha_mle(const __grid_constant__ AlphaArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
     Group grp;
     int g;
     bool valid;
-    map_lanes(a.lgT, a.G, grp, g, valid);
-    // per-gene psi(r + k) tables live behind the design pack and its mbarrier
-    double* psi = reinterpret_cast<double*>(smem + (size_t)(P + 2) * a.dv.Npad * 8 + 16) +
-                  (size_t)((threadIdx.x >> 5) * grp.gpw + ((threadIdx.x & 31) & (grp.gpw - 1))) * kPsiK;
     AlphaParams prm = a.prm;
     if (a.prior_var_dev) prm.prior_var = *a.prior_var_dev;
-    alpha_gene<P>(grp, d, prm, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha_hat[g], a.alpha + g, a.conv + g,
-                  a.status + g, valid, psi);
+    const int gpw = 32 >> a.lgT;
+    // per-gene psi(r + k) tables live behind the design pack and its mbarrier (one slot per gene of the warp's tile)
+    double* psi = reinterpret_cast<double*>(smem + (size_t)(P + 2) * a.dv.Npad * 8 + 16) +
+                  (size_t)((threadIdx.x >> 5) * gpw + ((threadIdx.x & 31) & (gpw - 1))) * kPsiK;
+    while (next_tile(a.ticket, a.lgT, a.G, grp, g, valid))
+        alpha_gene<P>(grp, d, prm, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha_hat[g], a.alpha + g, a.conv + g,
+                      a.status + g, valid, psi);
 }
 
 template <int P>
@@ -495,6 +525,16 @@ int prep(K kernel, size_t smem) {
     return 0;
 }
 
+// grid of a persistent kernel: every block the machine can hold at once, but no more blocks than warp tiles need
+template <class K>
+int persistent_grid(K kernel, size_t smem, int sm_count, int G, int lgT) {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int need = grid_for(G, lgT);
+    const int fit = per_sm * sm_count;
+    return need < fit ? need : fit;
+}
+
 template <int P>
 SmallMat<P> pinv_of(const DesignDev& d) {
     SmallMat<P> m;
@@ -537,10 +577,11 @@ int launch_irls(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, i
     PDQ_DISPATCH_P(d.p, {
         IrlsArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d),
                       IrlsParams{h.min_mu, h.beta_tol, h.min_beta, h.max_beta, h.maxiter, d.full_rank},
-                      counts, ld, G, c.lgT, disp, beta, mu, hat, conv, ld_out, status, n_fallback};
+                      counts, ld, G, c.lgT, disp, beta, mu, hat, conv, ld_out, status, n_fallback, c.tickets};
         if (int e = prep(k_irls<P>, d.smem_bytes)) return e;
         if (int e = prep(k_irls_optimizer<P>, d.smem_bytes)) return e;
-        k_irls<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+        if (cudaMemsetAsync(c.tickets, 0, sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;
+        k_irls<P><<<persistent_grid(k_irls<P>, d.smem_bytes, c.sm_count, G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
         k_irls_optimizer<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });
     if (int e = check_launch()) return e;
@@ -553,11 +594,12 @@ int launch_alpha_mle(const LaunchCfg& c, const DesignDev& d, const int64_t* coun
                      int* status) {
     PDQ_DISPATCH_P(d.p, {
         AlphaArgs<P> a{{d.pack, d.N, d.Npad}, AlphaParams{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg},
-                       counts, ld, G, c.lgT, mu, ld_mu, alpha_hat, alpha, conv, status, prior_var_dev};
+                       counts, ld, G, c.lgT, mu, ld_mu, alpha_hat, alpha, conv, status, prior_var_dev, c.tickets + 1};
         const size_t smem_alpha = d.smem_bytes + (size_t)kWarps * (32 >> c.lgT) * kPsiK * sizeof(double);
         if (int e = prep(k_alpha_mle<P>, smem_alpha)) return e;
         if (int e = prep(k_alpha_grid<P>, d.smem_bytes)) return e;
-        k_alpha_mle<P><<<grid_for(G, c.lgT), kBlock, smem_alpha, c.stream>>>(a);
+        if (cudaMemsetAsync(c.tickets + 1, 0, sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;
+        k_alpha_mle<P><<<persistent_grid(k_alpha_mle<P>, smem_alpha, c.sm_count, G, c.lgT), kBlock, smem_alpha, c.stream>>>(a);
         k_alpha_grid<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });
     if (int e = check_launch()) return e;
