@@ -59,6 +59,12 @@ int pdq_device_count(void);
 int pdq_device_info(const pdq_ctx* ctx, char* name, size_t name_len, int* sm_count, size_t* mem_bytes);
 /* lanes cooperating on one gene (1,2,4,8,16,32); 0 = choose from G (default) */
 int pdq_set_lanes_per_gene(pdq_ctx* ctx, int lanes);
+/* Test hook: PDQ_DEBUG_FORCE_IRLS_OPTIMIZER sends every gene of pdq_irls through the optimiser branch
+ * (utils.py:374-413) and PDQ_DEBUG_FORCE_ALPHA_GRID every gene of pdq_alpha_mle through the grid fallback
+ * (grid_search.py:54-142), so that the rarely taken kernels are exercised by the GPU test-suite. */
+#define PDQ_DEBUG_FORCE_IRLS_OPTIMIZER 1
+#define PDQ_DEBUG_FORCE_ALPHA_GRID 2
+int pdq_set_debug_flags(pdq_ctx* ctx, int flags);
 /* number of kernel launches issued through this context so far (bench.py `gpu_launches`) */
 int64_t pdq_launch_count(const pdq_ctx* ctx);
 

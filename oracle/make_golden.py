@@ -34,11 +34,11 @@ REF = "/root/reference"
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def synth(N, G, design, seed=0):
+def synth(N, G, design, seed=0, mean_log2=4.0):
     """SURVEY.md §8(d) generator (DESeq2 makeExampleDESeqDataSet-like)."""
     from pydeseq2_b200.synth import make_counts
 
-    return make_counts(N, G, design, seed)
+    return make_counts(N, G, design, seed, mean_log2=mean_log2)
 
 
 def ref_inference():
@@ -58,11 +58,11 @@ def ref_inference():
     return FloatFlags(n_cpus=1)
 
 
-def gen_calls(name, N, G, design_kind, seed):
+def gen_calls(name, N, G, design_kind, seed, mean_log2=4.0):
     from pydeseq2.preprocessing import deseq2_norm
 
     inf = ref_inference()
-    counts, X, _truth = synth(N, G, design_kind, seed)
+    counts, X, _truth = synth(N, G, design_kind, seed, mean_log2)
     # drop all-zero genes like dds.py:729-731
     counts = counts[:, ~(counts == 0).all(0)]
     normed, sf = deseq2_norm(counts)
@@ -76,7 +76,7 @@ def gen_calls(name, N, G, design_kind, seed):
     out["lin_mu"] = inf.lin_reg_mu(counts, sf, X, 0.5)
     b, m, h, c = inf.irls(counts, sf, X, mom, 0.5, 1e-8)
     out.update(irls0_beta=b, irls0_mu=np.ascontiguousarray(m), irls0_hat=np.ascontiguousarray(h), irls0_conv=c)
-    mu_hat = np.ascontiguousarray(out["lin_mu"] if design_kind == "two_level" else m)
+    mu_hat = np.ascontiguousarray(out["lin_mu"] if design_kind in ("two_level", "intercept") else m)
     out["mu_hat"] = mu_hat
     a, c = inf.alpha_mle(counts, X, mu_hat, mom, 1e-8, max_disp)
     out.update(gw_alpha=a, gw_conv=c)
@@ -93,7 +93,7 @@ def gen_calls(name, N, G, design_kind, seed):
     b, m, h, c = inf.irls(counts, sf, X, disp, 0.5, 1e-8)
     out.update(lfc_beta=b, lfc_mu=np.ascontiguousarray(m), lfc_hat=np.ascontiguousarray(h), lfc_conv=c)
     contrast = np.zeros(p)
-    contrast[1] = 1.0
+    contrast[min(1, p - 1)] = 1.0
     ridge = np.diag(np.repeat(1e-6, p))
     out.update(contrast=contrast, ridge=ridge)
     mu_w = np.ascontiguousarray(m)
@@ -202,6 +202,10 @@ def main():
     gen_calls("factorial_n30", 30, 40, "factorial", 1)
     gen_calls("continuous_n40", 40, 40, "continuous", 2)
     gen_calls("two_level_n200", 200, 64, "two_level", 3)
+    gen_calls("large_counts_n12", 12, 40, "two_level", 4, mean_log2=18.0)
+    gen_calls("five_columns_n36", 36, 40, "five", 5)
+    gen_calls("intercept_n10", 10, 30, "intercept", 6)
+    gen_calls("few_samples_n4", 4, 40, "two_level", 7)
 
     # shipped 100 x 10 synthetic dataset
     counts = pd.read_csv(f"{REF}/datasets/synthetic/test_counts.csv", index_col=0).T

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "pdq_last_error": (C.c_char_p, [c_ctx]),
     "pdq_device_info": (C.c_int, [c_ctx, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "pdq_set_lanes_per_gene": (C.c_int, [c_ctx, C.c_int]),
+    "pdq_set_debug_flags": (C.c_int, [c_ctx, C.c_int]),
     "pdq_launch_count": (C.c_int64, [c_ctx]),
     "pdq_malloc": (C.c_int, [c_ctx, C.c_size_t, C.POINTER(c_dptr)]),
     "pdq_free": (C.c_int, [c_ctx, c_dptr]),

@@ -54,6 +54,7 @@ struct pdq_ctx {
     bool stage_busy[2] = {false, false};
     int staging = 1;  // PDQ_STAGING=0 disables (plain cudaMemcpyAsync from pageable memory)
     int* tickets = nullptr;  // device ints for the persistent kernels' tile counters
+    int debug = 0;           // PDQ_DEBUG_* test hooks
     NcclApi nccl;
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
@@ -111,7 +112,7 @@ static int pick_lgT(const pdq_ctx* c, int G, int N) {
     return lg;
 }
 
-static LaunchCfg cfg(const pdq_ctx* c, int G, int N) { return LaunchCfg{c->stream, pick_lgT(c, G, N), c->prop.multiProcessorCount, c->tickets}; }
+static LaunchCfg cfg(const pdq_ctx* c, int G, int N) { return LaunchCfg{c->stream, pick_lgT(c, G, N), c->prop.multiProcessorCount, c->tickets, c->debug}; }
 
 // --------------------------------------------------------------------------------------------- context
 extern "C" const char* pdq_version(void) { return "pydeseq2_b200 0.1.0 (sm_100a)"; }
@@ -193,6 +194,12 @@ extern "C" int pdq_set_lanes_per_gene(pdq_ctx* c, int lanes) {
     if (!c) return PDQ_ERR_INVALID;
     if (lanes != 0 && (lanes < 1 || lanes > 32 || (lanes & (lanes - 1)))) return fail(c, PDQ_ERR_INVALID, "lanes per gene must be 0 or a power of two <= 32");
     c->lanes_override = lanes;
+    return PDQ_OK;
+}
+
+extern "C" int pdq_set_debug_flags(pdq_ctx* c, int flags) {
+    if (!c) return PDQ_ERR_INVALID;
+    c->debug = flags;
     return PDQ_OK;
 }
 
@@ -402,7 +409,7 @@ extern "C" int pdq_trend_fit_dev(pdq_ctx* c, const double* means, const double* 
     void *keep, *res;
     if (int e = ensure(c, kBufKeep, n, &keep)) return e;
     if (int e = ensure(c, kBufRes, n * 8, &res)) return e;
-    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets};
+    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets, c->debug};
     if (int e = done(c, launch_trend_fit(lc, means, genewise, (unsigned char*)keep, n, 1, min_disp, max_disp, 1, min_disp, trigamma_c, 1,
                                          (double*)res, out16), "trend_fit"))
         return e;
@@ -416,7 +423,7 @@ extern "C" int pdq_select_dispersions_dev(pdq_ctx* c, const double* genewise, co
     CHECK_CTX(c);
     if (!genewise || !map || !fitted || !trend_out16 || !disp_out || n == 0)
         return fail(c, PDQ_ERR_INVALID, "pdq_select_dispersions_dev: bad arguments");
-    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets};
+    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets, c->debug};
     return done(c, launch_select_disp(lc, genewise, map, fitted, trend_out16, n, min_disp, max_disp, disp_out, outlier_out), "select_dispersions");
 }
 
@@ -664,7 +671,7 @@ extern "C" int pdq_dispersion_trend_gamma_glm(pdq_ctx* c, const double* cov, con
     if (int e = ensure(c, kBufMisc, 256, &dout)) return e;
     CU(c, cudaMemcpyAsync(dx, cov, n * 8, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(dt, targets, n * 8, cudaMemcpyHostToDevice, c->stream));
-    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets};
+    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets, c->debug};
     const double inf = 1.0 / 0.0;
     if (int e = done(c, launch_trend_fit(lc, (const double*)dx, (const double*)dt, (unsigned char*)keep, n, 0, -inf, inf, 0, 0.0, 0.0, 0, nullptr,
                                          (double*)dout),

@@ -709,6 +709,10 @@ PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& pr
                        int* status_out, bool valid, double* psi_tab) {
     const double xhat = log(alpha_hat);
     const double tolx = 1e-5;   // last secant step is taken unevaluated: final error << tolx
+    // scipy's L-BFGS-B declares convergence as soon as the projected gradient is <= pgtol = 1e-5 (checked at the
+    // start point too).  This matters for parity, not accuracy: on the flat left tail of the objective (alpha -> 1e-8,
+    // |dloss| ~ 1e-7) the reference therefore never leaves its start value, and neither may we.
+    const double pgtol = 1e-5;
     double xb = fmin(fmax(xhat, prm.lo), prm.hi);
     double gb = alpha_dloss<P>(grp, d, prm, y, ld, mu, ld_mu, xb, xhat, psi_tab);
     double xa = xb, ga = gb;
@@ -720,8 +724,8 @@ PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& pr
     if (!(gb == gb)) {
         fail = true;
         active = false;
-    } else if (gb == 0.0 || (gb > 0.0 && xb <= prm.lo) || (gb < 0.0 && xb >= prm.hi)) {
-        active = false;  // stationary, or the projected gradient vanishes at a bound
+    } else if (fabs(gb) <= pgtol || (gb > 0.0 && xb <= prm.lo) || (gb < 0.0 && xb >= prm.hi)) {
+        active = false;  // stationary to L-BFGS-B's tolerance, or the projected gradient vanishes at a bound
     } else {
         xt = fmin(fmax(xb - sgn(gb) * 1.0, prm.lo), prm.hi);
     }
@@ -746,7 +750,7 @@ PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& pr
         xa = xb; ga = gb;
         xb = xt; gb = gt;
         xres = xb;
-        if (gt == 0.0) { active = false; continue; }
+        if (fabs(gt) <= pgtol) { active = false; continue; }
         if (!have_br && ((gb > 0.0 && xb <= prm.lo) || (gb < 0.0 && xb >= prm.hi))) {
             active = false;  // pushed against a bound: L-BFGS-B stops with zero projected gradient
             continue;

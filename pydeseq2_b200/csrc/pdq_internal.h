@@ -25,6 +25,7 @@ struct LaunchCfg {
     int lgT;       // log2(lanes per gene)
     int sm_count;
     int* tickets;  // device ints: tile counters of the persistent kernels
+    int debug;     // PDQ_DEBUG_* test hooks
 };
 
 struct IrlsHost {

@@ -150,6 +150,7 @@ struct IrlsArgs {
     int* status;
     int* n_fallback;
     int* ticket;  // tile counter of the persistent scheduler (zeroed before the launch)
+    int force;    // test hook: flag every gene for the optimiser branch
 };
 
 template <int P>
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(kBlock, PDQ_IRLS_MINB) k_irls(const __grid_con
         irls_gene<P>(grp, d, a.pinv, a.prm, a.counts + g, a.ld, a.disp[g], a.beta + (int64_t)g * P, a.mu + g, a.hat + g,
                      a.ld_out, a.conv + g, &st, valid);
         if (valid && grp.si == 0) {
+            if (a.force) st = kIrlsNeedsOptimizer;
             a.status[g] = st;
             if (st != kIrlsOk && a.n_fallback) atomicAdd(a.n_fallback, 1);
         }
@@ -200,6 +202,7 @@ struct AlphaArgs {
     int* status;
     const double* prior_var_dev;  // when set, overrides prm.prior_var (written by k_trend_prior on the same stream)
     int* ticket;                  // tile counter of the persistent scheduler (zeroed before the launch)
+    int force;                    // test hook: flag every gene for the grid fallback
 };
 
 template <int P>
@@ -215,9 +218,14 @@ __global__ void __launch_bounds__(kBlock, PDQ_ALPHA_MINB) k_alpha_mle(const __gr
     // per-gene psi(r + k) tables live behind the design pack and its mbarrier (one slot per gene of the warp's tile)
     double* psi = reinterpret_cast<double*>(smem + (size_t)(P + 2) * a.dv.Npad * 8 + 16) +
                   (size_t)((threadIdx.x >> 5) * gpw + ((threadIdx.x & 31) & (gpw - 1))) * kPsiK;
-    while (next_tile(a.ticket, a.lgT, a.G, grp, g, valid))
+    while (next_tile(a.ticket, a.lgT, a.G, grp, g, valid)) {
         alpha_gene<P>(grp, d, prm, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha_hat[g], a.alpha + g, a.conv + g,
                       a.status + g, valid, psi);
+        if (a.force && valid && grp.si == 0) {
+            a.status[g] = kAlphaNeedsGrid;
+            a.conv[g] = 0.0;
+        }
+    }
 }
 
 template <int P>
@@ -577,7 +585,8 @@ int launch_irls(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, i
     PDQ_DISPATCH_P(d.p, {
         IrlsArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d),
                       IrlsParams{h.min_mu, h.beta_tol, h.min_beta, h.max_beta, h.maxiter, d.full_rank},
-                      counts, ld, G, c.lgT, disp, beta, mu, hat, conv, ld_out, status, n_fallback, c.tickets};
+                      counts, ld, G, c.lgT, disp, beta, mu, hat, conv, ld_out, status, n_fallback, c.tickets,
+                      (c.debug & PDQ_DEBUG_FORCE_IRLS_OPTIMIZER) ? 1 : 0};
         if (int e = prep(k_irls<P>, d.smem_bytes)) return e;
         if (int e = prep(k_irls_optimizer<P>, d.smem_bytes)) return e;
         if (cudaMemsetAsync(c.tickets, 0, sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;
@@ -594,7 +603,8 @@ int launch_alpha_mle(const LaunchCfg& c, const DesignDev& d, const int64_t* coun
                      int* status) {
     PDQ_DISPATCH_P(d.p, {
         AlphaArgs<P> a{{d.pack, d.N, d.Npad}, AlphaParams{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg},
-                       counts, ld, G, c.lgT, mu, ld_mu, alpha_hat, alpha, conv, status, prior_var_dev, c.tickets + 1};
+                       counts, ld, G, c.lgT, mu, ld_mu, alpha_hat, alpha, conv, status, prior_var_dev, c.tickets + 1,
+                       (c.debug & PDQ_DEBUG_FORCE_ALPHA_GRID) ? 1 : 0};
         const size_t smem_alpha = d.smem_bytes + (size_t)kWarps * (32 >> c.lgT) * kPsiK * sizeof(double);
         if (int e = prep(k_alpha_mle<P>, smem_alpha)) return e;
         if (int e = prep(k_alpha_grid<P>, d.smem_bytes)) return e;

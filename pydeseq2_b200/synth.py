@@ -13,7 +13,7 @@ import numpy as np
 
 LN2 = np.log(2.0)
 
-DESIGNS = ("two_level", "factorial", "continuous")
+DESIGNS = ("two_level", "factorial", "continuous", "intercept", "five")
 
 
 def design_matrix(N: int, kind: str, seed: int = 0) -> np.ndarray:
@@ -27,19 +27,24 @@ def design_matrix(N: int, kind: str, seed: int = 0) -> np.ndarray:
     elif kind == "continuous":  # C4: p=3 with a continuous covariate
         z = np.random.default_rng(seed + 7919).normal(0.0, 1.0, N)
         cols = [np.ones(N), cond, z]
+    elif kind == "intercept":  # p=1 (the reference fits this for VST / iterative size factors, dds.py:425-430)
+        cols = [np.ones(N)]
+    elif kind == "five":  # p=5: two binary factors, a 3-level factor (two dummies), no continuous term
+        cols = [np.ones(N), cond, (i % 2).astype(float), (i % 3 == 1).astype(float), (i % 3 == 2).astype(float)]
     else:
         raise ValueError(f"unknown design kind {kind!r}; expected one of {DESIGNS}")
     return np.ascontiguousarray(np.stack(cols, axis=1))
 
 
-def make_counts(N: int, G: int, kind: str = "two_level", seed: int = 0, chunk: int = 1 << 16):
-    """Return ``(counts int64 (N, G), X float64 (N, p), truth dict)``."""
+def make_counts(N: int, G: int, kind: str = "two_level", seed: int = 0, chunk: int = 1 << 16, mean_log2: float = 4.0):
+    """Return ``(counts int64 (N, G), X float64 (N, p), truth dict)``.  ``mean_log2`` shifts the expression level
+    (4 = the reference-like default; 18 gives counts of 1e5-1e7 like the reference's ``large_counts`` test)."""
     rng = np.random.default_rng(seed)
     X = design_matrix(N, kind, seed)
     p = X.shape[1]
     sf = np.exp(rng.normal(0.0, 0.2, N))
     beta = np.empty((G, p))
-    beta[:, 0] = rng.normal(4.0, 2.0, G) * LN2
+    beta[:, 0] = rng.normal(mean_log2, 2.0, G) * LN2
     beta[:, 1:] = rng.normal(0.0, 0.5, (G, p - 1)) * LN2
     alpha = 4.0 / np.exp(beta[:, 0]) + 0.1
     counts = np.empty((N, G), dtype=np.int64)

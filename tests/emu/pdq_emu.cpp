@@ -112,7 +112,10 @@ int emu_alpha_mle(const int64_t* counts, int64_t ld, int N, int G, const double*
         double psi[kPsiK];
         for (int g = 0; g < G; ++g) {
             alpha_gene<P>(kOne, k.d, prm, counts + g, ld, mu + g, ld_mu, alpha_hat[g], alpha + g, conv + g, status + g, true, psi);
-            if (force_grid) status[g] = kAlphaNeedsGrid;
+            if (force_grid) {
+                status[g] = kAlphaNeedsGrid;
+                conv[g] = 0.0;
+            }
             if (status[g] == kAlphaNeedsGrid)
                 alpha_grid_gene<P>(kOne, k.d, prm.lo, prm.hi, counts + g, ld, mu + g, ld_mu, alpha + g, true);
         }
@@ -189,6 +192,11 @@ int emu_trend_fit(const double* x, const double* t, size_t n, int x_is_mean, dou
     return 0;
 }
 
+long emu_eval_count(int reset) {
+    long v = g_emu_alpha_evals;
+    if (reset) g_emu_alpha_evals = 0;
+    return v;
+}
 double emu_fast_log(double x) { return fast_log(x); }
 double emu_fast_exp(double x) { return fast_exp(x); }
 double emu_lgamma(double x) { return lgamma_pos(x); }

@@ -36,7 +36,7 @@ def assert_close(got, want, rtol, what, atol=0.0, mask=None):
     )
 
 
-def check_calls(inf, g, alpha_interior_only=True):
+def check_calls(inf, g, tol_alpha=TOL_ALPHA):
     """`g` is a calls_*.npz golden (outputs of the REAL reference); `inf` a B200Inference."""
     c, X, sf, N = g["counts"], g["X"], g["sf"], g["counts"].shape[0]
     max_disp = max(10.0, N)
@@ -46,10 +46,14 @@ def check_calls(inf, g, alpha_interior_only=True):
 
     for tag, disp in (("irls0", g["mom"]), ("lfc", g["disp"])):
         b, m, h, cv = inf.irls(c, sf, X, disp, 0.5, 1e-8)
-        assert_close(b, g[f"{tag}_beta"], TOL_BETA, f"{tag} beta", atol=1e-9)
-        assert_close(m, g[f"{tag}_mu"], TOL_MU, f"{tag} mu", atol=1e-12)
-        assert_close(h, g[f"{tag}_hat"], TOL_HAT, f"{tag} hat", atol=1e-12)
+        # genes the reference itself flags as not converged (IRLS hit maxiter, then L-BFGS-B gave up on the kinked
+        # clamped objective, utils.py:374-403) carry an optimiser-path-dependent value: flags must agree, values need not
+        ok = g[f"{tag}_conv"] == 1.0
+        assert_close(b[ok], g[f"{tag}_beta"][ok], TOL_BETA, f"{tag} beta", atol=1e-9)
+        assert_close(m[:, ok], g[f"{tag}_mu"][:, ok], TOL_MU, f"{tag} mu", atol=1e-12)
+        assert_close(h[:, ok], g[f"{tag}_hat"][:, ok], TOL_HAT, f"{tag} hat", atol=1e-12)
         np.testing.assert_array_equal(cv, g[f"{tag}_conv"])
+        assert np.isfinite(b).all()
         assert cv.dtype == np.float64
 
     lo, hi = 1e-8, max_disp
@@ -61,7 +65,7 @@ def check_calls(inf, g, alpha_interior_only=True):
         # at tiny dispersions the reference's own gradient is rounding noise (1/alpha^2 cancellation): compare
         # those genes after the caller's clip only (dds.py:792-794)
         interior = ok & (want > 1e-5) & (want < hi * (1 - 1e-9))
-        assert_close(a[interior], want[interior], TOL_ALPHA, f"{tag} alpha (interior optimum)")
+        assert_close(a[interior], want[interior], tol_alpha, f"{tag} alpha (interior optimum)")
         edge = ok & ~interior
         assert np.all(np.clip(a[edge], lo, hi) < 1e-4) or not edge.any() or np.allclose(
             np.clip(a[edge], lo, hi), np.clip(want[edge], lo, hi), rtol=1e-3), f"{tag} alpha (bound cases)"

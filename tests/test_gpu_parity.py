@@ -8,7 +8,8 @@ from parity import assert_close, check_calls, check_tape
 
 pytestmark = pytest.mark.gpu
 
-CALLS = ["calls_two_level_n24", "calls_factorial_n30", "calls_continuous_n40", "calls_two_level_n200"]
+CALLS = ["calls_two_level_n24", "calls_factorial_n30", "calls_continuous_n40", "calls_two_level_n200",
+         "calls_large_counts_n12", "calls_five_columns_n36", "calls_intercept_n10", "calls_few_samples_n4"]
 TAPES = ["tape_single_factor", "tape_multi_factor", "tape_continuous", "tape_wide"]
 
 
@@ -21,7 +22,9 @@ def inf():
 
 @pytest.mark.parametrize("name", CALLS)
 def test_gpu_calls_vs_reference_golden(inf, name):
-    check_calls(inf, load_golden(name))
+    # counts of 1e5-1e7: the objective itself is only resolved to ~1e-5 in float64 (cancellation in nb_nll), so the
+    # reference's L-BFGS-B and the root search agree to the north-star 1e-4 there, not to 2e-5
+    check_calls(inf, load_golden(name), **({"tol_alpha": 1e-4} if "large_counts" in name else {}))
 
 
 @pytest.mark.parametrize("name", TAPES)

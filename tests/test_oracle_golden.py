@@ -6,7 +6,8 @@ import pytest
 from oracle import nbglm
 from conftest import load_golden, tape_calls
 
-CALLS = ["calls_two_level_n24", "calls_factorial_n30", "calls_continuous_n40", "calls_two_level_n200"]
+CALLS = ["calls_two_level_n24", "calls_factorial_n30", "calls_continuous_n40", "calls_two_level_n200",
+         "calls_large_counts_n12", "calls_five_columns_n36", "calls_intercept_n10", "calls_few_samples_n4"]
 TAPES = ["tape_single_factor", "tape_multi_factor", "tape_continuous", "tape_wide"]
 # the oracle runs the same scipy/numpy wheels as the reference: expect agreement to rounding
 RTOL = 1e-9
