@@ -253,6 +253,10 @@ def main():
     rf.run(profile=True)
     rf.run(profile=True)
     stages = dict(rf.stage_ms)
+    ctx.sync()
+    t0 = time.perf_counter()
+    rf.device_size_factors()  # median of ratios on the device: reported for information, NOT part of the timed step
+    stages["size_factors_dev_untimed"] = (time.perf_counter() - t0) * 1e3
     alg_bytes = {"mom_dispersions": 8, "lin_reg_mu": 16, "irls_init": 24, "alpha_mle_genewise": 16, "alpha_mle_map": 16,
                  "irls_lfc": 24, "wald_test": 8}  # bytes per (gene, sample): SURVEY.md §8(d)
     kern = {k: v for k, v in stages.items() if k in alg_bytes}

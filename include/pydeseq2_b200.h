@@ -133,6 +133,12 @@ int pdq_fit_moments_dispersions(pdq_ctx* ctx, const double* normed_counts, int64
 int pdq_dispersion_trend_gamma_glm(pdq_ctx* ctx, const double* covariates, const double* targets, size_t n,
                                    double* coeffs_out, double* pred_out, int* converged_out);
 
+/* Median-of-ratios size factors -- preprocessing.deseq2_norm_fit/transform (preprocessing.py:31-102), the step before the
+ * plugin calls: per-gene mean of log counts, genes holding a zero dropped, per-sample exact median
+ * of log(count) - gene mean (radix select), exponentiated.  `sf_out` (N,).  All entries NaN when every gene holds a zero
+ * (the reference then switches to its iterative fallback, dds.py:682-690). */
+int pdq_size_factors(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N, int G, double* sf_out);
+
 /* ----------------------------------------------------------------- hot path, device-resident
  * Same semantics; every pointer except `design` is device memory from pdq_malloc.  Asynchronous. */
 int pdq_lin_reg_mu_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld, int G,
@@ -166,6 +172,9 @@ int pdq_mom_dispersions_dev(pdq_ctx* ctx, const pdq_design* design, const int64_
  * `fitted_out` (n,) device, may be NULL: c0 + c1 / mean. */
 int pdq_trend_fit_dev(pdq_ctx* ctx, const double* normed_means, const double* genewise, size_t n, double min_disp,
                       double max_disp, double trigamma_c, double* out16, double* fitted_out);
+/* device-resident flavour of pdq_size_factors; `logmeans_out` (G,) may be NULL */
+int pdq_size_factors_dev(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N, int G, double* sf_out,
+                         double* logmeans_out);
 /* Final dispersions (dds.py:918-932): clip(MAP), except genes with log(genewise) > log(fitted) + 2 sqrt(squared_logres)
  * which keep their clipped genewise value; `trend_out16` is the record written by pdq_trend_fit_dev.
  * `outlier_out` (n,) 0/1 may be NULL. */

@@ -417,6 +417,16 @@ extern "C" int pdq_trend_fit_dev(pdq_ctx* c, const double* means, const double* 
     return PDQ_OK;
 }
 
+extern "C" int pdq_size_factors_dev(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, double* sf_out, double* logmeans_out) {
+    CHECK_CTX(c);
+    if (!counts || !sf_out || N <= 0 || G <= 0 || ld < G) return fail(c, PDQ_ERR_INVALID, "pdq_size_factors_dev: bad arguments");
+    void *lm = logmeans_out, *scratch;
+    if (!lm)
+        if (int e = ensure(c, kBufF, (size_t)G * 8, &lm)) return e;
+    if (int e = ensure(c, kBufB, (size_t)N * G * 8, &scratch)) return e;
+    return done(c, launch_size_factors(cfg(c, G, N), counts, ld, N, G, (double*)lm, (double*)scratch, sf_out), "size_factors");
+}
+
 extern "C" int pdq_select_dispersions_dev(pdq_ctx* c, const double* genewise, const double* map, const double* fitted,
                                           const double* trend_out16, size_t n, double min_disp, double max_disp, double* disp_out,
                                           double* outlier_out) {
@@ -655,6 +665,19 @@ extern "C" int pdq_fit_moments_dispersions(pdq_ctx* c, const double* normed, int
     if (int e = done(c, launch_moments(cfg(c, G, N), d->d, (const double*)dn, G, G, (double*)da, (double*)dz), "fit_moments_dispersions")) return e;
     CU(c, cudaMemcpyAsync(alpha_out, da, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(all_zero_out, dz, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return PDQ_OK;
+}
+
+extern "C" int pdq_size_factors(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, double* sf_out) {
+    CHECK_CTX(c);
+    if (!counts || !sf_out || N <= 0 || G <= 0 || ld < G) return fail(c, PDQ_ERR_INVALID, "pdq_size_factors: bad arguments");
+    void *dc, *dsf;
+    if (int e = ensure(c, kBufCounts, (size_t)N * G * 8, &dc)) return e;
+    if (int e = ensure(c, kBufE, (size_t)N * 8, &dsf)) return e;
+    if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
+    if (int e = pdq_size_factors_dev(c, (const int64_t*)dc, G, N, G, (double*)dsf, nullptr)) return e;
+    CU(c, cudaMemcpyAsync(sf_out, dsf, (size_t)N * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return PDQ_OK;
 }

@@ -56,6 +56,8 @@ int launch_trend_fit(const LaunchCfg&, const double* x, const double* t, unsigne
                      double lo, double hi, int outer, double min_disp, double trigamma_c, int with_prior, double* res,
                      double* out16);
 int launch_trend_eval(const LaunchCfg&, const double* means, size_t n, const double* out16, double* fitted);
+int launch_size_factors(const LaunchCfg&, const int64_t* counts, int64_t ld, int N, int G, double* logmeans,
+                        double* scratch, double* sf_out);
 int launch_select_disp(const LaunchCfg&, const double* gw, const double* mp, const double* fitted, const double* out16,
                        size_t n, double lo, double hi, double* disp, double* outlier);
 

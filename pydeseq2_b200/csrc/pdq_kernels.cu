@@ -497,6 +497,46 @@ __global__ void __launch_bounds__(1024) k_trend_prior(const double* __restrict__
     cluster.sync();  // no block may exit while peers can still address its shared memory
 }
 
+// ---- median-of-ratios size factors (preprocessing.py:31-102), SURVEY.md §8 f-2 -------------------------------------
+// 1. per-gene mean of log counts (-inf when the gene holds a zero: such genes are filtered out, preprocessing.py:52-54)
+__global__ void __launch_bounds__(kBlock) k_log_means(const int64_t* __restrict__ counts, int64_t ld, int N, int G, int lgT,
+                                                      double* __restrict__ logmeans) {
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(lgT, G, grp, g, valid);
+    const int64_t* yp = counts + g + (int64_t)grp.si * ld;
+    double s = 0.0;
+    for (int n = grp.si; n < N; n += grp.T, yp += (int64_t)grp.T * ld) s += log((double)*yp);  // libdevice log: log(0) = -inf
+    s = grp.sum(s);
+    if (valid && grp.si == 0) logmeans[g] = s / (double)N;
+}
+
+// 2. one block per sample: log ratios of the sample against the gene means, exact median by radix select
+__global__ void __launch_bounds__(1024) k_size_factor_median(const int64_t* __restrict__ counts, int64_t ld, int G,
+                                                             const double* __restrict__ logmeans, double* scratch,
+                                                             double* sf_out) {
+    __shared__ unsigned hist[258];
+    __shared__ unsigned cnt_s;
+    const int n = blockIdx.x;
+    double* row = scratch + (size_t)n * G;
+    const int64_t* c = counts + (int64_t)n * ld;
+    if (threadIdx.x == 0) cnt_s = 0;
+    __syncthreads();
+    unsigned cnt = 0;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const double lm = logmeans[g];
+        const bool keep = fabs(lm) <= 1.7976931348623157e308;  // ~np.isinf(logmeans); NaN cannot occur for counts >= 0
+        row[g] = keep ? log((double)c[g]) - lm : __longlong_as_double(0x7ff8000000000000ll);
+        cnt += keep;
+    }
+    atomicAdd(&cnt_s, cnt);
+    __syncthreads();
+    ClusterReducer red{nullptr, nullptr, 0u, 1u, 0};  // only the block-local parts are used here
+    const double med = median_of(red, row, (size_t)G, (size_t)cnt_s, false, 0.0, hist);
+    if (threadIdx.x == 0) sf_out[n] = exp(med);
+}
+
 // fitted = c0 + c1 / mean (dds.py:1267-1275) from the device-resident coefficients
 __global__ void k_trend_eval(const double* __restrict__ means, size_t n, const TrendOut* __restrict__ c, double* fitted) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -709,6 +749,14 @@ int launch_trend_eval(const LaunchCfg& c, const double* means, size_t n, const d
     k_trend_eval<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(means, n, reinterpret_cast<const TrendOut*>(out16), fitted);
     if (int e = check_launch()) return e;
     return 1;
+}
+
+int launch_size_factors(const LaunchCfg& c, const int64_t* counts, int64_t ld, int N, int G, double* logmeans,
+                        double* scratch, double* sf_out) {
+    k_log_means<<<grid_for(G, c.lgT), kBlock, 0, c.stream>>>(counts, ld, N, G, c.lgT, logmeans);
+    k_size_factor_median<<<N, 1024, 0, c.stream>>>(counts, ld, G, logmeans, scratch, sf_out);
+    if (int e = check_launch()) return e;
+    return 2;
 }
 
 int launch_select_disp(const LaunchCfg& c, const double* gw, const double* mp, const double* fitted, const double* out16,

@@ -144,6 +144,10 @@ class _CudaOps:
                                                             as_f64p(all_zero)))
 
 
+    def size_factors(self, counts, ld, N, G, sf):
+        self._io((counts,), (sf,))
+        self.ctx.check(self.lib.pdq_size_factors(self.ctx.h, as_i64p(counts), ld, N, G, as_f64p(sf)))
+
     def trend_glm(self, cov, targets):
         n = len(cov)
         coeffs = np.empty(2)
@@ -303,6 +307,23 @@ class B200Inference(_InferenceBase):
             raise ValueError("covariates and targets must have the same length")
         coeffs, pred, ok = self._ops.trend_glm(cov, tgt)
         return coeffs, pred, ok
+
+    # ------------------------------------------------------------------ beyond the ABC
+    def size_factors(self, counts):
+        """Median-of-ratios size factors on the device (``preprocessing.deseq2_norm``, preprocessing.py:5-102).
+
+        Not part of the ``Inference`` ABC -- the reference computes them in the orchestrator (``dds.py:584-711``) --
+        but it is the step that precedes the plugin calls.  Returns ``(normed_counts, size_factors)`` like
+        ``deseq2_norm``; raises ``ValueError`` when every gene contains a zero (the reference's cue to switch to its
+        iterative estimator, ``dds.py:682-690``).
+        """
+        counts, ld = _rows(counts, np.int64, "counts")
+        N, G = counts.shape
+        sf = np.empty(N)
+        self._ops.size_factors(counts, ld, N, G, sf)
+        if not np.isfinite(sf).all():
+            raise ValueError("Every gene contains at least one zero, cannot compute log geometric means.")
+        return counts / sf[:, None], sf
 
     def lfc_shrink_nbinom_glm(self, design_matrix, counts, size, offset, prior_no_shrink_scale, prior_scale, optimizer,
                               shrink_index):  # noqa: D102

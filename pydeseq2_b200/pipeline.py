@@ -225,18 +225,42 @@ class ResidentFit:
         self.ctx = ctx
         self.lib = ctx.lib
         self.X = np.ascontiguousarray(X, dtype=np.float64)
-        self.sf = np.ascontiguousarray(size_factors, dtype=np.float64)
         self.N, self.p = self.X.shape
         self.min_mu, self.min_disp, self.beta_tol = min_mu, min_disp, beta_tol
         self.max_disp = max(max_disp, self.N)
         self.comm = comm
-        d = _lib.c_design()
-        ctx.check(self.lib.pdq_design_create(ctx.h, _lib.as_f64p(self.X), _lib.as_f64p(self.sf), self.N, self.p, C.byref(d)))
-        self.design = d
+        self.design = None
+        self.sf = None
+        if size_factors is not None:  # None: median of ratios on the device from the uploaded counts (see upload)
+            self._set_size_factors(size_factors)
         self.lin_branch = lin_mu_branch(self.X)
         self.G = 0
         self._bufs = {}
         self.stage_ms = {}
+
+    def _set_size_factors(self, sf):
+        _lib = self._lib_mod
+        self.sf = np.ascontiguousarray(sf, dtype=np.float64)
+        if self.design:
+            self.lib.pdq_design_destroy(self.ctx.h, self.design)
+        d = _lib.c_design()
+        self.ctx.check(self.lib.pdq_design_create(self.ctx.h, _lib.as_f64p(self.X), _lib.as_f64p(self.sf), self.N, self.p,
+                                                  C.byref(d)))
+        self.design = d
+
+    def device_size_factors(self):
+        """Median-of-ratios size factors from the resident counts (preprocessing.py:31-102); rebuilds the design pack.
+        With gene shards the medians are over the LOCAL genes only -- pass global size factors in that case."""
+        d_sf = self._dev("sf", self.N * 8)
+        self.ctx.check(self.lib.pdq_size_factors_dev(self.ctx.h, self._lib_mod.c_dptr(self.d_counts), self.G, self.N, self.G,
+                                                     self._lib_mod.c_dptr(d_sf), None))
+        sf = np.empty(self.N)
+        self.ctx.d2h(sf, d_sf)
+        self.ctx.sync()
+        if not np.isfinite(sf).all():
+            raise ValueError("Every gene contains at least one zero, cannot compute log geometric means.")
+        self._set_size_factors(sf)
+        return sf
 
     # -- memory --------------------------------------------------------------------------------
     def _dev(self, name, nbytes):
@@ -264,6 +288,8 @@ class ResidentFit:
         self.d_nfb = self._dev("nfb", 64)
         self.ctx.h2d(self.d_counts, counts)
         self.ctx.sync()
+        if self.design is None:
+            self.device_size_factors()
         self._h = {k: self.ctx.pinned_empty((G,)) for k in ("mom", "means", "gw", "gw_conv", "fitted", "map", "map_conv",
                                                               "disp", "conv", "pv", "stat", "se")}
         self._h["beta"] = self.ctx.pinned_empty((G, p))

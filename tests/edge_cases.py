@@ -134,3 +134,26 @@ def check_alpha_grid(inf, force):
     close = np.isclose(a, want, rtol=1e-9)
     assert close.mean() >= 0.9
     assert np.all(np.abs(np.log(a) - np.log(want)) <= 2 * (np.log(max(10, N)) - np.log(1e-8)) / 99 * 2 / 99 + 1e-12)
+
+
+def check_size_factors(inf):
+    """Median-of-ratios on the device: same values as the reference (golden `final_size_factors` of the reference's
+    shipped datasets and seeded inputs), and -- the north star's criterion -- bit-identical RANKS across samples."""
+    from pydeseq2_b200.pipeline import median_of_ratios
+
+    for name in ("tape_single_factor", "tape_continuous", "tape_wide"):
+        t = load_golden(name)
+        normed, sf = inf.size_factors(t["counts"])
+        np.testing.assert_allclose(sf, t["final_size_factors"], rtol=1e-12)
+        np.testing.assert_array_equal(np.argsort(np.argsort(sf)), np.argsort(np.argsort(t["final_size_factors"])))
+    for N, G, seed in ((200, 3000, 0), (37, 501, 1), (8, 64, 2)):
+        counts, _, _ = make_counts(N, G, "two_level", seed)
+        want_normed, want = median_of_ratios(counts)  # numpy restatement of preprocessing.py (== oracle)
+        normed, sf = inf.size_factors(counts)
+        np.testing.assert_allclose(sf, want, rtol=1e-12)
+        np.testing.assert_array_equal(np.argsort(np.argsort(sf)), np.argsort(np.argsort(want)))
+        np.testing.assert_allclose(normed, want_normed, rtol=1e-12)
+    # every gene holds a zero -> ValueError, like dds.fit_size_factors' fallback trigger
+    bad = np.array([[0, 3, 5], [2, 0, 1], [4, 1, 0]], dtype=np.int64)
+    with pytest.raises(ValueError, match="at least one zero"):
+        inf.size_factors(bad)

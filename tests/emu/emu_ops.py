@@ -86,3 +86,6 @@ class EmuOps:
         assert self.lib.emu_trend_fit(_p(means, f64p), _p(gw, f64p), C.c_size_t(len(gw)), 1, C.c_double(lo), C.c_double(hi), 1,
                                       C.c_double(min_disp), C.c_double(trigamma_c), int(with_prior), _p(out, f64p)) == 0
         return out
+
+    def size_factors(self, counts, ld, N, G, sf):
+        assert self.lib.emu_size_factors(_p(counts, i64p), C.c_int64(ld), N, G, _p(sf, f64p)) == 0

@@ -192,6 +192,28 @@ int emu_trend_fit(const double* x, const double* t, size_t n, int x_is_mean, dou
     return 0;
 }
 
+// median-of-ratios size factors with the device's selection code (k_log_means + k_size_factor_median, one "thread")
+int emu_size_factors(const int64_t* counts, int64_t ld, int N, int G, double* sf) {
+    std::vector<double> lm((size_t)G), row((size_t)G);
+    for (int g = 0; g < G; ++g) {
+        double s = 0.0;
+        for (int n = 0; n < N; ++n) s += log((double)counts[(size_t)n * ld + g]);
+        lm[g] = s / (double)N;
+    }
+    unsigned hist[258];
+    SerialReducer red;
+    for (int n = 0; n < N; ++n) {
+        size_t cnt = 0;
+        for (int g = 0; g < G; ++g) {
+            const bool keep = fabs(lm[g]) <= 1.7976931348623157e308;
+            row[g] = keep ? log((double)counts[(size_t)n * ld + g]) - lm[g] : (0.0 / 0.0);
+            cnt += keep;
+        }
+        sf[n] = exp(median_of(red, row.data(), (size_t)G, cnt, false, 0.0, hist));
+    }
+    return 0;
+}
+
 long emu_eval_count(int reset) {
     long v = g_emu_alpha_evals;
     if (reset) g_emu_alpha_evals = 0;

@@ -40,3 +40,7 @@ def test_irls_optimizer_branch(backend):
 def test_alpha_grid_fallback(backend):
     inf, ops = backend
     ec.check_alpha_grid(inf, lambda on: setattr(ops, "force_grid", int(on)))
+
+
+def test_size_factors(backend):
+    ec.check_size_factors(backend[0])

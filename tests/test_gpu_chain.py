@@ -83,6 +83,11 @@ def test_resident_driver_equals_host_buffer_driver(inf, N, G, kind):
     np.testing.assert_allclose(r["lfc"], host.lfc, rtol=1e-6, atol=1e-10)
     np.testing.assert_allclose(r["stat"], host.stat, rtol=1e-6, atol=1e-10)
     np.testing.assert_allclose(r["pvalue"], host.pvalue, rtol=1e-5, atol=1e-300)
+    rf_auto = ResidentFit(inf._ops.ctx, X, None)  # size factors by median of ratios on the device
+    rf_auto.upload(counts)
+    np.testing.assert_allclose(rf_auto.sf, sf, rtol=1e-12)
+    np.testing.assert_array_equal(np.argsort(rf_auto.sf), np.argsort(sf))
+    rf_auto.close()
     r2 = rf.run(fit_type="mean")  # trimmed-mean trend: host fallback path of the resident driver
     host2 = fit_host(counts, X, inf, size_factors=sf, fit_type="mean")
     np.testing.assert_allclose(r2["dispersions"], host2.dispersions, rtol=1e-6)

@@ -56,3 +56,7 @@ def test_design_too_large_is_reported(inf):
     X = np.ones((10, 9))
     with pytest.raises(B200Error, match="p <= 8"):
         inf.lin_reg_mu(np.ones((10, 3), dtype=np.int64), np.ones(10), X, 0.5)
+
+
+def test_size_factors(inf):
+    ec.check_size_factors(inf)
