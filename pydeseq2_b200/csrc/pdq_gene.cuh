@@ -126,6 +126,35 @@ PDQ_HD void linmu_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pi
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small-count tables shared by irls (lgamma) and alpha_mle (digamma): per gene, f(r + k) for k < kPsiK is built from
+// f(r) by the recurrence (one log / reciprocal per entry, split over the gene's lanes and stitched with an exclusive
+// scan); counts below kPsiK then cost one shared-memory read, and larger counts always satisfy the z >= 10
+// precondition of the unshifted Stirling series.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPsiK = 32;
+
+// log(k!) for k < kPsiK
+PDQ_CONST double kLogFact[kPsiK] = {0.0, 0.0, 0.693147180559945, 1.7917594692280554, 3.178053830347945, 4.787491742782047, 6.579251212010102, 8.525161361065415, 10.604602902745249, 12.801827480081467, 15.104412573075514, 17.502307845873887, 19.987214495661885, 22.55216385312342, 25.191221182738683, 27.89927138384089, 30.671860106080672, 33.50507345013689, 36.39544520803305, 39.339884187199495, 42.335616460753485, 45.38013889847691, 48.47118135183522, 51.60667556776438, 54.78472939811232, 58.00360522298052, 61.26170176100201, 64.55753862700634, 67.88974313718153, 71.257038967168, 74.65823634883017, 78.0922235533153};
+
+PDQ_HD void build_lgamma_table(const Group& grp, double* tab, double r) {
+    const int seg = kPsiK / grp.T;  // T in {1,...,32} divides 32
+    const int k0 = grp.si * seg;
+    double part = 0.0;
+    for (int k = k0; k < k0 + seg; ++k) {
+        const double lg = fast_log(r + (double)k);
+        tab[k] = lg;
+        part += lg;
+    }
+    double run = lgamma_pos(r) + grp.excl_scan(part);
+    for (int k = k0; k < k0 + seg; ++k) {
+        const double lg = tab[k];
+        tab[k] = run;  // lgamma(r + k) = lgamma(r) + sum_{j<k} log(r + j)
+        run += lg;
+    }
+    grp.sync();
+}
+
 // =============================================================================================
 // (a1) irls -- utils.py:273-438.
 // =============================================================================================
@@ -210,29 +239,49 @@ constexpr int kIrlsNeedsOptimizer = 1;  // left through utils.py:374 (|beta|>max
 template <int P>
 PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pinv, const IrlsParams& prm,
                       const int64_t* y, int64_t ld, double alpha, double* beta_out, double* mu_out,
-                      double* hat_out, int64_t ld_out, double* conv_out, int* status_out, bool valid) {
+                      double* hat_out, int64_t ld_out, double* conv_out, int* status_out, bool valid, double* lg_tab,
+                      const double* logfact) {
+    // lg_tab: kPsiK doubles of per-gene scratch (shared memory); logfact: log(k!) table, k < kPsiK (shared memory)
     const double r = 1.0 / alpha;
     const double Nd = (double)d.N;
     const double log_min_mu = log(prm.min_mu);
+    const bool tab_ok = (r > 0.0) && (r < 1e300);  // NaN / non-positive dispersion: plain lgamma path, IEEE semantics
+    grp.sync();
+    if (tab_ok) build_lgamma_table(grp, lg_tab, r);
 
     // ---- start value (utils.py:349-357) and the mu-independent part of nb_nll ----------------
     double v[P];
 #pragma unroll
     for (int j = 0; j < P; ++j) v[j] = 0.0;
     double lgsum = 0.0, logmean = 0.0;
-    for (int n = grp.si; n < d.N; n += grp.T) {
+    const int trips = (d.N + grp.T - 1) / grp.T;  // uniform across the warp: the loop body votes
+    for (int it = 0, n = grp.si; it < trips; ++it, n += grp.T) {
+        const bool in = n < d.N;
+        const int nn = in ? n : 0;
         double x[P];
-        load_x<P>(d, n, x);
-        const double yv = (double)y[n * ld];
-        const double q = fast_div(yv, d.sf[n]);
+        load_x<P>(d, nn, x);
+        const long long yi = y[nn * ld];
+        const double yv = (double)yi;
+        const double q = fast_div(yv, d.sf[nn]);
+        double t;
         if (prm.full_rank) {
-            const double t = fast_log(q + 0.1);
+            t = fast_log(q + 0.1);
 #pragma unroll
-            for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
+            for (int j = 0; j < P; ++j) v[j] = fma(x[j], in ? t : 0.0, v[j]);
         } else {
-            logmean += fast_log(q);
+            t = fast_log(q);
+            logmean += in ? t : 0.0;
         }
-        lgsum += lgamma_pos(yv + 1.0) - lgamma_pos(yv + r);
+        // lgamma(y + 1) - lgamma(y + r): table reads for small counts, unshifted Stirling series otherwise
+        const bool small = tab_ok && yi >= 0 && yi < kPsiK;
+        double term = small ? logfact[(int)(yi & (kPsiK - 1))] - lg_tab[(int)(yi & (kPsiK - 1))] : 0.0;
+        if (grp.any(in && !small)) {
+            const double z1 = small ? 40.0 : yv + 1.0, zr = small ? 40.0 : yv + r;
+            const double big = tab_ok ? lgamma_asym(z1, fast_log(z1)) - lgamma_asym(zr, fast_log(zr))
+                                      : lgamma_pos(yv + 1.0) - lgamma_pos(yv + r);
+            term = small ? term : big;
+        }
+        lgsum += in ? term : 0.0;
     }
     group_sum_vec<P>(grp, v);
     lgsum = grp.sum(lgsum);
@@ -550,12 +599,7 @@ struct AlphaParams {
     int cr_reg, prior_reg;
 };
 
-// psi(r + k), k = 0..kPsiK-1, per gene and per evaluation, in shared memory: psi(r+k) = psi(r) + sum_{j<k} 1/(r+j).
-// The lanes of the gene split the reciprocals into contiguous segments and stitch them with an exclusive scan.
-// Samples with count < kPsiK then cost one table read instead of a shifted asymptotic series, and counts >= kPsiK
-// always satisfy the z >= 10 precondition of the unshifted series.
-constexpr int kPsiK = 32;
-
+// psi(r + k), k < kPsiK, per gene and per evaluation: psi(r+k) = psi(r) + sum_{j<k} 1/(r+j)  (see the table note above)
 PDQ_HD void build_psi_table(const Group& grp, double* tab, double r) {
     const int seg = kPsiK / grp.T;              // T in {1,...,32} divides 32
     const int k0 = grp.si * seg;

@@ -160,10 +160,16 @@ __global__ void __launch_bounds__(kBlock, PDQ_IRLS_MINB) k_irls(const __grid_con
     Group grp;
     int g;
     bool valid;
+    // behind the design pack and its mbarrier: log(k!) table, then one lgamma(r + k) table per gene of the warp's tile
+    double* logfact = reinterpret_cast<double*>(smem + (size_t)(P + 2) * a.dv.Npad * 8 + 16);
+    if (threadIdx.x < kPsiK) logfact[threadIdx.x] = kLogFact[threadIdx.x];
+    __syncthreads();
+    const int gpw = 32 >> a.lgT;
+    double* lg_tab = logfact + kPsiK + (size_t)((threadIdx.x >> 5) * gpw + ((threadIdx.x & 31) & (gpw - 1))) * kPsiK;
     while (next_tile(a.ticket, a.lgT, a.G, grp, g, valid)) {
         int st = 0;
         irls_gene<P>(grp, d, a.pinv, a.prm, a.counts + g, a.ld, a.disp[g], a.beta + (int64_t)g * P, a.mu + g, a.hat + g,
-                     a.ld_out, a.conv + g, &st, valid);
+                     a.ld_out, a.conv + g, &st, valid, lg_tab, logfact);
         if (valid && grp.si == 0) {
             if (a.force) st = kIrlsNeedsOptimizer;
             a.status[g] = st;
@@ -627,10 +633,11 @@ int launch_irls(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, i
                       IrlsParams{h.min_mu, h.beta_tol, h.min_beta, h.max_beta, h.maxiter, d.full_rank},
                       counts, ld, G, c.lgT, disp, beta, mu, hat, conv, ld_out, status, n_fallback, c.tickets,
                       (c.debug & PDQ_DEBUG_FORCE_IRLS_OPTIMIZER) ? 1 : 0};
-        if (int e = prep(k_irls<P>, d.smem_bytes)) return e;
+        const size_t smem_irls = d.smem_bytes + (size_t)(1 + kWarps * (32 >> c.lgT)) * kPsiK * sizeof(double);
+        if (int e = prep(k_irls<P>, smem_irls)) return e;
         if (int e = prep(k_irls_optimizer<P>, d.smem_bytes)) return e;
         if (cudaMemsetAsync(c.tickets, 0, sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;
-        k_irls<P><<<persistent_grid(k_irls<P>, d.smem_bytes, c.sm_count, G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+        k_irls<P><<<persistent_grid(k_irls<P>, smem_irls, c.sm_count, G, c.lgT), kBlock, smem_irls, c.stream>>>(a);
         k_irls_optimizer<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });
     if (int e = check_launch()) return e;

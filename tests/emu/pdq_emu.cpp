@@ -91,9 +91,10 @@ int emu_irls(const int64_t* counts, int64_t ld, int N, int G, const double* sf, 
     EMU_DISPATCH(p, {
         const SmallMat<P> pi = pinv_of<P>(k);
         const IrlsParams prm{min_mu, beta_tol, min_beta, max_beta, maxiter, k.full_rank};
+        double lg_tab[kPsiK];
         for (int g = 0; g < G; ++g) {
             irls_gene<P>(kOne, k.d, pi, prm, counts + g, ld, disp[g], beta + (size_t)g * P, mu + g, hat + g, G, conv + g,
-                         status + g, true);
+                         status + g, true, lg_tab, kLogFact);
             if (force_optimizer) status[g] = kIrlsNeedsOptimizer;
             if (status[g] == kIrlsNeedsOptimizer)
                 irls_optimizer_gene<P>(kOne, k.d, pi, prm, counts + g, ld, disp[g], beta + (size_t)g * P, mu + g, hat + g,
