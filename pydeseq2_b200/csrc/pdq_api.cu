@@ -406,12 +406,11 @@ extern "C" int pdq_trend_fit_dev(pdq_ctx* c, const double* means, const double* 
                                  double trigamma_c, double* out16, double* fitted) {
     CHECK_CTX(c);
     if (!means || !genewise || !out16 || n == 0) return fail(c, PDQ_ERR_INVALID, "pdq_trend_fit_dev: bad arguments");
-    void *keep, *res;
-    if (int e = ensure(c, kBufKeep, n, &keep)) return e;
-    if (int e = ensure(c, kBufRes, n * 8, &res)) return e;
+    void* scratch;
+    if (int e = ensure(c, kBufRes, 3 * n * 8, &scratch)) return e;
     LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets, c->debug};
-    if (int e = done(c, launch_trend_fit(lc, means, genewise, (unsigned char*)keep, n, 1, min_disp, max_disp, 1, min_disp, trigamma_c, 1,
-                                         (double*)res, out16), "trend_fit"))
+    if (int e = done(c, launch_trend_fit(lc, means, genewise, (double*)scratch, n, 1, min_disp, max_disp, 1, min_disp, trigamma_c, 1, out16),
+                     "trend_fit"))
         return e;
     if (fitted) return done(c, launch_trend_eval(lc, means, n, out16, fitted), "trend_eval");
     return PDQ_OK;
@@ -687,17 +686,16 @@ extern "C" int pdq_dispersion_trend_gamma_glm(pdq_ctx* c, const double* cov, con
     CHECK_CTX(c);
     if (!cov || !targets || !coeffs_out || !pred_out || !converged_out || n == 0)
         return fail(c, PDQ_ERR_INVALID, "pdq_dispersion_trend_gamma_glm: bad arguments");
-    void *dx, *dt, *keep, *dout;
+    void *dx, *dt, *scratch, *dout;
     if (int e = ensure(c, kBufC, n * 8, &dx)) return e;
     if (int e = ensure(c, kBufD, n * 8, &dt)) return e;
-    if (int e = ensure(c, kBufKeep, n, &keep)) return e;
+    if (int e = ensure(c, kBufRes, 3 * n * 8, &scratch)) return e;
     if (int e = ensure(c, kBufMisc, 256, &dout)) return e;
     CU(c, cudaMemcpyAsync(dx, cov, n * 8, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(dt, targets, n * 8, cudaMemcpyHostToDevice, c->stream));
     LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets, c->debug};
     const double inf = 1.0 / 0.0;
-    if (int e = done(c, launch_trend_fit(lc, (const double*)dx, (const double*)dt, (unsigned char*)keep, n, 0, -inf, inf, 0, 0.0, 0.0, 0, nullptr,
-                                         (double*)dout),
+    if (int e = done(c, launch_trend_fit(lc, (const double*)dx, (const double*)dt, (double*)scratch, n, 0, -inf, inf, 0, 0.0, 0.0, 0, (double*)dout),
                      "dispersion_trend_gamma_glm"))
         return e;
     double out[16];

@@ -52,9 +52,8 @@ int launch_mom_from_counts(const LaunchCfg&, const DesignDev&, const int64_t* co
                            double min_disp, double max_disp, double* alpha, double* normed_mean);
 int launch_mu_from_lfc(const LaunchCfg&, const DesignDev&, const double* lfc, int G, double* mu, int64_t ld_out);
 
-int launch_trend_fit(const LaunchCfg&, const double* x, const double* t, unsigned char* keep, size_t n, int x_is_mean,
-                     double lo, double hi, int outer, double min_disp, double trigamma_c, int with_prior, double* res,
-                     double* out16);
+int launch_trend_fit(const LaunchCfg&, const double* x, const double* t, double* scratch3n, size_t n, int x_is_mean,
+                     double lo, double hi, int outer, double min_disp, double trigamma_c, int with_prior, double* out16);
 int launch_trend_eval(const LaunchCfg&, const double* means, size_t n, const double* out16, double* fitted);
 int launch_size_factors(const LaunchCfg&, const int64_t* counts, int64_t ld, int N, int G, double* logmeans,
                         double* scratch, double* sf_out);

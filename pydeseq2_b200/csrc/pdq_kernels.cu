@@ -488,16 +488,18 @@ struct ClusterReducer {
 };
 
 __global__ void __launch_bounds__(1024) k_trend_prior(const double* __restrict__ x, const double* __restrict__ t,
-                                                      unsigned char* keep, size_t n, int x_is_mean, double lo, double hi,
-                                                      int outer, double min_disp, double trigamma_c, int with_prior,
-                                                      double* res, TrendOut* out) {
+                                                      double* scratch /* 3 n doubles: xs | ts | res */, size_t n,
+                                                      int x_is_mean, double lo, double hi, int outer, double min_disp,
+                                                      double trigamma_c, int with_prior, TrendOut* out) {
     __shared__ double warp_part[32 * kTrendK];
     __shared__ double slots[2 * kTrendMaxCluster * kTrendK];
     __shared__ unsigned hist[258];
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     ClusterReducer red{warp_part, slots, cluster.block_rank(), cluster.num_blocks(), 0};
-    TrendOut o = trend_fit_outer(red, x, t, keep, n, x_is_mean != 0, lo, hi, outer != 0);
+    double *xs = scratch, *ts = scratch + n, *res = scratch + 2 * n;
+    trend_prepare(red, x, t, n, x_is_mean != 0, lo, hi, xs, ts);
+    TrendOut o = trend_fit_outer(red, xs, ts, n, outer != 0);
     if (with_prior && o.status == 0.0) trend_prior(red, x, t, n, lo, hi, min_disp, trigamma_c, res, hist, o);
     if (red.tid() == 0) *out = o;
     cluster.sync();  // no block may exit while peers can still address its shared memory
@@ -727,12 +729,19 @@ int launch_mu_from_lfc(const LaunchCfg& c, const DesignDev& d, const double* lfc
     return 1;
 }
 
-int launch_trend_fit(const LaunchCfg& c, const double* x, const double* t, unsigned char* keep, size_t n, int x_is_mean,
-                     double lo, double hi, int outer, double min_disp, double trigamma_c, int with_prior, double* res,
-                     double* out16) {
-    // cluster size: enough blocks for ~4 elements per thread, at most 8 (portable) -- the vectors are G-length
+int launch_trend_fit(const LaunchCfg& c, const double* x, const double* t, double* scratch3n, size_t n, int x_is_mean,
+                     double lo, double hi, int outer, double min_disp, double trigamma_c, int with_prior, double* out16) {
+    // cluster size: enough blocks for ~4 elements per thread; 8 is the portable maximum, 16 needs the opt-in attribute
+    static int max_cluster = 0;
+    if (!max_cluster) {
+        max_cluster = 8;
+        if (cudaFuncSetAttribute(k_trend_prior, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)
+            max_cluster = kTrendMaxCluster;
+        else
+            cudaGetLastError();
+    }
     unsigned nb = 1;
-    while (nb < 8 && (size_t)nb * 1024 * 4 < n) nb <<= 1;
+    while ((int)nb < max_cluster && (size_t)nb * 1024 * 4 < n) nb <<= 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nb, 1, 1);
     cfg.blockDim = dim3(1024, 1, 1);
@@ -745,9 +754,17 @@ int launch_trend_fit(const LaunchCfg& c, const double* x, const double* t, unsig
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, k_trend_prior, x, t, keep, n, x_is_mean, lo, hi, outer, min_disp, trigamma_c, with_prior, res,
-                           reinterpret_cast<TrendOut*>(out16)) != cudaSuccess)
-        return PDQ_ERR_CUDA;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, k_trend_prior, x, t, scratch3n, n, x_is_mean, lo, hi, outer, min_disp, trigamma_c,
+                                         with_prior, reinterpret_cast<TrendOut*>(out16));
+    if (err != cudaSuccess && nb > 8) {  // a 16-block cluster could not be placed: fall back to the portable size
+        cudaGetLastError();
+        max_cluster = 8;
+        attr[0].val.clusterDim.x = 8;
+        cfg.gridDim = dim3(8, 1, 1);
+        err = cudaLaunchKernelEx(&cfg, k_trend_prior, x, t, scratch3n, n, x_is_mean, lo, hi, outer, min_disp, trigamma_c, with_prior,
+                                 reinterpret_cast<TrendOut*>(out16));
+    }
+    if (err != cudaSuccess) return PDQ_ERR_CUDA;
     if (int e = check_launch()) return e;
     return 1;
 }

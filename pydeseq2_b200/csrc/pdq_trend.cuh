@@ -13,6 +13,7 @@
 
 #include <string.h>
 
+#include "pdq_fast.cuh"
 #include "pdq_math.cuh"
 
 namespace pdq {
@@ -56,29 +57,27 @@ struct TrendSums {
     double L, g0, g1, h00, h01, h11, f00, f01, f11, n;
 };
 
-// x[i]: covariate (1/mean) or the mean itself when `x_is_mean`; t[i]: genewise dispersion (clipped to [lo, hi]).
+// xs[i]: covariate; ts[i]: target, NaN when the gene is not (or no longer) part of the fit.  Both are prepared once per
+// launch by trend_prepare (clip, 1/mean, validity), so that a pass is: two loads, one reciprocal, one log, ten sums.
 template <class R>
-PDQ_HD TrendSums trend_sums(R& red, const double* x, const double* t, const unsigned char* keep, size_t n, bool x_is_mean,
-                            double lo, double hi, double c0, double c1) {
+PDQ_HD TrendSums trend_sums(R& red, const double* xs, const double* ts, size_t n, double c0, double c1) {
     double L = 0, g0 = 0, g1 = 0, h00 = 0, h01 = 0, h11 = 0, f00 = 0, f01 = 0, f11 = 0, cnt = 0;
     for (size_t i = red.tid(); i < n; i += red.nthreads()) {
-        if (!keep[i]) continue;
-        const double xv = x_is_mean ? 1.0 / x[i] : x[i];
-        double tv = t[i];
-        tv = (tv < lo) ? lo : ((tv > hi) ? hi : tv);
-        if (!(tv == tv)) continue;  // np.nanmean skips NaN targets
+        const double tv = ts[i];
+        if (!(tv == tv)) continue;  // dropped gene / np.nanmean skips NaN targets
+        const double xv = xs[i];
         const double m = fma(c1, xv, c0);
-        const double im = 1.0 / m;
+        const double im = fast_rcp(m);
         const double r = tv * im;
-        L += r + log(m);
-        const double gi = -(r - 1.0) * im;          // d/dm (t/m + log m) = (1 - t/m)/m
+        L += r + fast_log(m);
+        const double gi = -(r - 1.0) * im;             // d/dm (t/m + log m) = (1 - t/m)/m
         g0 += gi;
         g1 += gi * xv;
         const double hi2 = (2.0 * r - 1.0) * im * im;  // d2/dm2
         h00 += hi2;
         h01 += hi2 * xv;
         h11 += hi2 * xv * xv;
-        const double fi = im * im;                  // expected (Fisher) curvature
+        const double fi = im * im;                     // expected (Fisher) curvature
         f00 += fi;
         f01 += fi * xv;
         f11 += fi * xv * xv;
@@ -94,35 +93,17 @@ PDQ_HD TrendSums trend_sums(R& red, const double* x, const double* t, const unsi
     return s;
 }
 
+// One GLM fit; returns true when converged.  Starts from the incoming (c0, c1): (1, 1) for the first round like the
+// reference (default_inference.py:221); later rounds of the outer loop warm-start from the previous optimum -- the
+// minimiser does not depend on the start, only the iteration count does.  Every trial point costs ONE pass: the sums at
+// the candidate serve both the Armijo test and, once accepted, the next Newton direction.
 template <class R>
-PDQ_HD double trend_loss(R& red, const double* x, const double* t, const unsigned char* keep, size_t n, bool x_is_mean,
-                         double lo, double hi, double c0, double c1) {
-    double L = 0;
-    for (size_t i = red.tid(); i < n; i += red.nthreads()) {
-        if (!keep[i]) continue;
-        const double xv = x_is_mean ? 1.0 / x[i] : x[i];
-        double tv = t[i];
-        tv = (tv < lo) ? lo : ((tv > hi) ? hi : tv);
-        if (!(tv == tv)) continue;
-        const double m = fma(c1, xv, c0);
-        L += tv / m + log(m);
-    }
-    red.sum_many(&L, 1);
-    return L;
-}
-
-// one GLM fit from (1, 1); returns true when converged
-template <class R>
-PDQ_HD bool trend_fit_once(R& red, const double* x, const double* t, const unsigned char* keep, size_t n, bool x_is_mean,
-                           double lo, double hi, double& c0, double& c1, double& loss, int& iters) {
-    // Starts from the incoming (c0, c1): (1, 1) for the first round like the reference (default_inference.py:221);
-    // later rounds of the outer loop warm-start from the previous optimum -- the minimiser does not depend on the
-    // start, only the iteration count does.
+PDQ_HD bool trend_fit_once(R& red, const double* xs, const double* ts, size_t n, double& c0, double& c1, double& loss,
+                           int& iters) {
     const double kLB = 1e-12;  // bounds=[(1e-12, inf)] (default_inference.py:224)
-    bool ok = false;
+    TrendSums s = trend_sums(red, xs, ts, n, c0, c1);
+    ++iters;
     for (int it = 0; it < 200; ++it) {
-        ++iters;
-        const TrendSums s = trend_sums(red, x, t, keep, n, x_is_mean, lo, hi, c0, c1);
         loss = s.L / s.n;
         if (!(s.L == s.L) || s.n < 2.0) return false;
         // variables held at the lower bound with the gradient pushing outward are fixed
@@ -132,10 +113,8 @@ PDQ_HD bool trend_fit_once(R& red, const double* x, const double* t, const unsig
             double a = s.h00, b = s.h01, d = s.h11;
             const bool pd = (a > 0.0) && (a * d - b * b > 1e-12 * a * d);
             if (!pd) { a = s.f00; b = s.f01; d = s.f11; }  // Fisher scoring: always positive definite
-            if (fix0 && fix1) {
-                ok = true;
-                break;
-            } else if (fix0) {
+            if (fix0 && fix1) return true;
+            if (fix0) {
                 d1 = -s.g1 / d;
             } else if (fix1) {
                 d0 = -s.g0 / a;
@@ -145,50 +124,51 @@ PDQ_HD bool trend_fit_once(R& red, const double* x, const double* t, const unsig
                 d1 = -(a * s.g1 - b * s.g0) / det;
             }
         }
-        // Close to the minimiser (tiny Newton decrement) the summed loss can no longer resolve progress in FP64, but
-        // the Newton step itself still can: take it without a line search (quadratic convergence, Hessian PD here).
-        double n0 = c0, n1 = c1, Ln = s.L;
-        const double dec = -(s.g0 * d0 + s.g1 * d1);
-        if (dec <= 1e-9 * fabs(s.L)) {
-            n0 = fmax(c0 + d0, kLB);
-            n1 = fmax(c1 + d1, kLB);
-        } else {
-            // backtracking on the loss, projecting onto c >= 1e-12
-            double step = 1.0;
-            bool acc = false;
-            for (int ls = 0; ls < 40; ++ls) {
-                n0 = fmax(fma(step, d0, c0), kLB);
-                n1 = fmax(fma(step, d1, c1), kLB);
-                Ln = trend_loss(red, x, t, keep, n, x_is_mean, lo, hi, n0, n1);
-                if (Ln <= s.L + 1e-4 * (s.g0 * (n0 - c0) + s.g1 * (n1 - c1))) {
-                    acc = true;
-                    break;
-                }
-                step *= 0.5;
+        const double dec = -(s.g0 * d0 + s.g1 * d1);           // Newton decrement (>= 0 for a descent direction)
+        const bool endgame = dec <= 1e-9 * fabs(s.L);           // the summed loss no longer resolves progress in FP64
+        double step = 1.0, n0 = c0, n1 = c1;
+        TrendSums sn = s;
+        bool acc = false;
+        for (int ls = 0; ls < 40; ++ls) {
+            n0 = fmax(fma(step, d0, c0), kLB);
+            n1 = fmax(fma(step, d1, c1), kLB);
+            sn = trend_sums(red, xs, ts, n, n0, n1);
+            ++iters;
+            if (endgame || sn.L <= s.L + 1e-4 * (s.g0 * (n0 - c0) + s.g1 * (n1 - c1))) {
+                acc = true;
+                break;
             }
-            if (!acc) return false;
+            step *= 0.5;
         }
+        if (!acc || !(sn.L == sn.L)) return false;
         const double rel = fmax(fabs(n0 - c0) / fmax(fabs(n0), 1e-300), fabs(n1 - c1) / fmax(fabs(n1), 1e-300));
         c0 = n0;
         c1 = n1;
-        loss = Ln / s.n;
-        if (rel < 1e-12 || (dec <= 1e-9 * fabs(s.L) && rel < 1e-9 && it > 60)) {
-            ok = true;
-            break;
-        }
+        s = sn;
+        loss = s.L / s.n;
+        if (rel < 1e-12 || (endgame && rel < 1e-9 && it > 60)) return true;
     }
-    return ok;
+    return false;
 }
 
-// Full outer loop of dds.py:1199-1275.  `keep` (n bytes, scratch) holds the genes still in the fit.
+// validity, clipping and the covariate are resolved once: xs / ts are n doubles of scratch each
 template <class R>
-PDQ_HD TrendOut trend_fit_outer(R& red, const double* x, const double* t, unsigned char* keep, size_t n, bool x_is_mean,
-                                double lo, double hi, bool outer) {
+PDQ_HD void trend_prepare(R& red, const double* x, const double* t, size_t n, bool x_is_mean, double lo, double hi,
+                          double* xs, double* ts) {
     for (size_t i = red.tid(); i < n; i += red.nthreads()) {
         const double xv = x_is_mean ? 1.0 / x[i] : x[i];
-        keep[i] = (xv == xv) && (fabs(xv) <= 1.7976931348623157e308);  // drop inf / NaN covariates (dds.py:1225-1232)
+        double tv = t[i];
+        tv = (tv < lo) ? lo : ((tv > hi) ? hi : tv);
+        const bool ok = (xv == xv) && (fabs(xv) <= 1.7976931348623157e308);  // drop inf / NaN covariates (dds.py:1225-1232)
+        xs[i] = xv;
+        ts[i] = ok ? tv : (0.0 / 0.0);
     }
     red.sync();
+}
+
+// Full outer loop of dds.py:1199-1275 on the prepared vectors; ts[i] is set to NaN when gene i is dropped.
+template <class R>
+PDQ_HD TrendOut trend_fit_outer(R& red, const double* xs, double* ts, size_t n, bool outer) {
     double o0 = 0.1, o1 = 0.1, c0 = 1.0, c1 = 1.0, loss = 0.0;
     int rounds = 0, iters = 0;
     bool failed = false, last_conv = false;
@@ -197,7 +177,7 @@ PDQ_HD TrendOut trend_fit_outer(R& red, const double* x, const double* t, unsign
         if (!(c0 > 1e-10 && c1 > 1e-10) || !(l0 * l0 + l1 * l1 >= 1e-6)) break;  // dds.py:1236-1238
         o0 = c0;
         o1 = c1;
-        const bool conv = trend_fit_once(red, x, t, keep, n, x_is_mean, lo, hi, c0, c1, loss, iters);
+        const bool conv = trend_fit_once(red, xs, ts, n, c0, c1, loss, iters);
         ++rounds;
         last_conv = conv;
         if (!conv || c0 <= 1e-10 || c1 <= 1e-10) {  // dds.py:1243-1252 -> mean trend
@@ -205,19 +185,17 @@ PDQ_HD TrendOut trend_fit_outer(R& red, const double* x, const double* t, unsign
             break;
         }
         if (!outer) break;
-        // drop genes far from the curve before refitting (dds.py:1255-1265); uses the UNclipped-by-us genewise values
+        // drop genes far from the curve before refitting (dds.py:1255-1265)
         for (size_t i = red.tid(); i < n; i += red.nthreads()) {
-            if (!keep[i]) continue;
-            const double xv = x_is_mean ? 1.0 / x[i] : x[i];
-            double tv = t[i];
-            tv = (tv < lo) ? lo : ((tv > hi) ? hi : tv);
-            const double ratio = tv / fma(c1, xv, c0);
-            if (ratio < 1e-4 || ratio >= 15.0) keep[i] = 0;
+            const double tv = ts[i];
+            if (!(tv == tv)) continue;
+            const double ratio = tv / fma(c1, xs[i], c0);
+            if (ratio < 1e-4 || ratio >= 15.0) ts[i] = 0.0 / 0.0;
         }
         red.sync();
     }
     double used = 0.0;
-    for (size_t i = red.tid(); i < n; i += red.nthreads()) used += keep[i] ? 1.0 : 0.0;
+    for (size_t i = red.tid(); i < n; i += red.nthreads()) used += (ts[i] == ts[i]) ? 1.0 : 0.0;
     red.sum_many(&used, 1);
     TrendOut o;  // identical in every thread (all decisions were taken on block/cluster-wide sums)
     o.c0 = c0;
