@@ -415,8 +415,61 @@ struct ClusterReducer {
         cooperative_groups::this_cluster().sync();
 #endif
     }
-    // warp 0 scans the 256-bin histogram (8 bins per lane + shuffle scan) and publishes digit / count-before in hist[256..257]
-    __host__ __device__ void find_bin(unsigned* hist, size_t k, int& d, size_t& cum) {
+    // cluster-wide maximum of one value per thread (same exchange pattern as sum_many)
+    __host__ __device__ double max_one(double v) {
+#if defined(__CUDA_ARCH__)
+        namespace cg = cooperative_groups;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+        if (lane == 0) warp_part[warp * kTrendK] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m = warp_part[0];
+            const int nw = blockDim.x >> 5;
+            for (int w = 1; w < nw; ++w) m = fmax(m, warp_part[w * kTrendK]);
+            if (nblocks > 1) {
+                cg::cluster_group cluster = cg::this_cluster();
+                for (unsigned r = 0; r < nblocks; ++r)
+                    cluster.map_shared_rank(slots, r)[(parity * kTrendMaxCluster + rank) * kTrendK] = m;
+            } else {
+                slots[parity * kTrendMaxCluster * kTrendK] = m;
+            }
+        }
+        if (nblocks > 1) cg::this_cluster().sync(); else __syncthreads();
+        double m = slots[parity * kTrendMaxCluster * kTrendK];
+        for (unsigned r = 1; r < nblocks; ++r) m = fmax(m, slots[(parity * kTrendMaxCluster + r) * kTrendK]);
+        parity ^= 1;
+        return m;
+#else
+        return v;
+#endif
+    }
+    // histogram protocol of select_kth: zeroed bins become visible, blocks count disjoint slices, bins are merged
+    __host__ __device__ void hist_begin() {
+#if defined(__CUDA_ARCH__)
+        if (nblocks > 1) cooperative_groups::this_cluster().sync(); else __syncthreads();
+#endif
+    }
+    __host__ __device__ unsigned* hist_merge(unsigned* hist) {
+#if defined(__CUDA_ARCH__)
+        __syncthreads();  // local bins complete
+        if (nblocks == 1) return hist;
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        if (threadIdx.x < 256) {
+            const unsigned v = hist[threadIdx.x];
+            if (v)
+                for (unsigned r = 0; r < nblocks; ++r) atomicAdd(cluster.map_shared_rank(hist + 256, r) + threadIdx.x, v);
+        }
+        cluster.sync();
+        return hist + 256;
+#else
+        return hist;
+#endif
+    }
+    // warp 0 scans the 256-bin histogram (8 bins per lane + shuffle scan) and publishes digit / count-before in out[0..1]
+    __host__ __device__ void find_bin(const unsigned* hist, unsigned* out, size_t k, int& d, size_t& cum) {
 #if defined(__CUDA_ARCH__)
         if (threadIdx.x < 32) {
             const int lane = threadIdx.x;
@@ -441,15 +494,15 @@ struct ClusterReducer {
                     if (run + c[j] > kk) break;
                     run += c[j];
                 }
-                hist[256] = (unsigned)(lane * 8 + j);
-                hist[257] = run;
+                out[0] = (unsigned)(lane * 8 + j);
+                out[1] = run;
             }
         }
         __syncthreads();
-        d = (int)hist[256];
-        cum = hist[257];
+        d = (int)out[0];
+        cum = out[1];
 #else
-        (void)hist; (void)k; (void)d; (void)cum;
+        (void)hist; (void)out; (void)k; (void)d; (void)cum;
 #endif
     }
     __host__ __device__ void sum_many(double* v, int k) {
@@ -468,12 +521,16 @@ struct ClusterReducer {
             double tot = 0.0;
             const int nw = blockDim.x >> 5;
             for (int w = 0; w < nw; ++w) tot += warp_part[w * kTrendK + threadIdx.x];
-            for (unsigned r = 0; r < nblocks; ++r) {
-                double* remote = cluster.map_shared_rank(slots, r);
-                remote[(parity * kTrendMaxCluster + rank) * kTrendK + threadIdx.x] = tot;
+            if (nblocks > 1) {
+                for (unsigned r = 0; r < nblocks; ++r) {
+                    double* remote = cluster.map_shared_rank(slots, r);
+                    remote[(parity * kTrendMaxCluster + rank) * kTrendK + threadIdx.x] = tot;
+                }
+            } else {
+                slots[parity * kTrendMaxCluster * kTrendK + threadIdx.x] = tot;
             }
         }
-        cluster.sync();  // release the DSMEM stores / acquire the peers'
+        if (nblocks > 1) cluster.sync(); else __syncthreads();  // release the DSMEM stores / acquire the peers'
         for (int j = 0; j < k; ++j) {
             double tot = 0.0;
             for (unsigned r = 0; r < nblocks; ++r) tot += slots[(parity * kTrendMaxCluster + r) * kTrendK + j];
@@ -493,7 +550,7 @@ __global__ void __launch_bounds__(1024) k_trend_prior(const double* __restrict__
                                                       double trigamma_c, int with_prior, TrendOut* out) {
     __shared__ double warp_part[32 * kTrendK];
     __shared__ double slots[2 * kTrendMaxCluster * kTrendK];
-    __shared__ unsigned hist[258];
+    __shared__ unsigned hist[514];
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     ClusterReducer red{warp_part, slots, cluster.block_rank(), cluster.num_blocks(), 0};
@@ -524,7 +581,9 @@ __global__ void __launch_bounds__(kBlock) k_log_means(const int64_t* __restrict_
 __global__ void __launch_bounds__(1024) k_size_factor_median(const int64_t* __restrict__ counts, int64_t ld, int G,
                                                              const double* __restrict__ logmeans, double* scratch,
                                                              double* sf_out) {
-    __shared__ unsigned hist[258];
+    __shared__ unsigned hist[514];
+    __shared__ double warp_part[32 * kTrendK];
+    __shared__ double slots[2 * kTrendMaxCluster * kTrendK];
     __shared__ unsigned cnt_s;
     const int n = blockIdx.x;
     double* row = scratch + (size_t)n * G;
@@ -540,7 +599,7 @@ __global__ void __launch_bounds__(1024) k_size_factor_median(const int64_t* __re
     }
     atomicAdd(&cnt_s, cnt);
     __syncthreads();
-    ClusterReducer red{nullptr, nullptr, 0u, 1u, 0};  // only the block-local parts are used here
+    ClusterReducer red{warp_part, slots, 0u, 1u, 0};  // one block per sample: the single-block paths of the reducer
     const double med = median_of(red, row, (size_t)G, (size_t)cnt_s, false, 0.0, hist);
     if (threadIdx.x == 0) sf_out[n] = exp(med);
 }

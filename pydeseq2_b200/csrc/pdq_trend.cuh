@@ -43,7 +43,10 @@ struct SerialReducer {
     PDQ_HD int local_tid() const { return 0; }
     PDQ_HD int local_nthreads() const { return 1; }
     PDQ_HD void local_sync() {}
-    PDQ_HD void find_bin(const unsigned* hist, size_t k, int& d, size_t& cum) {
+    PDQ_HD double max_one(double v) { return v; }
+    PDQ_HD void hist_begin() {}
+    PDQ_HD unsigned* hist_merge(unsigned* hist) { return hist; }
+    PDQ_HD void find_bin(const unsigned* hist, unsigned*, size_t k, int& d, size_t& cum) {
         cum = 0;
         for (d = 0; d < 256; ++d) {
             const size_t c = hist[d];
@@ -238,14 +241,16 @@ PDQ_HD double f64_from_key(uint64_t k) {
 #endif
 }
 
-// k-th smallest (0-based) of { |res[i] - center| or res[i] } over the non-NaN entries
+// k-th smallest (0-based) of { |res[i] - center| or res[i] } over the non-NaN entries.  The blocks of the cluster
+// histogram disjoint slices of the vector and merge their 256-bin histograms (reducer hist_* hooks); `hist` holds
+// 256 local bins + 256 merged bins + 2 result slots.
 template <class R>
 PDQ_HD double select_kth(R& red, const double* res, size_t n, bool absdev, double center, unsigned* hist, size_t k) {
     uint64_t prefix = 0, mask = 0;
     for (int shift = 56; shift >= 0; shift -= 8) {
-        for (int b = red.local_tid(); b < 256; b += red.local_nthreads()) hist[b] = 0;
-        red.local_sync();
-        for (size_t i = red.local_tid(); i < n; i += red.local_nthreads()) {
+        for (int b = red.local_tid(); b < 512; b += red.local_nthreads()) hist[b] = 0;
+        red.hist_begin();
+        for (size_t i = red.tid(); i < n; i += red.nthreads()) {
             const double r = res[i];
             if (!(r == r)) continue;
             const uint64_t key = f64_key(absdev ? fabs(r - center) : r);
@@ -257,10 +262,10 @@ PDQ_HD double select_kth(R& red, const double* res, size_t n, bool absdev, doubl
 #endif
             }
         }
-        red.local_sync();
+        unsigned* tot = red.hist_merge(hist);  // totals over the cluster, identical in every block
         size_t cum = 0;
         int d = 0;
-        red.find_bin(hist, k, d, cum);  // first bin whose cumulative count exceeds k, and the count before it
+        red.find_bin(tot, hist + 512, k, d, cum);  // first bin whose cumulative count exceeds k, and the count before it
         k -= cum;
         prefix |= (uint64_t)d << shift;
         mask |= (uint64_t)0xff << shift;
@@ -272,27 +277,41 @@ PDQ_HD double select_kth(R& red, const double* res, size_t n, bool absdev, doubl
 template <class R>
 PDQ_HD double median_of(R& red, const double* res, size_t n, size_t cnt, bool absdev, double center, unsigned* hist) {
     if (cnt == 0) return 0.0 / 0.0;  // np.median([]) = nan
-    const double hi = select_kth(red, res, n, absdev, center, hist, cnt / 2);
+    const size_t k = cnt / 2;
+    const double hi = select_kth(red, res, n, absdev, center, hist, k);  // upper median
     if (cnt & 1) return hi;
-    return 0.5 * (select_kth(red, res, n, absdev, center, hist, cnt / 2 - 1) + hi);
+    // even count: the lower median is the largest value below `hi`, unless `hi` is duplicated down to rank k-1
+    double less = 0.0, mx = -1.7976931348623157e308;
+    for (size_t i = red.tid(); i < n; i += red.nthreads()) {
+        const double r = res[i];
+        if (!(r == r)) continue;
+        const double v = absdev ? fabs(r - center) : r;
+        if (v < hi) {
+            less += 1.0;
+            mx = v > mx ? v : mx;
+        }
+    }
+    red.sum_many(&less, 1);
+    mx = red.max_one(mx);
+    const double lo = ((size_t)less >= k) ? mx : hi;
+    return 0.5 * (lo + hi);
 }
 
-// `res` : n doubles of scratch; `hist`: 256 (+2 result slots) unsigned in block-shared memory; `trigamma_c` = polygamma(1, (N-p)/2)
+// `res` : n doubles of scratch; `hist`: 514 unsigned in block-shared memory (see select_kth); `trigamma_c` = polygamma(1, (N-p)/2)
 template <class R>
 PDQ_HD void trend_prior(R& red, const double* means, const double* t, size_t n, double lo, double hi, double min_disp,
                         double trigamma_c, double* res, unsigned* hist, TrendOut& out) {
     const double c0 = out.c0, c1 = out.c1;
     double cnt = 0.0;
-    // every block fills the whole scratch vector (redundantly, same values) so that no cluster barrier is needed
-    for (size_t i = red.local_tid(); i < n; i += red.local_nthreads()) {
+    // every thread fills (and later only ever reads) its own stride of the scratch vector: no barrier needed
+    for (size_t i = red.tid(); i < n; i += red.nthreads()) {
         double tv = t[i];
         tv = (tv < lo) ? lo : ((tv > hi) ? hi : tv);
         const double fit = c0 + c1 / means[i];
         const bool use = (tv >= 100.0 * min_disp) && (means[i] == means[i]);
         res[i] = use ? (log(tv) - log(fit)) : (0.0 / 0.0);
+        cnt += use ? 1.0 : 0.0;
     }
-    red.local_sync();
-    for (size_t i = red.tid(); i < n; i += red.nthreads()) cnt += (res[i] == res[i]) ? 1.0 : 0.0;
     red.sum_many(&cnt, 1);
     const size_t m = (size_t)cnt;
     const double med = median_of(red, res, n, m, false, 0.0, hist);

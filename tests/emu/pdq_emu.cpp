@@ -184,7 +184,7 @@ int emu_mom_from_counts(const int64_t* counts, int64_t ld, int N, int G, const d
 int emu_trend_fit(const double* x, const double* t, size_t n, int x_is_mean, double lo, double hi, int outer, double min_disp,
                   double trigamma_c, int with_prior, double* out16) {
     std::vector<double> xs(n), ts(n), res(n);
-    unsigned hist[258];
+    unsigned hist[514];
     SerialReducer red;
     trend_prepare(red, x, t, n, x_is_mean != 0, lo, hi, xs.data(), ts.data());
     TrendOut o = trend_fit_outer(red, xs.data(), ts.data(), n, outer != 0);
@@ -201,7 +201,7 @@ int emu_size_factors(const int64_t* counts, int64_t ld, int N, int G, double* sf
         for (int n = 0; n < N; ++n) s += log((double)counts[(size_t)n * ld + g]);
         lm[g] = s / (double)N;
     }
-    unsigned hist[258];
+    unsigned hist[514];
     SerialReducer red;
     for (int n = 0; n < N; ++n) {
         size_t cnt = 0;
