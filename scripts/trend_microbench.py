@@ -1,4 +1,4 @@
-import sys, time; sys.path.insert(0,'.')
+import sys, time; sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import numpy as np, ctypes as C
 from scipy.special import polygamma
 from pydeseq2_b200 import _lib
