@@ -139,6 +139,15 @@ int pdq_dispersion_trend_gamma_glm(pdq_ctx* ctx, const double* covariates, const
  * (the reference then switches to its iterative fallback, dds.py:682-690). */
 int pdq_size_factors(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N, int G, double* sf_out);
 
+/* Cook's distances -- DeseqDataSet.calculate_cooks (dds.py:986-1040) with the trimmed-moments dispersion
+ * (utils.py:914-960; cells = identical design rows with >= 3 replicates) -- and the two per-gene decisions derived from them:
+ * `outlier_out` = the p-value filter of cooks_outlier() (dds.py:1066-1110, no prior refit), `replaced_out` = any distance above
+ * `cutoff` (dds.py:1320-1323).  `cutoff` = F.ppf(0.99, p, N - p).  `mu`/`hat` are the outputs of pdq_irls.  `cooks_out` (N,G)
+ * may be NULL when only the per-gene results are wanted (saves the 8*N*G-byte copy).  SURVEY.md §8 f-1. */
+int pdq_calculate_cooks(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N, int G, const double* size_factors,
+                        const double* X, int p, const double* mu, const double* hat, int64_t ld2, double cutoff,
+                        double* cooks_out, double* robust_disp_out, double* outlier_out, double* replaced_out);
+
 /* ----------------------------------------------------------------- hot path, device-resident
  * Same semantics; every pointer except `design` is device memory from pdq_malloc.  Asynchronous. */
 int pdq_lin_reg_mu_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld, int G,
@@ -172,6 +181,9 @@ int pdq_mom_dispersions_dev(pdq_ctx* ctx, const pdq_design* design, const int64_
  * `fitted_out` (n,) device, may be NULL: c0 + c1 / mean. */
 int pdq_trend_fit_dev(pdq_ctx* ctx, const double* normed_means, const double* genewise, size_t n, double min_disp,
                       double max_disp, double trigamma_c, double* out16, double* fitted_out);
+int pdq_cooks_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld, int G, const double* mu,
+                  const double* hat, int64_t ld2, double cutoff, double* cooks_out, int64_t ld_out,
+                  double* robust_disp_out, double* outlier_out, double* replaced_out);
 /* device-resident flavour of pdq_size_factors; `logmeans_out` (G,) may be NULL */
 int pdq_size_factors_dev(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N, int G, double* sf_out,
                          double* logmeans_out);

@@ -123,8 +123,13 @@ class Tape:
             return fn
 
         def rec(*a, **k):
+            # snapshot the inputs NOW: the orchestrator hands out views of its own columns (e.g. `.values` of
+            # var["fitted_dispersions"]) and overwrites them in place later (outlier refit, dds.py:1440-1458)
+            snap = lambda v: v.copy() if hasattr(v, "copy") else v  # noqa: E731
+            a0, k0 = tuple(snap(v) for v in a), {kk: snap(v) for kk, v in k.items()}
             res = fn(*a, **k)
-            self.calls.append((name, a, k, res))
+            r0 = tuple(snap(v) for v in res) if isinstance(res, tuple) else snap(res)
+            self.calls.append((name, a0, k0, r0))
             return res
 
         return rec
@@ -175,6 +180,17 @@ def gen_tape(name, counts_df, metadata, design_df, contrast, r_res_csv, r_disp_c
     out["final_stat"] = ds.statistics.values
     out["final_se"] = ds.SE.values
     out["final_padj"] = ds.padj.values
+    # Cook's distances (dds.py:986-1040) and what the orchestrator derives from them
+    from pydeseq2.utils import robust_method_of_moments_disp
+
+    nzm = dds.var["non_zero"].values
+    out["final_cooks"] = dds.layers["cooks"]
+    out["final_robust_disp"] = robust_method_of_moments_disp(dds.layers["normed_counts"][:, nzm], dds.obsm["design_matrix"])
+    out["final_mu_LFC"] = np.ascontiguousarray(dds.obsm["_mu_LFC"])
+    out["final_hat"] = np.ascontiguousarray(dds.obsm["_hat_diagonals"])
+    out["final_cooks_outlier"] = np.asarray(dds.cooks_outlier(), dtype=float)
+    out["final_replaced"] = np.asarray(dds.var["replaced"], dtype=float)
+    out["final_non_zero"] = nzm.astype(float)
     out["counts"] = counts_df.values.astype(np.int64)
     out["design"] = design_df.values.astype(float)
     out["contrast"] = np.asarray(contrast, dtype=float)
@@ -233,6 +249,16 @@ def main():
                        "condition[T.B]": indicator(wm["condition"], "B")}, index=wm.index)
     gen_tape("wide", wc, wm, d4, [0, 0, 1], f"{REF}/tests/data/wide/r_test_res.csv",
              f"{REF}/tests/data/wide/r_test_dispersions.csv")
+    # outliers + a condition level with a single replicate (tests/test_pydeseq2.py:452-456): Cook's refit is triggered
+    co = counts.copy()
+    mo = meta.copy()
+    co.loc["sample1", "gene1"] = 2000
+    co.loc["sample11", "gene7"] = 1000
+    mo.loc["sample1", "condition"] = "C"
+    d5 = pd.DataFrame({"Intercept": 1.0, "group[T.Y]": indicator(mo["group"], "Y"),
+                       "condition[T.B]": indicator(mo["condition"], "B"),
+                       "condition[T.C]": indicator(mo["condition"], "C")}, index=mo.index)
+    gen_tape("multi_factor_outliers", co, mo, d5, [0, 0, 1, 0], f"{REF}/tests/data/multi_factor/r_test_res_outliers.csv")
 
 
 if __name__ == "__main__":

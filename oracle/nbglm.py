@@ -356,3 +356,76 @@ class OracleInference:
     fit_rough_dispersions = staticmethod(fit_rough_dispersions)
     fit_moments_dispersions = staticmethod(fit_moments_dispersions)
     dispersion_trend_gamma_glm = staticmethod(dispersion_trend_gamma_glm)
+
+
+# --------------------------------------------------------------------------- Cook's distance
+def _trimmed_mean_rows(x, trim):
+    """Mean over axis 0 after dropping floor(n*trim) smallest and largest entries of every column (utils.py:567-601)."""
+    n = x.shape[0]
+    k = int(np.floor(n * trim))
+    s = np.sort(x, axis=0)
+    return s[k:n - k].mean(0)
+
+
+def design_cells(X, min_replicates=3):
+    """Cell id per sample (-1 when the sample's design row has fewer than `min_replicates` replicates);
+    utils.py:888-912 `n_or_more_replicates` + the groupby of utils.py:935-941."""
+    X = np.asarray(X, dtype=float)
+    _, inv, cnt = np.unique(X, axis=0, return_inverse=True, return_counts=True)
+    inv = inv.ravel()
+    keep = cnt[inv] >= min_replicates
+    cell = np.full(len(X), -1)
+    ids = {}
+    for i in np.flatnonzero(keep):
+        cell[i] = ids.setdefault(inv[i], len(ids))
+    return cell
+
+
+def robust_method_of_moments_disp(normed_counts, X):
+    """utils.py:914-960: trimmed-moments dispersion used only for Cook's distances."""
+    cell = design_cells(X, 3)
+    if (cell >= 0).any():
+        y = normed_counts[cell >= 0]
+        c = cell[cell >= 0]
+        trimratio = (1 / 3, 1 / 4, 1 / 8)
+
+        def trimfn(n):
+            return 2 if n >= 23.5 else 1 if n >= 3.5 else 0
+
+        var_est = []
+        for lvl in np.unique(c):
+            rows = y[c == lvl]
+            k = trimfn(len(rows))
+            mean = _trimmed_mean_rows(rows, trimratio[k])
+            sq = (rows - mean[None, :]) ** 2
+            var_est.append([2.04, 1.86, 1.51][k] * _trimmed_mean_rows(sq, trimratio[k]))
+        v = np.max(var_est, axis=0)
+    else:
+        rm = _trimmed_mean_rows(normed_counts, 0.125)
+        v = 1.51 * _trimmed_mean_rows((normed_counts - rm) ** 2, 0.125)
+    m = normed_counts.mean(0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        alpha = (v - m) / m**2
+    return np.maximum(alpha, 0.04)
+
+
+def calculate_cooks(counts, normed_counts, X, mu, hat):
+    """dds.py:986-1040 on the non-zero genes: returns (cooks (N, G), robust dispersions (G,))."""
+    p = X.shape[1]
+    disp = robust_method_of_moments_disp(normed_counts, X)
+    V = mu**2 * disp[None, :] + mu
+    cooks = (counts - mu) ** 2 / V / p * (hat / (1 - hat) ** 2)
+    return cooks, disp
+
+
+def cooks_outlier(counts, cooks, X):
+    """dds.py:1066-1110 without a refit: genes whose p-value the Cook's filter masks."""
+    from scipy.stats import f
+
+    N, p = X.shape
+    cutoff = f.ppf(0.99, p, N - p)
+    use = design_cells(X, 3) >= 0
+    out = (cooks[use] > cutoff).any(axis=0)
+    pos = cooks[:, out].argmax(0)
+    out[out] = (counts[:, out] > counts[:, out][pos, np.arange(len(pos))]).sum(0) < 3
+    return out

@@ -281,6 +281,19 @@ extern "C" int pdq_design_create(pdq_ctx* c, const double* X, const double* sf, 
                     dd.smem_bytes, kMaxDynSmem);
     }
     design_linear_algebra(X, N, p, dd.pinv, &dd.full_rank);
+    {
+        const std::vector<int> plan = design_cell_plan(X, N, p);
+        dd.n_cells = plan[0];
+        dd.plan_len = (int)plan.size();
+        dd.n_in_cells = dd.plan_len - (2 + dd.n_cells + 1);
+        dd.cell_plan = nullptr;
+        if (cudaMalloc((void**)&dd.cell_plan, plan.size() * sizeof(int)) != cudaSuccess ||
+            cudaMemcpy(dd.cell_plan, plan.data(), plan.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+            if (dd.cell_plan) cudaFree(dd.cell_plan);
+            delete d;
+            return fail(c, PDQ_ERR_CUDA, "cudaMalloc/cudaMemcpy(cell plan) failed");
+        }
+    }
     std::vector<double> pack((size_t)(p + 2) * dd.Npad, 0.0);
     double inv_sum = 0.0;
     for (int n = 0; n < N; ++n) {
@@ -293,12 +306,14 @@ extern "C" int pdq_design_create(pdq_ctx* c, const double* X, const double* sf, 
     for (int n = N; n < dd.Npad; ++n) pack[(size_t)p * dd.Npad + n] = 1.0;
     dd.s_mean_inv = inv_sum / N;
     if (cudaMalloc((void**)&dd.pack, pack.size() * 8) != cudaSuccess) {
+        cudaFree(dd.cell_plan);
         delete d;
         return fail(c, PDQ_ERR_CUDA, "cudaMalloc(design pack) failed");
     }
     // synchronous copy: `pack` is a temporary
     if (cudaMemcpy(dd.pack, pack.data(), pack.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaFree(dd.pack);
+        cudaFree(dd.cell_plan);
         delete d;
         return fail(c, PDQ_ERR_CUDA, "cudaMemcpy(design pack) failed");
     }
@@ -311,6 +326,7 @@ extern "C" void pdq_design_destroy(pdq_ctx* c, pdq_design* d) {
     if (c) cudaSetDevice(c->device);
     if (c && c->cached == d) c->cached = nullptr;
     if (d->d.pack) cudaFree(d->d.pack);
+    if (d->d.cell_plan) cudaFree(d->d.cell_plan);
     delete d;
 }
 
@@ -414,6 +430,17 @@ extern "C" int pdq_trend_fit_dev(pdq_ctx* c, const double* means, const double* 
         return e;
     if (fitted) return done(c, launch_trend_eval(lc, means, n, out16, fitted), "trend_eval");
     return PDQ_OK;
+}
+
+extern "C" int pdq_cooks_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, const double* mu, const double* hat,
+                             int64_t ld2, double cutoff, double* cooks_out, int64_t ld_out, double* robust_disp_out, double* outlier_out,
+                             double* replaced_out) {
+    CHECK_CTX(c);
+    if (!d || !counts || !mu || !hat || !robust_disp_out || !outlier_out || !replaced_out || G <= 0 || ld < G || ld2 < G ||
+        (cooks_out && ld_out < G))
+        return fail(c, PDQ_ERR_INVALID, "pdq_cooks_dev: bad arguments");
+    return done(c, launch_cooks(cfg(c, G, d->d.N), d->d, counts, ld, G, mu, hat, ld2, cutoff, cooks_out, ld_out, robust_disp_out, outlier_out,
+                                replaced_out), "cooks");
 }
 
 extern "C" int pdq_size_factors_dev(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, double* sf_out, double* logmeans_out) {
@@ -664,6 +691,39 @@ extern "C" int pdq_fit_moments_dispersions(pdq_ctx* c, const double* normed, int
     if (int e = done(c, launch_moments(cfg(c, G, N), d->d, (const double*)dn, G, G, (double*)da, (double*)dz), "fit_moments_dispersions")) return e;
     CU(c, cudaMemcpyAsync(alpha_out, da, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(all_zero_out, dz, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return PDQ_OK;
+}
+
+extern "C" int pdq_calculate_cooks(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, const double* sf, const double* X, int p,
+                                   const double* mu, const double* hat, int64_t ld2, double cutoff, double* cooks_out, double* robust_disp_out,
+                                   double* outlier_out, double* replaced_out) {
+    CHECK_CTX(c);
+    if (!counts || !sf || !X || !mu || !hat || !robust_disp_out || !outlier_out || !replaced_out || N <= 0 || G <= 0 || ld < G || ld2 < G)
+        return fail(c, PDQ_ERR_INVALID, "pdq_calculate_cooks: bad arguments");
+    pdq_design* d;
+    if (int e = cached_design(c, X, sf, N, p, &d)) return e;
+    const size_t ng = (size_t)N * G;
+    void *dc, *dmu, *dhat, *dck = nullptr, *dd, *dout, *drep;
+    if (int e = ensure(c, kBufCounts, ng * 8, &dc)) return e;
+    if (int e = ensure(c, kBufA, ng * 8, &dmu)) return e;
+    if (int e = ensure(c, kBufB, ng * 8, &dhat)) return e;
+    if (cooks_out)
+        if (int e = ensure(c, kBufRes, ng * 8, &dck)) return e;
+    if (int e = ensure(c, kBufC, (size_t)G * 8, &dd)) return e;
+    if (int e = ensure(c, kBufE, (size_t)G * 8, &dout)) return e;
+    if (int e = ensure(c, kBufF, (size_t)G * 8, &drep)) return e;
+    if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
+    if (int e = h2d_2d(c, dmu, mu, ld2, N, G, 8)) return e;
+    if (int e = h2d_2d(c, dhat, hat, ld2, N, G, 8)) return e;
+    if (int e = pdq_cooks_dev(c, d, (const int64_t*)dc, G, G, (const double*)dmu, (const double*)dhat, G, cutoff, (double*)dck, G, (double*)dd,
+                              (double*)dout, (double*)drep))
+        return e;
+    if (cooks_out)
+        if (int e = copy_d2h(c, cooks_out, dck, ng * 8)) return e;
+    CU(c, cudaMemcpyAsync(robust_disp_out, dd, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(outlier_out, dout, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(replaced_out, drep, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return PDQ_OK;
 }

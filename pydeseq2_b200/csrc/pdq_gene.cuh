@@ -1033,3 +1033,139 @@ PDQ_HD double moments_disp_gene(const Group& grp, const DesignS& d, const Y& yy,
 }
 
 }  // namespace pdq
+
+namespace pdq {
+
+// =============================================================================================
+// (f-1) Cook's distances -- dds.py:986-1040 with the trimmed-moments dispersion of utils.py:567-679, 914-960,
+// and the two per-gene decisions the orchestrator derives from them (dds.py:1066-1110, :1320-1323).
+// Cells = groups of samples with identical design rows that hold >= 3 replicates; `order` lists the samples of those
+// cells cell by cell, `cell_start` (n_cells + 1 entries) delimits them.  When no cell qualifies the whole sample set is
+// one "cell" with the fixed trim 1/8 (utils.py:650-679 `trimmed_variance`).
+// Trimmed means are exact order-statistic sums: the rank of every value inside its cell is counted against all other
+// members (ties broken by position, like a stable sort); O(n_c^2 / T) comparisons per lane, values staged in shared memory.
+// =============================================================================================
+struct CellPlan {
+    const int* order;       // [n_in_cells] sample indices, grouped by cell
+    const int* cell_start;  // [n_cells + 1]
+    int n_cells;
+    int global_mode;        // 1: no cell has 3 replicates -> single cell, trim 1/8, scale 1.51
+};
+
+PDQ_HD void trim_class(int nc, bool global_mode, int& ntrim, double& scale) {
+    if (global_mode) {
+        ntrim = (int)floor((double)nc * 0.125);
+        scale = 1.51;
+        return;
+    }
+    const int k = (nc >= 23.5) ? 2 : ((nc >= 3.5) ? 1 : 0);             // utils.py:621-623
+    const double ratio = (k == 2) ? (1.0 / 8.0) : ((k == 1) ? (1.0 / 4.0) : (1.0 / 3.0));
+    ntrim = (int)floor((double)nc * ratio);
+    scale = (k == 2) ? 1.51 : ((k == 1) ? 1.86 : 2.04);
+}
+
+// mean of v[s:e) after dropping the ntrim smallest and ntrim largest entries (np.sort + slice + mean)
+PDQ_HD double trimmed_mean_cell(const Group& grp, const double* v, int s, int e, int ntrim) {
+    const int nc = e - s;
+    double part = 0.0;
+    for (int i = s + grp.si; i < e; i += grp.T) {
+        const double vi = v[i];
+        int rank = 0;
+        for (int j = s; j < e; ++j) {
+            const double vj = v[j];
+            rank += (vj < vi) || (vj == vi && j < i);
+        }
+        if (rank >= ntrim && rank < nc - ntrim) part += vi;
+    }
+    return grp.sum(part) / (double)(nc - 2 * ntrim);
+}
+
+template <int P>
+PDQ_HD void cooks_gene(const Group& grp, const DesignS& d, const CellPlan& plan, const int64_t* y, int64_t ld, const double* mu,
+                       const double* hat, int64_t ld2, double cutoff, double* vals /* smem: n_in_cells */,
+                       double* sq /* smem: n_in_cells */, double* cooks_out, int64_t ld_out, double* disp_out,
+                       double* outlier_out, double* replaced_out, bool valid) {
+    const int nf = plan.cell_start[plan.n_cells];
+    // normalised counts: mean over ALL samples, and the grouped copy of the samples that sit in cells
+    double msum = 0.0;
+    for (int n = grp.si; n < d.N; n += grp.T) msum += (double)y[n * ld] / d.sf[n];
+    const double m_all = grp.sum(msum) / (double)d.N;
+    grp.sync();
+    for (int i = grp.si; i < nf; i += grp.T) {
+        const int n = plan.order[i];
+        vals[i] = (double)y[n * ld] / d.sf[n];
+    }
+    grp.sync();
+    double v = -1.7976931348623157e308;
+    for (int c = 0; c < plan.n_cells; ++c) {
+        const int s = plan.cell_start[c], e = plan.cell_start[c + 1];
+        int ntrim;
+        double scale;
+        trim_class(e - s, plan.global_mode != 0, ntrim, scale);
+        const double tm = trimmed_mean_cell(grp, vals, s, e, ntrim);
+        for (int i = s + grp.si; i < e; i += grp.T) {
+            const double dlt = vals[i] - tm;
+            sq[i] = dlt * dlt;
+        }
+        grp.sync();
+        const double tv = scale * trimmed_mean_cell(grp, sq, s, e, ntrim);
+        v = (tv > v || tv != tv) ? tv : v;  // np.max propagates NaN
+    }
+    double alpha = (v - m_all) / (m_all * m_all);
+    alpha = (alpha < 0.04) ? 0.04 : alpha;  // np.maximum(alpha, 0.04): NaN stays NaN
+    // Cook's distance per sample, running maximum (first occurrence) and the cutoff tests
+    double best = -1.0, best_use = -1.0;
+    int best_n = 0x7fffffff;
+    bool any_all = false;
+    for (int n = grp.si; n < d.N; n += grp.T) {
+        const double yv = (double)y[n * ld], m = mu[n * ld2], h = hat[n * ld2];
+        const double V = fma(m * m, alpha, m);
+        const double omh = 1.0 - h;
+        const double ck = (yv - m) * (yv - m) / V / (double)P * (h / (omh * omh));
+        if (valid && cooks_out) cooks_out[n * ld_out] = ck;
+        any_all = any_all || (ck > cutoff);
+        if (ck > best) {  // lanes visit their samples in increasing n: strict > keeps the first maximum
+            best = ck;
+            best_n = n;
+        }
+    }
+    // samples in qualifying cells decide the p-value filter (dds.py:1077-1092)
+    if (!plan.global_mode) {
+        for (int i = grp.si; i < nf; i += grp.T) {
+            const int n = plan.order[i];
+            const double yv = (double)y[n * ld], m = mu[n * ld2], h = hat[n * ld2];
+            const double V = fma(m * m, alpha, m);
+            const double omh = 1.0 - h;
+            const double ck = (yv - m) * (yv - m) / V / (double)P * (h / (omh * omh));
+            best_use = ck > best_use ? ck : best_use;
+        }
+    }
+    // group-wide argmax (value, then smaller sample index) and flags
+#if defined(__CUDA_ARCH__)
+    for (int off = 16; off >= grp.gpw; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int on = __shfl_xor_sync(0xffffffffu, best_n, off);
+        if (ob > best || (ob == best && on < best_n)) {
+            best = ob;
+            best_n = on;
+        }
+        const double ou = __shfl_xor_sync(0xffffffffu, best_use, off);
+        best_use = ou > best_use ? ou : best_use;
+    }
+#endif
+    const bool replaced = grp.sum(any_all ? 1.0 : 0.0) > 0.0;
+    bool outlier = best_use > cutoff;
+    // a gene is not an outlier when 3 or more samples have larger counts than the sample with the largest distance
+    const long long ypos = y[(int64_t)(best_n == 0x7fffffff ? 0 : best_n) * ld];
+    double larger = 0.0;
+    for (int n = grp.si; n < d.N; n += grp.T) larger += (y[n * ld] > ypos) ? 1.0 : 0.0;
+    larger = grp.sum(larger);
+    outlier = outlier && (larger < 3.0);
+    if (valid && grp.si == 0) {
+        *disp_out = alpha;
+        *outlier_out = outlier ? 1.0 : 0.0;
+        *replaced_out = replaced ? 1.0 : 0.0;
+    }
+}
+
+}  // namespace pdq

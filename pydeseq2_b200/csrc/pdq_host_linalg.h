@@ -70,4 +70,46 @@ inline void design_linear_algebra(const double* X, int N, int p, double* pinv, i
 }
 
 
+// Cells of the design: samples with identical design rows, kept when they hold >= 3 replicates
+// (utils.py:888-912 + the groupby of utils.py:935-941, cells numbered by first appearance among the kept samples).
+// plan = [n_cells, global_mode, start_0 .. start_ncells, order_0 .. order_{nf-1}]
+inline std::vector<int> design_cell_plan(const double* X, int N, int p) {
+    std::vector<int> rep(N, -1);  // representative (first sample with the same row)
+    std::vector<int> count(N, 0);
+    for (int i = 0; i < N; ++i) {
+        for (int j = 0; j < i && rep[i] < 0; ++j) {
+            if (rep[j] != j) continue;
+            bool same = true;
+            for (int k = 0; k < p && same; ++k) same = X[(size_t)i * p + k] == X[(size_t)j * p + k];
+            if (same) rep[i] = j;
+        }
+        if (rep[i] < 0) rep[i] = i;
+        ++count[rep[i]];
+    }
+    std::vector<int> cells;  // representatives of the kept cells, by first appearance
+    for (int i = 0; i < N; ++i)
+        if (rep[i] == i && count[i] >= 3) cells.push_back(i);
+    std::vector<int> plan;
+    if (cells.empty()) {  // no replicates anywhere: one global cell (utils.py:942-945)
+        plan.push_back(1);
+        plan.push_back(1);
+        plan.push_back(0);
+        plan.push_back(N);
+        for (int i = 0; i < N; ++i) plan.push_back(i);
+        return plan;
+    }
+    plan.push_back((int)cells.size());
+    plan.push_back(0);
+    int acc = 0;
+    for (int c : cells) {
+        plan.push_back(acc);
+        acc += count[c];
+    }
+    plan.push_back(acc);
+    for (int c : cells)
+        for (int i = 0; i < N; ++i)
+            if (rep[i] == c) plan.push_back(i);
+    return plan;
+}
+
 }  // namespace pdq

@@ -18,6 +18,8 @@ struct DesignDev {
     double pinv[PDQ_MAX_P * PDQ_MAX_P];  // (X^T X)^+ row-major p x p (host copy, passed by value to kernels)
     double s_mean_inv;  // mean(1 / size_factors)  (utils.py:880)
     size_t smem_bytes;  // dynamic shared memory the kernels need for this pack
+    int* cell_plan;     // device: [n_cells, global_mode, starts (n_cells + 1), order (n_in_cells)]  (Cook's distances)
+    int n_cells, n_in_cells, plan_len;
 };
 
 struct LaunchCfg {
@@ -55,6 +57,8 @@ int launch_mu_from_lfc(const LaunchCfg&, const DesignDev&, const double* lfc, in
 int launch_trend_fit(const LaunchCfg&, const double* x, const double* t, double* scratch3n, size_t n, int x_is_mean,
                      double lo, double hi, int outer, double min_disp, double trigamma_c, int with_prior, double* out16);
 int launch_trend_eval(const LaunchCfg&, const double* means, size_t n, const double* out16, double* fitted);
+int launch_cooks(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64_t ld, int G, const double* mu, const double* hat,
+                 int64_t ld2, double cutoff, double* cooks, int64_t ld_out, double* disp, double* outlier, double* replaced);
 int launch_size_factors(const LaunchCfg&, const int64_t* counts, int64_t ld, int N, int G, double* logmeans,
                         double* scratch, double* sf_out);
 int launch_select_disp(const LaunchCfg&, const double* gw, const double* mp, const double* fitted, const double* out16,

@@ -333,6 +333,42 @@ __global__ void __launch_bounds__(kBlock) k_mom_from_counts(const __grid_constan
 }
 
 template <int P>
+struct CooksArgs {
+    DesignView dv;
+    const int* plan;
+    int plan_len, n_cells, n_in_cells;
+    const int64_t* counts;
+    int64_t ld;
+    int G, lgT;
+    const double *mu, *hat;
+    int64_t ld2;
+    double cutoff;
+    double* cooks;
+    int64_t ld_out;
+    double *disp, *outlier, *replaced;
+};
+
+// Cook's distances + trimmed-moments dispersions (dds.py:986-1040); the gene's cell members are staged in shared memory
+template <int P>
+__global__ void __launch_bounds__(kBlock) k_cooks(const __grid_constant__ CooksArgs<P> a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    int* plan_s = reinterpret_cast<int*>(smem + (size_t)(P + 2) * a.dv.Npad * 8 + 16);
+    for (int i = threadIdx.x; i < a.plan_len; i += blockDim.x) plan_s[i] = a.plan[i];
+    __syncthreads();
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(a.lgT, a.G, grp, g, valid);
+    const CellPlan plan{plan_s + 2 + a.n_cells + 1, plan_s + 2, a.n_cells, plan_s[1]};
+    const size_t plan_bytes = ((size_t)a.plan_len * 4 + 15) & ~(size_t)15;
+    const int gslot = (threadIdx.x >> 5) * grp.gpw + ((threadIdx.x & 31) & (grp.gpw - 1));
+    double* vals = reinterpret_cast<double*>(smem + (size_t)(P + 2) * a.dv.Npad * 8 + 16 + plan_bytes) + (size_t)gslot * 2 * a.n_in_cells;
+    cooks_gene<P>(grp, d, plan, a.counts + g, a.ld, a.mu + g, a.hat + g, a.ld2, a.cutoff, vals, vals + a.n_in_cells,
+                  a.cooks ? a.cooks + g : nullptr, a.ld_out, a.disp + g, a.outlier + g, a.replaced + g, valid);
+}
+
+template <int P>
 struct MuLfcArgs {
     DesignView dv;
     const double* lfc;
@@ -830,6 +866,24 @@ int launch_trend_fit(const LaunchCfg& c, const double* x, const double* t, doubl
 
 int launch_trend_eval(const LaunchCfg& c, const double* means, size_t n, const double* out16, double* fitted) {
     k_trend_eval<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(means, n, reinterpret_cast<const TrendOut*>(out16), fitted);
+    if (int e = check_launch()) return e;
+    return 1;
+}
+
+int launch_cooks(const LaunchCfg& c0, const DesignDev& d, const int64_t* counts, int64_t ld, int G, const double* mu, const double* hat,
+                 int64_t ld2, double cutoff, double* cooks, int64_t ld_out, double* disp, double* outlier, double* replaced) {
+    // the per-gene staging (2 * n_in_cells doubles) bounds the genes per block: widen the lane groups until it fits
+    LaunchCfg c = c0;
+    const size_t plan_bytes = ((size_t)d.plan_len * 4 + 15) & ~(size_t)15;
+    auto need = [&](int lgT) { return d.smem_bytes + plan_bytes + (size_t)kWarps * (32 >> lgT) * 2 * d.n_in_cells * sizeof(double); };
+    while (c.lgT < 5 && need(c.lgT) > 96 * 1024) ++c.lgT;
+    if (need(c.lgT) > kMaxDynSmem) return PDQ_ERR_UNSUPPORTED;
+    PDQ_DISPATCH_P(d.p, {
+        CooksArgs<P> a{{d.pack, d.N, d.Npad}, d.cell_plan, d.plan_len, d.n_cells, d.n_in_cells, counts, ld, G, c.lgT, mu, hat, ld2,
+                       cutoff, cooks, ld_out, disp, outlier, replaced};
+        if (int e = prep(k_cooks<P>, need(c.lgT))) return e;
+        k_cooks<P><<<grid_for(G, c.lgT), kBlock, need(c.lgT), c.stream>>>(a);
+    });
     if (int e = check_launch()) return e;
     return 1;
 }

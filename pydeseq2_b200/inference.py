@@ -144,6 +144,12 @@ class _CudaOps:
                                                             as_f64p(all_zero)))
 
 
+    def cooks(self, counts, ld, N, G, sf, X, p, mu, hat, ld2, cutoff, cooks, disp, outlier, replaced):
+        self._io((counts, mu, hat), (disp, outlier, replaced) + ((cooks,) if cooks is not None else ()))
+        self.ctx.check(self.lib.pdq_calculate_cooks(self.ctx.h, as_i64p(counts), ld, N, G, as_f64p(sf), as_f64p(X), p, as_f64p(mu),
+                                                    as_f64p(hat), ld2, cutoff, as_f64p(cooks) if cooks is not None else None,
+                                                    as_f64p(disp), as_f64p(outlier), as_f64p(replaced)))
+
     def size_factors(self, counts, ld, N, G, sf):
         self._io((counts,), (sf,))
         self.ctx.check(self.lib.pdq_size_factors(self.ctx.h, as_i64p(counts), ld, N, G, as_f64p(sf)))
@@ -324,6 +330,38 @@ class B200Inference(_InferenceBase):
         if not np.isfinite(sf).all():
             raise ValueError("Every gene contains at least one zero, cannot compute log geometric means.")
         return counts / sf[:, None], sf
+
+    def calculate_cooks(self, counts, size_factors, design_matrix, mu, hat_diagonals, return_matrix=True):
+        """Cook's distances on the device (``DeseqDataSet.calculate_cooks``, dds.py:986-1040).
+
+        ``mu`` / ``hat_diagonals`` are what :meth:`irls` returned for the LFC fit (``obsm["_mu_LFC"]``,
+        ``obsm["_hat_diagonals"]``).  Returns ``(cooks (N, G) or None, robust_dispersions (G,), cooks_outlier (G,) bool,
+        replaced (G,) bool)``: the trimmed-moments dispersions of ``utils.robust_method_of_moments_disp``, the genes whose
+        p-value ``cooks_outlier()`` masks (dds.py:1066-1110, before any refit) and the genes ``_replace_outliers`` would
+        refit (dds.py:1320-1323).  With ``return_matrix=False`` the (N, G) matrix never leaves the device.
+        """
+        from scipy.stats import f as _f
+
+        counts, ld = _rows(counts, np.int64, "counts")
+        mu, ld2 = _rows(mu, np.float64, "mu")
+        hat, ld3 = _rows(hat_diagonals, np.float64, "hat_diagonals")
+        if ld3 != ld2:
+            hat = np.ascontiguousarray(hat)
+            mu = np.ascontiguousarray(mu)
+            ld2 = mu.shape[1]
+        X = np.ascontiguousarray(_f64(design_matrix, "design_matrix", 2))
+        sf = np.ascontiguousarray(_f64(size_factors, "size_factors", 1))
+        N, G = counts.shape
+        p = X.shape[1]
+        self._check_design(X, N, sf)
+        if mu.shape != (N, G) or hat.shape != (N, G):
+            raise ValueError("counts, mu and hat_diagonals disagree on the number of samples/genes")
+        cutoff = float(_f.ppf(0.99, p, N - p))
+        cooks = self._ops.empty((N, G)) if return_matrix else None
+        disp, outlier, replaced = np.empty(G), np.empty(G), np.empty(G)
+        if G:
+            self._ops.cooks(counts, ld, N, G, sf, X, p, mu, hat, ld2, cutoff, cooks, disp, outlier, replaced)
+        return cooks, disp, outlier == 1.0, replaced == 1.0
 
     def lfc_shrink_nbinom_glm(self, design_matrix, counts, size, offset, prior_no_shrink_scale, prior_scale, optimizer,
                               shrink_index):  # noqa: D102

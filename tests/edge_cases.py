@@ -157,3 +157,51 @@ def check_size_factors(inf):
     bad = np.array([[0, 3, 5], [2, 0, 1], [4, 1, 0]], dtype=np.int64)
     with pytest.raises(ValueError, match="at least one zero"):
         inf.size_factors(bad)
+
+
+def check_cooks(inf):
+    """Cook's distances, trimmed-moments dispersions and the two per-gene decisions against the REAL orchestrator's layers
+    (tape goldens) and, on seeded inputs with planted outliers, against the oracle."""
+    for name in ("tape_single_factor", "tape_multi_factor", "tape_continuous", "tape_wide"):
+        t = load_golden(name)
+        nz = t["final_non_zero"] == 1
+        counts = np.ascontiguousarray(t["counts"][:, nz])
+        ck, disp, outl, repl = inf.calculate_cooks(counts, t["final_size_factors"], t["design"], t["final_mu_LFC"], t["final_hat"])
+        assert_close(disp, t["final_robust_disp"], 1e-10, f"{name}: robust dispersions")
+        assert_close(ck, t["final_cooks"][:, nz], 1e-9, f"{name}: cooks")
+        np.testing.assert_array_equal(outl, t["final_cooks_outlier"][nz] == 1)
+        np.testing.assert_array_equal(repl, t["final_replaced"][nz] == 1)
+        ck2, disp2, outl2, repl2 = inf.calculate_cooks(counts, t["final_size_factors"], t["design"], t["final_mu_LFC"],
+                                                       t["final_hat"], return_matrix=False)
+        assert ck2 is None
+        np.testing.assert_array_equal(disp2, disp)
+    t = load_golden("tape_multi_factor_outliers")  # a design level with ONE replicate: that sample sits in no cell
+    nz = t["final_non_zero"] == 1
+    normed = t["counts"][:, nz] / t["final_size_factors"][:, None]
+    _, disp, _, _ = inf.calculate_cooks(np.ascontiguousarray(t["counts"][:, nz]), t["final_size_factors"], t["design"],
+                                        np.ones_like(normed), np.full_like(normed, 0.1))
+    assert_close(disp, t["final_robust_disp"], 1e-10, "outlier tape: robust dispersions")
+    # seeded inputs with planted outliers, several designs (cells of 100, of 25, and none at all)
+    rng = np.random.default_rng(3)
+    for N, G, kind in ((40, 300, "two_level"), (60, 200, "factorial"), (30, 100, "continuous"), (9, 64, "five")):
+        counts, X, _ = make_counts(N, G, kind, seed=N)
+        counts = np.ascontiguousarray(counts[:, ~(counts == 0).all(0)])
+        G = counts.shape[1]
+        hit = rng.choice(G, G // 10, replace=False)
+        counts[rng.integers(0, N, len(hit)), hit] *= 40
+        counts[0, hit[:3]] += 5000
+        normed, sf = median_of_ratios(counts)
+        disp = np.clip(nbglm.fit_moments_dispersions(normed, sf), 1e-3, 10.0)
+        ref_inf = nbglm.OracleInference(n_cpus=1)
+        beta, mu, hat, _ = ref_inf.irls(counts, sf, X, disp, 0.5, 1e-8)
+        mu, hat = np.ascontiguousarray(mu), np.ascontiguousarray(hat)
+        want_ck, want_disp = nbglm.calculate_cooks(counts, normed, X, mu, hat)
+        ck, rd, outl, repl = inf.calculate_cooks(counts, sf, X, mu, hat)
+        assert_close(rd, want_disp, 1e-10, f"{kind}: robust dispersions")
+        assert_close(ck, want_ck, 1e-9, f"{kind}: cooks")
+        np.testing.assert_array_equal(outl, nbglm.cooks_outlier(counts, want_ck, X))
+        from scipy.stats import f
+
+        np.testing.assert_array_equal(repl, (want_ck > f.ppf(0.99, X.shape[1], N - X.shape[1])).any(0))
+        if kind != "continuous" and N >= 30:
+            assert outl.sum() >= 1

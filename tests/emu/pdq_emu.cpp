@@ -193,6 +193,22 @@ int emu_trend_fit(const double* x, const double* t, size_t n, int x_is_mean, dou
     return 0;
 }
 
+int emu_cooks(const int64_t* counts, int64_t ld, int N, int G, const double* sf, const double* X, int p, const double* mu,
+              const double* hat, int64_t ld2, double cutoff, double* cooks, double* disp, double* outlier, double* replaced) {
+    Pack k = make_pack(X, sf, N, p);
+    const std::vector<int> plan = design_cell_plan(X, N, p);
+    const int n_cells = plan[0];
+    const int nf = (int)plan.size() - (2 + n_cells + 1);
+    const CellPlan cp{plan.data() + 2 + n_cells + 1, plan.data() + 2, n_cells, plan[1]};
+    std::vector<double> vals((size_t)2 * nf);
+    EMU_DISPATCH(p, {
+        for (int g = 0; g < G; ++g)
+            cooks_gene<P>(kOne, k.d, cp, counts + g, ld, mu + g, hat + g, ld2, cutoff, vals.data(), vals.data() + nf,
+                          cooks ? cooks + g : nullptr, G, disp + g, outlier + g, replaced + g, true);
+    });
+    return 0;
+}
+
 // median-of-ratios size factors with the device's selection code (k_log_means + k_size_factor_median, one "thread")
 int emu_size_factors(const int64_t* counts, int64_t ld, int N, int G, double* sf) {
     std::vector<double> lm((size_t)G), row((size_t)G);

@@ -44,3 +44,7 @@ def test_alpha_grid_fallback(backend):
 
 def test_size_factors(backend):
     ec.check_size_factors(backend[0])
+
+
+def test_cooks(backend):
+    ec.check_cooks(backend[0])

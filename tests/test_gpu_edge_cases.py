@@ -60,3 +60,7 @@ def test_design_too_large_is_reported(inf):
 
 def test_size_factors(inf):
     ec.check_size_factors(inf)
+
+
+def test_cooks(inf):
+    ec.check_cooks(inf)

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 CALLS = ["calls_two_level_n24", "calls_factorial_n30", "calls_continuous_n40", "calls_two_level_n200",
          "calls_large_counts_n12", "calls_five_columns_n36", "calls_intercept_n10", "calls_few_samples_n4"]
-TAPES = ["tape_single_factor", "tape_multi_factor", "tape_continuous", "tape_wide"]
+TAPES = ["tape_single_factor", "tape_multi_factor", "tape_continuous", "tape_wide", "tape_multi_factor_outliers"]
 
 
 @pytest.fixture(scope="module")

@@ -8,7 +8,7 @@ from conftest import load_golden, tape_calls
 
 CALLS = ["calls_two_level_n24", "calls_factorial_n30", "calls_continuous_n40", "calls_two_level_n200",
          "calls_large_counts_n12", "calls_five_columns_n36", "calls_intercept_n10", "calls_few_samples_n4"]
-TAPES = ["tape_single_factor", "tape_multi_factor", "tape_continuous", "tape_wide"]
+TAPES = ["tape_single_factor", "tape_multi_factor", "tape_continuous", "tape_wide", "tape_multi_factor_outliers"]
 # the oracle runs the same scipy/numpy wheels as the reference: expect agreement to rounding
 RTOL = 1e-9
 
@@ -72,3 +72,19 @@ def test_nb_nll_is_a_normalised_pmf():
         assert abs(pmf.sum() - 1) < 1e-6
         assert abs((pmf * y).sum() - mu) < 1e-4 * mu
         assert abs((pmf * (y - mu) ** 2).sum() - (mu + alpha * mu**2)) < 1e-3 * (mu + alpha * mu**2)
+
+
+@pytest.mark.parametrize("name", TAPES)
+def test_oracle_cooks(name):
+    """Cook's distances / robust dispersions / Cook's p-value filter against the real orchestrator's layers."""
+    t = load_golden(name)
+    nz = t["final_non_zero"] == 1
+    counts = t["counts"][:, nz]
+    X, sf = t["design"], t["final_size_factors"]
+    normed = counts / sf[:, None]
+    np.testing.assert_allclose(nbglm.robust_method_of_moments_disp(normed, X), t["final_robust_disp"], rtol=1e-12)
+    if name == "tape_multi_factor_outliers":
+        return  # after a refit the stored mu/hat belong to the refitted genes; the pre-refit cooks layer is kept as is
+    cooks, disp = nbglm.calculate_cooks(counts, normed, X, t["final_mu_LFC"], t["final_hat"])
+    np.testing.assert_allclose(cooks, t["final_cooks"][:, nz], rtol=1e-10)
+    np.testing.assert_array_equal(nbglm.cooks_outlier(counts, cooks, X), t["final_cooks_outlier"][nz] == 1)
