@@ -253,6 +253,10 @@ def main():
     rf.run(profile=True)
     rf.run(profile=True)
     stages = dict(rf.stage_ms)
+    rf.with_cooks = True  # Cook's distances: reported for information, NOT part of the timed step
+    rf.run(profile=True)
+    stages["cooks_untimed"] = rf.stage_ms.get("cooks")
+    rf.with_cooks = False
     rf.device_size_factors()  # first call allocates its scratch
     ctx.sync()
     t0 = time.perf_counter()

@@ -218,7 +218,8 @@ class ResidentFit:
     gathers the per-gene vectors of all gene shards where the path needs them.
     """
 
-    def __init__(self, ctx, X, size_factors, min_mu=0.5, min_disp=1e-8, max_disp=10.0, beta_tol=1e-8, comm=None):
+    def __init__(self, ctx, X, size_factors, min_mu=0.5, min_disp=1e-8, max_disp=10.0, beta_tol=1e-8, comm=None,
+                 with_cooks=False):
         from . import _lib
 
         self._lib_mod = _lib
@@ -229,6 +230,7 @@ class ResidentFit:
         self.min_mu, self.min_disp, self.beta_tol = min_mu, min_disp, beta_tol
         self.max_disp = max(max_disp, self.N)
         self.comm = comm
+        self.with_cooks = with_cooks  # also compute Cook's distances (per-gene outlier flags) after the LFC fit
         self.design = None
         self.sf = None
         if size_factors is not None:  # None: median of ratios on the device from the uploaded counts (see upload)
@@ -415,7 +417,9 @@ class ResidentFit:
         return {"mom": H["mom"], "genewise": gw, "genewise_converged": H["gw_conv"], "trend": trend, "prior_var": prior_var,
                 "squared_logres": sq, "map": np.clip(H["map"], self.min_disp, self.max_disp), "map_converged": H["map_conv"],
                 "dispersions": H["disp"], "lfc": H["beta"], "lfc_converged": H["conv"], "pvalue": H["pv"], "stat": H["stat"],
-                "se": H["se"], "normed_means": means, "fitted": fitted, "outlier": H["outlier"]}
+                "se": H["se"], "normed_means": means, "fitted": fitted, "outlier": H["outlier"],
+                **({"robust_dispersions": H["robust_disp"], "cooks_outlier": H["cooks_outlier"] == 1.0,
+                    "cooks_replaced": H["cooks_replaced"] == 1.0} if self.with_cooks else {})}
 
     def _tail(self, d_fitted, d_t16, d_prior_var, prior_var, contrast, ridge, lfc_null, alt_hypothesis, begin, check):
         """MAP dispersions -> final dispersions -> LFC fit -> Wald, all enqueued without host synchronisation."""
@@ -443,6 +447,20 @@ class ResidentFit:
         check(L.pdq_wald_test_dev(h, d, c_d(self.d_disp), c_d(self.d_beta), c_d(self.d_mu), G, G,
                                   self._lib_mod.as_f64p(ridge), self._lib_mod.as_f64p(contrast), LN2 * lfc_null,
                                   self._lib_mod.ALT_CODES[alt_hypothesis], c_d(self.d_pv), c_d(self.d_stat), c_d(self.d_se)))
+        # 8. optional: Cook's distances from the resident mu / hat (dds.py:986-1040); only per-gene results leave the device
+        if self.with_cooks:
+            from scipy.stats import f as _f
+
+            for k in ("robust_disp", "cooks_outlier", "cooks_replaced"):
+                if k not in H:
+                    H[k] = ctx.pinned_empty((G,))
+                    setattr(self, "d_" + k, self._dev(k, G * 8))
+            begin("cooks")
+            check(L.pdq_cooks_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu), c_d(self.d_hat), G,
+                                  float(_f.ppf(0.99, self.p, self.N - self.p)), None, G, c_d(self.d_robust_disp),
+                                  c_d(self.d_cooks_outlier), c_d(self.d_cooks_replaced)))
+            for k in ("robust_disp", "cooks_outlier", "cooks_replaced"):
+                ctx.d2h(H[k], getattr(self, "d_" + k))
         for k in ("map", "map_conv", "disp", "pv", "stat", "se", "conv", "beta", "mom", "outlier"):
             ctx.d2h(H[k], getattr(self, "d_" + k))
 

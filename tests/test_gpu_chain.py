@@ -83,6 +83,13 @@ def test_resident_driver_equals_host_buffer_driver(inf, N, G, kind):
     np.testing.assert_allclose(r["lfc"], host.lfc, rtol=1e-6, atol=1e-10)
     np.testing.assert_allclose(r["stat"], host.stat, rtol=1e-6, atol=1e-10)
     np.testing.assert_allclose(r["pvalue"], host.pvalue, rtol=1e-5, atol=1e-300)
+    rf.with_cooks = True  # Cook's distances from the resident mu / hat, per-gene results only
+    rc = rf.run()
+    ck, rd, outl, repl = inf.calculate_cooks(counts, sf, X, *inf.irls(counts, sf, X, rc["dispersions"], 0.5, 1e-8)[1:3])
+    np.testing.assert_allclose(rc["robust_dispersions"], rd, rtol=1e-12)
+    np.testing.assert_array_equal(rc["cooks_outlier"], outl)
+    np.testing.assert_array_equal(rc["cooks_replaced"], repl)
+    rf.with_cooks = False
     rf_auto = ResidentFit(inf._ops.ctx, X, None)  # size factors by median of ratios on the device
     rf_auto.upload(counts)
     np.testing.assert_allclose(rf_auto.sf, sf, rtol=1e-12)
