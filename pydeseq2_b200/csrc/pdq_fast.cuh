@@ -1,6 +1,6 @@
 // pdq_fast.cuh -- FP64 log / exp / reciprocal tuned for the sm_100a FP64 pipe.
 //
-// Why not libdevice's `log`, `exp` and the `/` operator: the ncu profile of round 1 (profiles/r1_alpha_mle.md)
+// Why not libdevice's `log`, `exp` and the `/` operator: the ncu profile of round 1 (profiles/README.md)
 // showed that 32 % of all issued warp instructions were UMOV / IMAD.MOV pairs materialising 64-bit polynomial
 // coefficients next to every DFMA, plus BSSY/BSYNC/branch scaffolding around each division's slow path.  Here
 //   * coefficients live in __constant__ memory, so DFMA takes them as constant-bank operands (no extra instruction);
