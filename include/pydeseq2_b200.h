@@ -81,6 +81,16 @@ int pdq_sync(pdq_ctx* ctx);
 int pdq_event_record(pdq_ctx* ctx, int slot);
 int pdq_event_elapsed_ms(pdq_ctx* ctx, int slot_start, int slot_stop, float* ms);
 
+/* CUDA-graph capture of a sequence of `*_dev` calls (the resident pipeline enqueues ~20 launches + copies per pass and
+ * never synchronises in between: replaying them as ONE graph removes the per-launch host cost).  Everything enqueued on the
+ * context between begin and end is recorded instead of executed; all buffers must already exist (run the sequence once
+ * eagerly first).  `pdq_graph_launch` replays it on the context's stream. */
+typedef struct pdq_graph pdq_graph;
+int pdq_capture_begin(pdq_ctx* ctx);
+int pdq_capture_end(pdq_ctx* ctx, pdq_graph** out);
+int pdq_graph_launch(pdq_ctx* ctx, pdq_graph* g);
+void pdq_graph_destroy(pdq_ctx* ctx, pdq_graph* g);
+
 /* Design pack.  X is (N x p) row-major as the reference passes `design_matrix`
  * (`dds.py:740`), size_factors (N,) may be NULL for calls that take none (alpha_mle, wald_test). */
 int pdq_design_create(pdq_ctx* ctx, const double* X, const double* size_factors, int N, int p,

@@ -53,6 +53,10 @@ _SIGNATURES = {
     "pdq_sync": (C.c_int, [c_ctx]),
     "pdq_event_record": (C.c_int, [c_ctx, C.c_int]),
     "pdq_event_elapsed_ms": (C.c_int, [c_ctx, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "pdq_capture_begin": (C.c_int, [c_ctx]),
+    "pdq_capture_end": (C.c_int, [c_ctx, C.POINTER(C.c_void_p)]),
+    "pdq_graph_launch": (C.c_int, [c_ctx, C.c_void_p]),
+    "pdq_graph_destroy": (None, [c_ctx, C.c_void_p]),
     "pdq_design_create": (C.c_int, [c_ctx, f64p, f64p, C.c_int, C.c_int, C.POINTER(c_design)]),
     "pdq_design_destroy": (None, [c_ctx, c_design]),
     "pdq_lin_reg_mu": (C.c_int, [c_ctx, i64p, C.c_int64, C.c_int, C.c_int, f64p, f64p, C.c_int, C.c_double, f64p]),

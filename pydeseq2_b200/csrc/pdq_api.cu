@@ -55,6 +55,7 @@ struct pdq_ctx {
     int staging = 1;  // PDQ_STAGING=0 disables (plain cudaMemcpyAsync from pageable memory)
     int* tickets = nullptr;  // device ints for the persistent kernels' tile counters
     int debug = 0;           // PDQ_DEBUG_* test hooks
+    int64_t launches_at_capture = 0;
     NcclApi nccl;
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
@@ -264,6 +265,57 @@ extern "C" int pdq_event_elapsed_ms(pdq_ctx* c, int a, int b, float* ms) {
     return PDQ_OK;
 }
 
+#define CHECK_CTX(c) \
+    if (!(c)) return PDQ_ERR_INVALID; \
+    CU(c, cudaSetDevice((c)->device))
+
+// --------------------------------------------------------------------------------------------- CUDA graphs
+struct pdq_graph {
+    cudaGraphExec_t exec = nullptr;
+    int64_t kernels = 0;  // kernel nodes, added to the launch counter on every replay
+};
+
+extern "C" int pdq_capture_begin(pdq_ctx* c) {
+    CHECK_CTX(c);
+    c->launches_at_capture = c->launches;
+    // relaxed: host-side CUDA calls that are not stream work (attribute / occupancy queries) stay legal while capturing
+    CU(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    return PDQ_OK;
+}
+
+extern "C" int pdq_capture_end(pdq_ctx* c, pdq_graph** out) {
+    CHECK_CTX(c);
+    if (!out) return PDQ_ERR_INVALID;
+    cudaGraph_t graph = nullptr;
+    CU(c, cudaStreamEndCapture(c->stream, &graph));
+    pdq_graph* g = new pdq_graph();
+    g->kernels = c->launches - c->launches_at_capture;  // counted by the launchers while recording
+    c->launches = c->launches_at_capture;               // recorded, not executed
+    cudaError_t e = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        delete g;
+        return fail(c, PDQ_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    }
+    *out = g;
+    return PDQ_OK;
+}
+
+extern "C" int pdq_graph_launch(pdq_ctx* c, pdq_graph* g) {
+    CHECK_CTX(c);
+    if (!g || !g->exec) return PDQ_ERR_INVALID;
+    CU(c, cudaGraphLaunch(g->exec, c->stream));
+    c->launches += g->kernels;
+    return PDQ_OK;
+}
+
+extern "C" void pdq_graph_destroy(pdq_ctx* c, pdq_graph* g) {
+    if (!g) return;
+    if (c) cudaSetDevice(c->device);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    delete g;
+}
+
 // --------------------------------------------------------------------------------------------- design pack
 extern "C" int pdq_design_create(pdq_ctx* c, const double* X, const double* sf, int N, int p, pdq_design** out) {
     if (!c || !X || !out || N <= 0 || p < 1) return fail(c, PDQ_ERR_INVALID, "pdq_design_create: bad arguments");
@@ -350,10 +402,6 @@ static int cached_design(pdq_ctx* c, const double* X, const double* sf, int N, i
 }
 
 // --------------------------------------------------------------------------------------------- device-resident ops
-#define CHECK_CTX(c) \
-    if (!(c)) return PDQ_ERR_INVALID; \
-    CU(c, cudaSetDevice((c)->device))
-
 static int done(pdq_ctx* c, int rc, const char* what) {
     if (rc < 0) {
         if (rc == PDQ_ERR_UNSUPPORTED) return fail(c, rc, "%s: unsupported design (p=%d..%d, shared-memory stage <= %zu bytes)", what, 1, PDQ_MAX_P, kMaxDynSmem);

@@ -231,6 +231,8 @@ class ResidentFit:
         self.max_disp = max(max_disp, self.N)
         self.comm = comm
         self.with_cooks = with_cooks  # also compute Cook's distances (per-gene outlier flags) after the LFC fit
+        self.use_graph = True         # replay the pass as one CUDA graph after the first eager pass
+        self._graph, self._graph_key, self._eager_key = None, None, None
         self.design = None
         self.sf = None
         if size_factors is not None:  # None: median of ratios on the device from the uploaded counts (see upload)
@@ -249,6 +251,8 @@ class ResidentFit:
         self.ctx.check(self.lib.pdq_design_create(self.ctx.h, _lib.as_f64p(self.X), _lib.as_f64p(self.sf), self.N, self.p,
                                                   C.byref(d)))
         self.design = d
+        self._drop_graph()  # a captured pass holds the old design pack
+        self._eager_key = None
 
     def device_size_factors(self):
         """Median-of-ratios size factors from the resident counts (preprocessing.py:31-102); rebuilds the design pack.
@@ -277,6 +281,8 @@ class ResidentFit:
         """H2D of this shard's counts (genes that are all-zero must already be dropped, dds.py:729-731)."""
         counts = np.ascontiguousarray(counts, dtype=np.int64)
         assert counts.shape[0] == self.N
+        self._drop_graph()  # buffers may move
+        self._eager_key = None
         self.G = counts.shape[1]
         G, N, p = self.G, self.N, self.p
         ng = N * G * 8
@@ -296,7 +302,13 @@ class ResidentFit:
                                                               "disp", "conv", "pv", "stat", "se")}
         self._h["beta"] = self.ctx.pinned_empty((G, p))
 
+    def _drop_graph(self):
+        if self._graph is not None:
+            self.lib.pdq_graph_destroy(self.ctx.h, self._graph)
+        self._graph, self._graph_key = None, None
+
     def close(self):
+        self._drop_graph()
         for ptr, _ in self._bufs.values():
             self.ctx.free(ptr)
         self._bufs = {}
@@ -335,51 +347,74 @@ class ResidentFit:
         contrast = np.ascontiguousarray(contrast, dtype=np.float64)
         ridge = np.ascontiguousarray(np.diag(np.repeat(1e-6, p)))
         trigamma_c = float(polygamma(1, (N - p) / 2))
-        # 1. method-of-moments start values + normalised means (dds.py:1140-1162, :708)
-        begin("mom_dispersions")
-        check(L.pdq_mom_dispersions_dev(h, d, c_d(self.d_counts), G, G, self.min_disp, self.max_disp, c_d(self.d_mom),
-                                        c_d(self.d_means)))
-        # 2. initial mu_hat (dds.py:747-765)
-        if self.lin_branch:
-            begin("lin_reg_mu")
-            check(L.pdq_lin_reg_mu_dev(h, d, c_d(self.d_counts), G, G, self.min_mu, c_d(self.d_mu_hat), G))
-        else:
-            begin("irls_init")
-            check(L.pdq_irls_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mom), self.min_mu, self.beta_tol, -30.0, 30.0,
-                                 250, c_d(self.d_beta0), c_d(self.d_mu_hat), c_d(self.d_hat), G, c_d(self.d_conv),
-                                 c_d(self.d_nfb)))
-        # 3. genewise dispersions (dds.py:778-797)
-        begin("alpha_mle_genewise")
-        check(L.pdq_alpha_mle_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(self.d_mom), self.min_disp,
-                                  self.max_disp, 1.0, None, 1, 0, c_d(self.d_gw), c_d(self.d_gw_conv)))
-        # 4. trend + prior: global over ALL genes of ALL shards (dds.py:799-884).  With gene shards the per-gene
-        #    vectors are all-gathered over NCCL first, device to device; the fit itself is one cluster launch.
         W = self.comm.world if self.comm is not None else 1
         rank = self.comm.rank if self.comm is not None else 0
         m = self.comm.max_size if self.comm is not None else G
         n_all = W * m
         if self.comm is not None:
             d_gw_all, d_means_all = self._dev("gw_all", n_all * 8), self._dev("means_all", n_all * 8)
-            begin("allgather")
-            self.comm.allgather_dev(self.d_gw, d_gw_all, self.d_means, d_means_all, G)
-            if profile:
-                check(0)
         else:
             d_gw_all, d_means_all = self.d_gw, self.d_means
         d_fit_all = self._dev("fitted_all", n_all * 8)
         d_t16 = self._dev("trend16", 128)
         d_fitted = d_fit_all + rank * m * 8  # this shard's slice of the fitted curve
-        if fit_type == "parametric":
-            begin("trend_prior")
-            check(L.pdq_trend_fit_dev(h, c_d(d_means_all), c_d(d_gw_all), n_all, self.min_disp, self.max_disp, trigamma_c,
-                                      c_d(d_t16), c_d(d_fit_all)))
-            self._tail(d_fitted, d_t16, d_t16 + 9 * 8, 0.0, contrast, ridge, lfc_null, alt_hypothesis, begin, check)
         if "t16" not in H:
             H["t16"] = ctx.pinned_empty((16,))
-        if fit_type == "parametric":
-            ctx.d2h(H["t16"], d_t16)
-        for k in ("gw", "gw_conv", "means"):
-            ctx.d2h(H[k], getattr(self, "d_" + k))
+
+        def enqueue():
+            # 1. method-of-moments start values + normalised means (dds.py:1140-1162, :708)
+            begin("mom_dispersions")
+            check(L.pdq_mom_dispersions_dev(h, d, c_d(self.d_counts), G, G, self.min_disp, self.max_disp, c_d(self.d_mom),
+                                            c_d(self.d_means)))
+            # 2. initial mu_hat (dds.py:747-765)
+            if self.lin_branch:
+                begin("lin_reg_mu")
+                check(L.pdq_lin_reg_mu_dev(h, d, c_d(self.d_counts), G, G, self.min_mu, c_d(self.d_mu_hat), G))
+            else:
+                begin("irls_init")
+                check(L.pdq_irls_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mom), self.min_mu, self.beta_tol, -30.0, 30.0,
+                                     250, c_d(self.d_beta0), c_d(self.d_mu_hat), c_d(self.d_hat), G, c_d(self.d_conv),
+                                     c_d(self.d_nfb)))
+            # 3. genewise dispersions (dds.py:778-797)
+            begin("alpha_mle_genewise")
+            check(L.pdq_alpha_mle_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(self.d_mom), self.min_disp,
+                                      self.max_disp, 1.0, None, 1, 0, c_d(self.d_gw), c_d(self.d_gw_conv)))
+            # 4. trend + prior: global over ALL genes of ALL shards (dds.py:799-884).  With gene shards the per-gene
+            #    vectors are all-gathered over NCCL first, device to device; the fit itself is one cluster launch.
+            if self.comm is not None:
+                begin("allgather")
+                self.comm.allgather_dev(self.d_gw, d_gw_all, self.d_means, d_means_all, G)
+                if profile:
+                    check(0)
+            if fit_type == "parametric":
+                begin("trend_prior")
+                check(L.pdq_trend_fit_dev(h, c_d(d_means_all), c_d(d_gw_all), n_all, self.min_disp, self.max_disp, trigamma_c,
+                                          c_d(d_t16), c_d(d_fit_all)))
+                self._tail(d_fitted, d_t16, d_t16 + 9 * 8, 0.0, contrast, ridge, lfc_null, alt_hypothesis, begin, check)
+            if fit_type == "parametric":
+                ctx.d2h(H["t16"], d_t16)
+            for k in ("gw", "gw_conv", "means"):
+                ctx.d2h(H[k], getattr(self, "d_" + k))
+
+        # The pass is ~20 launches + copies with no host synchronisation in between: after one eager pass (which allocates
+        # every buffer) the identical sequence is captured into a CUDA graph and replayed with a single call.
+        ragged = self.comm is not None and len(set(self.comm.sizes)) > 1  # NaN-padding stages through pageable memory
+        key = (fit_type, contrast.tobytes(), float(lfc_null), alt_hypothesis, G, self.with_cooks, n_all)
+        if self.use_graph and not profile and not ragged and self._graph is not None and self._graph_key == key:
+            ctx.check(L.pdq_graph_launch(h, self._graph))
+        elif self.use_graph and not profile and not ragged and self._eager_key == key:
+            self._drop_graph()
+            ctx.check(L.pdq_capture_begin(h))
+            try:
+                enqueue()
+            finally:
+                g = C.c_void_p()
+                ctx.check(L.pdq_capture_end(h, C.byref(g)))
+            self._graph, self._graph_key = g, key
+            ctx.check(L.pdq_graph_launch(h, self._graph))
+        else:
+            enqueue()
+            self._eager_key = key
         ctx.sync()  # the only host synchronisation of the pass
         t16 = H["t16"]
         if fit_type == "parametric" and t16[2] == 0.0:
