@@ -180,7 +180,9 @@ int pdq_wald_test_dev(pdq_ctx* ctx, const pdq_design* design, const double* disp
  * per-gene normalised mean (`dds.py:708`).  Device-resident pipeline only. */
 int pdq_mom_dispersions_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld,
                             int G, double min_disp, double max_disp, double* alpha_out,
-                            double* normed_mean_out);
+                            double* normed_mean_out, double min_mu,
+                            double* mu_hat_out /* (N,G), may be NULL: also the lin_reg_mu result, same projection */,
+                            int64_t ld_mu);
 /* Parametric dispersion trend INCLUDING the caller's outer loop (dds.py:1199-1275: fit, drop genes with
  * genewise/fitted outside [1e-4, 15), refit until sum(log(c/c_old)^2) < 1e-6) AND the dispersion prior
  * (dds.py:840-884: squared scaled MAD of the log residuals, prior variance), entirely on the device in one launch of

@@ -76,7 +76,7 @@ _SIGNATURES = {
     "pdq_wald_test_dev": (C.c_int, [c_ctx, c_design, c_dptr, c_dptr, c_dptr, C.c_int64, C.c_int, f64p, f64p, C.c_double,
                                     C.c_int, c_dptr, c_dptr, c_dptr]),
     "pdq_mom_dispersions_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, C.c_double, C.c_double, c_dptr,
-                                          c_dptr]),
+                                          c_dptr, C.c_double, c_dptr, C.c_int64]),
     "pdq_calculate_cooks": (C.c_int, [c_ctx, i64p, C.c_int64, C.c_int, C.c_int, f64p, f64p, C.c_int, f64p, f64p, C.c_int64,
                                       C.c_double, f64p, f64p, f64p, f64p]),
     "pdq_cooks_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, c_dptr, c_dptr, C.c_int64, C.c_double, c_dptr,

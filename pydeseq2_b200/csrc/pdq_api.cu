@@ -453,11 +453,14 @@ extern "C" int pdq_wald_test_dev(pdq_ctx* c, const pdq_design* d, const double* 
 }
 
 extern "C" int pdq_mom_dispersions_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, double min_disp,
-                                       double max_disp, double* alpha, double* normed_mean) {
+                                       double max_disp, double* alpha, double* normed_mean, double min_mu, double* mu_hat_out,
+                                       int64_t ld_mu) {
     CHECK_CTX(c);
-    if (!d || !counts || !alpha || !normed_mean || G <= 0 || ld < G) return fail(c, PDQ_ERR_INVALID, "pdq_mom_dispersions_dev: bad arguments");
+    if (!d || !counts || !alpha || !normed_mean || G <= 0 || ld < G || (mu_hat_out && ld_mu < G))
+        return fail(c, PDQ_ERR_INVALID, "pdq_mom_dispersions_dev: bad arguments");
     if (d->d.N == d->d.p) return fail(c, PDQ_ERR_INVALID, "The number of samples and the number of design variables are equal");
-    return done(c, launch_mom_from_counts(cfg(c, G, d->d.N), d->d, counts, ld, G, min_disp, max_disp, alpha, normed_mean), "mom_dispersions");
+    return done(c, launch_mom_from_counts(cfg(c, G, d->d.N), d->d, counts, ld, G, min_disp, max_disp, alpha, normed_mean, min_mu, mu_hat_out, ld_mu),
+                "mom_dispersions");
 }
 
 extern "C" int pdq_mu_from_lfc_dev(pdq_ctx* c, const pdq_design* d, const double* lfc, int G, double* mu, int64_t ld_out) {

@@ -1003,6 +1003,71 @@ PDQ_HD double rough_disp_gene(const Group& grp, const DesignS& d, const SmallMat
     return (acc < 0.0) ? 0.0 : acc;  // np.maximum(alpha_rde, 0)
 }
 
+// Resident pipeline: rough + moments estimators, their min/clip (dds.py:1140-1162), the normalised mean (dds.py:708) and --
+// because lin_reg_mu is the SAME least-squares projection of counts/sf (utils.py:711-713 vs :846-848) -- optionally the
+// initial mu_hat = max(sf * X beta, min_mu) (utils.py:682-715), in two sweeps over the gene instead of six.
+template <int P>
+PDQ_HD void mom_fused_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pinv, const int64_t* y, int64_t ld,
+                           double s_mean_inv, double min_disp, double max_disp, double min_mu, double* alpha_out,
+                           double* mean_out, double* mu_out, int64_t ld_out, bool valid) {
+    double v[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) v[j] = 0.0;
+    double s = 0.0;
+    const int64_t ystep = (int64_t)grp.T * ld;
+    const int64_t* yp = y + (int64_t)grp.si * ld;
+    for (int n = grp.si; n < d.N; n += grp.T, yp += ystep) {
+        double x[P];
+        load_x<P>(d, n, x);
+        const double t = (double)*yp / d.sf[n];
+        s += t;
+#pragma unroll
+        for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
+    }
+    group_sum_vec<P>(grp, v);
+    const double m = grp.sum(s) / (double)d.N;
+    double beta[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) acc = fma(pinv.v[i * P + j], v[j], acc);
+        beta[i] = acc;
+    }
+    double rough = 0.0, ss = 0.0;
+    yp = y + (int64_t)grp.si * ld;
+    for (int n = grp.si; n < d.N; n += grp.T, yp += ystep) {
+        double x[P];
+        load_x<P>(d, n, x);
+        double fit = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) fit = fma(x[j], beta[j], fit);
+        const double t = (double)*yp / d.sf[n];
+        const double yh = (fit < 1.0) ? 1.0 : fit;  // np.maximum(y_hat, 1)
+        const double e = t - yh;
+        rough += (e * e - yh) / (yh * yh);
+        const double dm = t - m;
+        ss = fma(dm, dm, ss);
+        if (mu_out && valid) {
+            const double mu = d.sf[n] * fit;
+            mu_out[n * ld_out] = (mu < min_mu) ? min_mu : mu;
+        }
+    }
+    rough = grp.sum(rough) / (double)(d.N - P);
+    rough = (rough < 0.0) ? 0.0 : rough;  // np.maximum(alpha_rde, 0)
+    const double var = grp.sum(ss) / (double)(d.N - 1);
+    double mde = (var - s_mean_inv * m) / (m * m);
+    if (!(mde == mde)) mde = 0.0;  // np.nan_to_num
+    else if (mde > 1.7976931348623157e308) mde = 1.7976931348623157e308;
+    else if (mde < -1.7976931348623157e308) mde = -1.7976931348623157e308;
+    if (valid && grp.si == 0) {
+        double a = (mde < rough) ? mde : rough;                                // np.minimum (dds.py:1158)
+        a = (a < min_disp) ? min_disp : ((a > max_disp) ? max_disp : a);       // np.clip (dds.py:1161)
+        *alpha_out = a;
+        *mean_out = m;
+    }
+}
+
 // returns the moments estimate; `mean_out` = per-gene mean of the normalised counts, `all_zero` flag
 template <class Y>
 PDQ_HD double moments_disp_gene(const Group& grp, const DesignS& d, const Y& yy, double s_mean_inv, double& mean_out,

@@ -51,7 +51,8 @@ int launch_rough(const LaunchCfg&, const DesignDev&, const double* normed, int64
 int launch_moments(const LaunchCfg&, const DesignDev&, const double* normed, int64_t ld, int G, double* alpha,
                    double* all_zero);
 int launch_mom_from_counts(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64_t ld, int G,
-                           double min_disp, double max_disp, double* alpha, double* normed_mean);
+                           double min_disp, double max_disp, double* alpha, double* normed_mean, double min_mu, double* mu_hat,
+                           int64_t ld_mu);
 int launch_mu_from_lfc(const LaunchCfg&, const DesignDev&, const double* lfc, int G, double* mu, int64_t ld_out);
 
 int launch_trend_fit(const LaunchCfg&, const double* x, const double* t, double* scratch3n, size_t n, int x_is_mean,

@@ -280,6 +280,9 @@ struct MomArgs {
     int G, lgT;
     double s_mean_inv, min_disp, max_disp;
     double *alpha, *aux;     // aux: all_zero flags (moments) or normalised means (fused)
+    double min_mu;           // fused kernel only: also write mu_hat = max(sf * X beta, min_mu) when mu_hat != nullptr
+    double* mu_hat;
+    int64_t ld_mu;
 };
 
 template <int P>
@@ -319,17 +322,8 @@ __global__ void __launch_bounds__(kBlock) k_mom_from_counts(const __grid_constan
     int g;
     bool valid;
     map_lanes(a.lgT, a.G, grp, g, valid);
-    const NormedFromCounts yy{a.counts + g, a.ld};
-    const double rde = rough_disp_gene<P>(grp, d, a.pinv, yy);
-    double mean;
-    bool az;
-    const double mde = moments_disp_gene(grp, d, yy, a.s_mean_inv, mean, az);
-    if (valid && grp.si == 0) {
-        double v = (mde < rde) ? mde : rde;                       // np.minimum (dds.py:1158)
-        v = (v < a.min_disp) ? a.min_disp : ((v > a.max_disp) ? a.max_disp : v);  // np.clip (dds.py:1161)
-        a.alpha[g] = v;
-        a.aux[g] = mean;
-    }
+    mom_fused_gene<P>(grp, d, a.pinv, a.counts + g, a.ld, a.s_mean_inv, a.min_disp, a.max_disp, a.min_mu, a.alpha + g, a.aux + g,
+                      a.mu_hat ? a.mu_hat + g : nullptr, a.ld_mu, valid);
 }
 
 template <int P>
@@ -782,7 +776,7 @@ int launch_wald(const LaunchCfg& c, const DesignDev& d, const double* disp, cons
 int launch_rough(const LaunchCfg& c, const DesignDev& d, const double* normed, int64_t ld, int G, double* alpha) {
     PDQ_DISPATCH_P(d.p, {
         MomArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d), normed, nullptr, ld, G, c.lgT, d.s_mean_inv, 0.0, 0.0, alpha,
-                     nullptr};
+                     nullptr, 0.0, nullptr, 0};
         if (int e = prep(k_rough<P>, d.smem_bytes)) return e;
         k_rough<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });
@@ -794,7 +788,7 @@ int launch_moments(const LaunchCfg& c, const DesignDev& d, const double* normed,
                    double* all_zero) {
     PDQ_DISPATCH_P(d.p, {
         MomArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d), normed, nullptr, ld, G, c.lgT, d.s_mean_inv, 0.0, 0.0, alpha,
-                     all_zero};
+                     all_zero, 0.0, nullptr, 0};
         if (int e = prep(k_moments<P>, d.smem_bytes)) return e;
         k_moments<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });
@@ -803,10 +797,11 @@ int launch_moments(const LaunchCfg& c, const DesignDev& d, const double* normed,
 }
 
 int launch_mom_from_counts(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G,
-                           double min_disp, double max_disp, double* alpha, double* normed_mean) {
+                           double min_disp, double max_disp, double* alpha, double* normed_mean, double min_mu, double* mu_hat,
+                           int64_t ld_mu) {
     PDQ_DISPATCH_P(d.p, {
         MomArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d), nullptr, counts, ld, G, c.lgT, d.s_mean_inv, min_disp,
-                     max_disp, alpha, normed_mean};
+                     max_disp, alpha, normed_mean, min_mu, mu_hat, ld_mu};
         if (int e = prep(k_mom_from_counts<P>, d.smem_bytes)) return e;
         k_mom_from_counts<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });

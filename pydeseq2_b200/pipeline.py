@@ -290,17 +290,31 @@ class ResidentFit:
         self.d_mu_hat = self._dev("mu_hat", ng)
         self.d_mu = self._dev("mu", ng)
         self.d_hat = self._dev("hat", ng)
-        for name, n in (("mom", G), ("means", G), ("gw", G), ("gw_conv", G), ("fitted", G), ("map", G), ("map_conv", G),
-                        ("disp", G), ("beta", G * p), ("beta0", G * p), ("conv", G), ("pv", G), ("stat", G), ("se", G)):
+        # every per-gene result lives in ONE device slab mirrored by one page-locked host block: a pass ends with a single
+        # device-to-host copy instead of a dozen small ones
+        per_gene = ("mom", "means", "gw", "gw_conv", "map", "map_conv", "disp", "conv", "pv", "stat", "se", "outlier",
+                    "robust_disp", "cooks_outlier", "cooks_replaced")
+        total = len(per_gene) * G + G * p + 16
+        self.d_slab = self._dev("slab", total * 8)
+        self._h_slab = self.ctx.pinned_empty((total,))
+        self._h_slab[:] = 0.0
+        self._h = {}
+        off = 0
+        for name in per_gene:
+            setattr(self, "d_" + name, self.d_slab + off * 8)
+            self._h[name] = self._h_slab[off:off + G]
+            off += G
+        self.d_beta, self._h["beta"] = self.d_slab + off * 8, self._h_slab[off:off + G * p].reshape(G, p)
+        off += G * p
+        self.d_t16, self._h["t16"] = self.d_slab + off * 8, self._h_slab[off:off + 16]
+        for name, n in (("fitted", G), ("beta0", G * p)):
             setattr(self, "d_" + name, self._dev(name, n * 8))
         self.d_nfb = self._dev("nfb", 64)
         self.ctx.h2d(self.d_counts, counts)
         self.ctx.sync()
         if self.design is None:
             self.device_size_factors()
-        self._h = {k: self.ctx.pinned_empty((G,)) for k in ("mom", "means", "gw", "gw_conv", "fitted", "map", "map_conv",
-                                                              "disp", "conv", "pv", "stat", "se")}
-        self._h["beta"] = self.ctx.pinned_empty((G, p))
+        self._h["fitted"] = self.ctx.pinned_empty((G,))
 
     def _drop_graph(self):
         if self._graph is not None:
@@ -356,21 +370,17 @@ class ResidentFit:
         else:
             d_gw_all, d_means_all = self.d_gw, self.d_means
         d_fit_all = self._dev("fitted_all", n_all * 8)
-        d_t16 = self._dev("trend16", 128)
+        d_t16 = self.d_t16
         d_fitted = d_fit_all + rank * m * 8  # this shard's slice of the fitted curve
-        if "t16" not in H:
-            H["t16"] = ctx.pinned_empty((16,))
 
         def enqueue():
             # 1. method-of-moments start values + normalised means (dds.py:1140-1162, :708)
             begin("mom_dispersions")
+            #    -- and, on the lin_reg_mu branch (dds.py:747-756), the initial mu_hat from the same projection
             check(L.pdq_mom_dispersions_dev(h, d, c_d(self.d_counts), G, G, self.min_disp, self.max_disp, c_d(self.d_mom),
-                                            c_d(self.d_means)))
-            # 2. initial mu_hat (dds.py:747-765)
-            if self.lin_branch:
-                begin("lin_reg_mu")
-                check(L.pdq_lin_reg_mu_dev(h, d, c_d(self.d_counts), G, G, self.min_mu, c_d(self.d_mu_hat), G))
-            else:
+                                            c_d(self.d_means), self.min_mu, c_d(self.d_mu_hat) if self.lin_branch else None, G))
+            # 2. initial mu_hat by IRLS otherwise (dds.py:757-765)
+            if not self.lin_branch:
                 begin("irls_init")
                 check(L.pdq_irls_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mom), self.min_mu, self.beta_tol, -30.0, 30.0,
                                      250, c_d(self.d_beta0), c_d(self.d_mu_hat), c_d(self.d_hat), G, c_d(self.d_conv),
@@ -391,10 +401,7 @@ class ResidentFit:
                 check(L.pdq_trend_fit_dev(h, c_d(d_means_all), c_d(d_gw_all), n_all, self.min_disp, self.max_disp, trigamma_c,
                                           c_d(d_t16), c_d(d_fit_all)))
                 self._tail(d_fitted, d_t16, d_t16 + 9 * 8, 0.0, contrast, ridge, lfc_null, alt_hypothesis, begin, check)
-            if fit_type == "parametric":
-                ctx.d2h(H["t16"], d_t16)
-            for k in ("gw", "gw_conv", "means"):
-                ctx.d2h(H[k], getattr(self, "d_" + k))
+            ctx.d2h(self._h_slab, self.d_slab)  # every per-gene result + the trend record, one copy
 
         # The pass is ~20 launches + copies with no host synchronisation in between: after one eager pass (which allocates
         # every buffer) the identical sequence is captured into a CUDA graph and replayed with a single call.
@@ -441,6 +448,7 @@ class ResidentFit:
             ctx.h2d(d_t16, rec)
             ctx.h2d(d_fit_all, fit_all)
             self._tail(d_fitted, d_t16, None, prior_var, contrast, ridge, lfc_null, alt_hypothesis, begin, check)
+            ctx.d2h(self._h_slab, self.d_slab)
             ctx.sync()
         gw = np.clip(H["gw"], self.min_disp, self.max_disp)
         means = H["means"]
@@ -461,9 +469,6 @@ class ResidentFit:
         L, ctx, h, d, G = self.lib, self.ctx, self.ctx.h, self.design, self.G
         c_d = self._lib_mod.c_dptr
         H = self._h
-        if "outlier" not in H:
-            H["outlier"] = ctx.pinned_empty((G,))
-            self.d_outlier = self._dev("outlier", G * 8)
         # 5. MAP dispersions (dds.py:886-935); the prior variance is read from device memory (written by the trend kernel)
         begin("alpha_mle_map")
         check(L.pdq_alpha_mle_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(d_fitted), self.min_disp,
@@ -486,18 +491,10 @@ class ResidentFit:
         if self.with_cooks:
             from scipy.stats import f as _f
 
-            for k in ("robust_disp", "cooks_outlier", "cooks_replaced"):
-                if k not in H:
-                    H[k] = ctx.pinned_empty((G,))
-                    setattr(self, "d_" + k, self._dev(k, G * 8))
             begin("cooks")
             check(L.pdq_cooks_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu), c_d(self.d_hat), G,
                                   float(_f.ppf(0.99, self.p, self.N - self.p)), None, G, c_d(self.d_robust_disp),
                                   c_d(self.d_cooks_outlier), c_d(self.d_cooks_replaced)))
-            for k in ("robust_disp", "cooks_outlier", "cooks_replaced"):
-                ctx.d2h(H[k], getattr(self, "d_" + k))
-        for k in ("map", "map_conv", "disp", "pv", "stat", "se", "conv", "beta", "mom", "outlier"):
-            ctx.d2h(H[k], getattr(self, "d_" + k))
 
 class _HostTrend:
     """The trend GLM of B200Inference without needing a device context."""

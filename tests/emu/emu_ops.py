@@ -69,10 +69,12 @@ class EmuOps:
         N, G = counts.shape
         a = np.empty(G)
         m = np.empty(G)
+        mu = np.empty((N, G))
         rc = self.lib.emu_mom_from_counts(_p(counts, i64p), C.c_int64(G), N, G, _p(sf, f64p), _p(X, f64p), X.shape[1],
-                                          C.c_double(min_disp), C.c_double(max_disp), _p(a, f64p), _p(m, f64p))
+                                          C.c_double(min_disp), C.c_double(max_disp), _p(a, f64p), _p(m, f64p), C.c_double(0.5),
+                                          _p(mu, f64p))
         assert rc == 0
-        return a, m
+        return a, m, mu
 
     def trend_glm(self, cov, targets):
         out = np.zeros(16)

@@ -162,34 +162,14 @@ int emu_moments(const double* normed, int64_t ld, int N, int G, const double* sf
 }
 
 int emu_mom_from_counts(const int64_t* counts, int64_t ld, int N, int G, const double* sf, const double* X, int p,
-                        double min_disp, double max_disp, double* alpha, double* normed_mean) {
+                        double min_disp, double max_disp, double* alpha, double* normed_mean, double min_mu, double* mu_hat) {
     Pack k = make_pack(X, sf, N, p);
     EMU_DISPATCH(p, {
         const SmallMat<P> pi = pinv_of<P>(k);
-        for (int g = 0; g < G; ++g) {
-            const NormedFromCounts yy{counts + g, ld};
-            const double rde = rough_disp_gene<P>(kOne, k.d, pi, yy);
-            double mean;
-            bool az;
-            const double mde = moments_disp_gene(kOne, k.d, yy, k.s_mean_inv, mean, az);
-            double v = (mde < rde) ? mde : rde;
-            v = (v < min_disp) ? min_disp : ((v > max_disp) ? max_disp : v);
-            alpha[g] = v;
-            normed_mean[g] = mean;
-        }
+        for (int g = 0; g < G; ++g)
+            mom_fused_gene<P>(kOne, k.d, pi, counts + g, ld, k.s_mean_inv, min_disp, max_disp, min_mu, alpha + g, normed_mean + g,
+                              mu_hat ? mu_hat + g : nullptr, G, true);
     });
-    return 0;
-}
-
-int emu_trend_fit(const double* x, const double* t, size_t n, int x_is_mean, double lo, double hi, int outer, double min_disp,
-                  double trigamma_c, int with_prior, double* out16) {
-    std::vector<double> xs(n), ts(n), res(n);
-    unsigned hist[514];
-    SerialReducer red;
-    trend_prepare(red, x, t, n, x_is_mean != 0, lo, hi, xs.data(), ts.data());
-    TrendOut o = trend_fit_outer(red, xs.data(), ts.data(), n, outer != 0);
-    if (with_prior && o.status == 0.0) trend_prior(red, x, t, n, lo, hi, min_disp, trigamma_c, res.data(), hist, o);
-    memcpy(out16, &o, sizeof o);
     return 0;
 }
 

@@ -96,3 +96,16 @@ def test_device_trend_and_prior_match_host_glue(seed):
     sq2, pv2 = fit_prior_var(gwc, fitted, N, p, 1e-8)
     np.testing.assert_allclose(out[8], sq2, rtol=1e-12)
     np.testing.assert_allclose(out[9], pv2, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["calls_two_level_n24", "calls_two_level_n200", "calls_factorial_n30", "calls_few_samples_n4"])
+def test_fused_mom_kernel(name):
+    """k_mom_from_counts (resident path): min/clip of the two moment estimators, normalised means and -- same
+    projection -- the lin_reg_mu start values, against the reference's separate calls."""
+    g = load_golden(name)
+    c, X, sf = g["counts"], g["X"], g["sf"]
+    N = c.shape[0]
+    a, m, mu = EmuOps().mom_from_counts(c, sf, X, 1e-8, float(max(10, N)))
+    np.testing.assert_allclose(a, g["mom"], rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(m, g["normed"].mean(0), rtol=1e-12)
+    np.testing.assert_allclose(mu, g["lin_mu"], rtol=1e-9)
