@@ -66,6 +66,7 @@ class EmuOps:
         assert self.lib.emu_moments(_p(normed, f64p), C.c_int64(ld), N, G, _p(sf, f64p), _p(out, f64p), _p(all_zero, f64p)) == 0
 
     def mom_from_counts(self, counts, sf, X, min_disp, max_disp):
+        counts, sf, X = np.ascontiguousarray(counts), np.ascontiguousarray(sf), np.ascontiguousarray(X)
         N, G = counts.shape
         a = np.empty(G)
         m = np.empty(G)

@@ -173,6 +173,18 @@ int emu_mom_from_counts(const int64_t* counts, int64_t ld, int N, int G, const d
     return 0;
 }
 
+int emu_trend_fit(const double* x, const double* t, size_t n, int x_is_mean, double lo, double hi, int outer, double min_disp,
+                  double trigamma_c, int with_prior, double* out16) {
+    std::vector<double> xs(n), ts(n), res(n);
+    unsigned hist[514];
+    SerialReducer red;
+    trend_prepare(red, x, t, n, x_is_mean != 0, lo, hi, xs.data(), ts.data());
+    TrendOut o = trend_fit_outer(red, xs.data(), ts.data(), n, outer != 0);
+    if (with_prior && o.status == 0.0) trend_prior(red, x, t, n, lo, hi, min_disp, trigamma_c, res.data(), hist, o);
+    memcpy(out16, &o, sizeof o);
+    return 0;
+}
+
 int emu_cooks(const int64_t* counts, int64_t ld, int N, int G, const double* sf, const double* X, int p, const double* mu,
               const double* hat, int64_t ld2, double cutoff, double* cooks, double* disp, double* outlier, double* replaced) {
     Pack k = make_pack(X, sf, N, p);
