@@ -13,7 +13,7 @@ import numpy as np
 
 LN2 = np.log(2.0)
 
-DESIGNS = ("two_level", "factorial", "continuous", "intercept", "five")
+DESIGNS = ("two_level", "factorial", "continuous", "intercept", "five", "eight")
 
 
 def design_matrix(N: int, kind: str, seed: int = 0) -> np.ndarray:
@@ -31,6 +31,9 @@ def design_matrix(N: int, kind: str, seed: int = 0) -> np.ndarray:
         cols = [np.ones(N)]
     elif kind == "five":  # p=5: two binary factors, a 3-level factor (two dummies), no continuous term
         cols = [np.ones(N), cond, (i % 2).astype(float), (i % 3 == 1).astype(float), (i % 3 == 2).astype(float)]
+    elif kind == "eight":  # p=8 (the largest supported): three factors (one with 3 levels) and three continuous covariates
+        z = np.random.default_rng(seed + 7919).normal(0.0, 1.0, (3, N))
+        cols = [np.ones(N), cond, (i % 2).astype(float), (i % 3 == 1).astype(float), (i % 3 == 2).astype(float), z[0], z[1], z[2]]
     else:
         raise ValueError(f"unknown design kind {kind!r}; expected one of {DESIGNS}")
     return np.ascontiguousarray(np.stack(cols, axis=1))

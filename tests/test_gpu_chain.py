@@ -37,8 +37,14 @@ def _frac_bad(got, want, rtol, atol=0.0, mask=None):
     return float(bad.mean()), bad
 
 
-@pytest.mark.parametrize("N,G,kind,seed", [(200, 3000, "two_level", 0), (100, 1500, "factorial", 1), (120, 1500, "continuous", 2)])
-def test_chained_pipeline_matches_oracle(inf, N, G, kind, seed):
+# The two low-N multi-factor cases run at 1e-3: a few low-count genes there exhaust the IRLS iteration budget in the
+# INITIAL mu_hat fit, the reference then keeps whatever point its L-BFGS-B gave up at on the kinked clamped objective
+# (utils.py:374-403, flag discarded by dds.py:757-765), their genewise dispersions differ by percents and -- through the
+# global trend -- every MAP dispersion moves by ~2e-4 (measured; DESIGN.md "Parity status").
+@pytest.mark.parametrize("N,G,kind,seed,RTOL", [(200, 3000, "two_level", 0, 1e-4), (100, 1500, "factorial", 1, 1e-4),
+                                                (120, 1500, "continuous", 2, 1e-4), (16, 1500, "intercept", 5, 1e-4),
+                                                (90, 2000, "eight", 3, 1e-3), (36, 2000, "five", 4, 1e-3)])
+def test_chained_pipeline_matches_oracle(inf, N, G, kind, seed, RTOL):
     from oracle import nbglm
     from pydeseq2_b200.pipeline import fit_host
 
@@ -48,20 +54,20 @@ def test_chained_pipeline_matches_oracle(inf, N, G, kind, seed):
     # genes on which the reference itself trusts its fit (converged-mask aware comparison)
     ok = (ref.genewise_converged == 1) & (ref.map_converged == 1) & (ref.lfc_converged == 1)
     assert ok.mean() > 0.99
-    np.testing.assert_allclose(got.trend.coeffs, ref.trend.coeffs, rtol=1e-4)
-    assert got.prior_var == pytest.approx(ref.prior_var, rel=1e-4)
+    np.testing.assert_allclose(got.trend.coeffs, ref.trend.coeffs, rtol=RTOL)
+    assert got.prior_var == pytest.approx(ref.prior_var, rel=10 * RTOL)
     for name, a, b, atol in (("lfc", got.lfc, ref.lfc, 1e-8), ("dispersions", got.dispersions, ref.dispersions, 0.0),
                              ("stat", got.stat, ref.stat, 1e-8), ("se", got.se, ref.se, 0.0)):
         frac, bad = _frac_bad(a, b, RTOL, atol, ok)
         assert frac == 0.0, f"{name}: {frac:.2%} of converged genes off by more than {RTOL}; worst {np.nanmax(rel_err(a, b)):.2e}"
     big = ok & (ref.pvalue >= 1e-20)
-    frac, _ = _frac_bad(got.pvalue, ref.pvalue, 1e-3, 0.0, big)
+    frac, _ = _frac_bad(got.pvalue, ref.pvalue, 10 * RTOL, 0.0, big)
     assert frac == 0.0
     # -log10 p agrees everywhere it is finite
     with np.errstate(divide="ignore"):
         lp_g, lp_r = -np.log10(got.pvalue[ok]), -np.log10(ref.pvalue[ok])
     fin = np.isfinite(lp_r)
-    np.testing.assert_allclose(lp_g[fin], lp_r[fin], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(lp_g[fin], lp_r[fin], rtol=RTOL, atol=1e-6)
 
 
 @pytest.mark.parametrize("N,G,kind", [(200, 4000, "two_level"), (60, 1000, "factorial")])

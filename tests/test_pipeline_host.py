@@ -41,3 +41,30 @@ def test_chained_device_algorithms_match_reference_and_R(name):
     tol = 0.04 if name != "tape_single_factor" else 0.02
     np.testing.assert_allclose(log2fc, t["r_log2FoldChange"], rtol=tol)
     np.testing.assert_allclose(r.pvalue, t["r_pvalue"], rtol=tol)
+
+
+@pytest.mark.parametrize("N,G,kind,seed", [(90, 160, "eight", 3), (36, 160, "five", 4), (16, 120, "intercept", 5), (60, 200, "continuous", 6)])
+def test_chained_device_algorithms_match_oracle_on_wider_designs(N, G, kind, seed):
+    """p = 1, 5, 8 and a continuous covariate: the emulated device numerics chained through the pipeline against the
+    oracle chained through the same glue (north-star tolerance on reference-converged genes)."""
+    from pydeseq2_b200.pipeline import median_of_ratios
+    from pydeseq2_b200.synth import make_counts
+
+    counts, X, _ = make_counts(N, G, kind, seed)
+    counts = np.ascontiguousarray(counts[:, ~(counts == 0).all(0)])
+    sf = median_of_ratios(counts)[1]
+    ref = fit_host(counts, X, nbglm.OracleInference(n_cpus=1), size_factors=sf)
+    got = fit_host(counts, X, B200Inference(_ops=EmuOps()), size_factors=sf)
+    ok = (ref.genewise_converged == 1) & (ref.map_converged == 1) & (ref.lfc_converged == 1)
+    assert ok.mean() > 0.9
+    # Genewise dispersions (before the global trend step) agree to the optimiser's own slack ...
+    np.testing.assert_allclose(got.genewise[ok], ref.genewise[ok], rtol=2e-5)
+    # ... but with only ~150 genes the reference's trend fit is itself reproducible to ~2e-4 only: scipy's L-BFGS-B stops
+    # so early that a 1e-6 perturbation of its inputs moves its coefficients by 1.6e-4 (measured on this very case, with the
+    # reference's own optimiser on both sides).  Everything downstream of the trend inherits that; the 1e-4 bar is asserted
+    # on the large inputs of tests/test_gpu_chain.py and per call in tests/parity.py.
+    np.testing.assert_allclose(got.trend.coeffs, ref.trend.coeffs, rtol=1e-3)
+    np.testing.assert_allclose(got.lfc[ok], ref.lfc[ok], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(got.dispersions[ok], ref.dispersions[ok], rtol=1e-3)
+    np.testing.assert_allclose(got.stat[ok], ref.stat[ok], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(got.se[ok], ref.se[ok], rtol=1e-3)
