@@ -116,6 +116,7 @@ class FitResult:
     stat: np.ndarray
     se: np.ndarray
     timings: dict = field(default_factory=dict)
+    irls_init_converged: np.ndarray | None = None  # flag of the initial mu_hat IRLS (all ones on the lin_reg_mu branch)
 
 
 def _expand(v, nz, G_all):
@@ -169,8 +170,9 @@ def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5,
     mom = np.clip(np.minimum(rde, mde), min_disp, max_disp)
     if lin_mu_branch(X):                                 # dds.py:747-765
         mu_hat = timed("lin_reg_mu", inference.lin_reg_mu, c, sf, X, min_mu)
-    else:
-        _, mu_hat, _, _ = timed("irls_init", inference.irls, c, sf, X, mom, min_mu, beta_tol)
+        init_conv = np.ones(c.shape[1])
+    else:  # the orchestrator drops this call's `converged` flag (dds.py:757-765); kept here for diagnostics
+        _, mu_hat, _, init_conv = timed("irls_init", inference.irls, c, sf, X, mom, min_mu, beta_tol)
     mu_hat = np.ascontiguousarray(mu_hat)                # layers["_mu_hat"][:, non_zero_idx] is a fresh C array
     gw, gw_conv = timed("alpha_mle_genewise", inference.alpha_mle, c, X, mu_hat, mom, min_disp, max_disp)
     gw = np.clip(gw, min_disp, max_disp)                 # dds.py:792-794
@@ -206,7 +208,8 @@ def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5,
     pv, st, se = timed("wald_test", inference.wald_test, X, disp_all, lfc_all, mu_w, ridge, np.asarray(contrast, float),
                        LN2 * lfc_null, alt_hypothesis)
     return FitResult(sf, nz, mom, gw, np.asarray(gw_conv), trend, prior_var, sq, mp, np.asarray(mp_conv), disp_all,
-                     lfc_all, np.asarray(lfc_conv), np.asarray(pv), np.asarray(st), np.asarray(se), T)
+                     lfc_all, np.asarray(lfc_conv), np.asarray(pv), np.asarray(st), np.asarray(se), T,
+                     np.asarray(init_conv, dtype=float))
 
 
 # --------------------------------------------------------------------------------------- resident driver
