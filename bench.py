@@ -280,8 +280,9 @@ def main():
     c_host[:] = counts
     n_host = ctx.pinned_empty(counts.shape, np.float64)  # layers["normed_counts"] of the orchestrator (dds.py:700-708)
     np.divide(counts, sf[:, None], out=n_host)
+    n_means = n_host.mean(0)  # var["_normed_means"], also a product of fit_size_factors (dds.py:708)
     for _ in range(2):
-        fit_host(c_host, X, inf, size_factors=sf, comm=comm, normed_counts=n_host)
+        fit_host(c_host, X, inf, size_factors=sf, comm=comm, normed_counts=n_host, normed_means=n_means)
     barrier()
     ops = inf._ops
     h0, d0 = ops.h2d_bytes, ops.d2h_bytes
@@ -290,7 +291,7 @@ def main():
     for _ in range(args.steps):
         barrier()
         t0 = time.perf_counter()
-        fit_host(c_host, X, inf, size_factors=sf, comm=comm, timings=e2e_T, normed_counts=n_host)
+        fit_host(c_host, X, inf, size_factors=sf, comm=comm, timings=e2e_T, normed_counts=n_host, normed_means=n_means)
         ctx.sync()
         e2e_t.append(time.perf_counter() - t0)
     e2e_s = float(np.mean(e2e_t))

@@ -35,6 +35,12 @@ static const int kNcclFloat64 = 8;  // ncclDataType_t::ncclFloat64 (stable acros
 
 enum { kBufCounts, kBufA, kBufB, kBufC, kBufD, kBufE, kBufF, kBufG, kBufStatus, kBufMisc, kBufKeep, kBufRes, kNumBufs };
 
+struct DesignCacheEntry {
+    pdq_design* d = nullptr;
+    std::vector<double> X, sf;
+    uint64_t stamp = 0;
+};
+
 struct pdq_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -45,9 +51,9 @@ struct pdq_ctx {
     std::string err;
     void* buf[kNumBufs] = {};
     size_t cap[kNumBufs] = {};
-    // cached design of the host-buffer entry points (keyed on the bytes of X and size factors)
-    pdq_design* cached = nullptr;
-    std::vector<double> cached_X, cached_sf;
+    // design packs of the host-buffer entry points, keyed on the bytes of X and the size factors (small LRU)
+    std::vector<DesignCacheEntry> dcache;
+    uint64_t dcache_clock = 0;
     // page-locked staging ring for pageable host buffers (numpy arrays are pageable)
     void* stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
@@ -164,7 +170,8 @@ extern "C" void pdq_ctx_destroy(pdq_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
-    if (c->cached) pdq_design_destroy(c, c->cached);
+    for (auto& e : c->dcache) pdq_design_destroy(c, e.d);
+    c->dcache.clear();
     for (auto& b : c->buf)
         if (b) cudaFree(b);
     if (c->tickets) cudaFree(c->tickets);
@@ -376,7 +383,6 @@ extern "C" int pdq_design_create(pdq_ctx* c, const double* X, const double* sf, 
 extern "C" void pdq_design_destroy(pdq_ctx* c, pdq_design* d) {
     if (!d) return;
     if (c) cudaSetDevice(c->device);
-    if (c && c->cached == d) c->cached = nullptr;
     if (d->d.pack) cudaFree(d->d.pack);
     if (d->d.cell_plan) cudaFree(d->d.cell_plan);
     delete d;
@@ -384,20 +390,34 @@ extern "C" void pdq_design_destroy(pdq_ctx* c, pdq_design* d) {
 
 // design cache for the host-buffer entry points: deseq2() passes the same X (and size factors) to every call
 static int cached_design(pdq_ctx* c, const double* X, const double* sf, int N, int p, pdq_design** out) {
+    // a deseq2() pass alternates between three packs -- (X, sf), (X, no sf), (ones, sf) -- so a one-entry cache would
+    // rebuild (SVD, cell plan, two cudaMallocs, two synchronous copies) on almost every call: keep the last few
     const size_t nx = (size_t)N * p;
-    bool hit = c->cached && c->cached->d.N == N && c->cached->d.p == p && c->cached_X.size() == nx &&
-               memcmp(c->cached_X.data(), X, nx * 8) == 0 && ((sf == nullptr) == c->cached_sf.empty()) &&
-               (!sf || memcmp(c->cached_sf.data(), sf, (size_t)N * 8) == 0);
-    if (!hit) {
-        if (c->cached) pdq_design_destroy(c, c->cached);
-        c->cached = nullptr;
-        pdq_design* d = nullptr;
-        if (int e = pdq_design_create(c, X, sf, N, p, &d)) return e;
-        c->cached = d;
-        c->cached_X.assign(X, X + nx);
-        if (sf) c->cached_sf.assign(sf, sf + N); else c->cached_sf.clear();
+    for (size_t i = 0; i < c->dcache.size(); ++i) {
+        DesignCacheEntry& e = c->dcache[i];
+        if (e.d->d.N == N && e.d->d.p == p && e.X.size() == nx && memcmp(e.X.data(), X, nx * 8) == 0 &&
+            ((sf == nullptr) == e.sf.empty()) && (!sf || memcmp(e.sf.data(), sf, (size_t)N * 8) == 0)) {
+            e.stamp = ++c->dcache_clock;
+            *out = e.d;
+            return PDQ_OK;
+        }
     }
-    *out = c->cached;
+    pdq_design* d = nullptr;
+    if (int e = pdq_design_create(c, X, sf, N, p, &d)) return e;
+    if (c->dcache.size() >= 4) {  // evict the least recently used pack
+        size_t lru = 0;
+        for (size_t i = 1; i < c->dcache.size(); ++i)
+            if (c->dcache[i].stamp < c->dcache[lru].stamp) lru = i;
+        pdq_design_destroy(c, c->dcache[lru].d);
+        c->dcache.erase(c->dcache.begin() + lru);
+    }
+    DesignCacheEntry e;
+    e.d = d;
+    e.X.assign(X, X + nx);
+    if (sf) e.sf.assign(sf, sf + N);
+    e.stamp = ++c->dcache_clock;
+    c->dcache.push_back(std::move(e));
+    *out = d;
     return PDQ_OK;
 }
 

@@ -12,6 +12,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "pdq_gene.cuh"
 #include "pdq_trend.cuh"
@@ -832,6 +833,10 @@ int launch_trend_fit(const LaunchCfg& c, const double* x, const double* t, doubl
     }
     unsigned nb = 1;
     while ((int)nb < max_cluster && (size_t)nb * 1024 * 4 < n) nb <<= 1;
+    if (const char* e = getenv("PDQ_TREND_CLUSTER")) {  // tuning hook: force the cluster size (1, 2, 4, 8, 16)
+        const int v = atoi(e);
+        if (v >= 1 && v <= max_cluster && !(v & (v - 1))) nb = (unsigned)v;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nb, 1, 1);
     cfg.blockDim = dim3(1024, 1, 1);

@@ -127,15 +127,16 @@ def _expand(v, nz, G_all):
 
 def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5, min_disp=1e-8, max_disp=10.0,
              beta_tol=1e-8, fit_type="parametric", lfc_null=0.0, alt_hypothesis=None, timings=None, comm=None,
-             normed_counts=None, reuse_lfc_mu=True) -> FitResult:
+             normed_counts=None, normed_means=None, reuse_lfc_mu=True) -> FitResult:
     """deseq2() + run_wald_test() hot path through the plugin API with host buffers.
 
     ``comm`` (``sharding.NcclComm`` / ``TorchDistComm``): this process holds one gene shard; the genewise
     dispersions and normalised means of all shards are gathered for the trend and prior (the only cross-gene
     step).  ``size_factors`` must then be given (they are per sample, global over genes).
 
-    ``normed_counts``: ``counts / size_factors`` when the caller already holds it (the orchestrator keeps it as
-    ``layers["normed_counts"]`` from ``fit_size_factors``, dds.py:700-708).  ``reuse_lfc_mu``: feed the Wald stage
+    ``normed_counts`` / ``normed_means``: ``counts / size_factors`` and its per-gene mean when the caller already holds
+    them (the orchestrator keeps both from ``fit_size_factors``: ``layers["normed_counts"]``, ``var["_normed_means"]``,
+    dds.py:700-708).  ``counts`` must be non-negative (the reference validates that at construction, utils.py:100-133).  ``reuse_lfc_mu``: feed the Wald stage
     with the ``mu`` the LFC fit returned -- ``irls`` returns the UNclamped ``sf * exp(X beta)`` (utils.py:435-438),
     which is exactly what ``run_wald_test`` recomputes on the host (ds.py:320-324)."""
     T = timings if timings is not None else {}
@@ -159,11 +160,11 @@ def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5,
     else:
         sf = np.asarray(size_factors, dtype=float)
         normed = normed_counts if normed_counts is not None else timed("normed_counts", lambda: counts / sf[:, None])
-    nz = ~(counts == 0).all(axis=0)                      # dds.py:729-731
+    nz = counts.max(axis=0) != 0                         # dds.py:729-731: ~(X == 0).all(0) for non-negative counts, one pass
     all_nz = bool(nz.all())
     c = counts if all_nz else counts[:, nz]              # no copy when the caller already dropped all-zero genes
     nn = normed if all_nz else normed[:, nz]
-    normed_means = normed.mean(0)[nz]                    # dds.py:708
+    normed_means = (normed.mean(0) if normed_means is None else np.asarray(normed_means))[nz]   # dds.py:708
 
     rde = timed("fit_rough_dispersions", inference.fit_rough_dispersions, nn, X)       # dds.py:1150-1157
     mde = timed("fit_moments_dispersions", inference.fit_moments_dispersions, nn, sf)
