@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <initializer_list>
 #include <string>
 #include <vector>
 
@@ -59,7 +60,10 @@ struct pdq_ctx {
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     bool stage_busy[2] = {false, false};
     int staging = 1;  // PDQ_STAGING=0 disables (plain cudaMemcpyAsync from pageable memory)
-    int* tickets = nullptr;  // device ints for the persistent kernels' tile counters
+    int* tickets = nullptr;  // device ints for the persistent kernels' tile counters (4 per stream slot)
+    cudaStream_t pstream[2] = {nullptr, nullptr};  // gene-block pipeline of the host-buffer entry points
+    cudaEvent_t pfork = nullptr;
+    int pipeline = 1;        // PDQ_PIPELINE=0 disables
     int debug = 0;           // PDQ_DEBUG_* test hooks
     int64_t launches_at_capture = 0;
     NcclApi nccl;
@@ -158,7 +162,10 @@ extern "C" int pdq_ctx_create(int device, pdq_ctx** out) {
             return PDQ_ERR_CUDA;
         }
     if (const char* s = getenv("PDQ_STAGING")) c->staging = atoi(s);
-    if (cudaMalloc((void**)&c->tickets, 64) != cudaSuccess) {
+    if (const char* s = getenv("PDQ_PIPELINE")) c->pipeline = atoi(s);
+    if (cudaMalloc((void**)&c->tickets, 64) != cudaSuccess || cudaStreamCreateWithFlags(&c->pstream[0], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->pstream[1], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->pfork, cudaEventDisableTiming) != cudaSuccess) {
         delete c;
         return PDQ_ERR_CUDA;
     }
@@ -175,6 +182,9 @@ extern "C" void pdq_ctx_destroy(pdq_ctx* c) {
     for (auto& b : c->buf)
         if (b) cudaFree(b);
     if (c->tickets) cudaFree(c->tickets);
+    for (auto& st : c->pstream)
+        if (st) cudaStreamDestroy(st);
+    if (c->pfork) cudaEventDestroy(c->pfork);
     for (int i = 0; i < 2; ++i) {
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
         if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
@@ -620,6 +630,80 @@ static int h2d_2d(pdq_ctx* c, void* dst, const void* src, int64_t ld, int N, int
     return 0;
 }
 
+// ---- gene-block pipeline --------------------------------------------------------------------------------------
+// The plugin calls move 32-64 MB each way around a 0.3 ms kernel.  When every large host buffer is page-locked the call
+// is split into gene blocks on two streams: the column block k+1 is uploaded while block k computes and block k-1 is
+// downloaded (PCIe is full duplex, the kernels take `ld`, so a block is just a pointer offset).  Per-gene results do not
+// depend on the split (different lane-group widths only change the order of the floating-point sums).
+static const int kPipeBlocks = 4;
+
+struct Pipe {
+    pdq_ctx* c;
+    bool on;
+    int nb, G, Gb;
+    int g0(int b) const { return b * Gb; }
+    int gb(int b) const { return (b == nb - 1) ? G - b * Gb : Gb; }
+    cudaStream_t st(int b) const { return on ? c->pstream[b & 1] : c->stream; }
+    LaunchCfg cfg_for(int b, int N) const {
+        LaunchCfg lc = cfg(c, gb(b), N);
+        lc.stream = st(b);
+        lc.tickets = c->tickets + (on ? 4 * (1 + (b & 1)) : 0);
+        return lc;
+    }
+};
+
+static int pipe_begin(pdq_ctx* c, int G, std::initializer_list<const void*> big_host, Pipe* p) {
+    bool on = c->pipeline && c->staging && G >= 4096;
+    for (const void* h : big_host) on = on && is_pinned(h);
+    p->c = c;
+    p->on = on;
+    p->G = G;
+    p->nb = on ? kPipeBlocks : 1;
+    p->Gb = on ? (((G + kPipeBlocks - 1) / kPipeBlocks + 15) & ~15) : G;
+    if (on) {
+        while (p->nb > 1 && (p->nb - 1) * p->Gb >= G) --p->nb;
+        CU(c, cudaEventRecord(c->pfork, c->stream));
+        CU(c, cudaStreamWaitEvent(c->pstream[0], c->pfork, 0));
+        CU(c, cudaStreamWaitEvent(c->pstream[1], c->pfork, 0));
+    }
+    return 0;
+}
+
+static int pipe_end(pdq_ctx* c, const Pipe& p) {
+    if (p.on) {
+        CU(c, cudaStreamSynchronize(c->pstream[0]));
+        CU(c, cudaStreamSynchronize(c->pstream[1]));
+    } else {
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+// column block [g0, g0+gb) of an (N, G) array, host pitch ld_h elements <-> device pitch ld_d elements
+static int cols_h2d(pdq_ctx* c, const Pipe& p, int b, void* dev, int64_t ld_d, const void* host, int64_t ld_h, int N, size_t elem) {
+    if (!p.on) return h2d_2d(c, dev, host, ld_h, N, p.G, elem);
+    CU(c, cudaMemcpy2DAsync((char*)dev + (size_t)p.g0(b) * elem, (size_t)ld_d * elem, (const char*)host + (size_t)p.g0(b) * elem,
+                            (size_t)ld_h * elem, (size_t)p.gb(b) * elem, N, cudaMemcpyHostToDevice, p.st(b)));
+    return 0;
+}
+static int cols_d2h(pdq_ctx* c, const Pipe& p, int b, void* host, int64_t ld_h, const void* dev, int64_t ld_d, int N, size_t elem) {
+    if (!p.on) return copy_d2h(c, host, dev, (size_t)N * p.G * elem);
+    CU(c, cudaMemcpy2DAsync((char*)host + (size_t)p.g0(b) * elem, (size_t)ld_h * elem, (const char*)dev + (size_t)p.g0(b) * elem,
+                            (size_t)ld_d * elem, (size_t)p.gb(b) * elem, N, cudaMemcpyDeviceToHost, p.st(b)));
+    return 0;
+}
+// per-gene vector block (rows of `width` doubles per gene)
+static int vec_h2d(pdq_ctx* c, const Pipe& p, int b, void* dev, const void* host, size_t width) {
+    CU(c, cudaMemcpyAsync((char*)dev + (size_t)p.g0(b) * width * 8, (const char*)host + (size_t)p.g0(b) * width * 8,
+                          (size_t)p.gb(b) * width * 8, cudaMemcpyHostToDevice, p.st(b)));
+    return 0;
+}
+static int vec_d2h(pdq_ctx* c, const Pipe& p, int b, void* host, const void* dev, size_t width) {
+    CU(c, cudaMemcpyAsync((char*)host + (size_t)p.g0(b) * width * 8, (const char*)dev + (size_t)p.g0(b) * width * 8,
+                          (size_t)p.gb(b) * width * 8, cudaMemcpyDeviceToHost, p.st(b)));
+    return 0;
+}
+
 extern "C" int pdq_lin_reg_mu(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, const double* sf, const double* X, int p,
                               double min_mu, double* mu_out) {
     CHECK_CTX(c);
@@ -630,11 +714,16 @@ extern "C" int pdq_lin_reg_mu(pdq_ctx* c, const int64_t* counts, int64_t ld, int
     const size_t ng = (size_t)N * G;
     if (int e = ensure(c, kBufCounts, ng * 8, &dc)) return e;
     if (int e = ensure(c, kBufA, ng * 8, &dm)) return e;
-    if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
-    if (int e = pdq_lin_reg_mu_dev(c, d, (const int64_t*)dc, G, G, min_mu, (double*)dm, G)) return e;
-    if (int e = copy_d2h(c, mu_out, dm, ng * 8)) return e;
-    CU(c, cudaStreamSynchronize(c->stream));
-    return PDQ_OK;
+    Pipe pp;
+    if (int e = pipe_begin(c, G, {counts, mu_out}, &pp)) return e;
+    for (int b = 0; b < pp.nb; ++b) {
+        if (int e = cols_h2d(c, pp, b, dc, G, counts, ld, N, 8)) return e;
+        if (int e = done(c, launch_lin_reg_mu(pp.cfg_for(b, N), d->d, (const int64_t*)dc + pp.g0(b), G, pp.gb(b), min_mu,
+                                              (double*)dm + pp.g0(b), G), "lin_reg_mu"))
+            return e;
+        if (int e = cols_d2h(c, pp, b, mu_out, G, dm, G, N, 8)) return e;
+    }
+    return pipe_end(c, pp);
 }
 
 extern "C" int pdq_irls(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, const double* sf, const double* X, int p,
@@ -654,19 +743,28 @@ extern "C" int pdq_irls(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, in
     if (int e = ensure(c, kBufD, (size_t)G * p * 8, &dbeta)) return e;
     if (int e = ensure(c, kBufE, (size_t)G * 8, &dconv)) return e;
     if (int e = ensure(c, kBufMisc, 64, &dmisc)) return e;
-    if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
-    CU(c, cudaMemcpyAsync(ddisp, disp, (size_t)G * 8, cudaMemcpyHostToDevice, c->stream));
-    if (int e = pdq_irls_dev(c, d, (const int64_t*)dc, G, G, (const double*)ddisp, min_mu, beta_tol, min_beta, max_beta, maxiter,
-                             (double*)dbeta, (double*)dmu, (double*)dhat, G, (double*)dconv, (int*)dmisc))
-        return e;
-    CU(c, cudaMemcpyAsync(beta_out, dbeta, (size_t)G * p * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(conv_out, dconv, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (int e = copy_d2h(c, mu_out, dmu, ng * 8)) return e;
-    if (int e = copy_d2h(c, hat_out, dhat, ng * 8)) return e;
-    int nfb = 0;
-    CU(c, cudaMemcpyAsync(&nfb, dmisc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    if (n_fallback) *n_fallback = nfb;
+    void* status;
+    if (int e = ensure(c, kBufStatus, (size_t)G * sizeof(int), &status)) return e;
+    const IrlsHost h{min_mu, beta_tol, min_beta, max_beta, maxiter};
+    Pipe pp;
+    if (int e = pipe_begin(c, G, {counts, mu_out, hat_out}, &pp)) return e;
+    int nfb[kPipeBlocks] = {0, 0, 0, 0};
+    for (int b = 0; b < pp.nb; ++b) {
+        const int g0 = pp.g0(b), gb = pp.gb(b);
+        if (int e = cols_h2d(c, pp, b, dc, G, counts, ld, N, 8)) return e;
+        if (int e = vec_h2d(c, pp, b, ddisp, disp, 1)) return e;
+        if (int e = done(c, launch_irls(pp.cfg_for(b, N), d->d, (const int64_t*)dc + g0, G, gb, (const double*)ddisp + g0, h,
+                                        (double*)dbeta + (size_t)g0 * p, (double*)dmu + g0, (double*)dhat + g0, G, (double*)dconv + g0,
+                                        (int*)status + g0, (int*)dmisc + b), "irls"))
+            return e;
+        if (int e = vec_d2h(c, pp, b, beta_out, dbeta, (size_t)p)) return e;
+        if (int e = vec_d2h(c, pp, b, conv_out, dconv, 1)) return e;
+        if (int e = cols_d2h(c, pp, b, mu_out, G, dmu, G, N, 8)) return e;
+        if (int e = cols_d2h(c, pp, b, hat_out, G, dhat, G, N, 8)) return e;
+        CU(c, cudaMemcpyAsync(&nfb[b], (int*)dmisc + b, sizeof(int), cudaMemcpyDeviceToHost, pp.st(b)));
+    }
+    if (int e = pipe_end(c, pp)) return e;
+    if (n_fallback) *n_fallback = nfb[0] + nfb[1] + nfb[2] + nfb[3];
     return PDQ_OK;
 }
 
@@ -685,16 +783,24 @@ extern "C" int pdq_alpha_mle(pdq_ctx* c, const int64_t* counts, int64_t ld, int 
     if (int e = ensure(c, kBufC, (size_t)G * 8, &dah)) return e;
     if (int e = ensure(c, kBufD, (size_t)G * 8, &dal)) return e;
     if (int e = ensure(c, kBufE, (size_t)G * 8, &dconv)) return e;
-    if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
-    if (int e = h2d_2d(c, dmu, mu, ld_mu, N, G, 8)) return e;
-    CU(c, cudaMemcpyAsync(dah, alpha_hat, (size_t)G * 8, cudaMemcpyHostToDevice, c->stream));
-    if (int e = pdq_alpha_mle_dev(c, d, (const int64_t*)dc, G, G, (const double*)dmu, G, (const double*)dah, min_disp, max_disp,
-                                  prior_disp_var, nullptr, cr_reg, prior_reg, (double*)dal, (double*)dconv))
-        return e;
-    CU(c, cudaMemcpyAsync(alpha_out, dal, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(conv_out, dconv, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    return PDQ_OK;
+    if (prior_reg && !(prior_disp_var > 0.0)) return fail(c, PDQ_ERR_INVALID, "alpha_mle: prior_reg needs prior_disp_var > 0");
+    void* status;
+    if (int e = ensure(c, kBufStatus, (size_t)G * sizeof(int), &status)) return e;
+    Pipe pp;
+    if (int e = pipe_begin(c, G, {counts, mu}, &pp)) return e;
+    for (int b = 0; b < pp.nb; ++b) {
+        const int g0 = pp.g0(b), gb = pp.gb(b);
+        if (int e = cols_h2d(c, pp, b, dc, G, counts, ld, N, 8)) return e;
+        if (int e = cols_h2d(c, pp, b, dmu, G, mu, ld_mu, N, 8)) return e;
+        if (int e = vec_h2d(c, pp, b, dah, alpha_hat, 1)) return e;
+        if (int e = done(c, launch_alpha_mle(pp.cfg_for(b, N), d->d, (const int64_t*)dc + g0, G, gb, (const double*)dmu + g0, G,
+                                             (const double*)dah + g0, min_disp, max_disp, prior_disp_var, nullptr, cr_reg, prior_reg,
+                                             (double*)dal + g0, (double*)dconv + g0, (int*)status + g0), "alpha_mle"))
+            return e;
+        if (int e = vec_d2h(c, pp, b, alpha_out, dal, 1)) return e;
+        if (int e = vec_d2h(c, pp, b, conv_out, dconv, 1)) return e;
+    }
+    return pipe_end(c, pp);
 }
 
 extern "C" int pdq_wald_test(pdq_ctx* c, const double* X, int N, int p, const double* disp, const double* lfc, const double* mu,
@@ -713,17 +819,23 @@ extern "C" int pdq_wald_test(pdq_ctx* c, const double* X, int N, int p, const do
     if (int e = ensure(c, kBufE, (size_t)G * 8, &dp)) return e;
     if (int e = ensure(c, kBufF, (size_t)G * 8, &ds)) return e;
     if (int e = ensure(c, kBufG, (size_t)G * 8, &dse)) return e;
-    if (int e = h2d_2d(c, dmu, mu, ld_mu, N, G, 8)) return e;
-    CU(c, cudaMemcpyAsync(ddisp, disp, (size_t)G * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(dlfc, lfc, (size_t)G * p * 8, cudaMemcpyHostToDevice, c->stream));
-    if (int e = pdq_wald_test_dev(c, d, (const double*)ddisp, (const double*)dlfc, (const double*)dmu, G, G, ridge, contrast, lfc_null,
-                                  alt, (double*)dp, (double*)ds, (double*)dse))
-        return e;
-    CU(c, cudaMemcpyAsync(pv_out, dp, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(stat_out, ds, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(se_out, dse, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    return PDQ_OK;
+    if (alt < 0 || alt > 4) return fail(c, PDQ_ERR_INVALID, "pdq_wald_test: unknown alternative");
+    Pipe pp;
+    if (int e = pipe_begin(c, G, {mu}, &pp)) return e;
+    for (int b = 0; b < pp.nb; ++b) {
+        const int g0 = pp.g0(b), gb = pp.gb(b);
+        if (int e = cols_h2d(c, pp, b, dmu, G, mu, ld_mu, N, 8)) return e;
+        if (int e = vec_h2d(c, pp, b, ddisp, disp, 1)) return e;
+        if (int e = vec_h2d(c, pp, b, dlfc, lfc, (size_t)p)) return e;
+        if (int e = done(c, launch_wald(pp.cfg_for(b, N), d->d, (const double*)ddisp + g0, (const double*)dlfc + (size_t)g0 * p,
+                                        (const double*)dmu + g0, G, gb, ridge, contrast, lfc_null, alt, (double*)dp + g0, (double*)ds + g0,
+                                        (double*)dse + g0), "wald_test"))
+            return e;
+        if (int e = vec_d2h(c, pp, b, pv_out, dp, 1)) return e;
+        if (int e = vec_d2h(c, pp, b, stat_out, ds, 1)) return e;
+        if (int e = vec_d2h(c, pp, b, se_out, dse, 1)) return e;
+    }
+    return pipe_end(c, pp);
 }
 
 extern "C" int pdq_fit_rough_dispersions(pdq_ctx* c, const double* normed, int64_t ld, int N, int G, const double* X, int p,
