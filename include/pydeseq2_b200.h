@@ -61,9 +61,12 @@ int pdq_device_info(const pdq_ctx* ctx, char* name, size_t name_len, int* sm_cou
 int pdq_set_lanes_per_gene(pdq_ctx* ctx, int lanes);
 /* Test hook: PDQ_DEBUG_FORCE_IRLS_OPTIMIZER sends every gene of pdq_irls through the optimiser branch
  * (utils.py:374-413) and PDQ_DEBUG_FORCE_ALPHA_GRID every gene of pdq_alpha_mle through the grid fallback
- * (grid_search.py:54-142), so that the rarely taken kernels are exercised by the GPU test-suite. */
+ * (grid_search.py:54-142), so that the rarely taken kernels are exercised by the GPU test-suite ... */
 #define PDQ_DEBUG_FORCE_IRLS_OPTIMIZER 1
 #define PDQ_DEBUG_FORCE_ALPHA_GRID 2
+/* ... and PDQ_DEBUG_FORCE_SHRINK_GRID every gene of pdq_lfc_shrink_nbinom_glm (two-column designs) through
+ * grid_fit_shrink_beta (grid_search.py:224-318). */
+#define PDQ_DEBUG_FORCE_SHRINK_GRID 4
 int pdq_set_debug_flags(pdq_ctx* ctx, int flags);
 /* number of kernel launches issued through this context so far (bench.py `gpu_launches`) */
 int64_t pdq_launch_count(const pdq_ctx* ctx);
@@ -143,6 +146,18 @@ int pdq_fit_moments_dispersions(pdq_ctx* ctx, const double* normed_counts, int64
 int pdq_dispersion_trend_gamma_glm(pdq_ctx* ctx, const double* covariates, const double* targets, size_t n,
                                    double* coeffs_out, double* pred_out, int* converged_out);
 
+/* apeGLM LFC shrinkage -- Inference.lfc_shrink_nbinom_glm (inference.py:309-362) -> DefaultInference (default_inference.py:232-264)
+ * -> utils.nbinomGLM (utils.py:990-1145), grid fallback grid_search.py:224-318; caller DeseqStats.lfc_shrink (ds.py:363-443).
+ * SURVEY.md §8 f-3.  MAP coefficients under a normal(0, prior_no_shrink_scale) prior on every coefficient but `shrink_index`,
+ * which gets the Cauchy-type prior of scale `prior_scale`; the optimiser is the reference's (unconstrained L-BFGS-B, ftol =
+ * gtol = 1e-8 on the objective scaled by max(f(0), 1), start 0.1 * (-1)^j), iterate for iterate.  `size` (G,) = 1 / dispersion,
+ * `offset` (N,) = log size factors.  Outputs: `lfcs_out` (G,p), `inv_hessians_out` (G,p,p) = inverse of the reference's Hessian
+ * expression at the result (utils.py:1091-1108, 1143), `converged_out` (G,) 0/1 = scipy's `res.success`; genes that did not
+ * converge are refitted on the 2-D grid when p == 2 (their flag stays 0), `*n_grid` (may be NULL) counts them. */
+int pdq_lfc_shrink_nbinom_glm(pdq_ctx* ctx, const double* X, const int64_t* counts, int64_t ld, int N, int G, int p,
+                              const double* size, const double* offset, double prior_no_shrink_scale, double prior_scale,
+                              int shrink_index, double* lfcs_out, double* inv_hessians_out, double* converged_out, int* n_grid);
+
 /* Median-of-ratios size factors -- preprocessing.deseq2_norm_fit/transform (preprocessing.py:31-102), the step before the
  * plugin calls: per-gene mean of log counts, genes holding a zero dropped, per-sample exact median
  * of log(count) - gene mean (radix select), exponentiated.  `sf_out` (N,).  All entries NaN when every gene holds a zero
@@ -196,6 +211,11 @@ int pdq_trend_fit_dev(pdq_ctx* ctx, const double* normed_means, const double* ge
 int pdq_cooks_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld, int G, const double* mu,
                   const double* hat, int64_t ld2, double cutoff, double* cooks_out, int64_t ld_out,
                   double* robust_disp_out, double* outlier_out, double* replaced_out);
+/* device-resident flavour of pdq_lfc_shrink_nbinom_glm: the offsets are the log size factors of `design`;
+ * `status_out` (G,) ints, 1 = refitted on the grid */
+int pdq_lfc_shrink_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld, int G, const double* size,
+                       double prior_no_shrink_scale, double prior_scale, int shrink_index, double* lfcs_out,
+                       double* inv_hessians_out, double* converged_out, int* status_out);
 /* device-resident flavour of pdq_size_factors; `logmeans_out` (G,) may be NULL */
 int pdq_size_factors_dev(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N, int G, double* sf_out,
                          double* logmeans_out);

@@ -260,6 +260,128 @@ def main():
                        "condition[T.C]": indicator(mo["condition"], "C")}, index=mo.index)
     gen_tape("multi_factor_outliers", co, mo, d5, [0, 0, 1, 0], f"{REF}/tests/data/multi_factor/r_test_res_outliers.csv")
 
+def real_fit_prior_var(lfc_col, se, coeff_idx=0):
+    """The reference's own `DeseqStats._fit_prior_var` (ds.py:551-585) on bare arrays."""
+    from types import SimpleNamespace
+
+    from pydeseq2.ds import DeseqStats
+
+    fake = SimpleNamespace(LFC=pd.DataFrame({"c": lfc_col}), SE=pd.Series(se))
+    return float(DeseqStats._fit_prior_var(fake, coeff_idx=0))
+
+
+def gen_shrink_calls(name, source, shrink_index, prior_scale=None):
+    """apeGLM per-call fixture: the real `DefaultInference.lfc_shrink_nbinom_glm` on the inputs of an existing
+    calls_* fixture (counts, design, size factors, MAP dispersions; prior scale from the MLE LFCs and Wald SEs)."""
+    z = np.load(os.path.join(OUT, f"calls_{source}.npz"))
+    inf = ref_inference()
+    counts, X, sf, disp = z["counts"], z["X"], z["sf"], z["disp"]
+    p = X.shape[1]
+    contrast = np.zeros(p)
+    contrast[shrink_index] = 1.0
+    _, _, se = inf.wald_test(X, disp, z["lfc_beta"], np.ascontiguousarray(z["lfc_mu"]), z["ridge"], contrast, 0.0, None)
+    prior_var = real_fit_prior_var(z["lfc_beta"][:, shrink_index], se)
+    if prior_scale is None:
+        prior_scale = float(np.minimum(np.sqrt(prior_var), 1))
+    size, offset = 1.0 / disp, np.log(sf)
+    lfcs, ih, conv = inf.lfc_shrink_nbinom_glm(design_matrix=X, counts=counts, size=size, offset=offset, prior_no_shrink_scale=15,
+                                               prior_scale=prior_scale, optimizer="L-BFGS-B", shrink_index=shrink_index)
+    np.savez_compressed(os.path.join(OUT, f"shrink_{name}.npz"), counts=counts, X=X, size=size, offset=offset, mle_lfc=z["lfc_beta"],
+                        mle_se=se, prior_var=np.float64(prior_var), prior_scale=np.float64(prior_scale),
+                        prior_no_shrink_scale=np.float64(15.0), shrink_index=np.int64(shrink_index), lfcs=lfcs, inv_hessians=ih,
+                        converged=np.asarray(conv, dtype=float))
+    print(f"shrink_{name}: G={counts.shape[1]} p={p} idx={shrink_index} prior_scale={prior_scale:.4g} converged={np.mean(conv):.3f}")
+
+
+def gen_shrink_tape(name, counts_df, metadata, design_df, contrast, coeff, r_dir, r_shrunk="r_test_lfc_shrink_res.csv", adapt=True):
+    """The reference's own shrinkage tests (tests/test_pydeseq2.py:256-296, 299-341, 367-430, 470-509, 566-622): R's size factors,
+    dispersions, MLE LFCs and SEs go in, `lfc_shrink()` runs through the real orchestrator, R's shrunk table is stored next
+    to what the reference produced."""
+    from pydeseq2.dds import DeseqDataSet
+    from pydeseq2.ds import DeseqStats
+
+    r_res = pd.read_csv(f"{r_dir}/r_test_res.csv", index_col=0)
+    r_shr = pd.read_csv(f"{r_dir}/{r_shrunk}", index_col=0)
+    r_sf = pd.read_csv(f"{r_dir}/r_test_size_factors.csv", index_col=0).squeeze()
+    r_disp = pd.read_csv(f"{r_dir}/r_test_dispersions.csv", index_col=0).squeeze()
+    calls = []
+
+    class Rec(type(ref_inference())):
+        def lfc_shrink_nbinom_glm(self, **k):
+            res = super().lfc_shrink_nbinom_glm(**k)
+            res = (res[0], res[1], np.asarray(res[2], dtype=float))  # pandas-3: float flags (SURVEY.md §8c)
+            calls.append(({kk: (np.array(v, copy=True) if hasattr(v, "shape") else v) for kk, v in k.items()}, res))
+            return res
+
+    inf = Rec(n_cpus=1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dds = DeseqDataSet(counts=counts_df, metadata=metadata, design=design_df, inference=inf, quiet=True)
+        dds.deseq2()
+        dds.obs["size_factors"] = r_sf.values
+        dds.var["dispersions"] = r_disp.values
+        dds.varm["LFC"].iloc[:, 1] = r_res.log2FoldChange.values * np.log(2)
+        ds = DeseqStats(dds, contrast=np.asarray(contrast, dtype=float), inference=inf, quiet=True)
+        ds.summary()
+        ds.SE = r_res.lfcSE * np.log(2)
+        coeff_idx = ds.LFC.columns.get_loc(coeff)
+        mle_lfc, mle_se = ds.LFC.values.copy(), np.asarray(ds.SE, dtype=float).copy()
+        prior_var = ds._fit_prior_var(coeff_idx=coeff_idx) if adapt else np.nan
+        ds.lfc_shrink(coeff=coeff, adapt=adapt)
+    (k, (lfcs, ih, conv)), = calls
+    out = dict(counts=np.ascontiguousarray(k["counts"]).astype(np.int64), X=np.asarray(k["design_matrix"], dtype=float),
+               size=np.asarray(k["size"], dtype=float), offset=np.asarray(k["offset"], dtype=float),
+               prior_no_shrink_scale=np.float64(k["prior_no_shrink_scale"]), prior_scale=np.float64(k["prior_scale"]),
+               shrink_index=np.int64(k["shrink_index"]), lfcs=lfcs, inv_hessians=ih, converged=np.asarray(conv, dtype=float),
+               mle_lfc=mle_lfc, mle_se=mle_se, prior_var=np.float64(prior_var),
+               # what ds.py:414-431 writes into LFC / SE.  Taken from the call's outputs: under pandas 3 (copy-on-write) the
+               # reference's own `self.LFC.iloc[:, i].update(...)` updates a temporary and results_df keeps the MLE.
+               final_log2FoldChange=lfcs[:, int(k["shrink_index"])] / np.log(2),
+               final_lfcSE=np.sqrt(np.abs(ih[:, int(k["shrink_index"]), int(k["shrink_index"])])) / np.log(2),
+               r_log2FoldChange=r_shr["log2FoldChange"].values, r_lfcSE=r_shr["lfcSE"].values)
+    np.savez_compressed(os.path.join(OUT, f"shrinktape_{name}.npz"), **out)
+    rel = np.nanmax(np.abs(out["r_log2FoldChange"] - out["final_log2FoldChange"]) / np.abs(out["r_log2FoldChange"]))
+    print(f"shrinktape_{name}: G={lfcs.shape[0]} p={lfcs.shape[1]} idx={int(k['shrink_index'])} prior_scale={float(k['prior_scale']):.4g} "
+          f"max rel shrunk-LFC diff vs R = {rel:.2e}")
+
+
+def main_shrink():
+    gen_shrink_calls("two_level_n24", "two_level_n24", 1)
+    gen_shrink_calls("factorial_n30", "factorial_n30", 2)
+    gen_shrink_calls("factorial_n30_idx1", "factorial_n30", 1)
+    gen_shrink_calls("continuous_n40", "continuous_n40", 2)
+    gen_shrink_calls("two_level_n200", "two_level_n200", 1)
+    gen_shrink_calls("two_level_n200_noadapt", "two_level_n200", 1, prior_scale=1.0)
+    gen_shrink_calls("large_counts_n12", "large_counts_n12", 1)
+    gen_shrink_calls("five_columns_n36", "five_columns_n36", 3)
+    gen_shrink_calls("few_samples_n4", "few_samples_n4", 1)
+    counts = pd.read_csv(f"{REF}/datasets/synthetic/test_counts.csv", index_col=0).T
+    meta = pd.read_csv(f"{REF}/datasets/synthetic/test_metadata.csv", index_col=0)
+    d1 = pd.DataFrame({"Intercept": 1.0, "condition[T.B]": indicator(meta["condition"], "B")}, index=meta.index)
+    gen_shrink_tape("single_factor", counts, meta, d1, [0, 1], "condition[T.B]", f"{REF}/tests/data/single_factor")
+    gen_shrink_tape("single_factor_noadapt", counts, meta, d1, [0, 1], "condition[T.B]", f"{REF}/tests/data/single_factor",
+                    r_shrunk="r_test_lfc_shrink_no_apeAdapt_res.csv", adapt=False)
+    d2 = pd.DataFrame({"Intercept": 1.0, "group[T.Y]": indicator(meta["group"], "Y"),
+                       "condition[T.B]": indicator(meta["condition"], "B")}, index=meta.index)
+    gen_shrink_tape("multi_factor", counts, meta, d2, [0, 0, 1], "condition[T.B]", f"{REF}/tests/data/multi_factor")
+    cc = pd.read_csv(f"{REF}/tests/data/continuous/test_counts.csv", index_col=0).T
+    cm = pd.read_csv(f"{REF}/tests/data/continuous/test_metadata.csv", index_col=0)
+    d3 = pd.DataFrame({"Intercept": 1.0, "group[T.Y]": indicator(cm["group"], "Y"),
+                       "condition[T.B]": indicator(cm["condition"], "B"),
+                       "measurement": cm["measurement"].astype(float)}, index=cm.index)
+    gen_shrink_tape("continuous", cc, cm, d3, [0, 0, 0, 1], "measurement", f"{REF}/tests/data/continuous")
+    lc = pd.DataFrame(data=[[25, 405, 1355, 12558, 489843], [28, 480, 2144, 13844, 514571], [12, 690, 1919, 15632, 564106],
+                            [31, 420, 1684, 11513, 556380], [34, 278, 3849, 11577, 412551], [19, 249, 3086, 7296, 295565],
+                            [17, 491, 4089, 13805, 280945], [15, 251, 2785, 10492, 214062]],
+                      index=["A1", "A2", "A3", "A4", "B1", "B2", "B3", "B4"], columns=["g1", "g2", "g3", "g4", "g5"])
+    lm = pd.DataFrame(data=["A", "A", "A", "A", "B", "B", "B", "B"], index=lc.index, columns=["condition"])
+    d6 = pd.DataFrame({"Intercept": 1.0, "condition[T.B]": indicator(lm["condition"], "B")}, index=lm.index)
+    gen_shrink_tape("large_counts", lc, lm, d6, [0, 1], "condition[T.B]", f"{REF}/tests/data/large_counts")
+
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "shrink":  # apeGLM fixtures only (reads the existing calls_* fixtures)
+        main_shrink()
+    else:
+        main()
+        main_shrink()

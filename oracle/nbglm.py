@@ -304,6 +304,96 @@ def deseq2_norm(counts):
     return counts / sf[:, None], sf
 
 
+# --------------------------------------------------------------------------- apeGLM LFC shrinkage
+def nbinom_fn(beta, X, y, size, offset, prior_no_shrink_scale, prior_scale, shrink_index=1):
+    """NB negative log-likelihood + apeGLM prior (utils.py:1148-1207): zero-mean normal on every
+    coefficient except `shrink_index`, which gets the Cauchy-type prior log1p((b / scale)^2)."""
+    mask = np.zeros(X.shape[-1])
+    mask[shrink_index] = 1.0
+    xbeta = X @ beta
+    prior = ((beta * (1.0 - mask)) ** 2 / (2 * prior_no_shrink_scale**2)).sum() + np.log1p((beta[shrink_index] / prior_scale) ** 2)
+    nll = (y * xbeta - (y + size) * np.logaddexp(xbeta + offset, np.log(size))).sum(0)
+    return prior - nll
+
+
+def nbinom_grad(beta, X, y, size, offset, prior_no_shrink_scale, prior_scale, shrink_index=1):
+    """utils.py:1076-1089 (unscaled)."""
+    mask = np.zeros(X.shape[-1])
+    mask[shrink_index] = 1.0
+    xbeta = X @ beta
+    d_prior = beta * (1.0 - mask) / prior_no_shrink_scale**2 + 2 * beta * mask / (prior_scale**2 + beta[shrink_index] ** 2)
+    d_nll = (y - (y + size) / (1 + size * np.exp(-xbeta - offset))) @ X
+    return d_prior - d_nll
+
+
+def nbinom_hess(beta, X, y, size, offset, prior_no_shrink_scale, prior_scale, shrink_index=1):
+    """utils.py:1091-1108 (unscaled, `cnst = 1`).
+
+    Quirk kept on purpose: the reference builds ``h = np.diag(vector)`` and then adds ``np.diag(h)`` -- the diagonal
+    extracted again, a length-p vector -- to the p x p data term, so numpy broadcasting adds ``h_j`` to every entry of
+    column j rather than to the diagonal.  The result is not symmetric; only its inverse is ever used (utils.py:1143,
+    ``SE = sqrt(|inv[k, k]|)`` at ds.py:421-431)."""
+    mask = np.zeros(X.shape[-1])
+    mask[shrink_index] = 1.0
+    e = np.exp(X @ beta + offset)
+    frac = (y + size) * size * e / (size + e) ** 2
+    h11 = 1 / prior_no_shrink_scale**2
+    h22 = 2 * (prior_scale**2 - beta[shrink_index] ** 2) / (prior_scale**2 + beta[shrink_index] ** 2) ** 2
+    h = np.diag((1.0 - mask) * h11 + mask * h22)
+    return (X.T * frac) @ X + np.diag(h)
+
+
+def grid_fit_shrink_beta(y, offset, X, size, prior_no_shrink_scale, prior_scale, scale_cnst, grid_length=60,
+                         min_beta=-30, max_beta=30):
+    """2-D grid search of the shrunk fit (grid_search.py:224-318): coarse grid over [min, max]^2, then a
+    fine grid of one coarse cell either side of the best node; first minimum in row-major order wins."""
+    def loss(b):  # the reference leaves shrink_index at its default (1) here
+        return nbinom_fn(b, X, y, size, offset, prior_no_shrink_scale, prior_scale) / scale_cnst
+
+    xg = np.linspace(min_beta, max_beta, grid_length)
+    yg = np.linspace(min_beta, max_beta, grid_length)
+    ll = np.array([[loss(np.array([x, v])) for v in yg] for x in xg])
+    i, j = np.unravel_index(np.argmin(ll), ll.shape)
+    delta = xg[1] - xg[0]
+    fx = np.linspace(xg[i] - delta, xg[i] + delta, grid_length)
+    fy = np.linspace(yg[j] - delta, yg[j] + delta, grid_length)
+    ll = np.array([[loss(np.array([x, v])) for v in fy] for x in fx])
+    i, j = np.unravel_index(np.argmin(ll), ll.shape)
+    return np.array([fx[i], fy[j]])
+
+
+def nbinom_glm_gene(X, y, size, offset, prior_no_shrink_scale, prior_scale, optimizer="L-BFGS-B", shrink_index=1,
+                    force_grid=False):
+    """MAP LFC of one gene under the apeGLM prior (utils.py:990-1145).  Returns (beta, inv_hessian, converged)."""
+    p = X.shape[-1]
+    beta_init = np.ones(p) * 0.1 * (-1) ** np.arange(p)
+    args = (X, y, size, offset, prior_no_shrink_scale, prior_scale, shrink_index)
+    cnst = np.maximum(nbinom_fn(np.zeros(p), *args), 1)
+    res = _minimize(lambda b: nbinom_fn(b, *args) / cnst, beta_init, jac=lambda b: nbinom_grad(b, *args) / cnst,
+                    hess=(lambda b: nbinom_hess(b, *args) / cnst) if optimizer == "Newton-CG" else None,
+                    method=optimizer, options={"ftol": 1e-8, "gtol": 1e-8})
+    beta, converged = res.x, bool(res.success) and not force_grid
+    if not converged and p == 2:
+        beta = grid_fit_shrink_beta(y, offset, X, size, prior_no_shrink_scale, prior_scale, cnst)
+    return beta, np.linalg.inv(nbinom_hess(beta, *args)), converged
+
+
+def fit_shrink_prior_var(lfc, se, min_var=1e-6, max_var=400.0):
+    """Prior variance of the apeGLM model from the MLE LFCs and their SEs (ds.py:551-585)."""
+    from scipy.optimize import root_scalar
+
+    keep = ~np.isnan(lfc)
+    S, D = lfc[keep] ** 2, se[keep] ** 2
+
+    def objective(a):
+        coeff = 1 / (2 * (a + D) ** 2)
+        return ((S - D) * coeff).sum() / coeff.sum() - a
+
+    if objective(min_var) < 0:
+        return min_var
+    return root_scalar(objective, bracket=(min_var, max_var)).root
+
+
 # --------------------------------------------------------------------------- gene fan-out (a6)
 class OracleInference:
     """Gene fan-out with the reference's scheduling (default_inference.py:14-198).
@@ -352,6 +442,15 @@ class OracleInference:
                                  alt_hypothesis))
         pv, st, se = (np.array(v, dtype=float) for v in zip(*r))
         return pv, st, se
+
+    def lfc_shrink_nbinom_glm(self, design_matrix, counts, size, offset, prior_no_shrink_scale, prior_scale,
+                              optimizer="L-BFGS-B", shrink_index=1):
+        """default_inference.py:232-264."""
+        r = self._map(nbinom_glm_gene, counts.shape[1],
+                      lambda i: (design_matrix, counts[:, i], size[i], offset, prior_no_shrink_scale, prior_scale,
+                                 optimizer, shrink_index))
+        b, ih, c = (np.array(v) for v in zip(*r))
+        return b, ih, c.astype(float)
 
     fit_rough_dispersions = staticmethod(fit_rough_dispersions)
     fit_moments_dispersions = staticmethod(fit_moments_dispersions)

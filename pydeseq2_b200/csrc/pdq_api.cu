@@ -39,6 +39,7 @@ enum { kBufCounts, kBufA, kBufB, kBufC, kBufD, kBufE, kBufF, kBufG, kBufStatus, 
 struct DesignCacheEntry {
     pdq_design* d = nullptr;
     std::vector<double> X, sf;
+    bool offsets = false;  // `sf` holds log size factors given by the caller (apeGLM offsets)
     uint64_t stamp = 0;
 };
 
@@ -62,8 +63,8 @@ struct pdq_ctx {
     int staging = 1;  // PDQ_STAGING=0 disables (plain cudaMemcpyAsync from pageable memory)
     int* tickets = nullptr;  // device ints for the persistent kernels' tile counters (4 per stream slot)
     cudaStream_t pstream[2] = {nullptr, nullptr};  // gene-block pipeline of the host-buffer entry points
-    cudaEvent_t pfork = nullptr;
-    int pipeline = 1;        // PDQ_PIPELINE=0 disables
+    cudaEvent_t pfork = nullptr, pjoin[2] = {nullptr, nullptr};
+    int pipeline = 4;        // gene blocks per pipelined call; PDQ_PIPELINE=0 disables
     int debug = 0;           // PDQ_DEBUG_* test hooks
     int64_t launches_at_capture = 0;
     NcclApi nccl;
@@ -165,7 +166,9 @@ extern "C" int pdq_ctx_create(int device, pdq_ctx** out) {
     if (const char* s = getenv("PDQ_PIPELINE")) c->pipeline = atoi(s);
     if (cudaMalloc((void**)&c->tickets, 64) != cudaSuccess || cudaStreamCreateWithFlags(&c->pstream[0], cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->pstream[1], cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->pfork, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&c->pfork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->pjoin[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->pjoin[1], cudaEventDisableTiming) != cudaSuccess) {
         delete c;
         return PDQ_ERR_CUDA;
     }
@@ -185,6 +188,8 @@ extern "C" void pdq_ctx_destroy(pdq_ctx* c) {
     for (auto& st : c->pstream)
         if (st) cudaStreamDestroy(st);
     if (c->pfork) cudaEventDestroy(c->pfork);
+    for (auto& ev : c->pjoin)
+        if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) {
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
         if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
@@ -334,7 +339,8 @@ extern "C" void pdq_graph_destroy(pdq_ctx* c, pdq_graph* g) {
 }
 
 // --------------------------------------------------------------------------------------------- design pack
-extern "C" int pdq_design_create(pdq_ctx* c, const double* X, const double* sf, int N, int p, pdq_design** out) {
+// `offsets`: `sf` holds LOG size factors (the apeGLM call receives them in that form, and exp/log is not the identity in FP64)
+static int design_create(pdq_ctx* c, const double* X, const double* sf, bool offsets, int N, int p, pdq_design** out) {
     if (!c || !X || !out || N <= 0 || p < 1) return fail(c, PDQ_ERR_INVALID, "pdq_design_create: bad arguments");
     if (p > PDQ_MAX_P) return fail(c, PDQ_ERR_UNSUPPORTED, "design has %d columns; this build supports p <= %d", p, PDQ_MAX_P);
     CU(c, cudaSetDevice(c->device));
@@ -367,9 +373,9 @@ extern "C" int pdq_design_create(pdq_ctx* c, const double* X, const double* sf, 
     double inv_sum = 0.0;
     for (int n = 0; n < N; ++n) {
         for (int j = 0; j < p; ++j) pack[(size_t)j * dd.Npad + n] = X[(size_t)n * p + j];
-        const double s = sf ? sf[n] : 1.0;
+        const double s = sf ? (offsets ? exp(sf[n]) : sf[n]) : 1.0;
         pack[(size_t)p * dd.Npad + n] = s;
-        pack[(size_t)(p + 1) * dd.Npad + n] = log(s);
+        pack[(size_t)(p + 1) * dd.Npad + n] = (sf && offsets) ? sf[n] : log(s);
         inv_sum += 1.0 / s;
     }
     for (int n = N; n < dd.Npad; ++n) pack[(size_t)p * dd.Npad + n] = 1.0;
@@ -390,6 +396,10 @@ extern "C" int pdq_design_create(pdq_ctx* c, const double* X, const double* sf, 
     return PDQ_OK;
 }
 
+extern "C" int pdq_design_create(pdq_ctx* c, const double* X, const double* sf, int N, int p, pdq_design** out) {
+    return design_create(c, X, sf, false, N, p, out);
+}
+
 extern "C" void pdq_design_destroy(pdq_ctx* c, pdq_design* d) {
     if (!d) return;
     if (c) cudaSetDevice(c->device);
@@ -399,21 +409,21 @@ extern "C" void pdq_design_destroy(pdq_ctx* c, pdq_design* d) {
 }
 
 // design cache for the host-buffer entry points: deseq2() passes the same X (and size factors) to every call
-static int cached_design(pdq_ctx* c, const double* X, const double* sf, int N, int p, pdq_design** out) {
+static int cached_design(pdq_ctx* c, const double* X, const double* sf, int N, int p, pdq_design** out, bool offsets = false) {
     // a deseq2() pass alternates between three packs -- (X, sf), (X, no sf), (ones, sf) -- so a one-entry cache would
     // rebuild (SVD, cell plan, two cudaMallocs, two synchronous copies) on almost every call: keep the last few
     const size_t nx = (size_t)N * p;
     for (size_t i = 0; i < c->dcache.size(); ++i) {
         DesignCacheEntry& e = c->dcache[i];
         if (e.d->d.N == N && e.d->d.p == p && e.X.size() == nx && memcmp(e.X.data(), X, nx * 8) == 0 &&
-            ((sf == nullptr) == e.sf.empty()) && (!sf || memcmp(e.sf.data(), sf, (size_t)N * 8) == 0)) {
+            ((sf == nullptr) == e.sf.empty()) && e.offsets == offsets && (!sf || memcmp(e.sf.data(), sf, (size_t)N * 8) == 0)) {
             e.stamp = ++c->dcache_clock;
             *out = e.d;
             return PDQ_OK;
         }
     }
     pdq_design* d = nullptr;
-    if (int e = pdq_design_create(c, X, sf, N, p, &d)) return e;
+    if (int e = design_create(c, X, sf, offsets, N, p, &d)) return e;
     if (c->dcache.size() >= 4) {  // evict the least recently used pack
         size_t lru = 0;
         for (size_t i = 1; i < c->dcache.size(); ++i)
@@ -425,6 +435,7 @@ static int cached_design(pdq_ctx* c, const double* X, const double* sf, int N, i
     e.d = d;
     e.X.assign(X, X + nx);
     if (sf) e.sf.assign(sf, sf + N);
+    e.offsets = offsets;
     e.stamp = ++c->dcache_clock;
     c->dcache.push_back(std::move(e));
     *out = d;
@@ -480,6 +491,17 @@ extern "C" int pdq_wald_test_dev(pdq_ctx* c, const pdq_design* d, const double* 
     if (!d || !disp || !lfc || !mu || !ridge || !contrast || !pv || !stat || !se || G <= 0 || ld_mu < G || alt < 0 || alt > 4)
         return fail(c, PDQ_ERR_INVALID, "pdq_wald_test_dev: bad arguments");
     return done(c, launch_wald(cfg(c, G, d->d.N), d->d, disp, lfc, mu, ld_mu, G, ridge, contrast, lfc_null, alt, pv, stat, se), "wald_test");
+}
+
+extern "C" int pdq_lfc_shrink_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, const double* size,
+                                  double prior_no_shrink_scale, double prior_scale, int shrink_index, double* lfcs, double* inv_hessians,
+                                  double* conv, int* status) {
+    CHECK_CTX(c);
+    if (!d || !counts || !size || !lfcs || !inv_hessians || !conv || !status || G <= 0 || ld < G || shrink_index < 0 ||
+        shrink_index >= d->d.p || !(prior_no_shrink_scale > 0.0) || !(prior_scale > 0.0))
+        return fail(c, PDQ_ERR_INVALID, "pdq_lfc_shrink_dev: bad arguments");
+    return done(c, launch_lfc_shrink(cfg(c, G, d->d.N), d->d, counts, ld, G, size, prior_no_shrink_scale, prior_scale, shrink_index, lfcs,
+                                     inv_hessians, conv, status), "lfc_shrink");
 }
 
 extern "C" int pdq_mom_dispersions_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, double min_disp,
@@ -635,7 +657,7 @@ static int h2d_2d(pdq_ctx* c, void* dst, const void* src, int64_t ld, int N, int
 // is split into gene blocks on two streams: the column block k+1 is uploaded while block k computes and block k-1 is
 // downloaded (PCIe is full duplex, the kernels take `ld`, so a block is just a pointer offset).  Per-gene results do not
 // depend on the split (different lane-group widths only change the order of the floating-point sums).
-static const int kPipeBlocks = 4;
+static const int kPipeMaxBlocks = 16;  // PDQ_PIPELINE=<blocks> (0/1 = off)
 
 struct Pipe {
     pdq_ctx* c;
@@ -653,13 +675,14 @@ struct Pipe {
 };
 
 static int pipe_begin(pdq_ctx* c, int G, std::initializer_list<const void*> big_host, Pipe* p) {
-    bool on = c->pipeline && c->staging && G >= 4096;
+    const int want = c->pipeline > kPipeMaxBlocks ? kPipeMaxBlocks : c->pipeline;
+    bool on = want > 1 && c->staging && G >= 4096;
     for (const void* h : big_host) on = on && is_pinned(h);
     p->c = c;
     p->on = on;
     p->G = G;
-    p->nb = on ? kPipeBlocks : 1;
-    p->Gb = on ? (((G + kPipeBlocks - 1) / kPipeBlocks + 15) & ~15) : G;
+    p->nb = on ? want : 1;
+    p->Gb = on ? (((G + want - 1) / want + 15) & ~15) : G;
     if (on) {
         while (p->nb > 1 && (p->nb - 1) * p->Gb >= G) --p->nb;
         CU(c, cudaEventRecord(c->pfork, c->stream));
@@ -669,13 +692,21 @@ static int pipe_begin(pdq_ctx* c, int G, std::initializer_list<const void*> big_
     return 0;
 }
 
-static int pipe_end(pdq_ctx* c, const Pipe& p) {
+// joins the block streams back into c->stream (small per-gene vectors are moved whole on c->stream, before the fork and
+// after the join: they may be pageable, and a pageable async copy blocks the host until the stream reaches it)
+static int pipe_join(pdq_ctx* c, const Pipe& p) {
     if (p.on) {
-        CU(c, cudaStreamSynchronize(c->pstream[0]));
-        CU(c, cudaStreamSynchronize(c->pstream[1]));
-    } else {
-        CU(c, cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 2; ++i) {
+            CU(c, cudaEventRecord(c->pjoin[i], c->pstream[i]));
+            CU(c, cudaStreamWaitEvent(c->stream, c->pjoin[i], 0));
+        }
     }
+    return 0;
+}
+
+static int pipe_end(pdq_ctx* c, const Pipe& p) {
+    if (int e = pipe_join(c, p)) return e;
+    CU(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -692,15 +723,12 @@ static int cols_d2h(pdq_ctx* c, const Pipe& p, int b, void* host, int64_t ld_h, 
                             (size_t)ld_d * elem, (size_t)p.gb(b) * elem, N, cudaMemcpyDeviceToHost, p.st(b)));
     return 0;
 }
-// per-gene vector block (rows of `width` doubles per gene)
-static int vec_h2d(pdq_ctx* c, const Pipe& p, int b, void* dev, const void* host, size_t width) {
-    CU(c, cudaMemcpyAsync((char*)dev + (size_t)p.g0(b) * width * 8, (const char*)host + (size_t)p.g0(b) * width * 8,
-                          (size_t)p.gb(b) * width * 8, cudaMemcpyHostToDevice, p.st(b)));
+static int vec_h2d(pdq_ctx* c, void* dev, const void* host, size_t bytes) {
+    CU(c, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
-static int vec_d2h(pdq_ctx* c, const Pipe& p, int b, void* host, const void* dev, size_t width) {
-    CU(c, cudaMemcpyAsync((char*)host + (size_t)p.g0(b) * width * 8, (const char*)dev + (size_t)p.g0(b) * width * 8,
-                          (size_t)p.gb(b) * width * 8, cudaMemcpyDeviceToHost, p.st(b)));
+static int vec_d2h(pdq_ctx* c, void* host, const void* dev, size_t bytes) {
+    CU(c, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
     return 0;
 }
 
@@ -747,24 +775,28 @@ extern "C" int pdq_irls(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, in
     if (int e = ensure(c, kBufStatus, (size_t)G * sizeof(int), &status)) return e;
     const IrlsHost h{min_mu, beta_tol, min_beta, max_beta, maxiter};
     Pipe pp;
+    if (int e = vec_h2d(c, ddisp, disp, (size_t)G * 8)) return e;
     if (int e = pipe_begin(c, G, {counts, mu_out, hat_out}, &pp)) return e;
-    int nfb[kPipeBlocks] = {0, 0, 0, 0};
+    int nfb[kPipeMaxBlocks] = {};
     for (int b = 0; b < pp.nb; ++b) {
         const int g0 = pp.g0(b), gb = pp.gb(b);
         if (int e = cols_h2d(c, pp, b, dc, G, counts, ld, N, 8)) return e;
-        if (int e = vec_h2d(c, pp, b, ddisp, disp, 1)) return e;
         if (int e = done(c, launch_irls(pp.cfg_for(b, N), d->d, (const int64_t*)dc + g0, G, gb, (const double*)ddisp + g0, h,
                                         (double*)dbeta + (size_t)g0 * p, (double*)dmu + g0, (double*)dhat + g0, G, (double*)dconv + g0,
                                         (int*)status + g0, (int*)dmisc + b), "irls"))
             return e;
-        if (int e = vec_d2h(c, pp, b, beta_out, dbeta, (size_t)p)) return e;
-        if (int e = vec_d2h(c, pp, b, conv_out, dconv, 1)) return e;
         if (int e = cols_d2h(c, pp, b, mu_out, G, dmu, G, N, 8)) return e;
         if (int e = cols_d2h(c, pp, b, hat_out, G, dhat, G, N, 8)) return e;
-        CU(c, cudaMemcpyAsync(&nfb[b], (int*)dmisc + b, sizeof(int), cudaMemcpyDeviceToHost, pp.st(b)));
     }
-    if (int e = pipe_end(c, pp)) return e;
-    if (n_fallback) *n_fallback = nfb[0] + nfb[1] + nfb[2] + nfb[3];
+    if (int e = pipe_join(c, pp)) return e;
+    if (int e = vec_d2h(c, beta_out, dbeta, (size_t)G * p * 8)) return e;
+    if (int e = vec_d2h(c, conv_out, dconv, (size_t)G * 8)) return e;
+    if (int e = vec_d2h(c, nfb, dmisc, (size_t)pp.nb * sizeof(int))) return e;
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (n_fallback) {
+        *n_fallback = 0;
+        for (int b = 0; b < pp.nb; ++b) *n_fallback += nfb[b];
+    }
     return PDQ_OK;
 }
 
@@ -787,20 +819,22 @@ extern "C" int pdq_alpha_mle(pdq_ctx* c, const int64_t* counts, int64_t ld, int 
     void* status;
     if (int e = ensure(c, kBufStatus, (size_t)G * sizeof(int), &status)) return e;
     Pipe pp;
+    if (int e = vec_h2d(c, dah, alpha_hat, (size_t)G * 8)) return e;
     if (int e = pipe_begin(c, G, {counts, mu}, &pp)) return e;
     for (int b = 0; b < pp.nb; ++b) {
         const int g0 = pp.g0(b), gb = pp.gb(b);
         if (int e = cols_h2d(c, pp, b, dc, G, counts, ld, N, 8)) return e;
         if (int e = cols_h2d(c, pp, b, dmu, G, mu, ld_mu, N, 8)) return e;
-        if (int e = vec_h2d(c, pp, b, dah, alpha_hat, 1)) return e;
         if (int e = done(c, launch_alpha_mle(pp.cfg_for(b, N), d->d, (const int64_t*)dc + g0, G, gb, (const double*)dmu + g0, G,
                                              (const double*)dah + g0, min_disp, max_disp, prior_disp_var, nullptr, cr_reg, prior_reg,
                                              (double*)dal + g0, (double*)dconv + g0, (int*)status + g0), "alpha_mle"))
             return e;
-        if (int e = vec_d2h(c, pp, b, alpha_out, dal, 1)) return e;
-        if (int e = vec_d2h(c, pp, b, conv_out, dconv, 1)) return e;
     }
-    return pipe_end(c, pp);
+    if (int e = pipe_join(c, pp)) return e;
+    if (int e = vec_d2h(c, alpha_out, dal, (size_t)G * 8)) return e;
+    if (int e = vec_d2h(c, conv_out, dconv, (size_t)G * 8)) return e;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return PDQ_OK;
 }
 
 extern "C" int pdq_wald_test(pdq_ctx* c, const double* X, int N, int p, const double* disp, const double* lfc, const double* mu,
@@ -821,21 +855,23 @@ extern "C" int pdq_wald_test(pdq_ctx* c, const double* X, int N, int p, const do
     if (int e = ensure(c, kBufG, (size_t)G * 8, &dse)) return e;
     if (alt < 0 || alt > 4) return fail(c, PDQ_ERR_INVALID, "pdq_wald_test: unknown alternative");
     Pipe pp;
+    if (int e = vec_h2d(c, ddisp, disp, (size_t)G * 8)) return e;
+    if (int e = vec_h2d(c, dlfc, lfc, (size_t)G * p * 8)) return e;
     if (int e = pipe_begin(c, G, {mu}, &pp)) return e;
     for (int b = 0; b < pp.nb; ++b) {
         const int g0 = pp.g0(b), gb = pp.gb(b);
         if (int e = cols_h2d(c, pp, b, dmu, G, mu, ld_mu, N, 8)) return e;
-        if (int e = vec_h2d(c, pp, b, ddisp, disp, 1)) return e;
-        if (int e = vec_h2d(c, pp, b, dlfc, lfc, (size_t)p)) return e;
         if (int e = done(c, launch_wald(pp.cfg_for(b, N), d->d, (const double*)ddisp + g0, (const double*)dlfc + (size_t)g0 * p,
                                         (const double*)dmu + g0, G, gb, ridge, contrast, lfc_null, alt, (double*)dp + g0, (double*)ds + g0,
                                         (double*)dse + g0), "wald_test"))
             return e;
-        if (int e = vec_d2h(c, pp, b, pv_out, dp, 1)) return e;
-        if (int e = vec_d2h(c, pp, b, stat_out, ds, 1)) return e;
-        if (int e = vec_d2h(c, pp, b, se_out, dse, 1)) return e;
     }
-    return pipe_end(c, pp);
+    if (int e = pipe_join(c, pp)) return e;
+    if (int e = vec_d2h(c, pv_out, dp, (size_t)G * 8)) return e;
+    if (int e = vec_d2h(c, stat_out, ds, (size_t)G * 8)) return e;
+    if (int e = vec_d2h(c, se_out, dse, (size_t)G * 8)) return e;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return PDQ_OK;
 }
 
 extern "C" int pdq_fit_rough_dispersions(pdq_ctx* c, const double* normed, int64_t ld, int N, int G, const double* X, int p,
@@ -908,6 +944,42 @@ extern "C" int pdq_calculate_cooks(pdq_ctx* c, const int64_t* counts, int64_t ld
     CU(c, cudaMemcpyAsync(outlier_out, dout, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(replaced_out, drep, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    return PDQ_OK;
+}
+
+extern "C" int pdq_lfc_shrink_nbinom_glm(pdq_ctx* c, const double* X, const int64_t* counts, int64_t ld, int N, int G, int p, const double* size,
+                                         const double* offset, double prior_no_shrink_scale, double prior_scale, int shrink_index,
+                                         double* lfcs_out, double* inv_hessians_out, double* conv_out, int* n_grid) {
+    CHECK_CTX(c);
+    if (!X || !counts || !size || !offset || !lfcs_out || !inv_hessians_out || !conv_out || N <= 0 || G <= 0 || ld < G)
+        return fail(c, PDQ_ERR_INVALID, "pdq_lfc_shrink_nbinom_glm: bad arguments");
+    pdq_design* d;  // the kernel reads the offsets from the log-size-factor row of the design pack
+    if (int e = cached_design(c, X, offset, N, p, &d, true)) return e;
+    void *dc, *dsize, *dbeta, *dih, *dconv, *status;
+    if (int e = ensure(c, kBufCounts, (size_t)N * G * 8, &dc)) return e;
+    if (int e = ensure(c, kBufC, (size_t)G * 8, &dsize)) return e;
+    if (int e = ensure(c, kBufD, (size_t)G * p * 8, &dbeta)) return e;
+    if (int e = ensure(c, kBufA, (size_t)G * p * p * 8, &dih)) return e;
+    if (int e = ensure(c, kBufE, (size_t)G * 8, &dconv)) return e;
+    if (int e = ensure(c, kBufStatus, (size_t)G * sizeof(int), &status)) return e;
+    if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
+    CU(c, cudaMemcpyAsync(dsize, size, (size_t)G * 8, cudaMemcpyHostToDevice, c->stream));
+    if (int e = pdq_lfc_shrink_dev(c, d, (const int64_t*)dc, G, G, (const double*)dsize, prior_no_shrink_scale, prior_scale, shrink_index,
+                                   (double*)dbeta, (double*)dih, (double*)dconv, (int*)status))
+        return e;
+    CU(c, cudaMemcpyAsync(lfcs_out, dbeta, (size_t)G * p * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(inv_hessians_out, dih, (size_t)G * p * p * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(conv_out, dconv, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<int> st;
+    if (n_grid) {
+        st.resize((size_t)G);
+        CU(c, cudaMemcpyAsync(st.data(), status, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (n_grid) {
+        *n_grid = 0;
+        for (int v : st) *n_grid += (v != 0);
+    }
     return PDQ_OK;
 }
 

@@ -60,6 +60,9 @@ int launch_trend_fit(const LaunchCfg&, const double* x, const double* t, double*
 int launch_trend_eval(const LaunchCfg&, const double* means, size_t n, const double* out16, double* fitted);
 int launch_cooks(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64_t ld, int G, const double* mu, const double* hat,
                  int64_t ld2, double cutoff, double* cooks, int64_t ld_out, double* disp, double* outlier, double* replaced);
+int launch_lfc_shrink(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64_t ld, int G, const double* size,
+                      double prior_no_shrink_scale, double prior_scale, int shrink_index, double* beta, double* inv_hessian,
+                      double* conv, int* status);
 int launch_size_factors(const LaunchCfg&, const int64_t* counts, int64_t ld, int N, int G, double* logmeans,
                         double* scratch, double* sf_out);
 int launch_select_disp(const LaunchCfg&, const double* gw, const double* mp, const double* fitted, const double* out16,

@@ -16,6 +16,7 @@
 
 #include "pdq_gene.cuh"
 #include "pdq_trend.cuh"
+#include "pdq_shrink.cuh"
 #include "pdq_internal.h"
 
 namespace pdq {
@@ -688,6 +689,46 @@ SmallMat<P> pinv_of(const DesignDev& d) {
     return m;
 }
 
+
+// ---- apeGLM shrinkage ----------------------------------------------------------------------------
+template <int P>
+struct ShrinkArgs {
+    DesignView dv;
+    ShrinkParams prm;
+    const int64_t* counts;
+    int64_t ld;
+    int G, lgT;
+    const double* size;
+    double *beta, *ih, *conv;
+    int* status;
+    int force;  // test hook: send every gene of a two-column design through the grid fallback
+};
+
+template <int P>
+__global__ void __launch_bounds__(kBlock) k_lfc_shrink(const __grid_constant__ ShrinkArgs<P> a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(a.lgT, a.G, grp, g, valid);
+    shrink_gene<P>(grp, d, a.prm, a.counts + g, a.ld, a.size[g], a.beta + (int64_t)g * P, a.ih + (int64_t)g * P * P, a.conv + g,
+                   a.status + g, valid, a.force != 0);
+}
+
+__global__ void __launch_bounds__(kBlock) k_lfc_shrink_grid(const __grid_constant__ ShrinkArgs<2> a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Group grp;
+    int g;
+    bool valid;
+    map_lanes(a.lgT, a.G, grp, g, valid);
+    const bool run = valid && a.status[g] == kShrinkNeedsGrid;
+    if (!__syncthreads_or(run)) return;
+    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, 2, smem);
+    if (!__any_sync(0xffffffffu, run)) return;
+    shrink_grid_gene(grp, d, a.prm, a.counts + g, a.ld, a.size[g], a.beta + (int64_t)g * 2, a.ih + (int64_t)g * 4, run);
+}
+
 #define PDQ_DISPATCH_P(p, ...)             \
     switch (p) {                           \
         case 1: { constexpr int P = 1; __VA_ARGS__; } break; \
@@ -886,6 +927,27 @@ int launch_cooks(const LaunchCfg& c0, const DesignDev& d, const int64_t* counts,
     });
     if (int e = check_launch()) return e;
     return 1;
+}
+
+
+int launch_lfc_shrink(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G, const double* size,
+                      double prior_no_shrink_scale, double prior_scale, int shrink_index, double* beta, double* inv_hessian,
+                      double* conv, int* status) {
+    if (shrink_index < 0 || shrink_index >= d.p) return PDQ_ERR_INVALID;
+    const ShrinkParams prm{1.0 / (prior_no_shrink_scale * prior_no_shrink_scale), prior_scale * prior_scale, shrink_index};
+    const int force = (c.debug & PDQ_DEBUG_FORCE_SHRINK_GRID) ? 1 : 0;
+    PDQ_DISPATCH_P(d.p, {
+        ShrinkArgs<P> a{{d.pack, d.N, d.Npad}, prm, counts, ld, G, c.lgT, size, beta, inv_hessian, conv, status, force};
+        if (int e = prep(k_lfc_shrink<P>, d.smem_bytes)) return e;
+        k_lfc_shrink<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+    });
+    if (d.p == 2) {
+        ShrinkArgs<2> a{{d.pack, d.N, d.Npad}, prm, counts, ld, G, c.lgT, size, beta, inv_hessian, conv, status, force};
+        if (int e = prep(k_lfc_shrink_grid, d.smem_bytes)) return e;
+        k_lfc_shrink_grid<<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+    }
+    if (int e = check_launch()) return e;
+    return d.p == 2 ? 2 : 1;
 }
 
 int launch_size_factors(const LaunchCfg& c, const int64_t* counts, int64_t ld, int N, int G, double* logmeans,

@@ -15,7 +15,7 @@ Deliberate differences from ``DefaultInference`` (all documented in DESIGN.md):
 * the dispersion optimum is located by a bounded root search on the analytic derivative instead of
   scipy's L-BFGS-B, so a gene for which L-BFGS-B reports ``ABNORMAL`` and the reference substitutes
   its grid value (``utils.py:556-564``) is returned at the true optimum with ``converged = 1``.
-* ``lfc_shrink_nbinom_glm`` (apeGLM, not part of ``deseq2()`` + Wald) is outside this backend.
+* ``lfc_shrink_nbinom_glm`` (apeGLM, ``DeseqStats.lfc_shrink``) runs the reference's own L-BFGS-B iteration per gene.
 """
 from __future__ import annotations
 
@@ -153,6 +153,15 @@ class _CudaOps:
     def size_factors(self, counts, ld, N, G, sf):
         self._io((counts,), (sf,))
         self.ctx.check(self.lib.pdq_size_factors(self.ctx.h, as_i64p(counts), ld, N, G, as_f64p(sf)))
+
+    def lfc_shrink(self, X, counts, ld, N, G, p, size, offset, prior_no_shrink_scale, prior_scale, shrink_index, lfcs, inv_hessians,
+                   conv):
+        n_grid = C.c_int(0)
+        self._io((counts,), (lfcs, inv_hessians, conv))
+        self.ctx.check(self.lib.pdq_lfc_shrink_nbinom_glm(self.ctx.h, as_f64p(X), as_i64p(counts), ld, N, G, p, as_f64p(size),
+                                                          as_f64p(offset), prior_no_shrink_scale, prior_scale, shrink_index,
+                                                          as_f64p(lfcs), as_f64p(inv_hessians), as_f64p(conv), C.byref(n_grid)))
+        return n_grid.value
 
     def trend_glm(self, cov, targets):
         n = len(cov)
@@ -363,12 +372,35 @@ class B200Inference(_InferenceBase):
             self._ops.cooks(counts, ld, N, G, sf, X, p, mu, hat, ld2, cutoff, cooks, disp, outlier, replaced)
         return cooks, disp, outlier == 1.0, replaced == 1.0
 
-    def lfc_shrink_nbinom_glm(self, design_matrix, counts, size, offset, prior_no_shrink_scale, prior_scale, optimizer,
-                              shrink_index):  # noqa: D102
-        raise NotImplementedError(
-            "apeGLM LFC shrinkage (inference.py:309-362) is outside the B200 hot path (SURVEY.md §8f-3); "
-            "pass the reference's DefaultInference to DeseqStats.lfc_shrink()."
-        )
+    def lfc_shrink_nbinom_glm(self, design_matrix, counts, size, offset, prior_no_shrink_scale, prior_scale,
+                              optimizer="L-BFGS-B", shrink_index=1):
+        """apeGLM MAP log-fold changes (``inference.py:309-362`` -> ``utils.nbinomGLM`` utils.py:990-1145).
+
+        Returns ``(lfcs (G, p), inv_hessians (G, p, p), l_bfgs_b_converged (G,) float 0/1)``.  The kernel walks the
+        reference's own optimiser path (unconstrained L-BFGS-B, ftol = gtol = 1e-8) and, for two-column designs, refits
+        the genes that did not converge on the reference's 2-D grid; ``last_shrink_grid`` counts them.  ``optimizer`` must be
+        ``"L-BFGS-B"``, the only value the reference's caller passes (ds.py:400-409).
+        """
+        if optimizer != "L-BFGS-B":
+            raise NotImplementedError(f"optimizer={optimizer!r}: only the reference's default 'L-BFGS-B' path is implemented")
+        counts, ld = _rows(counts, np.int64, "counts")
+        X = np.ascontiguousarray(_f64(design_matrix, "design_matrix", 2))
+        N, G = counts.shape
+        p = X.shape[1]
+        self._check_design(X, N)
+        size = np.ascontiguousarray(_f64(size, "size", 1))
+        offset = np.ascontiguousarray(_f64(offset, "offset", 1))
+        shrink_index = int(shrink_index)
+        if size.shape != (G,) or offset.shape != (N,):
+            raise ValueError("size must have one entry per gene and offset one per sample")
+        if not 0 <= shrink_index < p:
+            raise IndexError(f"shrink_index {shrink_index} out of range for {p} design columns")
+        lfcs, ih, conv = np.empty((G, p)), np.empty((G, p, p)), np.empty(G)
+        self.last_shrink_grid = 0
+        if G:
+            self.last_shrink_grid = self._ops.lfc_shrink(X, counts, ld, N, G, p, size, offset, float(prior_no_shrink_scale),
+                                                         float(prior_scale), shrink_index, lfcs, ih, conv)
+        return lfcs, ih, conv
 
     # ------------------------------------------------------------------ helpers
     @staticmethod

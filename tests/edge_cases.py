@@ -136,6 +136,49 @@ def check_alpha_grid(inf, force):
     assert np.all(np.abs(np.log(a) - np.log(want)) <= 2 * (np.log(max(10, N)) - np.log(1e-8)) / 99 * 2 / 99 + 1e-12)
 
 
+def check_shrink_grid(inf, force):
+    """apeGLM grid fallback (grid_search.py:224-318), forced for every gene of a two-column design: same grid nodes as the
+    reference, so the result is the oracle's bit for bit unless two nodes tie to rounding."""
+    for name, n in (("shrink_two_level_n24", 10), ("shrink_few_samples_n4", 6), ("shrinktape_large_counts", 5)):
+        g = load_golden(name)
+        c = np.ascontiguousarray(g["counts"][:, :n])
+        args = (float(g["prior_no_shrink_scale"]), float(g["prior_scale"]), "L-BFGS-B", int(g["shrink_index"]))
+        force(True)
+        try:
+            lfcs, ih, conv = inf.lfc_shrink_nbinom_glm(g["X"], c, g["size"][:n], g["offset"], *args)
+        finally:
+            force(False)
+        assert (conv == 0).all() and inf.last_shrink_grid == n
+        for i in range(n):
+            b, h, cv = nbglm.nbinom_glm_gene(g["X"], c[:, i], g["size"][i], g["offset"], *args, force_grid=True)
+            assert not cv
+            np.testing.assert_allclose(lfcs[i], b, rtol=0, atol=2.1 * 60.0 / 59.0 * 2.0 / 59.0)  # at most one fine-grid node away
+            if np.array_equal(lfcs[i], b):
+                np.testing.assert_allclose(ih[i], h, rtol=1e-9)
+        assert np.mean([np.array_equal(lfcs[i], nbglm.nbinom_glm_gene(g["X"], c[:, i], g["size"][i], g["offset"], *args,
+                                                                      force_grid=True)[0]) for i in range(n)]) >= 0.8
+
+
+def check_shrink_arguments(inf):
+    g = load_golden("shrink_two_level_n24")
+    a = (g["X"], g["counts"], g["size"], g["offset"], 15.0, 1.0)
+    with pytest.raises(NotImplementedError):
+        inf.lfc_shrink_nbinom_glm(*a, "Newton-CG", 1)
+    with pytest.raises(IndexError):
+        inf.lfc_shrink_nbinom_glm(*a, "L-BFGS-B", 2)
+    with pytest.raises(ValueError):
+        inf.lfc_shrink_nbinom_glm(g["X"], g["counts"], g["size"][:-1], g["offset"], 15.0, 1.0, "L-BFGS-B", 1)
+    lfcs, ih, conv = inf.lfc_shrink_nbinom_glm(g["X"], g["counts"][:, :0], g["size"][:0], g["offset"], 15.0, 1.0, "L-BFGS-B", 1)
+    assert lfcs.shape == (0, 2) and ih.shape == (0, 2, 2) and conv.shape == (0,)
+    # genes are independent and the call is deterministic: a permutation of the genes permutes the results bit for bit
+    perm = np.random.default_rng(0).permutation(g["counts"].shape[1])
+    r1 = inf.lfc_shrink_nbinom_glm(*a, "L-BFGS-B", 1)
+    r2 = inf.lfc_shrink_nbinom_glm(g["X"], np.ascontiguousarray(g["counts"][:, perm]), g["size"][perm], g["offset"], 15.0, 1.0,
+                                   "L-BFGS-B", 1)
+    for u, v in zip(r1, r2):
+        np.testing.assert_array_equal(u[perm], v)
+
+
 def check_size_factors(inf):
     """Median-of-ratios on the device: same values as the reference (golden `final_size_factors` of the reference's
     shipped datasets and seeded inputs), and -- the north star's criterion -- bit-identical RANKS across samples."""

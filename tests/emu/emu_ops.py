@@ -16,7 +16,7 @@ def _p(a, t):
 
 
 class EmuOps:
-    def __init__(self, force_optimizer=False, force_grid=False):
+    def __init__(self, force_optimizer=False, force_grid=False, force_shrink_grid=False):
         self.lib = C.CDLL(_build.build())
         self.lib.emu_lgamma.restype = C.c_double
         self.lib.emu_lgamma.argtypes = [C.c_double]
@@ -24,6 +24,7 @@ class EmuOps:
         self.lib.emu_digamma.argtypes = [C.c_double]
         self.force_optimizer = int(force_optimizer)
         self.force_grid = int(force_grid)
+        self.force_shrink_grid = int(force_shrink_grid)
         self.last_status = None
 
     def empty(self, shape):
@@ -89,6 +90,16 @@ class EmuOps:
         assert self.lib.emu_trend_fit(_p(means, f64p), _p(gw, f64p), C.c_size_t(len(gw)), 1, C.c_double(lo), C.c_double(hi), 1,
                                       C.c_double(min_disp), C.c_double(trigamma_c), int(with_prior), _p(out, f64p)) == 0
         return out
+
+    def lfc_shrink(self, X, counts, ld, N, G, p, size, offset, prior_no_shrink_scale, prior_scale, shrink_index, lfcs, inv_hessians,
+                   conv):
+        status = np.zeros(G, dtype=np.int32)
+        rc = self.lib.emu_lfc_shrink(_p(X, f64p), _p(counts, i64p), C.c_int64(ld), N, G, p, _p(size, f64p), _p(offset, f64p),
+                                     C.c_double(prior_no_shrink_scale), C.c_double(prior_scale), shrink_index, _p(lfcs, f64p),
+                                     _p(inv_hessians, f64p), _p(conv, f64p), _p(status, i32p), self.force_shrink_grid)
+        assert rc == 0
+        self.last_status = status
+        return int((status != 0).sum())
 
     def size_factors(self, counts, ld, N, G, sf):
         assert self.lib.emu_size_factors(_p(counts, i64p), C.c_int64(ld), N, G, _p(sf, f64p)) == 0

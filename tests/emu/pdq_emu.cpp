@@ -16,6 +16,7 @@ extern long g_emu_alpha_evals;
 #include "../../pydeseq2_b200/csrc/pdq_gene.cuh"
 #include "../../pydeseq2_b200/csrc/pdq_host_linalg.h"
 #include "../../pydeseq2_b200/csrc/pdq_trend.cuh"
+#include "../../pydeseq2_b200/csrc/pdq_shrink.cuh"
 
 long g_emu_alpha_evals = 0;
 using namespace pdq;
@@ -121,6 +122,24 @@ int emu_alpha_mle(const int64_t* counts, int64_t ld, int N, int G, const double*
                 alpha_grid_gene<P>(kOne, k.d, prm.lo, prm.hi, counts + g, ld, mu + g, ld_mu, alpha + g, true);
         }
     });
+    return 0;
+}
+
+int emu_lfc_shrink(const double* X, const int64_t* counts, int64_t ld, int N, int G, int p, const double* size, const double* offset,
+                   double prior_no_shrink_scale, double prior_scale, int shrink_index, double* lfcs, double* inv_hessians, double* conv,
+                   int* status, int force_grid) {
+    Pack k = make_pack(X, nullptr, N, p);
+    for (int n = 0; n < N; ++n) k.buf[(size_t)(p + 1) * k.d.Npad + n] = offset[n];
+    const ShrinkParams prm{1.0 / (prior_no_shrink_scale * prior_no_shrink_scale), prior_scale * prior_scale, shrink_index};
+    EMU_DISPATCH(p, {
+        for (int g = 0; g < G; ++g)
+            shrink_gene<P>(kOne, k.d, prm, counts + g, ld, size[g], lfcs + (size_t)g * P, inv_hessians + (size_t)g * P * P, conv + g,
+                           status + g, true, force_grid != 0);
+    });
+    if (p == 2)
+        for (int g = 0; g < G; ++g)
+            if (status[g] == kShrinkNeedsGrid)
+                shrink_grid_gene(kOne, k.d, prm, counts + g, ld, size[g], lfcs + (size_t)g * 2, inv_hessians + (size_t)g * 4, true);
     return 0;
 }
 

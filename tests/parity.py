@@ -100,3 +100,28 @@ def check_tape(inf, t, name):
                 assert_close(got, want, 1e-7, f"{name}:{meth} p", atol=1e-300)
             else:
                 assert_close(got, want, 1e-6, f"{name}:{meth}[{k}]", atol=1e-10)
+
+
+SHRINK = ["shrink_two_level_n24", "shrink_factorial_n30", "shrink_factorial_n30_idx1", "shrink_continuous_n40",
+          "shrink_two_level_n200", "shrink_two_level_n200_noadapt", "shrink_large_counts_n12", "shrink_five_columns_n36",
+          "shrink_few_samples_n4", "shrinktape_single_factor", "shrinktape_single_factor_noadapt", "shrinktape_multi_factor",
+          "shrinktape_continuous", "shrinktape_large_counts"]
+# apeGLM: the backend walks the reference's optimiser path, so it lands on the reference's (loosely converged) iterate:
+# measured <= 5e-10 on every fixture; the tolerance leaves room for a different summation order on the device
+TOL_SHRINK = 1e-7
+
+
+def check_shrink(inf, g, tol=TOL_SHRINK):
+    """`lfc_shrink_nbinom_glm` against the real reference's outputs (oracle/make_golden.py `gen_shrink_*`)."""
+    k = int(g["shrink_index"])
+    lfcs, ih, conv = inf.lfc_shrink_nbinom_glm(g["X"], g["counts"], g["size"], g["offset"], float(g["prior_no_shrink_scale"]),
+                                               float(g["prior_scale"]), "L-BFGS-B", k)
+    assert lfcs.shape == g["lfcs"].shape and ih.shape == g["inv_hessians"].shape
+    np.testing.assert_array_equal(conv, g["converged"])
+    assert_close(lfcs, g["lfcs"], tol, "shrunk coefficients", atol=1e-10)
+    assert_close(ih, g["inv_hessians"], tol, "inverse Hessians", atol=1e-14)
+    if "r_log2FoldChange" in g:  # the reference's own test: within 2 % of R's apeglm (tests/test_pydeseq2.py:256-296 ...)
+        got = lfcs[:, k] / np.log(2)
+        assert np.nanmax(np.abs(g["r_log2FoldChange"] - got) / np.abs(g["r_log2FoldChange"])) < 0.02
+        se = np.sqrt(np.abs(ih[:, k, k])) / np.log(2)
+        np.testing.assert_allclose(se, g["final_lfcSE"], rtol=tol)

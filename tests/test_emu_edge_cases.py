@@ -48,3 +48,12 @@ def test_size_factors(backend):
 
 def test_cooks(backend):
     ec.check_cooks(backend[0])
+
+
+def test_shrink_grid_fallback(backend):
+    inf, ops = backend
+    ec.check_shrink_grid(inf, lambda on: setattr(ops, "force_shrink_grid", int(on)))
+
+
+def test_shrink_arguments(backend):
+    ec.check_shrink_arguments(backend[0])

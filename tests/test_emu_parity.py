@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from conftest import load_golden
-from parity import check_calls, check_tape
+from parity import SHRINK, check_calls, check_shrink, check_tape
 from pydeseq2_b200.inference import B200Inference
 from emu.emu_ops import EmuOps
 
@@ -109,3 +109,8 @@ def test_fused_mom_kernel(name):
     np.testing.assert_allclose(a, g["mom"], rtol=1e-9, atol=1e-14)
     np.testing.assert_allclose(m, g["normed"].mean(0), rtol=1e-12)
     np.testing.assert_allclose(mu, g["lin_mu"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("name", SHRINK)
+def test_emu_lfc_shrink(inf, name):
+    check_shrink(inf, load_golden(name))

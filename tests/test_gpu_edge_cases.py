@@ -64,3 +64,11 @@ def test_size_factors(inf):
 
 def test_cooks(inf):
     ec.check_cooks(inf)
+
+
+def test_shrink_grid_fallback(inf):
+    ec.check_shrink_grid(inf, _force(inf, 4))
+
+
+def test_shrink_arguments(inf):
+    ec.check_shrink_arguments(inf)

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from conftest import load_golden
-from parity import assert_close, check_calls, check_tape
+from parity import SHRINK, assert_close, check_calls, check_shrink, check_tape
 
 pytestmark = pytest.mark.gpu
 
@@ -61,3 +61,8 @@ def test_ragged_gene_counts_and_strided_input(inf):
     rb, rm, rh, rc = nbglm.OracleInference(n_cpus=1).irls(c[:N], sf[:N], X[:N], g["mom"], 0.5, 1e-8)
     assert_close(b1, rb, 1e-6, "odd-N beta", atol=1e-9)
     assert_close(h1, rh, 1e-6, "odd-N hat", atol=1e-12)
+
+
+@pytest.mark.parametrize("name", SHRINK)
+def test_gpu_lfc_shrink_vs_reference_golden(inf, name):
+    check_shrink(inf, load_golden(name))

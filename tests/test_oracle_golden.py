@@ -88,3 +88,44 @@ def test_oracle_cooks(name):
     cooks, disp = nbglm.calculate_cooks(counts, normed, X, t["final_mu_LFC"], t["final_hat"])
     np.testing.assert_allclose(cooks, t["final_cooks"][:, nz], rtol=1e-10)
     np.testing.assert_array_equal(nbglm.cooks_outlier(counts, cooks, X), t["final_cooks_outlier"][nz] == 1)
+
+
+# --------------------------------------------------------------------------- apeGLM shrinkage
+from parity import SHRINK  # noqa: E402
+
+
+@pytest.mark.parametrize("name", SHRINK)
+def test_oracle_lfc_shrink(name):
+    g = load_golden(name)
+    k = int(g["shrink_index"])
+    lfcs, ih, conv = nbglm.OracleInference(n_cpus=1).lfc_shrink_nbinom_glm(
+        g["X"], g["counts"], g["size"], g["offset"], float(g["prior_no_shrink_scale"]), float(g["prior_scale"]), "L-BFGS-B", k)
+    np.testing.assert_allclose(lfcs, g["lfcs"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(ih, g["inv_hessians"], rtol=RTOL)
+    np.testing.assert_array_equal(conv, g["converged"])
+    if not np.isnan(g["prior_var"]):  # the prior scale the reference derived from the MLE LFCs and their SEs (ds.py:551-585)
+        col = g["mle_lfc"][:, k] if g["mle_lfc"].ndim == 2 else g["mle_lfc"]
+        assert nbglm.fit_shrink_prior_var(col, g["mle_se"]) == pytest.approx(float(g["prior_var"]), rel=1e-9)
+
+
+@pytest.mark.parametrize("name", ["shrink_two_level_n24", "shrink_five_columns_n36", "shrink_large_counts_n12", "shrinktape_continuous"])
+def test_restated_lbfgsb_walks_scipys_path(name):
+    """oracle/lbfgsb_restated.py (the specification of the CUDA optimiser) against scipy's L-BFGS-B on the reference's
+    objective: same number of iterations and evaluations, same end point."""
+    from scipy.optimize import minimize
+
+    from oracle.lbfgsb_restated import minimize_lbfgsb_unbounded
+
+    g = load_golden(name)
+    X, p = g["X"], g["X"].shape[1]
+    for i in range(g["counts"].shape[1]):
+        args = (X, g["counts"][:, i], g["size"][i], g["offset"], float(g["prior_no_shrink_scale"]), float(g["prior_scale"]),
+                int(g["shrink_index"]))
+        cn = np.maximum(nbglm.nbinom_fn(np.zeros(p), *args), 1)
+        fun = lambda b: nbglm.nbinom_fn(b, *args) / cn  # noqa: E731
+        jac = lambda b: nbglm.nbinom_grad(b, *args) / cn  # noqa: E731
+        x0 = np.ones(p) * 0.1 * (-1) ** np.arange(p)
+        ref = minimize(fun, x0, jac=jac, method="L-BFGS-B", options={"ftol": 1e-8, "gtol": 1e-8})
+        x, ok, nit, nfev = minimize_lbfgsb_unbounded(fun, jac, x0)
+        assert (nit, nfev, ok) == (ref.nit, ref.nfev, ref.success)
+        np.testing.assert_allclose(x, ref.x, rtol=1e-8, atol=1e-12)
