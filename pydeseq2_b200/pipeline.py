@@ -213,6 +213,53 @@ def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5,
                      np.asarray(init_conv, dtype=float))
 
 
+# --------------------------------------------------------------------------------------- apeGLM shrinkage (ds.py:363-443)
+def fit_shrink_prior_var(lfc_coeff: np.ndarray, se: np.ndarray, min_var: float = 1e-6, max_var: float = 400.0) -> float:
+    """Prior variance of the apeGLM model from the MLE LFCs of the shrunk coefficient and their standard errors
+    (``DeseqStats._fit_prior_var``, ds.py:551-585): the zero of a weighted moment equation, bracketed on [min_var, max_var]."""
+    from scipy.optimize import root_scalar
+
+    keep = ~np.isnan(lfc_coeff)
+    S, D = lfc_coeff[keep] ** 2, se[keep] ** 2
+
+    def objective(a):
+        coeff = 1 / (2 * (a + D) ** 2)
+        return ((S - D) * coeff).sum() / coeff.sum() - a
+
+    if objective(min_var) < 0:
+        return min_var
+    return float(root_scalar(objective, bracket=(min_var, max_var)).root)
+
+
+@dataclass
+class ShrinkResult:
+    lfc: np.ndarray          # (G, p) natural log scale; only column `coeff_idx` differs in meaning from the MLE table
+    se: np.ndarray           # (G,) sqrt(|inv_hessian[k, k]|), all-zero genes NaN
+    converged: np.ndarray    # (G,) 0/1, NaN for all-zero genes
+    prior_scale: float
+    prior_var: float
+
+
+def lfc_shrink_host(fit: FitResult, counts, X, inference, coeff_idx: int, adapt: bool = True, se=None) -> ShrinkResult:
+    """``DeseqStats.lfc_shrink`` (ds.py:363-443) on top of a finished fit: prior scale from the MLE LFCs and the Wald SEs of
+    the shrunk coefficient (``se`` defaults to ``fit.se``, which is that coefficient's SE when the Wald contrast selected
+    it), one ``lfc_shrink_nbinom_glm`` plugin call on the non-zero genes, results written over the MLE column."""
+    counts = np.asarray(counts)
+    nz = fit.non_zero
+    prior_var, prior_scale = float("nan"), 1.0
+    if adapt:
+        prior_var = fit_shrink_prior_var(fit.lfc[:, coeff_idx], fit.se if se is None else np.asarray(se, dtype=float))
+        prior_scale = float(np.minimum(np.sqrt(prior_var), 1))
+    cz = counts if nz.all() else np.ascontiguousarray(counts[:, nz])
+    lfcs, ih, conv = inference.lfc_shrink_nbinom_glm(X, cz, 1.0 / fit.dispersions[nz], np.log(fit.size_factors), 15, prior_scale,
+                                                     "L-BFGS-B", coeff_idx)
+    G_all = counts.shape[1]
+    lfc = fit.lfc.copy()
+    lfc[nz, coeff_idx] = np.asarray(lfcs)[:, coeff_idx]
+    se_out = _expand(np.sqrt(np.abs(np.asarray(ih)[:, coeff_idx, coeff_idx])), nz, G_all)
+    return ShrinkResult(lfc, se_out, _expand(np.asarray(conv, dtype=float), nz, G_all), prior_scale, prior_var)
+
+
 # --------------------------------------------------------------------------------------- resident driver
 class ResidentFit:
     """Same sequence with counts and all (N, G) intermediates resident in HBM (C ABI ``*_dev`` entry points).
@@ -467,6 +514,39 @@ class ResidentFit:
                 "se": H["se"], "normed_means": means, "fitted": fitted, "outlier": H["outlier"],
                 **({"robust_dispersions": H["robust_disp"], "cooks_outlier": H["cooks_outlier"] == 1.0,
                     "cooks_replaced": H["cooks_replaced"] == 1.0} if self.with_cooks else {})}
+
+    # -- apeGLM shrinkage on the resident counts ----------------------------------------------------------
+    def lfc_shrink(self, result, coeff_idx: int, adapt: bool = True, se=None, prior_scale=None):
+        """``DeseqStats.lfc_shrink`` (ds.py:363-443) after :meth:`run`: counts, design pack and dispersions are already in HBM,
+        so the call moves 8*G bytes up (size = 1/dispersion) and 8*G*(p*p+p+1) down.  ``result`` is what :meth:`run`
+        returned; the prior scale comes from its LFC column ``coeff_idx`` and ``se`` (default: the Wald SEs of that run, i.e.
+        the run's contrast must have selected the same coefficient).  With gene shards pass ``prior_scale`` computed from the
+        gathered tables (the prior is global over genes).  Returns a :class:`ShrinkResult` for this shard's genes."""
+        L, ctx, h, G, p = self.lib, self.ctx, self.ctx.h, self.G, self.p
+        c_d = self._lib_mod.c_dptr
+        prior_var = float("nan")
+        if prior_scale is None:
+            prior_scale = 1.0
+            if adapt:
+                if self.comm is not None:
+                    raise ValueError("gene shards: pass prior_scale fitted on the gathered LFC / SE tables")
+                prior_var = fit_shrink_prior_var(np.asarray(result["lfc"])[:, coeff_idx],
+                                                 np.asarray(result["se"] if se is None else se, dtype=float))
+                prior_scale = float(np.minimum(np.sqrt(prior_var), 1))
+        host = ctx.pinned_empty((G * (1 + p + p * p + 1),))
+        size, lfcs = host[:G], host[G:G + G * p].reshape(G, p)
+        ih, conv = host[G + G * p:G + G * p + G * p * p].reshape(G, p, p), host[G + G * p + G * p * p:]
+        size[:] = 1.0 / np.asarray(result["dispersions"])
+        d_size, d_out = self._dev("shrink_size", G * 8), self._dev("shrink_out", G * (p + p * p + 1) * 8)
+        d_status = self._dev("shrink_status", G * 4)
+        ctx.h2d(d_size, size)
+        ctx.check(L.pdq_lfc_shrink_dev(h, self.design, c_d(self.d_counts), G, G, c_d(d_size), 15.0, float(prior_scale), int(coeff_idx),
+                                       c_d(d_out), c_d(d_out + G * p * 8), c_d(d_out + G * (p + p * p) * 8), c_d(d_status)))
+        ctx.d2h(host[G:], d_out)
+        ctx.sync()
+        lfc = np.array(result["lfc"], copy=True)
+        lfc[:, coeff_idx] = lfcs[:, coeff_idx]
+        return ShrinkResult(lfc, np.sqrt(np.abs(ih[:, coeff_idx, coeff_idx])), conv.copy(), float(prior_scale), prior_var)
 
     def _tail(self, d_fitted, d_t16, d_prior_var, prior_var, contrast, ridge, lfc_null, alt_hypothesis, begin, check):
         """MAP dispersions -> final dispersions -> LFC fit -> Wald, all enqueued without host synchronisation."""

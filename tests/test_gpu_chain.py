@@ -71,6 +71,21 @@ def test_chained_pipeline_matches_oracle(inf, N, G, kind, seed, RTOL):
             lp_g, lp_r = -np.log10(got.pvalue[ok]), -np.log10(ref.pvalue[ok])
         fin = np.isfinite(lp_r)
         np.testing.assert_allclose(lp_g[fin], lp_r[fin], rtol=RTOL, atol=1e-6)
+    if kind in ("two_level", "factorial"):
+        # apeGLM shrinkage chained on top (ds.py:363-443).  Both sides walk the same L-BFGS-B path from dispersions that
+        # differ by ~1e-5, and the path's end point is only loosely converged (ftol 1e-8 on the scaled objective): a gene
+        # whose stopping test flips ends an iteration apart, i.e. up to ~1e-2 away -- hence a mismatch budget, as above.
+        from pydeseq2_b200.pipeline import lfc_shrink_host
+
+        k = X.shape[1] - 1
+        cpu_ctx = nbglm.OracleInference(n_cpus=os.cpu_count())
+        sh_ref, sh_got = lfc_shrink_host(ref, counts, X, cpu_ctx, k), lfc_shrink_host(got, counts, X, inf, k)
+        assert sh_got.prior_scale == pytest.approx(sh_ref.prior_scale, rel=RTOL)
+        frac, _ = _frac_bad(sh_got.lfc[:, k], sh_ref.lfc[:, k], RTOL, 1e-8, ok)
+        assert frac <= 0.01, f"shrunk LFC: {frac:.2%} off by more than {RTOL}"
+        frac, _ = _frac_bad(sh_got.se, sh_ref.se, RTOL, 0.0, ok)
+        assert frac <= 0.01, f"shrunk SE: {frac:.2%} off by more than {RTOL}"
+        np.testing.assert_array_equal(sh_got.converged[ok], sh_ref.converged[ok])
 
 
 @pytest.mark.parametrize("N,G,kind", [(200, 4000, "two_level"), (60, 1000, "factorial")])
@@ -92,6 +107,17 @@ def test_resident_driver_equals_host_buffer_driver(inf, N, G, kind):
     np.testing.assert_allclose(r["lfc"], host.lfc, rtol=1e-6, atol=1e-10)
     np.testing.assert_allclose(r["stat"], host.stat, rtol=1e-6, atol=1e-10)
     np.testing.assert_allclose(r["pvalue"], host.pvalue, rtol=1e-5, atol=1e-300)
+    # apeGLM shrinkage of the last coefficient: resident counts / dispersions vs the plugin call on host buffers
+    from pydeseq2_b200.pipeline import lfc_shrink_host
+
+    k = X.shape[1] - 1
+    sh_dev, sh_host = rf.lfc_shrink(r, k), lfc_shrink_host(host, counts, X, inf, k)
+    assert sh_dev.prior_scale == pytest.approx(sh_host.prior_scale, rel=1e-6)
+    # same optimiser path from inputs that differ by ~1e-7: a few genes may stop one iteration apart (path-dependent result)
+    close = np.isclose(sh_dev.lfc[:, k], sh_host.lfc[:, k], rtol=1e-5, atol=1e-9)
+    assert close.mean() > 0.995, (1 - close.mean(), np.abs(sh_dev.lfc[:, k] - sh_host.lfc[:, k]).max())
+    assert np.isclose(sh_dev.se, sh_host.se, rtol=1e-5).mean() > 0.995
+    np.testing.assert_array_equal(sh_dev.converged, sh_host.converged)
     rf.with_cooks = True  # Cook's distances from the resident mu / hat, per-gene results only
     rc = rf.run()
     ck, rd, outl, repl = inf.calculate_cooks(counts, sf, X, *inf.irls(counts, sf, X, rc["dispersions"], 0.5, 1e-8)[1:3])
