@@ -257,10 +257,14 @@ def main():
     rf.run(profile=True)
     stages["cooks_untimed"] = rf.stage_ms.get("cooks")
     rf.with_cooks = False
+    from pydeseq2_b200.pipeline import fit_shrink_prior_var
+
     res_sh = rf.run()
-    rf.lfc_shrink(res_sh, p - 1)  # first call allocates its buffers
+    k_sh = X.shape[1] - 1
+    ps_sh = float(min(np.sqrt(fit_shrink_prior_var(np.asarray(res_sh["lfc"])[:, k_sh], np.asarray(res_sh["se"]))), 1.0))
+    rf.lfc_shrink(res_sh, k_sh, prior_scale=ps_sh)  # first call allocates its buffers
     t0 = time.perf_counter()
-    rf.lfc_shrink(res_sh, p - 1)  # apeGLM shrinkage: reported for information, NOT part of the timed step
+    rf.lfc_shrink(res_sh, k_sh, prior_scale=ps_sh)  # apeGLM shrinkage: for information, NOT in the timed step
     stages["lfc_shrink_untimed"] = (time.perf_counter() - t0) * 1e3
     rf.device_size_factors()  # first call allocates its scratch
     ctx.sync()
