@@ -379,9 +379,60 @@ def main_shrink():
     gen_shrink_tape("large_counts", lc, lm, d6, [0, 1], "condition[T.B]", f"{REF}/tests/data/large_counts")
 
 
+def gen_e2e(name, N, G, design_kind, seed, n_outliers, contrast_index=None, **stats_kwargs):
+    """End-to-end fixture on seeded counts with injected outliers: only the final tables of the real `deseq2()` + `summary()`
+    (refit of replaceable outliers, Cook's filtering of the others, independent filtering) -- the orchestration steps around
+    the plugin calls."""
+    from pydeseq2.dds import DeseqDataSet
+    from pydeseq2.ds import DeseqStats
+
+    counts, X, _ = synth(N, G, design_kind, seed)
+    rng = np.random.default_rng(seed + 100)
+    for g in rng.choice(G, n_outliers, replace=False):   # one wild count per chosen gene
+        counts[rng.integers(N), g] = int(counts[:, g].max() * 40 + 500)
+    p = X.shape[1]
+    contrast = np.zeros(p)
+    contrast[p - 1 if contrast_index is None else contrast_index] = 1.0
+    idx = [f"s{i}" for i in range(N)]
+    counts_df = pd.DataFrame(counts, index=idx, columns=[f"g{i}" for i in range(G)])
+    design_df = pd.DataFrame(X, index=idx, columns=[f"x{j}" for j in range(p)])
+    meta = pd.DataFrame({"dummy": np.arange(N)}, index=idx)
+    inf = ref_inference()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dds = DeseqDataSet(counts=counts_df, metadata=meta, design=design_df, inference=inf, quiet=True)
+        dds.deseq2()
+        ds = DeseqStats(dds, contrast=contrast, inference=inf, quiet=True, **stats_kwargs)
+        ds.summary()
+    res = ds.results_df
+    out = dict(counts=counts, design=X, contrast=contrast,
+               final_baseMean=res["baseMean"].values, final_log2FoldChange=res["log2FoldChange"].values, final_lfcSE=res["lfcSE"].values,
+               final_stat=res["stat"].values, final_pvalue=res["pvalue"].values, final_padj=res["padj"].values,
+               final_LFC=dds.varm["LFC"].values, final_dispersions=dds.var["dispersions"].values,
+               final_genewise=dds.var["genewise_dispersions"].values, final_fitted=dds.var["fitted_dispersions"].values,
+               final_size_factors=dds.obs["size_factors"].values, final_replaced=np.asarray(dds.var["replaced"], dtype=float),
+               final_refitted=np.asarray(dds.var["refitted"], dtype=float), final_cooks_outlier=np.asarray(dds.cooks_outlier(), dtype=float),
+               independent_filter=np.float64(stats_kwargs.get("independent_filter", True)),
+               cooks_filter=np.float64(stats_kwargs.get("cooks_filter", True)), alpha=np.float64(stats_kwargs.get("alpha", 0.05)))
+    np.savez_compressed(os.path.join(OUT, f"e2e_{name}.npz"), **out)
+    print(f"e2e_{name}: N={N} G={G} p={p} replaced={int(out['final_replaced'].sum())} refitted={int(out['final_refitted'].sum())} "
+          f"cooks_outlier={int(out['final_cooks_outlier'].sum())} padj<alpha={int((res['padj'] < 0.05).sum())} "
+          f"padj NaN={int(res['padj'].isna().sum())} p NaN={int(res['pvalue'].isna().sum())}")
+
+
+def main_e2e():
+    gen_e2e("two_level_n24", 24, 400, "two_level", 11, 12)               # cells of 12 >= 7: outliers are replaced and refitted
+    gen_e2e("factorial_n20", 20, 400, "factorial", 12, 12)               # cells of 5 < 7: outliers lose their p-value instead
+    gen_e2e("two_level_n16_bh", 16, 300, "two_level", 13, 8, independent_filter=False)
+    gen_e2e("continuous_n30", 30, 300, "continuous", 14, 8)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "shrink":  # apeGLM fixtures only (reads the existing calls_* fixtures)
+    if len(sys.argv) > 1 and sys.argv[1] == "e2e":  # end-to-end fixtures only
+        main_e2e()
+    elif len(sys.argv) > 1 and sys.argv[1] == "shrink":  # apeGLM fixtures only (reads the existing calls_* fixtures)
         main_shrink()
     else:
         main()
         main_shrink()
+        main_e2e()

@@ -117,6 +117,11 @@ class FitResult:
     se: np.ndarray
     timings: dict = field(default_factory=dict)
     irls_init_converged: np.ndarray | None = None  # flag of the initial mu_hat IRLS (all ones on the lin_reg_mu branch)
+    # what the orchestrator keeps for the steps after the LFC fit (non-zero genes only): obsm["_mu_LFC"], obsm["_hat_diagonals"]
+    # (dds.py:980-981) and var["_normed_means"] (dds.py:708)
+    mu_lfc: np.ndarray | None = None
+    hat: np.ndarray | None = None
+    normed_means: np.ndarray | None = None
 
 
 def _expand(v, nz, G_all):
@@ -210,7 +215,7 @@ def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5,
                        LN2 * lfc_null, alt_hypothesis)
     return FitResult(sf, nz, mom, gw, np.asarray(gw_conv), trend, prior_var, sq, mp, np.asarray(mp_conv), disp_all,
                      lfc_all, np.asarray(lfc_conv), np.asarray(pv), np.asarray(st), np.asarray(se), T,
-                     np.asarray(init_conv, dtype=float))
+                     np.asarray(init_conv, dtype=float), mu_lfc, hat, normed_means)
 
 
 # --------------------------------------------------------------------------------------- apeGLM shrinkage (ds.py:363-443)

@@ -125,3 +125,55 @@ def check_shrink(inf, g, tol=TOL_SHRINK):
         assert np.nanmax(np.abs(g["r_log2FoldChange"] - got) / np.abs(g["r_log2FoldChange"])) < 0.02
         se = np.sqrt(np.abs(ih[:, k, k])) / np.log(2)
         np.testing.assert_allclose(se, g["final_lfcSE"], rtol=tol)
+
+
+E2E = ["e2e_two_level_n24", "e2e_factorial_n20", "e2e_two_level_n16_bh", "e2e_continuous_n30"]
+TAPES_E2E = ["tape_single_factor", "tape_multi_factor", "tape_continuous", "tape_wide", "tape_multi_factor_outliers"]
+
+
+def assert_mostly_close(got, want, rtol, what, atol=0.0, max_frac=0.0, slack=100.0):
+    """All entries within `rtol`, except at most `max_frac` of them, which must still be within `slack * rtol`.
+
+    The budget exists for the path-dependent fits: IRLS stops on a relative deviance change of 1e-8 and, on a flat likelihood
+    (an outlier gene with dispersion ~3), two runs whose dispersions differ by 1e-6 can stop one iteration apart, i.e. ~1e-3
+    apart in beta -- the reference would do the same to itself."""
+    got, want = np.asarray(got, dtype=float), np.asarray(want, dtype=float)
+    bad = ~np.isclose(got, want, rtol=rtol, atol=atol, equal_nan=True)
+    if bad.mean() > max_frac:
+        assert_close(got, want, rtol, what, atol=atol)
+    assert_close(got, want, slack * rtol, what + " (outside the mismatch budget)", atol=slack * atol)
+
+
+def check_e2e(inf, g, rtol, name="", max_frac=0.0):
+    """`workflow.deseq2_results` (deseq2() + summary(): refit of Cook's outliers, Cook's / independent filtering, BH) against the
+    final tables of the real orchestrator (oracle/make_golden.py `gen_e2e`, `gen_tape`)."""
+    from pydeseq2_b200.workflow import deseq2_results
+
+    kw = {}
+    if "independent_filter" in g:
+        kw = dict(independent_filter=bool(g["independent_filter"]), cooks_filter=bool(g["cooks_filter"]), alpha=float(g["alpha"]))
+    r = deseq2_results(g["counts"], g["design"], inf, g["contrast"], **kw)
+    # decisions first: they are discrete, so they must agree exactly
+    np.testing.assert_array_equal(r.replaced, g["final_replaced"] == 1, err_msg="replaced genes")
+    if "final_refitted" in g:
+        np.testing.assert_array_equal(r.refitted, g["final_refitted"] == 1, err_msg="refitted genes")
+    np.testing.assert_array_equal(r.cooks_outlier, g["final_cooks_outlier"] == 1, err_msg="Cook's outlier genes")
+    pv_ref = g["final_pvalue"] if "final_pvalue" in g else g["final_pvalues"]
+    np.testing.assert_array_equal(np.isnan(r.pvalue), np.isnan(pv_ref), err_msg="masked p-values")
+    np.testing.assert_array_equal(np.isnan(r.padj), np.isnan(g["final_padj"]), err_msg="independent-filtering threshold")
+    np.testing.assert_allclose(r.size_factors, g["final_size_factors"], rtol=1e-12)
+    assert_mostly_close(r.lfc, g["final_LFC"], rtol, "LFC", 1e-8, max_frac)
+    assert_close(r.dispersions, g["final_dispersions"], rtol, "dispersions")
+    assert_close(r.genewise_dispersions, g["final_genewise"], rtol, "genewise dispersions")
+    if "final_stat" in g:
+        assert_mostly_close(r.stat, g["final_stat"], rtol, "Wald statistic", 1e-8, max_frac)
+    big = pv_ref >= 1e-20
+    assert_mostly_close(r.pvalue[big], pv_ref[big], 10 * rtol, "p-values", 0.0, max_frac)
+    ok = ~np.isnan(g["final_padj"])
+    assert_mostly_close(r.padj[ok & big], g["final_padj"][ok & big], 10 * rtol, "adjusted p-values", 0.0, max_frac)
+    if "final_baseMean" in g:
+        assert_close(r.base_mean, g["final_baseMean"], 1e-12, "baseMean")
+        assert_mostly_close(r.log2_fold_change, g["final_log2FoldChange"], rtol, "log2FoldChange", 1e-8, max_frac)
+        assert_mostly_close(r.lfc_se, g["final_lfcSE"], rtol, "lfcSE", 0.0, max_frac)
+        assert_close(r.fitted_dispersions, g["final_fitted"], rtol, "fitted dispersions")
+    return r

@@ -190,3 +190,14 @@ def test_full_size_properties(inf):
         h = 1e-4
         curv = (dloss(np.log(a) + h) - dloss(np.log(a) - h)) / (2 * h)
         assert abs(dloss(np.log(a)) / curv) < 1e-5, (g, a)  # Newton distance to the stationary point, in log alpha
+
+
+from conftest import load_golden  # noqa: E402
+from parity import E2E, TAPES_E2E, check_e2e  # noqa: E402
+
+
+@pytest.mark.parametrize("name", TAPES_E2E + E2E)
+def test_end_to_end_tables_match_the_real_orchestrator(inf, name):
+    """deseq2() + summary() through `workflow.deseq2_results` on the GPU backend -- outlier refit, Cook's filtering, independent
+    filtering / BH included -- against the final tables the real reference produced (tests/golden/tape_*, e2e_*)."""
+    check_e2e(inf, load_golden(name), RTOL, name, max_frac=0.005)
