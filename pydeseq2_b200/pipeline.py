@@ -165,11 +165,14 @@ def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5,
     else:
         sf = np.asarray(size_factors, dtype=float)
         normed = normed_counts if normed_counts is not None else timed("normed_counts", lambda: counts / sf[:, None])
-    nz = counts.max(axis=0) != 0                         # dds.py:729-731: ~(X == 0).all(0) for non-negative counts, one pass
+    # dds.py:729-731 `~(X == 0).all(0)`.  Counts are non-negative, so a gene is all-zero exactly when the mean of its normalised
+    # counts is 0: with var["_normed_means"] at hand (dds.py:708) the mask costs O(G) instead of a pass over the (N, G) matrix.
+    normed_means = normed.mean(0) if normed_means is None else np.asarray(normed_means)
+    nz = normed_means != 0
     all_nz = bool(nz.all())
     c = counts if all_nz else counts[:, nz]              # no copy when the caller already dropped all-zero genes
     nn = normed if all_nz else normed[:, nz]
-    normed_means = (normed.mean(0) if normed_means is None else np.asarray(normed_means))[nz]   # dds.py:708
+    normed_means = normed_means[nz]
 
     rde = timed("fit_rough_dispersions", inference.fit_rough_dispersions, nn, X)       # dds.py:1150-1157
     mde = timed("fit_moments_dispersions", inference.fit_moments_dispersions, nn, sf)
