@@ -113,9 +113,13 @@ static int pick_lgT(const pdq_ctx* c, int G, int N) {
     if (c->lanes_override) {
         T = c->lanes_override;
     } else {
-        // fill ~1024 resident threads per SM: T = smallest power of two with G*T >= SMs*1024, capped by 32
+        // fill ~1024 resident threads per SM: T = smallest power of two with G*T >= SMs*1024, capped by 32 -- but never
+        // fewer than 8 lanes: a warp then owns 4 adjacent genes = one full 32-byte sector per sample row, and its tile
+        // (4 genes x N samples x 16 B for counts + means) stays small enough for the resident warps of an SM to keep
+        // their tiles in L2 across evaluations.  Measured (scripts/lanes_sweep.sh, ms/step, T = 2|4|8|16|32):
+        // 20 000 x 200: -|1.40|1.25|1.35|- ; 60 000 x 500: -|9.05|8.51|9.23|11.6 ; 125 000 x 1000: 25.1|-|21.5|24.9|35.4
         const double want = (double)c->prop.multiProcessorCount * 1024.0 / (double)(G > 0 ? G : 1);
-        T = 1;
+        T = 8;
         while (T < 32 && (double)T < want) T <<= 1;
     }
     while (T > 1 && T > N) T >>= 1;  // never more lanes than samples
@@ -356,6 +360,8 @@ static int design_create(pdq_ctx* c, const double* X, const double* sf, bool off
                     dd.smem_bytes, kMaxDynSmem);
     }
     design_linear_algebra(X, N, p, dd.pinv, &dd.full_rank);
+    dd.few_rows = design_distinct_rows(X, N, p, 16) <= 16;
+    if (const char* e = getenv("PDQ_IRLS_MEMO")) dd.few_rows = dd.few_rows && atoi(e) != 0;  // tuning hook (A/B runs)
     {
         const std::vector<int> plan = design_cell_plan(X, N, p);
         dd.n_cells = plan[0];

@@ -14,6 +14,10 @@
 #include "pdq_fast.cuh"
 #include "pdq_math.cuh"
 
+#ifndef PDQ_PREFETCH
+#define PDQ_PREFETCH 1
+#endif
+
 namespace pdq {
 
 struct Group {
@@ -162,15 +166,20 @@ struct IrlsParams {
     double min_mu, beta_tol, min_beta, max_beta;
     int maxiter;
     int full_rank;
+    int few_rows;  // the design has few distinct rows (categorical factors): reuse exp(x'beta) while the row repeats
 };
 
 // one fused sweep over the gene's samples at coefficient vector `beta`:
 //   A = X^T W X, b = X^T W z  (utils.py:368-371, W and z from the CLAMPED mu)
 //   S = sum (y + r) log(r + mu) - y log(mu)  -- the mu-dependent part of nb_nll (utils.py:220-234)
 // contribution of one sample to the sweep.  NB = branch-free math cores; arguments outside their domain raise `odd`
-template <int P, bool NB>
+// MEMO: a lane walks samples si, si+T, ...; with a categorical design consecutive ones usually share their design row, so
+// eta = x'beta repeats bit for bit and exp(eta) -- a third of the body's instructions -- is carried over instead of recomputed
+// (same value, results unchanged).  All lanes of a warp look at the same rows, so the skip is close to warp-uniform.
+template <int P, bool NB, bool MEMO>
 PDQ_HD void irls_sample(const double* xp, int Npad, double yv, const double (&beta)[P], double alpha, double r,
-                        double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P], double& S, bool& odd) {
+                        double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P], double& S, bool& odd, double& eta_prev,
+                        double& exp_prev) {
     double x[P];
 #pragma unroll
     for (int j = 0; j < P; ++j) x[j] = xp[j * Npad];
@@ -179,7 +188,17 @@ PDQ_HD void irls_sample(const double* xp, int Npad, double yv, const double (&be
 #pragma unroll
     for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
     if (NB) odd = odd || !(fabs(eta) < 300.0);
-    const double mu_raw = sfn * (NB ? fast_exp_nb(eta) : fast_exp(eta));
+    double ex;
+    if (MEMO) {
+        if (eta != eta_prev) {
+            exp_prev = NB ? fast_exp_nb(eta) : fast_exp(eta);
+            eta_prev = eta;
+        }
+        ex = exp_prev;
+    } else {
+        ex = NB ? fast_exp_nb(eta) : fast_exp(eta);
+    }
+    const double mu_raw = sfn * ex;
     const bool cl = mu_raw < min_mu;
     const double mu = cl ? min_mu : mu_raw;                            // np.maximum(sf*exp(X b), min_mu)
     const double lmu_sf = cl ? (log_min_mu - lsfn) : eta;              // log(mu / sf)
@@ -195,7 +214,7 @@ PDQ_HD void irls_sample(const double* xp, int Npad, double yv, const double (&be
     S += fma(yv + r, NB ? fast_log_nb(r + mu) : fast_log(r + mu), -yv * lmu);
 }
 
-template <int P, bool NB>
+template <int P, bool NB, bool MEMO>
 PDQ_HD bool irls_sweep_t(const Group& grp, const DesignS& d, const int64_t* y, int64_t ld, const double (&beta)[P],
                          double alpha, double r, double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P], double& S) {
     sym_zero<P>(A);
@@ -208,25 +227,46 @@ PDQ_HD bool irls_sweep_t(const Group& grp, const DesignS& d, const int64_t* y, i
     const int64_t* yp = y + (int64_t)grp.si * ld;
     const double* xp = d.X + grp.si;
     int n = grp.si;
-    // two samples per trip, straight-line: their exp / log / reciprocal chains interleave on the FP64 pipe
+    // NaN never compares equal: the first sample always computes its exponential
+    double eta_prev = __builtin_nan(""), exp_prev = 0.0;
+    // two samples per trip, straight-line: their exp / log / reciprocal chains interleave on the FP64 pipe.  The counts of the
+    // NEXT trip are requested before this trip's arithmetic starts (register double buffer): the L1/L2 latency of the strided
+    // column walk hides behind ~350 instructions instead of stalling the first use (long-scoreboard stalls were 22 %).
+#if PDQ_PREFETCH
+    int64_t c0 = (n + T < d.N) ? yp[0] : 0, c1 = (n + T < d.N) ? yp[ystep] : 0;
+    for (; n + T < d.N; n += 2 * T, yp += 2 * ystep, xp += 2 * T) {
+        const double y0 = (double)c0, y1 = (double)c1;
+        if (n + 3 * T < d.N) {
+            c0 = yp[2 * ystep];
+            c1 = yp[3 * ystep];
+        }
+        irls_sample<P, NB, MEMO>(xp, d.Npad, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp + T, d.Npad, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+    }
+#else
     for (; n + T < d.N; n += 2 * T, yp += 2 * ystep, xp += 2 * T) {
         const double y0 = (double)yp[0], y1 = (double)yp[ystep];
-        irls_sample<P, NB>(xp, d.Npad, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd);
-        irls_sample<P, NB>(xp + T, d.Npad, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd);
+        irls_sample<P, NB, MEMO>(xp, d.Npad, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp + T, d.Npad, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
     }
-    if (n < d.N) irls_sample<P, NB>(xp, d.Npad, (double)yp[0], beta, alpha, r, min_mu, log_min_mu, A, b, S, odd);
+#endif
+    if (n < d.N)
+        irls_sample<P, NB, MEMO>(xp, d.Npad, (double)yp[0], beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
     return odd;
 }
 
 template <int P>
 PDQ_HD void irls_sweep(const Group& grp, const DesignS& d, const int64_t* y, int64_t ld, const double (&beta)[P],
                        double alpha, double r, double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P],
-                       double& S) {
+                       double& S, bool few_rows) {
     // the branch-free cores need r = 1/alpha positive finite and a positive clamp
     bool odd = !(alpha > 0.0 && r > 0.0 && r < 1e300 && min_mu > 0.0);
-    if (!odd) odd = irls_sweep_t<P, true>(grp, d, y, ld, beta, alpha, r, min_mu, log_min_mu, A, b, S);
+    if (!odd) {
+        odd = few_rows ? irls_sweep_t<P, true, true>(grp, d, y, ld, beta, alpha, r, min_mu, log_min_mu, A, b, S)
+                       : irls_sweep_t<P, true, false>(grp, d, y, ld, beta, alpha, r, min_mu, log_min_mu, A, b, S);
+    }
     if (grp.any(odd))  // rare (diverging beta, NaN dispersion): guarded libdevice path, IEEE semantics of the reference
-        irls_sweep_t<P, false>(grp, d, y, ld, beta, alpha, r, min_mu, log_min_mu, A, b, S);
+        irls_sweep_t<P, false, false>(grp, d, y, ld, beta, alpha, r, min_mu, log_min_mu, A, b, S);
     group_sum_sym<P>(grp, A);
     group_sum_vec<P>(grp, b);
     S = grp.sum(S);
@@ -306,7 +346,7 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
     // ---- IRLS loop (utils.py:359-421) ---------------------------------------------------------
     Sym<P> A;
     double b[P], S;
-    irls_sweep<P>(grp, d, y, ld, beta, alpha, r, prm.min_mu, log_min_mu, A, b, S);
+    irls_sweep<P>(grp, d, y, ld, beta, alpha, r, prm.min_mu, log_min_mu, A, b, S, prm.few_rows != 0);
     double dev = 1000.0, ratio = 1.0;
     int it = 0, status = kIrlsOk;
     bool active = true;
@@ -335,7 +375,7 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
             }
         }
         // frozen groups recompute the same sums (keeps the warp's shuffles uniform)
-        irls_sweep<P>(grp, d, y, ld, beta, alpha, r, prm.min_mu, log_min_mu, A, b, S);
+        irls_sweep<P>(grp, d, y, ld, beta, alpha, r, prm.min_mu, log_min_mu, A, b, S, prm.few_rows != 0);
         if (active) {
             const double old = dev;
             dev = -2.0 * (C + S);
@@ -670,6 +710,21 @@ PDQ_HD bool alpha_sweep_t(const Group& grp, const DesignS& d, bool cr_reg, const
     // the trip count is made uniform across the warp (lanes past N contribute a masked dummy) because alpha_pair votes
     const int trips = (d.N + 2 * T - 1) / (2 * T);
     int n = grp.si;
+#if PDQ_PREFETCH
+    // register double buffer: the next trip's counts and means are requested before this trip's arithmetic (see irls_sweep_t)
+    bool v0 = n < d.N, v1 = n + T < d.N;
+    long long yi0 = v0 ? yp[0] : 0, yi1 = v1 ? yp[ystep] : 0;
+    double m0 = v0 ? mp[0] : 1.0, m1 = v1 ? mp[mstep] : 1.0;
+    for (int it = 0; it < trips; ++it, n += 2 * T, yp += 2 * ystep, mp += 2 * mstep, xp += 2 * T) {
+        const bool w0 = n + 2 * T < d.N, w1 = n + 3 * T < d.N;
+        const long long ny0 = w0 ? yp[2 * ystep] : 0, ny1 = w1 ? yp[3 * ystep] : 0;
+        const double nm0 = w0 ? mp[2 * mstep] : 1.0, nm1 = w1 ? mp[3 * mstep] : 1.0;
+        // one call site: every lane of the warp reaches the vote inside alpha_pair together
+        alpha_pair<P, NB>(grp, v0 ? xp : d.X, v1 ? xp + T : d.X, d.Npad, yi0, yi1, m0, m1, v0, v1, r, cr_reg, psi_tab, Sg, A,
+                          B, odd);
+        v0 = w0; v1 = w1; yi0 = ny0; yi1 = ny1; m0 = nm0; m1 = nm1;
+    }
+#else
     for (int it = 0; it < trips; ++it, n += 2 * T, yp += 2 * ystep, mp += 2 * mstep, xp += 2 * T) {
         const bool v0 = n < d.N, v1 = n + T < d.N;
         const long long yi0 = v0 ? yp[0] : 0, yi1 = v1 ? yp[ystep] : 0;
@@ -678,6 +733,7 @@ PDQ_HD bool alpha_sweep_t(const Group& grp, const DesignS& d, bool cr_reg, const
         alpha_pair<P, NB>(grp, v0 ? xp : d.X, v1 ? xp + T : d.X, d.Npad, yi0, yi1, m0, m1, v0, v1, r, cr_reg, psi_tab, Sg, A,
                           B, odd);
     }
+#endif
     return odd;
 }
 

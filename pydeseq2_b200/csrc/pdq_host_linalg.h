@@ -3,6 +3,7 @@
 #pragma once
 
 #include <math.h>
+#include <string.h>
 
 #include <vector>
 
@@ -15,6 +16,21 @@ namespace pdq {
 // One-sided Jacobi SVD of X (N x p, p <= 8): the right singular vectors V and singular values give
 //   rank(X)   with numpy.linalg.matrix_rank's tolerance  s_max * max(N, p) * eps     (utils.py:349)
 //   (X^T X)^+ = V diag(1/s_i^2 for s_i > tol) V^T        (least-squares / minimum-norm projector)
+// number of distinct rows of X (capped at `cap + 1`): categorical designs have a handful, continuous covariates ~N
+inline int design_distinct_rows(const double* X, int N, int p, int cap) {
+    std::vector<int> reps;
+    for (int n = 0; n < N; ++n) {
+        bool seen = false;
+        for (int r : reps)
+            if (memcmp(X + (size_t)r * p, X + (size_t)n * p, (size_t)p * sizeof(double)) == 0) { seen = true; break; }
+        if (!seen) {
+            reps.push_back(n);
+            if ((int)reps.size() > cap) break;
+        }
+    }
+    return (int)reps.size();
+}
+
 inline void design_linear_algebra(const double* X, int N, int p, double* pinv, int* full_rank) {
     std::vector<double> U((size_t)N * p);
     for (size_t i = 0; i < (size_t)N * p; ++i) U[i] = X[i];

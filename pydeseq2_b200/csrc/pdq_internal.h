@@ -15,6 +15,7 @@ struct DesignDev {
     double* pack;       // device
     int N, Npad, p;
     int full_rank;      // np.linalg.matrix_rank(X) == p  (utils.py:349)
+    int few_rows;       // X has at most 16 distinct rows (categorical design): k_irls reuses exp(x'beta) across equal rows
     double pinv[PDQ_MAX_P * PDQ_MAX_P];  // (X^T X)^+ row-major p x p (host copy, passed by value to kernels)
     double s_mean_inv;  // mean(1 / size_factors)  (utils.py:880)
     size_t smem_bytes;  // dynamic shared memory the kernels need for this pack

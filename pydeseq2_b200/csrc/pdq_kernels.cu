@@ -763,7 +763,7 @@ int launch_irls(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, i
     if (n_fallback && cudaMemsetAsync(n_fallback, 0, sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;
     PDQ_DISPATCH_P(d.p, {
         IrlsArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d),
-                      IrlsParams{h.min_mu, h.beta_tol, h.min_beta, h.max_beta, h.maxiter, d.full_rank},
+                      IrlsParams{h.min_mu, h.beta_tol, h.min_beta, h.max_beta, h.maxiter, d.full_rank, d.few_rows},
                       counts, ld, G, c.lgT, disp, beta, mu, hat, conv, ld_out, status, n_fallback, c.tickets,
                       (c.debug & PDQ_DEBUG_FORCE_IRLS_OPTIMIZER) ? 1 : 0};
         const size_t smem_irls = d.smem_bytes + (size_t)(1 + kWarps * (32 >> c.lgT)) * kPsiK * sizeof(double);

@@ -91,7 +91,7 @@ int emu_irls(const int64_t* counts, int64_t ld, int N, int G, const double* sf, 
     Pack k = make_pack(X, sf, N, p);
     EMU_DISPATCH(p, {
         const SmallMat<P> pi = pinv_of<P>(k);
-        const IrlsParams prm{min_mu, beta_tol, min_beta, max_beta, maxiter, k.full_rank};
+        const IrlsParams prm{min_mu, beta_tol, min_beta, max_beta, maxiter, k.full_rank, design_distinct_rows(X, N, p, 16) <= 16};
         double lg_tab[kPsiK];
         for (int g = 0; g < G; ++g) {
             irls_gene<P>(kOne, k.d, pi, prm, counts + g, ld, disp[g], beta + (size_t)g * P, mu + g, hat + g, G, conv + g,
