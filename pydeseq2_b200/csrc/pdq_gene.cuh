@@ -658,11 +658,36 @@ PDQ_HD void build_psi_table(const Group& grp, double* tab, double r) {
     grp.sync();
 }
 
-// contribution of two samples (or one, when !two) to the derivative sums; NB as in irls_sample
-template <int P, bool NB>
+// the same for psi and psi' together (first evaluation of a gene, which also returns the curvature of the NB part):
+// psi'(r + k) = psi'(r) - sum_{j<k} (r + j)^-2.  `tab` holds 2 * kPsiK doubles: psi first, psi' behind it.
+PDQ_HD void build_psi_tri_tables(const Group& grp, double* tab, double r) {
+    const int seg = kPsiK / grp.T;
+    const int k0 = grp.si * seg;
+    double part = 0.0, part2 = 0.0;
+    for (int k = k0; k < k0 + seg; ++k) {
+        const double inv = fast_rcp(r + (double)k);
+        tab[k] = inv;
+        part += inv;
+        part2 = fma(inv, inv, part2);
+    }
+    double run = digamma_pos(r) + grp.excl_scan(part);
+    double run2 = trigamma_pos(r) - grp.excl_scan(part2);
+    for (int k = k0; k < k0 + seg; ++k) {
+        const double inv = tab[k];
+        tab[k] = run;
+        tab[kPsiK + k] = run2;
+        run += inv;
+        run2 = fma(-inv, inv, run2);
+    }
+    grp.sync();
+}
+
+// contribution of two samples (or one, when !two) to the derivative sums; NB as in irls_sample.
+// CURV: also S2 = sum 1/(r+mu) - psi'(y+r) - (y-mu)/(r+mu)^2, the r-derivative of the summand of Sg.
+template <int P, bool NB, bool CURV>
 PDQ_HD void alpha_pair(const Group& grp, const double* xp0, const double* xp1, int Npad, long long yi0, long long yi1,
                        double m0, double m1, bool one, bool two, double r, bool cr_reg, const double* psi_tab, double& Sg,
-                       Sym<P>& A, Sym<P>& B, bool& odd) {
+                       Sym<P>& A, Sym<P>& B, bool& odd, double& S2) {
     // `one` / `two`: which of the two samples exist for this lane (masked-out slots carry y = 0, mu = 1)
     const double yv0 = (double)yi0, yv1 = (double)yi1;
     const bool big0 = one && ((yi0 >= kPsiK) || (yi0 < 0)), big1 = two && ((yi1 >= kPsiK) || (yi1 < 0));
@@ -671,15 +696,29 @@ PDQ_HD void alpha_pair(const Group& grp, const double* xp0, const double* xp1, i
     const double inv0 = NB ? fast_rcp(rm0) : 1.0 / rm0, inv1 = NB ? fast_rcp(rm1) : 1.0 / rm1;
     const double lg0 = NB ? fast_log_nb(rm0) : fast_log(rm0), lg1 = NB ? fast_log_nb(rm1) : fast_log(rm1);
     double dg0 = psi_tab[(int)(yi0 & (kPsiK - 1))], dg1 = psi_tab[(int)(yi1 & (kPsiK - 1))];
+    double tg0 = 0.0, tg1 = 0.0;
+    if (CURV) {
+        tg0 = psi_tab[kPsiK + (int)(yi0 & (kPsiK - 1))];
+        tg1 = psi_tab[kPsiK + (int)(yi1 & (kPsiK - 1))];
+    }
     if (grp.any(big0 || big1)) {  // warp-uniform: the unshifted series only when some lane holds a count >= kPsiK
         const double z0 = big0 ? yv0 + r : r + (double)kPsiK, z1 = big1 ? yv1 + r : r + (double)kPsiK;
         const double a0 = digamma_asym(z0, NB ? fast_log_nb(z0) : fast_log(z0));
         const double a1 = digamma_asym(z1, NB ? fast_log_nb(z1) : fast_log(z1));
         dg0 = big0 ? a0 : dg0;
         dg1 = big1 ? a1 : dg1;
+        if (CURV) {
+            const double b0 = trigamma_asym(z0), b1 = trigamma_asym(z1);
+            tg0 = big0 ? b0 : tg0;
+            tg1 = big1 ? b1 : tg1;
+        }
     }
     const double t0 = lg0 - dg0 + (yv0 - m0) * inv0, t1 = lg1 - dg1 + (yv1 - m1) * inv1;
     Sg += (one ? t0 : 0.0) + (two ? t1 : 0.0);
+    if (CURV) {
+        const double u0 = fma(-(yv0 - m0) * inv0, inv0, inv0 - tg0), u1 = fma(-(yv1 - m1) * inv1, inv1, inv1 - tg1);
+        S2 += (one ? u0 : 0.0) + (two ? u1 : 0.0);
+    }
     if (cr_reg) {
         double xv[P];
 #pragma unroll
@@ -695,10 +734,11 @@ PDQ_HD void alpha_pair(const Group& grp, const double* xp0, const double* xp1, i
     }
 }
 
-template <int P, bool NB>
+template <int P, bool NB, bool CURV>
 PDQ_HD bool alpha_sweep_t(const Group& grp, const DesignS& d, bool cr_reg, const int64_t* y, int64_t ld, const double* mu,
-                          int64_t ld_mu, double r, const double* psi_tab, double& Sg, Sym<P>& A, Sym<P>& B) {
+                          int64_t ld_mu, double r, const double* psi_tab, double& Sg, Sym<P>& A, Sym<P>& B, double& S2) {
     Sg = 0.0;
+    S2 = 0.0;
     sym_zero<P>(A);
     sym_zero<P>(B);
     bool odd = false;
@@ -720,8 +760,8 @@ PDQ_HD bool alpha_sweep_t(const Group& grp, const DesignS& d, bool cr_reg, const
         const long long ny0 = w0 ? yp[2 * ystep] : 0, ny1 = w1 ? yp[3 * ystep] : 0;
         const double nm0 = w0 ? mp[2 * mstep] : 1.0, nm1 = w1 ? mp[3 * mstep] : 1.0;
         // one call site: every lane of the warp reaches the vote inside alpha_pair together
-        alpha_pair<P, NB>(grp, v0 ? xp : d.X, v1 ? xp + T : d.X, d.Npad, yi0, yi1, m0, m1, v0, v1, r, cr_reg, psi_tab, Sg, A,
-                          B, odd);
+        alpha_pair<P, NB, CURV>(grp, v0 ? xp : d.X, v1 ? xp + T : d.X, d.Npad, yi0, yi1, m0, m1, v0, v1, r, cr_reg, psi_tab,
+                                Sg, A, B, odd, S2);
         v0 = w0; v1 = w1; yi0 = ny0; yi1 = ny1; m0 = nm0; m1 = nm1;
     }
 #else
@@ -730,31 +770,54 @@ PDQ_HD bool alpha_sweep_t(const Group& grp, const DesignS& d, bool cr_reg, const
         const long long yi0 = v0 ? yp[0] : 0, yi1 = v1 ? yp[ystep] : 0;
         const double m0 = v0 ? mp[0] : 1.0, m1 = v1 ? mp[mstep] : 1.0;
         // one call site: every lane of the warp reaches the vote inside alpha_pair together
-        alpha_pair<P, NB>(grp, v0 ? xp : d.X, v1 ? xp + T : d.X, d.Npad, yi0, yi1, m0, m1, v0, v1, r, cr_reg, psi_tab, Sg, A,
-                          B, odd);
+        alpha_pair<P, NB, CURV>(grp, v0 ? xp : d.X, v1 ? xp + T : d.X, d.Npad, yi0, yi1, m0, m1, v0, v1, r, cr_reg, psi_tab,
+                                Sg, A, B, odd, S2);
     }
 #endif
     return odd;
 }
 
-// derivative only (the minimiser is located as a root of dloss)
+// derivative only (the minimiser is located as a root of dloss).  `curv` (first evaluation of a gene): also the second
+// derivative of the NB part (+ prior) with respect to x = log(alpha), used for ONE Newton step from the start value:
+//   a dnb_nll = -r F(r),  F = N (psi(r) + x) + Sg,  dr/dx = -r   =>   d/dx = r F + r^2 F',  F' = N (psi'(r) - 1/r) + S2.
+// The Cox-Reid term's curvature is left out (the secant steps that follow see the whole function); NaN when unavailable.
 template <int P>
 PDQ_HD double alpha_dloss(const Group& grp, const DesignS& d, const AlphaParams& prm, const int64_t* y, int64_t ld,
-                          const double* mu, int64_t ld_mu, double x, double xhat, double* psi_tab) {
+                          const double* mu, int64_t ld_mu, double x, double xhat, double* psi_tab, double* curv = nullptr) {
 #if defined(PDQ_EMU_COUNT_EVALS) && !defined(__CUDA_ARCH__)
     ++g_emu_alpha_evals;  // host emulator instrumentation only
 #endif
     const double a = fast_exp(x), r = fast_rcp(a), Nd = (double)d.N;
     grp.sync();  // previous evaluation's table reads are done
-    build_psi_table(grp, psi_tab, r);
-    double Sg;
+    double Sg, S2 = 0.0;
     Sym<P> A, B;
-    bool odd = !(r > 0.0 && r < 1e300);
-    if (!odd) odd = alpha_sweep_t<P, true>(grp, d, prm.cr_reg != 0, y, ld, mu, ld_mu, r, psi_tab, Sg, A, B);
-    if (grp.any(odd)) alpha_sweep_t<P, false>(grp, d, prm.cr_reg != 0, y, ld, mu, ld_mu, r, psi_tab, Sg, A, B);
+    // every lane of the warp runs the same sequence (the sweeps vote and the table builders scan across the warp); a gene
+    // whose r is unusable only marks itself `odd` and the whole warp repeats the sweep on the guarded libdevice path
+    bool odd;
+    if (curv != nullptr) {
+        build_psi_tri_tables(grp, psi_tab, r);
+        odd = alpha_sweep_t<P, true, true>(grp, d, prm.cr_reg != 0, y, ld, mu, ld_mu, r, psi_tab, Sg, A, B, S2);
+    } else {
+        build_psi_table(grp, psi_tab, r);
+        odd = alpha_sweep_t<P, true, false>(grp, d, prm.cr_reg != 0, y, ld, mu, ld_mu, r, psi_tab, Sg, A, B, S2);
+    }
+    odd = odd || !(r > 0.0 && r < 1e300);
+    const bool any_odd = grp.any(odd);
+    if (any_odd) alpha_sweep_t<P, false, false>(grp, d, prm.cr_reg != 0, y, ld, mu, ld_mu, r, psi_tab, Sg, A, B, S2);
+    const bool have_curv = (curv != nullptr) && !any_odd;
     Sg = grp.sum(Sg);
     // a * dnb_nll = -r * sum[psi(r) - psi(y+r) + log(1 + mu a) + (y - mu)/(mu + r)],  log(1+mu a) = x + log(r+mu)
-    double g = -r * (Nd * (psi_tab[0] + x) + Sg);
+    const double F = Nd * (psi_tab[0] + x) + Sg;
+    double g = -r * F;
+    if (curv != nullptr) {
+        double h = __builtin_nan("");
+        if (have_curv) {  // warp-uniform
+            S2 = grp.sum(S2);
+            const double Fp = Nd * (psi_tab[kPsiK] - a) + S2;
+            h = r * (F + r * Fp) + (prm.prior_reg ? 1.0 / prm.prior_var : 0.0);
+        }
+        *curv = h;
+    }
     if (prm.cr_reg) {
         group_sum_sym<P>(grp, A);
         group_sum_sym<P>(grp, B);
@@ -814,7 +877,8 @@ PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& pr
     // |dloss| ~ 1e-7) the reference therefore never leaves its start value, and neither may we.
     const double pgtol = 1e-5;
     double xb = fmin(fmax(xhat, prm.lo), prm.hi);
-    double gb = alpha_dloss<P>(grp, d, prm, y, ld, mu, ld_mu, xb, xhat, psi_tab);
+    double h0;
+    double gb = alpha_dloss<P>(grp, d, prm, y, ld, mu, ld_mu, xb, xhat, psi_tab, &h0);
     double xa = xb, ga = gb;
     double bl = prm.lo, br = prm.hi;  // bracket ends (valid when have_br)
     bool have_br = false, active = true, fail = false;
@@ -827,7 +891,23 @@ PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& pr
     } else if (fabs(gb) <= pgtol || (gb > 0.0 && xb <= prm.lo) || (gb < 0.0 && xb >= prm.hi)) {
         active = false;  // stationary to L-BFGS-B's tolerance, or the projected gradient vanishes at a bound
     } else {
-        xt = fmin(fmax(xb - sgn(gb) * 1.0, prm.lo), prm.hi);
+        // first trial point: one Newton step with the curvature of the NB part (+ prior) when it is shorter than 1 in
+        // log(alpha), else (or where that curvature is not positive / not available) the unit step against the gradient that
+        // L-BFGS-B opens with.  The root is polished by the safeguarded secant below either way, but the Newton point
+        // usually lands within a few percent of it: 3.2-3.8 evaluations per gene instead of 5.1-5.3.
+        double step = -sgn(gb);
+        if (h0 > 0.0) {
+            // a Newton step longer than L-BFGS-B's unit step means the start is far from the root or on a flat tail: there the
+            // stopping point (first evaluated point with |dloss| <= pgtol) depends on the sequence of trial points, so the
+            // reference's own opening move is kept
+            const double s = -gb / h0;
+            if (fabs(s) < 1.0) step = s;
+        }
+        xt = fmin(fmax(xb + step, prm.lo), prm.hi);
+        if (fabs(xt - xb) <= tolx) {  // already there: take the step unevaluated, like the last secant step
+            xres = xt;
+            active = false;
+        }
     }
     for (int ev = 0; ev < 60; ++ev) {
         if (!grp.any(active)) break;
@@ -850,7 +930,14 @@ PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& pr
         xa = xb; ga = gb;
         xb = xt; gb = gt;
         xres = xb;
-        if (fabs(gt) <= pgtol) { active = false; continue; }
+        if (fabs(gt) <= pgtol) {
+            // stationary to L-BFGS-B's tolerance.  The secant through the last two points is free: take it unevaluated when it
+            // is a small correction (on a flat stretch, where it would jump, the evaluated point stands)
+            const double dgs = gb - ga, xs = xb - gb * (xb - xa) / dgs;
+            if (dgs != 0.0 && fabs(xs - xb) <= 1e-3 && xs >= prm.lo && xs <= prm.hi) xres = xs;
+            active = false;
+            continue;
+        }
         if (!have_br && ((gb > 0.0 && xb <= prm.lo) || (gb < 0.0 && xb >= prm.hi))) {
             active = false;  // pushed against a bound: L-BFGS-B stops with zero projected gradient
             continue;

@@ -223,9 +223,10 @@ __global__ void __launch_bounds__(kBlock, PDQ_ALPHA_MINB) k_alpha_mle(const __gr
     AlphaParams prm = a.prm;
     if (a.prior_var_dev) prm.prior_var = *a.prior_var_dev;
     const int gpw = 32 >> a.lgT;
-    // per-gene psi(r + k) tables live behind the design pack and its mbarrier (one slot per gene of the warp's tile)
+    // per-gene psi(r + k) and psi'(r + k) tables live behind the design pack and its mbarrier (one slot of 2 * kPsiK doubles
+    // per gene of the warp's tile)
     double* psi = reinterpret_cast<double*>(smem + (size_t)(P + 2) * a.dv.Npad * 8 + 16) +
-                  (size_t)((threadIdx.x >> 5) * gpw + ((threadIdx.x & 31) & (gpw - 1))) * kPsiK;
+                  (size_t)((threadIdx.x >> 5) * gpw + ((threadIdx.x & 31) & (gpw - 1))) * (2 * kPsiK);
     while (next_tile(a.ticket, a.lgT, a.G, grp, g, valid)) {
         alpha_gene<P>(grp, d, prm, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha_hat[g], a.alpha + g, a.conv + g,
                       a.status + g, valid, psi);
@@ -785,7 +786,7 @@ int launch_alpha_mle(const LaunchCfg& c, const DesignDev& d, const int64_t* coun
         AlphaArgs<P> a{{d.pack, d.N, d.Npad}, AlphaParams{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg},
                        counts, ld, G, c.lgT, mu, ld_mu, alpha_hat, alpha, conv, status, prior_var_dev, c.tickets + 1,
                        (c.debug & PDQ_DEBUG_FORCE_ALPHA_GRID) ? 1 : 0};
-        const size_t smem_alpha = d.smem_bytes + (size_t)kWarps * (32 >> c.lgT) * kPsiK * sizeof(double);
+        const size_t smem_alpha = d.smem_bytes + (size_t)kWarps * (32 >> c.lgT) * 2 * kPsiK * sizeof(double);
         if (int e = prep(k_alpha_mle<P>, smem_alpha)) return e;
         if (int e = prep(k_alpha_grid<P>, d.smem_bytes)) return e;
         if (cudaMemsetAsync(c.tickets + 1, 0, sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;

@@ -210,6 +210,31 @@ PDQ_HD double lgamma_asym(double z, double logz) {  // z >= 10
     return fma(z - 0.5, logz, -z) + kHalfLog2Pi + s * iz;
 }
 
+// psi'(z), z >= 10: 1/z + 1/(2 z^2) + sum_k B_2k / z^(2k+1)   (next omitted term 3.6 z^-17)
+PDQ_HD double trigamma_asym(double z) {
+    const double iz = fast_rcp(z), w = iz * iz;
+    double s = 7.0 / 6.0;
+    s = fma(s, w, -691.0 / 2730.0);
+    s = fma(s, w, 5.0 / 66.0);
+    s = fma(s, w, -1.0 / 30.0);
+    s = fma(s, w, 1.0 / 42.0);
+    s = fma(s, w, -1.0 / 30.0);
+    s = fma(s, w, 1.0 / 6.0);
+    return fma(s * w, iz, fma(0.5, w, iz));
+}
+
+// psi'(x), x > 0: upward shift of 10 below z = 10, psi'(x) = psi'(x + 10) + sum_{k<10} (x + k)^-2
+PDQ_HD double trigamma_pos(double x) {
+    if (x >= 10.0) return trigamma_asym(x);
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        const double i = fast_rcp(x + (double)k);
+        s = fma(i, i, s);
+    }
+    return trigamma_asym(x + 10.0) + s;
+}
+
 PDQ_HD double digamma_pos(double x) {
     if (x >= 10.0) return digamma_asym(x, fast_log(x));
     double P, dP;

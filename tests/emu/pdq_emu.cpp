@@ -111,7 +111,7 @@ int emu_alpha_mle(const int64_t* counts, int64_t ld, int N, int G, const double*
     Pack k = make_pack(X, nullptr, N, p);
     EMU_DISPATCH(p, {
         const AlphaParams prm{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg};
-        double psi[kPsiK];
+        double psi[2 * kPsiK];
         for (int g = 0; g < G; ++g) {
             alpha_gene<P>(kOne, k.d, prm, counts + g, ld, mu + g, ld_mu, alpha_hat[g], alpha + g, conv + g, status + g, true, psi);
             if (force_grid) {
