@@ -25,11 +25,13 @@ namespace {
 constexpr int kBlock = 128;
 constexpr int kWarps = kBlock / 32;
 // resident blocks per SM the two heavy kernels are compiled for (register cap = 65536 / (128 * blocks)); tuned on B200
+// (scripts/variants_sweep.sh; irls 6|5|4: 0.304|0.310|0.308 ms at 20 000 x 200, 1.93|1.92|1.79 ms at 60 000 x 500;
+//  alpha_mle 5|4|3: 0.249|0.240|0.203 ms and 1.29|1.23|1.09 ms -- the Newton-opening sweep needs the registers)
 #ifndef PDQ_IRLS_MINB
-#define PDQ_IRLS_MINB 6
+#define PDQ_IRLS_MINB 4
 #endif
 #ifndef PDQ_ALPHA_MINB
-#define PDQ_ALPHA_MINB 4
+#define PDQ_ALPHA_MINB 3
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
