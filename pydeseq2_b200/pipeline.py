@@ -523,6 +523,20 @@ class ResidentFit:
                 **({"robust_dispersions": H["robust_disp"], "cooks_outlier": H["cooks_outlier"] == 1.0,
                     "cooks_replaced": H["cooks_replaced"] == 1.0} if self.with_cooks else {})}
 
+    def gather_results(self, result: dict) -> dict:
+        """End-of-call exchange of the gene shards (SURVEY.md §8 e): one packed NCCL all-gather of every per-gene result of
+        :meth:`run`, after which each rank holds the full-length tables (rank order = gene order).  No-op without shards."""
+        if self.comm is None:
+            return result
+        keys = [k for k, v in result.items() if isinstance(v, np.ndarray) and v.shape[:1] == (self.G,)]
+        full = self.comm.allgather_table({k: np.asarray(result[k], dtype=np.float64) for k in keys})
+        out = dict(result)
+        out.update(full)
+        for k in ("cooks_outlier", "cooks_replaced"):
+            if k in full:
+                out[k] = full[k] == 1.0
+        return out
+
     # -- apeGLM shrinkage on the resident counts ----------------------------------------------------------
     def lfc_shrink(self, result, coeff_idx: int, adapt: bool = True, se=None, prior_scale=None):
         """``DeseqStats.lfc_shrink`` (ds.py:363-443) after :meth:`run`: counts, design pack and dispersions are already in HBM,

@@ -50,6 +50,28 @@ class _PaddedGather:
                 np.concatenate([out[r, 1, :n] for r, n in enumerate(self.sizes)]))
 
 
+    def allgather_table(self, cols: dict) -> dict:
+        """All-gather of several per-gene arrays at once (``(n_local,)`` or ``(n_local, k)``): ONE collective on a packed
+        buffer; returns full-length arrays in rank order.  This is the end-of-call exchange of SURVEY.md §8(e): after it every
+        rank holds the complete per-gene result tables."""
+        m = max(self.sizes)
+        names = list(cols)
+        widths = [1 if np.ndim(cols[k]) == 1 else int(np.shape(cols[k])[1]) for k in names]
+        send = np.full((sum(widths), m), np.nan)
+        row = 0
+        for k, w in zip(names, widths):
+            v = np.asarray(cols[k], dtype=np.float64)
+            send[row:row + w, : v.shape[0]] = v.reshape(v.shape[0], w).T
+            row += w
+        out = self._gather_equal(send.ravel()).reshape(len(self.sizes), sum(widths), m)
+        res, row = {}, 0
+        for k, w in zip(names, widths):
+            full = np.concatenate([out[r, row:row + w, :n].T for r, n in enumerate(self.sizes)])
+            res[k] = full[:, 0] if np.ndim(cols[k]) == 1 else full
+            row += w
+        return res
+
+
 class TorchDistComm(_PaddedGather):
     """torch.distributed flavour (gloo on CPU for tests; also works with nccl + cuda tensors)."""
 

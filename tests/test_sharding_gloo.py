@@ -26,7 +26,9 @@ def _worker(rank, world, port, q):
     lo, hi = shard_bounds(G, world, rank)
     comm = TorchDistComm(shard_sizes(G, world))
     r = fit_host(counts[:, lo:hi], X, nbglm.OracleInference(n_cpus=1), size_factors=sf, comm=comm)
-    q.put((rank, lo, hi, r.lfc, r.dispersions, r.pvalue, r.trend.coeffs, r.prior_var))
+    # end-of-call exchange (SURVEY.md §8 e): one packed all-gather, every rank ends up with the full tables
+    full = comm.allgather_table({"lfc": r.lfc, "disp": r.dispersions, "pv": r.pvalue})
+    q.put((rank, lo, hi, r.lfc, r.dispersions, r.pvalue, r.trend.coeffs, r.prior_var, full))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -61,6 +63,10 @@ def test_two_rank_gene_shards_reproduce_single_process_fit():
     for g in got:
         np.testing.assert_allclose(g[6], full.trend.coeffs, rtol=1e-12)
         assert g[7] == pytest.approx(full.prior_var, rel=1e-12)
+        # the gathered tables are identical on both ranks and equal the concatenation of the shards
+        np.testing.assert_array_equal(g[8]["lfc"], lfc)
+        np.testing.assert_array_equal(g[8]["disp"], disp)
+        np.testing.assert_array_equal(g[8]["pv"], pv)
 
 
 def test_shard_bounds_cover_and_partition():
