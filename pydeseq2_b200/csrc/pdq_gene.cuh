@@ -1162,7 +1162,7 @@ PDQ_HD void mom_fused_gene(const Group& grp, const DesignS& d, const SmallMat<P>
     for (int n = grp.si; n < d.N; n += grp.T, yp += ystep) {
         double x[P];
         load_x<P>(d, n, x);
-        const double t = (double)*yp / d.sf[n];
+        const double t = fast_div((double)*yp, d.sf[n]);  // <= 1 ulp from counts / sf
         s += t;
 #pragma unroll
         for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
@@ -1185,10 +1185,10 @@ PDQ_HD void mom_fused_gene(const Group& grp, const DesignS& d, const SmallMat<P>
         double fit = 0.0;
 #pragma unroll
         for (int j = 0; j < P; ++j) fit = fma(x[j], beta[j], fit);
-        const double t = (double)*yp / d.sf[n];
+        const double t = fast_div((double)*yp, d.sf[n]);  // <= 1 ulp from counts / sf
         const double yh = (fit < 1.0) ? 1.0 : fit;  // np.maximum(y_hat, 1)
         const double e = t - yh;
-        rough += (e * e - yh) / (yh * yh);
+        rough += fast_div(e * e - yh, yh * yh);
         const double dm = t - m;
         ss = fma(dm, dm, ss);
         if (mu_out && valid) {
