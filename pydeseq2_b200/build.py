@@ -33,8 +33,11 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
     tag = "".join(d.replace("-D", "_").replace("=", "") for d in defines)
     objdir = os.path.join(HERE, "build" + tag)
     target = os.path.join(HERE, out) if out else OUT
-    os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
+    # the library is newer than every source: nothing to do (the object directory does not travel with gpurun snapshots)
+    if not force and not _stale(target, [os.path.join(CSRC, s) for s in SOURCES] + hdrs):
+        return target
+    os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
