@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpydeseq2_b200.so")
 SOURCES = ["pdq_kernels.cu", "pdq_api.cu"]
-HEADERS = ["pdq_math.cuh", "pdq_fast.cuh", "pdq_trend.cuh", "pdq_gene.cuh", "pdq_internal.h", "pdq_host_linalg.h",
+HEADERS = ["pdq_math.cuh", "pdq_fast.cuh", "pdq_trend.cuh", "pdq_gene.cuh", "pdq_shrink.cuh", "pdq_internal.h", "pdq_host_linalg.h",
            os.path.join("..", "..", "include", "pydeseq2_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-fopenmp", "--expt-relaxed-constexpr"]
