@@ -72,3 +72,10 @@ def test_shrink_grid_fallback(inf):
 
 def test_shrink_arguments(inf):
     ec.check_shrink_arguments(inf)
+
+
+@pytest.mark.parametrize("p,N", [(1, 9), (2, 13), (3, 17), (4, 21), (5, 24), (6, 27), (7, 31), (8, 35)])
+def test_every_design_width(inf, p, N):
+    from oracle import nbglm
+
+    ec.check_design_width(inf, nbglm.OracleInference(n_cpus=4), p, N)
