@@ -1,0 +1,62 @@
+"""Helper of tests/test_reference_dropin.py, run in a SUBPROCESS (build container only): the REAL, unmodified orchestrator of the
+reference (`DeseqDataSet.deseq2()`, `DeseqStats.summary()`, `lfc_shrink()`) with `B200Inference` injected as its `inference=`
+backend -- device algorithms through the host emulator, since this container has no GPU.  Writes the final tables to an .npz.
+The import shims (oracle/refshim*) stay inside this process."""
+import os
+import sys
+import warnings
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for d in ("refshim", "refshim_orch"):
+    sys.path.insert(0, os.path.join(ROOT, "oracle", d))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import pandas as pd  # noqa: E402
+
+
+def main(fixture, out):
+    from pydeseq2.dds import DeseqDataSet
+    from pydeseq2.ds import DeseqStats
+    from pydeseq2.inference import Inference
+
+    from emu.emu_ops import EmuOps
+    from pydeseq2_b200.inference import B200Inference
+
+    assert issubclass(B200Inference, Inference)       # with the reference importable the backend IS a pydeseq2 Inference
+    g = np.load(fixture)
+    counts, X, contrast = g["counts"], g["design"], g["contrast"]
+    N, G = counts.shape
+    idx = [f"s{i}" for i in range(N)]
+    counts_df = pd.DataFrame(counts, index=idx, columns=[f"g{i}" for i in range(G)])
+    design_df = pd.DataFrame(X, index=idx, columns=[f"x{j}" for j in range(X.shape[1])])
+    meta = pd.DataFrame({"dummy": np.arange(N)}, index=idx)
+    backend = B200Inference(_ops=EmuOps())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dds = DeseqDataSet(counts=counts_df, metadata=meta, design=design_df, inference=backend, quiet=True)
+        dds.deseq2()
+        ds = DeseqStats(dds, contrast=contrast, inference=backend, quiet=True)
+        ds.summary()
+        res = ds.results_df.copy()   # lfc_shrink() below overwrites columns of results_df in place
+        k = int(np.flatnonzero(contrast)[-1])
+        # ds.lfc_shrink() itself: under pandas 3 its `.iloc[:, k].update(...)` writes into a temporary (oracle/make_golden.py notes
+        # the same for the reference's own backend), so the plugin call is what is checked here
+        size = 1.0 / dds.var["dispersions"].values
+        offset = np.log(dds.obs["size_factors"]).values
+        nz = dds.non_zero_idx
+        prior_var = ds._fit_prior_var(coeff_idx=k)
+        ds.lfc_shrink(coeff=design_df.columns[k])
+        shrunk = backend.lfc_shrink_nbinom_glm(design_matrix=X, counts=dds.X[:, nz], size=size[nz], offset=offset,
+                                              prior_no_shrink_scale=15, prior_scale=float(np.minimum(np.sqrt(prior_var), 1)),
+                                              optimizer="L-BFGS-B", shrink_index=k)
+    np.savez(out, baseMean=res["baseMean"].values, log2FoldChange=res["log2FoldChange"].values, lfcSE=res["lfcSE"].values,
+             stat=res["stat"].values, pvalue=res["pvalue"].values, padj=res["padj"].values, LFC=dds.varm["LFC"].values,
+             dispersions=dds.var["dispersions"].values, replaced=np.asarray(dds.var["replaced"], dtype=float),
+             cooks_outlier=np.asarray(dds.cooks_outlier(), dtype=float), shrunk_lfc=shrunk[0], shrink_converged=shrunk[2],
+             shrink_flag_set=np.float64(ds.shrunk_LFCs), n_cpus=np.float64(backend.n_cpus or 0))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2])

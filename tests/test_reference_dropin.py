@@ -1,0 +1,51 @@
+"""CPU suite, build container only: `B200Inference` plugged into the REAL reference orchestrator (`DeseqDataSet(..., inference=)`,
+`DeseqStats(..., inference=)`), i.e. the drop-in claim of INTEGRATION.md exercised with the reference's own objects.  The device
+algorithms run through the host emulator.  Skipped where the read-only checkout is absent (the GPU box)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = [pytest.mark.refcheck,
+              pytest.mark.skipif(not os.path.isdir("/root/reference/pydeseq2"), reason="needs the reference checkout")]
+
+
+@pytest.mark.parametrize("name", ["e2e_two_level_n24", "e2e_factorial_n20"])
+def test_real_orchestrator_with_b200_backend(name, tmp_path):
+    out = str(tmp_path / "res.npz")
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "dropin_reference_run.py"), os.path.join(GOLDEN, name + ".npz"), out],
+                       capture_output=True, text=True, timeout=1500, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    got, ref = np.load(out), load_golden(name)
+    # discrete outcomes of the orchestrator equal those it reached with its own CPU backend
+    np.testing.assert_array_equal(got["replaced"], ref["final_replaced"])
+    np.testing.assert_array_equal(got["cooks_outlier"], ref["final_cooks_outlier"])
+    np.testing.assert_array_equal(np.isnan(got["pvalue"]), np.isnan(ref["final_pvalue"]))
+    np.testing.assert_array_equal(np.isnan(got["padj"]), np.isnan(ref["final_padj"]))
+    np.testing.assert_allclose(got["baseMean"], ref["final_baseMean"], rtol=1e-12)
+
+    def mostly(a, b, rtol, atol=0.0):  # same mismatch budget as tests/parity.py::check_e2e
+        bad = ~np.isclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
+        assert bad.mean() <= 0.005, bad.mean()
+        np.testing.assert_allclose(a, b, rtol=100 * rtol, atol=100 * atol, equal_nan=True)
+
+    mostly(got["LFC"], ref["final_LFC"], 1e-4, 1e-8)
+    mostly(got["dispersions"], ref["final_dispersions"], 1e-4)
+    mostly(got["log2FoldChange"], ref["final_log2FoldChange"], 1e-4, 1e-8)
+    mostly(got["lfcSE"], ref["final_lfcSE"], 1e-4)
+    mostly(got["stat"], ref["final_stat"], 1e-4, 1e-8)
+    big = ref["final_pvalue"] >= 1e-20
+    mostly(got["pvalue"][big], ref["final_pvalue"][big], 1e-3)
+    ok = ~np.isnan(ref["final_padj"]) & big
+    mostly(got["padj"][ok], ref["final_padj"][ok], 1e-3)
+    # the shrinkage plugin call made by the orchestrator's own lfc_shrink() went through the backend
+    assert got["shrink_flag_set"] == 1.0 and got["shrink_converged"].mean() > 0.99
+    assert np.isfinite(got["shrunk_lfc"]).all()
+    assert got["n_cpus"] > 0   # the orchestrator set the attribute it expects on a backend (dds.py:323-333)
