@@ -283,6 +283,21 @@ def main():
                 "frac": achieved / peak, "traffic": traffic_from_profiles(kname), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes[top] * N * G, "kernel_ms": kern[top],
                 "note": "FP64-pipe bound (lgamma/digamma/exp/log per gene-sample-iteration), see DESIGN.md §5"}
+    # second roofline, the one that binds: FP64 arithmetic.  Peak = DFMA throughput measured now on this device; achieved = the
+    # kernel's FP64 flop count (2*DFMA + DMUL + DADD thread instructions, from the committed ncu capture of the same workload,
+    # scaled to this run's gene-sample count) over its CUDA-event duration.
+    prof = {}
+    if os.path.exists(os.path.join(ROOT, "profiles", "traffic.json")):
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    flop_ref = prof.get("fp64_flop_per_launch", {}).get(kname)
+    fp64_peak = ctx.fp64_peak_tflops()
+    fp64 = {"peak_tflops": fp64_peak, "peak_source": "measured in this run (pdq_fp64_peak_tflops: DFMA chains on every SM)"}
+    if flop_ref:
+        flop = flop_ref * (N * G) / (19800 * 200)
+        fp64.update({"achieved_tflops": flop / (kern[top] * 1e-3) / 1e12, "flop_per_launch": flop,
+                     "frac": flop / (kern[top] * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,
+                     "pipe_active_pct_ncu": prof.get("fp64_pipe_active_pct", {}).get(kname)})
+    roofline["fp64"] = fp64
 
     # ---------------------------------------------------------------- e2e: plugin calls with host buffers
     c_host = ctx.pinned_empty(counts.shape, np.int64)

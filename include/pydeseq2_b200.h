@@ -68,6 +68,9 @@ int pdq_set_lanes_per_gene(pdq_ctx* ctx, int lanes);
  * grid_fit_shrink_beta (grid_search.py:224-318). */
 #define PDQ_DEBUG_FORCE_SHRINK_GRID 4
 int pdq_set_debug_flags(pdq_ctx* ctx, int flags);
+/* Measured FP64 FMA throughput of the context's device in TFLOP/s (dependent-free DFMA chains on every SM, CUDA-event timed):
+ * the arithmetic roofline bench.py reports next to the HBM one -- the per-gene kernels are FP64-pipe bound. */
+int pdq_fp64_peak_tflops(pdq_ctx* ctx, double* tflops_out);
 /* number of kernel launches issued through this context so far (bench.py `gpu_launches`) */
 int64_t pdq_launch_count(const pdq_ctx* ctx);
 

@@ -82,6 +82,7 @@ _SIGNATURES = {
     "pdq_cooks_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, c_dptr, c_dptr, C.c_int64, C.c_double, c_dptr,
                                 C.c_int64, c_dptr, c_dptr, c_dptr]),
     "pdq_size_factors": (C.c_int, [c_ctx, i64p, C.c_int64, C.c_int, C.c_int, f64p]),
+    "pdq_fp64_peak_tflops": (C.c_int, [c_ctx, f64p]),
     "pdq_lfc_shrink_nbinom_glm": (C.c_int, [c_ctx, f64p, i64p, C.c_int64, C.c_int, C.c_int, C.c_int, f64p, f64p, C.c_double,
                                             C.c_double, C.c_int, f64p, f64p, f64p, C.POINTER(C.c_int)]),
     "pdq_lfc_shrink_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, c_dptr, C.c_double, C.c_double, C.c_int, c_dptr,
@@ -202,6 +203,12 @@ class Context:
 
     def launches(self) -> int:
         return int(self.lib.pdq_launch_count(self.h))
+
+    def fp64_peak_tflops(self) -> float:
+        """Measured DFMA throughput of this device (TFLOP/s): the arithmetic roofline of the FP64-bound kernels."""
+        out = np.zeros(1)
+        self.check(self.lib.pdq_fp64_peak_tflops(self.h, as_f64p(out)))
+        return float(out[0])
 
     def pinned_empty(self, shape, dtype=np.float64) -> np.ndarray:
         """numpy array backed by page-locked host memory (released when the array is collected)."""

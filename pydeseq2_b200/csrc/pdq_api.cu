@@ -510,6 +510,31 @@ extern "C" int pdq_lfc_shrink_dev(pdq_ctx* c, const pdq_design* d, const int64_t
                                      inv_hessians, conv, status), "lfc_shrink");
 }
 
+extern "C" int pdq_fp64_peak_tflops(pdq_ctx* c, double* tflops_out) {
+    CHECK_CTX(c);
+    if (!tflops_out) return fail(c, PDQ_ERR_INVALID, "pdq_fp64_peak_tflops: bad arguments");
+    void* buf;
+    if (int e = ensure(c, kBufA, (size_t)c->prop.multiProcessorCount * 8 * 256 * 8, &buf)) return e;
+    const LaunchCfg lc = cfg(c, 1, 1);
+    cudaEvent_t e0, e1;
+    CU(c, cudaEventCreate(&e0));
+    CU(c, cudaEventCreate(&e1));
+    double flop = 0.0, best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+        CU(c, cudaEventRecord(e0, c->stream));
+        if (int e = done(c, launch_fp64_peak(lc, (double*)buf, 20000, &flop), "fp64_peak")) return e;
+        CU(c, cudaEventRecord(e1, c->stream));
+        CU(c, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(c, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms > 0.f) best = fmax(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops_out = best;
+    return PDQ_OK;
+}
+
 extern "C" int pdq_mom_dispersions_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, double min_disp,
                                        double max_disp, double* alpha, double* normed_mean, double min_mu, double* mu_hat_out,
                                        int64_t ld_mu) {

@@ -732,6 +732,22 @@ __global__ void __launch_bounds__(kBlock) k_lfc_shrink_grid(const __grid_constan
     shrink_grid_gene(grp, d, a.prm, a.counts + g, a.ld, a.size[g], a.beta + (int64_t)g * 2, a.ih + (int64_t)g * 4, run);
 }
 
+// ---- FP64 peak probe (bench.py: the second roofline of these kernels) ------------------------------------------------
+// 8 independent DFMA chains per thread, 8 blocks of 256 threads per SM: enough independent work to saturate the FP64 pipe.
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double m, double c) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1.0 + 1e-9 * (double)(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = fma(a[k], m, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 #define PDQ_DISPATCH_P(p, ...)             \
     switch (p) {                           \
         case 1: { constexpr int P = 1; __VA_ARGS__; } break; \
@@ -951,6 +967,14 @@ int launch_lfc_shrink(const LaunchCfg& c, const DesignDev& d, const int64_t* cou
     }
     if (int e = check_launch()) return e;
     return d.p == 2 ? 2 : 1;
+}
+
+int launch_fp64_peak(const LaunchCfg& c, double* out, int iters, double* flop) {
+    const int blocks = c.sm_count * 8, threads = 256;
+    k_fp64_peak<<<blocks, threads, 0, c.stream>>>(out, iters, 0.999999999, 1e-9);
+    *flop = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    if (int e = check_launch()) return e;
+    return 1;
 }
 
 int launch_size_factors(const LaunchCfg& c, const int64_t* counts, int64_t ld, int N, int G, double* logmeans,
