@@ -393,6 +393,15 @@ def gen_e2e(name, N, G, design_kind, seed, n_outliers, contrast_index=None, **st
     p = X.shape[1]
     contrast = np.zeros(p)
     contrast[p - 1 if contrast_index is None else contrast_index] = 1.0
+    run_e2e(name, counts, X, contrast, **stats_kwargs)
+
+
+def run_e2e(name, counts, X, contrast, **stats_kwargs):
+    from pydeseq2.dds import DeseqDataSet
+    from pydeseq2.ds import DeseqStats
+
+    N, G = counts.shape
+    p = X.shape[1]
     idx = [f"s{i}" for i in range(N)]
     counts_df = pd.DataFrame(counts, index=idx, columns=[f"g{i}" for i in range(G)])
     design_df = pd.DataFrame(X, index=idx, columns=[f"x{j}" for j in range(p)])
@@ -420,6 +429,33 @@ def gen_e2e(name, N, G, design_kind, seed, n_outliers, contrast_index=None, **st
           f"padj NaN={int(res['padj'].isna().sum())} p NaN={int(res['pvalue'].isna().sum())}")
 
 
+def main_e2e_edge():
+    """The reference's own orchestrator-level edge cases (tests/test_edge_cases.py:323-465) on its shipped dataset."""
+    counts = pd.read_csv(f"{REF}/datasets/synthetic/test_counts.csv", index_col=0).T
+    meta = pd.read_csv(f"{REF}/datasets/synthetic/test_metadata.csv", index_col=0)
+
+    def design(m):
+        return np.stack([np.ones(len(m)), indicator(m["condition"], "B").values], axis=1)
+
+    # test_few_samples: two samples per condition, one outlier -> nothing can be replaced
+    keep = ["sample1", "sample2", "sample99", "sample100"]
+    c = counts.loc[keep].copy()
+    c.iloc[0, 0] = 1000
+    run_e2e("edge_few_samples", c.values.astype(np.int64), design(meta.loc[keep]), np.array([0.0, 1.0]))
+    # test_few_samples_and_outlier: a 2-sample cohort next to a 9-sample one, two outliers
+    keep = ["sample1", "sample2"] + [f"sample{i}" for i in range(92, 101)]
+    c = counts.loc[keep].copy()
+    c.iloc[0, 0] = 1000
+    c.iloc[-1, -1] = 1000
+    run_e2e("edge_few_samples_and_outlier", c.values.astype(np.int64), design(meta.loc[keep]), np.array([0.0, 1.0]))
+    # test_new_all_zero_gene: replacement turns geneX into an all-zero gene (and the parametric trend fit fails on 11 genes)
+    keep = [f"sample{i}" for i in [*range(1, 11), *range(91, 101)]]
+    c = counts.loc[keep].copy()
+    c["geneX"] = 0
+    c.loc["sample100", "geneX"] = 100
+    run_e2e("edge_new_all_zero_gene", c.values.astype(np.int64), design(meta.loc[keep]), np.array([0.0, 1.0]))
+
+
 def main_e2e():
     gen_e2e("two_level_n24", 24, 400, "two_level", 11, 12)               # cells of 12 >= 7: outliers are replaced and refitted
     gen_e2e("factorial_n20", 20, 400, "factorial", 12, 12)               # cells of 5 < 7: outliers lose their p-value instead
@@ -430,9 +466,13 @@ def main_e2e():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "e2e":  # end-to-end fixtures only
         main_e2e()
+        main_e2e_edge()
+    elif len(sys.argv) > 1 and sys.argv[1] == "e2e_edge":
+        main_e2e_edge()
     elif len(sys.argv) > 1 and sys.argv[1] == "shrink":  # apeGLM fixtures only (reads the existing calls_* fixtures)
         main_shrink()
     else:
         main()
         main_shrink()
         main_e2e()
+        main_e2e_edge()

@@ -127,7 +127,9 @@ def check_shrink(inf, g, tol=TOL_SHRINK):
         np.testing.assert_allclose(se, g["final_lfcSE"], rtol=tol)
 
 
-E2E = ["e2e_two_level_n24", "e2e_factorial_n20", "e2e_two_level_n16_bh", "e2e_continuous_n30"]
+E2E = ["e2e_two_level_n24", "e2e_factorial_n20", "e2e_two_level_n16_bh", "e2e_continuous_n30",
+       # the reference's orchestrator-level edge cases (its tests/test_edge_cases.py:323-465)
+       "e2e_edge_few_samples", "e2e_edge_few_samples_and_outlier", "e2e_edge_new_all_zero_gene"]
 TAPES_E2E = ["tape_single_factor", "tape_multi_factor", "tape_continuous", "tape_wide", "tape_multi_factor_outliers"]
 
 
