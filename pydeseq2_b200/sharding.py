@@ -29,6 +29,12 @@ class _PaddedGather:
     """All-gather of ragged per-rank vectors through an equal-count primitive (pad with NaN, strip after)."""
 
     sizes: list
+    rank: int
+
+    def local_slice(self) -> slice:
+        """Position of this rank's genes in a gathered (full-length) vector."""
+        lo = int(sum(self.sizes[: self.rank]))
+        return slice(lo, lo + int(self.sizes[self.rank]))
 
     def _gather_equal(self, send: np.ndarray) -> np.ndarray:  # (world * len(send),)
         raise NotImplementedError
@@ -82,6 +88,8 @@ class TorchDistComm(_PaddedGather):
         self.group = group
         self.sizes = list(sizes)
         self.device = device
+        self.rank = dist.get_rank(group)
+        self.world = len(self.sizes)
 
     def _gather_equal(self, send):
         import torch

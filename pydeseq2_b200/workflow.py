@@ -124,10 +124,16 @@ class Deseq2Results:
 
 def deseq2_results(counts, X, inference, contrast=None, size_factors=None, refit_cooks=True, min_replicates=7, cooks_filter=True,
                    independent_filter=True, alpha=0.05, lfc_null=0.0, alt_hypothesis=None, fit_type="parametric", min_mu=0.5,
-                   min_disp=1e-8, max_disp=10.0, beta_tol=1e-8, shrink_coeff=None, shrink_adapt=True, keep_cooks=False) -> Deseq2Results:
+                   min_disp=1e-8, max_disp=10.0, beta_tol=1e-8, shrink_coeff=None, shrink_adapt=True, keep_cooks=False,
+                   comm=None) -> Deseq2Results:
     """The reference's default analysis -- ``dds.deseq2()`` then ``DeseqStats(dds, contrast).summary()`` (and ``lfc_shrink`` when
     ``shrink_coeff`` is given) -- through ``inference``.  ``counts`` (N, G) non-negative integers, ``X`` (N, p) expanded design,
-    ``contrast`` (p,) numeric contrast vector (default: last coefficient)."""
+    ``contrast`` (p,) numeric contrast vector (default: last coefficient).
+
+    ``comm`` (``sharding.TorchDistComm`` / ``NcclComm``): ``counts`` is this rank's gene shard and ``size_factors`` must be given.
+    Everything per gene -- fits, Cook's distances, the outlier refit -- stays local; the three steps that look at ALL genes are
+    exchanged: the dispersion trend / prior (inside ``fit_host``), the multiple-testing step (base means and p-values are
+    all-gathered, adjusted identically on every rank, and the local slice is kept) and the apeGLM prior scale."""
     from scipy.stats import f as f_dist
 
     counts = np.ascontiguousarray(counts, dtype=np.int64)
@@ -140,8 +146,10 @@ def deseq2_results(counts, X, inference, contrast=None, size_factors=None, refit
     contrast = np.asarray(contrast, dtype=float)
     if lfc_null < 0 and alt_hypothesis in ("greaterAbs", "lessAbs"):
         raise ValueError(f"The alternative hypothesis being {alt_hypothesis}, please provide a positive lfc_null value (got {lfc_null}).")
+    if comm is not None and size_factors is None:
+        raise ValueError("gene shards: size factors are per sample and global over genes -- pass them in")
     fit = fit_host(counts, X, inference, contrast=contrast, size_factors=size_factors, min_mu=min_mu, min_disp=min_disp, max_disp=max_disp,
-                   beta_tol=beta_tol, fit_type=fit_type, lfc_null=lfc_null, alt_hypothesis=alt_hypothesis)
+                   beta_tol=beta_tol, fit_type=fit_type, lfc_null=lfc_null, alt_hypothesis=alt_hypothesis, comm=comm)
     max_disp = max(max_disp, N)
     sf, nz = fit.size_factors, fit.non_zero
     lfc, disp = fit.lfc.copy(), fit.dispersions.copy()
@@ -202,13 +210,19 @@ def deseq2_results(counts, X, inference, contrast=None, size_factors=None, refit
     if cooks_filter:
         pv[outlier] = np.nan
 
-    # ---- multiple testing (ds.py:486-542)
+    # ---- multiple testing (ds.py:486-542): global over genes
+    bm_all, pv_all = base_mean, pv
+    if comm is not None:
+        g = comm.allgather_table({"bm": base_mean, "pv": pv})
+        bm_all, pv_all = g["bm"], g["pv"]
     if independent_filter:
-        padj = independent_filtering(base_mean, pv, alpha)
+        padj = independent_filtering(bm_all, pv_all, alpha)
     else:
-        padj = np.full(G, np.nan)
-        ok = ~np.isnan(pv)
-        padj[ok] = bh_adjust(pv[ok])
+        padj = np.full(len(pv_all), np.nan)
+        ok = ~np.isnan(pv_all)
+        padj[ok] = bh_adjust(pv_all[ok])
+    if comm is not None:
+        padj = padj[comm.local_slice()]
 
     res = Deseq2Results(base_mean, lfc @ contrast / LN2, se / LN2, stat, pv, padj, lfc, disp, genewise, fitted, sf, nz, replaced, refitted,
                         outlier, cooks if keep_cooks else None, fit)
@@ -216,7 +230,11 @@ def deseq2_results(counts, X, inference, contrast=None, size_factors=None, refit
         k = int(shrink_coeff)
         scale = 1.0
         if shrink_adapt:
-            scale = float(np.minimum(np.sqrt(fit_shrink_prior_var(lfc[:, k], se)), 1))
+            lk, sk = lfc[:, k], se
+            if comm is not None:
+                g = comm.allgather_table({"l": lk, "s": sk})
+                lk, sk = g["l"], g["s"]
+            scale = float(np.minimum(np.sqrt(fit_shrink_prior_var(lk, sk)), 1))
         sh, ih, _ = inference.lfc_shrink_nbinom_glm(X, c_nz, 1.0 / disp[nz], np.log(sf), 15, scale, "L-BFGS-B", k)
         lfc[nz, k] = np.asarray(sh)[:, k]
         se = se.copy()
