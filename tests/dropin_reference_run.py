@@ -16,7 +16,7 @@ import numpy as np  # noqa: E402
 import pandas as pd  # noqa: E402
 
 
-def main(fixture, out):
+def main(fixture, out, subclass=False):
     from pydeseq2.dds import DeseqDataSet
     from pydeseq2.ds import DeseqStats
     from pydeseq2.inference import Inference
@@ -33,6 +33,10 @@ def main(fixture, out):
     design_df = pd.DataFrame(X, index=idx, columns=[f"x{j}" for j in range(X.shape[1])])
     meta = pd.DataFrame({"dummy": np.arange(N)}, index=idx)
     backend = B200Inference(_ops=EmuOps())
+    if subclass:   # size factors and Cook's distances through the backend as well (pydeseq2_b200/integration.py)
+        from pydeseq2_b200.integration import b200_dataset_class
+
+        DeseqDataSet = b200_dataset_class()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         dds = DeseqDataSet(counts=counts_df, metadata=meta, design=design_df, inference=backend, quiet=True)
@@ -59,4 +63,4 @@ def main(fixture, out):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], subclass=len(sys.argv) > 3 and sys.argv[3] == "subclass")

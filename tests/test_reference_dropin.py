@@ -15,12 +15,15 @@ pytestmark = [pytest.mark.refcheck,
               pytest.mark.skipif(not os.path.isdir("/root/reference/pydeseq2"), reason="needs the reference checkout")]
 
 
-@pytest.mark.parametrize("name", ["e2e_two_level_n24", "e2e_factorial_n20"])
-def test_real_orchestrator_with_b200_backend(name, tmp_path):
+@pytest.mark.parametrize("name,mode", [("e2e_two_level_n24", "plugin"), ("e2e_factorial_n20", "plugin"),
+                                       ("e2e_two_level_n24", "subclass"), ("e2e_factorial_n20", "subclass")])
+def test_real_orchestrator_with_b200_backend(name, mode, tmp_path):
+    """mode "plugin": the stock DeseqDataSet with `inference=B200Inference`; mode "subclass": `integration.b200_dataset_class()`,
+    which also routes size factors and Cook's distances through the backend."""
     out = str(tmp_path / "res.npz")
     env = dict(os.environ)
     env.pop("PYTHONPATH", None)
-    r = subprocess.run([sys.executable, os.path.join(HERE, "dropin_reference_run.py"), os.path.join(GOLDEN, name + ".npz"), out],
+    r = subprocess.run([sys.executable, os.path.join(HERE, "dropin_reference_run.py"), os.path.join(GOLDEN, name + ".npz"), out, mode],
                        capture_output=True, text=True, timeout=1500, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
     got, ref = np.load(out), load_golden(name)
