@@ -187,12 +187,39 @@ class B200Inference(_InferenceBase):
         (``dds.py:323-333``, ``ds.py:194-204``); it has no effect on the GPU path.
     lanes_per_gene : int
         0 (default) picks the lanes cooperating on one gene from the number of genes.
+    trace : bool
+        Record every plugin call in ``self.trace`` (method, milliseconds, bytes requested host→device / device→host).
     """
 
-    def __init__(self, device: int = 0, n_cpus: int | None = None, lanes_per_gene: int = 0, _ops=None):
+    _TRACED = ("lin_reg_mu", "irls", "alpha_mle", "wald_test", "fit_rough_dispersions", "fit_moments_dispersions",
+               "dispersion_trend_gamma_glm", "lfc_shrink_nbinom_glm", "size_factors", "calculate_cooks")
+
+    def __init__(self, device: int = 0, n_cpus: int | None = None, lanes_per_gene: int = 0, _ops=None, trace: bool = False):
         self._ops = _ops if _ops is not None else _CudaOps(device, lanes_per_gene)
         self._n_cpus = n_cpus or 1
         self.last_irls_fallbacks = 0
+        # per-call tracing (the reference prints wall-clock per phase to stderr, dds.py:626-711 ...; a backend is better served by
+        # a record it can be asked for): one dict per plugin call -- method, milliseconds, bytes requested in / out
+        self.trace = [] if trace else None
+        if trace:
+            for name in self._TRACED:
+                setattr(self, name, self._traced(name, getattr(self, name)))
+
+    def _traced(self, name, fn):
+        import functools
+        import time
+
+        @functools.wraps(fn)
+        def call(*a, **k):
+            ops = self._ops
+            h0, d0 = getattr(ops, "h2d_bytes", 0), getattr(ops, "d2h_bytes", 0)
+            t0 = time.perf_counter()
+            out = fn(*a, **k)
+            self.trace.append({"method": name, "ms": (time.perf_counter() - t0) * 1e3,
+                               "h2d_bytes": getattr(ops, "h2d_bytes", 0) - h0, "d2h_bytes": getattr(ops, "d2h_bytes", 0) - d0})
+            return out
+
+        return call
 
     @property
     def n_cpus(self) -> int:  # noqa: D102

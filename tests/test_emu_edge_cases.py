@@ -57,3 +57,20 @@ def test_shrink_grid_fallback(backend):
 
 def test_shrink_arguments(backend):
     ec.check_shrink_arguments(backend[0])
+
+
+def test_call_trace():
+    import numpy as np
+
+    from conftest import load_golden
+    from pydeseq2_b200.workflow import deseq2_results
+
+    inf = B200Inference(_ops=EmuOps(), trace=True)
+    g = load_golden("e2e_edge_few_samples_and_outlier")
+    deseq2_results(g["counts"], g["design"], inf, g["contrast"], shrink_coeff=1)
+    seen = [t["method"] for t in inf.trace]
+    # the call order of deseq2() + summary() + lfc_shrink, refit of the replaced genes included
+    assert seen[:4] == ["fit_rough_dispersions", "fit_moments_dispersions", "lin_reg_mu", "alpha_mle"]
+    assert seen.count("alpha_mle") == 4 and seen.count("irls") == 2 and "calculate_cooks" in seen and seen[-1] == "lfc_shrink_nbinom_glm"
+    assert all(t["ms"] >= 0 for t in inf.trace)
+    assert B200Inference(_ops=EmuOps()).trace is None
