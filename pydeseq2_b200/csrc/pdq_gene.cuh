@@ -18,6 +18,17 @@
 #define PDQ_PREFETCH 1
 #endif
 
+#if defined(PDQ_EMU_LANES) && !defined(__CUDA_ARCH__)
+// host emulator with T > 1 "lanes" (one std::thread each, tests/emu/pdq_emu.cpp): the same exchange patterns as the shuffles
+namespace pdq_emu {
+double lane_sum(int si, int T, double v);
+double lane_excl_scan(int si, int T, double v);
+bool lane_any(int si, int T, bool p);
+void lane_sync(int T);
+void lane_argmax(int si, int T, double& best, int& best_n, double& best_use);  // the butterfly of cooks_gene
+}  // namespace pdq_emu
+#endif
+
 namespace pdq {
 
 struct Group {
@@ -34,6 +45,8 @@ struct Group {
             if (lane >= off) inc += t;
         }
         return inc - v;
+#elif defined(PDQ_EMU_LANES)
+        return pdq_emu::lane_excl_scan(si, T, v);
 #else
         (void)v;
         return 0.0;
@@ -42,17 +55,23 @@ struct Group {
     PDQ_HD void sync() const {
 #if defined(__CUDA_ARCH__)
         __syncwarp();
+#elif defined(PDQ_EMU_LANES)
+        pdq_emu::lane_sync(T);
 #endif
     }
     PDQ_HD double sum(double v) const {
 #if defined(__CUDA_ARCH__)
         for (int off = 16; off >= gpw; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+#elif defined(PDQ_EMU_LANES)
+        v = pdq_emu::lane_sum(si, T, v);
 #endif
         return v;
     }
     PDQ_HD bool any(bool p) const {
 #if defined(__CUDA_ARCH__)
         return __any_sync(0xffffffffu, p) != 0;
+#elif defined(PDQ_EMU_LANES)
+        return pdq_emu::lane_any(si, T, p);
 #else
         return p;
 #endif
@@ -785,7 +804,7 @@ template <int P>
 PDQ_HD double alpha_dloss(const Group& grp, const DesignS& d, const AlphaParams& prm, const int64_t* y, int64_t ld,
                           const double* mu, int64_t ld_mu, double x, double xhat, double* psi_tab, double* curv = nullptr) {
 #if defined(PDQ_EMU_COUNT_EVALS) && !defined(__CUDA_ARCH__)
-    ++g_emu_alpha_evals;  // host emulator instrumentation only
+    if (grp.si == 0) ++g_emu_alpha_evals;  // host emulator instrumentation only
 #endif
     const double a = fast_exp(x), r = fast_rcp(a), Nd = (double)d.N;
     grp.sync();  // previous evaluation's table reads are done
@@ -1360,6 +1379,8 @@ PDQ_HD void cooks_gene(const Group& grp, const DesignS& d, const CellPlan& plan,
         const double ou = __shfl_xor_sync(0xffffffffu, best_use, off);
         best_use = ou > best_use ? ou : best_use;
     }
+#elif defined(PDQ_EMU_LANES)
+    pdq_emu::lane_argmax(grp.si, grp.T, best, best_n, best_use);
 #endif
     const bool replaced = grp.sum(any_all ? 1.0 : 0.0) > 0.0;
     bool outlier = best_use > cutoff;

@@ -16,7 +16,7 @@ def _p(a, t):
 
 
 class EmuOps:
-    def __init__(self, force_optimizer=False, force_grid=False, force_shrink_grid=False):
+    def __init__(self, force_optimizer=False, force_grid=False, force_shrink_grid=False, lanes=1):
         self.lib = C.CDLL(_build.build())
         self.lib.emu_lgamma.restype = C.c_double
         self.lib.emu_lgamma.argtypes = [C.c_double]
@@ -25,10 +25,18 @@ class EmuOps:
         self.force_optimizer = int(force_optimizer)
         self.force_grid = int(force_grid)
         self.force_shrink_grid = int(force_shrink_grid)
+        self.lanes = int(lanes)  # 2..32: one std::thread per lane of a gene, the device's exchange patterns (pdq_emu.cpp)
         self.last_status = None
 
     def empty(self, shape):
         return np.empty(shape, dtype=np.float64)
+
+    def __getattribute__(self, name):
+        # the lane count is a global of the emulator library: select this object's before any of its calls
+        if name in ("lin_reg_mu", "irls", "alpha_mle", "wald_test", "rough", "moments", "mom_from_counts", "cooks", "lfc_shrink"):
+            lib = object.__getattribute__(self, "lib")
+            assert lib.emu_set_lanes(object.__getattribute__(self, "lanes")) == 0
+        return object.__getattribute__(self, name)
 
     def lin_reg_mu(self, counts, ld, N, G, sf, X, p, min_mu, mu):
         rc = self.lib.emu_lin_reg_mu(_p(counts, i64p), C.c_int64(ld), N, G, _p(sf, f64p), _p(X, f64p), p, C.c_double(min_mu),

@@ -6,13 +6,21 @@
 // the dispersion, Cholesky algebra, special functions -- against the oracle without a GPU.
 // It is built by tests/emu/build.py into tests/emu/_build/ and loaded only by tests/; the product
 // (pydeseq2_b200) never loads it and has no CPU fallback.
+//
+// emu_set_lanes(T) switches to T = 2..32 cooperating "lanes" per gene, one std::thread each: Group::sum / excl_scan / any /
+// sync then exchange through a shared board with the device's own patterns (xor butterfly over the lane index, Hillis-Steele
+// scan), so the lane-cooperative code paths -- strided sample walks, split table builds, replicated control flow -- and the
+// device's summation ORDER are exercised on the CPU as well.
 #include <stdint.h>
 #include <string.h>
 
+#include <barrier>
+#include <thread>
 #include <vector>
 
 extern long g_emu_alpha_evals;
 #define PDQ_EMU_COUNT_EVALS 1
+#define PDQ_EMU_LANES 1
 #include "../../pydeseq2_b200/csrc/pdq_gene.cuh"
 #include "../../pydeseq2_b200/csrc/pdq_host_linalg.h"
 #include "../../pydeseq2_b200/csrc/pdq_trend.cuh"
@@ -20,6 +28,75 @@ extern long g_emu_alpha_evals;
 
 long g_emu_alpha_evals = 0;
 using namespace pdq;
+
+// ---- lane team: what a warp's shuffles and votes become on the host ------------------------------------------------------
+namespace {
+struct LaneTeam {
+    explicit LaneTeam(int T) : bar(T) {}
+    std::barrier<> bar;
+    double board[32], board2[32];
+    int flags[32];
+};
+thread_local LaneTeam* t_team = nullptr;
+int g_lanes = 1;
+}  // namespace
+
+namespace pdq_emu {
+// every lane ends with the same total, accumulated in the order of the device's xor butterfly (largest stride first)
+double lane_sum(int si, int T, double v) {
+    if (T == 1 || !t_team) return v;
+    for (int s = T >> 1; s >= 1; s >>= 1) {
+        t_team->board[si] = v;
+        t_team->bar.arrive_and_wait();
+        const double o = t_team->board[si ^ s];
+        t_team->bar.arrive_and_wait();
+        v += o;
+    }
+    return v;
+}
+double lane_excl_scan(int si, int T, double v) {
+    if (T == 1 || !t_team) return 0.0;
+    double inc = v;
+    for (int s = 1; s < T; s <<= 1) {
+        t_team->board[si] = inc;
+        t_team->bar.arrive_and_wait();
+        const double o = (si >= s) ? t_team->board[si - s] : 0.0;
+        t_team->bar.arrive_and_wait();
+        if (si >= s) inc += o;
+    }
+    return inc - v;
+}
+bool lane_any(int si, int T, bool p) {
+    if (T == 1 || !t_team) return p;
+    t_team->flags[si] = p ? 1 : 0;
+    t_team->bar.arrive_and_wait();
+    int any = 0;
+    for (int i = 0; i < T; ++i) any |= t_team->flags[i];
+    t_team->bar.arrive_and_wait();
+    return any != 0;
+}
+void lane_sync(int T) {
+    if (T == 1 || !t_team) return;
+    t_team->bar.arrive_and_wait();
+}
+void lane_argmax(int si, int T, double& best, int& best_n, double& best_use) {
+    if (T == 1 || !t_team) return;
+    for (int s = T >> 1; s >= 1; s >>= 1) {
+        t_team->board[si] = best;
+        t_team->flags[si] = best_n;
+        t_team->board2[si] = best_use;
+        t_team->bar.arrive_and_wait();
+        const double ob = t_team->board[si ^ s], ou = t_team->board2[si ^ s];
+        const int on = t_team->flags[si ^ s];
+        t_team->bar.arrive_and_wait();
+        if (ob > best || (ob == best && on < best_n)) {
+            best = ob;
+            best_n = on;
+        }
+        best_use = ou > best_use ? ou : best_use;
+    }
+}
+}  // namespace pdq_emu
 
 namespace {
 
@@ -58,6 +135,26 @@ SmallMat<P> pinv_of(const Pack& k) {
 
 const Group kOne{0, 1, 32};
 
+// runs f(Group) once per lane of one gene: directly for one lane, on T threads sharing a LaneTeam otherwise
+template <class F>
+void with_lanes(F&& f) {
+    const int T = g_lanes;
+    if (T <= 1) {
+        t_team = nullptr;
+        f(kOne);
+        return;
+    }
+    LaneTeam team(T);
+    std::vector<std::thread> th;
+    th.reserve((size_t)T);
+    for (int si = 0; si < T; ++si)
+        th.emplace_back([&team, &f, si, T] {
+            t_team = &team;
+            f(Group{si, T, 32 / T});
+        });
+    for (auto& t : th) t.join();
+}
+
 #define EMU_DISPATCH(p, ...)                               \
     switch (p) {                                           \
         case 1: { constexpr int P = 1; __VA_ARGS__; } break; \
@@ -80,7 +177,8 @@ int emu_lin_reg_mu(const int64_t* counts, int64_t ld, int N, int G, const double
     Pack k = make_pack(X, sf, N, p);
     EMU_DISPATCH(p, {
         const SmallMat<P> pi = pinv_of<P>(k);
-        for (int g = 0; g < G; ++g) linmu_gene<P>(kOne, k.d, pi, counts + g, ld, min_mu, mu + g, G, true);
+        for (int g = 0; g < G; ++g)
+            with_lanes([&](const Group& grp) { linmu_gene<P>(grp, k.d, pi, counts + g, ld, min_mu, mu + g, G, true); });
     });
     return 0;
 }
@@ -94,12 +192,16 @@ int emu_irls(const int64_t* counts, int64_t ld, int N, int G, const double* sf, 
         const IrlsParams prm{min_mu, beta_tol, min_beta, max_beta, maxiter, k.full_rank, design_distinct_rows(X, N, p, 16) <= 16};
         double lg_tab[kPsiK];
         for (int g = 0; g < G; ++g) {
-            irls_gene<P>(kOne, k.d, pi, prm, counts + g, ld, disp[g], beta + (size_t)g * P, mu + g, hat + g, G, conv + g,
-                         status + g, true, lg_tab, kLogFact);
+            with_lanes([&](const Group& grp) {
+                irls_gene<P>(grp, k.d, pi, prm, counts + g, ld, disp[g], beta + (size_t)g * P, mu + g, hat + g, G, conv + g,
+                             status + g, true, lg_tab, kLogFact);
+            });
             if (force_optimizer) status[g] = kIrlsNeedsOptimizer;
             if (status[g] == kIrlsNeedsOptimizer)
-                irls_optimizer_gene<P>(kOne, k.d, pi, prm, counts + g, ld, disp[g], beta + (size_t)g * P, mu + g, hat + g,
-                                       G, conv + g, true);
+                with_lanes([&](const Group& grp) {
+                    irls_optimizer_gene<P>(grp, k.d, pi, prm, counts + g, ld, disp[g], beta + (size_t)g * P, mu + g, hat + g, G,
+                                           conv + g, true);
+                });
         }
     });
     return 0;
@@ -113,13 +215,17 @@ int emu_alpha_mle(const int64_t* counts, int64_t ld, int N, int G, const double*
         const AlphaParams prm{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg};
         double psi[2 * kPsiK];
         for (int g = 0; g < G; ++g) {
-            alpha_gene<P>(kOne, k.d, prm, counts + g, ld, mu + g, ld_mu, alpha_hat[g], alpha + g, conv + g, status + g, true, psi);
+            with_lanes([&](const Group& grp) {
+                alpha_gene<P>(grp, k.d, prm, counts + g, ld, mu + g, ld_mu, alpha_hat[g], alpha + g, conv + g, status + g, true, psi);
+            });
             if (force_grid) {
                 status[g] = kAlphaNeedsGrid;
                 conv[g] = 0.0;
             }
             if (status[g] == kAlphaNeedsGrid)
-                alpha_grid_gene<P>(kOne, k.d, prm.lo, prm.hi, counts + g, ld, mu + g, ld_mu, alpha + g, true);
+                with_lanes([&](const Group& grp) {
+                    alpha_grid_gene<P>(grp, k.d, prm.lo, prm.hi, counts + g, ld, mu + g, ld_mu, alpha + g, true);
+                });
         }
     });
     return 0;
@@ -133,13 +239,17 @@ int emu_lfc_shrink(const double* X, const int64_t* counts, int64_t ld, int N, in
     const ShrinkParams prm{1.0 / (prior_no_shrink_scale * prior_no_shrink_scale), prior_scale * prior_scale, shrink_index};
     EMU_DISPATCH(p, {
         for (int g = 0; g < G; ++g)
-            shrink_gene<P>(kOne, k.d, prm, counts + g, ld, size[g], lfcs + (size_t)g * P, inv_hessians + (size_t)g * P * P, conv + g,
-                           status + g, true, force_grid != 0);
+            with_lanes([&](const Group& grp) {
+                shrink_gene<P>(grp, k.d, prm, counts + g, ld, size[g], lfcs + (size_t)g * P, inv_hessians + (size_t)g * P * P,
+                               conv + g, status + g, true, force_grid != 0);
+            });
     });
     if (p == 2)
         for (int g = 0; g < G; ++g)
             if (status[g] == kShrinkNeedsGrid)
-                shrink_grid_gene(kOne, k.d, prm, counts + g, ld, size[g], lfcs + (size_t)g * 2, inv_hessians + (size_t)g * 4, true);
+                with_lanes([&](const Group& grp) {
+                    shrink_grid_gene(grp, k.d, prm, counts + g, ld, size[g], lfcs + (size_t)g * 2, inv_hessians + (size_t)g * 4, true);
+                });
     return 0;
 }
 
@@ -154,7 +264,9 @@ int emu_wald_test(const double* X, int N, int p, const double* disp, const doubl
         prm.lfc_null = lfc_null;
         prm.alt = alt;
         for (int g = 0; g < G; ++g)
-            wald_gene<P>(kOne, k.d, prm, disp[g], lfc + (size_t)g * P, mu + g, ld_mu, pv + g, stat + g, se + g, true);
+            with_lanes([&](const Group& grp) {
+                wald_gene<P>(grp, k.d, prm, disp[g], lfc + (size_t)g * P, mu + g, ld_mu, pv + g, stat + g, se + g, true);
+            });
     });
     return 0;
 }
@@ -163,7 +275,11 @@ int emu_rough(const double* normed, int64_t ld, int N, int G, const double* X, i
     Pack k = make_pack(X, nullptr, N, p);
     EMU_DISPATCH(p, {
         const SmallMat<P> pi = pinv_of<P>(k);
-        for (int g = 0; g < G; ++g) alpha[g] = rough_disp_gene<P>(kOne, k.d, pi, NormedF64{normed + g, ld});
+        for (int g = 0; g < G; ++g)
+            with_lanes([&](const Group& grp) {
+                const double a = rough_disp_gene<P>(grp, k.d, pi, NormedF64{normed + g, ld});
+                if (grp.si == 0) alpha[g] = a;
+            });
     });
     return 0;
 }
@@ -172,10 +288,15 @@ int emu_moments(const double* normed, int64_t ld, int N, int G, const double* sf
     std::vector<double> ones((size_t)N, 1.0);
     Pack k = make_pack(ones.data(), sf, N, 1);
     for (int g = 0; g < G; ++g) {
-        double mean;
-        bool az;
-        alpha[g] = moments_disp_gene(kOne, k.d, NormedF64{normed + g, ld}, k.s_mean_inv, mean, az);
-        all_zero[g] = az ? 1.0 : 0.0;
+        with_lanes([&](const Group& grp) {
+            double mean;
+            bool az;
+            const double a = moments_disp_gene(grp, k.d, NormedF64{normed + g, ld}, k.s_mean_inv, mean, az);
+            if (grp.si == 0) {
+                alpha[g] = a;
+                all_zero[g] = az ? 1.0 : 0.0;
+            }
+        });
     }
     return 0;
 }
@@ -186,8 +307,10 @@ int emu_mom_from_counts(const int64_t* counts, int64_t ld, int N, int G, const d
     EMU_DISPATCH(p, {
         const SmallMat<P> pi = pinv_of<P>(k);
         for (int g = 0; g < G; ++g)
-            mom_fused_gene<P>(kOne, k.d, pi, counts + g, ld, k.s_mean_inv, min_disp, max_disp, min_mu, alpha + g, normed_mean + g,
-                              mu_hat ? mu_hat + g : nullptr, G, true);
+            with_lanes([&](const Group& grp) {
+                mom_fused_gene<P>(grp, k.d, pi, counts + g, ld, k.s_mean_inv, min_disp, max_disp, min_mu, alpha + g, normed_mean + g,
+                                  mu_hat ? mu_hat + g : nullptr, G, true);
+            });
     });
     return 0;
 }
@@ -214,8 +337,10 @@ int emu_cooks(const int64_t* counts, int64_t ld, int N, int G, const double* sf,
     std::vector<double> vals((size_t)2 * nf);
     EMU_DISPATCH(p, {
         for (int g = 0; g < G; ++g)
-            cooks_gene<P>(kOne, k.d, cp, counts + g, ld, mu + g, hat + g, ld2, cutoff, vals.data(), vals.data() + nf,
-                          cooks ? cooks + g : nullptr, G, disp + g, outlier + g, replaced + g, true);
+            with_lanes([&](const Group& grp) {
+                cooks_gene<P>(grp, k.d, cp, counts + g, ld, mu + g, hat + g, ld2, cutoff, vals.data(), vals.data() + nf,
+                              cooks ? cooks + g : nullptr, G, disp + g, outlier + g, replaced + g, true);
+            });
     });
     return 0;
 }
@@ -239,6 +364,12 @@ int emu_size_factors(const int64_t* counts, int64_t ld, int N, int G, double* sf
         }
         sf[n] = exp(median_of(red, row.data(), (size_t)G, cnt, false, 0.0, hist));
     }
+    return 0;
+}
+
+int emu_set_lanes(int lanes) {
+    if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return -1;
+    g_lanes = lanes;
     return 0;
 }
 

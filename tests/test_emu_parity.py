@@ -114,3 +114,34 @@ def test_fused_mom_kernel(name):
 @pytest.mark.parametrize("name", SHRINK)
 def test_emu_lfc_shrink(inf, name):
     check_shrink(inf, load_golden(name))
+
+
+# ---- the same algorithms with T > 1 cooperating lanes per gene (one thread each; tests/emu/pdq_emu.cpp): the strided sample walks,
+# ---- the split table builds and the replicated control flow of the kernels, with the device's own reduction order
+@pytest.mark.parametrize("lanes,name", [(2, "calls_two_level_n24"), (8, "calls_two_level_n24"), (4, "calls_factorial_n30"),
+                                        (8, "calls_continuous_n40"), (4, "calls_five_columns_n36"), (4, "calls_few_samples_n4"),
+                                        (8, "calls_large_counts_n12"), (2, "calls_intercept_n10")])
+def test_emu_calls_multi_lane(lanes, name):
+    check_calls(B200Inference(_ops=EmuOps(lanes=lanes)), load_golden(name), **({"tol_alpha": 1e-4} if "large_counts" in name else {}))
+
+
+@pytest.mark.parametrize("lanes,name", [(4, "shrink_two_level_n24"), (8, "shrink_five_columns_n36"), (2, "shrink_few_samples_n4"),
+                                        (8, "shrinktape_continuous"), (16, "shrink_two_level_n200")])
+def test_emu_lfc_shrink_multi_lane(lanes, name):
+    check_shrink(B200Inference(_ops=EmuOps(lanes=lanes)), load_golden(name))
+
+
+@pytest.mark.parametrize("lanes,name", [(4, "tape_multi_factor_outliers"), (8, "tape_wide")])
+def test_emu_tape_multi_lane(lanes, name):
+    check_tape(B200Inference(_ops=EmuOps(lanes=lanes)), load_golden(name), name)
+
+
+def test_lane_count_does_not_change_results():
+    """Only the summation tree differs between lane-group widths (cf. the GPU suite's test of the same name)."""
+    g = load_golden("calls_two_level_n200")
+    ref_full = B200Inference(_ops=EmuOps(lanes=1)).irls(g["counts"], g["sf"], g["X"], g["mom"], 0.5, 1e-8)
+    for lanes in (2, 16, 32):
+        got = B200Inference(_ops=EmuOps(lanes=lanes)).irls(g["counts"][:, :24], g["sf"], g["X"], g["mom"][:24], 0.5, 1e-8)
+        ref = tuple(np.ascontiguousarray(r[..., :24]) if r.shape[-1] == g["counts"].shape[1] else r[:24] for r in ref_full)
+        for a, b in zip(got, ref):
+            np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-13)
