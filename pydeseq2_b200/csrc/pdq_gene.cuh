@@ -17,6 +17,9 @@
 #ifndef PDQ_PREFETCH
 #define PDQ_PREFETCH 1
 #endif
+#ifndef PDQ_IRLS_UNROLL
+#define PDQ_IRLS_UNROLL 2
+#endif
 
 #if defined(PDQ_EMU_LANES) && !defined(__CUDA_ARCH__)
 // host emulator with T > 1 "lanes" (one std::thread each, tests/emu/pdq_emu.cpp): the same exchange patterns as the shuffles
@@ -251,7 +254,22 @@ PDQ_HD bool irls_sweep_t(const Group& grp, const DesignS& d, const int64_t* y, i
     // two samples per trip, straight-line: their exp / log / reciprocal chains interleave on the FP64 pipe.  The counts of the
     // NEXT trip are requested before this trip's arithmetic starts (register double buffer): the L1/L2 latency of the strided
     // column walk hides behind ~350 instructions instead of stalling the first use (long-scoreboard stalls were 22 %).
-#if PDQ_PREFETCH
+#if PDQ_IRLS_UNROLL == 4
+    // experiment (default off): four samples per trip -- more independent exp / log / reciprocal chains in flight per lane
+    // against the fixed-latency dependency stalls of the capture; costs registers
+    for (; n + 3 * T < d.N; n += 4 * T, yp += 4 * ystep, xp += 4 * T) {
+        const double y0 = (double)yp[0], y1 = (double)yp[ystep], y2 = (double)yp[2 * ystep], y3 = (double)yp[3 * ystep];
+        irls_sample<P, NB, MEMO>(xp, d.Npad, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp + T, d.Npad, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp + 2 * T, d.Npad, y2, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp + 3 * T, d.Npad, y3, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+    }
+    for (; n + T < d.N; n += 2 * T, yp += 2 * ystep, xp += 2 * T) {
+        const double y0 = (double)yp[0], y1 = (double)yp[ystep];
+        irls_sample<P, NB, MEMO>(xp, d.Npad, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp + T, d.Npad, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+    }
+#elif PDQ_PREFETCH
     int64_t c0 = (n + T < d.N) ? yp[0] : 0, c1 = (n + T < d.N) ? yp[ystep] : 0;
     for (; n + T < d.N; n += 2 * T, yp += 2 * ystep, xp += 2 * T) {
         const double y0 = (double)c0, y1 = (double)c1;
