@@ -396,7 +396,7 @@ def gen_e2e(name, N, G, design_kind, seed, n_outliers, contrast_index=None, **st
     run_e2e(name, counts, X, contrast, **stats_kwargs)
 
 
-def run_e2e(name, counts, X, contrast, **stats_kwargs):
+def run_e2e(name, counts, X, contrast, r_csv=None, **stats_kwargs):
     from pydeseq2.dds import DeseqDataSet
     from pydeseq2.ds import DeseqStats
 
@@ -421,8 +421,13 @@ def run_e2e(name, counts, X, contrast, **stats_kwargs):
                final_genewise=dds.var["genewise_dispersions"].values, final_fitted=dds.var["fitted_dispersions"].values,
                final_size_factors=dds.obs["size_factors"].values, final_replaced=np.asarray(dds.var["replaced"], dtype=float),
                final_refitted=np.asarray(dds.var["refitted"], dtype=float), final_cooks_outlier=np.asarray(dds.cooks_outlier(), dtype=float),
+               alt_hypothesis=np.array(stats_kwargs.get("alt_hypothesis") or ""), lfc_null=np.float64(stats_kwargs.get("lfc_null", 0.0)),
                independent_filter=np.float64(stats_kwargs.get("independent_filter", True)),
                cooks_filter=np.float64(stats_kwargs.get("cooks_filter", True)), alpha=np.float64(stats_kwargs.get("alpha", 0.05)))
+    if r_csv:
+        r = pd.read_csv(r_csv, index_col=0)
+        out.update(r_log2FoldChange=r["log2FoldChange"].values, r_stat=r["stat"].values, r_pvalue=r["pvalue"].values,
+                   r_padj=r["padj"].values)
     np.savez_compressed(os.path.join(OUT, f"e2e_{name}.npz"), **out)
     print(f"e2e_{name}: N={N} G={G} p={p} replaced={int(out['final_replaced'].sum())} refitted={int(out['final_refitted'].sum())} "
           f"cooks_outlier={int(out['final_cooks_outlier'].sum())} padj<alpha={int((res['padj'] < 0.05).sum())} "
@@ -456,6 +461,17 @@ def main_e2e_edge():
     run_e2e("edge_new_all_zero_gene", c.values.astype(np.int64), design(meta.loc[keep]), np.array([0.0, 1.0]))
 
 
+def main_e2e_alt():
+    """The reference's alternative-hypothesis test (tests/test_pydeseq2.py:180-225) on its shipped dataset, R tables alongside."""
+    counts = pd.read_csv(f"{REF}/datasets/synthetic/test_counts.csv", index_col=0).T
+    meta = pd.read_csv(f"{REF}/datasets/synthetic/test_metadata.csv", index_col=0)
+    X = np.stack([np.ones(len(meta)), indicator(meta["condition"], "B").values], axis=1)
+    for alt in ("lessAbs", "greaterAbs", "less", "greater"):
+        run_e2e(f"alt_{alt}", counts.values.astype(np.int64), X, np.array([0.0, 1.0]),
+                r_csv=f"{REF}/tests/data/single_factor/r_test_res_{alt}.csv",
+                alt_hypothesis=alt, lfc_null=-0.5 if alt == "less" else 0.5)
+
+
 def main_e2e():
     gen_e2e("two_level_n24", 24, 400, "two_level", 11, 12)               # cells of 12 >= 7: outliers are replaced and refitted
     gen_e2e("factorial_n20", 20, 400, "factorial", 12, 12)               # cells of 5 < 7: outliers lose their p-value instead
@@ -467,8 +483,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "e2e":  # end-to-end fixtures only
         main_e2e()
         main_e2e_edge()
+        main_e2e_alt()
     elif len(sys.argv) > 1 and sys.argv[1] == "e2e_edge":
         main_e2e_edge()
+    elif len(sys.argv) > 1 and sys.argv[1] == "e2e_alt":
+        main_e2e_alt()
     elif len(sys.argv) > 1 and sys.argv[1] == "shrink":  # apeGLM fixtures only (reads the existing calls_* fixtures)
         main_shrink()
     else:
@@ -476,3 +495,4 @@ if __name__ == "__main__":
         main_shrink()
         main_e2e()
         main_e2e_edge()
+        main_e2e_alt()

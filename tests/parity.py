@@ -129,7 +129,9 @@ def check_shrink(inf, g, tol=TOL_SHRINK):
 
 E2E = ["e2e_two_level_n24", "e2e_factorial_n20", "e2e_two_level_n16_bh", "e2e_continuous_n30",
        # the reference's orchestrator-level edge cases (its tests/test_edge_cases.py:323-465)
-       "e2e_edge_few_samples", "e2e_edge_few_samples_and_outlier", "e2e_edge_new_all_zero_gene"]
+       "e2e_edge_few_samples", "e2e_edge_few_samples_and_outlier", "e2e_edge_new_all_zero_gene",
+       # its alternative-hypothesis test (tests/test_pydeseq2.py:180-225), R tables alongside
+       "e2e_alt_lessAbs", "e2e_alt_greaterAbs", "e2e_alt_less", "e2e_alt_greater"]
 TAPES_E2E = ["tape_single_factor", "tape_multi_factor", "tape_continuous", "tape_wide", "tape_multi_factor_outliers"]
 
 
@@ -154,6 +156,8 @@ def check_e2e(inf, g, rtol, name="", max_frac=0.0):
     kw = {}
     if "independent_filter" in g:
         kw = dict(independent_filter=bool(g["independent_filter"]), cooks_filter=bool(g["cooks_filter"]), alpha=float(g["alpha"]))
+    if "alt_hypothesis" in g:
+        kw.update(alt_hypothesis=str(g["alt_hypothesis"]) or None, lfc_null=float(g["lfc_null"]))
     r = deseq2_results(g["counts"], g["design"], inf, g["contrast"], **kw)
     # decisions first: they are discrete, so they must agree exactly
     np.testing.assert_array_equal(r.replaced, g["final_replaced"] == 1, err_msg="replaced genes")
@@ -178,4 +182,12 @@ def check_e2e(inf, g, rtol, name="", max_frac=0.0):
         assert_mostly_close(r.log2_fold_change, g["final_log2FoldChange"], rtol, "log2FoldChange", 1e-8, max_frac)
         assert_mostly_close(r.lfc_se, g["final_lfcSE"], rtol, "lfcSE", 0.0, max_frac)
         assert_close(r.fitted_dispersions, g["final_fitted"], rtol, "fitted dispersions")
+    if "r_stat" in g and "r_padj" in g:  # the reference's own criteria against R DESeq2 (2 %; |stat| for lessAbs; p-values where stat != 0)
+        assert np.array_equal(np.isnan(r.pvalue), np.isnan(g["r_pvalue"])) and np.array_equal(np.isnan(r.padj), np.isnan(g["r_padj"]))
+        assert np.max(np.abs(g["r_log2FoldChange"] - r.log2_fold_change) / np.abs(g["r_log2FoldChange"])) < 0.02
+        st = np.abs(r.stat) if kw.get("alt_hypothesis") == "lessAbs" else r.stat
+        with np.errstate(invalid="ignore", divide="ignore"):  # 0/0 where both statistics are exactly 0 (pandas' max skips NaN)
+            assert np.nanmax(np.abs(g["r_stat"] - st) / np.abs(g["r_stat"])) < 0.02
+        nzs = g["r_stat"] != 0
+        assert np.max(np.abs(g["r_pvalue"][nzs] - r.pvalue[nzs]) / g["r_pvalue"][nzs]) < 0.02
     return r
