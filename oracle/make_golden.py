@@ -396,7 +396,7 @@ def gen_e2e(name, N, G, design_kind, seed, n_outliers, contrast_index=None, **st
     run_e2e(name, counts, X, contrast, **stats_kwargs)
 
 
-def run_e2e(name, counts, X, contrast, r_csv=None, **stats_kwargs):
+def run_e2e(name, counts, X, contrast, r_csv=None, dds_kwargs=None, **stats_kwargs):
     from pydeseq2.dds import DeseqDataSet
     from pydeseq2.ds import DeseqStats
 
@@ -409,7 +409,7 @@ def run_e2e(name, counts, X, contrast, r_csv=None, **stats_kwargs):
     inf = ref_inference()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        dds = DeseqDataSet(counts=counts_df, metadata=meta, design=design_df, inference=inf, quiet=True)
+        dds = DeseqDataSet(counts=counts_df, metadata=meta, design=design_df, inference=inf, quiet=True, **(dds_kwargs or {}))
         dds.deseq2()
         ds = DeseqStats(dds, contrast=contrast, inference=inf, quiet=True, **stats_kwargs)
         ds.summary()
@@ -419,8 +419,10 @@ def run_e2e(name, counts, X, contrast, r_csv=None, **stats_kwargs):
                final_stat=res["stat"].values, final_pvalue=res["pvalue"].values, final_padj=res["padj"].values,
                final_LFC=dds.varm["LFC"].values, final_dispersions=dds.var["dispersions"].values,
                final_genewise=dds.var["genewise_dispersions"].values, final_fitted=dds.var["fitted_dispersions"].values,
-               final_size_factors=dds.obs["size_factors"].values, final_replaced=np.asarray(dds.var["replaced"], dtype=float),
-               final_refitted=np.asarray(dds.var["refitted"], dtype=float), final_cooks_outlier=np.asarray(dds.cooks_outlier(), dtype=float),
+               final_size_factors=dds.obs["size_factors"].values, final_replaced=np.asarray(dds.var["replaced"], dtype=float) if "replaced" in dds.var else np.zeros(G),
+               final_refitted=np.asarray(dds.var["refitted"], dtype=float) if "refitted" in dds.var else np.zeros(G), final_cooks_outlier=np.asarray(dds.cooks_outlier(), dtype=float),
+               fit_type=np.array((dds_kwargs or {}).get("fit_type", "parametric")),
+               refit_cooks=np.float64((dds_kwargs or {}).get("refit_cooks", True)),
                alt_hypothesis=np.array(stats_kwargs.get("alt_hypothesis") or ""), lfc_null=np.float64(stats_kwargs.get("lfc_null", 0.0)),
                independent_filter=np.float64(stats_kwargs.get("independent_filter", True)),
                cooks_filter=np.float64(stats_kwargs.get("cooks_filter", True)), alpha=np.float64(stats_kwargs.get("alpha", 0.05)))
@@ -470,6 +472,13 @@ def main_e2e_alt():
         run_e2e(f"alt_{alt}", counts.values.astype(np.int64), X, np.array([0.0, 1.0]),
                 r_csv=f"{REF}/tests/data/single_factor/r_test_res_{alt}.csv",
                 alt_hypothesis=alt, lfc_null=-0.5 if alt == "less" else 0.5)
+    # mean-type dispersion trend (tests/test_pydeseq2.py:121-145) and no Cook's refit on data with outliers (:228-253 + :434-467)
+    run_e2e("mean_fit", counts.values.astype(np.int64), X, np.array([0.0, 1.0]),
+            r_csv=f"{REF}/tests/data/single_factor/r_test_res_mean_curve.csv", dds_kwargs={"fit_type": "mean"})
+    co = counts.copy()
+    co.loc["sample1", "gene1"] = 2000
+    co.loc["sample11", "gene7"] = 1000
+    run_e2e("no_refit_outliers", co.values.astype(np.int64), X, np.array([0.0, 1.0]), dds_kwargs={"refit_cooks": False})
 
 
 def main_e2e():

@@ -131,7 +131,9 @@ E2E = ["e2e_two_level_n24", "e2e_factorial_n20", "e2e_two_level_n16_bh", "e2e_co
        # the reference's orchestrator-level edge cases (its tests/test_edge_cases.py:323-465)
        "e2e_edge_few_samples", "e2e_edge_few_samples_and_outlier", "e2e_edge_new_all_zero_gene",
        # its alternative-hypothesis test (tests/test_pydeseq2.py:180-225), R tables alongside
-       "e2e_alt_lessAbs", "e2e_alt_greaterAbs", "e2e_alt_less", "e2e_alt_greater"]
+       "e2e_alt_lessAbs", "e2e_alt_greaterAbs", "e2e_alt_less", "e2e_alt_greater",
+       # mean-type trend (:121-145) and outliers without the Cook's refit (:228-253)
+       "e2e_mean_fit", "e2e_no_refit_outliers"]
 TAPES_E2E = ["tape_single_factor", "tape_multi_factor", "tape_continuous", "tape_wide", "tape_multi_factor_outliers"]
 
 
@@ -158,6 +160,8 @@ def check_e2e(inf, g, rtol, name="", max_frac=0.0):
         kw = dict(independent_filter=bool(g["independent_filter"]), cooks_filter=bool(g["cooks_filter"]), alpha=float(g["alpha"]))
     if "alt_hypothesis" in g:
         kw.update(alt_hypothesis=str(g["alt_hypothesis"]) or None, lfc_null=float(g["lfc_null"]))
+    if "fit_type" in g:
+        kw.update(fit_type=str(g["fit_type"]), refit_cooks=bool(g["refit_cooks"]))
     r = deseq2_results(g["counts"], g["design"], inf, g["contrast"], **kw)
     # decisions first: they are discrete, so they must agree exactly
     np.testing.assert_array_equal(r.replaced, g["final_replaced"] == 1, err_msg="replaced genes")
