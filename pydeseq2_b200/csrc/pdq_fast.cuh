@@ -31,6 +31,54 @@ PDQ_CONST double kLn2Hi = 6.93147180369123816490e-01;  // ln2 with the low 21 bi
 PDQ_CONST double kLn2Lo = 1.90821492927058770002e-10;
 PDQ_CONST double kLog2e = 1.44269504088896338700e+00;
 
+// Polynomial tails.  Default: Horner (fewest instructions, one dependent DFMA per coefficient).  -DPDQ_ESTRIN=1 (experiment,
+// default off): Estrin's scheme -- pairs, then powers of the square -- halves the dependent depth (log: 6 -> 4, exp: 9 -> 5) for two
+// or three extra multiplications; the kernels stall on fixed-latency dependencies, not on FP64 issue slots.
+#ifndef PDQ_ESTRIN
+#define PDQ_ESTRIN 0
+#endif
+
+PDQ_HD double poly_log_g(double s) {
+#if PDQ_ESTRIN
+    const double s2 = s * s;
+    const double p01 = fma(kLogG[1], s, kLogG[0]), p23 = fma(kLogG[3], s, kLogG[2]), p45 = fma(kLogG[5], s, kLogG[4]);
+    const double s4 = s2 * s2;
+    const double lo = fma(p23, s2, p01), hi = fma(kLogG[6], s2, p45);
+    return fma(hi, s4, lo);
+#else
+    double g = kLogG[6];
+    g = fma(g, s, kLogG[5]);
+    g = fma(g, s, kLogG[4]);
+    g = fma(g, s, kLogG[3]);
+    g = fma(g, s, kLogG[2]);
+    g = fma(g, s, kLogG[1]);
+    return fma(g, s, kLogG[0]);
+#endif
+}
+
+PDQ_HD double poly_exp_q(double r) {
+#if PDQ_ESTRIN
+    const double r2 = r * r;
+    const double p01 = fma(kExpQ[1], r, kExpQ[0]), p23 = fma(kExpQ[3], r, kExpQ[2]), p45 = fma(kExpQ[5], r, kExpQ[4]);
+    const double p67 = fma(kExpQ[7], r, kExpQ[6]), p89 = fma(kExpQ[9], r, kExpQ[8]);
+    const double r4 = r2 * r2;
+    const double q03 = fma(p23, r2, p01), q47 = fma(p67, r2, p45);
+    const double r8 = r4 * r4;
+    return fma(p89, r8, fma(q47, r4, q03));
+#else
+    double q = kExpQ[9];
+    q = fma(q, r, kExpQ[8]);
+    q = fma(q, r, kExpQ[7]);
+    q = fma(q, r, kExpQ[6]);
+    q = fma(q, r, kExpQ[5]);
+    q = fma(q, r, kExpQ[4]);
+    q = fma(q, r, kExpQ[3]);
+    q = fma(q, r, kExpQ[2]);
+    q = fma(q, r, kExpQ[1]);
+    return fma(q, r, kExpQ[0]);
+#endif
+}
+
 // 1/d for normal finite d (|d| in [2^-1000, 2^1000]): hardware seed + two Newton-Raphson steps
 PDQ_HD double fast_rcp(double d) {
 #if defined(__CUDA_ARCH__)
@@ -83,13 +131,7 @@ PDQ_HD double fast_log(double x) {
 #endif
     const double f = fast_div(m - 1.0, m + 1.0);
     const double s = f * f;
-    double g = kLogG[6];
-    g = fma(g, s, kLogG[5]);
-    g = fma(g, s, kLogG[4]);
-    g = fma(g, s, kLogG[3]);
-    g = fma(g, s, kLogG[2]);
-    g = fma(g, s, kLogG[1]);
-    g = fma(g, s, kLogG[0]);
+    const double g = poly_log_g(s);
     const double f2 = f + f;
     // e*ln2_hi is exact (|e| < 2^11, ln2_hi has 21 trailing zero bits)
     return fma(ed, kLn2Hi, f2 + fma(f2 * s, g, ed * kLn2Lo));
@@ -113,13 +155,7 @@ PDQ_HD double fast_log_nb(double x) {
     const double ed = (double)e;
     const double f = fast_div(m - 1.0, m + 1.0);
     const double s = f * f;
-    double g = kLogG[6];
-    g = fma(g, s, kLogG[5]);
-    g = fma(g, s, kLogG[4]);
-    g = fma(g, s, kLogG[3]);
-    g = fma(g, s, kLogG[2]);
-    g = fma(g, s, kLogG[1]);
-    g = fma(g, s, kLogG[0]);
+    const double g = poly_log_g(s);
     const double f2 = f + f;
     return fma(ed, kLn2Hi, f2 + fma(f2 * s, g, ed * kLn2Lo));
 #else
@@ -131,16 +167,7 @@ PDQ_HD double fast_exp_nb(double x) {
 #if defined(__CUDA_ARCH__)
     const double kd = rint(x * kLog2e);
     const double r = fma(-kd, kLn2Lo, fma(-kd, kLn2Hi, x));
-    double q = kExpQ[9];
-    q = fma(q, r, kExpQ[8]);
-    q = fma(q, r, kExpQ[7]);
-    q = fma(q, r, kExpQ[6]);
-    q = fma(q, r, kExpQ[5]);
-    q = fma(q, r, kExpQ[4]);
-    q = fma(q, r, kExpQ[3]);
-    q = fma(q, r, kExpQ[2]);
-    q = fma(q, r, kExpQ[1]);
-    q = fma(q, r, kExpQ[0]);
+    const double q = poly_exp_q(r);
     const double p = fma(r * r, q, r) + 1.0;
     return p * __hiloint2double(((int)kd + 1023) << 20, 0);
 #else
@@ -152,16 +179,7 @@ PDQ_HD double fast_exp(double x) {
     if (!(fabs(x) < 700.0)) return exp(x);  // overflow/underflow edge, inf, NaN: libm/libdevice semantics
     const double kd = rint(x * kLog2e);
     const double r = fma(-kd, kLn2Lo, fma(-kd, kLn2Hi, x));
-    double q = kExpQ[9];
-    q = fma(q, r, kExpQ[8]);
-    q = fma(q, r, kExpQ[7]);
-    q = fma(q, r, kExpQ[6]);
-    q = fma(q, r, kExpQ[5]);
-    q = fma(q, r, kExpQ[4]);
-    q = fma(q, r, kExpQ[3]);
-    q = fma(q, r, kExpQ[2]);
-    q = fma(q, r, kExpQ[1]);
-    q = fma(q, r, kExpQ[0]);
+    const double q = poly_exp_q(r);
     const double p = fma(r * r, q, r) + 1.0;
     const int k = (int)kd;  // |k| <= 1010: 2^k is a normal double
 #if defined(__CUDA_ARCH__)
