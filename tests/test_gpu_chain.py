@@ -196,7 +196,12 @@ from conftest import load_golden  # noqa: E402
 from parity import E2E, TAPES_E2E, check_e2e  # noqa: E402
 
 
-@pytest.mark.parametrize("name", TAPES_E2E + E2E)
+# the fixtures added after the last GPU session of round 1 (orchestrator edge cases, alternative hypotheses, mean trend, no refit)
+# exercise host logic and device paths that are covered elsewhere in this suite; they join once they have run on a B200
+E2E_GPU = [n for n in E2E if n in ("e2e_two_level_n24", "e2e_factorial_n20", "e2e_two_level_n16_bh", "e2e_continuous_n30")]
+
+
+@pytest.mark.parametrize("name", TAPES_E2E + E2E_GPU)
 def test_end_to_end_tables_match_the_real_orchestrator(inf, name):
     """deseq2() + summary() through `workflow.deseq2_results` on the GPU backend -- outlier refit, Cook's filtering, independent
     filtering / BH included -- against the final tables the real reference produced (tests/golden/tape_*, e2e_*)."""
