@@ -121,7 +121,7 @@ Pack make_pack(const double* X, const double* sf, int N, int p) {
         inv += 1.0 / s;
     }
     k.s_mean_inv = inv / N;
-    k.d = DesignS{k.buf.data(), k.buf.data() + (size_t)p * Npad, k.buf.data() + (size_t)(p + 1) * Npad, N, Npad};
+    k.d = DesignS{k.buf.data(), k.buf.data() + (size_t)p * Npad, k.buf.data() + (size_t)(p + 1) * Npad, N, Npad, host_math_table()};
     design_linear_algebra(X, N, p, k.pinv, &k.full_rank);
     return k;
 }
