@@ -8,16 +8,19 @@
 One "step" = one pass of the hot path over one batch of synthetic counts: method-of-moments start values,
 initial mu (lin_reg_mu or IRLS), genewise dispersion MLE, dispersion trend + prior, MAP dispersions, the
 log-fold-change IRLS and the Wald test -- the Inference calls `DeseqDataSet.deseq2()` +
-`DeseqStats.run_wald_test()` make (reference dds.py:516-562, ds.py:303-360).  Size factors are computed once
-outside the timed region for both arms (median of ratios is "next" scope).
+`DeseqStats.run_wald_test()` make (reference dds.py:516-562, ds.py:303-360) -- and, with gene shards (N > 1), the two
+exchanges of the path: the grouped NCCL all-gather of the per-gene vectors before the trend step and the end-of-call
+all-gather of the result tables.  Size factors are computed once outside the timed region for both arms.
 
-Workload = BASELINE.json configs[1]: 20 000 genes x 200 samples, one 2-level factor, per GPU (weak scaling:
-every rank owns a 20 000-gene shard, the trend/prior step all-gathers the per-gene vectors over NCCL).
+Headline workload (`value`, `e2e`, `roofline`, `cpu_baseline`) = BASELINE.json configs[1]: 20 000 genes x 200 samples, one
+2-level factor, per GPU (weak scaling).  The `configs` block of the same JSON line carries BASELINE's larger shapes, timed the
+same way: C3 (60 000 x 500, 3 covariates, one GPU holds it) at N = 1, and at every N the per-GPU shards of the two 8-GPU
+configs, C5 (125 000 x 1 000 of 10^6 x 1 000) and C4 (7 500 x 2 000 of 60 000 x 2 000, continuous covariate).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (counts already in HBM), timed per step with
 CUDA events on the library's stream, L2 flushed between steps, max over ranks.  `e2e` = the same metric through the
-reference-facing plugin calls with HOST buffers (H2D/D2H inside the timed region).  `roofline` describes the
-dominant kernel, `cpu_baseline` the oracle port (joblib over genes, like the reference) on a bounded sample.
+reference-facing plugin calls with HOST buffers (H2D/D2H inside the timed region; page-locked and pageable variants).
+`roofline` describes the dominant kernel, `cpu_baseline` the oracle port (joblib over genes, like the reference).
 """
 from __future__ import annotations
 
@@ -36,6 +39,12 @@ sys.path.insert(0, ROOT)
 
 METRIC = "genes/sec full deseq2() fit (disp+IRLS+Wald)"
 UNIT = "genes/s"
+P_OF = {"two_level": 2, "factorial": 3, "continuous": 3}
+# bytes per (gene, sample) each Inference call reads + writes once: SURVEY.md §8(d)
+ALG_BYTES = {"mom_dispersions": 8, "lin_reg_mu": 16, "irls_init": 24, "alpha_mle_genewise": 16, "alpha_mle_map": 16,
+             "irls_lfc": 24, "irls_lfc_wald": 24, "wald_test": 8}
+KERNEL_OF = {"alpha_mle_genewise": "k_alpha_mle", "alpha_mle_map": "k_alpha_mle", "irls_lfc": "k_irls", "irls_lfc_wald": "k_irls",
+             "irls_init": "k_irls", "lin_reg_mu": "k_lin_reg_mu", "wald_test": "k_wald", "mom_dispersions": "k_mom_from_counts"}
 
 
 def parse():
@@ -48,22 +57,29 @@ def parse():
     ap.add_argument("--samples", type=int, default=200)
     ap.add_argument("--design", default="two_level", choices=["two_level", "factorial", "continuous"])
     ap.add_argument("--cpu-sample-genes", type=int, default=20000,
-                    help="genes of the workload the CPU baseline is timed on (20 000 x 200 is ~15 s on the GPU box)")
+                    help="genes of the workload the CPU baseline is timed on (20 000 x 200 is ~6 s per pass on the GPU box)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the `configs` block (C3 / C5 shard / C4 shard)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per gene override (0 = auto)")
     return ap.parse_args()
 
 
-def workload(args, rank):
+def make_workload(samples, genes, design, rank, dist=None):
+    """This rank's gene shard of one synthetic cohort: samples (design matrix, true size factors) are common to all ranks, genes
+    are drawn per rank; the median-of-ratios size factors are per sample and global over genes -- rank 0's estimate serves all."""
     from pydeseq2_b200.pipeline import median_of_ratios
     from pydeseq2_b200.synth import make_counts
 
-    counts, X, _ = make_counts(args.samples, args.genes, args.design, seed=rank)
+    counts, X, _ = make_counts(samples, genes, design, seed=rank, sample_seed=0)
     G_in = counts.shape[1]
     counts = np.ascontiguousarray(counts[:, ~(counts == 0).all(0)])  # dds.py:729-731 (throughput counts input G)
-    # size factors are per sample and global over genes: every rank derives them from the rank-0 shard's generator
-    ref_counts = counts if rank == 0 else make_counts(args.samples, args.genes, args.design, seed=0)[0]
-    _, sf = median_of_ratios(ref_counts[:, ~(ref_counts == 0).all(0)])
+    _, sf = median_of_ratios(counts[:, :20000])
+    if dist is not None:
+        import torch
+
+        t = torch.from_numpy(sf).cuda()
+        dist.broadcast(t, 0)
+        sf = t.cpu().numpy()
     return counts, X, sf, G_in
 
 
@@ -114,11 +130,9 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_from_profiles(kernel):
+def profile_record():
     path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(path):
-        return json.load(open(path)).get(kernel)
-    return None
+    return json.load(open(path)) if os.path.exists(path) else {}
 
 
 def cpu_fit(counts, X, sf, n_cpus):
@@ -132,37 +146,45 @@ def cpu_fit(counts, X, sf, n_cpus):
     return time.perf_counter() - t0
 
 
+def cpu_sample_desc(n, args, passes):
+    return (f"{'all' if n >= args.genes else 'first'} {n} of {args.genes} genes x {args.samples} samples "
+            f"(non-all-zero genes of them), median of {passes} timed passes after a warm-up pass")
+
+
 def run_reference(args, rank, world):
+    """CPU arm: the oracle port of DefaultInference on all host cores, the FULL headline workload per step."""
     if rank != 0:
         return
-    counts, X, sf, _ = workload(args, 0)
-    n = min(args.cpu_sample_genes, 8000, counts.shape[1])  # bounded: K + W passes must end within minutes
-    sample = np.ascontiguousarray(counts[:, :n])
+    counts, X, sf, G_in = make_workload(args.samples, args.genes, args.design, 0)
+    n_in = min(args.cpu_sample_genes, G_in)
+    sample = counts if n_in >= G_in else np.ascontiguousarray(counts[:, :n_in])
     cores = os.cpu_count() or 1
     cpu_fit(sample[:, :256], X, sf, cores)  # spawn the loky pool outside the timed region
-    for _ in range(args.warmup):
+    for _ in range(max(1, min(args.warmup, 2))):
         cpu_fit(sample, X, sf, cores)
-    times = [cpu_fit(sample, X, sf, cores) for _ in range(args.steps)]
-    dt = float(np.mean(times))
-    val = n / dt
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+    steps = max(1, min(args.steps, 5))  # bounded: the arm must end within minutes (one pass is ~6 s on 128 cores)
+    times = [cpu_fit(sample, X, sf, cores) for _ in range(steps)]
+    dt = float(np.median(times))
+    val = n_in / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config(args, note=f"reference CPU path: oracle port of DefaultInference (numpy/scipy per gene, joblib/loky, "
-                                        f"{cores} processes); each step = the first {n} genes of the workload"),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"first {n} of {args.genes} genes x {args.samples} samples, {args.steps} timed passes"},
+                                        f"{cores} processes); each step = {cpu_sample_desc(n_in, args, steps)}"),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_desc(n_in, args, steps),
+                             "pass_s": [round(t, 3) for t in times]},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def config(args, note=None):
-    p = {"two_level": 2, "factorial": 3, "continuous": 3}[args.design]
+    p = P_OF[args.design]
     c = {"workload": f"{args.genes} genes x {args.samples} samples per GPU, {args.design} design (p={p}); BASELINE.json configs[1]"
                      if (args.genes, args.samples, args.design) == (20000, 200, "two_level")
                      else f"{args.genes} genes x {args.samples} samples per GPU, {args.design} design (p={p})",
          "genes_per_gpu": args.genes, "samples": args.samples, "p": p,
-         "parallelism": f"gene shards x{args.gpus}, one NCCL all-gather of per-gene vectors before the trend fit",
+         "parallelism": f"gene shards x{args.gpus}; per step one grouped NCCL all-gather of the per-gene vectors before the trend fit "
+                        f"and one all-gather of the result tables at the end",
          "size_factors": "median of ratios, precomputed outside the timed region (both arms)",
          "l2": "flushed between timed steps (256 MiB device memset)"}
     if note:
@@ -170,198 +192,288 @@ def config(args, note=None):
     return c
 
 
-def main():
-    args = parse()
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    if args.impl == "reference":
-        return run_reference(args, rank, world)
+class Bench:
+    """One process = one GPU: context, NCCL communicator (N > 1) and the measurements of one workload at a time."""
 
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
+    def __init__(self, args):
+        self.args = args
+        self.rank = int(os.environ.get("RANK", 0))
+        self.world = int(os.environ.get("WORLD_SIZE", 1))
+        self.local = int(os.environ.get("LOCAL_RANK", 0))
+        self.dist = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
 
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        from pydeseq2_b200 import _lib
+        from pydeseq2_b200.inference import B200Inference
 
-    from pydeseq2_b200 import _lib
-    from pydeseq2_b200.inference import B200Inference
-    from pydeseq2_b200.pipeline import ResidentFit, fit_host
-    from pydeseq2_b200.sharding import NcclComm
+        self._lib = _lib
+        self.inf = B200Inference(device=self.local, lanes_per_gene=args.lanes)
+        self.ctx = self.inf._ops.ctx
+        self.uid = None
+        if self.world > 1:
+            import torch
+            from pydeseq2_b200.sharding import NcclComm
 
-    counts, X, sf, G_in = workload(args, rank)
-    N, G = counts.shape
-    inf = B200Inference(device=local, lanes_per_gene=args.lanes)
-    ctx = inf._ops.ctx
-    comm = None
-    if world > 1:
-        import torch
+            uid = torch.zeros(_lib.UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+            if self.rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(NcclComm.make_unique_id(self.ctx)), dtype=torch.uint8))
+            self.dist.broadcast(uid, 0)
+            self.uid = uid.cpu().numpy().tobytes()
+        self.comm = None
+        self.flush = self.ctx.malloc(256 << 20)
+        self.peak, self.peak_src = peaks()
+        self.fp64_peak = None
 
-        uid = torch.zeros(_lib.UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(NcclComm.make_unique_id(ctx)), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        comm = NcclComm(ctx, _all_sizes(dist, G, world), rank, uid.cpu().numpy().tobytes())
-
-    def barrier():
-        ctx.sync()
-        if dist is not None:
+    # -- plumbing ---------------------------------------------------------------------------------------------
+    def barrier(self):
+        self.ctx.sync()
+        if self.dist is not None:
             import torch
 
-            dist.barrier()
+            self.dist.barrier()
             torch.cuda.synchronize()
 
-    rf = ResidentFit(ctx, X, sf, comm=comm)
-    rf.upload(counts)
-    flush = ctx.malloc(256 << 20)
-
-    def flush_l2():
-        ctx.check(ctx.lib.pdq_memset(ctx.h, _lib.c_dptr(flush), 1, 256 << 20))
-        ctx.sync()
-
-    # ---------------------------------------------------------------- value: device-resident
-    clk = ClockSampler(local).__enter__()  # sampled from the warm-up until the end of the e2e loop (steps last only ms)
-    for _ in range(max(args.warmup, 3)):
-        rf.run()
-    barrier()
-    launches0 = ctx.launches()
-    step_ms = []
-    if True:
-        for _ in range(args.steps):
-            flush_l2()
-            barrier()
-            ctx.record(0)
-            rf.run()
-            ctx.record(1)
-            ctx.sync()
-            step_ms.append(ctx.elapsed_ms(0, 1))
-    barrier()
-    launches = ctx.launches() - launches0
-    total_ms = float(np.sum(step_ms))
-    if dist is not None:
+    def max_over_ranks(self, v):
+        if self.dist is None:
+            return float(v)
         import torch
 
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = G_in * world / (ms_per_step * 1e-3)
+        t = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---------------------------------------------------------------- per-kernel timings -> roofline
-    rf.run(profile=True)
-    rf.run(profile=True)
-    stages = dict(rf.stage_ms)
-    rf.with_cooks = True  # Cook's distances: reported for information, NOT part of the timed step
-    rf.run(profile=True)
-    stages["cooks_untimed"] = rf.stage_ms.get("cooks")
-    rf.with_cooks = False
+    def all_sizes(self, G):
+        if self.dist is None:
+            return [G]
+        import torch
+
+        t = torch.tensor([G], device="cuda", dtype=torch.int64)
+        out = [torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [int(o.item()) for o in out]
+
+    def comm_for(self, G):
+        """Shard sizes differ per workload (every rank drops its own all-zero genes): one NCCL communicator, sizes re-set."""
+        if self.world == 1:
+            return None
+        from pydeseq2_b200.sharding import NcclComm
+
+        sizes = self.all_sizes(G)
+        if self.comm is None:
+            self.comm = NcclComm(self.ctx, sizes, self.rank, self.uid)
+        else:
+            self.comm.sizes, self.comm.max_size = list(sizes), max(sizes)
+        return self.comm
+
+    def flush_l2(self):
+        self.ctx.check(self.ctx.lib.pdq_memset(self.ctx.h, self._lib.c_dptr(self.flush), 1, 256 << 20))
+        self.ctx.sync()
+
+    # -- measurements -----------------------------------------------------------------------------------------
+    def resident(self, counts, X, sf, G_in, steps, warmup):
+        """Device-resident steps (CUDA events on the library's stream, L2 flushed, max over ranks) + per-stage timings."""
+        from pydeseq2_b200.pipeline import ResidentFit
+
+        N, G = counts.shape
+        rf = ResidentFit(self.ctx, X, sf, comm=self.comm_for(G))
+        rf.upload(counts)
+        for _ in range(max(warmup, 3)):
+            rf.run()
+        self.barrier()
+        launches0 = self.ctx.launches()
+        step_ms = []
+        for _ in range(steps):
+            self.flush_l2()
+            self.barrier()
+            rf.run(events=(0, 1))  # CUDA events around the device work of the pass: first launch ... result copy done
+            step_ms.append(self.ctx.elapsed_ms(0, 1))
+        self.barrier()
+        launches = self.ctx.launches() - launches0
+        ms = self.max_over_ranks(float(np.sum(step_ms))) / steps
+        rf.run(profile=True)
+        rf.run(profile=True)
+        stages = dict(rf.stage_ms)
+        rec = {"ms_per_step": ms, "genes_per_s": G_in * self.world / (ms * 1e-3), "gpu_launches": int(launches),
+               "stages_ms": {k: round(v, 4) for k, v in stages.items()}}
+        rec.update(self.rooflines(stages, N, G, X.shape[1], ms))
+        return rf, rec
+
+    def rooflines(self, stages, N, G, p, step_ms):
+        """HBM roofline of the dominant kernel and of the whole step; FP64 roofline of the dominant kernel (DFMA peak measured in
+        this run; flop count per (gene, sample) from the committed ncu capture of the same kernel, profiles/traffic.json)."""
+        kern = {k: v for k, v in stages.items() if k in ALG_BYTES}
+        top = max(kern, key=kern.get)
+        achieved = ALG_BYTES[top] * N * G / (kern[top] * 1e-3) / 1e9
+        step_bytes = sum(ALG_BYTES[k] for k in kern) * N * G
+        if "irls_lfc_wald" in kern:
+            step_bytes += ALG_BYTES["wald_test"] * N * G  # the fused launch also does the Wald call's work (its mu read is saved)
+        kname = KERNEL_OF[top]
+        prof = profile_record()
+        roof = {"bound": "hbm", "kernel": f"{kname} ({top})", "achieved": achieved, "peak": self.peak, "unit": "GB/s",
+                "frac": achieved / self.peak, "traffic": prof.get("dram_bytes_per_launch", {}).get(kname),
+                "peak_source": self.peak_src, "algorithmic_bytes_per_launch": ALG_BYTES[top] * N * G, "kernel_ms": kern[top],
+                "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
+                         "frac": step_bytes / (step_ms * 1e-3) / 1e9 / self.peak},
+                "note": "issue / FP64-pipe bound (log, exp, reciprocal, digamma per gene-sample-iteration), see DESIGN.md §5"}
+        if self.fp64_peak is None:
+            self.fp64_peak = self.ctx.fp64_peak_tflops()
+        fp64 = {"peak_tflops": self.fp64_peak, "peak_source": "measured in this run (pdq_fp64_peak_tflops: DFMA chains on every SM)"}
+        per_pair = prof.get("fp64_flop_per_gene_sample", {}).get(kname)
+        if per_pair:
+            flop = per_pair * N * G
+            fp64.update({"achieved_tflops": flop / (kern[top] * 1e-3) / 1e12, "flop_per_launch": flop,
+                         "frac": flop / (kern[top] * 1e-3) / 1e12 / self.fp64_peak if self.fp64_peak > 0 else None,
+                         "flop_source": prof.get("fp64_flop_source"),
+                         "pipe_active_pct_ncu": prof.get("fp64_pipe_active_pct", {}).get(kname)})
+        roof["fp64"] = fp64
+        return {"roofline": roof}
+
+    def e2e(self, counts, X, sf, G_in, steps, pinned):
+        """The same pass through the plugin calls with HOST buffers (H2D / D2H inside the timed region)."""
+        from pydeseq2_b200.inference import B200Inference
+        from pydeseq2_b200.pipeline import fit_host
+
+        inf = self.inf if pinned else B200Inference(device=self.local, lanes_per_gene=self.args.lanes, pinned_outputs=False)
+        alloc = (lambda shape, dt: self.ctx.pinned_empty(shape, dt)) if pinned else (lambda shape, dt: np.empty(shape, dt))
+        c_host = alloc(counts.shape, np.int64)
+        c_host[:] = counts
+        n_host = alloc(counts.shape, np.float64)  # layers["normed_counts"] of the orchestrator (dds.py:700-708)
+        np.divide(counts, sf[:, None], out=n_host)
+        n_means = n_host.mean(0)  # var["_normed_means"], also a product of fit_size_factors (dds.py:708)
+        comm = self.comm_for(counts.shape[1])
+        for _ in range(2):
+            fit_host(c_host, X, inf, size_factors=sf, comm=comm, normed_counts=n_host, normed_means=n_means)
+        self.barrier()
+        ops = inf._ops
+        h0, d0 = ops.h2d_bytes, ops.d2h_bytes
+        ts, T = [], {}
+        for _ in range(steps):
+            self.barrier()
+            t0 = time.perf_counter()
+            fit_host(c_host, X, inf, size_factors=sf, comm=comm, timings=T, normed_counts=n_host, normed_means=n_means)
+            ops.ctx.sync()
+            ts.append(time.perf_counter() - t0)
+        s = self.max_over_ranks(float(np.mean(ts)))
+        return {"value": G_in * self.world / s, "unit": UNIT, "ms_per_step": s * 1e3,
+                "h2d_bytes_per_step": (ops.h2d_bytes - h0) // steps, "d2h_bytes_per_step": (ops.d2h_bytes - d0) // steps,
+                "host_buffers": "page-locked" if pinned else "pageable (what the orchestrator's fancy-indexed copies are, dds.py:752)",
+                "calls_ms": {k: round(v * 1e3 / steps, 3) for k, v in T.items()}}
+
+    def check_shards(self, rf):
+        """N > 1: the sharded pass must equal a single-process fit -- (a) every rank holds the same trend record and tables,
+        (b) the trend / prior of the gathered vectors recomputed by ONE rank on the concatenation (no NaN pads) agree."""
+        import torch
+
+        res = rf.run()
+        full = rf.gather_results(res)
+        t16 = torch.from_numpy(np.array([res["trend"].coeffs[0], res["trend"].coeffs[1], res["prior_var"], res["squared_logres"],
+                                         float(np.nansum(full["dispersions"])), float(np.nansum(np.abs(full["lfc"]))),
+                                         float(len(full["dispersions"]))])).cuda()
+        outs = [torch.empty_like(t16) for _ in range(self.world)]
+        self.dist.all_gather(outs, t16)
+        same = all(bool(torch.equal(o, outs[0])) for o in outs)
+        out = {"ranks_hold_identical_tables": same, "genes_gathered": int(len(full["dispersions"]))}
+        if self.rank == 0:
+            tp = self.inf.trend_and_prior(full["normed_means"], full["genewise"], rf.min_disp, rf.max_disp, rf.N, rf.p)
+            if tp is not None:
+                out["trend_coeff_rel_err_vs_single_process"] = float(np.max(np.abs(tp[0] / res["trend"].coeffs - 1)))
+                out["prior_var_rel_err_vs_single_process"] = abs(tp[3] / res["prior_var"] - 1)
+                out["ok"] = bool(same and out["trend_coeff_rel_err_vs_single_process"] < 1e-9
+                                 and out["prior_var_rel_err_vs_single_process"] < 1e-9)
+        return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args, int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)))
+    B = Bench(args)
+    rank, world, ctx = B.rank, B.world, B.ctx
+    counts, X, sf, G_in = make_workload(args.samples, args.genes, args.design, rank, B.dist)
+    N, G = counts.shape
+
+    # ---------------------------------------------------------------- value: device-resident (headline workload)
+    clk = ClockSampler(B.local).__enter__()  # sampled from the warm-up until the end of the e2e loop (steps last only ms)
+    rf, head = B.resident(counts, X, sf, G_in, args.steps, args.warmup)
+    stages = dict(head["stages_ms"])
+    shard_check = B.check_shards(rf) if world > 1 else None
+
+    # untimed extras (reported for information, NOT part of the timed step): Cook's distances, apeGLM shrinkage, device size factors
     from pydeseq2_b200.pipeline import fit_shrink_prior_var
 
+    rf.with_cooks = True
+    rf.run(profile=True)
+    stages["cooks_untimed"] = round(rf.stage_ms.get("cooks", float("nan")), 4)
+    rf.with_cooks = False
     res_sh = rf.run()
     k_sh = X.shape[1] - 1
     ps_sh = float(min(np.sqrt(fit_shrink_prior_var(np.asarray(res_sh["lfc"])[:, k_sh], np.asarray(res_sh["se"]))), 1.0))
     rf.lfc_shrink(res_sh, k_sh, prior_scale=ps_sh)  # first call allocates its buffers
     t0 = time.perf_counter()
-    rf.lfc_shrink(res_sh, k_sh, prior_scale=ps_sh)  # apeGLM shrinkage: for information, NOT in the timed step
-    stages["lfc_shrink_untimed"] = (time.perf_counter() - t0) * 1e3
-    rf.device_size_factors()  # first call allocates its scratch
-    ctx.sync()
-    t0 = time.perf_counter()
-    rf.device_size_factors()  # median of ratios on the device: reported for information, NOT part of the timed step
-    stages["size_factors_dev_untimed"] = (time.perf_counter() - t0) * 1e3
-    alg_bytes = {"mom_dispersions": 8, "lin_reg_mu": 16, "irls_init": 24, "alpha_mle_genewise": 16, "alpha_mle_map": 16,
-                 "irls_lfc": 24, "wald_test": 8}  # bytes per (gene, sample): SURVEY.md §8(d)
-    kern = {k: v for k, v in stages.items() if k in alg_bytes}
-    top = max(kern, key=kern.get)
-    peak, peak_src = peaks()
-    achieved = alg_bytes[top] * N * G / (kern[top] * 1e-3) / 1e9
-    kname = {"alpha_mle_genewise": "k_alpha_mle", "alpha_mle_map": "k_alpha_mle", "irls_lfc": "k_irls", "irls_init": "k_irls",
-             "lin_reg_mu": "k_lin_reg_mu", "wald_test": "k_wald", "mom_dispersions": "k_mom_from_counts"}[top]
-    roofline = {"bound": "hbm", "kernel": f"{kname} ({top})", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic_from_profiles(kname), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes[top] * N * G, "kernel_ms": kern[top],
-                "note": "FP64-pipe bound (lgamma/digamma/exp/log per gene-sample-iteration), see DESIGN.md §5"}
-    # second roofline, the one that binds: FP64 arithmetic.  Peak = DFMA throughput measured now on this device; achieved = the
-    # kernel's FP64 flop count (2*DFMA + DMUL + DADD thread instructions, from the committed ncu capture of the same workload,
-    # scaled to this run's gene-sample count) over its CUDA-event duration.
-    prof = {}
-    if os.path.exists(os.path.join(ROOT, "profiles", "traffic.json")):
-        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-    flop_ref = prof.get("fp64_flop_per_launch", {}).get(kname)
-    fp64_peak = ctx.fp64_peak_tflops()
-    fp64 = {"peak_tflops": fp64_peak, "peak_source": "measured in this run (pdq_fp64_peak_tflops: DFMA chains on every SM)"}
-    if flop_ref:
-        flop = flop_ref * (N * G) / (19800 * 200)
-        fp64.update({"achieved_tflops": flop / (kern[top] * 1e-3) / 1e12, "flop_per_launch": flop,
-                     "frac": flop / (kern[top] * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,
-                     "pipe_active_pct_ncu": prof.get("fp64_pipe_active_pct", {}).get(kname)})
-    roofline["fp64"] = fp64
+    rf.lfc_shrink(res_sh, k_sh, prior_scale=ps_sh)
+    stages["lfc_shrink_untimed"] = round((time.perf_counter() - t0) * 1e3, 4)
+    if world == 1:
+        rf.device_size_factors()  # first call allocates its scratch
+        ctx.sync()
+        t0 = time.perf_counter()
+        rf.device_size_factors()
+        stages["size_factors_dev_untimed"] = round((time.perf_counter() - t0) * 1e3, 4)
+    rf.close()
 
     # ---------------------------------------------------------------- e2e: plugin calls with host buffers
-    c_host = ctx.pinned_empty(counts.shape, np.int64)
-    c_host[:] = counts
-    n_host = ctx.pinned_empty(counts.shape, np.float64)  # layers["normed_counts"] of the orchestrator (dds.py:700-708)
-    np.divide(counts, sf[:, None], out=n_host)
-    n_means = n_host.mean(0)  # var["_normed_means"], also a product of fit_size_factors (dds.py:708)
-    for _ in range(2):
-        fit_host(c_host, X, inf, size_factors=sf, comm=comm, normed_counts=n_host, normed_means=n_means)
-    barrier()
-    ops = inf._ops
-    h0, d0 = ops.h2d_bytes, ops.d2h_bytes
-    e2e_t = []
-    e2e_T = {}
-    for _ in range(args.steps):
-        barrier()
-        t0 = time.perf_counter()
-        fit_host(c_host, X, inf, size_factors=sf, comm=comm, timings=e2e_T, normed_counts=n_host, normed_means=n_means)
-        ctx.sync()
-        e2e_t.append(time.perf_counter() - t0)
-    e2e_s = float(np.mean(e2e_t))
+    e2e = B.e2e(counts, X, sf, G_in, args.steps, pinned=True)
+    e2e_pageable = B.e2e(counts, X, sf, G_in, max(2, min(args.steps, 5)), pinned=False)
+    e2e["pageable"] = {k: e2e_pageable[k] for k in ("value", "ms_per_step", "host_buffers", "calls_ms")}
     time.sleep(0.25)  # let nvidia-smi emit at least one more sample
     clk.__exit__()
-    if dist is not None:
-        import torch
 
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = {"value": G_in * world / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
-           "h2d_bytes_per_step": (ops.h2d_bytes - h0) // args.steps, "d2h_bytes_per_step": (ops.d2h_bytes - d0) // args.steps}
+    # ---------------------------------------------------------------- BASELINE's larger shapes, same measurement
+    configs = {}
+    if not args.no_extra_configs and (args.genes, args.samples, args.design) == (20000, 200, "two_level"):
+        extra = [("C5_shard", 125000, 1000, "two_level", "BASELINE.json configs[4] (10^6 x 1 000 over 8 GPUs): one 125 000-gene shard per GPU"),
+                 ("C4_shard", 7500, 2000, "continuous", "BASELINE.json configs[3] (60 000 x 2 000 over 8 GPUs): one 7 500-gene shard per GPU")]
+        if world == 1:
+            extra.insert(0, ("C3", 60000, 500, "factorial", "BASELINE.json configs[2]: 60 000 genes x 500 samples, 3 covariates, whole on one GPU"))
+        for name, g, n, design, what in extra:
+            c2, X2, sf2, gin2 = make_workload(n, g, design, rank, B.dist)
+            rf2, rec = B.resident(c2, X2, sf2, gin2, max(3, min(args.steps, 10)), 3)
+            rec["workload"] = f"{what}; {g} genes x {n} samples per GPU, {design} design (p={P_OF[design]})"
+            if world > 1:
+                rec["shard_check"] = B.check_shards(rf2)
+            rf2.close()
+            if name == "C3":
+                rec["e2e"] = B.e2e(c2, X2, sf2, gin2, 3, pinned=True)
+            configs[name] = rec
+            del c2, rf2
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n = min(args.cpu_sample_genes, G)
+        n_in = min(args.cpu_sample_genes, G_in)
         cores = os.cpu_count() or 1
-        sample = np.ascontiguousarray(counts[:, :n])
+        sample = counts if n_in >= G_in else np.ascontiguousarray(counts[:, :n_in])
         cpu_fit(sample[:, :256], X, sf, cores)  # pool start-up outside the timed region
-        dt = cpu_fit(sample, X, sf, cores)
-        cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {n} of {G_in} genes x {N} samples, one pass after pool warm-up ({dt:.1f} s)"}
+        cpu_fit(sample, X, sf, cores)           # warm-up pass
+        times = [cpu_fit(sample, X, sf, cores) for _ in range(3)]
+        dt = float(np.median(times))
+        cpu = {"value": n_in / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_desc(n_in, args, 3),
+               "pass_s": [round(t, 3) for t in times]}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": config(args), "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
-                "stages_ms": {k: round(v, 4) for k, v in stages.items()},
-                "e2e_calls_ms": {k: round(v * 1e3 / args.steps, 3) for k, v in e2e_T.items()}, "device": ctx.info()["name"]}
+        line = {"metric": METRIC, "value": head["genes_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(args), "e2e": e2e,
+                "gpu_launches": head["gpu_launches"], "clocks": clk.summary(), "roofline": head["roofline"], "cpu_baseline": cpu,
+                "stages_ms": stages, "configs": configs, "shard_check": shard_check, "device": ctx.info()["name"]}
         print(json.dumps(line), flush=True)
-    rf.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-
-
-def _all_sizes(dist, G, world):
-    import torch
-
-    t = torch.tensor([G], device="cuda", dtype=torch.int64)
-    out = [torch.zeros_like(t) for _ in range(world)]
-    dist.all_gather(out, t)
-    return [int(o.item()) for o in out]
+    if B.dist is not None:
+        B.dist.barrier()
+        B.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -73,6 +73,10 @@ int pdq_set_debug_flags(pdq_ctx* ctx, int flags);
 int pdq_fp64_peak_tflops(pdq_ctx* ctx, double* tflops_out);
 /* number of kernel launches issued through this context so far (bench.py `gpu_launches`) */
 int64_t pdq_launch_count(const pdq_ctx* ctx);
+/* Number of times a context-owned scratch buffer has been re-allocated.  A CUDA graph captured with pdq_capture_begin / _end
+ * holds pointers into that scratch: compare the value at capture time with the current one before pdq_graph_launch and
+ * re-capture when it changed. */
+int64_t pdq_buffer_epoch(const pdq_ctx* ctx);
 
 int pdq_malloc(pdq_ctx* ctx, size_t bytes, void** dptr);
 int pdq_free(pdq_ctx* ctx, void* dptr);
@@ -148,6 +152,13 @@ int pdq_fit_moments_dispersions(pdq_ctx* ctx, const double* normed_counts, int64
  * ~4e-6 of the minimiser; this converges to the minimiser itself. */
 int pdq_dispersion_trend_gamma_glm(pdq_ctx* ctx, const double* covariates, const double* targets, size_t n,
                                    double* coeffs_out, double* pred_out, int* converged_out);
+/* Dispersion trend AND dispersion prior in one launch, host vectors: the whole outer loop of
+ * DeseqDataSet.fit_dispersion_trend (dds.py:1199-1275: gamma-GLM fit, drop genes far from the curve, refit until the
+ * coefficients settle) followed by fit_dispersion_prior (dds.py:840-884).  `out16` receives the record
+ * [c0, c1, status (0 ok / 1 -> fall back to the mean trend), n_outer, n_used, n_iter, loss, last_converged, squared_logres,
+ * prior_var, n_above, ...]; `fitted_out` (may be NULL) the fitted curve c0 + c1 / mean per gene.  NaN means are skipped. */
+int pdq_trend_prior(pdq_ctx* ctx, const double* normed_means, const double* genewise, size_t n, double min_disp,
+                    double max_disp, double trigamma_c, double* out16, double* fitted_out);
 
 /* apeGLM LFC shrinkage -- Inference.lfc_shrink_nbinom_glm (inference.py:309-362) -> DefaultInference (default_inference.py:232-264)
  * -> utils.nbinomGLM (utils.py:990-1145), grid fallback grid_search.py:224-318; caller DeseqStats.lfc_shrink (ds.py:363-443).
@@ -184,6 +195,16 @@ int pdq_irls_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, 
                  const double* disp, double min_mu, double beta_tol, double min_beta, double max_beta,
                  int maxiter, double* beta_out, double* mu_out, double* hat_out, int64_t ld_out,
                  double* converged_out, int* n_fallback_dev /* device int, may be NULL */);
+/* pdq_irls_dev + pdq_wald_test_dev in one launch: the Wald test (ds.py:303-360 -> utils.py:718-811) of the coefficients the
+ * fit returns, built from the X^T W X of the last IRLS sweep (corrected for samples on the min_mu clamp, because the
+ * orchestrator's test uses mu = sf * exp(X beta) unclamped, ds.py:320-324) instead of a second pass over mu.  `disp` serves
+ * both.  Results equal calling the two entry points in sequence up to rounding. */
+int pdq_irls_wald_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld, int G,
+                      const double* disp, double min_mu, double beta_tol, double min_beta, double max_beta,
+                      int maxiter, double* beta_out, double* mu_out, double* hat_out, int64_t ld_out,
+                      double* converged_out, int* n_fallback_dev, const double* ridge_host,
+                      const double* contrast_host, double lfc_null, int alt, double* pvalue_out,
+                      double* stat_out, double* se_out);
 int pdq_alpha_mle_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld, int G,
                       const double* mu, int64_t ld_mu, const double* alpha_hat, double min_disp,
                       double max_disp, double prior_disp_var,
@@ -241,6 +262,9 @@ int pdq_mu_from_lfc_dev(pdq_ctx* ctx, const pdq_design* design, const double* lf
 int pdq_comm_unique_id(pdq_ctx* ctx, void* id_out);
 int pdq_comm_init(pdq_ctx* ctx, const void* id, int world_size, int rank);
 int pdq_allgather_f64_dev(pdq_ctx* ctx, const double* send, double* recv, size_t count);
+/* k (<= 16) equal-count all-gathers issued as one NCCL group -- a single fused launch on the context's stream.  `send` / `recv`
+ * are HOST arrays of k device pointers; recv[i] receives world * count doubles in rank order. */
+int pdq_allgather_multi_f64_dev(pdq_ctx* ctx, int k, const double* const* send, double* const* recv, size_t count);
 int pdq_comm_destroy(pdq_ctx* ctx);
 
 #ifdef __cplusplus

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "pdq_set_lanes_per_gene": (C.c_int, [c_ctx, C.c_int]),
     "pdq_set_debug_flags": (C.c_int, [c_ctx, C.c_int]),
     "pdq_launch_count": (C.c_int64, [c_ctx]),
+    "pdq_buffer_epoch": (C.c_int64, [c_ctx]),
     "pdq_malloc": (C.c_int, [c_ctx, C.c_size_t, C.POINTER(c_dptr)]),
     "pdq_free": (C.c_int, [c_ctx, c_dptr]),
     "pdq_host_alloc": (C.c_int, [c_ctx, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -71,6 +72,9 @@ _SIGNATURES = {
     "pdq_lin_reg_mu_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, C.c_double, c_dptr, C.c_int64]),
     "pdq_irls_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, c_dptr, C.c_double, C.c_double, C.c_double,
                                C.c_double, C.c_int, c_dptr, c_dptr, c_dptr, C.c_int64, c_dptr, c_dptr]),
+    "pdq_irls_wald_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, c_dptr, C.c_double, C.c_double, C.c_double,
+                                    C.c_double, C.c_int, c_dptr, c_dptr, c_dptr, C.c_int64, c_dptr, c_dptr, f64p, f64p,
+                                    C.c_double, C.c_int, c_dptr, c_dptr, c_dptr]),
     "pdq_alpha_mle_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, c_dptr, C.c_int64, c_dptr, C.c_double,
                                     C.c_double, C.c_double, c_dptr, C.c_int, C.c_int, c_dptr, c_dptr]),
     "pdq_wald_test_dev": (C.c_int, [c_ctx, c_design, c_dptr, c_dptr, c_dptr, C.c_int64, C.c_int, f64p, f64p, C.c_double,
@@ -89,6 +93,7 @@ _SIGNATURES = {
                                      c_dptr, c_dptr, c_dptr]),
     "pdq_size_factors_dev": (C.c_int, [c_ctx, c_dptr, C.c_int64, C.c_int, C.c_int, c_dptr, c_dptr]),
     "pdq_dispersion_trend_gamma_glm": (C.c_int, [c_ctx, f64p, f64p, C.c_size_t, f64p, f64p, C.POINTER(C.c_int)]),
+    "pdq_trend_prior": (C.c_int, [c_ctx, f64p, f64p, C.c_size_t, C.c_double, C.c_double, C.c_double, f64p, f64p]),
     "pdq_trend_fit_dev": (C.c_int, [c_ctx, c_dptr, c_dptr, C.c_size_t, C.c_double, C.c_double, C.c_double, c_dptr, c_dptr]),
     "pdq_select_dispersions_dev": (C.c_int, [c_ctx, c_dptr, c_dptr, c_dptr, c_dptr, C.c_size_t, C.c_double, C.c_double, c_dptr,
                                              c_dptr]),
@@ -96,6 +101,7 @@ _SIGNATURES = {
     "pdq_comm_unique_id": (C.c_int, [c_ctx, C.c_void_p]),
     "pdq_comm_init": (C.c_int, [c_ctx, C.c_void_p, C.c_int, C.c_int]),
     "pdq_allgather_f64_dev": (C.c_int, [c_ctx, c_dptr, c_dptr, C.c_size_t]),
+    "pdq_allgather_multi_f64_dev": (C.c_int, [c_ctx, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t]),
     "pdq_comm_destroy": (C.c_int, [c_ctx]),
 }
 

@@ -30,6 +30,8 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static const int kNcclFloat64 = 8;  // ncclDataType_t::ncclFloat64 (stable across NCCL 2.x)
@@ -67,6 +69,7 @@ struct pdq_ctx {
     int pipeline = 4;        // gene blocks per pipelined call; PDQ_PIPELINE=0 disables
     int debug = 0;           // PDQ_DEBUG_* test hooks
     int64_t launches_at_capture = 0;
+    int64_t buf_epoch = 0;   // bumped whenever ensure() re-allocates a context-owned buffer (captured graphs hold those pointers)
     NcclApi nccl;
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
@@ -97,7 +100,10 @@ static int fail(pdq_ctx* c, int code, const char* fmt, ...) {
 
 static int ensure(pdq_ctx* c, int which, size_t bytes, void** out) {
     if (bytes > c->cap[which]) {
-        if (c->buf[which]) CU(c, cudaFree(c->buf[which]));
+        if (c->buf[which]) {
+            CU(c, cudaFree(c->buf[which]));
+            ++c->buf_epoch;
+        }
         c->buf[which] = nullptr;
         c->cap[which] = 0;
         const size_t want = bytes + bytes / 8 + 256;
@@ -231,6 +237,7 @@ extern "C" int pdq_set_debug_flags(pdq_ctx* c, int flags) {
 }
 
 extern "C" int64_t pdq_launch_count(const pdq_ctx* c) { return c ? c->launches : 0; }
+extern "C" int64_t pdq_buffer_epoch(const pdq_ctx* c) { return c ? c->buf_epoch : 0; }
 
 extern "C" int pdq_malloc(pdq_ctx* c, size_t bytes, void** dptr) {
     if (!c || !dptr) return PDQ_ERR_INVALID;
@@ -352,13 +359,15 @@ static int design_create(pdq_ctx* c, const double* X, const double* sf, bool off
     DesignDev& dd = d->d;
     dd.N = N;
     dd.p = p;
-    dd.Npad = (N + 1) & ~1;
-    dd.smem_bytes = (size_t)(p + 2) * dd.Npad * 8 + 16;
-    if (dd.smem_bytes > kMaxDynSmem) {
-        delete d;
-        return fail(c, PDQ_ERR_UNSUPPORTED, "design pack (%d samples x %d columns = %zu bytes) exceeds the %zu-byte shared-memory stage", N, p,
-                    dd.smem_bytes, kMaxDynSmem);
-    }
+    dd.RS = (p + 3) & ~1;  // row stride of the pack in doubles (design_row_stride, pdq_gene.cuh)
+    // Staging limit: a pack of up to 40 KB leaves room for four blocks per SM next to the math table and the per-gene tables of
+    // the two heavy kernels; larger packs (N > ~1 280 at p = 2, ~850 at p = 3) are read from global memory, where they live in
+    // L1 / L2 (every warp walks the same rows), so the number of samples is not bounded by shared memory.
+    const size_t pack_bytes = (size_t)(N + 1) * dd.RS * 8;  // N sample rows + the row of column maxima
+    size_t stage_max = 40 * 1024;
+    if (const char* e = getenv("PDQ_STAGE_MAX_BYTES")) stage_max = (size_t)atoll(e);  // tuning hook
+    dd.staged = pack_bytes <= stage_max && pack_bytes + 16 <= kMaxDynSmem / 2;
+    dd.smem_bytes = (dd.staged ? pack_bytes : 0) + 16;
     design_linear_algebra(X, N, p, dd.pinv, &dd.full_rank);
     dd.few_rows = design_distinct_rows(X, N, p, 16) <= 16;
     if (const char* e = getenv("PDQ_IRLS_MEMO")) dd.few_rows = dd.few_rows && atoi(e) != 0;  // tuning hook (A/B runs)
@@ -375,16 +384,20 @@ static int design_create(pdq_ctx* c, const double* X, const double* sf, bool off
             return fail(c, PDQ_ERR_CUDA, "cudaMalloc/cudaMemcpy(cell plan) failed");
         }
     }
-    std::vector<double> pack((size_t)(p + 2) * dd.Npad, 0.0);
+    std::vector<double> pack((size_t)(N + 1) * dd.RS, 0.0);
     double inv_sum = 0.0;
     for (int n = 0; n < N; ++n) {
-        for (int j = 0; j < p; ++j) pack[(size_t)j * dd.Npad + n] = X[(size_t)n * p + j];
+        double* row = pack.data() + (size_t)n * dd.RS;
+        for (int j = 0; j < p; ++j) {
+            row[j] = X[(size_t)n * p + j];
+            double& mx = pack[(size_t)N * dd.RS + j];
+            mx = !(fabs(row[j]) <= mx) ? fabs(row[j]) : mx;  // NaN propagates into the bound
+        }
         const double s = sf ? (offsets ? exp(sf[n]) : sf[n]) : 1.0;
-        pack[(size_t)p * dd.Npad + n] = s;
-        pack[(size_t)(p + 1) * dd.Npad + n] = (sf && offsets) ? sf[n] : log(s);
+        row[p] = s;
+        row[p + 1] = (sf && offsets) ? sf[n] : log(s);
         inv_sum += 1.0 / s;
     }
-    for (int n = N; n < dd.Npad; ++n) pack[(size_t)p * dd.Npad + n] = 1.0;
     dd.s_mean_inv = inv_sum / N;
     if (cudaMalloc((void**)&dd.pack, pack.size() * 8) != cudaSuccess) {
         cudaFree(dd.cell_plan);
@@ -475,6 +488,22 @@ extern "C" int pdq_irls_dev(pdq_ctx* c, const pdq_design* d, const int64_t* coun
     if (int e = ensure(c, kBufStatus, (size_t)G * sizeof(int), &status)) return e;
     IrlsHost h{min_mu, beta_tol, min_beta, max_beta, maxiter};
     return done(c, launch_irls(cfg(c, G, d->d.N), d->d, counts, ld, G, disp, h, beta, mu, hat, ld_out, conv, (int*)status, n_fallback_dev), "irls");
+}
+
+extern "C" int pdq_irls_wald_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, const double* disp,
+                                 double min_mu, double beta_tol, double min_beta, double max_beta, int maxiter, double* beta,
+                                 double* mu, double* hat, int64_t ld_out, double* conv, int* n_fallback_dev, const double* ridge,
+                                 const double* contrast, double lfc_null, int alt, double* pv, double* stat, double* se) {
+    CHECK_CTX(c);
+    if (!d || !counts || !disp || !beta || !mu || !hat || !conv || G <= 0 || ld < G || ld_out < G || !ridge || !contrast || !pv ||
+        !stat || !se || alt < 0 || alt > 4)
+        return fail(c, PDQ_ERR_INVALID, "pdq_irls_wald_dev: bad arguments");
+    void* status;
+    if (int e = ensure(c, kBufStatus, (size_t)G * sizeof(int), &status)) return e;
+    IrlsHost h{min_mu, beta_tol, min_beta, max_beta, maxiter};
+    const WaldHost w{ridge, contrast, lfc_null, alt, pv, stat, se};
+    return done(c, launch_irls(cfg(c, G, d->d.N), d->d, counts, ld, G, disp, h, beta, mu, hat, ld_out, conv, (int*)status, n_fallback_dev, &w),
+                "irls+wald");
 }
 
 extern "C" int pdq_alpha_mle_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, const double* mu,
@@ -1054,6 +1083,28 @@ extern "C" int pdq_dispersion_trend_gamma_glm(pdq_ctx* c, const double* cov, con
     return PDQ_OK;
 }
 
+// Trend + prior in one launch with host vectors: the orchestrator's whole `fit_dispersion_trend` loop (dds.py:1199-1275) and
+// `fit_dispersion_prior` (dds.py:840-884) -- what pdq_trend_fit_dev does for the resident pipeline.  out16 = TrendOut record.
+extern "C" int pdq_trend_prior(pdq_ctx* c, const double* means, const double* genewise, size_t n, double min_disp, double max_disp,
+                               double trigamma_c, double* out16, double* fitted_out) {
+    CHECK_CTX(c);
+    if (!means || !genewise || !out16 || n == 0) return fail(c, PDQ_ERR_INVALID, "pdq_trend_prior: bad arguments");
+    void *dm, *dg, *df, *dout;
+    if (int e = ensure(c, kBufC, n * 8, &dm)) return e;
+    if (int e = ensure(c, kBufD, n * 8, &dg)) return e;
+    if (int e = ensure(c, kBufF, n * 8, &df)) return e;
+    if (int e = ensure(c, kBufMisc, 256, &dout)) return e;
+    CU(c, cudaMemcpyAsync(dm, means, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dg, genewise, n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (int e = pdq_trend_fit_dev(c, (const double*)dm, (const double*)dg, n, min_disp, max_disp, trigamma_c, (double*)dout,
+                                  fitted_out ? (double*)df : nullptr))
+        return e;
+    CU(c, cudaMemcpyAsync(out16, dout, 16 * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (fitted_out) CU(c, cudaMemcpyAsync(fitted_out, df, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return PDQ_OK;
+}
+
 // --------------------------------------------------------------------------------------------- NCCL gene-shard exchange
 static int nccl_load(pdq_ctx* c) {
     if (c->nccl.handle) return 0;
@@ -1069,7 +1120,10 @@ static int nccl_load(pdq_ctx* c) {
     c->nccl.AllGather = (decltype(c->nccl.AllGather))sym("ncclAllGather");
     c->nccl.CommDestroy = (decltype(c->nccl.CommDestroy))sym("ncclCommDestroy");
     c->nccl.GetErrorString = (decltype(c->nccl.GetErrorString))sym("ncclGetErrorString");
-    if (!c->nccl.GetUniqueId || !c->nccl.CommInitRank || !c->nccl.AllGather || !c->nccl.CommDestroy)
+    c->nccl.GroupStart = (decltype(c->nccl.GroupStart))sym("ncclGroupStart");
+    c->nccl.GroupEnd = (decltype(c->nccl.GroupEnd))sym("ncclGroupEnd");
+    if (!c->nccl.GetUniqueId || !c->nccl.CommInitRank || !c->nccl.AllGather || !c->nccl.CommDestroy || !c->nccl.GroupStart ||
+        !c->nccl.GroupEnd)
         return fail(c, PDQ_ERR_NCCL, "libnccl is missing a required symbol");
     return 0;
 }
@@ -1112,6 +1166,32 @@ extern "C" int pdq_allgather_f64_dev(pdq_ctx* c, const double* send, double* rec
     }
     ncclResult_t r = c->nccl.AllGather(send, recv, count, kNcclFloat64, c->comm, c->stream);
     if (r != 0) return nccl_fail(c, r, "ncclAllGather");
+    return PDQ_OK;
+}
+
+// k equal-count all-gathers issued as ONE NCCL group (one fused launch on the stream): the exchange of the per-gene vectors the
+// trend / prior step needs from every gene shard, and the end-of-call exchange of the result tables
+extern "C" int pdq_allgather_multi_f64_dev(pdq_ctx* c, int k, const double* const* send, double* const* recv, size_t count) {
+    CHECK_CTX(c);
+    if (k < 1 || k > 16 || !send || !recv) return fail(c, PDQ_ERR_INVALID, "pdq_allgather_multi_f64_dev: bad arguments");
+    for (int i = 0; i < k; ++i)
+        if (!send[i] || !recv[i]) return fail(c, PDQ_ERR_INVALID, "pdq_allgather_multi_f64_dev: null buffer");
+    if (!c->comm) {  // single rank: the gathers are copies
+        for (int i = 0; i < k; ++i)
+            if (send[i] != recv[i]) CU(c, cudaMemcpyAsync(recv[i], send[i], count * 8, cudaMemcpyDeviceToDevice, c->stream));
+        return PDQ_OK;
+    }
+    ncclResult_t r = c->nccl.GroupStart();
+    if (r != 0) return nccl_fail(c, r, "ncclGroupStart");
+    for (int i = 0; i < k; ++i) {
+        r = c->nccl.AllGather(send[i], recv[i], count, kNcclFloat64, c->comm, c->stream);
+        if (r != 0) {
+            c->nccl.GroupEnd();
+            return nccl_fail(c, r, "ncclAllGather");
+        }
+    }
+    r = c->nccl.GroupEnd();
+    if (r != 0) return nccl_fail(c, r, "ncclGroupEnd");
     return PDQ_OK;
 }
 

@@ -10,7 +10,10 @@
 // tests/test_emu_parity.py through the host emulator, which compiles the same polynomials).
 #pragma once
 
+#include <string.h>
+
 #include "pdq_math.cuh"
+#include "pdq_tables.h"
 
 namespace pdq {
 
@@ -187,6 +190,87 @@ PDQ_HD double fast_exp(double x) {
 #else
     return ldexp(p, k);
 #endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Table-driven logarithm / exponential (round 2).  The ncu captures of round 1 showed both heavy kernels bound by the FP64
+// pipe with a third of its instructions spent inside fast_log (a division -- seed + 2 Newton steps + residual -- and a
+// degree-6 polynomial: ~24 FP64 instructions).  With a 512-entry table of (c ~ 1/m, -log c) staged in shared memory the
+// argument reduction is ONE fma, r = m c - 1 with |r| <= 2^-10 (first interval: [0, 2^-9)), and log1p(r) is its Taylor
+// polynomial of degree 6: 10 FP64 instructions and one 16-byte shared-memory read.  Table construction and the sqrt(2) split
+// that keeps the result relatively accurate around x = 1: scripts/gen_math_tables.py.  <= 1.5 ulp (tests/test_emu_parity.py).
+// `tab` points at kMathTab (shared memory on the device, host_math_table() in the emulator).
+// ---------------------------------------------------------------------------------------------------------------------
+inline const double* host_math_table() {
+    static const double t[kMathTabLen] = {PDQ_MATH_TABLE_VALUES};
+    return t;
+}
+
+// x positive, normal, finite (callers track violations like for fast_log_nb)
+PDQ_HD double tlog_nb(double x, const double* tab) {
+#if defined(__CUDA_ARCH__)
+    const int hi = __double2hiint(x);
+    const int idx = (hi >> (20 - kLogTabBits)) & (kLogTabN - 1);
+    // exponent, +1 when the mantissa lies at or above the table's sqrt(2) split: the bias makes exactly those mantissas carry
+    const int e = (hi + (0x00100000 - (kLogTabSplit << (20 - kLogTabBits))) - 0x3ff00000) >> 20;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    const double2 cl = reinterpret_cast<const double2*>(tab)[idx];
+    const double c = cl.x, l = cl.y;
+#else
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    const int hi = (int)(u >> 32);
+    const int idx = (hi >> (20 - kLogTabBits)) & (kLogTabN - 1);
+    const int e = ((hi >> 20) & 0x7ff) - 1023 + (idx >= kLogTabSplit ? 1 : 0);
+    u = (u & 0x000fffffffffffffull) | 0x3ff0000000000000ull;
+    double m;
+    memcpy(&m, &u, 8);
+    const double c = tab[2 * idx], l = tab[2 * idx + 1];
+#endif
+    const double r = fma(m, c, -1.0);
+    // log1p(r) = r + r^2 (-1/2 + r (1/3 + r (-1/4 + r (1/5 - r/6))))
+    double q = fma(r, -1.0 / 6.0, 0.2);
+    q = fma(q, r, -0.25);
+    q = fma(q, r, 1.0 / 3.0);
+    q = fma(q, r, -0.5);
+    const double t = fma(r * r, q, r) + l;
+    const double ed = (double)e;
+    return fma(ed, kLn2Hi, fma(ed, kLn2Lo, t));
+}
+
+// guarded version: <= 0, denormal, inf, NaN take the libm / libdevice path
+PDQ_HD double tlog(double x, const double* tab) {
+    if (!(x >= 2.2250738585072014e-308) || !(x <= 1.7976931348623157e308)) return log(x);
+    return tlog_nb(x, tab);
+}
+
+PDQ_CONST double kLn2o64Hi = 6.93147180369123816490e-01 / 64.0;  // exact scalings of the fdlibm split
+PDQ_CONST double kLn2o64Lo = 1.90821492927058770002e-10 / 64.0;
+PDQ_CONST double k64oLn2 = 64.0 * 1.44269504088896338700e+00;
+
+// e^x = 2^(k >> 6) * 2^((k & 63) / 64) * e^r,  k = rint(64 x / ln2), |r| <= ln2 / 128; needs |x| < 700
+PDQ_HD double texp_nb(double x, const double* tab) {
+    const double kd = rint(x * k64oLn2);
+    const double r = fma(-kd, kLn2o64Lo, fma(-kd, kLn2o64Hi, x));
+    const int k = (int)kd;
+    const double T = tab[2 * kLogTabN + (k & 63)];
+    // e^r - 1 = r + r^2 (1/2 + r (1/6 + r (1/24 + r (1/120 + r/720))))
+    double q = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+    q = fma(q, r, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    const double p = fma(r * r, q, r);
+    const double v = fma(T, p, T);  // in [1, 2): scaling by 2^(k >> 6) is an exponent-field addition (result stays normal)
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+#else
+    return ldexp(v, k >> 6);
+#endif
+}
+
+PDQ_HD double texp(double x, const double* tab) {
+    if (!(fabs(x) < 700.0)) return exp(x);
+    return texp_nb(x, tab);
 }
 
 }  // namespace pdq

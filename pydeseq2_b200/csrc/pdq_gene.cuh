@@ -81,13 +81,18 @@ struct Group {
     }
 };
 
-// staged design pack (shared memory on the device): X column-major [P][Npad], sf, log sf
+// staged design pack (shared memory on the device), ROW-major: row n = [ x_n0 .. x_n,p-1 | sf_n | log sf_n | pad ], RS doubles
+// per row (p + 2 rounded up to even, so every row is 16-byte aligned: a sample's design row + size factor is one or two
+// 128-bit shared-memory reads at immediate offsets from one walking pointer).  `sf` / `lsf` = X + p / X + p + 1, indexed [n * RS].
+// Row N (one past the samples) holds the column maxima max_n |x_nj| (used to bound |x'beta| once per sweep).
+constexpr int design_row_stride(int p) { return (p + 3) & ~1; }
 struct DesignS {
     const double* X;
     const double* sf;
     const double* lsf;
     int N;
-    int Npad;
+    int RS;
+    const double* mtab = nullptr;  // kMathTab of the table-driven log / exp (shared memory; set by the kernels that use it)
 };
 
 template <int P>
@@ -95,10 +100,27 @@ struct SmallMat {
     double v[P * P];
 };
 
+// A lane's walk over its samples n = si, si + T, ... of one (N, G) column, `p` pointing at the first of them and `step` = T * ld:
+// four loads are issued before the first is used, so that a streaming pass keeps several requests in flight per lane (a
+// one-load-per-trip walk is bound by the memory latency, not the bandwidth).  `f(n, value)` is called in increasing n.
+template <class V, class F>
+PDQ_HD void walk4(const Group& grp, int N, const V* p, int64_t step, F&& f) {
+    int n = grp.si;
+    const int T = grp.T;
+    for (; n + 3 * T < N; n += 4 * T, p += 4 * step) {
+        const V v0 = p[0], v1 = p[step], v2 = p[2 * step], v3 = p[3 * step];
+        f(n, v0);
+        f(n + T, v1);
+        f(n + 2 * T, v2);
+        f(n + 3 * T, v3);
+    }
+    for (; n < N; n += T, p += step) f(n, *p);
+}
+
 template <int P>
 PDQ_HD void load_x(const DesignS& d, int n, double (&x)[P]) {
 #pragma unroll
-    for (int j = 0; j < P; ++j) x[j] = d.X[j * d.Npad + n];
+    for (int j = 0; j < P; ++j) x[j] = d.X[n * design_row_stride(P) + j];
 }
 
 template <int P>
@@ -124,13 +146,13 @@ PDQ_HD void linmu_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pi
     double v[P];
 #pragma unroll
     for (int j = 0; j < P; ++j) v[j] = 0.0;
-    for (int n = grp.si; n < d.N; n += grp.T) {
+    walk4(grp, d.N, y + (int64_t)grp.si * ld, (int64_t)grp.T * ld, [&](int n, int64_t c) {
         double x[P];
         load_x<P>(d, n, x);
-        const double t = (double)y[n * ld] / d.sf[n];
+        const double t = (double)c / d.sf[n * d.RS];
 #pragma unroll
         for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
-    }
+    });
     group_sum_vec<P>(grp, v);
     double beta[P];
 #pragma unroll
@@ -147,7 +169,7 @@ PDQ_HD void linmu_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pi
         double e = 0.0;
 #pragma unroll
         for (int j = 0; j < P; ++j) e = fma(x[j], beta[j], e);
-        const double m = d.sf[n] * e;
+        const double m = d.sf[n * d.RS] * e;
         mu_out[n * ld_out] = (m < min_mu) ? min_mu : m;  // np.maximum (NaN propagates)
     }
 }
@@ -163,12 +185,12 @@ constexpr int kPsiK = 32;
 // log(k!) for k < kPsiK
 PDQ_CONST double kLogFact[kPsiK] = {0.0, 0.0, 0.693147180559945, 1.7917594692280554, 3.178053830347945, 4.787491742782047, 6.579251212010102, 8.525161361065415, 10.604602902745249, 12.801827480081467, 15.104412573075514, 17.502307845873887, 19.987214495661885, 22.55216385312342, 25.191221182738683, 27.89927138384089, 30.671860106080672, 33.50507345013689, 36.39544520803305, 39.339884187199495, 42.335616460753485, 45.38013889847691, 48.47118135183522, 51.60667556776438, 54.78472939811232, 58.00360522298052, 61.26170176100201, 64.55753862700634, 67.88974313718153, 71.257038967168, 74.65823634883017, 78.0922235533153};
 
-PDQ_HD void build_lgamma_table(const Group& grp, double* tab, double r) {
+PDQ_HD void build_lgamma_table(const Group& grp, double* tab, double r, const double* mtab) {
     const int seg = kPsiK / grp.T;  // T in {1,...,32} divides 32
     const int k0 = grp.si * seg;
     double part = 0.0;
     for (int k = k0; k < k0 + seg; ++k) {
-        const double lg = fast_log(r + (double)k);
+        const double lg = tlog(r + (double)k, mtab);
         tab[k] = lg;
         part += lg;
     }
@@ -179,6 +201,97 @@ PDQ_HD void build_lgamma_table(const Group& grp, double* tab, double r) {
         run += lg;
     }
     grp.sync();
+}
+
+// =============================================================================================
+// (a3) wald_test -- utils.py:718-811.
+// =============================================================================================
+template <int P>
+struct WaldParams {
+    double ridge[P * P];
+    double contrast[P];
+    double lfc_null;
+    int alt;
+};
+
+// the per-gene algebra once M = X^T W X (W from the caller's mu) is known: H = (M + ridge)^-1, SE, statistic, p-value
+template <int P>
+PDQ_HD void wald_finish(const Group& grp, const Sym<P>& M, const WaldParams<P>& prm, const double* lfc, double* p_out,
+                        double* stat_out, double* se_out, bool valid) {
+    Sym<P> L = M, H;
+#pragma unroll
+    for (int i = 0; i < P; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L.a[tri(i, j)] += prm.ridge[i * P + j];
+    chol<P>(L);
+    chol_inverse<P>(L, H);
+    double Hc[P], MHc[P];
+    sym_matvec<P>(H, prm.contrast, Hc);
+    sym_matvec<P>(M, Hc, MHc);
+    double q = 0.0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) q = fma(Hc[j], MHc[j], q);
+    const double se = sqrt(q);
+    double b[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) b[j] = lfc[j];
+    const double t0 = prm.lfc_null;
+    double stat, pv;
+    // each variant applies the elementwise transform to every coefficient, then dots with the contrast
+    auto greater = [&](double t, double& s, double& p) {
+        s = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], fmax((b[j] - t) / se, 0.0), s);
+        p = norm_sf(s);
+    };
+    auto less = [&](double t, double& s, double& p) {
+        s = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], fmin((b[j] - t) / se, 0.0), s);
+        p = norm_sf(fabs(s));
+    };
+    if (prm.alt == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], b[j] - t0, s);
+        stat = s / se;
+        pv = 2.0 * norm_sf(fabs(stat));
+    } else if (prm.alt == 1) {  // greaterAbs
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], sgn(b[j]) * fmax((fabs(b[j]) - t0) / se, 0.0), s);
+        stat = s;
+        pv = 2.0 * norm_sf(fabs(s));
+    } else if (prm.alt == 2) {  // lessAbs
+        double sa, pa, sb, pb;
+        greater(-fabs(t0), sa, pa);
+        less(fabs(t0), sb, pb);
+        stat = (fabs(sb) < fabs(sa)) ? sb : sa;  // min(sa, sb, key=abs): first wins ties
+        pv = (pb > pa) ? pb : pa;                // max(pa, pb)
+    } else if (prm.alt == 3) {
+        greater(t0, stat, pv);
+    } else {
+        less(t0, stat, pv);
+    }
+    if (valid && grp.si == 0) {
+        *p_out = pv;
+        *stat_out = stat;
+        *se_out = se;
+    }
+}
+
+template <int P>
+PDQ_HD void wald_gene(const Group& grp, const DesignS& d, const WaldParams<P>& prm, double disp, const double* lfc,
+                      const double* mu, int64_t ld_mu, double* p_out, double* stat_out, double* se_out, bool valid) {
+    Sym<P> M;
+    sym_zero<P>(M);
+    walk4(grp, d.N, mu + (int64_t)grp.si * ld_mu, (int64_t)grp.T * ld_mu, [&](int n, double m) {
+        double x[P];
+        load_x<P>(d, n, x);
+        sym_rank1<P>(M, m / fma(m, disp, 1.0), x);
+    });
+    group_sum_sym<P>(grp, M);
+    wald_finish<P>(grp, M, prm, lfc, p_out, stat_out, se_out, valid);
 }
 
 // =============================================================================================
@@ -199,41 +312,40 @@ struct IrlsParams {
 // eta = x'beta repeats bit for bit and exp(eta) -- a third of the body's instructions -- is carried over instead of recomputed
 // (same value, results unchanged).  All lanes of a warp look at the same rows, so the skip is close to warp-uniform.
 template <int P, bool NB, bool MEMO>
-PDQ_HD void irls_sample(const double* xp, int Npad, double yv, const double (&beta)[P], double alpha, double r,
-                        double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P], double& S, bool& odd, double& eta_prev,
-                        double& exp_prev) {
+PDQ_HD void irls_sample(const double* xp, const double* mtab, double yv, const double (&beta)[P], double alpha,
+                        double r, double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P], double& S, bool& odd,
+                        double& eta_prev, double& exp_prev) {
     double x[P];
 #pragma unroll
-    for (int j = 0; j < P; ++j) x[j] = xp[j * Npad];
-    const double sfn = xp[P * Npad], lsfn = xp[(P + 1) * Npad];      // sf and log sf follow X in the pack
+    for (int j = 0; j < P; ++j) x[j] = xp[j];
+    const double sfn = xp[P], lsfn = xp[P + 1];                      // sf and log sf close the design row
     double eta = 0.0;
 #pragma unroll
     for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
-    if (NB) odd = odd || !(fabs(eta) < 300.0);
     double ex;
     if (MEMO) {
         if (eta != eta_prev) {
-            exp_prev = NB ? fast_exp_nb(eta) : fast_exp(eta);
+            exp_prev = NB ? texp_nb(eta, mtab) : fast_exp(eta);
             eta_prev = eta;
         }
         ex = exp_prev;
     } else {
-        ex = NB ? fast_exp_nb(eta) : fast_exp(eta);
+        ex = NB ? texp_nb(eta, mtab) : fast_exp(eta);
     }
     const double mu_raw = sfn * ex;
     const bool cl = mu_raw < min_mu;
     const double mu = cl ? min_mu : mu_raw;                            // np.maximum(sf*exp(X b), min_mu)
-    const double lmu_sf = cl ? (log_min_mu - lsfn) : eta;              // log(mu / sf)
     const double lmu = cl ? log_min_mu : (eta + lsfn);                 // log(mu)
+    const double lmu_sf = lmu - lsfn;                                  // log(mu / sf)
     const double den = fma(mu, alpha, 1.0);
-    const double q = NB ? fast_rcp(mu * den) : 1.0 / (mu * den);
-    const double W = mu * mu * q;                                      // mu / (1 + mu alpha)
-    const double z = fma(yv - mu, den * q, lmu_sf);                    // log(mu/sf) + (y - mu)/mu
+    // W = mu / (1 + mu alpha);  W z = W log(mu/sf) + W (y - mu)/mu = W log(mu/sf) + (y - mu) / (1 + mu alpha)
+    const double iden = NB ? fast_rcp(den) : 1.0 / den;
+    const double W = mu * iden;
+    const double Wz = fma(yv - mu, iden, W * lmu_sf);
     sym_rank1<P>(A, W, x);
-    const double Wz = W * z;
 #pragma unroll
     for (int j = 0; j < P; ++j) b[j] = fma(Wz, x[j], b[j]);
-    S += fma(yv + r, NB ? fast_log_nb(r + mu) : fast_log(r + mu), -yv * lmu);
+    S += fma(yv + r, NB ? tlog_nb(r + mu, mtab) : fast_log(r + mu), -yv * lmu);
 }
 
 template <int P, bool NB, bool MEMO>
@@ -245,9 +357,10 @@ PDQ_HD bool irls_sweep_t(const Group& grp, const DesignS& d, const int64_t* y, i
     S = 0.0;
     bool odd = false;
     const int T = grp.T;
+    constexpr int RS = design_row_stride(P);
     const int64_t ystep = (int64_t)T * ld;
     const int64_t* yp = y + (int64_t)grp.si * ld;
-    const double* xp = d.X + grp.si;
+    const double* xp = d.X + grp.si * RS;
     int n = grp.si;
     // NaN never compares equal: the first sample always computes its exponential
     double eta_prev = __builtin_nan(""), exp_prev = 0.0;
@@ -257,38 +370,38 @@ PDQ_HD bool irls_sweep_t(const Group& grp, const DesignS& d, const int64_t* y, i
 #if PDQ_IRLS_UNROLL == 4
     // experiment (default off): four samples per trip -- more independent exp / log / reciprocal chains in flight per lane
     // against the fixed-latency dependency stalls of the capture; costs registers
-    for (; n + 3 * T < d.N; n += 4 * T, yp += 4 * ystep, xp += 4 * T) {
+    for (; n + 3 * T < d.N; n += 4 * T, yp += 4 * ystep, xp += 4 * T * RS) {
         const double y0 = (double)yp[0], y1 = (double)yp[ystep], y2 = (double)yp[2 * ystep], y3 = (double)yp[3 * ystep];
-        irls_sample<P, NB, MEMO>(xp, d.Npad, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
-        irls_sample<P, NB, MEMO>(xp + T, d.Npad, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
-        irls_sample<P, NB, MEMO>(xp + 2 * T, d.Npad, y2, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
-        irls_sample<P, NB, MEMO>(xp + 3 * T, d.Npad, y3, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp, d.mtab, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp + T * RS, d.mtab, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp + 2 * T * RS, d.mtab, y2, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp + 3 * T * RS, d.mtab, y3, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
     }
-    for (; n + T < d.N; n += 2 * T, yp += 2 * ystep, xp += 2 * T) {
+    for (; n + T < d.N; n += 2 * T, yp += 2 * ystep, xp += 2 * T * RS) {
         const double y0 = (double)yp[0], y1 = (double)yp[ystep];
-        irls_sample<P, NB, MEMO>(xp, d.Npad, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
-        irls_sample<P, NB, MEMO>(xp + T, d.Npad, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp, d.mtab, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp + T * RS, d.mtab, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
     }
 #elif PDQ_PREFETCH
     int64_t c0 = (n + T < d.N) ? yp[0] : 0, c1 = (n + T < d.N) ? yp[ystep] : 0;
-    for (; n + T < d.N; n += 2 * T, yp += 2 * ystep, xp += 2 * T) {
+    for (; n + T < d.N; n += 2 * T, yp += 2 * ystep, xp += 2 * T * RS) {
         const double y0 = (double)c0, y1 = (double)c1;
         if (n + 3 * T < d.N) {
             c0 = yp[2 * ystep];
             c1 = yp[3 * ystep];
         }
-        irls_sample<P, NB, MEMO>(xp, d.Npad, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
-        irls_sample<P, NB, MEMO>(xp + T, d.Npad, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp, d.mtab, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp + T * RS, d.mtab, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
     }
 #else
-    for (; n + T < d.N; n += 2 * T, yp += 2 * ystep, xp += 2 * T) {
+    for (; n + T < d.N; n += 2 * T, yp += 2 * ystep, xp += 2 * T * RS) {
         const double y0 = (double)yp[0], y1 = (double)yp[ystep];
-        irls_sample<P, NB, MEMO>(xp, d.Npad, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
-        irls_sample<P, NB, MEMO>(xp + T, d.Npad, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp, d.mtab, y0, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp + T * RS, d.mtab, y1, beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
     }
 #endif
     if (n < d.N)
-        irls_sample<P, NB, MEMO>(xp, d.Npad, (double)yp[0], beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
+        irls_sample<P, NB, MEMO>(xp, d.mtab, (double)yp[0], beta, alpha, r, min_mu, log_min_mu, A, b, S, odd, eta_prev, exp_prev);
     return odd;
 }
 
@@ -296,8 +409,15 @@ template <int P>
 PDQ_HD void irls_sweep(const Group& grp, const DesignS& d, const int64_t* y, int64_t ld, const double (&beta)[P],
                        double alpha, double r, double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P],
                        double& S, bool few_rows) {
-    // the branch-free cores need r = 1/alpha positive finite and a positive clamp
+    // the branch-free cores need r = 1/alpha positive finite, a positive clamp and |x'beta| < 300 for every sample; the last
+    // is checked once per sweep through |x'beta| <= sum_j |beta_j| max_n |x_nj| (the column maxima close the design pack)
     bool odd = !(alpha > 0.0 && r > 0.0 && r < 1e300 && min_mu > 0.0);
+    {
+        double bound = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) bound = fma(fabs(beta[j]), d.X[d.N * design_row_stride(P) + j], bound);
+        odd = odd || !(bound < 300.0);
+    }
     if (!odd) {
         odd = few_rows ? irls_sweep_t<P, true, true>(grp, d, y, ld, beta, alpha, r, min_mu, log_min_mu, A, b, S)
                        : irls_sweep_t<P, true, false>(grp, d, y, ld, beta, alpha, r, min_mu, log_min_mu, A, b, S);
@@ -317,14 +437,17 @@ template <int P>
 PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pinv, const IrlsParams& prm,
                       const int64_t* y, int64_t ld, double alpha, double* beta_out, double* mu_out,
                       double* hat_out, int64_t ld_out, double* conv_out, int* status_out, bool valid, double* lg_tab,
-                      const double* logfact) {
+                      const double* logfact, const WaldParams<P>* wald = nullptr, double* wald_p = nullptr,
+                      double* wald_stat = nullptr, double* wald_se = nullptr) {
+    // wald != nullptr: also the Wald test of this fit (ds.py:303-360 / utils.py:718-811) from the sums of the last sweep -- the
+    // caller would otherwise re-read the mu written below (8 N G bytes) just to rebuild X^T W X
     // lg_tab: kPsiK doubles of per-gene scratch (shared memory); logfact: log(k!) table, k < kPsiK (shared memory)
     const double r = 1.0 / alpha;
     const double Nd = (double)d.N;
     const double log_min_mu = log(prm.min_mu);
     const bool tab_ok = (r > 0.0) && (r < 1e300);  // NaN / non-positive dispersion: plain lgamma path, IEEE semantics
     grp.sync();
-    if (tab_ok) build_lgamma_table(grp, lg_tab, r);
+    if (tab_ok) build_lgamma_table(grp, lg_tab, r, d.mtab);
 
     // ---- start value (utils.py:349-357) and the mu-independent part of nb_nll ----------------
     double v[P];
@@ -339,14 +462,14 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
         load_x<P>(d, nn, x);
         const long long yi = y[nn * ld];
         const double yv = (double)yi;
-        const double q = fast_div(yv, d.sf[nn]);
+        const double q = fast_div(yv, d.sf[nn * d.RS]);
         double t;
         if (prm.full_rank) {
-            t = fast_log(q + 0.1);
+            t = tlog(q + 0.1, d.mtab);
 #pragma unroll
             for (int j = 0; j < P; ++j) v[j] = fma(x[j], in ? t : 0.0, v[j]);
         } else {
-            t = fast_log(q);
+            t = tlog(q, d.mtab);
             logmean += in ? t : 0.0;
         }
         // lgamma(y + 1) - lgamma(y + r): table reads for small counts, unshifted Stirling series otherwise
@@ -354,7 +477,7 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
         double term = small ? logfact[(int)(yi & (kPsiK - 1))] - lg_tab[(int)(yi & (kPsiK - 1))] : 0.0;
         if (grp.any(in && !small)) {
             const double z1 = small ? 40.0 : yv + 1.0, zr = small ? 40.0 : yv + r;
-            const double big = tab_ok ? lgamma_asym(z1, fast_log(z1)) - lgamma_asym(zr, fast_log(zr))
+            const double big = tab_ok ? lgamma_asym(z1, tlog(z1, d.mtab)) - lgamma_asym(zr, tlog(zr, d.mtab))
                                       : lgamma_pos(yv + 1.0) - lgamma_pos(yv + r);
             term = small ? term : big;
         }
@@ -429,20 +552,43 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
         chol<P>(L);
         chol_inverse<P>(L, Hinv);
     }
-    if (!valid) return;
+    double eta_prev = __builtin_nan(""), exp_prev = 0.0;
+    Sym<P> Dc;  // run_wald_test uses the UNCLAMPED mu (ds.py:320-324): correction of A for the samples on the min_mu clamp
+    sym_zero<P>(Dc);
+    bool clamped = false;
     for (int n = grp.si; n < d.N; n += grp.T) {
         double x[P];
         load_x<P>(d, n, x);
         double eta = 0.0;
 #pragma unroll
         for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
-        const double mu_raw = d.sf[n] * fast_exp(eta);
-        const double mu = (mu_raw < prm.min_mu) ? prm.min_mu : mu_raw;
+        if (eta != eta_prev) {  // same carry-over as the sweeps: equal design rows share their exponential
+            exp_prev = texp(eta, d.mtab);
+            eta_prev = eta;
+        }
+        const double mu_raw = d.sf[n * d.RS] * exp_prev;
+        const bool cl = mu_raw < prm.min_mu;
+        const double mu = cl ? prm.min_mu : mu_raw;
         const double W = fast_div(mu, fma(mu, alpha, 1.0));
-        mu_out[n * ld_out] = mu_raw;
-        hat_out[n * ld_out] = W * sym_quad<P>(Hinv, x);
+        if (valid) {
+            mu_out[(int64_t)n * ld_out] = mu_raw;
+            hat_out[(int64_t)n * ld_out] = W * sym_quad<P>(Hinv, x);
+        }
+        if (wald && cl) {
+            clamped = true;
+            sym_rank1<P>(Dc, mu_raw / fma(mu_raw, alpha, 1.0) - W, x);
+        }
     }
-    if (grp.si == 0) {
+    if (wald) {
+        Sym<P> M = A;
+        if (grp.any(clamped)) {
+            group_sum_sym<P>(grp, Dc);
+#pragma unroll
+            for (int k = 0; k < P * (P + 1) / 2; ++k) M.a[k] += Dc.a[k];
+        }
+        wald_finish<P>(grp, M, *wald, beta, wald_p, wald_stat, wald_se, valid);
+    }
+    if (valid && grp.si == 0) {
 #pragma unroll
         for (int j = 0; j < P; ++j) beta_out[j] = beta[j];
         *conv_out = 1.0;  // IRLS exits are "converged" (utils.py:365); the optimiser branch overwrites
@@ -472,10 +618,10 @@ PDQ_HD void irls_obj_sweep(const Group& grp, const DesignS& d, const int64_t* y,
         double eta = 0.0;
 #pragma unroll
         for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
-        const double mu_raw = d.sf[n] * exp(eta);
+        const double mu_raw = d.sf[n * d.RS] * exp(eta);
         const bool cl = mu_raw < min_mu;
         const double mu = cl ? min_mu : mu_raw;
-        const double lmu = cl ? log_min_mu : (eta + d.lsf[n]);
+        const double lmu = cl ? log_min_mu : (eta + d.lsf[n * d.RS]);
         f += fma(yv + r, log(r + mu), -yv * lmu);
         // df of the reference: -X^T y + ((r + y) mu / (r + mu)) X  (treats d mu / d eta = mu everywhere)
         const double t = (r + yv) * mu / (r + mu);
@@ -499,7 +645,8 @@ PDQ_HD void irls_obj_sweep(const Group& grp, const DesignS& d, const int64_t* y,
 template <int P>
 PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pinv, const IrlsParams& prm,
                                 const int64_t* y, int64_t ld, double alpha, double* beta_out, double* mu_out,
-                                double* hat_out, int64_t ld_out, double* conv_out, bool valid) {
+                                double* hat_out, int64_t ld_out, double* conv_out, bool valid, const WaldParams<P>* wald = nullptr,
+                                double* wald_p = nullptr, double* wald_stat = nullptr, double* wald_se = nullptr) {
     const double r = 1.0 / alpha;
     const double log_min_mu = log(prm.min_mu);
     // start value: same as irls_gene (utils.py:349-357, `beta_init`)
@@ -510,7 +657,7 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
     for (int n = grp.si; n < d.N; n += grp.T) {
         double x[P];
         load_x<P>(d, n, x);
-        const double q = (double)y[n * ld] / d.sf[n];
+        const double q = (double)y[n * ld] / d.sf[n * d.RS];
         if (prm.full_rank) {
             const double t = log(q + 0.1);
 #pragma unroll
@@ -627,19 +774,25 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
         }
     }
     // outputs exactly like the tail of irls_solver: W from clamped mu, ridge 1e-6, mu unclamped
-    Sym<P> A;
+    Sym<P> A, M;  // M: the Wald test's X^T W X, W from the unclamped mu
     sym_zero<P>(A);
+    sym_zero<P>(M);
     for (int n = grp.si; n < d.N; n += grp.T) {
         double x[P];
         load_x<P>(d, n, x);
         double eta = 0.0;
 #pragma unroll
         for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
-        const double mu_raw = d.sf[n] * exp(eta);
+        const double mu_raw = d.sf[n * d.RS] * exp(eta);
         const double mu = (mu_raw < prm.min_mu) ? prm.min_mu : mu_raw;
         sym_rank1<P>(A, mu / fma(mu, alpha, 1.0), x);
+        if (wald) sym_rank1<P>(M, mu_raw / fma(mu_raw, alpha, 1.0), x);
     }
     group_sum_sym<P>(grp, A);
+    if (wald) {
+        group_sum_sym<P>(grp, M);
+        wald_finish<P>(grp, M, *wald, beta, wald_p, wald_stat, wald_se, valid);
+    }
     Sym<P> Hinv;
 #pragma unroll
     for (int i = 0; i < P; ++i) A.a[tri(i, i)] += kRidge;
@@ -652,7 +805,7 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
         double eta = 0.0;
 #pragma unroll
         for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
-        const double mu_raw = d.sf[n] * exp(eta);
+        const double mu_raw = d.sf[n * d.RS] * exp(eta);
         const double mu = (mu_raw < prm.min_mu) ? prm.min_mu : mu_raw;
         mu_out[n * ld_out] = mu_raw;
         hat_out[n * ld_out] = mu / fma(mu, alpha, 1.0) * sym_quad<P>(Hinv, x);
@@ -722,16 +875,21 @@ PDQ_HD void build_psi_tri_tables(const Group& grp, double* tab, double r) {
 // contribution of two samples (or one, when !two) to the derivative sums; NB as in irls_sample.
 // CURV: also S2 = sum 1/(r+mu) - psi'(y+r) - (y-mu)/(r+mu)^2, the r-derivative of the summand of Sg.
 template <int P, bool NB, bool CURV>
-PDQ_HD void alpha_pair(const Group& grp, const double* xp0, const double* xp1, int Npad, long long yi0, long long yi1,
+PDQ_HD void alpha_pair(const Group& grp, const double* xp0, const double* xp1, const double* mtab, long long yi0, long long yi1,
                        double m0, double m1, bool one, bool two, double r, bool cr_reg, const double* psi_tab, double& Sg,
                        Sym<P>& A, Sym<P>& B, bool& odd, double& S2) {
     // `one` / `two`: which of the two samples exist for this lane (masked-out slots carry y = 0, mu = 1)
     const double yv0 = (double)yi0, yv1 = (double)yi1;
     const bool big0 = one && ((yi0 >= kPsiK) || (yi0 < 0)), big1 = two && ((yi1 >= kPsiK) || (yi1 < 0));
+#if defined(__CUDA_ARCH__)
+    // means outside [+0, ~1e300) (negative, NaN, inf) send the gene to the guarded path: one integer compare on the high word
+    if (NB) odd = odd || ((unsigned)__double2hiint(m0) >= 0x7e300000u) || ((unsigned)__double2hiint(m1) >= 0x7e300000u);
+#else
     if (NB) odd = odd || !(m0 >= 0.0 && m0 < 1e300) || !(m1 >= 0.0 && m1 < 1e300);
+#endif
     const double rm0 = r + m0, rm1 = r + m1;
     const double inv0 = NB ? fast_rcp(rm0) : 1.0 / rm0, inv1 = NB ? fast_rcp(rm1) : 1.0 / rm1;
-    const double lg0 = NB ? fast_log_nb(rm0) : fast_log(rm0), lg1 = NB ? fast_log_nb(rm1) : fast_log(rm1);
+    const double lg0 = NB ? tlog_nb(rm0, mtab) : fast_log(rm0), lg1 = NB ? tlog_nb(rm1, mtab) : fast_log(rm1);
     double dg0 = psi_tab[(int)(yi0 & (kPsiK - 1))], dg1 = psi_tab[(int)(yi1 & (kPsiK - 1))];
     double tg0 = 0.0, tg1 = 0.0;
     if (CURV) {
@@ -740,8 +898,8 @@ PDQ_HD void alpha_pair(const Group& grp, const double* xp0, const double* xp1, i
     }
     if (grp.any(big0 || big1)) {  // warp-uniform: the unshifted series only when some lane holds a count >= kPsiK
         const double z0 = big0 ? yv0 + r : r + (double)kPsiK, z1 = big1 ? yv1 + r : r + (double)kPsiK;
-        const double a0 = digamma_asym(z0, NB ? fast_log_nb(z0) : fast_log(z0));
-        const double a1 = digamma_asym(z1, NB ? fast_log_nb(z1) : fast_log(z1));
+        const double a0 = digamma_asym(z0, NB ? tlog_nb(z0, mtab) : fast_log(z0));
+        const double a1 = digamma_asym(z1, NB ? tlog_nb(z1, mtab) : fast_log(z1));
         dg0 = big0 ? a0 : dg0;
         dg1 = big1 ? a1 : dg1;
         if (CURV) {
@@ -759,12 +917,12 @@ PDQ_HD void alpha_pair(const Group& grp, const double* xp0, const double* xp1, i
     if (cr_reg) {
         double xv[P];
 #pragma unroll
-        for (int j = 0; j < P; ++j) xv[j] = xp0[j * Npad];
+        for (int j = 0; j < P; ++j) xv[j] = xp0[j];
         const double W0 = one ? m0 * r * inv0 : 0.0;
         sym_rank1<P>(A, W0, xv);
         sym_rank1<P>(B, W0 * W0, xv);
 #pragma unroll
-        for (int j = 0; j < P; ++j) xv[j] = xp1[j * Npad];
+        for (int j = 0; j < P; ++j) xv[j] = xp1[j];
         const double W1 = two ? m1 * r * inv1 : 0.0;
         sym_rank1<P>(A, W1, xv);
         sym_rank1<P>(B, W1 * W1, xv);
@@ -783,7 +941,8 @@ PDQ_HD bool alpha_sweep_t(const Group& grp, const DesignS& d, bool cr_reg, const
     const int64_t ystep = (int64_t)T * ld, mstep = (int64_t)T * ld_mu;
     const int64_t* yp = y + (int64_t)grp.si * ld;
     const double* mp = mu + (int64_t)grp.si * ld_mu;
-    const double* xp = d.X + grp.si;
+    constexpr int RS = design_row_stride(P);
+    const double* xp = d.X + grp.si * RS;
     // the trip count is made uniform across the warp (lanes past N contribute a masked dummy) because alpha_pair votes
     const int trips = (d.N + 2 * T - 1) / (2 * T);
     int n = grp.si;
@@ -792,22 +951,22 @@ PDQ_HD bool alpha_sweep_t(const Group& grp, const DesignS& d, bool cr_reg, const
     bool v0 = n < d.N, v1 = n + T < d.N;
     long long yi0 = v0 ? yp[0] : 0, yi1 = v1 ? yp[ystep] : 0;
     double m0 = v0 ? mp[0] : 1.0, m1 = v1 ? mp[mstep] : 1.0;
-    for (int it = 0; it < trips; ++it, n += 2 * T, yp += 2 * ystep, mp += 2 * mstep, xp += 2 * T) {
+    for (int it = 0; it < trips; ++it, n += 2 * T, yp += 2 * ystep, mp += 2 * mstep, xp += 2 * T * RS) {
         const bool w0 = n + 2 * T < d.N, w1 = n + 3 * T < d.N;
         const long long ny0 = w0 ? yp[2 * ystep] : 0, ny1 = w1 ? yp[3 * ystep] : 0;
         const double nm0 = w0 ? mp[2 * mstep] : 1.0, nm1 = w1 ? mp[3 * mstep] : 1.0;
         // one call site: every lane of the warp reaches the vote inside alpha_pair together
-        alpha_pair<P, NB, CURV>(grp, v0 ? xp : d.X, v1 ? xp + T : d.X, d.Npad, yi0, yi1, m0, m1, v0, v1, r, cr_reg, psi_tab,
+        alpha_pair<P, NB, CURV>(grp, v0 ? xp : d.X, v1 ? xp + T * RS : d.X, d.mtab, yi0, yi1, m0, m1, v0, v1, r, cr_reg, psi_tab,
                                 Sg, A, B, odd, S2);
         v0 = w0; v1 = w1; yi0 = ny0; yi1 = ny1; m0 = nm0; m1 = nm1;
     }
 #else
-    for (int it = 0; it < trips; ++it, n += 2 * T, yp += 2 * ystep, mp += 2 * mstep, xp += 2 * T) {
+    for (int it = 0; it < trips; ++it, n += 2 * T, yp += 2 * ystep, mp += 2 * mstep, xp += 2 * T * RS) {
         const bool v0 = n < d.N, v1 = n + T < d.N;
         const long long yi0 = v0 ? yp[0] : 0, yi1 = v1 ? yp[ystep] : 0;
         const double m0 = v0 ? mp[0] : 1.0, m1 = v1 ? mp[mstep] : 1.0;
         // one call site: every lane of the warp reaches the vote inside alpha_pair together
-        alpha_pair<P, NB, CURV>(grp, v0 ? xp : d.X, v1 ? xp + T : d.X, d.Npad, yi0, yi1, m0, m1, v0, v1, r, cr_reg, psi_tab,
+        alpha_pair<P, NB, CURV>(grp, v0 ? xp : d.X, v1 ? xp + T * RS : d.X, d.mtab, yi0, yi1, m0, m1, v0, v1, r, cr_reg, psi_tab,
                                 Sg, A, B, odd, S2);
     }
 #endif
@@ -1047,91 +1206,6 @@ PDQ_HD void alpha_grid_gene(const Group& grp, const DesignS& d, double lo, doubl
 }
 
 // =============================================================================================
-// (a3) wald_test -- utils.py:718-811.
-// =============================================================================================
-template <int P>
-struct WaldParams {
-    double ridge[P * P];
-    double contrast[P];
-    double lfc_null;
-    int alt;
-};
-
-template <int P>
-PDQ_HD void wald_gene(const Group& grp, const DesignS& d, const WaldParams<P>& prm, double disp, const double* lfc,
-                      const double* mu, int64_t ld_mu, double* p_out, double* stat_out, double* se_out, bool valid) {
-    Sym<P> M;
-    sym_zero<P>(M);
-    for (int n = grp.si; n < d.N; n += grp.T) {
-        double x[P];
-        load_x<P>(d, n, x);
-        const double m = mu[n * ld_mu];
-        sym_rank1<P>(M, m / fma(m, disp, 1.0), x);
-    }
-    group_sum_sym<P>(grp, M);
-    Sym<P> L = M, H;
-#pragma unroll
-    for (int i = 0; i < P; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j) L.a[tri(i, j)] += prm.ridge[i * P + j];
-    chol<P>(L);
-    chol_inverse<P>(L, H);
-    double Hc[P], MHc[P];
-    sym_matvec<P>(H, prm.contrast, Hc);
-    sym_matvec<P>(M, Hc, MHc);
-    double q = 0.0;
-#pragma unroll
-    for (int j = 0; j < P; ++j) q = fma(Hc[j], MHc[j], q);
-    const double se = sqrt(q);
-    double b[P];
-#pragma unroll
-    for (int j = 0; j < P; ++j) b[j] = lfc[j];
-    const double t0 = prm.lfc_null;
-    double stat, pv;
-    // each variant applies the elementwise transform to every coefficient, then dots with the contrast
-    auto greater = [&](double t, double& s, double& p) {
-        s = 0.0;
-#pragma unroll
-        for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], fmax((b[j] - t) / se, 0.0), s);
-        p = norm_sf(s);
-    };
-    auto less = [&](double t, double& s, double& p) {
-        s = 0.0;
-#pragma unroll
-        for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], fmin((b[j] - t) / se, 0.0), s);
-        p = norm_sf(fabs(s));
-    };
-    if (prm.alt == 0) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], b[j] - t0, s);
-        stat = s / se;
-        pv = 2.0 * norm_sf(fabs(stat));
-    } else if (prm.alt == 1) {  // greaterAbs
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], sgn(b[j]) * fmax((fabs(b[j]) - t0) / se, 0.0), s);
-        stat = s;
-        pv = 2.0 * norm_sf(fabs(s));
-    } else if (prm.alt == 2) {  // lessAbs
-        double sa, pa, sb, pb;
-        greater(-fabs(t0), sa, pa);
-        less(fabs(t0), sb, pb);
-        stat = (fabs(sb) < fabs(sa)) ? sb : sa;  // min(sa, sb, key=abs): first wins ties
-        pv = (pb > pa) ? pb : pa;                // max(pa, pb)
-    } else if (prm.alt == 3) {
-        greater(t0, stat, pv);
-    } else {
-        less(t0, stat, pv);
-    }
-    if (valid && grp.si == 0) {
-        *p_out = pv;
-        *stat_out = stat;
-        *se_out = se;
-    }
-}
-
-// =============================================================================================
 // (a5) fit_rough_dispersions (utils.py:814-853) / fit_moments_dispersions (utils.py:856-885)
 // `Y` abstracts where normalised counts come from: a float64 (N,G) array (the plugin call) or raw
 // int64 counts divided by the staged size factors on the fly (resident pipeline).
@@ -1144,7 +1218,7 @@ struct NormedF64 {
 struct NormedFromCounts {
     const int64_t* p;
     int64_t ld;
-    PDQ_HD double at(const DesignS& d, int n) const { return (double)p[n * ld] / d.sf[n]; }
+    PDQ_HD double at(const DesignS& d, int n) const { return (double)p[n * ld] / d.sf[n * d.RS]; }
 };
 
 template <int P, class Y>
@@ -1196,14 +1270,14 @@ PDQ_HD void mom_fused_gene(const Group& grp, const DesignS& d, const SmallMat<P>
     double s = 0.0;
     const int64_t ystep = (int64_t)grp.T * ld;
     const int64_t* yp = y + (int64_t)grp.si * ld;
-    for (int n = grp.si; n < d.N; n += grp.T, yp += ystep) {
+    walk4(grp, d.N, yp, ystep, [&](int n, int64_t c) {
         double x[P];
         load_x<P>(d, n, x);
-        const double t = fast_div((double)*yp, d.sf[n]);  // <= 1 ulp from counts / sf
+        const double t = fast_div((double)c, d.sf[n * d.RS]);  // <= 1 ulp from counts / sf
         s += t;
 #pragma unroll
         for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
-    }
+    });
     group_sum_vec<P>(grp, v);
     const double m = grp.sum(s) / (double)d.N;
     double beta[P];
@@ -1215,24 +1289,23 @@ PDQ_HD void mom_fused_gene(const Group& grp, const DesignS& d, const SmallMat<P>
         beta[i] = acc;
     }
     double rough = 0.0, ss = 0.0;
-    yp = y + (int64_t)grp.si * ld;
-    for (int n = grp.si; n < d.N; n += grp.T, yp += ystep) {
+    walk4(grp, d.N, yp, ystep, [&](int n, int64_t c) {
         double x[P];
         load_x<P>(d, n, x);
         double fit = 0.0;
 #pragma unroll
         for (int j = 0; j < P; ++j) fit = fma(x[j], beta[j], fit);
-        const double t = fast_div((double)*yp, d.sf[n]);  // <= 1 ulp from counts / sf
+        const double t = fast_div((double)c, d.sf[n * d.RS]);  // <= 1 ulp from counts / sf
         const double yh = (fit < 1.0) ? 1.0 : fit;  // np.maximum(y_hat, 1)
         const double e = t - yh;
         rough += fast_div(e * e - yh, yh * yh);
         const double dm = t - m;
         ss = fma(dm, dm, ss);
         if (mu_out && valid) {
-            const double mu = d.sf[n] * fit;
-            mu_out[n * ld_out] = (mu < min_mu) ? min_mu : mu;
+            const double mu = d.sf[n * d.RS] * fit;
+            mu_out[(int64_t)n * ld_out] = (mu < min_mu) ? min_mu : mu;
         }
-    }
+    });
     rough = grp.sum(rough) / (double)(d.N - P);
     rough = (rough < 0.0) ? 0.0 : rough;  // np.maximum(alpha_rde, 0)
     const double var = grp.sum(ss) / (double)(d.N - 1);
@@ -1333,12 +1406,12 @@ PDQ_HD void cooks_gene(const Group& grp, const DesignS& d, const CellPlan& plan,
     const int nf = plan.cell_start[plan.n_cells];
     // normalised counts: mean over ALL samples, and the grouped copy of the samples that sit in cells
     double msum = 0.0;
-    for (int n = grp.si; n < d.N; n += grp.T) msum += (double)y[n * ld] / d.sf[n];
+    for (int n = grp.si; n < d.N; n += grp.T) msum += (double)y[n * ld] / d.sf[n * d.RS];
     const double m_all = grp.sum(msum) / (double)d.N;
     grp.sync();
     for (int i = grp.si; i < nf; i += grp.T) {
         const int n = plan.order[i];
-        vals[i] = (double)y[n * ld] / d.sf[n];
+        vals[i] = (double)y[n * ld] / d.sf[n * d.RS];
     }
     grp.sync();
     double v = -1.7976931348623157e308;

@@ -9,16 +9,17 @@
 namespace pdq {
 
 // Device-resident design pack:
-//   pack = [ X column-major (p x Npad) | sf (Npad) | log sf (Npad) ]  float64, Npad = N rounded up to 2
-// so that one `cp.async.bulk` (TMA 1-D bulk copy, 16-byte granularity) stages it into shared memory.
+//   pack = N rows of [ x_n0 .. x_n,p-1 | sf_n | log sf_n | pad ]  float64, RS = p + 2 rounded up to even doubles per row,
+// so that rows are 16-byte aligned and `cp.async.bulk` (TMA 1-D bulk copy, 16-byte granularity) stages it into shared memory.
 struct DesignDev {
     double* pack;       // device
-    int N, Npad, p;
+    int N, RS, p;
     int full_rank;      // np.linalg.matrix_rank(X) == p  (utils.py:349)
     int few_rows;       // X has at most 16 distinct rows (categorical design): k_irls reuses exp(x'beta) across equal rows
     double pinv[PDQ_MAX_P * PDQ_MAX_P];  // (X^T X)^+ row-major p x p (host copy, passed by value to kernels)
     double s_mean_inv;  // mean(1 / size_factors)  (utils.py:880)
-    size_t smem_bytes;  // dynamic shared memory the kernels need for this pack
+    int staged;         // the pack is small enough to be copied into shared memory by every block (else read from global / L1)
+    size_t smem_bytes;  // dynamic shared memory the kernels need for the design: staged pack + mbarrier, or the mbarrier alone
     int* cell_plan;     // device: [n_cells, global_mode, starts (n_cells + 1), order (n_in_cells)]  (Cook's distances)
     int n_cells, n_in_cells, plan_len;
 };
@@ -36,12 +37,21 @@ struct IrlsHost {
     int maxiter;
 };
 
+// Wald test fused into the IRLS launch (resident pipeline): host copies of the small parameters, device outputs
+struct WaldHost {
+    const double* ridge;     // p x p row-major (host)
+    const double* contrast;  // p (host)
+    double lfc_null;
+    int alt;
+    double *pv, *stat, *se;  // device, one per gene
+};
+
 // launchers (pdq_kernels.cu); each returns the number of kernels launched or a negative pdq_status
 int launch_lin_reg_mu(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64_t ld, int G, double min_mu,
                       double* mu_out, int64_t ld_out);
 int launch_irls(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64_t ld, int G, const double* disp,
                 const IrlsHost& prm, double* beta, double* mu, double* hat, int64_t ld_out, double* conv, int* status,
-                int* n_fallback);
+                int* n_fallback, const WaldHost* wald = nullptr);
 int launch_alpha_mle(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64_t ld, int G, const double* mu,
                      int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp, double prior_var,
                      const double* prior_var_dev, int cr_reg, int prior_reg, double* alpha, double* conv, int* status);

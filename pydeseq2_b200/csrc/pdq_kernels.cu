@@ -36,58 +36,95 @@ constexpr int kWarps = kBlock / 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// lookup tables of the table-driven log / exp (pdq_fast.cuh); staged into shared memory by the kernels that use them
+__device__ const double g_math_tab[kMathTabLen] = {PDQ_MATH_TABLE_VALUES};
+constexpr uint32_t kMathTabBytes = (uint32_t)kMathTabLen * 8u;
+static_assert(kMathTabBytes % 16 == 0, "bulk copies are 16-byte granular");
+
 // ---- TMA 1-D bulk copy global -> shared, mbarrier completion --------------------------------------
-__device__ __forceinline__ DesignS stage_design(const double* __restrict__ pack, int N, int Npad, int P,
-                                                unsigned char* smem) {
+// Shared-memory layout: [ design pack (when staged) | mbarrier (16 B) | math table (kernels with TAB) | kernel-specific scratch ]
+// Packs above the staging limit (pdq_api.cu: they would leave fewer than four blocks per SM) are NOT copied: the kernels then
+// read the design rows straight from global memory -- every warp of the machine walks the same <= few-hundred-KB pack, so the
+// rows live in L1 / L2 -- and shared memory no longer bounds the number of samples or resident blocks.
+struct DesignView {
+    const double* pack;
+    int N;
+    int pack_smem;  // bytes of the pack staged in shared memory; 0 = read it from global memory
+};
+
+// MODE: 1 = pack staged (shared-memory pointers, LDS), 0 = pack in global memory, -1 = decided at run time (generic loads)
+template <bool TAB, int MODE>
+__device__ __forceinline__ DesignS stage_design_t(const DesignView& dv, int P, unsigned char* smem) {
     double* s = reinterpret_cast<double*>(smem);
-    const uint32_t bytes = (uint32_t)((P + 2) * Npad) * 8u;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + bytes);
-    const uint32_t bar_a = smem_u32(bar);
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
-        // chunked so a single descriptor never exceeds 32 KB; all chunks complete on the same barrier
-        uint32_t off = 0;
-        while (off < bytes) {
-            const uint32_t n = (bytes - off > 32768u) ? 32768u : (bytes - off);
+    const int RS = design_row_stride(P);
+    const bool staged = MODE == 1 || (MODE == -1 && dv.pack_smem != 0);
+    const uint32_t bytes = staged ? (uint32_t)((dv.N + 1) * RS) * 8u : 0u;  // N sample rows + the row of column maxima
+    if (staged || TAB) {
+        uint64_t* bar = reinterpret_cast<uint64_t*>(smem + bytes);
+        const uint32_t bar_a = smem_u32(bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes + (TAB ? kMathTabBytes : 0u))
+                         : "memory");
+            if (TAB)
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        smem_u32(smem + bytes + 16)),
+                    "l"(reinterpret_cast<const unsigned char*>(g_math_tab)), "r"(kMathTabBytes), "r"(bar_a)
+                    : "memory");
+            // chunked so a single descriptor never exceeds 32 KB; all chunks complete on the same barrier
+            uint32_t off = 0;
+            while (off < bytes) {
+                const uint32_t n = (bytes - off > 32768u) ? 32768u : (bytes - off);
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        smem_u32(smem + off)),
+                    "l"(reinterpret_cast<const unsigned char*>(dv.pack) + off), "r"(n), "r"(bar_a)
+                    : "memory");
+                off += n;
+            }
+        }
+        uint32_t done = 0;
+        while (!done) {
             asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                    smem_u32(smem + off)),
-                "l"(reinterpret_cast<const unsigned char*>(pack) + off), "r"(n), "r"(bar_a)
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar_a), "r"(0u)
                 : "memory");
-            off += n;
         }
     }
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar_a), "r"(0u)
-            : "memory");
-    }
     DesignS d;
-    d.X = s;
-    d.sf = s + P * Npad;
-    d.lsf = s + (P + 1) * Npad;
-    d.N = N;
-    d.Npad = Npad;
+    if (MODE == 1) d.X = s;
+    else if (MODE == 0) d.X = dv.pack;
+    else d.X = staged ? s : dv.pack;
+    d.sf = d.X + P;
+    d.lsf = d.X + P + 1;
+    d.N = dv.N;
+    d.RS = RS;
+    d.mtab = TAB ? reinterpret_cast<const double*>(smem + bytes + 16) : nullptr;
     return d;
 }
 
-__device__ __forceinline__ void map_lanes(int lgT, int G, Group& grp, int& gene, bool& valid) {
+// the light kernels: staged or not is a run-time property of the design
+__device__ __forceinline__ DesignS stage_design(const DesignView& dv, int P, unsigned char* smem) {
+    return stage_design_t<false, -1>(dv, P, smem);
+}
+// offset of the kernel-specific scratch behind the pack + mbarrier (+ table)
+__device__ __forceinline__ size_t scratch_off(const DesignView& dv, bool tab) { return (size_t)dv.pack_smem + 16 + (tab ? kMathTabBytes : 0u); }
+
+__device__ __forceinline__ void map_lanes(int lgT, int G, Group& grp, int& gene, bool& valid, int block = -1) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     grp.T = 1 << lgT;
     grp.gpw = 32 >> lgT;
     grp.si = lane >> (5 - lgT);
     const int gi = lane & (grp.gpw - 1);
-    const int gidx = (blockIdx.x * kWarps + warp) * grp.gpw + gi;
+    const int gidx = ((block < 0 ? (int)blockIdx.x : block) * kWarps + warp) * grp.gpw + gi;
     valid = gidx < G;
     gene = valid ? gidx : (G - 1);
 }
@@ -111,10 +148,6 @@ __device__ __forceinline__ bool next_tile(int* ticket, int lgT, int G, Group& gr
     return true;
 }
 
-struct DesignView {
-    const double* pack;
-    int N, Npad;
-};
 
 // ---- kernels --------------------------------------------------------------------------------------
 template <int P>
@@ -132,7 +165,7 @@ struct LinMuArgs {
 template <int P>
 __global__ void __launch_bounds__(kBlock) k_lin_reg_mu(const __grid_constant__ LinMuArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    const DesignS d = stage_design(a.dv, P, smem);
     Group grp;
     int g;
     bool valid;
@@ -153,19 +186,23 @@ struct IrlsArgs {
     int64_t ld_out;
     int* status;
     int* n_fallback;
-    int* ticket;  // tile counter of the persistent scheduler (zeroed before the launch)
+    int* ticket;  // [0] tile counter of the persistent scheduler, [1] number of genes flagged for the optimiser branch (both
+                  // zeroed before the launch)
     int force;    // test hook: flag every gene for the optimiser branch
+    int with_wald;         // also the Wald test of the fit (resident pipeline): parameters and outputs below
+    WaldParams<P> wald;
+    double *wald_p, *wald_stat, *wald_se;
 };
 
-template <int P>
+template <int P, bool STAGED>
 __global__ void __launch_bounds__(kBlock, PDQ_IRLS_MINB) k_irls(const __grid_constant__ IrlsArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    const DesignS d = stage_design_t<true, STAGED ? 1 : 0>(a.dv, P, smem);
     Group grp;
     int g;
     bool valid;
-    // behind the design pack and its mbarrier: log(k!) table, then one lgamma(r + k) table per gene of the warp's tile
-    double* logfact = reinterpret_cast<double*>(smem + (size_t)(P + 2) * a.dv.Npad * 8 + 16);
+    // behind the design pack, its mbarrier and the math table: log(k!) table, then one lgamma(r + k) table per gene of the warp's tile
+    double* logfact = reinterpret_cast<double*>(smem + scratch_off(a.dv, true));
     if (threadIdx.x < kPsiK) logfact[threadIdx.x] = kLogFact[threadIdx.x];
     __syncthreads();
     const int gpw = 32 >> a.lgT;
@@ -173,29 +210,39 @@ __global__ void __launch_bounds__(kBlock, PDQ_IRLS_MINB) k_irls(const __grid_con
     while (next_tile(a.ticket, a.lgT, a.G, grp, g, valid)) {
         int st = 0;
         irls_gene<P>(grp, d, a.pinv, a.prm, a.counts + g, a.ld, a.disp[g], a.beta + (int64_t)g * P, a.mu + g, a.hat + g,
-                     a.ld_out, a.conv + g, &st, valid, lg_tab, logfact);
+                     a.ld_out, a.conv + g, &st, valid, lg_tab, logfact, a.with_wald ? &a.wald : nullptr, a.wald_p + g,
+                     a.wald_stat + g, a.wald_se + g);
         if (valid && grp.si == 0) {
             if (a.force) st = kIrlsNeedsOptimizer;
             a.status[g] = st;
-            if (st != kIrlsOk && a.n_fallback) atomicAdd(a.n_fallback, 1);
+            if (st != kIrlsOk) {
+                atomicAdd(a.ticket + 1, 1);
+                if (a.n_fallback) atomicAdd(a.n_fallback, 1);
+            }
         }
     }
 }
 
-// optimiser branch for the genes k_irls flagged (utils.py:374-413); blocks without a flagged gene exit
+// optimiser branch for the genes k_irls flagged (utils.py:374-413).  Normally no gene is flagged: the launch is one wave of
+// blocks that read the flagged-gene counter and exit; otherwise the blocks stride over the gene tiles and skip those without one.
 template <int P>
 __global__ void __launch_bounds__(kBlock) k_irls_optimizer(const __grid_constant__ IrlsArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    Group grp;
-    int g;
-    bool valid;
-    map_lanes(a.lgT, a.G, grp, g, valid);
-    const bool run = valid && a.status[g] == kIrlsNeedsOptimizer;
-    if (!__syncthreads_or(run)) return;
-    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
-    if (!__any_sync(0xffffffffu, run)) return;
-    irls_optimizer_gene<P>(grp, d, a.pinv, a.prm, a.counts + g, a.ld, a.disp[g], a.beta + (int64_t)g * P, a.mu + g,
-                           a.hat + g, a.ld_out, a.conv + g, run);
+    if (*reinterpret_cast<volatile const int*>(a.ticket + 1) == 0) return;
+    const DesignS d = stage_design(a.dv, P, smem);
+    const int per_block = kWarps * (32 >> a.lgT), nbt = (a.G + per_block - 1) / per_block;
+    for (int bt = blockIdx.x; bt < nbt; bt += gridDim.x) {
+        Group grp;
+        int g;
+        bool valid;
+        map_lanes(a.lgT, a.G, grp, g, valid, bt);
+        const bool run = valid && a.status[g] == kIrlsNeedsOptimizer;
+        if (!__syncthreads_or(run)) continue;
+        if (!__any_sync(0xffffffffu, run)) continue;
+        irls_optimizer_gene<P>(grp, d, a.pinv, a.prm, a.counts + g, a.ld, a.disp[g], a.beta + (int64_t)g * P, a.mu + g,
+                               a.hat + g, a.ld_out, a.conv + g, run, a.with_wald ? &a.wald : nullptr, a.wald_p + g,
+                               a.wald_stat + g, a.wald_se + g);
+    }
 }
 
 template <int P>
@@ -211,14 +258,14 @@ struct AlphaArgs {
     double *alpha, *conv;
     int* status;
     const double* prior_var_dev;  // when set, overrides prm.prior_var (written by k_trend_prior on the same stream)
-    int* ticket;                  // tile counter of the persistent scheduler (zeroed before the launch)
+    int* ticket;                  // [0] tile counter of the persistent scheduler, [1] genes flagged for the grid (zeroed before)
     int force;                    // test hook: flag every gene for the grid fallback
 };
 
-template <int P>
+template <int P, bool STAGED>
 __global__ void __launch_bounds__(kBlock, PDQ_ALPHA_MINB) k_alpha_mle(const __grid_constant__ AlphaArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    const DesignS d = stage_design_t<true, STAGED ? 1 : 0>(a.dv, P, smem);
     Group grp;
     int g;
     bool valid;
@@ -227,30 +274,38 @@ __global__ void __launch_bounds__(kBlock, PDQ_ALPHA_MINB) k_alpha_mle(const __gr
     const int gpw = 32 >> a.lgT;
     // per-gene psi(r + k) and psi'(r + k) tables live behind the design pack and its mbarrier (one slot of 2 * kPsiK doubles
     // per gene of the warp's tile)
-    double* psi = reinterpret_cast<double*>(smem + (size_t)(P + 2) * a.dv.Npad * 8 + 16) +
+    double* psi = reinterpret_cast<double*>(smem + scratch_off(a.dv, true)) +
                   (size_t)((threadIdx.x >> 5) * gpw + ((threadIdx.x & 31) & (gpw - 1))) * (2 * kPsiK);
     while (next_tile(a.ticket, a.lgT, a.G, grp, g, valid)) {
         alpha_gene<P>(grp, d, prm, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha_hat[g], a.alpha + g, a.conv + g,
                       a.status + g, valid, psi);
-        if (a.force && valid && grp.si == 0) {
-            a.status[g] = kAlphaNeedsGrid;
-            a.conv[g] = 0.0;
+        if (valid && grp.si == 0) {
+            if (a.force) {
+                a.status[g] = kAlphaNeedsGrid;
+                a.conv[g] = 0.0;
+            }
+            if (a.status[g] == kAlphaNeedsGrid) atomicAdd(a.ticket + 1, 1);
         }
     }
 }
 
+// the reference's grid fallback for the genes k_alpha_mle flagged; same launch scheme as k_irls_optimizer
 template <int P>
 __global__ void __launch_bounds__(kBlock) k_alpha_grid(const __grid_constant__ AlphaArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    Group grp;
-    int g;
-    bool valid;
-    map_lanes(a.lgT, a.G, grp, g, valid);
-    const bool run = valid && a.status[g] == kAlphaNeedsGrid;
-    if (!__syncthreads_or(run)) return;
-    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
-    if (!__any_sync(0xffffffffu, run)) return;
-    alpha_grid_gene<P>(grp, d, a.prm.lo, a.prm.hi, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha + g, run);
+    if (*reinterpret_cast<volatile const int*>(a.ticket + 1) == 0) return;
+    const DesignS d = stage_design(a.dv, P, smem);
+    const int per_block = kWarps * (32 >> a.lgT), nbt = (a.G + per_block - 1) / per_block;
+    for (int bt = blockIdx.x; bt < nbt; bt += gridDim.x) {
+        Group grp;
+        int g;
+        bool valid;
+        map_lanes(a.lgT, a.G, grp, g, valid, bt);
+        const bool run = valid && a.status[g] == kAlphaNeedsGrid;
+        if (!__syncthreads_or(run)) continue;
+        if (!__any_sync(0xffffffffu, run)) continue;
+        alpha_grid_gene<P>(grp, d, a.prm.lo, a.prm.hi, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha + g, run);
+    }
 }
 
 template <int P>
@@ -266,7 +321,7 @@ struct WaldArgs {
 template <int P>
 __global__ void __launch_bounds__(kBlock) k_wald(const __grid_constant__ WaldArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    const DesignS d = stage_design(a.dv, P, smem);
     Group grp;
     int g;
     bool valid;
@@ -293,7 +348,7 @@ struct MomArgs {
 template <int P>
 __global__ void __launch_bounds__(kBlock) k_rough(const __grid_constant__ MomArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    const DesignS d = stage_design(a.dv, P, smem);
     Group grp;
     int g;
     bool valid;
@@ -305,7 +360,7 @@ __global__ void __launch_bounds__(kBlock) k_rough(const __grid_constant__ MomArg
 template <int P>
 __global__ void __launch_bounds__(kBlock) k_moments(const __grid_constant__ MomArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    const DesignS d = stage_design(a.dv, P, smem);
     Group grp;
     int g;
     bool valid;
@@ -322,7 +377,7 @@ __global__ void __launch_bounds__(kBlock) k_moments(const __grid_constant__ MomA
 template <int P>
 __global__ void __launch_bounds__(kBlock) k_mom_from_counts(const __grid_constant__ MomArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    const DesignS d = stage_design(a.dv, P, smem);
     Group grp;
     int g;
     bool valid;
@@ -351,8 +406,8 @@ struct CooksArgs {
 template <int P>
 __global__ void __launch_bounds__(kBlock) k_cooks(const __grid_constant__ CooksArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
-    int* plan_s = reinterpret_cast<int*>(smem + (size_t)(P + 2) * a.dv.Npad * 8 + 16);
+    const DesignS d = stage_design(a.dv, P, smem);
+    int* plan_s = reinterpret_cast<int*>(smem + scratch_off(a.dv, false));
     for (int i = threadIdx.x; i < a.plan_len; i += blockDim.x) plan_s[i] = a.plan[i];
     __syncthreads();
     Group grp;
@@ -362,7 +417,7 @@ __global__ void __launch_bounds__(kBlock) k_cooks(const __grid_constant__ CooksA
     const CellPlan plan{plan_s + 2 + a.n_cells + 1, plan_s + 2, a.n_cells, plan_s[1]};
     const size_t plan_bytes = ((size_t)a.plan_len * 4 + 15) & ~(size_t)15;
     const int gslot = (threadIdx.x >> 5) * grp.gpw + ((threadIdx.x & 31) & (grp.gpw - 1));
-    double* vals = reinterpret_cast<double*>(smem + (size_t)(P + 2) * a.dv.Npad * 8 + 16 + plan_bytes) + (size_t)gslot * 2 * a.n_in_cells;
+    double* vals = reinterpret_cast<double*>(smem + scratch_off(a.dv, false) + plan_bytes) + (size_t)gslot * 2 * a.n_in_cells;
     cooks_gene<P>(grp, d, plan, a.counts + g, a.ld, a.mu + g, a.hat + g, a.ld2, a.cutoff, vals, vals + a.n_in_cells,
                   a.cooks ? a.cooks + g : nullptr, a.ld_out, a.disp + g, a.outlier + g, a.replaced + g, valid);
 }
@@ -379,7 +434,7 @@ struct MuLfcArgs {
 template <int P>
 __global__ void __launch_bounds__(kBlock) k_mu_from_lfc(const __grid_constant__ MuLfcArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    const DesignS d = stage_design(a.dv, P, smem);
     Group grp;
     int g;
     bool valid;
@@ -394,7 +449,7 @@ __global__ void __launch_bounds__(kBlock) k_mu_from_lfc(const __grid_constant__ 
         double eta = 0.0;
 #pragma unroll
         for (int j = 0; j < P; ++j) eta = fma(x[j], b[j], eta);
-        a.mu[n * a.ld_out + g] = d.sf[n] * exp(eta);  // ds.py:320-324
+        a.mu[n * a.ld_out + g] = d.sf[n * d.RS] * exp(eta);  // ds.py:320-324
     }
 }
 
@@ -665,6 +720,12 @@ inline int grid_for(int G, int lgT) {
     return (G + genes_per_block - 1) / genes_per_block;
 }
 
+// one wave of blocks for the (normally idle) fallback kernels
+inline int fallback_grid(int sm_count, int G, int lgT) {
+    const int need = grid_for(G, lgT);
+    return need < 2 * sm_count ? need : 2 * sm_count;
+}
+
 template <class K>
 int prep(K kernel, size_t smem) {
     if (smem > kMaxDynSmem) return PDQ_ERR_UNSUPPORTED;
@@ -710,7 +771,7 @@ struct ShrinkArgs {
 template <int P>
 __global__ void __launch_bounds__(kBlock) k_lfc_shrink(const __grid_constant__ ShrinkArgs<P> a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, P, smem);
+    const DesignS d = stage_design(a.dv, P, smem);
     Group grp;
     int g;
     bool valid;
@@ -727,7 +788,7 @@ __global__ void __launch_bounds__(kBlock) k_lfc_shrink_grid(const __grid_constan
     map_lanes(a.lgT, a.G, grp, g, valid);
     const bool run = valid && a.status[g] == kShrinkNeedsGrid;
     if (!__syncthreads_or(run)) return;
-    const DesignS d = stage_design(a.dv.pack, a.dv.N, a.dv.Npad, 2, smem);
+    const DesignS d = stage_design(a.dv, 2, smem);
     if (!__any_sync(0xffffffffu, run)) return;
     shrink_grid_gene(grp, d, a.prm, a.counts + g, a.ld, a.size[g], a.beta + (int64_t)g * 2, a.ih + (int64_t)g * 4, run);
 }
@@ -768,7 +829,7 @@ inline int check_launch() { return cudaGetLastError() == cudaSuccess ? 0 : PDQ_E
 int launch_lin_reg_mu(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G, double min_mu,
                       double* mu_out, int64_t ld_out) {
     PDQ_DISPATCH_P(d.p, {
-        LinMuArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d), counts, ld, G, c.lgT, min_mu, mu_out, ld_out};
+        LinMuArgs<P> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, pinv_of<P>(d), counts, ld, G, c.lgT, min_mu, mu_out, ld_out};
         if (int e = prep(k_lin_reg_mu<P>, d.smem_bytes)) return e;
         k_lin_reg_mu<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });
@@ -778,19 +839,37 @@ int launch_lin_reg_mu(const LaunchCfg& c, const DesignDev& d, const int64_t* cou
 
 int launch_irls(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G, const double* disp,
                 const IrlsHost& h, double* beta, double* mu, double* hat, int64_t ld_out, double* conv, int* status,
-                int* n_fallback) {
+                int* n_fallback, const WaldHost* w) {
     if (n_fallback && cudaMemsetAsync(n_fallback, 0, sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;
     PDQ_DISPATCH_P(d.p, {
-        IrlsArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d),
-                      IrlsParams{h.min_mu, h.beta_tol, h.min_beta, h.max_beta, h.maxiter, d.full_rank, d.few_rows},
-                      counts, ld, G, c.lgT, disp, beta, mu, hat, conv, ld_out, status, n_fallback, c.tickets,
-                      (c.debug & PDQ_DEBUG_FORCE_IRLS_OPTIMIZER) ? 1 : 0};
-        const size_t smem_irls = d.smem_bytes + (size_t)(1 + kWarps * (32 >> c.lgT)) * kPsiK * sizeof(double);
-        if (int e = prep(k_irls<P>, smem_irls)) return e;
+        IrlsArgs<P> a;
+        a.dv = DesignView{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0};
+        a.pinv = pinv_of<P>(d);
+        a.prm = IrlsParams{h.min_mu, h.beta_tol, h.min_beta, h.max_beta, h.maxiter, d.full_rank, d.few_rows};
+        a.counts = counts; a.ld = ld; a.G = G; a.lgT = c.lgT; a.disp = disp;
+        a.beta = beta; a.mu = mu; a.hat = hat; a.conv = conv; a.ld_out = ld_out;
+        a.status = status; a.n_fallback = n_fallback; a.ticket = c.tickets;
+        a.force = (c.debug & PDQ_DEBUG_FORCE_IRLS_OPTIMIZER) ? 1 : 0;
+        a.with_wald = w ? 1 : 0;
+        a.wald_p = a.wald_stat = a.wald_se = nullptr;
+        if (w) {
+            for (int i = 0; i < P * P; ++i) a.wald.ridge[i] = w->ridge[i];
+            for (int i = 0; i < P; ++i) a.wald.contrast[i] = w->contrast[i];
+            a.wald.lfc_null = w->lfc_null;
+            a.wald.alt = w->alt;
+            a.wald_p = w->pv; a.wald_stat = w->stat; a.wald_se = w->se;
+        }
+        const size_t smem_irls = d.smem_bytes + kMathTabBytes + (size_t)(1 + kWarps * (32 >> c.lgT)) * kPsiK * sizeof(double);
         if (int e = prep(k_irls_optimizer<P>, d.smem_bytes)) return e;
-        if (cudaMemsetAsync(c.tickets, 0, sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;
-        k_irls<P><<<persistent_grid(k_irls<P>, smem_irls, c.sm_count, G, c.lgT), kBlock, smem_irls, c.stream>>>(a);
-        k_irls_optimizer<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+        if (cudaMemsetAsync(c.tickets, 0, 2 * sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;
+        if (d.staged) {
+            if (int e = prep(k_irls<P, true>, smem_irls)) return e;
+            k_irls<P, true><<<persistent_grid(k_irls<P, true>, smem_irls, c.sm_count, G, c.lgT), kBlock, smem_irls, c.stream>>>(a);
+        } else {
+            if (int e = prep(k_irls<P, false>, smem_irls)) return e;
+            k_irls<P, false><<<persistent_grid(k_irls<P, false>, smem_irls, c.sm_count, G, c.lgT), kBlock, smem_irls, c.stream>>>(a);
+        }
+        k_irls_optimizer<P><<<fallback_grid(c.sm_count, G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });
     if (int e = check_launch()) return e;
     return 2;
@@ -801,15 +880,20 @@ int launch_alpha_mle(const LaunchCfg& c, const DesignDev& d, const int64_t* coun
                      double prior_var, const double* prior_var_dev, int cr_reg, int prior_reg, double* alpha, double* conv,
                      int* status) {
     PDQ_DISPATCH_P(d.p, {
-        AlphaArgs<P> a{{d.pack, d.N, d.Npad}, AlphaParams{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg},
-                       counts, ld, G, c.lgT, mu, ld_mu, alpha_hat, alpha, conv, status, prior_var_dev, c.tickets + 1,
+        AlphaArgs<P> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, AlphaParams{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg},
+                       counts, ld, G, c.lgT, mu, ld_mu, alpha_hat, alpha, conv, status, prior_var_dev, c.tickets + 2,
                        (c.debug & PDQ_DEBUG_FORCE_ALPHA_GRID) ? 1 : 0};
-        const size_t smem_alpha = d.smem_bytes + (size_t)kWarps * (32 >> c.lgT) * 2 * kPsiK * sizeof(double);
-        if (int e = prep(k_alpha_mle<P>, smem_alpha)) return e;
+        const size_t smem_alpha = d.smem_bytes + kMathTabBytes + (size_t)kWarps * (32 >> c.lgT) * 2 * kPsiK * sizeof(double);
         if (int e = prep(k_alpha_grid<P>, d.smem_bytes)) return e;
-        if (cudaMemsetAsync(c.tickets + 1, 0, sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;
-        k_alpha_mle<P><<<persistent_grid(k_alpha_mle<P>, smem_alpha, c.sm_count, G, c.lgT), kBlock, smem_alpha, c.stream>>>(a);
-        k_alpha_grid<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
+        if (cudaMemsetAsync(c.tickets + 2, 0, 2 * sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;
+        if (d.staged) {
+            if (int e = prep(k_alpha_mle<P, true>, smem_alpha)) return e;
+            k_alpha_mle<P, true><<<persistent_grid(k_alpha_mle<P, true>, smem_alpha, c.sm_count, G, c.lgT), kBlock, smem_alpha, c.stream>>>(a);
+        } else {
+            if (int e = prep(k_alpha_mle<P, false>, smem_alpha)) return e;
+            k_alpha_mle<P, false><<<persistent_grid(k_alpha_mle<P, false>, smem_alpha, c.sm_count, G, c.lgT), kBlock, smem_alpha, c.stream>>>(a);
+        }
+        k_alpha_grid<P><<<fallback_grid(c.sm_count, G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });
     if (int e = check_launch()) return e;
     return 2;
@@ -820,7 +904,7 @@ int launch_wald(const LaunchCfg& c, const DesignDev& d, const double* disp, cons
                 double* stat, double* se) {
     PDQ_DISPATCH_P(d.p, {
         WaldArgs<P> a;
-        a.dv = DesignView{d.pack, d.N, d.Npad};
+        a.dv = DesignView{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0};
         for (int i = 0; i < P * P; ++i) a.prm.ridge[i] = ridge[i];
         for (int i = 0; i < P; ++i) a.prm.contrast[i] = contrast[i];
         a.prm.lfc_null = lfc_null;
@@ -836,7 +920,7 @@ int launch_wald(const LaunchCfg& c, const DesignDev& d, const double* disp, cons
 
 int launch_rough(const LaunchCfg& c, const DesignDev& d, const double* normed, int64_t ld, int G, double* alpha) {
     PDQ_DISPATCH_P(d.p, {
-        MomArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d), normed, nullptr, ld, G, c.lgT, d.s_mean_inv, 0.0, 0.0, alpha,
+        MomArgs<P> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, pinv_of<P>(d), normed, nullptr, ld, G, c.lgT, d.s_mean_inv, 0.0, 0.0, alpha,
                      nullptr, 0.0, nullptr, 0};
         if (int e = prep(k_rough<P>, d.smem_bytes)) return e;
         k_rough<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
@@ -848,7 +932,7 @@ int launch_rough(const LaunchCfg& c, const DesignDev& d, const double* normed, i
 int launch_moments(const LaunchCfg& c, const DesignDev& d, const double* normed, int64_t ld, int G, double* alpha,
                    double* all_zero) {
     PDQ_DISPATCH_P(d.p, {
-        MomArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d), normed, nullptr, ld, G, c.lgT, d.s_mean_inv, 0.0, 0.0, alpha,
+        MomArgs<P> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, pinv_of<P>(d), normed, nullptr, ld, G, c.lgT, d.s_mean_inv, 0.0, 0.0, alpha,
                      all_zero, 0.0, nullptr, 0};
         if (int e = prep(k_moments<P>, d.smem_bytes)) return e;
         k_moments<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
@@ -861,7 +945,7 @@ int launch_mom_from_counts(const LaunchCfg& c, const DesignDev& d, const int64_t
                            double min_disp, double max_disp, double* alpha, double* normed_mean, double min_mu, double* mu_hat,
                            int64_t ld_mu) {
     PDQ_DISPATCH_P(d.p, {
-        MomArgs<P> a{{d.pack, d.N, d.Npad}, pinv_of<P>(d), nullptr, counts, ld, G, c.lgT, d.s_mean_inv, min_disp,
+        MomArgs<P> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, pinv_of<P>(d), nullptr, counts, ld, G, c.lgT, d.s_mean_inv, min_disp,
                      max_disp, alpha, normed_mean, min_mu, mu_hat, ld_mu};
         if (int e = prep(k_mom_from_counts<P>, d.smem_bytes)) return e;
         k_mom_from_counts<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
@@ -872,7 +956,7 @@ int launch_mom_from_counts(const LaunchCfg& c, const DesignDev& d, const int64_t
 
 int launch_mu_from_lfc(const LaunchCfg& c, const DesignDev& d, const double* lfc, int G, double* mu, int64_t ld_out) {
     PDQ_DISPATCH_P(d.p, {
-        MuLfcArgs<P> a{{d.pack, d.N, d.Npad}, lfc, G, c.lgT, mu, ld_out};
+        MuLfcArgs<P> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, lfc, G, c.lgT, mu, ld_out};
         if (int e = prep(k_mu_from_lfc<P>, d.smem_bytes)) return e;
         k_mu_from_lfc<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });
@@ -939,7 +1023,7 @@ int launch_cooks(const LaunchCfg& c0, const DesignDev& d, const int64_t* counts,
     while (c.lgT < 5 && need(c.lgT) > 96 * 1024) ++c.lgT;
     if (need(c.lgT) > kMaxDynSmem) return PDQ_ERR_UNSUPPORTED;
     PDQ_DISPATCH_P(d.p, {
-        CooksArgs<P> a{{d.pack, d.N, d.Npad}, d.cell_plan, d.plan_len, d.n_cells, d.n_in_cells, counts, ld, G, c.lgT, mu, hat, ld2,
+        CooksArgs<P> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, d.cell_plan, d.plan_len, d.n_cells, d.n_in_cells, counts, ld, G, c.lgT, mu, hat, ld2,
                        cutoff, cooks, ld_out, disp, outlier, replaced};
         if (int e = prep(k_cooks<P>, need(c.lgT))) return e;
         k_cooks<P><<<grid_for(G, c.lgT), kBlock, need(c.lgT), c.stream>>>(a);
@@ -956,12 +1040,12 @@ int launch_lfc_shrink(const LaunchCfg& c, const DesignDev& d, const int64_t* cou
     const ShrinkParams prm{1.0 / (prior_no_shrink_scale * prior_no_shrink_scale), prior_scale * prior_scale, shrink_index};
     const int force = (c.debug & PDQ_DEBUG_FORCE_SHRINK_GRID) ? 1 : 0;
     PDQ_DISPATCH_P(d.p, {
-        ShrinkArgs<P> a{{d.pack, d.N, d.Npad}, prm, counts, ld, G, c.lgT, size, beta, inv_hessian, conv, status, force};
+        ShrinkArgs<P> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, prm, counts, ld, G, c.lgT, size, beta, inv_hessian, conv, status, force};
         if (int e = prep(k_lfc_shrink<P>, d.smem_bytes)) return e;
         k_lfc_shrink<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });
     if (d.p == 2) {
-        ShrinkArgs<2> a{{d.pack, d.N, d.Npad}, prm, counts, ld, G, c.lgT, size, beta, inv_hessian, conv, status, force};
+        ShrinkArgs<2> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, prm, counts, ld, G, c.lgT, size, beta, inv_hessian, conv, status, force};
         if (int e = prep(k_lfc_shrink_grid, d.smem_bytes)) return e;
         k_lfc_shrink_grid<<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     }

@@ -48,7 +48,7 @@ PDQ_HD void shrink_eval(const Group& grp, const DesignS& d, const ShrinkParams& 
         double xb = 0.0;
 #pragma unroll
         for (int j = 0; j < P; ++j) xb = fma(x[j], beta[j], xb);
-        const double e = xb + d.lsf[n];
+        const double e = xb + d.lsf[n * d.RS];
         const double dd = e - lsize;
         const double t = exp(-fabs(dd));                    // in (0, 1]
         const double lae = fmax(e, lsize) + log1p(t);       // logaddexp(e, log s)
@@ -93,7 +93,7 @@ PDQ_HD void shrink_inv_hessian(const Group& grp, const DesignS& d, const ShrinkP
         double xb = 0.0;
 #pragma unroll
         for (int j = 0; j < P; ++j) xb = fma(x[j], beta[j], xb);
-        const double dd = xb + d.lsf[n] - lsize;
+        const double dd = xb + d.lsf[n * d.RS] - lsize;
         const double t = exp(-fabs(dd));
         const double w = (yv + size) * (t / ((1.0 + t) * (1.0 + t)));  // (y+s) s e / (s+e)^2 = (y+s) q (1-q)
         sym_rank1<P>(A, w, x);

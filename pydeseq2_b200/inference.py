@@ -174,6 +174,15 @@ class _CudaOps:
         return coeffs, pred, bool(ok.value)
 
 
+    def trend_prior(self, means, genewise, min_disp, max_disp, trigamma_c):
+        n = len(means)
+        out16, fitted = np.empty(16), np.empty(n)
+        self._io((means, genewise), (out16, fitted))
+        self.ctx.check(self.lib.pdq_trend_prior(self.ctx.h, as_f64p(means), as_f64p(genewise), n, min_disp, max_disp, trigamma_c,
+                                                as_f64p(out16), as_f64p(fitted)))
+        return out16, fitted
+
+
 class B200Inference(_InferenceBase):
     """B200 implementation of the reference's ``Inference`` plugin API.
 
@@ -194,8 +203,11 @@ class B200Inference(_InferenceBase):
     _TRACED = ("lin_reg_mu", "irls", "alpha_mle", "wald_test", "fit_rough_dispersions", "fit_moments_dispersions",
                "dispersion_trend_gamma_glm", "lfc_shrink_nbinom_glm", "size_factors", "calculate_cooks")
 
-    def __init__(self, device: int = 0, n_cpus: int | None = None, lanes_per_gene: int = 0, _ops=None, trace: bool = False):
-        self._ops = _ops if _ops is not None else _CudaOps(device, lanes_per_gene)
+    def __init__(self, device: int = 0, n_cpus: int | None = None, lanes_per_gene: int = 0, _ops=None, trace: bool = False,
+                 pinned_outputs: bool = True):
+        # pinned_outputs: large results are returned in page-locked numpy blocks (full-rate device-to-host copies, and full-rate
+        # uploads when the caller hands them back); False returns ordinary pageable arrays
+        self._ops = _ops if _ops is not None else _CudaOps(device, lanes_per_gene, pinned_outputs)
         self._n_cpus = n_cpus or 1
         self.last_irls_fallbacks = 0
         # per-call tracing (the reference prints wall-clock per phase to stderr, dds.py:626-711 ...; a backend is better served by
@@ -350,7 +362,27 @@ class B200Inference(_InferenceBase):
         coeffs, pred, ok = self._ops.trend_glm(cov, tgt)
         return coeffs, pred, ok
 
-    # ------------------------------------------------------------------ beyond the ABC (SURVEY.md §8 f-2)
+    # ------------------------------------------------------------------ beyond the ABC
+    def trend_and_prior(self, normed_means, genewise, min_disp, max_disp, n_samples, n_coeffs):
+        """``fit_dispersion_trend`` (parametric, dds.py:1199-1275) and ``fit_dispersion_prior`` (dds.py:840-884) in ONE kernel
+        launch on the gene-length vectors, instead of one plugin call per round of the orchestrator's outlier loop plus numpy
+        medians.  Returns ``(coeffs (2,), fitted (G,), squared_logres, prior_var, n_rounds)`` or ``None`` when the parametric
+        fit fails (the caller then falls back to the mean trend exactly like the orchestrator, dds.py:1243-1252) or the
+        backend cannot run it."""
+        if not hasattr(self._ops, "trend_prior"):
+            return None
+        from scipy.special import polygamma
+
+        means = np.ascontiguousarray(_f64(normed_means, "normed_means", 1))
+        gw = np.ascontiguousarray(_f64(genewise, "genewise", 1))
+        if means.shape != gw.shape or not len(means):
+            raise ValueError("normed_means and genewise must be non-empty vectors of the same length")
+        out16, fitted = self._ops.trend_prior(means, gw, float(min_disp), float(max_disp),
+                                              float(polygamma(1, (n_samples - n_coeffs) / 2)))
+        if out16[2] != 0.0:
+            return None
+        return np.array([out16[0], out16[1]]), fitted, float(out16[8]), float(out16[9]), int(out16[3])
+
     def size_factors(self, counts):
         """Median-of-ratios size factors on the device (``preprocessing.deseq2_norm``, preprocessing.py:5-102).
 

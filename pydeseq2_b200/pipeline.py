@@ -185,13 +185,23 @@ def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5,
     mu_hat = np.ascontiguousarray(mu_hat)                # layers["_mu_hat"][:, non_zero_idx] is a fresh C array
     gw, gw_conv = timed("alpha_mle_genewise", inference.alpha_mle, c, X, mu_hat, mom, min_disp, max_disp)
     gw = np.clip(gw, min_disp, max_disp)                 # dds.py:792-794
+    # trend + prior are global over ALL genes of ALL shards (dds.py:799-884): with gene shards the two per-gene vectors are
+    # all-gathered first (the only exchange on the path)
     if comm is None:
-        trend = timed("trend", fit_trend, inference, normed_means, gw, min_disp, fit_type)
-        sq, prior_var = timed("prior", fit_prior_var, gw, trend.fitted, N, p, min_disp)
+        gw_all, means_all = gw, normed_means
     else:
+        assert len(gw) == len(normed_means) <= comm.sizes[comm.rank], "comm.sizes must bound the shard's non-zero genes"
         gw_all, means_all = timed("allgather", comm.allgather_pair, gw, normed_means)
+        keep = ~np.isnan(means_all)  # NaN = padding of shorter shards (and nothing else: means of non-zero genes are finite)
+        gw_all, means_all = gw_all[keep], means_all[keep]
+    one_launch = getattr(inference, "trend_and_prior", None) if fit_type == "parametric" else None
+    tp = timed("trend_prior", one_launch, means_all, gw_all, min_disp, max_disp, N, p) if one_launch is not None else None
+    if tp is not None:   # backend runs the orchestrator's trend loop + prior in one launch (B200Inference.trend_and_prior)
+        trend, sq, prior_var = TrendFit("parametric", tp[0], tp[1], tp[4]), tp[2], tp[3]
+    else:
         trend = timed("trend", fit_trend, inference, means_all, gw_all, min_disp, fit_type)
         sq, prior_var = timed("prior", fit_prior_var, gw_all, trend.fitted, N, p, min_disp)
+    if comm is not None:
         local = (trend.coeffs[0] + trend.coeffs[1] / normed_means) if trend.kind == "parametric" else np.full_like(gw, trend.coeffs[0])
         trend = TrendFit(trend.kind, trend.coeffs, local, trend.n_iter)
     mp, mp_conv = timed("alpha_mle_map", inference.alpha_mle, c, X, mu_hat, trend.fitted, min_disp, max_disp,
@@ -291,7 +301,9 @@ class ResidentFit:
         self.comm = comm
         self.with_cooks = with_cooks  # also compute Cook's distances (per-gene outlier flags) after the LFC fit
         self.use_graph = True         # replay the pass as one CUDA graph after the first eager pass
-        self._graph, self._graph_key, self._eager_key = None, None, None
+        self.fuse_wald = True         # Wald test inside the LFC-fit launch (False: the two plugin-shaped calls in sequence)
+        self.gather = comm is not None  # end the pass with the all-gather of the result tables of all gene shards
+        self._graph, self._graph_key, self._eager_key, self._graph_epoch = None, None, None, -1
         self.design = None
         self.sf = None
         if size_factors is not None:  # None: median of ratios on the device from the uploaded counts (see upload)
@@ -350,22 +362,31 @@ class ResidentFit:
         self.d_mu = self._dev("mu", ng)
         self.d_hat = self._dev("hat", ng)
         # every per-gene result lives in ONE device slab mirrored by one page-locked host block: a pass ends with a single
-        # device-to-host copy instead of a dozen small ones
+        # device-to-host copy instead of a dozen small ones.  With gene shards every vector is laid out with the LARGEST shard's
+        # length `Gs` and NaN behind this shard's last gene (written here, once): the slab then is directly the send buffer of the
+        # equal-count NCCL all-gathers -- no per-step padding, no staging.
         per_gene = ("mom", "means", "gw", "gw_conv", "map", "map_conv", "disp", "conv", "pv", "stat", "se", "outlier",
                     "robust_disp", "cooks_outlier", "cooks_replaced")
-        total = len(per_gene) * G + G * p + 16
+        Gs = self.Gs = self.comm.max_size if self.comm is not None else G
+        assert Gs >= G
+        total = self._slab_len = len(per_gene) * Gs + Gs * p + 16
         self.d_slab = self._dev("slab", total * 8)
         self._h_slab = self.ctx.pinned_empty((total,))
-        self._h_slab[:] = 0.0
+        self._h_slab[:] = np.nan
         self._h = {}
+        self._slab_off = {}
         off = 0
         for name in per_gene:
             setattr(self, "d_" + name, self.d_slab + off * 8)
             self._h[name] = self._h_slab[off:off + G]
-            off += G
+            self._slab_off[name] = (off, 1)
+            off += Gs
         self.d_beta, self._h["beta"] = self.d_slab + off * 8, self._h_slab[off:off + G * p].reshape(G, p)
-        off += G * p
+        self._slab_off["beta"] = (off, p)
+        off += Gs * p
         self.d_t16, self._h["t16"] = self.d_slab + off * 8, self._h_slab[off:off + 16]
+        self._h_slab[off:off + 16] = 0.0
+        self.ctx.h2d(self.d_slab, self._h_slab)  # NaN pads (and zeros) land on the device once
         for name, n in (("fitted", G), ("beta0", G * p)):
             setattr(self, "d_" + name, self._dev(name, n * 8))
         self.d_nfb = self._dev("nfb", 64)
@@ -390,11 +411,13 @@ class ResidentFit:
             self.design = None
 
     # -- one pass ----------------------------------------------------------------------------------
-    def run(self, contrast=None, lfc_null=0.0, alt_hypothesis=None, fit_type="parametric", profile=False):
+    def run(self, contrast=None, lfc_null=0.0, alt_hypothesis=None, fit_type="parametric", profile=False, copy=True, events=None):
         """One pass of the hot path.  Every stage is enqueued on the context's stream back to back -- the trend and
         the dispersion prior run on the device too -- so the host synchronises exactly once, at the end.
         ``profile=True`` brackets every stage with CUDA events (``stage_ms``); it serialises the host against each
-        stage, so never time a step with it."""
+        stage, so never time a step with it.  ``copy=False`` returns views into the page-locked result block, which the NEXT
+        pass overwrites.  ``events=(a, b)``: record the context's event slots around the device work of the pass -- first launch
+        to the end of the result copy -- so that a caller can time exactly that (``ctx.elapsed_ms(a, b)`` after the call)."""
         L, ctx, h, d, G = self.lib, self.ctx, self.ctx.h, self.design, self.G
         c_d = self._lib_mod.c_dptr
         p, N = self.p, self.N
@@ -426,8 +449,9 @@ class ResidentFit:
         n_all = W * m
         if self.comm is not None:
             d_gw_all, d_means_all = self._dev("gw_all", n_all * 8), self._dev("means_all", n_all * 8)
+            d_table_all = self._dev("table_all", W * self._slab_len * 8) if self.gather else None
         else:
-            d_gw_all, d_means_all = self.d_gw, self.d_means
+            d_gw_all, d_means_all, d_table_all = self.d_gw, self.d_means, None
         d_fit_all = self._dev("fitted_all", n_all * 8)
         d_t16 = self.d_t16
         d_fitted = d_fit_all + rank * m * 8  # this shard's slice of the fitted curve
@@ -452,7 +476,7 @@ class ResidentFit:
             #    vectors are all-gathered over NCCL first, device to device; the fit itself is one cluster launch.
             if self.comm is not None:
                 begin("allgather")
-                self.comm.allgather_dev(self.d_gw, d_gw_all, self.d_means, d_means_all, G)
+                self.comm.allgather_dev([(self.d_gw, d_gw_all), (self.d_means, d_means_all)], m)
                 if profile:
                     check(0)
             if fit_type == "parametric":
@@ -460,15 +484,28 @@ class ResidentFit:
                 check(L.pdq_trend_fit_dev(h, c_d(d_means_all), c_d(d_gw_all), n_all, self.min_disp, self.max_disp, trigamma_c,
                                           c_d(d_t16), c_d(d_fit_all)))
                 self._tail(d_fitted, d_t16, d_t16 + 9 * 8, 0.0, contrast, ridge, lfc_null, alt_hypothesis, begin, check)
-            ctx.d2h(self._h_slab, self.d_slab)  # every per-gene result + the trend record, one copy
+                if d_table_all is not None:
+                    # end-of-call exchange (SURVEY.md §8e / north star): ONE all-gather of the whole result slab -- dispersions,
+                    # coefficients, flags, Wald statistics of every shard -- after which each rank holds the full tables in HBM
+                    begin("gather_results")
+                    self.comm.allgather_dev([(self.d_slab, d_table_all)], self._slab_len)
+                    if profile:
+                        check(0)
+            ctx.d2h(self._h_slab, self.d_slab)  # every per-gene result of THIS shard + the trend record, one copy
 
         # The pass is ~20 launches + copies with no host synchronisation in between: after one eager pass (which allocates
         # every buffer) the identical sequence is captured into a CUDA graph and replayed with a single call.
-        ragged = self.comm is not None and len(set(self.comm.sizes)) > 1  # NaN-padding stages through pageable memory
-        key = (fit_type, contrast.tobytes(), float(lfc_null), alt_hypothesis, G, self.with_cooks, n_all)
-        if self.use_graph and not profile and not ragged and self._graph is not None and self._graph_key == key:
+        key = (fit_type, contrast.tobytes(), float(lfc_null), alt_hypothesis, G, self.with_cooks, n_all, self.fuse_wald)
+        # a captured pass holds pointers into context-owned scratch (per-gene status words, trend scratch); host-buffer calls on the
+        # same context may have re-allocated it since: the context counts re-allocations, a stale graph is dropped and re-captured
+        if events:
+            ctx.record(events[0])
+        if self._graph is not None and self._graph_epoch != L.pdq_buffer_epoch(h):
+            self._drop_graph()
+            self._eager_key = None
+        if self.use_graph and not profile and self._graph is not None and self._graph_key == key:
             ctx.check(L.pdq_graph_launch(h, self._graph))
-        elif self.use_graph and not profile and not ragged and self._eager_key == key:
+        elif self.use_graph and not profile and self._eager_key == key:
             self._drop_graph()
             ctx.check(L.pdq_capture_begin(h))
             try:
@@ -476,11 +513,13 @@ class ResidentFit:
             finally:
                 g = C.c_void_p()
                 ctx.check(L.pdq_capture_end(h, C.byref(g)))
-            self._graph, self._graph_key = g, key
+            self._graph, self._graph_key, self._graph_epoch = g, key, L.pdq_buffer_epoch(h)
             ctx.check(L.pdq_graph_launch(h, self._graph))
         else:
             enqueue()
             self._eager_key = key
+        if events:
+            ctx.record(events[1])
         ctx.sync()  # the only host synchronisation of the pass
         t16 = H["t16"]
         if fit_type == "parametric" and t16[2] == 0.0:
@@ -507,6 +546,8 @@ class ResidentFit:
             ctx.h2d(d_t16, rec)
             ctx.h2d(d_fit_all, fit_all)
             self._tail(d_fitted, d_t16, None, prior_var, contrast, ridge, lfc_null, alt_hypothesis, begin, check)
+            if d_table_all is not None:
+                self.comm.allgather_dev([(self.d_slab, d_table_all)], self._slab_len)
             ctx.d2h(self._h_slab, self.d_slab)
             ctx.sync()
         gw = np.clip(H["gw"], self.min_disp, self.max_disp)
@@ -516,25 +557,47 @@ class ResidentFit:
             trend = TrendFit("parametric", trend.coeffs, fitted, trend.n_iter)
         else:
             fitted = np.full(G, trend.coeffs[0])
-        return {"mom": H["mom"], "genewise": gw, "genewise_converged": H["gw_conv"], "trend": trend, "prior_var": prior_var,
-                "squared_logres": sq, "map": np.clip(H["map"], self.min_disp, self.max_disp), "map_converged": H["map_conv"],
-                "dispersions": H["disp"], "lfc": H["beta"], "lfc_converged": H["conv"], "pvalue": H["pv"], "stat": H["stat"],
-                "se": H["se"], "normed_means": means, "fitted": fitted, "outlier": H["outlier"],
-                **({"robust_dispersions": H["robust_disp"], "cooks_outlier": H["cooks_outlier"] == 1.0,
+        # the slab is reused by the next pass: hand out copies (a result dict must survive later run() calls)
+        cp = np.array if copy else (lambda v: v)
+        return {"mom": cp(H["mom"]), "genewise": gw, "genewise_converged": cp(H["gw_conv"]), "trend": trend, "prior_var": prior_var,
+                "squared_logres": sq, "map": np.clip(H["map"], self.min_disp, self.max_disp), "map_converged": cp(H["map_conv"]),
+                "dispersions": cp(H["disp"]), "lfc": cp(H["beta"]), "lfc_converged": cp(H["conv"]), "pvalue": cp(H["pv"]),
+                "stat": cp(H["stat"]), "se": cp(H["se"]), "normed_means": cp(means), "fitted": fitted, "outlier": cp(H["outlier"]),
+                **({"robust_dispersions": cp(H["robust_disp"]), "cooks_outlier": H["cooks_outlier"] == 1.0,
                     "cooks_replaced": H["cooks_replaced"] == 1.0} if self.with_cooks else {})}
 
     def gather_results(self, result: dict) -> dict:
-        """End-of-call exchange of the gene shards (SURVEY.md §8 e): one packed NCCL all-gather of every per-gene result of
-        :meth:`run`, after which each rank holds the full-length tables (rank order = gene order).  No-op without shards."""
+        """Full-length per-gene tables on this rank (rank order = gene order) from the end-of-call all-gather :meth:`run` issued
+        (``self.gather``): one device-to-host copy of the gathered slab, NaN pads of short shards stripped.  No-op without shards."""
         if self.comm is None:
             return result
-        keys = [k for k, v in result.items() if isinstance(v, np.ndarray) and v.shape[:1] == (self.G,)]
-        full = self.comm.allgather_table({k: np.asarray(result[k], dtype=np.float64) for k in keys})
+        if not self.gather:
+            raise RuntimeError("run() was told not to gather (ResidentFit.gather = False)")
+        W, L = self.comm.world, self._slab_len
+        tab = self.ctx.pinned_empty((W, L))
+        self.ctx.d2h(tab, self._dev("table_all", W * L * 8))
+        self.ctx.sync()
+        sizes = self.comm.sizes
+        names = {"mom": "mom", "genewise": "gw", "genewise_converged": "gw_conv", "map": "map", "map_converged": "map_conv",
+                 "dispersions": "disp", "lfc": "beta", "lfc_converged": "conv", "pvalue": "pv", "stat": "stat", "se": "se",
+                 "normed_means": "means", "outlier": "outlier"}
+        if self.with_cooks:
+            names.update(robust_dispersions="robust_disp", cooks_outlier="cooks_outlier", cooks_replaced="cooks_replaced")
         out = dict(result)
-        out.update(full)
+        for key, slot in names.items():
+            off, w = self._slab_off[slot]
+            parts = [tab[r, off:off + sizes[r] * w] for r in range(W)]
+            full = np.concatenate(parts)
+            out[key] = full.reshape(-1, w) if w > 1 else full
+        out["genewise"] = np.clip(out["genewise"], self.min_disp, self.max_disp)
+        out["map"] = np.clip(out["map"], self.min_disp, self.max_disp)
+        if result["trend"].kind == "parametric":
+            out["fitted"] = result["trend"].coeffs[0] + result["trend"].coeffs[1] / out["normed_means"]
+        else:
+            out["fitted"] = np.full(len(out["normed_means"]), result["trend"].coeffs[0])
         for k in ("cooks_outlier", "cooks_replaced"):
-            if k in full:
-                out[k] = full[k] == 1.0
+            if k in out and k in names:
+                out[k] = out[k] == 1.0
         return out
 
     # -- apeGLM shrinkage on the resident counts ----------------------------------------------------------
@@ -584,15 +647,22 @@ class ResidentFit:
         begin("select_dispersions")
         check(L.pdq_select_dispersions_dev(h, c_d(self.d_gw), c_d(self.d_map), c_d(d_fitted), c_d(d_t16), G, self.min_disp,
                                            self.max_disp, c_d(self.d_disp), c_d(self.d_outlier)))
-        # 6. LFC fit (dds.py:937-984): beta, mu (unclamped), hat diagonal stay on the device
-        begin("irls_lfc")
-        check(L.pdq_irls_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_disp), self.min_mu, self.beta_tol, -30.0, 30.0, 250,
-                             c_d(self.d_beta), c_d(self.d_mu), c_d(self.d_hat), G, c_d(self.d_conv), c_d(self.d_nfb)))
-        # 7. Wald (ds.py:303-360): mu = sf * exp(X beta) is exactly the mu the LFC fit just wrote (unclamped)
-        begin("wald_test")
-        check(L.pdq_wald_test_dev(h, d, c_d(self.d_disp), c_d(self.d_beta), c_d(self.d_mu), G, G,
-                                  self._lib_mod.as_f64p(ridge), self._lib_mod.as_f64p(contrast), LN2 * lfc_null,
-                                  self._lib_mod.ALT_CODES[alt_hypothesis], c_d(self.d_pv), c_d(self.d_stat), c_d(self.d_se)))
+        # 6. + 7. LFC fit (dds.py:937-984: beta, mu (unclamped), hat diagonal stay on the device) and the Wald test of its
+        #    coefficients (ds.py:303-360) in ONE launch: the test's X^T W X is the last IRLS sweep's, so mu is not read again
+        begin("irls_lfc_wald" if self.fuse_wald else "irls_lfc")
+        if self.fuse_wald:
+            check(L.pdq_irls_wald_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_disp), self.min_mu, self.beta_tol, -30.0, 30.0, 250,
+                                      c_d(self.d_beta), c_d(self.d_mu), c_d(self.d_hat), G, c_d(self.d_conv), c_d(self.d_nfb),
+                                      self._lib_mod.as_f64p(ridge), self._lib_mod.as_f64p(contrast), LN2 * lfc_null,
+                                      self._lib_mod.ALT_CODES[alt_hypothesis], c_d(self.d_pv), c_d(self.d_stat), c_d(self.d_se)))
+        else:
+            check(L.pdq_irls_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_disp), self.min_mu, self.beta_tol, -30.0, 30.0, 250,
+                                 c_d(self.d_beta), c_d(self.d_mu), c_d(self.d_hat), G, c_d(self.d_conv), c_d(self.d_nfb)))
+            # mu = sf * exp(X beta) is exactly the mu the LFC fit just wrote (unclamped)
+            begin("wald_test")
+            check(L.pdq_wald_test_dev(h, d, c_d(self.d_disp), c_d(self.d_beta), c_d(self.d_mu), G, G,
+                                      self._lib_mod.as_f64p(ridge), self._lib_mod.as_f64p(contrast), LN2 * lfc_null,
+                                      self._lib_mod.ALT_CODES[alt_hypothesis], c_d(self.d_pv), c_d(self.d_stat), c_d(self.d_se)))
         # 8. optional: Cook's distances from the resident mu / hat (dds.py:986-1040); only per-gene results leave the device
         if self.with_cooks:
             from scipy.stats import f as _f
@@ -601,11 +671,3 @@ class ResidentFit:
             check(L.pdq_cooks_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu), c_d(self.d_hat), G,
                                   float(_f.ppf(0.99, self.p, self.N - self.p)), None, G, c_d(self.d_robust_disp),
                                   c_d(self.d_cooks_outlier), c_d(self.d_cooks_replaced)))
-
-class _HostTrend:
-    """The trend GLM of B200Inference without needing a device context."""
-
-    def dispersion_trend_gamma_glm(self, covariates, targets):
-        from .inference import B200Inference
-
-        return B200Inference.dispersion_trend_gamma_glm(None, covariates, targets)

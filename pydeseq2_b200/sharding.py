@@ -118,7 +118,6 @@ class NcclComm(_PaddedGather):
         self._send = self._recv = None
         self.world = len(self.sizes)
         self.max_size = max(self.sizes)
-        self._pad = None
 
     @staticmethod
     def make_unique_id(ctx) -> bytes:
@@ -147,21 +146,15 @@ class NcclComm(_PaddedGather):
         self.ctx.sync()
         return self._hr.copy()
 
-    def allgather_dev(self, d_a, d_a_all, d_b, d_b_all, n_local):
-        """Device-to-device all-gather of two per-gene vectors (genewise dispersions, normalised means).  Ragged
-        shards are NaN-padded to the largest shard so that NCCL's equal-count all-gather applies."""
-        m = self.max_size
-        lib, h, cd = self.ctx.lib, self.ctx.h, self._c_dptr
-        for src, dst in ((d_a, d_a_all), (d_b, d_b_all)):
-            send = src
-            if n_local < m:  # stage a NaN-padded copy of the short shard
-                if self._pad is None:
-                    self._pad = self.ctx.malloc(m * 8)
-                    self._nan = np.full(m, np.nan)
-                self.ctx.h2d(self._pad, self._nan)
-                self.ctx.check(lib.pdq_memcpy_d2d(h, cd(self._pad), cd(src), n_local * 8))
-                send = self._pad
-            self.ctx.check(lib.pdq_allgather_f64_dev(h, cd(send), cd(dst), m))
+    def allgather_dev(self, pairs, count):
+        """Device-to-device all-gather of several equal-length vectors as ONE NCCL group (a single fused launch on the context's
+        stream, capturable into a CUDA graph).  ``pairs`` = [(send_ptr, recv_ptr), ...], every send buffer holds ``count``
+        doubles -- the largest shard's length; shorter shards keep NaN behind their last gene (written once at upload time,
+        never per step) -- and every recv buffer ``world * count``."""
+        k = len(pairs)
+        send = (C.c_void_p * k)(*[p[0] for p in pairs])
+        recv = (C.c_void_p * k)(*[p[1] for p in pairs])
+        self.ctx.check(self.ctx.lib.pdq_allgather_multi_f64_dev(self.ctx.h, k, send, recv, int(count)))
 
     def close(self):
         self.ctx.check(self.ctx.lib.pdq_comm_destroy(self.ctx.h))

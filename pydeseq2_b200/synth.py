@@ -39,13 +39,19 @@ def design_matrix(N: int, kind: str, seed: int = 0) -> np.ndarray:
     return np.ascontiguousarray(np.stack(cols, axis=1))
 
 
-def make_counts(N: int, G: int, kind: str = "two_level", seed: int = 0, chunk: int = 1 << 16, mean_log2: float = 4.0):
+def make_counts(N: int, G: int, kind: str = "two_level", seed: int = 0, chunk: int = 1 << 16, mean_log2: float = 4.0,
+                sample_seed: int | None = None):
     """Return ``(counts int64 (N, G), X float64 (N, p), truth dict)``.  ``mean_log2`` shifts the expression level
-    (4 = the reference-like default; 18 gives counts of 1e5-1e7 like the reference's ``large_counts`` test)."""
+    (4 = the reference-like default; 18 gives counts of 1e5-1e7 like the reference's ``large_counts`` test).
+    ``sample_seed``: draw the per-SAMPLE quantities (design matrix, true size factors) from this seed and only the per-gene
+    ones from ``seed`` -- gene shards of one cohort (same samples, different genes) are ``sample_seed`` fixed, ``seed`` = rank."""
     rng = np.random.default_rng(seed)
-    X = design_matrix(N, kind, seed)
+    X = design_matrix(N, kind, seed if sample_seed is None else sample_seed)
     p = X.shape[1]
-    sf = np.exp(rng.normal(0.0, 0.2, N))
+    if sample_seed is None:
+        sf = np.exp(rng.normal(0.0, 0.2, N))
+    else:
+        sf = np.exp(np.random.default_rng(sample_seed + 1000003).normal(0.0, 0.2, N))
     beta = np.empty((G, p))
     beta[:, 0] = rng.normal(mean_log2, 2.0, G) * LN2
     beta[:, 1:] = rng.normal(0.0, 0.5, (G, p - 1)) * LN2

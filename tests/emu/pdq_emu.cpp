@@ -110,18 +110,22 @@ struct Pack {
 
 Pack make_pack(const double* X, const double* sf, int N, int p) {
     Pack k;
-    const int Npad = (N + 1) & ~1;
-    k.buf.assign((size_t)(p + 2) * Npad, 0.0);
+    const int RS = design_row_stride(p);
+    k.buf.assign((size_t)(N + 1) * RS, 0.0);
     double inv = 0;
     for (int n = 0; n < N; ++n) {
-        for (int j = 0; j < p; ++j) k.buf[(size_t)j * Npad + n] = X[(size_t)n * p + j];
+        for (int j = 0; j < p; ++j) {
+            k.buf[(size_t)n * RS + j] = X[(size_t)n * p + j];
+            double& mx = k.buf[(size_t)N * RS + j];
+            mx = !(fabs(X[(size_t)n * p + j]) <= mx) ? fabs(X[(size_t)n * p + j]) : mx;
+        }
         const double s = sf ? sf[n] : 1.0;
-        k.buf[(size_t)p * Npad + n] = s;
-        k.buf[(size_t)(p + 1) * Npad + n] = log(s);
+        k.buf[(size_t)n * RS + p] = s;
+        k.buf[(size_t)n * RS + p + 1] = log(s);
         inv += 1.0 / s;
     }
     k.s_mean_inv = inv / N;
-    k.d = DesignS{k.buf.data(), k.buf.data() + (size_t)p * Npad, k.buf.data() + (size_t)(p + 1) * Npad, N, Npad, host_math_table()};
+    k.d = DesignS{k.buf.data(), k.buf.data() + p, k.buf.data() + p + 1, N, RS, host_math_table()};
     design_linear_algebra(X, N, p, k.pinv, &k.full_rank);
     return k;
 }
@@ -235,7 +239,7 @@ int emu_lfc_shrink(const double* X, const int64_t* counts, int64_t ld, int N, in
                    double prior_no_shrink_scale, double prior_scale, int shrink_index, double* lfcs, double* inv_hessians, double* conv,
                    int* status, int force_grid) {
     Pack k = make_pack(X, nullptr, N, p);
-    for (int n = 0; n < N; ++n) k.buf[(size_t)(p + 1) * k.d.Npad + n] = offset[n];
+    for (int n = 0; n < N; ++n) k.buf[(size_t)n * k.d.RS + p + 1] = offset[n];
     const ShrinkParams prm{1.0 / (prior_no_shrink_scale * prior_no_shrink_scale), prior_scale * prior_scale, shrink_index};
     EMU_DISPATCH(p, {
         for (int g = 0; g < G; ++g)
