@@ -78,6 +78,15 @@ int64_t pdq_launch_count(const pdq_ctx* ctx);
  * re-capture when it changed. */
 int64_t pdq_buffer_epoch(const pdq_ctx* ctx);
 
+/* Residency of the host-buffer entry points: (samples, genes) inputs of at least 1 MB are keyed on a 128-bit checksum of their
+ * full content (computed by a few host threads at memory bandwidth) and kept on the device, (samples, genes) outputs are kept
+ * under the same checksum computed on the device; a later call that is handed the same CONTENT -- the orchestrator passes the
+ * same counts to four calls and feeds mu_hat / mu back (dds.py:752-779, 902, 954; ds.py:338), always as fresh host copies --
+ * skips the upload.  Never keyed on pointers.  Environment: PDQ_RESIDENCY=0 disables, PDQ_RESIDENCY_BYTES caps the device bytes
+ * (default: a quarter of device memory, at most 16 GB). */
+int pdq_residency_stats(const pdq_ctx* ctx, int64_t* hits, int64_t* misses, int64_t* hit_bytes, int64_t* resident_bytes);
+int pdq_residency_clear(pdq_ctx* ctx);
+
 int pdq_malloc(pdq_ctx* ctx, size_t bytes, void** dptr);
 int pdq_free(pdq_ctx* ctx, void* dptr);
 int pdq_host_alloc(pdq_ctx* ctx, size_t bytes, void** hptr); /* pinned host memory */

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "pdq_set_debug_flags": (C.c_int, [c_ctx, C.c_int]),
     "pdq_launch_count": (C.c_int64, [c_ctx]),
     "pdq_buffer_epoch": (C.c_int64, [c_ctx]),
+    "pdq_residency_stats": (C.c_int, [c_ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "pdq_residency_clear": (C.c_int, [c_ctx]),
     "pdq_malloc": (C.c_int, [c_ctx, C.c_size_t, C.POINTER(c_dptr)]),
     "pdq_free": (C.c_int, [c_ctx, c_dptr]),
     "pdq_host_alloc": (C.c_int, [c_ctx, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -209,6 +211,15 @@ class Context:
 
     def launches(self) -> int:
         return int(self.lib.pdq_launch_count(self.h))
+
+    def residency_stats(self) -> dict:
+        """Counters of the content-addressed residency cache of the host-buffer entry points."""
+        v = [C.c_int64() for _ in range(4)]
+        self.check(self.lib.pdq_residency_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("hits", "misses", "hit_bytes", "resident_bytes"), (x.value for x in v)))
+
+    def residency_clear(self):
+        self.check(self.lib.pdq_residency_clear(self.h))
 
     def fp64_peak_tflops(self) -> float:
         """Measured DFMA throughput of this device (TFLOP/s): the arithmetic roofline of the FP64-bound kernels."""

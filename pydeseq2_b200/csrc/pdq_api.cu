@@ -73,6 +73,25 @@ struct pdq_ctx {
     NcclApi nccl;
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
+    // content-addressed residency of the (N, G) buffers of the host-buffer entry points (see "residency" below)
+    struct ResEntry {
+        uint64_t h[2];
+        size_t bytes;
+        void* dptr;
+        uint64_t stamp;   // LRU clock
+        uint64_t call;    // id of the last call that used the entry (entries of the running call are never evicted)
+        int pending;      // >= 0: output whose device-side hash lands in hash_host[2 * pending] after the call's final sync
+        int state;        // 0 spare allocation, 1 being filled by the running call, 2 valid
+    };
+    std::vector<ResEntry*> res;  // heap objects: a slot handed to a call stays valid when other entries are evicted
+    size_t res_bytes = 0, res_cap = 0;
+    uint64_t res_clock = 0, res_call = 0;
+    int residency = 1;           // PDQ_RESIDENCY=0 disables
+    uint64_t* hash_dev = nullptr;   // 2 x 8 slots
+    uint64_t* hash_host = nullptr;  // page-locked mirror
+    int hash_pending = 0;
+    int64_t res_hits = 0, res_misses = 0;
+    int64_t res_hit_bytes = 0;
 };
 
 struct pdq_design {
@@ -174,6 +193,10 @@ extern "C" int pdq_ctx_create(int device, pdq_ctx** out) {
         }
     if (const char* s = getenv("PDQ_STAGING")) c->staging = atoi(s);
     if (const char* s = getenv("PDQ_PIPELINE")) c->pipeline = atoi(s);
+    if (const char* s = getenv("PDQ_RESIDENCY")) c->residency = atoi(s);
+    c->res_cap = c->prop.totalGlobalMem / 4;
+    if (c->res_cap > ((size_t)16 << 30)) c->res_cap = (size_t)16 << 30;
+    if (const char* s = getenv("PDQ_RESIDENCY_BYTES")) c->res_cap = (size_t)atoll(s);
     if (cudaMalloc((void**)&c->tickets, 64) != cudaSuccess || cudaStreamCreateWithFlags(&c->pstream[0], cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->pstream[1], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->pfork, cudaEventDisableTiming) != cudaSuccess ||
@@ -194,6 +217,12 @@ extern "C" void pdq_ctx_destroy(pdq_ctx* c) {
     c->dcache.clear();
     for (auto& b : c->buf)
         if (b) cudaFree(b);
+    for (auto* e : c->res) {
+        if (e->dptr) cudaFree(e->dptr);
+        delete e;
+    }
+    if (c->hash_dev) cudaFree(c->hash_dev);
+    if (c->hash_host) cudaFreeHost(c->hash_host);
     if (c->tickets) cudaFree(c->tickets);
     for (auto& st : c->pstream)
         if (st) cudaStreamDestroy(st);
@@ -712,6 +741,198 @@ static int h2d_2d(pdq_ctx* c, void* dst, const void* src, int64_t ld, int N, int
     return 0;
 }
 
+// ---- residency: content-addressed device copies of the (N, G) buffers ------------------------------------------------
+// One deseq2() hands the backend the SAME counts four times (dds.py:752 / 759, 779, 902, 954), the same mu_hat twice and the
+// mu it got back from the LFC fit once more (ds.py:338) -- each time as a fresh host array, so pointer identity says nothing.
+// The entry points therefore key device copies on a 128-bit checksum of the FULL content, computed at memory bandwidth by a
+// few host threads; an (N, G) OUTPUT is kept on the device under the same checksum, computed there by a reduction kernel, so
+// that handing it back costs a checksum instead of an upload.  A hit replaces a PCIe transfer (50 GB/s page-locked, ~10-25 GB/s
+// pageable) by a read of host memory.  Never by pointer, never by a sample of the content.  PDQ_RESIDENCY=0 switches it off.
+static const size_t kResMinBytes = 1u << 20;
+static const int kHashSlots = 8;
+
+static inline uint64_t hash_a(uint64_t w, uint64_t i) {
+    uint64_t t = (w + (i + 1) * 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+    return t ^ (t >> 31);
+}
+static inline uint64_t hash_b(uint64_t w, uint64_t i) {
+    uint64_t u = (w ^ ((i + 1) * 0xD6E8FEB86659FD93ull)) * 0x94D049BB133111EBull;
+    return u ^ (u >> 29);
+}
+
+// sum over the 64-bit words of the buffer of two position-dependent mixes (wrapping): order-free, so host threads and device
+// blocks may reduce in any order and agree bit for bit
+static void host_hash(const void* p, size_t bytes, uint64_t out[2]) {
+    const uint64_t* w = (const uint64_t*)p;
+    const size_t n = bytes / 8;
+    int nt = (int)(bytes >> 20);  // one thread per MB ...
+    if (nt < 1) nt = 1;
+    if (nt > 32) nt = 32;         // ... up to 32: enough to reach the memory bandwidth of a socket
+    uint64_t a = 0, b = 0;
+#pragma omp parallel for num_threads(nt) schedule(static) reduction(+ : a, b)
+    for (long long i = 0; i < (long long)n; ++i) {
+        a += hash_a(w[i], (uint64_t)i);
+        b += hash_b(w[i], (uint64_t)i);
+    }
+    out[0] = a;
+    out[1] = b;
+}
+
+// entry states: 0 = spare allocation, 1 = being filled by the running call (becomes valid when that call succeeds), 2 = valid
+typedef pdq_ctx::ResEntry ResEntry;
+
+static void res_begin(pdq_ctx* c) {
+    ++c->res_call;
+    for (auto* e : c->res)
+        if (e->state == 1) e->state = 0;  // left behind by a call that failed: never addressable
+}
+
+// a cache-owned buffer of `bytes` in state "filling": a spare of that size, else a new allocation (evicting least recently used
+// entries of other calls while the byte budget or the entry limit is exceeded); nullptr when nothing fits
+static ResEntry* res_new_entry(pdq_ctx* c, size_t bytes) {
+    if (bytes > c->res_cap / 2) return nullptr;
+    ResEntry* k = nullptr;
+    for (auto* e : c->res)
+        if (e->state == 0 && e->bytes == bytes) k = e;
+    while (!k && (c->res_bytes + bytes > c->res_cap || c->res.size() >= 16)) {
+        int lru = -1;
+        for (size_t i = 0; i < c->res.size(); ++i) {
+            const ResEntry* e = c->res[i];
+            if (e->call == c->res_call && e->state != 0) continue;  // in use by the running call
+            if (lru < 0 || (e->state == 0 && c->res[lru]->state != 0) ||
+                ((e->state == 0) == (c->res[lru]->state == 0) && e->stamp < c->res[lru]->stamp))
+                lru = (int)i;
+        }
+        if (lru < 0) return nullptr;
+        ResEntry* v = c->res[lru];
+        if (v->bytes == bytes) {  // same size: take the allocation over instead of free + malloc
+            k = v;
+            break;
+        }
+        if (cudaFree(v->dptr) != cudaSuccess) return nullptr;
+        c->res_bytes -= v->bytes;
+        c->res.erase(c->res.begin() + lru);
+        delete v;
+    }
+    if (!k) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        k = new ResEntry();
+        k->dptr = p;
+        k->bytes = bytes;
+        c->res.push_back(k);
+        c->res_bytes += bytes;
+    }
+    k->h[0] = k->h[1] = 0;
+    k->pending = -1;
+    k->state = 1;
+    k->call = c->res_call;
+    k->stamp = ++c->res_clock;
+    return k;
+}
+
+static bool res_on(const pdq_ctx* c, int64_t ld, int G, size_t bytes) { return c->residency && ld == G && bytes >= kResMinBytes && bytes % 8 == 0; }
+
+// Device buffer holding the caller's (N, G) input.  *need_upload = the caller still has to fill it (cache miss, or cache off:
+// then `scratch` names the context buffer used instead).
+static int res_input(pdq_ctx* c, const void* host, int64_t ld, int N, int G, size_t elem, int scratch, void** dptr, bool* need_upload) {
+    const size_t bytes = (size_t)N * G * elem;
+    *need_upload = true;
+    if (res_on(c, ld, G, bytes)) {
+        uint64_t h[2];
+        host_hash(host, bytes, h);
+        for (auto* e : c->res)
+            if (e->state == 2 && e->bytes == bytes && e->h[0] == h[0] && e->h[1] == h[1]) {
+                e->stamp = ++c->res_clock;
+                e->call = c->res_call;
+                *dptr = e->dptr;
+                *need_upload = false;
+                ++c->res_hits;
+                c->res_hit_bytes += (int64_t)bytes;
+                return 0;
+            }
+        if (ResEntry* k = res_new_entry(c, bytes)) {
+            k->h[0] = h[0];
+            k->h[1] = h[1];
+            *dptr = k->dptr;
+            ++c->res_misses;
+            return 0;
+        }
+    }
+    return ensure(c, scratch, bytes, dptr);
+}
+
+// Device buffer for an (N, G) OUTPUT; *slot != nullptr when it is cache-owned (then call res_commit once the kernels are enqueued)
+static int res_output(pdq_ctx* c, size_t bytes, int scratch, void** dptr, ResEntry** slot) {
+    *slot = nullptr;
+    if (c->residency && bytes >= kResMinBytes && bytes % 8 == 0 && c->hash_pending < kHashSlots) {
+        if (ResEntry* k = res_new_entry(c, bytes)) {
+            *dptr = k->dptr;
+            *slot = k;
+            return 0;
+        }
+    }
+    return ensure(c, scratch, bytes, dptr);
+}
+
+// checksum of a finished output on the device (same function as host_hash), delivered to the host with the call's final sync
+static int res_commit(pdq_ctx* c, ResEntry* e) {
+    if (!e) return 0;
+    if (!c->hash_dev) {
+        CU(c, cudaMalloc((void**)&c->hash_dev, 2 * kHashSlots * 8));
+        CU(c, cudaHostAlloc((void**)&c->hash_host, 2 * kHashSlots * 8, cudaHostAllocDefault));
+    }
+    const int q = c->hash_pending++;
+    e->pending = q;
+    CU(c, cudaMemsetAsync(c->hash_dev + 2 * q, 0, 16, c->stream));
+    if (launch_hash(c->stream, c->prop.multiProcessorCount, e->dptr, e->bytes / 8, c->hash_dev + 2 * q) < 0)
+        return fail(c, PDQ_ERR_CUDA, "hash kernel launch failed");
+    ++c->launches;
+    CU(c, cudaMemcpyAsync(c->hash_host + 2 * q, c->hash_dev + 2 * q, 16, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+// the call succeeded and its stream is synchronised: inputs uploaded and outputs written by it become addressable
+static void res_finalize(pdq_ctx* c) {
+    for (auto* e : c->res) {
+        if (e->state != 1 || e->call != c->res_call) continue;
+        if (e->pending >= 0) {
+            e->h[0] = c->hash_host[2 * e->pending];
+            e->h[1] = c->hash_host[2 * e->pending + 1];
+            e->pending = -1;
+        }
+        e->state = 2;
+        for (auto* o : c->res)  // the same content from an earlier call: keep one copy, the other becomes a spare
+            if (o != e && o->state == 2 && o->bytes == e->bytes && o->h[0] == e->h[0] && o->h[1] == e->h[1]) o->state = 0;
+    }
+    c->hash_pending = 0;
+}
+
+extern "C" int pdq_residency_stats(const pdq_ctx* c, int64_t* hits, int64_t* misses, int64_t* hit_bytes, int64_t* resident_bytes) {
+    if (!c) return PDQ_ERR_INVALID;
+    if (hits) *hits = c->res_hits;
+    if (misses) *misses = c->res_misses;
+    if (hit_bytes) *hit_bytes = c->res_hit_bytes;
+    if (resident_bytes) *resident_bytes = (int64_t)c->res_bytes;
+    return PDQ_OK;
+}
+
+extern "C" int pdq_residency_clear(pdq_ctx* c) {
+    CHECK_CTX(c);
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (auto* e : c->res) {
+        if (e->dptr) cudaFree(e->dptr);
+        delete e;
+    }
+    c->res.clear();
+    c->res_bytes = 0;
+    c->hash_pending = 0;
+    return PDQ_OK;
+}
+
 // ---- gene-block pipeline --------------------------------------------------------------------------------------
 // The plugin calls move 32-64 MB each way around a 0.3 ms kernel.  When every large host buffer is page-locked the call
 // is split into gene blocks on two streams: the column block k+1 is uploaded while block k computes and block k-1 is
@@ -727,7 +948,9 @@ struct Pipe {
     int gb(int b) const { return (b == nb - 1) ? G - b * Gb : Gb; }
     cudaStream_t st(int b) const { return on ? c->pstream[b & 1] : c->stream; }
     LaunchCfg cfg_for(int b, int N) const {
-        LaunchCfg lc = cfg(c, gb(b), N);
+        // lane-group width from the WHOLE call's gene count, not the block's: per-gene results then do not depend on whether (and
+        // how) a call was split -- only the width of the lane group fixes the order of a gene's floating-point sums
+        LaunchCfg lc = cfg(c, G, N);
         lc.stream = st(b);
         lc.tickets = c->tickets + (on ? 4 * (1 + (b & 1)) : 0);
         return lc;
@@ -737,7 +960,7 @@ struct Pipe {
 static int pipe_begin(pdq_ctx* c, int G, std::initializer_list<const void*> big_host, Pipe* p) {
     const int want = c->pipeline > kPipeMaxBlocks ? kPipeMaxBlocks : c->pipeline;
     bool on = want > 1 && c->staging && G >= 4096;
-    for (const void* h : big_host) on = on && is_pinned(h);
+    for (const void* h : big_host) on = on && (h == nullptr || is_pinned(h));  // nullptr: not transferred (resident already)
     p->c = c;
     p->on = on;
     p->G = G;
@@ -762,6 +985,17 @@ static int pipe_join(pdq_ctx* c, const Pipe& p) {
         }
     }
     return 0;
+}
+
+// end of a host-buffer call: join the block streams, checksum the cache-owned outputs, synchronise, publish the cache entries
+static int call_end(pdq_ctx* c, const Pipe* p, std::initializer_list<pdq_ctx::ResEntry*> out_slots) {
+    if (p)
+        if (int e = pipe_join(c, *p)) return e;
+    for (pdq_ctx::ResEntry* s : out_slots)
+        if (int e = res_commit(c, s)) return e;
+    CU(c, cudaStreamSynchronize(c->stream));
+    res_finalize(c);
+    return PDQ_OK;
 }
 
 static int pipe_end(pdq_ctx* c, const Pipe& p) {
@@ -800,18 +1034,22 @@ extern "C" int pdq_lin_reg_mu(pdq_ctx* c, const int64_t* counts, int64_t ld, int
     if (int e = cached_design(c, X, sf, N, p, &d)) return e;
     void *dc, *dm;
     const size_t ng = (size_t)N * G;
-    if (int e = ensure(c, kBufCounts, ng * 8, &dc)) return e;
-    if (int e = ensure(c, kBufA, ng * 8, &dm)) return e;
+    res_begin(c);
+    bool up_c;
+    pdq_ctx::ResEntry* slot_m;
+    if (int e = res_input(c, counts, ld, N, G, 8, kBufCounts, &dc, &up_c)) return e;
+    if (int e = res_output(c, ng * 8, kBufA, &dm, &slot_m)) return e;
     Pipe pp;
-    if (int e = pipe_begin(c, G, {counts, mu_out}, &pp)) return e;
+    if (int e = pipe_begin(c, G, {up_c ? (const void*)counts : nullptr, mu_out}, &pp)) return e;
     for (int b = 0; b < pp.nb; ++b) {
-        if (int e = cols_h2d(c, pp, b, dc, G, counts, ld, N, 8)) return e;
+        if (up_c)
+            if (int e = cols_h2d(c, pp, b, dc, G, counts, ld, N, 8)) return e;
         if (int e = done(c, launch_lin_reg_mu(pp.cfg_for(b, N), d->d, (const int64_t*)dc + pp.g0(b), G, pp.gb(b), min_mu,
                                               (double*)dm + pp.g0(b), G), "lin_reg_mu"))
             return e;
         if (int e = cols_d2h(c, pp, b, mu_out, G, dm, G, N, 8)) return e;
     }
-    return pipe_end(c, pp);
+    return call_end(c, &pp, {slot_m});
 }
 
 extern "C" int pdq_irls(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, const double* sf, const double* X, int p,
@@ -824,9 +1062,12 @@ extern "C" int pdq_irls(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, in
     if (int e = cached_design(c, X, sf, N, p, &d)) return e;
     const size_t ng = (size_t)N * G;
     void *dc, *dmu, *dhat, *ddisp, *dbeta, *dconv, *dmisc;
-    if (int e = ensure(c, kBufCounts, ng * 8, &dc)) return e;
-    if (int e = ensure(c, kBufA, ng * 8, &dmu)) return e;
-    if (int e = ensure(c, kBufB, ng * 8, &dhat)) return e;
+    res_begin(c);
+    bool up_c;
+    pdq_ctx::ResEntry *slot_mu, *slot_hat;
+    if (int e = res_input(c, counts, ld, N, G, 8, kBufCounts, &dc, &up_c)) return e;
+    if (int e = res_output(c, ng * 8, kBufA, &dmu, &slot_mu)) return e;
+    if (int e = res_output(c, ng * 8, kBufB, &dhat, &slot_hat)) return e;
     if (int e = ensure(c, kBufC, (size_t)G * 8, &ddisp)) return e;
     if (int e = ensure(c, kBufD, (size_t)G * p * 8, &dbeta)) return e;
     if (int e = ensure(c, kBufE, (size_t)G * 8, &dconv)) return e;
@@ -836,11 +1077,12 @@ extern "C" int pdq_irls(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, in
     const IrlsHost h{min_mu, beta_tol, min_beta, max_beta, maxiter};
     Pipe pp;
     if (int e = vec_h2d(c, ddisp, disp, (size_t)G * 8)) return e;
-    if (int e = pipe_begin(c, G, {counts, mu_out, hat_out}, &pp)) return e;
+    if (int e = pipe_begin(c, G, {up_c ? (const void*)counts : nullptr, mu_out, hat_out}, &pp)) return e;
     int nfb[kPipeMaxBlocks] = {};
     for (int b = 0; b < pp.nb; ++b) {
         const int g0 = pp.g0(b), gb = pp.gb(b);
-        if (int e = cols_h2d(c, pp, b, dc, G, counts, ld, N, 8)) return e;
+        if (up_c)
+            if (int e = cols_h2d(c, pp, b, dc, G, counts, ld, N, 8)) return e;
         if (int e = done(c, launch_irls(pp.cfg_for(b, N), d->d, (const int64_t*)dc + g0, G, gb, (const double*)ddisp + g0, h,
                                         (double*)dbeta + (size_t)g0 * p, (double*)dmu + g0, (double*)dhat + g0, G, (double*)dconv + g0,
                                         (int*)status + g0, (int*)dmisc + b), "irls"))
@@ -852,7 +1094,7 @@ extern "C" int pdq_irls(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, in
     if (int e = vec_d2h(c, beta_out, dbeta, (size_t)G * p * 8)) return e;
     if (int e = vec_d2h(c, conv_out, dconv, (size_t)G * 8)) return e;
     if (int e = vec_d2h(c, nfb, dmisc, (size_t)pp.nb * sizeof(int))) return e;
-    CU(c, cudaStreamSynchronize(c->stream));
+    if (int e = call_end(c, nullptr, {slot_mu, slot_hat})) return e;
     if (n_fallback) {
         *n_fallback = 0;
         for (int b = 0; b < pp.nb; ++b) *n_fallback += nfb[b];
@@ -870,8 +1112,10 @@ extern "C" int pdq_alpha_mle(pdq_ctx* c, const int64_t* counts, int64_t ld, int 
     if (int e = cached_design(c, X, nullptr, N, p, &d)) return e;
     const size_t ng = (size_t)N * G;
     void *dc, *dmu, *dah, *dal, *dconv;
-    if (int e = ensure(c, kBufCounts, ng * 8, &dc)) return e;
-    if (int e = ensure(c, kBufA, ng * 8, &dmu)) return e;
+    res_begin(c);
+    bool up_c, up_m;
+    if (int e = res_input(c, counts, ld, N, G, 8, kBufCounts, &dc, &up_c)) return e;
+    if (int e = res_input(c, mu, ld_mu, N, G, 8, kBufA, &dmu, &up_m)) return e;
     if (int e = ensure(c, kBufC, (size_t)G * 8, &dah)) return e;
     if (int e = ensure(c, kBufD, (size_t)G * 8, &dal)) return e;
     if (int e = ensure(c, kBufE, (size_t)G * 8, &dconv)) return e;
@@ -880,11 +1124,13 @@ extern "C" int pdq_alpha_mle(pdq_ctx* c, const int64_t* counts, int64_t ld, int 
     if (int e = ensure(c, kBufStatus, (size_t)G * sizeof(int), &status)) return e;
     Pipe pp;
     if (int e = vec_h2d(c, dah, alpha_hat, (size_t)G * 8)) return e;
-    if (int e = pipe_begin(c, G, {counts, mu}, &pp)) return e;
+    if (int e = pipe_begin(c, G, {up_c ? (const void*)counts : nullptr, up_m ? (const void*)mu : nullptr}, &pp)) return e;
     for (int b = 0; b < pp.nb; ++b) {
         const int g0 = pp.g0(b), gb = pp.gb(b);
-        if (int e = cols_h2d(c, pp, b, dc, G, counts, ld, N, 8)) return e;
-        if (int e = cols_h2d(c, pp, b, dmu, G, mu, ld_mu, N, 8)) return e;
+        if (up_c)
+            if (int e = cols_h2d(c, pp, b, dc, G, counts, ld, N, 8)) return e;
+        if (up_m)
+            if (int e = cols_h2d(c, pp, b, dmu, G, mu, ld_mu, N, 8)) return e;
         if (int e = done(c, launch_alpha_mle(pp.cfg_for(b, N), d->d, (const int64_t*)dc + g0, G, gb, (const double*)dmu + g0, G,
                                              (const double*)dah + g0, min_disp, max_disp, prior_disp_var, nullptr, cr_reg, prior_reg,
                                              (double*)dal + g0, (double*)dconv + g0, (int*)status + g0), "alpha_mle"))
@@ -893,8 +1139,7 @@ extern "C" int pdq_alpha_mle(pdq_ctx* c, const int64_t* counts, int64_t ld, int 
     if (int e = pipe_join(c, pp)) return e;
     if (int e = vec_d2h(c, alpha_out, dal, (size_t)G * 8)) return e;
     if (int e = vec_d2h(c, conv_out, dconv, (size_t)G * 8)) return e;
-    CU(c, cudaStreamSynchronize(c->stream));
-    return PDQ_OK;
+    return call_end(c, nullptr, {});
 }
 
 extern "C" int pdq_wald_test(pdq_ctx* c, const double* X, int N, int p, const double* disp, const double* lfc, const double* mu,
@@ -907,7 +1152,9 @@ extern "C" int pdq_wald_test(pdq_ctx* c, const double* X, int N, int p, const do
     if (int e = cached_design(c, X, nullptr, N, p, &d)) return e;
     const size_t ng = (size_t)N * G;
     void *dmu, *ddisp, *dlfc, *dp, *ds, *dse;
-    if (int e = ensure(c, kBufA, ng * 8, &dmu)) return e;
+    res_begin(c);
+    bool up_m;
+    if (int e = res_input(c, mu, ld_mu, N, G, 8, kBufA, &dmu, &up_m)) return e;
     if (int e = ensure(c, kBufC, (size_t)G * 8, &ddisp)) return e;
     if (int e = ensure(c, kBufD, (size_t)G * p * 8, &dlfc)) return e;
     if (int e = ensure(c, kBufE, (size_t)G * 8, &dp)) return e;
@@ -917,10 +1164,11 @@ extern "C" int pdq_wald_test(pdq_ctx* c, const double* X, int N, int p, const do
     Pipe pp;
     if (int e = vec_h2d(c, ddisp, disp, (size_t)G * 8)) return e;
     if (int e = vec_h2d(c, dlfc, lfc, (size_t)G * p * 8)) return e;
-    if (int e = pipe_begin(c, G, {mu}, &pp)) return e;
+    if (int e = pipe_begin(c, G, {up_m ? (const void*)mu : nullptr}, &pp)) return e;
     for (int b = 0; b < pp.nb; ++b) {
         const int g0 = pp.g0(b), gb = pp.gb(b);
-        if (int e = cols_h2d(c, pp, b, dmu, G, mu, ld_mu, N, 8)) return e;
+        if (up_m)
+            if (int e = cols_h2d(c, pp, b, dmu, G, mu, ld_mu, N, 8)) return e;
         if (int e = done(c, launch_wald(pp.cfg_for(b, N), d->d, (const double*)ddisp + g0, (const double*)dlfc + (size_t)g0 * p,
                                         (const double*)dmu + g0, G, gb, ridge, contrast, lfc_null, alt, (double*)dp + g0, (double*)ds + g0,
                                         (double*)dse + g0), "wald_test"))
@@ -930,8 +1178,7 @@ extern "C" int pdq_wald_test(pdq_ctx* c, const double* X, int N, int p, const do
     if (int e = vec_d2h(c, pv_out, dp, (size_t)G * 8)) return e;
     if (int e = vec_d2h(c, stat_out, ds, (size_t)G * 8)) return e;
     if (int e = vec_d2h(c, se_out, dse, (size_t)G * 8)) return e;
-    CU(c, cudaStreamSynchronize(c->stream));
-    return PDQ_OK;
+    return call_end(c, nullptr, {});
 }
 
 extern "C" int pdq_fit_rough_dispersions(pdq_ctx* c, const double* normed, int64_t ld, int N, int G, const double* X, int p,
@@ -943,13 +1190,15 @@ extern "C" int pdq_fit_rough_dispersions(pdq_ctx* c, const double* normed, int64
     if (int e = cached_design(c, X, nullptr, N, p, &d)) return e;
     const size_t ng = (size_t)N * G;
     void *dn, *da;
-    if (int e = ensure(c, kBufA, ng * 8, &dn)) return e;
+    res_begin(c);
+    bool up_n;
+    if (int e = res_input(c, normed, ld, N, G, 8, kBufA, &dn, &up_n)) return e;
     if (int e = ensure(c, kBufC, (size_t)G * 8, &da)) return e;
-    if (int e = h2d_2d(c, dn, normed, ld, N, G, 8)) return e;
+    if (up_n)
+        if (int e = h2d_2d(c, dn, normed, ld, N, G, 8)) return e;
     if (int e = done(c, launch_rough(cfg(c, G, N), d->d, (const double*)dn, G, G, (double*)da), "fit_rough_dispersions")) return e;
     CU(c, cudaMemcpyAsync(alpha_out, da, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    return PDQ_OK;
+    return call_end(c, nullptr, {});
 }
 
 extern "C" int pdq_fit_moments_dispersions(pdq_ctx* c, const double* normed, int64_t ld, int N, int G, const double* sf,
@@ -963,15 +1212,17 @@ extern "C" int pdq_fit_moments_dispersions(pdq_ctx* c, const double* normed, int
     if (int e = cached_design(c, ones.data(), sf, N, 1, &d)) return e;
     const size_t ng = (size_t)N * G;
     void *dn, *da, *dz;
-    if (int e = ensure(c, kBufA, ng * 8, &dn)) return e;
+    res_begin(c);
+    bool up_n;
+    if (int e = res_input(c, normed, ld, N, G, 8, kBufA, &dn, &up_n)) return e;
     if (int e = ensure(c, kBufC, (size_t)G * 8, &da)) return e;
     if (int e = ensure(c, kBufE, (size_t)G * 8, &dz)) return e;
-    if (int e = h2d_2d(c, dn, normed, ld, N, G, 8)) return e;
+    if (up_n)
+        if (int e = h2d_2d(c, dn, normed, ld, N, G, 8)) return e;
     if (int e = done(c, launch_moments(cfg(c, G, N), d->d, (const double*)dn, G, G, (double*)da, (double*)dz), "fit_moments_dispersions")) return e;
     CU(c, cudaMemcpyAsync(alpha_out, da, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(all_zero_out, dz, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    return PDQ_OK;
+    return call_end(c, nullptr, {});
 }
 
 extern "C" int pdq_calculate_cooks(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, const double* sf, const double* X, int p,
@@ -984,17 +1235,22 @@ extern "C" int pdq_calculate_cooks(pdq_ctx* c, const int64_t* counts, int64_t ld
     if (int e = cached_design(c, X, sf, N, p, &d)) return e;
     const size_t ng = (size_t)N * G;
     void *dc, *dmu, *dhat, *dck = nullptr, *dd, *dout, *drep;
-    if (int e = ensure(c, kBufCounts, ng * 8, &dc)) return e;
-    if (int e = ensure(c, kBufA, ng * 8, &dmu)) return e;
-    if (int e = ensure(c, kBufB, ng * 8, &dhat)) return e;
+    res_begin(c);
+    bool up_c, up_m, up_h;
+    if (int e = res_input(c, counts, ld, N, G, 8, kBufCounts, &dc, &up_c)) return e;
+    if (int e = res_input(c, mu, ld2, N, G, 8, kBufA, &dmu, &up_m)) return e;
+    if (int e = res_input(c, hat, ld2, N, G, 8, kBufB, &dhat, &up_h)) return e;
     if (cooks_out)
         if (int e = ensure(c, kBufRes, ng * 8, &dck)) return e;
     if (int e = ensure(c, kBufC, (size_t)G * 8, &dd)) return e;
     if (int e = ensure(c, kBufE, (size_t)G * 8, &dout)) return e;
     if (int e = ensure(c, kBufF, (size_t)G * 8, &drep)) return e;
-    if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
-    if (int e = h2d_2d(c, dmu, mu, ld2, N, G, 8)) return e;
-    if (int e = h2d_2d(c, dhat, hat, ld2, N, G, 8)) return e;
+    if (up_c)
+        if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
+    if (up_m)
+        if (int e = h2d_2d(c, dmu, mu, ld2, N, G, 8)) return e;
+    if (up_h)
+        if (int e = h2d_2d(c, dhat, hat, ld2, N, G, 8)) return e;
     if (int e = pdq_cooks_dev(c, d, (const int64_t*)dc, G, G, (const double*)dmu, (const double*)dhat, G, cutoff, (double*)dck, G, (double*)dd,
                               (double*)dout, (double*)drep))
         return e;
@@ -1003,8 +1259,7 @@ extern "C" int pdq_calculate_cooks(pdq_ctx* c, const int64_t* counts, int64_t ld
     CU(c, cudaMemcpyAsync(robust_disp_out, dd, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(outlier_out, dout, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(replaced_out, drep, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    return PDQ_OK;
+    return call_end(c, nullptr, {});
 }
 
 extern "C" int pdq_lfc_shrink_nbinom_glm(pdq_ctx* c, const double* X, const int64_t* counts, int64_t ld, int N, int G, int p, const double* size,
@@ -1016,13 +1271,16 @@ extern "C" int pdq_lfc_shrink_nbinom_glm(pdq_ctx* c, const double* X, const int6
     pdq_design* d;  // the kernel reads the offsets from the log-size-factor row of the design pack
     if (int e = cached_design(c, X, offset, N, p, &d, true)) return e;
     void *dc, *dsize, *dbeta, *dih, *dconv, *status;
-    if (int e = ensure(c, kBufCounts, (size_t)N * G * 8, &dc)) return e;
+    res_begin(c);
+    bool up_c;
+    if (int e = res_input(c, counts, ld, N, G, 8, kBufCounts, &dc, &up_c)) return e;
     if (int e = ensure(c, kBufC, (size_t)G * 8, &dsize)) return e;
     if (int e = ensure(c, kBufD, (size_t)G * p * 8, &dbeta)) return e;
     if (int e = ensure(c, kBufA, (size_t)G * p * p * 8, &dih)) return e;
     if (int e = ensure(c, kBufE, (size_t)G * 8, &dconv)) return e;
     if (int e = ensure(c, kBufStatus, (size_t)G * sizeof(int), &status)) return e;
-    if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
+    if (up_c)
+        if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
     CU(c, cudaMemcpyAsync(dsize, size, (size_t)G * 8, cudaMemcpyHostToDevice, c->stream));
     if (int e = pdq_lfc_shrink_dev(c, d, (const int64_t*)dc, G, G, (const double*)dsize, prior_no_shrink_scale, prior_scale, shrink_index,
                                    (double*)dbeta, (double*)dih, (double*)dconv, (int*)status))
@@ -1035,7 +1293,7 @@ extern "C" int pdq_lfc_shrink_nbinom_glm(pdq_ctx* c, const double* X, const int6
         st.resize((size_t)G);
         CU(c, cudaMemcpyAsync(st.data(), status, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     }
-    CU(c, cudaStreamSynchronize(c->stream));
+    if (int e = call_end(c, nullptr, {})) return e;
     if (n_grid) {
         *n_grid = 0;
         for (int v : st) *n_grid += (v != 0);
@@ -1047,13 +1305,15 @@ extern "C" int pdq_size_factors(pdq_ctx* c, const int64_t* counts, int64_t ld, i
     CHECK_CTX(c);
     if (!counts || !sf_out || N <= 0 || G <= 0 || ld < G) return fail(c, PDQ_ERR_INVALID, "pdq_size_factors: bad arguments");
     void *dc, *dsf;
-    if (int e = ensure(c, kBufCounts, (size_t)N * G * 8, &dc)) return e;
+    res_begin(c);
+    bool up_c;
+    if (int e = res_input(c, counts, ld, N, G, 8, kBufCounts, &dc, &up_c)) return e;
     if (int e = ensure(c, kBufE, (size_t)N * 8, &dsf)) return e;
-    if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
+    if (up_c)
+        if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
     if (int e = pdq_size_factors_dev(c, (const int64_t*)dc, G, N, G, (double*)dsf, nullptr)) return e;
     CU(c, cudaMemcpyAsync(sf_out, dsf, (size_t)N * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    return PDQ_OK;
+    return call_end(c, nullptr, {});
 }
 
 extern "C" int pdq_dispersion_trend_gamma_glm(pdq_ctx* c, const double* cov, const double* targets, size_t n, double* coeffs_out,

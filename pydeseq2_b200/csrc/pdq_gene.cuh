@@ -455,12 +455,19 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
     for (int j = 0; j < P; ++j) v[j] = 0.0;
     double lgsum = 0.0, logmean = 0.0;
     const int trips = (d.N + grp.T - 1) / grp.T;  // uniform across the warp: the loop body votes
-    for (int it = 0, n = grp.si; it < trips; ++it, n += grp.T) {
+    // this pass is the gene tile's first touch (DRAM / L2 latency): the counts of the next two trips are already requested
+    // while a trip computes (the capture of round 2 showed 9.5 % of the kernel's stall samples on this one load)
+    const int64_t ystep = (int64_t)grp.T * ld;
+    const int64_t* yp = y + (int64_t)grp.si * ld;
+    long long c_cur = (grp.si < d.N) ? yp[0] : 0, c_nxt = (grp.si + grp.T < d.N) ? yp[ystep] : 0;
+    for (int it = 0, n = grp.si; it < trips; ++it, n += grp.T, yp += ystep) {
         const bool in = n < d.N;
         const int nn = in ? n : 0;
         double x[P];
         load_x<P>(d, nn, x);
-        const long long yi = y[nn * ld];
+        const long long yi = c_cur;
+        c_cur = c_nxt;
+        c_nxt = (n + 2 * grp.T < d.N) ? yp[2 * ystep] : 0;
         const double yv = (double)yi;
         const double q = fast_div(yv, d.sf[nn * d.RS]);
         double t;
@@ -504,13 +511,22 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
     const double C = Nd * r * log(alpha) + Nd * lgamma_pos(r) + lgsum;
 
     // ---- IRLS loop (utils.py:359-421) ---------------------------------------------------------
+    // ONE call site of the sweep (the kernel's instruction footprint decides its instruction-cache behaviour: 15 % of the stall
+    // samples of the p = 3 capture were instruction fetches): the trip of the start value skips the deviance bookkeeping.
     Sym<P> A;
     double b[P], S;
-    irls_sweep<P>(grp, d, y, ld, beta, alpha, r, prm.min_mu, log_min_mu, A, b, S, prm.few_rows != 0);
     double dev = 1000.0, ratio = 1.0;
     int it = 0, status = kIrlsOk;
-    bool active = true;
+    bool active = true, first = true;
     for (;;) {
+        // frozen groups recompute the same sums (keeps the warp's shuffles uniform)
+        irls_sweep<P>(grp, d, y, ld, beta, alpha, r, prm.min_mu, log_min_mu, A, b, S, prm.few_rows != 0);
+        if (active && !first) {
+            const double old = dev;
+            dev = -2.0 * (C + S);
+            ratio = fabs(dev - old) / (fabs(dev) + 0.1);
+        }
+        first = false;
         if (active && !(ratio > prm.beta_tol)) active = false;  // `while dev_ratio > beta_tol` (NaN exits)
         if (!grp.any(active)) break;
         Sym<P> L = A;
@@ -533,13 +549,6 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
 #pragma unroll
                 for (int j = 0; j < P; ++j) beta[j] = bh[j];
             }
-        }
-        // frozen groups recompute the same sums (keeps the warp's shuffles uniform)
-        irls_sweep<P>(grp, d, y, ld, beta, alpha, r, prm.min_mu, log_min_mu, A, b, S, prm.few_rows != 0);
-        if (active) {
-            const double old = dev;
-            dev = -2.0 * (C + S);
-            ratio = fabs(dev - old) / (fabs(dev) + 0.1);
         }
     }
 
@@ -947,18 +956,21 @@ PDQ_HD bool alpha_sweep_t(const Group& grp, const DesignS& d, bool cr_reg, const
     const int trips = (d.N + 2 * T - 1) / (2 * T);
     int n = grp.si;
 #if PDQ_PREFETCH
-    // register double buffer: the next trip's counts and means are requested before this trip's arithmetic (see irls_sweep_t)
-    bool v0 = n < d.N, v1 = n + T < d.N;
-    long long yi0 = v0 ? yp[0] : 0, yi1 = v1 ? yp[ystep] : 0;
-    double m0 = v0 ? mp[0] : 1.0, m1 = v1 ? mp[mstep] : 1.0;
+    // register triple buffer: the counts and means of the NEXT TWO trips are in flight while this trip computes -- one trip of
+    // cover (~150 instructions) hides an L2 hit, not a DRAM access (first evaluation of a gene; 9 % long-scoreboard samples at
+    // 60 000 x 500 with one trip of cover)
+    bool v0 = n < d.N, v1 = n + T < d.N, w0 = n + 2 * T < d.N, w1 = n + 3 * T < d.N;
+    long long yi0 = v0 ? yp[0] : 0, yi1 = v1 ? yp[ystep] : 0, ny0 = w0 ? yp[2 * ystep] : 0, ny1 = w1 ? yp[3 * ystep] : 0;
+    double m0 = v0 ? mp[0] : 1.0, m1 = v1 ? mp[mstep] : 1.0, nm0 = w0 ? mp[2 * mstep] : 1.0, nm1 = w1 ? mp[3 * mstep] : 1.0;
     for (int it = 0; it < trips; ++it, n += 2 * T, yp += 2 * ystep, mp += 2 * mstep, xp += 2 * T * RS) {
-        const bool w0 = n + 2 * T < d.N, w1 = n + 3 * T < d.N;
-        const long long ny0 = w0 ? yp[2 * ystep] : 0, ny1 = w1 ? yp[3 * ystep] : 0;
-        const double nm0 = w0 ? mp[2 * mstep] : 1.0, nm1 = w1 ? mp[3 * mstep] : 1.0;
+        const bool u0 = n + 4 * T < d.N, u1 = n + 5 * T < d.N;
+        const long long fy0 = u0 ? yp[4 * ystep] : 0, fy1 = u1 ? yp[5 * ystep] : 0;
+        const double fm0 = u0 ? mp[4 * mstep] : 1.0, fm1 = u1 ? mp[5 * mstep] : 1.0;
         // one call site: every lane of the warp reaches the vote inside alpha_pair together
         alpha_pair<P, NB, CURV>(grp, v0 ? xp : d.X, v1 ? xp + T * RS : d.X, d.mtab, yi0, yi1, m0, m1, v0, v1, r, cr_reg, psi_tab,
                                 Sg, A, B, odd, S2);
         v0 = w0; v1 = w1; yi0 = ny0; yi1 = ny1; m0 = nm0; m1 = nm1;
+        w0 = u0; w1 = u1; ny0 = fy0; ny1 = fy1; nm0 = fm0; nm1 = fm1;
     }
 #else
     for (int it = 0; it < trips; ++it, n += 2 * T, yp += 2 * ystep, mp += 2 * mstep, xp += 2 * T * RS) {

@@ -132,22 +132,27 @@ __device__ __forceinline__ void map_lanes(int lgT, int G, Group& grp, int& gene,
 // Persistent scheduling for the two heavy kernels: the grid holds as many blocks as fit on the machine and every WARP
 // draws gene tiles (32/T adjacent genes) from a global ticket counter until the tiles run out.  Genes differ in
 // iteration count, so a static assignment leaves SMs idle at the tail (20 % of the cycles in the first profile).
-__device__ __forceinline__ bool next_tile(int* ticket, int lgT, int G, Group& grp, int& gene, bool& valid) {
+// The ticket of the NEXT tile is drawn before the current tile is worked on (`ahead`), so the atomic's round trip to L2 is hidden.
+__device__ __forceinline__ int draw_ticket(int* ticket) {
+    int t = 0;
+    if ((threadIdx.x & 31) == 0) t = atomicAdd(ticket, 1);
+    return t;  // valid in lane 0; broadcast when consumed
+}
+
+__device__ __forceinline__ bool next_tile(int* ticket, int lgT, int G, Group& grp, int& gene, bool& valid, int& ahead) {
     const int lane = threadIdx.x & 31;
     grp.T = 1 << lgT;
     grp.gpw = 32 >> lgT;
     grp.si = lane >> (5 - lgT);
-    int tile = 0;
-    if (lane == 0) tile = atomicAdd(ticket, 1);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
+    const int tile = __shfl_sync(0xffffffffu, ahead, 0);
     const int ntiles = (G + grp.gpw - 1) >> (5 - lgT);
     if (tile >= ntiles) return false;
+    ahead = draw_ticket(ticket);
     const int gidx = tile * grp.gpw + (lane & (grp.gpw - 1));
     valid = gidx < G;
     gene = valid ? gidx : (G - 1);
     return true;
 }
-
 
 // ---- kernels --------------------------------------------------------------------------------------
 template <int P>
@@ -207,7 +212,8 @@ __global__ void __launch_bounds__(kBlock, PDQ_IRLS_MINB) k_irls(const __grid_con
     __syncthreads();
     const int gpw = 32 >> a.lgT;
     double* lg_tab = logfact + kPsiK + (size_t)((threadIdx.x >> 5) * gpw + ((threadIdx.x & 31) & (gpw - 1))) * kPsiK;
-    while (next_tile(a.ticket, a.lgT, a.G, grp, g, valid)) {
+    int ahead = draw_ticket(a.ticket);
+    while (next_tile(a.ticket, a.lgT, a.G, grp, g, valid, ahead)) {
         int st = 0;
         irls_gene<P>(grp, d, a.pinv, a.prm, a.counts + g, a.ld, a.disp[g], a.beta + (int64_t)g * P, a.mu + g, a.hat + g,
                      a.ld_out, a.conv + g, &st, valid, lg_tab, logfact, a.with_wald ? &a.wald : nullptr, a.wald_p + g,
@@ -276,7 +282,8 @@ __global__ void __launch_bounds__(kBlock, PDQ_ALPHA_MINB) k_alpha_mle(const __gr
     // per gene of the warp's tile)
     double* psi = reinterpret_cast<double*>(smem + scratch_off(a.dv, true)) +
                   (size_t)((threadIdx.x >> 5) * gpw + ((threadIdx.x & 31) & (gpw - 1))) * (2 * kPsiK);
-    while (next_tile(a.ticket, a.lgT, a.G, grp, g, valid)) {
+    int ahead = draw_ticket(a.ticket);
+    while (next_tile(a.ticket, a.lgT, a.G, grp, g, valid, ahead)) {
         alpha_gene<P>(grp, d, prm, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha_hat[g], a.alpha + g, a.conv + g,
                       a.status + g, valid, psi);
         if (valid && grp.si == 0) {
@@ -809,6 +816,28 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// ---- content checksum of a device buffer: the device half of the residency cache of pdq_api.cu (host_hash there computes the
+// same two wrapping sums with host threads).  HBM-bound: 32 MB in ~10 us.
+__global__ void __launch_bounds__(256) k_hash(const uint64_t* __restrict__ w, size_t n, unsigned long long* out) {
+    unsigned long long a = 0, b = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t v = w[i];
+        uint64_t t = (v + (i + 1) * 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+        a += t ^ (t >> 31);
+        uint64_t u = (v ^ ((i + 1) * 0xD6E8FEB86659FD93ull)) * 0x94D049BB133111EBull;
+        b += u ^ (u >> 29);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, a);
+        atomicAdd(out + 1, b);
+    }
+}
+
 #define PDQ_DISPATCH_P(p, ...)             \
     switch (p) {                           \
         case 1: { constexpr int P = 1; __VA_ARGS__; } break; \
@@ -1051,6 +1080,12 @@ int launch_lfc_shrink(const LaunchCfg& c, const DesignDev& d, const int64_t* cou
     }
     if (int e = check_launch()) return e;
     return d.p == 2 ? 2 : 1;
+}
+
+int launch_hash(cudaStream_t stream, int sm_count, const void* dptr, size_t words, uint64_t* out2) {
+    k_hash<<<sm_count * 8, 256, 0, stream>>>(reinterpret_cast<const uint64_t*>(dptr), words, reinterpret_cast<unsigned long long*>(out2));
+    if (int e = check_launch()) return e;
+    return 1;
 }
 
 int launch_fp64_peak(const LaunchCfg& c, double* out, int iters, double* flop) {

@@ -132,7 +132,7 @@ def _expand(v, nz, G_all):
 
 def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5, min_disp=1e-8, max_disp=10.0,
              beta_tol=1e-8, fit_type="parametric", lfc_null=0.0, alt_hypothesis=None, timings=None, comm=None,
-             normed_counts=None, normed_means=None, reuse_lfc_mu=True) -> FitResult:
+             normed_counts=None, normed_means=None, reuse_lfc_mu=True, fresh_copies=False) -> FitResult:
     """deseq2() + run_wald_test() hot path through the plugin API with host buffers.
 
     ``comm`` (``sharding.NcclComm`` / ``TorchDistComm``): this process holds one gene shard; the genewise
@@ -143,8 +143,19 @@ def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5,
     them (the orchestrator keeps both from ``fit_size_factors``: ``layers["normed_counts"]``, ``var["_normed_means"]``,
     dds.py:700-708).  ``counts`` must be non-negative (the reference validates that at construction, utils.py:100-133).  ``reuse_lfc_mu``: feed the Wald stage
     with the ``mu`` the LFC fit returned -- ``irls`` returns the UNclamped ``sf * exp(X beta)`` (utils.py:435-438),
-    which is exactly what ``run_wald_test`` recomputes on the host (ds.py:320-324)."""
+    which is exactly what ``run_wald_test`` recomputes on the host (ds.py:320-324).  ``fresh_copies``: hand every plugin call
+    a FRESH pageable copy of its (N, G) arguments, like the orchestrator's fancy-indexed ``self.X[:, self.non_zero_idx]`` /
+    ``self.layers["_mu_hat"][:, self.non_zero_idx]`` (dds.py:752, 759, 779-781, 902-904, 954); the time spent copying is the
+    orchestrator's, it is accumulated under ``timings["orchestrator_copies"]``."""
     T = timings if timings is not None else {}
+
+    def fresh(a):
+        if not fresh_copies:
+            return a
+        t0 = time.perf_counter()
+        b = np.array(a)
+        T["orchestrator_copies"] = T.get("orchestrator_copies", 0.0) + time.perf_counter() - t0
+        return b
 
     def timed(key, fn, *a, **k):
         t0 = time.perf_counter()
@@ -178,12 +189,12 @@ def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5,
     mde = timed("fit_moments_dispersions", inference.fit_moments_dispersions, nn, sf)
     mom = np.clip(np.minimum(rde, mde), min_disp, max_disp)
     if lin_mu_branch(X):                                 # dds.py:747-765
-        mu_hat = timed("lin_reg_mu", inference.lin_reg_mu, c, sf, X, min_mu)
+        mu_hat = timed("lin_reg_mu", inference.lin_reg_mu, fresh(c), sf, X, min_mu)
         init_conv = np.ones(c.shape[1])
     else:  # the orchestrator drops this call's `converged` flag (dds.py:757-765); kept here for diagnostics
-        _, mu_hat, _, init_conv = timed("irls_init", inference.irls, c, sf, X, mom, min_mu, beta_tol)
+        _, mu_hat, _, init_conv = timed("irls_init", inference.irls, fresh(c), sf, X, mom, min_mu, beta_tol)
     mu_hat = np.ascontiguousarray(mu_hat)                # layers["_mu_hat"][:, non_zero_idx] is a fresh C array
-    gw, gw_conv = timed("alpha_mle_genewise", inference.alpha_mle, c, X, mu_hat, mom, min_disp, max_disp)
+    gw, gw_conv = timed("alpha_mle_genewise", inference.alpha_mle, fresh(c), X, fresh(mu_hat), mom, min_disp, max_disp)
     gw = np.clip(gw, min_disp, max_disp)                 # dds.py:792-794
     # trend + prior are global over ALL genes of ALL shards (dds.py:799-884): with gene shards the two per-gene vectors are
     # all-gathered first (the only exchange on the path)
@@ -204,13 +215,13 @@ def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5,
     if comm is not None:
         local = (trend.coeffs[0] + trend.coeffs[1] / normed_means) if trend.kind == "parametric" else np.full_like(gw, trend.coeffs[0])
         trend = TrendFit(trend.kind, trend.coeffs, local, trend.n_iter)
-    mp, mp_conv = timed("alpha_mle_map", inference.alpha_mle, c, X, mu_hat, trend.fitted, min_disp, max_disp,
+    mp, mp_conv = timed("alpha_mle_map", inference.alpha_mle, fresh(c), X, fresh(mu_hat), trend.fitted, min_disp, max_disp,
                         prior_disp_var=prior_var, cr_reg=True, prior_reg=True)
     mp = np.clip(mp, min_disp, max_disp)
     disp = mp.copy()
     outlier = np.log(gw) > np.log(trend.fitted) + 2 * np.sqrt(sq)   # dds.py:926-932
     disp[outlier] = gw[outlier]
-    lfc, mu_lfc, hat, lfc_conv = timed("irls_lfc", inference.irls, c, sf, X, disp, min_mu, beta_tol)
+    lfc, mu_lfc, hat, lfc_conv = timed("irls_lfc", inference.irls, fresh(c), sf, X, disp, min_mu, beta_tol)
 
     # Wald stage on ALL genes, all-zero genes carry NaN (ds.py:320-347)
     lfc_all = _expand(np.asarray(lfc), nz, G_all)
@@ -224,7 +235,7 @@ def fit_host(counts, X, inference, contrast=None, size_factors=None, min_mu=0.5,
         mu_w = np.exp(X @ lfc_all.T) * sf[:, None]
     T["wald_mu_host"] = T.get("wald_mu_host", 0.0) + time.perf_counter() - t0
     ridge = np.diag(np.repeat(1e-6, p))
-    pv, st, se = timed("wald_test", inference.wald_test, X, disp_all, lfc_all, mu_w, ridge, np.asarray(contrast, float),
+    pv, st, se = timed("wald_test", inference.wald_test, X, disp_all, lfc_all, fresh(mu_w), ridge, np.asarray(contrast, float),
                        LN2 * lfc_null, alt_hypothesis)
     return FitResult(sf, nz, mom, gw, np.asarray(gw_conv), trend, prior_var, sq, mp, np.asarray(mp_conv), disp_all,
                      lfc_all, np.asarray(lfc_conv), np.asarray(pv), np.asarray(st), np.asarray(se), T,

@@ -79,3 +79,51 @@ def test_every_design_width(inf, p, N):
     from oracle import nbglm
 
     ec.check_design_width(inf, nbglm.OracleInference(n_cpus=4), p, N)
+
+
+def test_content_addressed_residency():
+    """Host-buffer entry points key device copies of (N, G) buffers on a checksum of the full content: fresh host copies of the
+    same content skip the upload (also for an OUTPUT handed back: device-side and host-side checksums must agree bit for bit),
+    any change of the content does not, and results never depend on the cache."""
+    import numpy as np
+
+    from pydeseq2_b200.inference import B200Inference
+    from pydeseq2_b200.synth import make_counts
+
+    counts, X, _ = make_counts(64, 4096, "factorial", seed=3)  # 2 MB per (N, G) array: above the 1 MB threshold
+    sf = np.exp(np.random.default_rng(0).normal(0, 0.1, 64))
+    inf = B200Inference(device=0)
+    ctx = inf._ops.ctx
+    ctx.residency_clear()
+    s0 = ctx.residency_stats()
+    mu1 = inf.lin_reg_mu(counts, sf, X, 0.5)                      # counts: miss
+    mu2 = inf.lin_reg_mu(np.array(counts), sf, X, 0.5)            # fresh copy, same content: hit
+    s1 = ctx.residency_stats()
+    assert s1["hits"] - s0["hits"] == 1 and s1["misses"] - s0["misses"] == 1
+    np.testing.assert_array_equal(mu1, mu2)
+    disp = np.full(counts.shape[1], 0.1)
+    a1, c1 = inf.alpha_mle(np.array(counts), X, np.array(mu1), disp, 1e-8, 64.0)  # counts hit; mu_hat: OUTPUT of the call above
+    s2 = ctx.residency_stats()
+    assert s2["hits"] - s1["hits"] == 2, "an output handed back as a fresh copy must be found by its device-side checksum"
+    changed = np.array(counts)
+    changed[17, 123] += 1
+    mu3 = inf.lin_reg_mu(changed, sf, X, 0.5)
+    s3 = ctx.residency_stats()
+    assert s3["hits"] == s2["hits"] and s3["misses"] - s2["misses"] == 1
+    assert not np.array_equal(mu3[:, 123], mu1[:, 123]) and np.array_equal(np.delete(mu3, 123, 1), np.delete(mu1, 123, 1))
+    swapped = np.array(counts)                                     # same multiset of words, other positions: must miss
+    swapped[[0, 1]] = swapped[[1, 0]]
+    inf.lin_reg_mu(swapped, sf, X, 0.5)
+    assert ctx.residency_stats()["hits"] == s3["hits"]
+    off = B200Inference(device=0)
+    off._ops.ctx.check(off._ops.lib.pdq_residency_clear(off._ops.ctx.h))
+    os_env = __import__("os").environ
+    os_env["PDQ_RESIDENCY"] = "0"
+    try:
+        plain = B200Inference(device=0)
+        a2, c2 = plain.alpha_mle(counts, X, mu1, disp, 1e-8, 64.0)
+        assert plain._ops.ctx.residency_stats()["hits"] == 0 and plain._ops.ctx.residency_stats()["misses"] == 0
+    finally:
+        del os_env["PDQ_RESIDENCY"]
+    np.testing.assert_array_equal(a1, a2)
+    np.testing.assert_array_equal(c1, c2)
