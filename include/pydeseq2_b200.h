@@ -35,12 +35,12 @@ typedef enum pdq_status {
     PDQ_OK = 0,
     PDQ_ERR_CUDA = -1,        /* a CUDA runtime call failed */
     PDQ_ERR_INVALID = -2,     /* bad argument (null pointer, N<=0, p<1, ld<G, ...) */
-    PDQ_ERR_UNSUPPORTED = -3, /* p > PDQ_MAX_P, or the design pack exceeds shared memory */
+    PDQ_ERR_UNSUPPORTED = -3, /* p > PDQ_MAX_P */
     PDQ_ERR_NCCL = -4,        /* NCCL missing or a collective failed */
     PDQ_ERR_NO_DEVICE = -5    /* no CUDA device / not an sm_100 part */
 } pdq_status;
 
-#define PDQ_MAX_P 8 /* design columns supported by the register-resident p x p solvers */
+#define PDQ_MAX_P 16 /* design columns supported (p <= 8: register-resident p x p solvers; 9..16: the same code with the small matrices in local memory) */
 
 /* alt_hypothesis codes of Inference.wald_test (utils.py:778-806) */
 #define PDQ_ALT_NONE 0

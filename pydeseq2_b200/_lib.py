@@ -20,7 +20,7 @@ c_dptr = C.c_void_p
 f64p = C.POINTER(C.c_double)
 i64p = C.POINTER(C.c_int64)
 
-PDQ_MAX_P = 8
+PDQ_MAX_P = 16
 ALT_CODES = {None: 0, "greaterAbs": 1, "lessAbs": 2, "greater": 3, "less": 4}
 UNIQUE_ID_BYTES = 128
 

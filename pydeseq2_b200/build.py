@@ -5,13 +5,20 @@ import os
 import shutil
 import subprocess
 import sys
+import time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpydeseq2_b200.so")
-SOURCES = ["pdq_kernels.cu", "pdq_api.cu"]
-HEADERS = ["pdq_math.cuh", "pdq_fast.cuh", "pdq_trend.cuh", "pdq_gene.cuh", "pdq_shrink.cuh", "pdq_internal.h", "pdq_host_linalg.h",
-           os.path.join("..", "..", "include", "pydeseq2_b200.h")]
+# translation units: (source, object tag, extra defines).  pdq_kernels.cu is compiled once for p = 1..8 and once per wide design
+# width p = 9..16 (see the note at its top); the units are independent and compile in parallel.
+WIDE_P = tuple(range(9, 17))
+UNITS = [("pdq_api.cu", "pdq_api", ()), ("pdq_dispatch.cu", "pdq_dispatch", ()), ("pdq_kernels.cu", "pdq_kernels_p1to8", ())] + \
+        [("pdq_kernels.cu", f"pdq_kernels_p{p}", (f"-DPDQ_TU_P={p}", "-Xptxas", "-O1")) for p in WIDE_P]
+# (ptxas -O1 for the wide widths: 12 s instead of 85 s per unit; their kernels keep the small matrices in local memory anyway)
+SOURCES = sorted({u[0] for u in UNITS})
+HEADERS = ["pdq_math.cuh", "pdq_fast.cuh", "pdq_tables.h", "pdq_trend.cuh", "pdq_gene.cuh", "pdq_shrink.cuh", "pdq_internal.h",
+           "pdq_host_linalg.h", os.path.join("..", "..", "include", "pydeseq2_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-fopenmp", "--expt-relaxed-constexpr"]
 
@@ -38,21 +45,37 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
     if not force and not _stale(target, [os.path.join(CSRC, s) for s in SOURCES] + hdrs):
         return target
     os.makedirs(objdir, exist_ok=True)
-    objs = []
-    procs = []
-    for src in SOURCES:
+    objs, todo = [], []
+    for src, name, unit_defs in UNITS:
         s = os.path.join(CSRC, src)
-        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        o = os.path.join(objdir, name + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [_nvcc()] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
-            procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for cmd, pr in procs:
-        out, _ = pr.communicate()
-        if verbose or pr.returncode:
-            sys.stderr.write(out)
-        if pr.returncode:
-            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+            todo.append([_nvcc()] + NVCC_FLAGS + list(defines) + list(unit_defs) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+    jobs = max(1, min(len(todo), int(os.environ.get("PDQ_BUILD_JOBS", os.cpu_count() or 1))))
+    running, failed = [], None
+    while todo or running:
+        while todo and len(running) < jobs:
+            cmd = todo.pop(0)
+            log = open(cmd[-1] + ".log", "w+")
+            running.append((cmd, subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT), log))
+        still = []
+        for cmd, pr, log in running:
+            if pr.poll() is None:
+                still.append((cmd, pr, log))
+                continue
+            log.seek(0)
+            out = log.read()
+            log.close()
+            if verbose or pr.returncode:
+                sys.stderr.write(out)
+            if pr.returncode and failed is None:
+                failed = cmd
+        running = still
+        if running:
+            time.sleep(0.2)
+    if failed is not None:
+        raise RuntimeError("nvcc failed: " + " ".join(failed))
     if force or _stale(target, objs):
         cmd = [_nvcc(), "-shared", "-o", target] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
                                                         "-ldl", "-lrt", "-lpthread", "-lgomp"]

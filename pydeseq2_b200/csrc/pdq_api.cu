@@ -9,14 +9,100 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <functional>
 #include <initializer_list>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pdq_internal.h"
 #include "pdq_host_linalg.h"
 
 using namespace pdq;
+
+// --------------------------------------------------------------------------------------------- host worker threads
+// A few persistent host threads for the two memory-bound host loops of the host-buffer path (content checksums, staging copies of
+// pageable buffers).  Workers SLEEP between jobs (condition variable): with one process per GPU, eight ranks share the host, and
+// spinning runtimes (OpenMP's default wait policy) made eight ranks slower than one.  Threads per process: the host's hardware
+// threads divided by the ranks on it (LOCAL_WORLD_SIZE), at most 32; PDQ_HOST_THREADS overrides.
+class HostPool {
+public:
+    static HostPool& get() {
+        static HostPool p;
+        return p;
+    }
+    int size() const { return n_; }
+    // f(t, nt) for t = 0 .. nt-1, the caller runs t = 0
+    void run(int nt, const std::function<void(int, int)>& f) {
+        if (nt > n_) nt = n_;
+        if (nt <= 1) {
+            f(0, 1);
+            return;
+        }
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            job_ = &f;
+            nt_ = nt;
+            pending_ = nt - 1;
+            ++gen_;
+        }
+        cv_.notify_all();
+        f(0, nt);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    HostPool() {
+        int hw = (int)std::thread::hardware_concurrency();
+        if (hw < 1) hw = 1;
+        int ranks = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
+        n_ = hw / ranks;
+        if (n_ > 32) n_ = 32;
+        if (const char* e = getenv("PDQ_HOST_THREADS")) n_ = atoi(e);
+        if (n_ < 1) n_ = 1;
+        for (int t = 1; t < n_; ++t) th_.emplace_back([this, t] { loop(t); });
+    }
+    ~HostPool() {
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            stop_ = true;
+            ++gen_;
+        }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void loop(int t) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int, int)>* job = nullptr;
+            int nt = 0;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                if (t >= nt_) continue;  // this job uses fewer threads
+                job = job_;
+                nt = nt_;
+            }
+            (*job)(t, nt);
+            std::unique_lock<std::mutex> lk(m_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int, int)>* job_ = nullptr;
+    int n_ = 1, nt_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
 
 // --------------------------------------------------------------------------------------------- NCCL (dlopen)
 // NCCL is resolved at run time so that the library loads on boxes without it and never clashes with
@@ -672,12 +758,11 @@ static bool is_pinned(const void* p) {
 }
 
 static void par_memcpy(void* dst, const void* src, size_t n) {
-    const int nt = n >= (2u << 20) ? 4 : 1;
-#pragma omp parallel for num_threads(nt) schedule(static)
-    for (int t = 0; t < nt; ++t) {
-        const size_t lo = n * t / nt, hi = n * (t + 1) / nt;
+    const int nt = n >= (2u << 20) ? 8 : 1;
+    HostPool::get().run(nt, [&](int t, int k) {
+        const size_t lo = n * t / k, hi = n * (t + 1) / k;
         memcpy((char*)dst + lo, (const char*)src + lo, hi - lo);
-    }
+    });
 }
 
 static int stage_init(pdq_ctx* c) {
@@ -765,17 +850,24 @@ static inline uint64_t hash_b(uint64_t w, uint64_t i) {
 static void host_hash(const void* p, size_t bytes, uint64_t out[2]) {
     const uint64_t* w = (const uint64_t*)p;
     const size_t n = bytes / 8;
-    int nt = (int)(bytes >> 20);  // one thread per MB ...
+    int nt = (int)(bytes >> 20);  // one thread per MB, up to the pool: enough to reach the memory bandwidth of a socket
     if (nt < 1) nt = 1;
-    if (nt > 32) nt = 32;         // ... up to 32: enough to reach the memory bandwidth of a socket
-    uint64_t a = 0, b = 0;
-#pragma omp parallel for num_threads(nt) schedule(static) reduction(+ : a, b)
-    for (long long i = 0; i < (long long)n; ++i) {
-        a += hash_a(w[i], (uint64_t)i);
-        b += hash_b(w[i], (uint64_t)i);
+    uint64_t part[64][2] = {};
+    HostPool::get().run(nt > 32 ? 32 : nt, [&](int t, int k) {
+        const size_t lo = n * t / k, hi = n * (t + 1) / k;
+        uint64_t a = 0, b = 0;
+        for (size_t i = lo; i < hi; ++i) {
+            a += hash_a(w[i], (uint64_t)i);
+            b += hash_b(w[i], (uint64_t)i);
+        }
+        part[t][0] = a;
+        part[t][1] = b;
+    });
+    out[0] = out[1] = 0;
+    for (int t = 0; t < 64; ++t) {
+        out[0] += part[t][0];
+        out[1] += part[t][1];
     }
-    out[0] = a;
-    out[1] = b;
 }
 
 // entry states: 0 = spare allocation, 1 = being filled by the running call (becomes valid when that call succeeds), 2 = valid

@@ -29,6 +29,7 @@ double lane_excl_scan(int si, int T, double v);
 bool lane_any(int si, int T, bool p);
 void lane_sync(int T);
 void lane_argmax(int si, int T, double& best, int& best_n, double& best_use);  // the butterfly of cooks_gene
+int lane_argext(int si, int T, double v, bool want_max);                       // lane holding the group's min / max
 }  // namespace pdq_emu
 #endif
 
@@ -69,6 +70,28 @@ struct Group {
         v = pdq_emu::lane_sum(si, T, v);
 #endif
         return v;
+    }
+    // lane index (si) of the group's smallest (largest) v, ties to the smaller si; identical in every lane of the group
+    PDQ_HD int argext(double v, bool want_max) const {
+#if defined(__CUDA_ARCH__)
+        int who = si;
+        for (int off = 16; off >= gpw; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+            const int ow = __shfl_xor_sync(0xffffffffu, who, off);
+            const bool better = want_max ? (ov > v) : (ov < v);
+            if (better || (ov == v && ow < who)) {
+                v = ov;
+                who = ow;
+            }
+        }
+        return who;
+#elif defined(PDQ_EMU_LANES)
+        return pdq_emu::lane_argext(si, T, v, want_max);
+#else
+        (void)v;
+        (void)want_max;
+        return 0;
+#endif
     }
     PDQ_HD bool any(bool p) const {
 #if defined(__CUDA_ARCH__)
@@ -119,19 +142,19 @@ PDQ_HD void walk4(const Group& grp, int N, const V* p, int64_t step, F&& f) {
 
 template <int P>
 PDQ_HD void load_x(const DesignS& d, int n, double (&x)[P]) {
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) x[j] = d.X[n * design_row_stride(P) + j];
 }
 
 template <int P>
 PDQ_HD void group_sum_sym(const Group& g, Sym<P>& s) {
-#pragma unroll
+PDQ_UNROLL_P
     for (int k = 0; k < P * (P + 1) / 2; ++k) s.a[k] = g.sum(s.a[k]);
 }
 
 template <int P>
 PDQ_HD void group_sum_vec(const Group& g, double (&v)[P]) {
-#pragma unroll
+PDQ_UNROLL_P
     for (int k = 0; k < P; ++k) v[k] = g.sum(v[k]);
 }
 
@@ -144,21 +167,21 @@ template <int P>
 PDQ_HD void linmu_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pinv, const int64_t* y,
                        int64_t ld, double min_mu, double* mu_out, int64_t ld_out, bool valid) {
     double v[P];
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) v[j] = 0.0;
     walk4(grp, d.N, y + (int64_t)grp.si * ld, (int64_t)grp.T * ld, [&](int n, int64_t c) {
         double x[P];
         load_x<P>(d, n, x);
         const double t = (double)c / d.sf[n * d.RS];
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
     });
     group_sum_vec<P>(grp, v);
     double beta[P];
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = 0; i < P; ++i) {
         double s = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) s = fma(pinv.v[i * P + j], v[j], s);
         beta[i] = s;
     }
@@ -167,7 +190,7 @@ PDQ_HD void linmu_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pi
         double x[P];
         load_x<P>(d, n, x);
         double e = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) e = fma(x[j], beta[j], e);
         const double m = d.sf[n * d.RS] * e;
         mu_out[n * ld_out] = (m < min_mu) ? min_mu : m;  // np.maximum (NaN propagates)
@@ -219,9 +242,9 @@ template <int P>
 PDQ_HD void wald_finish(const Group& grp, const Sym<P>& M, const WaldParams<P>& prm, const double* lfc, double* p_out,
                         double* stat_out, double* se_out, bool valid) {
     Sym<P> L = M, H;
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = 0; i < P; ++i)
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j <= i; ++j) L.a[tri(i, j)] += prm.ridge[i * P + j];
     chol<P>(L);
     chol_inverse<P>(L, H);
@@ -229,36 +252,36 @@ PDQ_HD void wald_finish(const Group& grp, const Sym<P>& M, const WaldParams<P>& 
     sym_matvec<P>(H, prm.contrast, Hc);
     sym_matvec<P>(M, Hc, MHc);
     double q = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) q = fma(Hc[j], MHc[j], q);
     const double se = sqrt(q);
     double b[P];
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) b[j] = lfc[j];
     const double t0 = prm.lfc_null;
     double stat, pv;
     // each variant applies the elementwise transform to every coefficient, then dots with the contrast
     auto greater = [&](double t, double& s, double& p) {
         s = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], fmax((b[j] - t) / se, 0.0), s);
         p = norm_sf(s);
     };
     auto less = [&](double t, double& s, double& p) {
         s = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], fmin((b[j] - t) / se, 0.0), s);
         p = norm_sf(fabs(s));
     };
     if (prm.alt == 0) {
         double s = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], b[j] - t0, s);
         stat = s / se;
         pv = 2.0 * norm_sf(fabs(stat));
     } else if (prm.alt == 1) {  // greaterAbs
         double s = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) s = fma(prm.contrast[j], sgn(b[j]) * fmax((fabs(b[j]) - t0) / se, 0.0), s);
         stat = s;
         pv = 2.0 * norm_sf(fabs(s));
@@ -316,11 +339,11 @@ PDQ_HD void irls_sample(const double* xp, const double* mtab, double yv, const d
                         double r, double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P], double& S, bool& odd,
                         double& eta_prev, double& exp_prev) {
     double x[P];
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) x[j] = xp[j];
     const double sfn = xp[P], lsfn = xp[P + 1];                      // sf and log sf close the design row
     double eta = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
     double ex;
     if (MEMO) {
@@ -343,7 +366,7 @@ PDQ_HD void irls_sample(const double* xp, const double* mtab, double yv, const d
     const double W = mu * iden;
     const double Wz = fma(yv - mu, iden, W * lmu_sf);
     sym_rank1<P>(A, W, x);
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) b[j] = fma(Wz, x[j], b[j]);
     S += fma(yv + r, NB ? tlog_nb(r + mu, mtab) : fast_log(r + mu), -yv * lmu);
 }
@@ -352,7 +375,7 @@ template <int P, bool NB, bool MEMO>
 PDQ_HD bool irls_sweep_t(const Group& grp, const DesignS& d, const int64_t* y, int64_t ld, const double (&beta)[P],
                          double alpha, double r, double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P], double& S) {
     sym_zero<P>(A);
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) b[j] = 0.0;
     S = 0.0;
     bool odd = false;
@@ -414,7 +437,7 @@ PDQ_HD void irls_sweep(const Group& grp, const DesignS& d, const int64_t* y, int
     bool odd = !(alpha > 0.0 && r > 0.0 && r < 1e300 && min_mu > 0.0);
     {
         double bound = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) bound = fma(fabs(beta[j]), d.X[d.N * design_row_stride(P) + j], bound);
         odd = odd || !(bound < 300.0);
     }
@@ -451,7 +474,7 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
 
     // ---- start value (utils.py:349-357) and the mu-independent part of nb_nll ----------------
     double v[P];
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) v[j] = 0.0;
     double lgsum = 0.0, logmean = 0.0;
     const int trips = (d.N + grp.T - 1) / grp.T;  // uniform across the warp: the loop body votes
@@ -473,7 +496,7 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
         double t;
         if (prm.full_rank) {
             t = tlog(q + 0.1, d.mtab);
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) v[j] = fma(x[j], in ? t : 0.0, v[j]);
         } else {
             t = tlog(q, d.mtab);
@@ -494,16 +517,16 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
     lgsum = grp.sum(lgsum);
     double beta[P];
     if (prm.full_rank) {
-#pragma unroll
+PDQ_UNROLL_P
         for (int i = 0; i < P; ++i) {
             double s = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) s = fma(pinv.v[i * P + j], v[j], s);
             beta[i] = s;
         }
     } else {
         logmean = grp.sum(logmean);
-#pragma unroll
+PDQ_UNROLL_P
         for (int i = 0; i < P; ++i) beta[i] = 0.0;
         beta[0] = logmean / Nd;
     }
@@ -530,23 +553,23 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
         if (active && !(ratio > prm.beta_tol)) active = false;  // `while dev_ratio > beta_tol` (NaN exits)
         if (!grp.any(active)) break;
         Sym<P> L = A;
-#pragma unroll
+PDQ_UNROLL_P
         for (int i = 0; i < P; ++i) L.a[tri(i, i)] += kRidge;
         chol<P>(L);
         double bh[P];
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) bh[j] = b[j];
         chol_solve<P>(L, bh);
         if (active) {
             ++it;
             bool div = it >= prm.maxiter;
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) div = div || (fabs(bh[j]) > prm.max_beta);
             if (div) {
                 status = kIrlsNeedsOptimizer;
                 active = false;
             } else {
-#pragma unroll
+PDQ_UNROLL_P
                 for (int j = 0; j < P; ++j) beta[j] = bh[j];
             }
         }
@@ -556,7 +579,7 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
     Sym<P> Hinv;
     {
         Sym<P> L = A;
-#pragma unroll
+PDQ_UNROLL_P
         for (int i = 0; i < P; ++i) L.a[tri(i, i)] += kRidge;
         chol<P>(L);
         chol_inverse<P>(L, Hinv);
@@ -569,7 +592,7 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
         double x[P];
         load_x<P>(d, n, x);
         double eta = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
         if (eta != eta_prev) {  // same carry-over as the sweeps: equal design rows share their exponential
             exp_prev = texp(eta, d.mtab);
@@ -592,13 +615,13 @@ PDQ_HD void irls_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pin
         Sym<P> M = A;
         if (grp.any(clamped)) {
             group_sum_sym<P>(grp, Dc);
-#pragma unroll
+PDQ_UNROLL_P
             for (int k = 0; k < P * (P + 1) / 2; ++k) M.a[k] += Dc.a[k];
         }
         wald_finish<P>(grp, M, *wald, beta, wald_p, wald_stat, wald_se, valid);
     }
     if (valid && grp.si == 0) {
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) beta_out[j] = beta[j];
         *conv_out = 1.0;  // IRLS exits are "converged" (utils.py:365); the optimiser branch overwrites
         *status_out = status;
@@ -617,7 +640,7 @@ PDQ_HD void irls_obj_sweep(const Group& grp, const DesignS& d, const int64_t* y,
                            double alpha, double r, double min_mu, double log_min_mu, double& f, double (&g)[P],
                            Sym<P>& H) {
     sym_zero<P>(H);
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) g[j] = 0.0;
     f = 0.0;
     for (int n = grp.si; n < d.N; n += grp.T) {
@@ -625,7 +648,7 @@ PDQ_HD void irls_obj_sweep(const Group& grp, const DesignS& d, const int64_t* y,
         load_x<P>(d, n, x);
         const double yv = (double)y[n * ld];
         double eta = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
         const double mu_raw = d.sf[n * d.RS] * exp(eta);
         const bool cl = mu_raw < min_mu;
@@ -636,14 +659,14 @@ PDQ_HD void irls_obj_sweep(const Group& grp, const DesignS& d, const int64_t* y,
         const double t = (r + yv) * mu / (r + mu);
         const double gi = t - yv;
         const double hi = t * r / (r + mu);  // d t / d eta where the clamp is inactive
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) g[j] = fma(gi, x[j], g[j]);
         sym_rank1<P>(H, hi, x);
     }
     f = grp.sum(f);
     group_sum_vec<P>(grp, g);
     group_sum_sym<P>(grp, H);
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) {
         f = fma(0.5 * kRidge * beta[j], beta[j], f);
         g[j] = fma(kRidge, beta[j], g[j]);
@@ -660,7 +683,7 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
     const double log_min_mu = log(prm.min_mu);
     // start value: same as irls_gene (utils.py:349-357, `beta_init`)
     double v[P];
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) v[j] = 0.0;
     double logmean = 0.0;
     for (int n = grp.si; n < d.N; n += grp.T) {
@@ -669,7 +692,7 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
         const double q = (double)y[n * ld] / d.sf[n * d.RS];
         if (prm.full_rank) {
             const double t = log(q + 0.1);
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
         } else {
             logmean += log(q);
@@ -678,20 +701,20 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
     group_sum_vec<P>(grp, v);
     double beta[P];
     if (prm.full_rank) {
-#pragma unroll
+PDQ_UNROLL_P
         for (int i = 0; i < P; ++i) {
             double s = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) s = fma(pinv.v[i * P + j], v[j], s);
             beta[i] = s;
         }
     } else {
         logmean = grp.sum(logmean);
-#pragma unroll
+PDQ_UNROLL_P
         for (int i = 0; i < P; ++i) beta[i] = 0.0;
         beta[0] = logmean / (double)d.N;
     }
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) beta[j] = fmin(fmax(beta[j], prm.min_beta), prm.max_beta);
 
     double f, g[P];
@@ -702,7 +725,7 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
         // projected-gradient norm (free variables only)
         double pg = 0.0;
         bool fixed[P];
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) {
             fixed[j] = (beta[j] <= prm.min_beta && g[j] > 0.0) || (beta[j] >= prm.max_beta && g[j] < 0.0);
             if (!fixed[j]) pg = fmax(pg, fabs(g[j]));
@@ -715,11 +738,11 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
         // Newton direction on the free set
         Sym<P> L = H;
         double dir[P];
-#pragma unroll
+PDQ_UNROLL_P
         for (int i = 0; i < P; ++i) {
             dir[i] = fixed[i] ? 0.0 : -g[i];
             if (fixed[i]) {
-#pragma unroll
+PDQ_UNROLL_P
                 for (int j = 0; j < P; ++j)
                     if (j != i) L.a[j <= i ? tri(i, j) : tri(j, i)] = 0.0;
                 L.a[tri(i, i)] = 1.0;
@@ -728,11 +751,11 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
         chol<P>(L);
         chol_solve<P>(L, dir);
         double slope = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) slope = fma(g[j], dir[j], slope);
         if (!(slope < 0.0)) {  // not a descent direction (indefinite/NaN): steepest descent on the free set
             slope = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) {
                 dir[j] = fixed[j] ? 0.0 : -g[j];
                 slope = fma(g[j], dir[j], slope);
@@ -742,11 +765,11 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
         double step = 1.0, fn = f, gn[P], bn[P];
         Sym<P> Hn = H;
         bool accepted = false;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) { gn[j] = g[j]; bn[j] = beta[j]; }
         for (int ls = 0; ls < 30; ++ls) {
             double bt[P], dec = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) {
                 bt[j] = fmin(fmax(fma(step, dir[j], beta[j]), prm.min_beta), prm.max_beta);
                 dec = fma(g[j], bt[j] - beta[j], dec);
@@ -759,7 +782,7 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
                 accepted = true;
                 fn = ft;
                 Hn = Ht;
-#pragma unroll
+PDQ_UNROLL_P
                 for (int j = 0; j < P; ++j) { gn[j] = gt[j]; bn[j] = bt[j]; }
             }
             if (!grp.any(active && !accepted)) break;
@@ -773,7 +796,7 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
                 const double df = f - fn;
                 f = fn;
                 H = Hn;
-#pragma unroll
+PDQ_UNROLL_P
                 for (int j = 0; j < P; ++j) { g[j] = gn[j]; beta[j] = bn[j]; }
                 if (df <= 1e-15 * (1.0 + fabs(f))) {  // no further decrease possible in FP64
                     active = false;
@@ -790,7 +813,7 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
         double x[P];
         load_x<P>(d, n, x);
         double eta = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
         const double mu_raw = d.sf[n * d.RS] * exp(eta);
         const double mu = (mu_raw < prm.min_mu) ? prm.min_mu : mu_raw;
@@ -803,7 +826,7 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
         wald_finish<P>(grp, M, *wald, beta, wald_p, wald_stat, wald_se, valid);
     }
     Sym<P> Hinv;
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = 0; i < P; ++i) A.a[tri(i, i)] += kRidge;
     chol<P>(A);
     chol_inverse<P>(A, Hinv);
@@ -812,7 +835,7 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
         double x[P];
         load_x<P>(d, n, x);
         double eta = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) eta = fma(x[j], beta[j], eta);
         const double mu_raw = d.sf[n * d.RS] * exp(eta);
         const double mu = (mu_raw < prm.min_mu) ? prm.min_mu : mu_raw;
@@ -820,7 +843,7 @@ PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallM
         hat_out[n * ld_out] = mu / fma(mu, alpha, 1.0) * sym_quad<P>(Hinv, x);
     }
     if (grp.si == 0) {
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) beta_out[j] = beta[j];
         *conv_out = ok ? 1.0 : 0.0;
     }
@@ -925,12 +948,12 @@ PDQ_HD void alpha_pair(const Group& grp, const double* xp0, const double* xp1, c
     }
     if (cr_reg) {
         double xv[P];
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) xv[j] = xp0[j];
         const double W0 = one ? m0 * r * inv0 : 0.0;
         sym_rank1<P>(A, W0, xv);
         sym_rank1<P>(B, W0 * W0, xv);
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) xv[j] = xp1[j];
         const double W1 = two ? m1 * r * inv1 : 0.0;
         sym_rank1<P>(A, W1, xv);
@@ -1236,21 +1259,21 @@ struct NormedFromCounts {
 template <int P, class Y>
 PDQ_HD double rough_disp_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pinv, const Y& yy) {
     double v[P];
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) v[j] = 0.0;
     for (int n = grp.si; n < d.N; n += grp.T) {
         double x[P];
         load_x<P>(d, n, x);
         const double t = yy.at(d, n);
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
     }
     group_sum_vec<P>(grp, v);
     double beta[P];
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = 0; i < P; ++i) {
         double s = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) s = fma(pinv.v[i * P + j], v[j], s);
         beta[i] = s;
     }
@@ -1259,7 +1282,7 @@ PDQ_HD double rough_disp_gene(const Group& grp, const DesignS& d, const SmallMat
         double x[P];
         load_x<P>(d, n, x);
         double yh = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) yh = fma(x[j], beta[j], yh);
         yh = (yh < 1.0) ? 1.0 : yh;  // np.maximum(y_hat, 1)
         const double e = yy.at(d, n) - yh;
@@ -1277,7 +1300,7 @@ PDQ_HD void mom_fused_gene(const Group& grp, const DesignS& d, const SmallMat<P>
                            double s_mean_inv, double min_disp, double max_disp, double min_mu, double* alpha_out,
                            double* mean_out, double* mu_out, int64_t ld_out, bool valid) {
     double v[P];
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) v[j] = 0.0;
     double s = 0.0;
     const int64_t ystep = (int64_t)grp.T * ld;
@@ -1287,16 +1310,16 @@ PDQ_HD void mom_fused_gene(const Group& grp, const DesignS& d, const SmallMat<P>
         load_x<P>(d, n, x);
         const double t = fast_div((double)c, d.sf[n * d.RS]);  // <= 1 ulp from counts / sf
         s += t;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) v[j] = fma(x[j], t, v[j]);
     });
     group_sum_vec<P>(grp, v);
     const double m = grp.sum(s) / (double)d.N;
     double beta[P];
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = 0; i < P; ++i) {
         double acc = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) acc = fma(pinv.v[i * P + j], v[j], acc);
         beta[i] = acc;
     }
@@ -1305,7 +1328,7 @@ PDQ_HD void mom_fused_gene(const Group& grp, const DesignS& d, const SmallMat<P>
         double x[P];
         load_x<P>(d, n, x);
         double fit = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) fit = fma(x[j], beta[j], fit);
         const double t = fast_div((double)c, d.sf[n * d.RS]);  // <= 1 ulp from counts / sf
         const double yh = (fit < 1.0) ? 1.0 : fit;  // np.maximum(y_hat, 1)
@@ -1394,19 +1417,34 @@ PDQ_HD void trim_class(int nc, bool global_mode, int& ntrim, double& scale) {
     scale = (k == 2) ? 1.51 : ((k == 1) ? 1.86 : 2.04);
 }
 
-// mean of v[s:e) after dropping the ntrim smallest and ntrim largest entries (np.sort + slice + mean)
-PDQ_HD double trimmed_mean_cell(const Group& grp, const double* v, int s, int e, int ntrim) {
-    const int nc = e - s;
-    double part = 0.0;
-    for (int i = s + grp.si; i < e; i += grp.T) {
-        const double vi = v[i];
-        int rank = 0;
-        for (int j = s; j < e; ++j) {
-            const double vj = v[j];
-            rank += (vj < vi) || (vj == vi && j < i);
+// mean of v[s:e) after dropping the ntrim smallest and ntrim largest entries (np.sort + slice + mean), by SELECTION: every lane
+// sorts its own strided share of the cell in place (insertion sort, m = n_c / T entries), then the group pops the smallest and
+// the largest remaining head ntrim times (one argmin / argmax butterfly each); what is left between the lanes' cursors is the
+// kept set, summed directly.  O(m^2 + ntrim log T) per lane instead of the O(n_c^2 / T) rank counting of round 1 (1.1 ms at
+// two cells of 100 samples, 58 ms at two cells of 500).  Ties carry equal values, so which of them is dropped does not matter.
+// The cell is left permuted (callers only need it as a multiset).
+PDQ_HD double trimmed_mean_cell(const Group& grp, double* v, int s, int e, int ntrim) {
+    const int nc = e - s, T = grp.T;
+    const int m = (nc - grp.si + T - 1) / T;        // this lane's entries: v[s + si + k T], k < m   (m <= 0: none)
+    double* mine = v + s + grp.si;
+    for (int i = 1; i < m; ++i) {
+        const double x = mine[i * T];
+        int j = i - 1;
+        while (j >= 0 && mine[j * T] > x) {
+            mine[(j + 1) * T] = mine[j * T];
+            --j;
         }
-        if (rank >= ntrim && rank < nc - ntrim) part += vi;
+        mine[(j + 1) * T] = x;
     }
+    int lo = 0, hi = m > 0 ? m : 0;
+    for (int k = 0; k < ntrim; ++k) {                // uniform trip count across the warp: the butterflies vote
+        const double head = lo < hi ? mine[lo * T] : 1.7976931348623157e308 * 10.0;
+        if (grp.argext(head, false) == grp.si) ++lo;
+        const double tail = lo < hi ? mine[(hi - 1) * T] : -1.7976931348623157e308 * 10.0;
+        if (grp.argext(tail, true) == grp.si) --hi;
+    }
+    double part = 0.0;
+    for (int k = lo; k < hi; ++k) part += mine[k * T];
     return grp.sum(part) / (double)(nc - 2 * ntrim);
 }
 

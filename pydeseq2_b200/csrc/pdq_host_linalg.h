@@ -8,7 +8,7 @@
 #include <vector>
 
 #ifndef PDQ_MAX_P
-#define PDQ_MAX_P 8
+#define PDQ_MAX_P 16
 #endif
 
 namespace pdq {

@@ -19,6 +19,21 @@
 #include "pdq_shrink.cuh"
 #include "pdq_internal.h"
 
+// This file is compiled once per RANGE OF DESIGN WIDTHS (pydeseq2_b200/build.py): the base unit (PDQ_TU_P = 0) holds the kernels
+// for p = 1..8 -- p x p algebra fully unrolled in registers -- and everything that does not depend on p; one further unit per
+// wide design width p = 9..16 (PDQ_TU_P = p) holds that width's kernels, same source, loops over the design columns not
+// unrolled.  The units compile in parallel; pdq_dispatch.cu routes a launch to the unit that owns the design's width.
+#ifndef PDQ_TU_P
+#define PDQ_TU_P 0
+#endif
+#define PDQ_CAT_(a, b) a##b
+#define PDQ_CAT(a, b) PDQ_CAT_(a, b)
+#if PDQ_TU_P == 0
+#define PDQ_TUFN(name) name##_p1to8
+#else
+#define PDQ_TUFN(name) PDQ_CAT(name##_p, PDQ_TU_P)
+#endif
+
 namespace pdq {
 namespace {
 
@@ -448,19 +463,20 @@ __global__ void __launch_bounds__(kBlock) k_mu_from_lfc(const __grid_constant__ 
     map_lanes(a.lgT, a.G, grp, g, valid);
     if (!valid) return;
     double b[P];
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) b[j] = a.lfc[(int64_t)g * P + j];
     for (int n = grp.si; n < d.N; n += grp.T) {
         double x[P];
         load_x<P>(d, n, x);
         double eta = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) eta = fma(x[j], b[j], eta);
         a.mu[n * a.ld_out + g] = d.sf[n * d.RS] * exp(eta);  // ds.py:320-324
     }
 }
 
 
+#if PDQ_TU_P == 0
 // ---- dispersion trend + prior: the whole gamma-GLM fit (all iterations, all outer rounds) and the MAD-based prior
 // variance in ONE launch of one thread-block cluster.  Per iteration the blocks reduce their partial sums with warp
 // shuffles + shared memory, exchange the block totals through distributed shared memory (DSMEM stores into every
@@ -472,6 +488,7 @@ constexpr int kTrendMaxCluster = 16;
 struct ClusterReducer {
     double* warp_part;  // [32][kTrendK]
     double* slots;      // [2][kTrendMaxCluster][kTrendK], written by every block of the cluster (DSMEM)
+    double* totals;     // [2][kTrendK]: the cluster-wide sums, broadcast to the block's threads
     unsigned rank, nblocks;
     int parity;
     __host__ __device__ int tid() const {
@@ -628,11 +645,15 @@ struct ClusterReducer {
             }
         }
         if (nblocks > 1) cluster.sync(); else __syncthreads();  // release the DSMEM stores / acquire the peers'
-        for (int j = 0; j < k; ++j) {
+        // k threads add up the blocks' slots, everybody reads the k totals (broadcast reads).  The first version had EVERY thread
+        // add nblocks * k slots itself: 160 shared-memory reads per thread and pass -- that alone was ~5 us of every pass.
+        if ((int)threadIdx.x < k) {
             double tot = 0.0;
-            for (unsigned r = 0; r < nblocks; ++r) tot += slots[(parity * kTrendMaxCluster + r) * kTrendK + j];
-            v[j] = tot;
+            for (unsigned r = 0; r < nblocks; ++r) tot += slots[(parity * kTrendMaxCluster + r) * kTrendK + threadIdx.x];
+            totals[parity * kTrendK + threadIdx.x] = tot;
         }
+        __syncthreads();
+        for (int j = 0; j < k; ++j) v[j] = totals[parity * kTrendK + j];
         parity ^= 1;
 #else
         (void)v;
@@ -647,10 +668,11 @@ __global__ void __launch_bounds__(1024) k_trend_prior(const double* __restrict__
                                                       double trigamma_c, int with_prior, TrendOut* out) {
     __shared__ double warp_part[32 * kTrendK];
     __shared__ double slots[2 * kTrendMaxCluster * kTrendK];
+    __shared__ double totals[2 * kTrendK];
     __shared__ unsigned hist[514];
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    ClusterReducer red{warp_part, slots, cluster.block_rank(), cluster.num_blocks(), 0};
+    ClusterReducer red{warp_part, slots, totals, cluster.block_rank(), cluster.num_blocks(), 0};
     double *xs = scratch, *ts = scratch + n, *res = scratch + 2 * n;
     trend_prepare(red, x, t, n, x_is_mean != 0, lo, hi, xs, ts);
     TrendOut o = trend_fit_outer(red, xs, ts, n, outer != 0);
@@ -681,6 +703,7 @@ __global__ void __launch_bounds__(1024) k_size_factor_median(const int64_t* __re
     __shared__ unsigned hist[514];
     __shared__ double warp_part[32 * kTrendK];
     __shared__ double slots[2 * kTrendMaxCluster * kTrendK];
+    __shared__ double totals[2 * kTrendK];
     __shared__ unsigned cnt_s;
     const int n = blockIdx.x;
     double* row = scratch + (size_t)n * G;
@@ -696,7 +719,7 @@ __global__ void __launch_bounds__(1024) k_size_factor_median(const int64_t* __re
     }
     atomicAdd(&cnt_s, cnt);
     __syncthreads();
-    ClusterReducer red{warp_part, slots, 0u, 1u, 0};  // one block per sample: the single-block paths of the reducer
+    ClusterReducer red{warp_part, slots, totals, 0u, 1u, 0};  // one block per sample: the single-block paths of the reducer
     const double med = median_of(red, row, (size_t)G, (size_t)cnt_s, false, 0.0, hist);
     if (threadIdx.x == 0) sf_out[n] = exp(med);
 }
@@ -720,6 +743,8 @@ __global__ void k_select_disp(const double* __restrict__ gw, const double* __res
     disp[i] = out ? g : m;
     if (outlier) outlier[i] = out ? 1.0 : 0.0;
 }
+
+#endif  // PDQ_TU_P == 0
 
 // ---- launch helpers ---------------------------------------------------------------------------------
 inline int grid_for(int G, int lgT) {
@@ -787,6 +812,7 @@ __global__ void __launch_bounds__(kBlock) k_lfc_shrink(const __grid_constant__ S
                    a.status + g, valid, a.force != 0);
 }
 
+#if PDQ_TU_P == 0
 __global__ void __launch_bounds__(kBlock) k_lfc_shrink_grid(const __grid_constant__ ShrinkArgs<2> a) {
     extern __shared__ __align__(128) unsigned char smem[];
     Group grp;
@@ -800,6 +826,9 @@ __global__ void __launch_bounds__(kBlock) k_lfc_shrink_grid(const __grid_constan
     shrink_grid_gene(grp, d, a.prm, a.counts + g, a.ld, a.size[g], a.beta + (int64_t)g * 2, a.ih + (int64_t)g * 4, run);
 }
 
+#endif
+
+#if PDQ_TU_P == 0
 // ---- FP64 peak probe (bench.py: the second roofline of these kernels) ------------------------------------------------
 // 8 independent DFMA chains per thread, 8 blocks of 256 threads per SM: enough independent work to saturate the FP64 pipe.
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double m, double c) {
@@ -838,6 +867,9 @@ __global__ void __launch_bounds__(256) k_hash(const uint64_t* __restrict__ w, si
     }
 }
 
+#endif  // PDQ_TU_P == 0
+
+#if PDQ_TU_P == 0
 #define PDQ_DISPATCH_P(p, ...)             \
     switch (p) {                           \
         case 1: { constexpr int P = 1; __VA_ARGS__; } break; \
@@ -850,12 +882,20 @@ __global__ void __launch_bounds__(256) k_hash(const uint64_t* __restrict__ w, si
         case 8: { constexpr int P = 8; __VA_ARGS__; } break; \
         default: return PDQ_ERR_UNSUPPORTED; \
     }
+#else
+#define PDQ_DISPATCH_P(p, ...)                              \
+    {                                                       \
+        if ((p) != PDQ_TU_P) return PDQ_ERR_UNSUPPORTED;    \
+        constexpr int P = PDQ_TU_P;                         \
+        __VA_ARGS__;                                        \
+    }
+#endif
 
 inline int check_launch() { return cudaGetLastError() == cudaSuccess ? 0 : PDQ_ERR_CUDA; }
 
 }  // namespace
 
-int launch_lin_reg_mu(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G, double min_mu,
+int PDQ_TUFN(launch_lin_reg_mu)(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G, double min_mu,
                       double* mu_out, int64_t ld_out) {
     PDQ_DISPATCH_P(d.p, {
         LinMuArgs<P> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, pinv_of<P>(d), counts, ld, G, c.lgT, min_mu, mu_out, ld_out};
@@ -866,7 +906,7 @@ int launch_lin_reg_mu(const LaunchCfg& c, const DesignDev& d, const int64_t* cou
     return 1;
 }
 
-int launch_irls(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G, const double* disp,
+int PDQ_TUFN(launch_irls)(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G, const double* disp,
                 const IrlsHost& h, double* beta, double* mu, double* hat, int64_t ld_out, double* conv, int* status,
                 int* n_fallback, const WaldHost* w) {
     if (n_fallback && cudaMemsetAsync(n_fallback, 0, sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;
@@ -904,7 +944,7 @@ int launch_irls(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, i
     return 2;
 }
 
-int launch_alpha_mle(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G,
+int PDQ_TUFN(launch_alpha_mle)(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G,
                      const double* mu, int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp,
                      double prior_var, const double* prior_var_dev, int cr_reg, int prior_reg, double* alpha, double* conv,
                      int* status) {
@@ -928,7 +968,7 @@ int launch_alpha_mle(const LaunchCfg& c, const DesignDev& d, const int64_t* coun
     return 2;
 }
 
-int launch_wald(const LaunchCfg& c, const DesignDev& d, const double* disp, const double* lfc, const double* mu,
+int PDQ_TUFN(launch_wald)(const LaunchCfg& c, const DesignDev& d, const double* disp, const double* lfc, const double* mu,
                 int64_t ld_mu, int G, const double* ridge, const double* contrast, double lfc_null, int alt, double* pv,
                 double* stat, double* se) {
     PDQ_DISPATCH_P(d.p, {
@@ -947,7 +987,7 @@ int launch_wald(const LaunchCfg& c, const DesignDev& d, const double* disp, cons
     return 1;
 }
 
-int launch_rough(const LaunchCfg& c, const DesignDev& d, const double* normed, int64_t ld, int G, double* alpha) {
+int PDQ_TUFN(launch_rough)(const LaunchCfg& c, const DesignDev& d, const double* normed, int64_t ld, int G, double* alpha) {
     PDQ_DISPATCH_P(d.p, {
         MomArgs<P> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, pinv_of<P>(d), normed, nullptr, ld, G, c.lgT, d.s_mean_inv, 0.0, 0.0, alpha,
                      nullptr, 0.0, nullptr, 0};
@@ -958,7 +998,7 @@ int launch_rough(const LaunchCfg& c, const DesignDev& d, const double* normed, i
     return 1;
 }
 
-int launch_moments(const LaunchCfg& c, const DesignDev& d, const double* normed, int64_t ld, int G, double* alpha,
+int PDQ_TUFN(launch_moments)(const LaunchCfg& c, const DesignDev& d, const double* normed, int64_t ld, int G, double* alpha,
                    double* all_zero) {
     PDQ_DISPATCH_P(d.p, {
         MomArgs<P> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, pinv_of<P>(d), normed, nullptr, ld, G, c.lgT, d.s_mean_inv, 0.0, 0.0, alpha,
@@ -970,7 +1010,7 @@ int launch_moments(const LaunchCfg& c, const DesignDev& d, const double* normed,
     return 1;
 }
 
-int launch_mom_from_counts(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G,
+int PDQ_TUFN(launch_mom_from_counts)(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G,
                            double min_disp, double max_disp, double* alpha, double* normed_mean, double min_mu, double* mu_hat,
                            int64_t ld_mu) {
     PDQ_DISPATCH_P(d.p, {
@@ -983,7 +1023,7 @@ int launch_mom_from_counts(const LaunchCfg& c, const DesignDev& d, const int64_t
     return 1;
 }
 
-int launch_mu_from_lfc(const LaunchCfg& c, const DesignDev& d, const double* lfc, int G, double* mu, int64_t ld_out) {
+int PDQ_TUFN(launch_mu_from_lfc)(const LaunchCfg& c, const DesignDev& d, const double* lfc, int G, double* mu, int64_t ld_out) {
     PDQ_DISPATCH_P(d.p, {
         MuLfcArgs<P> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, lfc, G, c.lgT, mu, ld_out};
         if (int e = prep(k_mu_from_lfc<P>, d.smem_bytes)) return e;
@@ -993,6 +1033,7 @@ int launch_mu_from_lfc(const LaunchCfg& c, const DesignDev& d, const double* lfc
     return 1;
 }
 
+#if PDQ_TU_P == 0
 int launch_trend_fit(const LaunchCfg& c, const double* x, const double* t, double* scratch3n, size_t n, int x_is_mean,
                      double lo, double hi, int outer, double min_disp, double trigamma_c, int with_prior, double* out16) {
     // cluster size: enough blocks for ~4 elements per thread; 8 is the portable maximum, 16 needs the opt-in attribute
@@ -1004,15 +1045,23 @@ int launch_trend_fit(const LaunchCfg& c, const double* x, const double* t, doubl
         else
             cudaGetLastError();
     }
+    // threads per block: the per-pass cost of a small fit is the reduction (ten packed sums through warp shuffles and shared
+    // memory per warp), not the arithmetic -- 256 threads per block (~5 genes per thread at 20 000 genes) instead of 1024 cut
+    // it four-fold; large vectors keep 1024
+    unsigned threads = n <= 24576 ? 256u : (n <= 49152 ? 512u : 1024u);
+    if (const char* e = getenv("PDQ_TREND_THREADS")) {  // tuning hook
+        const int v = atoi(e);
+        if (v == 256 || v == 512 || v == 1024) threads = (unsigned)v;
+    }
     unsigned nb = 1;
-    while ((int)nb < max_cluster && (size_t)nb * 1024 * 4 < n) nb <<= 1;
+    while ((int)nb < max_cluster && (size_t)nb * threads * 4 < n) nb <<= 1;
     if (const char* e = getenv("PDQ_TREND_CLUSTER")) {  // tuning hook: force the cluster size (1, 2, 4, 8, 16)
         const int v = atoi(e);
         if (v >= 1 && v <= max_cluster && !(v & (v - 1))) nb = (unsigned)v;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nb, 1, 1);
-    cfg.blockDim = dim3(1024, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = c.stream;
     cudaLaunchAttribute attr[1];
@@ -1043,7 +1092,9 @@ int launch_trend_eval(const LaunchCfg& c, const double* means, size_t n, const d
     return 1;
 }
 
-int launch_cooks(const LaunchCfg& c0, const DesignDev& d, const int64_t* counts, int64_t ld, int G, const double* mu, const double* hat,
+#endif  // PDQ_TU_P == 0
+
+int PDQ_TUFN(launch_cooks)(const LaunchCfg& c0, const DesignDev& d, const int64_t* counts, int64_t ld, int G, const double* mu, const double* hat,
                  int64_t ld2, double cutoff, double* cooks, int64_t ld_out, double* disp, double* outlier, double* replaced) {
     // the per-gene staging (2 * n_in_cells doubles) bounds the genes per block: widen the lane groups until it fits
     LaunchCfg c = c0;
@@ -1062,7 +1113,7 @@ int launch_cooks(const LaunchCfg& c0, const DesignDev& d, const int64_t* counts,
 }
 
 
-int launch_lfc_shrink(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G, const double* size,
+int PDQ_TUFN(launch_lfc_shrink)(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G, const double* size,
                       double prior_no_shrink_scale, double prior_scale, int shrink_index, double* beta, double* inv_hessian,
                       double* conv, int* status) {
     if (shrink_index < 0 || shrink_index >= d.p) return PDQ_ERR_INVALID;
@@ -1073,15 +1124,18 @@ int launch_lfc_shrink(const LaunchCfg& c, const DesignDev& d, const int64_t* cou
         if (int e = prep(k_lfc_shrink<P>, d.smem_bytes)) return e;
         k_lfc_shrink<P><<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     });
+#if PDQ_TU_P == 0
     if (d.p == 2) {
         ShrinkArgs<2> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, prm, counts, ld, G, c.lgT, size, beta, inv_hessian, conv, status, force};
         if (int e = prep(k_lfc_shrink_grid, d.smem_bytes)) return e;
         k_lfc_shrink_grid<<<grid_for(G, c.lgT), kBlock, d.smem_bytes, c.stream>>>(a);
     }
+#endif
     if (int e = check_launch()) return e;
     return d.p == 2 ? 2 : 1;
 }
 
+#if PDQ_TU_P == 0
 int launch_hash(cudaStream_t stream, int sm_count, const void* dptr, size_t words, uint64_t* out2) {
     k_hash<<<sm_count * 8, 256, 0, stream>>>(reinterpret_cast<const uint64_t*>(dptr), words, reinterpret_cast<unsigned long long*>(out2));
     if (int e = check_launch()) return e;
@@ -1111,5 +1165,7 @@ int launch_select_disp(const LaunchCfg& c, const double* gw, const double* mp, c
     if (int e = check_launch()) return e;
     return 1;
 }
+
+#endif  // PDQ_TU_P == 0
 
 }  // namespace pdq

@@ -10,8 +10,18 @@
 
 #if defined(__CUDACC__)
 #define PDQ_HD __host__ __device__ __forceinline__
+// Loops over the p design columns: fully unrolled (register-resident p x p algebra) in the translation unit of p = 1..8; in the
+// units of the wide designs (PDQ_TU_P = 9..16, see pdq_kernels.cu) they stay loops and the small matrices live in local
+// memory -- slower per gene, but any design of up to 16 columns runs.  (A single `unroll (P <= 8 ? 64 : 1)` was tried first:
+// a numeric factor made the base unit's kernels twice as large and its compilation seven times slower.)
+#if defined(PDQ_TU_P) && PDQ_TU_P > 8
+#define PDQ_UNROLL_P _Pragma("unroll 1")
+#else
+#define PDQ_UNROLL_P _Pragma("unroll")
+#endif
 #else
 #define PDQ_HD inline
+#define PDQ_UNROLL_P
 #endif
 
 namespace pdq {
@@ -33,17 +43,17 @@ struct Sym {
 
 template <int P>
 PDQ_HD void sym_zero(Sym<P>& s) {
-#pragma unroll
+PDQ_UNROLL_P
     for (int k = 0; k < P * (P + 1) / 2; ++k) s.a[k] = 0.0;
 }
 
 // s += w * x x^T
 template <int P>
 PDQ_HD void sym_rank1(Sym<P>& s, double w, const double (&x)[P]) {
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = 0; i < P; ++i) {
         const double wx = w * x[i];
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j <= i; ++j) s.a[tri(i, j)] = fma(wx, x[j], s.a[tri(i, j)]);
     }
 }
@@ -51,18 +61,18 @@ PDQ_HD void sym_rank1(Sym<P>& s, double w, const double (&x)[P]) {
 // in-place L L^T = A
 template <int P>
 PDQ_HD void chol(Sym<P>& L) {
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) {
         double d = L.a[tri(j, j)];
-#pragma unroll
+PDQ_UNROLL_P
         for (int k = 0; k < j; ++k) d = fma(-L.a[tri(j, k)], L.a[tri(j, k)], d);
         d = sqrt(d);
         L.a[tri(j, j)] = d;
         const double inv = 1.0 / d;
-#pragma unroll
+PDQ_UNROLL_P
         for (int i = j + 1; i < P; ++i) {
             double s = L.a[tri(i, j)];
-#pragma unroll
+PDQ_UNROLL_P
             for (int k = 0; k < j; ++k) s = fma(-L.a[tri(i, k)], L.a[tri(j, k)], s);
             L.a[tri(i, j)] = s * inv;
         }
@@ -72,17 +82,17 @@ PDQ_HD void chol(Sym<P>& L) {
 // solve (L L^T) x = b in place
 template <int P>
 PDQ_HD void chol_solve(const Sym<P>& L, double (&b)[P]) {
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = 0; i < P; ++i) {
         double s = b[i];
-#pragma unroll
+PDQ_UNROLL_P
         for (int k = 0; k < i; ++k) s = fma(-L.a[tri(i, k)], b[k], s);
         b[i] = s / L.a[tri(i, i)];
     }
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = P - 1; i >= 0; --i) {
         double s = b[i];
-#pragma unroll
+PDQ_UNROLL_P
         for (int k = i + 1; k < P; ++k) s = fma(-L.a[tri(k, i)], b[k], s);
         b[i] = s / L.a[tri(i, i)];
     }
@@ -91,7 +101,7 @@ PDQ_HD void chol_solve(const Sym<P>& L, double (&b)[P]) {
 template <int P>
 PDQ_HD double chol_logdet(const Sym<P>& L) {
     double s = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = 0; i < P; ++i) s += log(L.a[tri(i, i)]);
     return 2.0 * s;
 }
@@ -100,24 +110,24 @@ PDQ_HD double chol_logdet(const Sym<P>& L) {
 template <int P>
 PDQ_HD void chol_inverse(const Sym<P>& L, Sym<P>& Ainv) {
     Sym<P> Li;  // L^{-1}, lower
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) {
         Li.a[tri(j, j)] = 1.0 / L.a[tri(j, j)];
-#pragma unroll
+PDQ_UNROLL_P
         for (int i = j + 1; i < P; ++i) {
             double s = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
             for (int k = j; k < i; ++k) s = fma(-L.a[tri(i, k)], Li.a[tri(k, j)], s);
             Li.a[tri(i, j)] = s / L.a[tri(i, i)];
         }
     }
     // Ainv = Li^T Li
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = 0; i < P; ++i)
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j <= i; ++j) {
             double s = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
             for (int k = i; k < P; ++k) s = fma(Li.a[tri(k, i)], Li.a[tri(k, j)], s);
             Ainv.a[tri(i, j)] = s;
         }
@@ -127,10 +137,10 @@ PDQ_HD void chol_inverse(const Sym<P>& L, Sym<P>& Ainv) {
 template <int P>
 PDQ_HD double sym_quad(const Sym<P>& S, const double (&x)[P]) {
     double q = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = 0; i < P; ++i) {
         double r = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < i; ++j) r = fma(S.a[tri(i, j)], x[j], r);
         q = fma(x[i], fma(2.0, r, S.a[tri(i, i)] * x[i]), q);
     }
@@ -140,10 +150,10 @@ PDQ_HD double sym_quad(const Sym<P>& S, const double (&x)[P]) {
 // y = S x
 template <int P>
 PDQ_HD void sym_matvec(const Sym<P>& S, const double (&x)[P], double (&y)[P]) {
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = 0; i < P; ++i) {
         double r = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) r = fma(S.a[j <= i ? tri(i, j) : tri(j, i)], x[j], r);
         y[i] = r;
     }
@@ -153,10 +163,10 @@ PDQ_HD void sym_matvec(const Sym<P>& S, const double (&x)[P], double (&y)[P]) {
 template <int P>
 PDQ_HD double sym_dot(const Sym<P>& S, const Sym<P>& T) {
     double d = 0.0, o = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = 0; i < P; ++i) {
         d = fma(S.a[tri(i, i)], T.a[tri(i, i)], d);
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < i; ++j) o = fma(S.a[tri(i, j)], T.a[tri(i, j)], o);
     }
     return fma(2.0, o, d);

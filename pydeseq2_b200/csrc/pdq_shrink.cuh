@@ -39,14 +39,14 @@ template <int P, bool GRAD>
 PDQ_HD void shrink_eval(const Group& grp, const DesignS& d, const ShrinkParams& prm, const int64_t* y, int64_t ld, double size,
                         double lsize, const double (&beta)[P], double& f, double (&g)[P]) {
     double nll = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) g[j] = 0.0;
     for (int n = grp.si; n < d.N; n += grp.T) {
         double x[P];
         load_x<P>(d, n, x);
         const double yv = (double)y[n * ld];
         double xb = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) xb = fma(x[j], beta[j], xb);
         const double e = xb + d.lsf[n * d.RS];
         const double dd = e - lsize;
@@ -57,14 +57,14 @@ PDQ_HD void shrink_eval(const Group& grp, const DesignS& d, const ShrinkParams& 
         if (GRAD) {
             const double q = ((dd >= 0.0) ? 1.0 : t) / (1.0 + t);  // 1 / (1 + s exp(-e)) without overflow
             const double gi = ys * q - yv;
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) g[j] = fma(gi, x[j], g[j]);
         }
     }
     nll = grp.sum(nll);
     if (GRAD) group_sum_vec<P>(grp, g);
     double prior = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) {
         if (j == prm.k) {
             prior += log1p(beta[j] * beta[j] / prm.scale2);
@@ -91,7 +91,7 @@ PDQ_HD void shrink_inv_hessian(const Group& grp, const DesignS& d, const ShrinkP
         load_x<P>(d, n, x);
         const double yv = (double)y[n * ld];
         double xb = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) xb = fma(x[j], beta[j], xb);
         const double dd = xb + d.lsf[n * d.RS] - lsize;
         const double t = exp(-fabs(dd));
@@ -104,13 +104,13 @@ PDQ_HD void shrink_inv_hessian(const Group& grp, const DesignS& d, const ShrinkP
     chol_inverse<P>(A, Ai);
     double h[P], u[P], v[P];
     const double bk = beta[prm.k], den = prm.scale2 + bk * bk;
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) h[j] = (j == prm.k) ? 2.0 * (prm.scale2 - bk * bk) / (den * den) : prm.inv_var0;
     double hu = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
     for (int i = 0; i < P; ++i) {
         double su = 0.0, sv = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) {
             const double aij = Ai.a[j <= i ? tri(i, j) : tri(j, i)];
             su += aij;
@@ -119,13 +119,13 @@ PDQ_HD void shrink_inv_hessian(const Group& grp, const DesignS& d, const ShrinkP
         u[i] = su;
         v[i] = sv;
     }
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) hu = fma(h[j], u[j], hu);
     const double inv = 1.0 / (1.0 + hu);
     if (write && grp.si == 0) {
-#pragma unroll
+PDQ_UNROLL_P
         for (int i = 0; i < P; ++i)
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) ih_out[i * P + j] = Ai.a[j <= i ? tri(i, j) : tri(j, i)] - u[i] * v[j] * inv;
     }
 }
@@ -271,10 +271,10 @@ struct Lbfgs {
 template <int P>
 PDQ_HD void lbfgs_point(const Lbfgs<P>& m, const double (&x)[P], const double (&g)[P], double (&z)[P]) {
     double q[P];
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) q[j] = -g[j];
     if (m.col == 0) {
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) z[j] = x[j] + (1.0 / m.theta) * q[j];
         return;
     }
@@ -282,25 +282,25 @@ PDQ_HD void lbfgs_point(const Lbfgs<P>& m, const double (&x)[P], const double (&
     for (int i = m.col - 1; i >= 0; --i) {  // newest -> oldest
         const int s = (m.head + i) % kShrinkMem;
         double sq = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) sq = fma(m.S[s][j], q[j], sq);
         const double a = sq / m.sy[s];
         al[i] = a;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) q[j] = q[j] - a * m.Y[s][j];
     }
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) q[j] = q[j] / m.theta;
     for (int i = 0; i < m.col; ++i) {  // oldest -> newest
         const int s = (m.head + i) % kShrinkMem;
         double yr = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) yr = fma(m.Y[s][j], q[j], yr);
         const double b = yr / m.sy[s];
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) q[j] = q[j] + m.S[s][j] * (al[i] - b);
     }
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) z[j] = x[j] + q[j];
 }
 
@@ -310,15 +310,15 @@ PDQ_HD void shrink_gene(const Group& grp, const DesignS& d, const ShrinkParams& 
     const double lsize = log(size);
     const double ftol = 1e-8, gtol = 1e-8;  // utils.py:1116-1119
     double x[P], g[P], f;
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) x[j] = 0.0;
     shrink_eval<P, false>(grp, d, prm, y, ld, size, lsize, x, f, g);
     const double cnst = (f < 1.0) ? 1.0 : f;  // np.maximum(scale_cnst, 1)
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) x[j] = (j & 1) ? -0.1 : 0.1;  // beta_init, utils.py:1051
     shrink_eval<P, true>(grp, d, prm, y, ld, size, lsize, x, f, g);
     f = f / cnst;
-#pragma unroll
+PDQ_UNROLL_P
     for (int j = 0; j < P; ++j) g[j] = g[j] / cnst;
 
     Lbfgs<P> mem;
@@ -336,15 +336,15 @@ PDQ_HD void shrink_gene(const Group& grp, const DesignS& d, const ShrinkParams& 
         for (;;) {
             lbfgs_point<P>(mem, x, g, z);
             double dtd = 0.0, gd = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) {
                 dir[j] = z[j] - x[j];
                 dtd = fma(dir[j], dir[j], dtd);
             }
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) gd = fma(g[j], dir[j], gd);
             stp = (nit == 0) ? fmin(1.0 / sqrt(dtd), kLsStpMax) : 1.0;
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) { t[j] = x[j]; r[j] = g[j]; }
             fold = f;
             gdold = gd;
@@ -357,7 +357,7 @@ PDQ_HD void shrink_gene(const Group& grp, const DesignS& d, const ShrinkParams& 
                 continue;
             }
             dcsrch_start(ls, stp, f, gd);
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) xt[j] = (stp == 1.0) ? z[j] : fma(stp, dir[j], t[j]);
             return true;
         }
@@ -365,7 +365,7 @@ PDQ_HD void shrink_gene(const Group& grp, const DesignS& d, const ShrinkParams& 
 
     {
         double gn = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) gn = fmax(gn, fabs(g[j]));
         if (active && gn <= gtol) { ok = true; active = false; }
         if (active && !begin_iteration()) active = false;
@@ -377,16 +377,16 @@ PDQ_HD void shrink_gene(const Group& grp, const DesignS& d, const ShrinkParams& 
         if (!active) continue;
         f = ft / cnst;
         double gd = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) {
             g[j] = gt[j] / cnst;
             x[j] = xt[j];
         }
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) gd = fma(g[j], dir[j], gd);
         if (dcsrch_step(ls, stp, f, gd)) {  // another trial point
             if (++iback >= kShrinkMaxLs) {  // line search failed: restore, restart from steepest descent or give up
-#pragma unroll
+PDQ_UNROLL_P
                 for (int j = 0; j < P; ++j) { x[j] = t[j]; g[j] = r[j]; }
                 f = fold;
                 if (mem.col == 0) { active = false; continue; }
@@ -396,14 +396,14 @@ PDQ_HD void shrink_gene(const Group& grp, const DesignS& d, const ShrinkParams& 
                 if (!begin_iteration()) active = false;
                 continue;
             }
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) xt[j] = (stp == 1.0) ? z[j] : fma(stp, dir[j], t[j]);
             continue;
         }
         // ---- new iterate
         ++nit;
         double gn = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) gn = fmax(gn, fabs(g[j]));
         if (gn <= gtol || (fold - f) <= ftol * fmax(fmax(fabs(fold), fabs(f)), 1.0)) {
             ok = true;
@@ -413,7 +413,7 @@ PDQ_HD void shrink_gene(const Group& grp, const DesignS& d, const ShrinkParams& 
         if (nit >= kShrinkMaxIter) { active = false; continue; }
         // memory update (skipped when the curvature s'y is not safely positive)
         double rr = 0.0, yv[P];
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) {
             yv[j] = g[j] - r[j];
             rr = fma(yv[j], yv[j], rr);
@@ -429,13 +429,13 @@ PDQ_HD void shrink_gene(const Group& grp, const DesignS& d, const ShrinkParams& 
                 slot = mem.head;
                 mem.head = (mem.head + 1) % kShrinkMem;
             }
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) {
                 mem.S[slot][j] = (stp == 1.0) ? dir[j] : stp * dir[j];
                 mem.Y[slot][j] = yv[j];
             }
             double sy = 0.0;
-#pragma unroll
+PDQ_UNROLL_P
             for (int j = 0; j < P; ++j) sy = fma(mem.Y[slot][j], mem.S[slot][j], sy);
             mem.sy[slot] = sy;
             mem.theta = rr / dr;
@@ -446,7 +446,7 @@ PDQ_HD void shrink_gene(const Group& grp, const DesignS& d, const ShrinkParams& 
     if (force_grid) ok = false;
     shrink_inv_hessian<P>(grp, d, prm, y, ld, size, lsize, x, ih_out, valid);
     if (valid && grp.si == 0) {
-#pragma unroll
+PDQ_UNROLL_P
         for (int j = 0; j < P; ++j) beta_out[j] = x[j];
         *conv_out = ok ? 1.0 : 0.0;
         *status_out = (!ok && P == 2) ? kShrinkNeedsGrid : kShrinkOk;

@@ -79,6 +79,24 @@ void lane_sync(int T) {
     if (T == 1 || !t_team) return;
     t_team->bar.arrive_and_wait();
 }
+int lane_argext(int si, int T, double v, bool want_max) {
+    if (T == 1 || !t_team) return 0;
+    int who = si;
+    for (int s = T >> 1; s >= 1; s >>= 1) {
+        t_team->board[si] = v;
+        t_team->flags[si] = who;
+        t_team->bar.arrive_and_wait();
+        const double ov = t_team->board[si ^ s];
+        const int ow = t_team->flags[si ^ s];
+        t_team->bar.arrive_and_wait();
+        const bool better = want_max ? (ov > v) : (ov < v);
+        if (better || (ov == v && ow < who)) {
+            v = ov;
+            who = ow;
+        }
+    }
+    return who;
+}
 void lane_argmax(int si, int T, double& best, int& best_n, double& best_use) {
     if (T == 1 || !t_team) return;
     for (int s = T >> 1; s >= 1; s >>= 1) {
@@ -169,6 +187,14 @@ void with_lanes(F&& f) {
         case 6: { constexpr int P = 6; __VA_ARGS__; } break; \
         case 7: { constexpr int P = 7; __VA_ARGS__; } break; \
         case 8: { constexpr int P = 8; __VA_ARGS__; } break; \
+        case 9: { constexpr int P = 9; __VA_ARGS__; } break; \
+        case 10: { constexpr int P = 10; __VA_ARGS__; } break; \
+        case 11: { constexpr int P = 11; __VA_ARGS__; } break; \
+        case 12: { constexpr int P = 12; __VA_ARGS__; } break; \
+        case 13: { constexpr int P = 13; __VA_ARGS__; } break; \
+        case 14: { constexpr int P = 14; __VA_ARGS__; } break; \
+        case 15: { constexpr int P = 15; __VA_ARGS__; } break; \
+        case 16: { constexpr int P = 16; __VA_ARGS__; } break; \
         default: return -3;                                \
     }
 

@@ -53,9 +53,9 @@ def test_design_too_large_is_reported(inf):
 
     from pydeseq2_b200._lib import B200Error
 
-    X = np.ones((10, 9))
-    with pytest.raises(B200Error, match="p <= 8"):
-        inf.lin_reg_mu(np.ones((10, 3), dtype=np.int64), np.ones(10), X, 0.5)
+    X = np.ones((20, 17))
+    with pytest.raises(B200Error, match="p <= 16"):
+        inf.lin_reg_mu(np.ones((20, 3), dtype=np.int64), np.ones(20), X, 0.5)
 
 
 def test_size_factors(inf):
@@ -74,7 +74,7 @@ def test_shrink_arguments(inf):
     ec.check_shrink_arguments(inf)
 
 
-@pytest.mark.parametrize("p,N", [(1, 9), (2, 13), (3, 17), (4, 21), (5, 24), (6, 27), (7, 31), (8, 35)])
+@pytest.mark.parametrize("p,N", [(1, 9), (2, 13), (3, 17), (4, 21), (5, 24), (6, 27), (7, 31), (8, 35), (9, 91), (12, 121), (16, 161)])
 def test_every_design_width(inf, p, N):
     from oracle import nbglm
 
@@ -127,3 +127,38 @@ def test_content_addressed_residency():
         del os_env["PDQ_RESIDENCY"]
     np.testing.assert_array_equal(a1, a2)
     np.testing.assert_array_equal(c1, c2)
+
+
+def test_many_samples_design_read_from_global_memory(inf):
+    """N = 8 000 (p = 3): the design pack (384 KB) exceeds any shared-memory stage; the kernels read it from global memory.
+    Every plugin method of the hot path against the oracle (reference: utils.py:273-438 has no sample limit)."""
+    import os
+
+    import numpy as np
+
+    from oracle import nbglm
+    from pydeseq2_b200.pipeline import median_of_ratios
+    from pydeseq2_b200.synth import make_counts
+
+    counts, X, _ = make_counts(8000, 64, "continuous", seed=21)
+    counts = np.ascontiguousarray(counts[:, ~(counts == 0).all(0)])
+    sf = median_of_ratios(counts)[1]
+    ora = nbglm.OracleInference(n_cpus=os.cpu_count())
+    disp = np.full(counts.shape[1], 0.2)
+    b, m, h, cv = inf.irls(counts, sf, X, disp, 0.5, 1e-8)
+    rb, rm, rh, rcv = ora.irls(counts, sf, X, disp, 0.5, 1e-8)
+    ok = (rcv == 1) & (cv == 1)
+    assert ok.mean() > 0.9
+    np.testing.assert_allclose(b[ok], rb[ok], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(m[:, ok], rm[:, ok], rtol=1e-6)
+    np.testing.assert_allclose(h[:, ok], rh[:, ok], rtol=1e-6, atol=1e-12)
+    a, ac = inf.alpha_mle(counts, X, np.ascontiguousarray(rm), disp, 1e-8, 8000.0)
+    ra, rac = ora.alpha_mle(counts, X, np.ascontiguousarray(rm), disp, 1e-8, 8000.0)
+    both = (ac == 1) & (rac == 1) & (ra > 1e-5)
+    np.testing.assert_allclose(a[both], ra[both], rtol=1e-4)
+    ridge = np.diag(np.repeat(1e-6, 3))
+    got = inf.wald_test(X, disp, rb, rm, ridge, np.array([0.0, 0.0, 1.0]), 0.0, None)
+    want = ora.wald_test(X, disp, rb, rm, ridge, np.array([0.0, 0.0, 1.0]), 0.0, None)
+    for g, w in zip(got, want):
+        np.testing.assert_allclose(g, w, rtol=1e-8, atol=1e-300)
+    np.testing.assert_allclose(inf.lin_reg_mu(counts, sf, X, 0.5), ora.lin_reg_mu(counts, sf, X, 0.5), rtol=1e-9)
