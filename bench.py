@@ -379,6 +379,30 @@ class Bench:
                 "step_wall_ms": [round(t * 1e3, 2) for t in ts],
                 "calls_ms": {k: round(v * 1e3 / steps, 3) for k, v in T.items()}}
 
+    def full_deseq2(self, counts, X, sf, G_in, steps):
+        """Second metric (N = 1): the whole `DeseqDataSet.deseq2()` of the reference (dds.py:516-562) -- the hot path PLUS
+        `calculate_cooks` and the outlier `refit` -- and the Wald test, resident: one pass with Cook's distances on the device,
+        then the replaced genes' refit on a compact resident matrix (workflow.deseq2_results_resident).  Wall clock per call."""
+        from pydeseq2_b200.pipeline import ResidentFit
+        from pydeseq2_b200.workflow import deseq2_results_resident
+
+        rf = ResidentFit(self.ctx, X, sf)
+        rf.upload(counts)
+        for _ in range(2):
+            r = deseq2_results_resident(rf, adjust=False)
+        ts = []
+        for _ in range(steps):
+            self.flush_l2()
+            t0 = time.perf_counter()
+            r = deseq2_results_resident(rf, adjust=False)
+            ts.append(time.perf_counter() - t0)
+        rf.close()
+        s = float(np.mean(ts))
+        return {"metric": "genes/sec deseq2() incl. Cook's distances + outlier refit, + Wald", "ms_per_step": s * 1e3, "genes_per_s": G_in / s,
+                "timed": "wall clock per call (counts resident; includes the host-side replacement of the flagged genes' counts)",
+                "replaced_genes": int(r.replaced.sum()), "refitted_genes": int(r.refitted.sum()),
+                "cooks_outlier_genes": int(r.cooks_outlier.sum())}
+
     def check_shards(self, rf):
         """N > 1: the sharded pass must equal a single-process fit -- (a) every rank holds the same trend record and tables,
         (b) the trend / prior of the gathered vectors recomputed by ONE rank on the concatenation (no NaN pads) agree."""
@@ -447,6 +471,8 @@ def main():
     time.sleep(0.25)  # let nvidia-smi emit at least one more sample
     clk.__exit__()
 
+    full = B.full_deseq2(counts, X, sf, G_in, max(3, min(args.steps, 10))) if world == 1 else None
+
     # ---------------------------------------------------------------- BASELINE's larger shapes, same measurement
     configs = {}
     if not args.no_extra_configs and (args.genes, args.samples, args.design) == (20000, 200, "two_level"):
@@ -484,7 +510,7 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(args), "e2e": e2e,
                 "gpu_launches": head["gpu_launches"], "clocks": clk.summary(), "roofline": head["roofline"], "cpu_baseline": cpu,
-                "stages_ms": stages, "configs": configs, "shard_check": shard_check, "device": ctx.info()["name"]}
+                "stages_ms": stages, "full_deseq2": full, "configs": configs, "shard_check": shard_check, "device": ctx.info()["name"]}
         print(json.dumps(line), flush=True)
     if B.dist is not None:
         B.dist.barrier()

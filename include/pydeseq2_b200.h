@@ -87,6 +87,18 @@ int64_t pdq_buffer_epoch(const pdq_ctx* ctx);
 int pdq_residency_stats(const pdq_ctx* ctx, int64_t* hits, int64_t* misses, int64_t* hit_bytes, int64_t* resident_bytes);
 int pdq_residency_clear(pdq_ctx* ctx);
 
+/* ---- count-matrix ingestion (the reference: pandas.read_csv(..., index_col=0).T,
+ * examples/plot_pandas_io_example.py:57-66).  Host code, no device needed.  A CSV whose header line holds the column labels and
+ * whose lines start with a row label, the remaining fields read counts (non-negative integers; labels may be double-quoted).
+ * pdq_csv_scan: number of data rows / columns and the bytes the labels need.  pdq_csv_read_counts: parse with `threads` host
+ * threads (0 = all, at most 32) into `out` -- with `transpose` the file's rows become the matrix' columns (the shipped datasets are
+ * genes x samples, the hot path consumes (samples, genes) int64, dds.py:245-249) -- e.g. a page-locked buffer from pdq_host_alloc.
+ * `labels` (may be NULL): column labels '\n'-separated, '\0', row labels '\n'-separated, '\0'.  A field that is not a non-negative
+ * integer fails the call with PDQ_ERR_INVALID and its position in bad_row / bad_col. */
+int pdq_csv_scan(const char* path, char sep, int64_t* n_rows, int64_t* n_cols, size_t* label_bytes);
+int pdq_csv_read_counts(const char* path, char sep, int transpose, int64_t* out, int64_t ld_out, int64_t n_rows, int64_t n_cols,
+                        char* labels, size_t label_cap, int threads, int64_t* bad_row, int64_t* bad_col);
+
 int pdq_malloc(pdq_ctx* ctx, size_t bytes, void** dptr);
 int pdq_free(pdq_ctx* ctx, void* dptr);
 int pdq_host_alloc(pdq_ctx* ctx, size_t bytes, void** hptr); /* pinned host memory */
@@ -185,7 +197,7 @@ int pdq_lfc_shrink_nbinom_glm(pdq_ctx* ctx, const double* X, const int64_t* coun
  * plugin calls: per-gene mean of log counts, genes holding a zero dropped, per-sample exact median
  * of log(count) - gene mean (radix select), exponentiated.  `sf_out` (N,).  All entries NaN when every gene holds a zero
  * (the reference then switches to its iterative fallback, dds.py:682-690). */
-int pdq_size_factors(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N, int G, double* sf_out);
+int pdq_size_factors(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N, int G, double* sf_out, double* logmeans_out /* per-gene mean log count (-inf when the gene holds a zero), may be NULL */);
 
 /* Cook's distances -- DeseqDataSet.calculate_cooks (dds.py:986-1040) with the trimmed-moments dispersion
  * (utils.py:914-960; cells = identical design rows with >= 3 replicates) -- and the two per-gene decisions derived from them:
@@ -255,6 +267,10 @@ int pdq_size_factors_dev(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N,
 /* Final dispersions (dds.py:918-932): clip(MAP), except genes with log(genewise) > log(fitted) + 2 sqrt(squared_logres)
  * which keep their clipped genewise value; `trend_out16` is the record written by pdq_trend_fit_dev.
  * `outlier_out` (n,) 0/1 may be NULL. */
+/* out[n, j] = in[n, idx[j]] for j < R: selected gene columns of a resident (samples, genes) array as a compact (samples, R)
+ * array -- what the Cook's outlier refit (dds.py:1301-1458) needs from the device for the few replaced genes. */
+int pdq_gather_columns_dev(pdq_ctx* ctx, const double* in, int64_t ld_in, int N, const int* idx_dev, int R, double* out,
+                           int64_t ld_out);
 int pdq_select_dispersions_dev(pdq_ctx* ctx, const double* genewise, const double* map, const double* fitted,
                                const double* trend_out16, size_t n, double min_disp, double max_disp,
                                double* disp_out, double* outlier_out);

@@ -45,6 +45,9 @@ _SIGNATURES = {
     "pdq_buffer_epoch": (C.c_int64, [c_ctx]),
     "pdq_residency_stats": (C.c_int, [c_ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pdq_residency_clear": (C.c_int, [c_ctx]),
+    "pdq_csv_scan": (C.c_int, [C.c_char_p, C.c_char, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_size_t)]),
+    "pdq_csv_read_counts": (C.c_int, [C.c_char_p, C.c_char, C.c_int, i64p, C.c_int64, C.c_int64, C.c_int64, C.c_char_p, C.c_size_t,
+                                      C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pdq_malloc": (C.c_int, [c_ctx, C.c_size_t, C.POINTER(c_dptr)]),
     "pdq_free": (C.c_int, [c_ctx, c_dptr]),
     "pdq_host_alloc": (C.c_int, [c_ctx, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -87,7 +90,7 @@ _SIGNATURES = {
                                       C.c_double, f64p, f64p, f64p, f64p]),
     "pdq_cooks_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, c_dptr, c_dptr, C.c_int64, C.c_double, c_dptr,
                                 C.c_int64, c_dptr, c_dptr, c_dptr]),
-    "pdq_size_factors": (C.c_int, [c_ctx, i64p, C.c_int64, C.c_int, C.c_int, f64p]),
+    "pdq_size_factors": (C.c_int, [c_ctx, i64p, C.c_int64, C.c_int, C.c_int, f64p, f64p]),
     "pdq_fp64_peak_tflops": (C.c_int, [c_ctx, f64p]),
     "pdq_lfc_shrink_nbinom_glm": (C.c_int, [c_ctx, f64p, i64p, C.c_int64, C.c_int, C.c_int, C.c_int, f64p, f64p, C.c_double,
                                             C.c_double, C.c_int, f64p, f64p, f64p, C.POINTER(C.c_int)]),
@@ -97,6 +100,7 @@ _SIGNATURES = {
     "pdq_dispersion_trend_gamma_glm": (C.c_int, [c_ctx, f64p, f64p, C.c_size_t, f64p, f64p, C.POINTER(C.c_int)]),
     "pdq_trend_prior": (C.c_int, [c_ctx, f64p, f64p, C.c_size_t, C.c_double, C.c_double, C.c_double, f64p, f64p]),
     "pdq_trend_fit_dev": (C.c_int, [c_ctx, c_dptr, c_dptr, C.c_size_t, C.c_double, C.c_double, C.c_double, c_dptr, c_dptr]),
+    "pdq_gather_columns_dev": (C.c_int, [c_ctx, c_dptr, C.c_int64, C.c_int, c_dptr, C.c_int, c_dptr, C.c_int64]),
     "pdq_select_dispersions_dev": (C.c_int, [c_ctx, c_dptr, c_dptr, c_dptr, c_dptr, C.c_size_t, C.c_double, C.c_double, c_dptr,
                                              c_dptr]),
     "pdq_mu_from_lfc_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int, c_dptr, C.c_int64]),

@@ -731,6 +731,14 @@ extern "C" int pdq_size_factors_dev(pdq_ctx* c, const int64_t* counts, int64_t l
     return done(c, launch_size_factors(cfg(c, G, N), counts, ld, N, G, (double*)lm, (double*)scratch, sf_out), "size_factors");
 }
 
+extern "C" int pdq_gather_columns_dev(pdq_ctx* c, const double* in, int64_t ld_in, int N, const int* idx_dev, int R, double* out,
+                                      int64_t ld_out) {
+    CHECK_CTX(c);
+    if (!in || !idx_dev || !out || N <= 0 || R < 0 || ld_out < R) return fail(c, PDQ_ERR_INVALID, "pdq_gather_columns_dev: bad arguments");
+    const int rc = launch_gather_cols(c->stream, in, ld_in, N, idx_dev, R, out, ld_out);
+    return done(c, rc, "gather_columns");
+}
+
 extern "C" int pdq_select_dispersions_dev(pdq_ctx* c, const double* genewise, const double* map, const double* fitted,
                                           const double* trend_out16, size_t n, double min_disp, double max_disp, double* disp_out,
                                           double* outlier_out) {
@@ -1393,18 +1401,21 @@ extern "C" int pdq_lfc_shrink_nbinom_glm(pdq_ctx* c, const double* X, const int6
     return PDQ_OK;
 }
 
-extern "C" int pdq_size_factors(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, double* sf_out) {
+extern "C" int pdq_size_factors(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, double* sf_out, double* logmeans_out) {
     CHECK_CTX(c);
     if (!counts || !sf_out || N <= 0 || G <= 0 || ld < G) return fail(c, PDQ_ERR_INVALID, "pdq_size_factors: bad arguments");
-    void *dc, *dsf;
+    void *dc, *dsf, *dlm = nullptr;
     res_begin(c);
     bool up_c;
     if (int e = res_input(c, counts, ld, N, G, 8, kBufCounts, &dc, &up_c)) return e;
     if (int e = ensure(c, kBufE, (size_t)N * 8, &dsf)) return e;
+    if (logmeans_out)
+        if (int e = ensure(c, kBufG, (size_t)G * 8, &dlm)) return e;
     if (up_c)
         if (int e = h2d_2d(c, dc, counts, ld, N, G, 8)) return e;
-    if (int e = pdq_size_factors_dev(c, (const int64_t*)dc, G, N, G, (double*)dsf, nullptr)) return e;
+    if (int e = pdq_size_factors_dev(c, (const int64_t*)dc, G, N, G, (double*)dsf, (double*)dlm)) return e;
     CU(c, cudaMemcpyAsync(sf_out, dsf, (size_t)N * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (logmeans_out) CU(c, cudaMemcpyAsync(logmeans_out, dlm, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
     return call_end(c, nullptr, {});
 }
 

@@ -845,6 +845,14 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// ---- selected gene columns of a resident (N, G) array into a compact (N, R) array: the outlier refit works on the few replaced
+// genes only (dds.py:1360-1458), so their mu / hat columns are all that has to leave the device
+__global__ void k_gather_cols(const double* __restrict__ in, int64_t ld_in, int N, const int* __restrict__ idx, int R,
+                              double* __restrict__ out, int64_t ld_out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+    if (j < R && n < N) out[(int64_t)n * ld_out + j] = in[(int64_t)n * ld_in + idx[j]];
+}
+
 // ---- content checksum of a device buffer: the device half of the residency cache of pdq_api.cu (host_hash there computes the
 // same two wrapping sums with host threads).  HBM-bound: 32 MB in ~10 us.
 __global__ void __launch_bounds__(256) k_hash(const uint64_t* __restrict__ w, size_t n, unsigned long long* out) {
@@ -1136,6 +1144,13 @@ int PDQ_TUFN(launch_lfc_shrink)(const LaunchCfg& c, const DesignDev& d, const in
 }
 
 #if PDQ_TU_P == 0
+int launch_gather_cols(cudaStream_t stream, const double* in, int64_t ld_in, int N, const int* idx, int R, double* out, int64_t ld_out) {
+    if (R <= 0 || N <= 0) return 0;
+    k_gather_cols<<<dim3((unsigned)((R + 127) / 128), (unsigned)N), 128, 0, stream>>>(in, ld_in, N, idx, R, out, ld_out);
+    if (int e = check_launch()) return e;
+    return 1;
+}
+
 int launch_hash(cudaStream_t stream, int sm_count, const void* dptr, size_t words, uint64_t* out2) {
     k_hash<<<sm_count * 8, 256, 0, stream>>>(reinterpret_cast<const uint64_t*>(dptr), words, reinterpret_cast<unsigned long long*>(out2));
     if (int e = check_launch()) return e;

@@ -150,9 +150,10 @@ class _CudaOps:
                                                     as_f64p(hat), ld2, cutoff, as_f64p(cooks) if cooks is not None else None,
                                                     as_f64p(disp), as_f64p(outlier), as_f64p(replaced)))
 
-    def size_factors(self, counts, ld, N, G, sf):
+    def size_factors(self, counts, ld, N, G, sf, logmeans=None):
         self._io((counts,), (sf,))
-        self.ctx.check(self.lib.pdq_size_factors(self.ctx.h, as_i64p(counts), ld, N, G, as_f64p(sf)))
+        self.ctx.check(self.lib.pdq_size_factors(self.ctx.h, as_i64p(counts), ld, N, G, as_f64p(sf),
+                                                 as_f64p(logmeans) if logmeans is not None else None))
 
     def lfc_shrink(self, X, counts, ld, N, G, p, size, offset, prior_no_shrink_scale, prior_scale, shrink_index, lfcs, inv_hessians,
                    conv):
@@ -383,7 +384,7 @@ class B200Inference(_InferenceBase):
             return None
         return np.array([out16[0], out16[1]]), fitted, float(out16[8]), float(out16[9]), int(out16[3])
 
-    def size_factors(self, counts):
+    def size_factors(self, counts, return_logmeans: bool = False):
         """Median-of-ratios size factors on the device (``preprocessing.deseq2_norm``, preprocessing.py:5-102).
 
         Not part of the ``Inference`` ABC -- the reference computes them in the orchestrator (``dds.py:584-711``) --
@@ -394,9 +395,17 @@ class B200Inference(_InferenceBase):
         counts, ld = _rows(counts, np.int64, "counts")
         N, G = counts.shape
         sf = np.empty(N)
-        self._ops.size_factors(counts, ld, N, G, sf)
+        logmeans = np.empty(G) if return_logmeans else None  # what deseq2_norm_fit returns (preprocessing.py:31-59)
+        try:
+            self._ops.size_factors(counts, ld, N, G, sf, logmeans)
+        except TypeError:  # an ops object without the logmeans output (test emulator)
+            self._ops.size_factors(counts, ld, N, G, sf)
+            with np.errstate(divide="ignore"):
+                logmeans = np.log(counts).mean(0) if return_logmeans else None
         if not np.isfinite(sf).all():
             raise ValueError("Every gene contains at least one zero, cannot compute log geometric means.")
+        if return_logmeans:
+            return counts / sf[:, None], sf, logmeans
         return counts / sf[:, None], sf
 
     def calculate_cooks(self, counts, size_factors, design_matrix, mu, hat_diagonals, return_matrix=True):

@@ -30,9 +30,11 @@ def b200_dataset_class():
                      and hasattr(self.inference, "size_factors") and isinstance(self.X, np.ndarray))
             if plain:
                 try:
-                    normed, sf = self.inference.size_factors(self.X)
+                    normed, sf, logmeans = self.inference.size_factors(self.X, return_logmeans=True)
                 except ValueError:  # every gene holds a zero: the reference switches to its iterative estimator (dds.py:682-690)
                     return super().fit_size_factors(fit_type=fit_type, control_genes=control_genes)
+                # what the reference keeps from deseq2_norm_fit (dds.py:693): vst_fit / vst_transform normalise NEW counts with them
+                self.logmeans, self.filtered_genes = logmeans, ~np.isinf(logmeans)
                 self.layers["normed_counts"] = normed
                 self.obs["size_factors"] = sf
                 self.var["_normed_means"] = normed.mean(0)

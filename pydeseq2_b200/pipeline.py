@@ -401,6 +401,7 @@ class ResidentFit:
         for name, n in (("fitted", G), ("beta0", G * p)):
             setattr(self, "d_" + name, self._dev(name, n * 8))
         self.d_nfb = self._dev("nfb", 64)
+        self._h_counts = counts  # the outlier refit (refit_subset) replaces counts of a few genes on the host
         self.ctx.h2d(self.d_counts, counts)
         self.ctx.sync()
         if self.design is None:
@@ -610,6 +611,78 @@ class ResidentFit:
             if k in out and k in names:
                 out[k] = out[k] == 1.0
         return out
+
+    # -- Cook's outlier refit on the resident state (dds.py:1301-1458) ----------------------------------------
+    def gather_columns(self, which: str, idx: np.ndarray) -> np.ndarray:
+        """Columns ``idx`` of the resident ``"mu"`` / ``"hat"`` array of the last pass as a host (N, len(idx)) array: the only (N, .)
+        data the outlier refit needs from the device."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        R = len(idx)
+        out = self.ctx.pinned_empty((self.N, R))
+        if R == 0:
+            return out
+        d_idx, d_out = self._dev("gather_idx", R * 4), self._dev("gather_out", self.N * R * 8)
+        self.ctx.h2d(d_idx, idx)
+        src = {"mu": self.d_mu, "hat": self.d_hat}[which]
+        c_d = self._lib_mod.c_dptr
+        self.ctx.check(self.lib.pdq_gather_columns_dev(self.ctx.h, c_d(src), self.G, self.N, c_d(d_idx), R, c_d(d_out), R))
+        self.ctx.d2h(out, d_out)
+        self.ctx.sync()
+        return out
+
+    def refit_subset(self, sub_counts: np.ndarray, trend: "TrendFit", prior_var: float, contrast=None, lfc_null=0.0, alt_hypothesis=None):
+        """``_refit_without_outliers`` (dds.py:1393-1458) for a few genes whose outlier counts were replaced: the same kernels as
+        :meth:`run` on the compact (N, R) matrix -- genewise dispersions from scratch, the main fit's trend FUNCTION and prior
+        (neither is re-estimated; the trend record of the last pass is still on the device), MAP dispersions, LFCs, Wald test.
+        Returns R-length per-gene results."""
+        L, ctx, h, d = self.lib, self.ctx, self.ctx.h, self.design
+        c_d = self._lib_mod.c_dptr
+        sub = np.ascontiguousarray(sub_counts, dtype=np.int64)
+        N, p = self.N, self.p
+        R = sub.shape[1]
+        assert sub.shape[0] == N and R > 0
+        if contrast is None:
+            contrast = np.zeros(p)
+            contrast[-1] = 1.0
+        contrast = np.ascontiguousarray(contrast, dtype=np.float64)
+        ridge = np.ascontiguousarray(np.diag(np.repeat(1e-6, p)))
+        ng = N * R * 8
+        dv = lambda name, nbytes: self._dev("refit_" + name, nbytes)  # noqa: E731
+        d_c, d_muhat, d_mu, d_hat = dv("counts", ng), dv("mu_hat", ng), dv("mu", ng), dv("hat", ng)
+        names = ("mom", "means", "gw", "gw_conv", "fitted", "map", "map_conv", "disp", "outl", "conv", "pv", "stat", "se")
+        d_vec = dv("vec", (len(names) + p) * R * 8)
+        dptr = {k: d_vec + i * R * 8 for i, k in enumerate(names)}
+        d_beta = d_vec + len(names) * R * 8
+        d_beta0 = dv("beta0", R * p * 8)
+        ctx.h2d(d_c, sub)
+        check = ctx.check
+        check(L.pdq_mom_dispersions_dev(h, d, c_d(d_c), R, R, self.min_disp, self.max_disp, c_d(dptr["mom"]), c_d(dptr["means"]),
+                                        self.min_mu, c_d(d_muhat) if self.lin_branch else None, R))
+        if not self.lin_branch:
+            check(L.pdq_irls_dev(h, d, c_d(d_c), R, R, c_d(dptr["mom"]), self.min_mu, self.beta_tol, -30.0, 30.0, 250, c_d(d_beta0),
+                                 c_d(d_muhat), c_d(d_hat), R, c_d(dptr["conv"]), c_d(self.d_nfb)))
+        check(L.pdq_alpha_mle_dev(h, d, c_d(d_c), R, R, c_d(d_muhat), R, c_d(dptr["mom"]), self.min_disp, self.max_disp, 1.0, None, 1, 0,
+                                  c_d(dptr["gw"]), c_d(dptr["gw_conv"])))
+        means = np.empty(R)
+        ctx.d2h(means, dptr["means"])
+        ctx.sync()
+        with np.errstate(divide="ignore"):
+            fitted = (trend.coeffs[0] + trend.coeffs[1] / means) if trend.kind == "parametric" else np.full(R, trend.coeffs[0])
+        ctx.h2d(dptr["fitted"], np.ascontiguousarray(fitted))
+        check(L.pdq_alpha_mle_dev(h, d, c_d(d_c), R, R, c_d(d_muhat), R, c_d(dptr["fitted"]), self.min_disp, self.max_disp, float(prior_var),
+                                  None, 1, 1, c_d(dptr["map"]), c_d(dptr["map_conv"])))
+        check(L.pdq_select_dispersions_dev(h, c_d(dptr["gw"]), c_d(dptr["map"]), c_d(dptr["fitted"]), c_d(self.d_t16), R, self.min_disp,
+                                           self.max_disp, c_d(dptr["disp"]), c_d(dptr["outl"])))
+        check(L.pdq_irls_wald_dev(h, d, c_d(d_c), R, R, c_d(dptr["disp"]), self.min_mu, self.beta_tol, -30.0, 30.0, 250, c_d(d_beta),
+                                  c_d(d_mu), c_d(d_hat), R, c_d(dptr["conv"]), c_d(self.d_nfb), self._lib_mod.as_f64p(ridge),
+                                  self._lib_mod.as_f64p(contrast), LN2 * lfc_null, self._lib_mod.ALT_CODES[alt_hypothesis],
+                                  c_d(dptr["pv"]), c_d(dptr["stat"]), c_d(dptr["se"])))
+        host = np.empty((len(names) + p) * R)
+        ctx.d2h(host, d_vec)
+        ctx.sync()
+        v = {k: host[i * R:(i + 1) * R] for i, k in enumerate(names)}
+        return {"normed_means": means, "genewise": np.clip(v["gw"], self.min_disp, self.max_disp), "fitted": fitted, "disp": v["disp"],
+                "lfc": host[len(names) * R:].reshape(R, p), "pvalue": v["pv"], "stat": v["stat"], "se": v["se"]}
 
     # -- apeGLM shrinkage on the resident counts ----------------------------------------------------------
     def lfc_shrink(self, result, coeff_idx: int, adapt: bool = True, se=None, prior_scale=None):

@@ -210,19 +210,7 @@ def deseq2_results(counts, X, inference, contrast=None, size_factors=None, refit
     if cooks_filter:
         pv[outlier] = np.nan
 
-    # ---- multiple testing (ds.py:486-542): global over genes
-    bm_all, pv_all = base_mean, pv
-    if comm is not None:
-        g = comm.allgather_table({"bm": base_mean, "pv": pv})
-        bm_all, pv_all = g["bm"], g["pv"]
-    if independent_filter:
-        padj = independent_filtering(bm_all, pv_all, alpha)
-    else:
-        padj = np.full(len(pv_all), np.nan)
-        ok = ~np.isnan(pv_all)
-        padj[ok] = bh_adjust(pv_all[ok])
-    if comm is not None:
-        padj = padj[comm.local_slice()]
+    padj = _adjust(base_mean, pv, independent_filter, alpha, comm)
 
     res = Deseq2Results(base_mean, lfc @ contrast / LN2, se / LN2, stat, pv, padj, lfc, disp, genewise, fitted, sf, nz, replaced, refitted,
                         outlier, cooks if keep_cooks else None, fit)
@@ -241,6 +229,121 @@ def deseq2_results(counts, X, inference, contrast=None, size_factors=None, refit
         se[nz] = np.sqrt(np.abs(np.asarray(ih)[:, k, k]))
         res.lfc, res.log2_fold_change, res.lfc_se, res.shrink_prior_scale = lfc, lfc[:, k] / LN2, se / LN2, scale
     return res
+
+
+def _adjust(base_mean, pv, independent_filter, alpha, comm=None):
+    """Multiple testing (ds.py:486-542): global over the genes of all shards."""
+    bm_all, pv_all = base_mean, pv
+    if comm is not None:
+        g = comm.allgather_table({"bm": base_mean, "pv": pv})
+        bm_all, pv_all = g["bm"], g["pv"]
+    if independent_filter:
+        padj = independent_filtering(bm_all, pv_all, alpha)
+    else:
+        padj = np.full(len(pv_all), np.nan)
+        ok = ~np.isnan(pv_all)
+        padj[ok] = bh_adjust(pv_all[ok])
+    if comm is not None:
+        padj = padj[comm.local_slice()]
+    return padj
+
+
+def deseq2_results_resident(rf, contrast=None, refit_cooks=True, min_replicates=7, cooks_filter=True, independent_filter=True,
+                            alpha=0.05, lfc_null=0.0, alt_hypothesis=None, fit_type="parametric", non_zero=None,
+                            adjust=True) -> Deseq2Results:
+    """:func:`deseq2_results` on a :class:`pipeline.ResidentFit` whose counts are already in HBM (``rf.upload(counts)``, all-zero
+    genes dropped by the caller): the hot path, Cook's distances and their per-gene decisions run in ONE resident pass; only
+    per-gene vectors come back.  For the few genes whose outlier counts get replaced (dds.py:1301-1358) the mu / hat columns are
+    gathered on the device, the replacement is decided on the host (R columns), and the refit (dds.py:1360-1458) runs resident
+    again on the compact matrix.  Multiple testing is G-length host work as in :func:`deseq2_results`.  ``non_zero``: boolean mask of
+    the uploaded genes within the caller's full gene list (all-zero genes are not fitted but take part in the independent
+    filtering with base mean 0, ds.py:486-528); the returned tables then have the full length."""
+    from scipy.stats import f as f_dist
+
+    X, N, p, G = rf.X, rf.N, rf.p, rf.G
+    sf = rf.sf
+    if contrast is None:
+        contrast = np.zeros(p)
+        contrast[-1] = 1.0
+    contrast = np.asarray(contrast, dtype=float)
+    if lfc_null < 0 and alt_hypothesis in ("greaterAbs", "lessAbs"):
+        raise ValueError(f"The alternative hypothesis being {alt_hypothesis}, please provide a positive lfc_null value (got {lfc_null}).")
+    was = rf.with_cooks
+    rf.with_cooks = True
+    try:
+        r = rf.run(contrast=contrast, lfc_null=lfc_null, alt_hypothesis=alt_hypothesis, fit_type=fit_type)
+    finally:
+        rf.with_cooks = was
+    base_mean = np.array(r["normed_means"])
+    lfc, disp = np.array(r["lfc"]), np.array(r["dispersions"])
+    genewise, fitted = np.array(r["genewise"]), np.array(r["fitted"])
+    pv, stat, se = np.array(r["pvalue"]), np.array(r["stat"]), np.array(r["se"])
+    outlier = np.array(r["cooks_outlier"], dtype=bool)
+    cutoff = f_dist.ppf(0.99, p, N - p)
+    replaced, refitted, new_zero = np.zeros(G, bool), np.zeros(G, bool), np.zeros(G, bool)
+    if refit_cooks:
+        replaceable = n_or_more_replicates(X, min_replicates)
+        if replaceable.any():
+            replaced = np.array(r["cooks_replaced"], dtype=bool)
+        if replaced.any():
+            ridx = np.flatnonzero(replaced)
+            counts = rf._h_counts
+            sub = np.ascontiguousarray(counts[:, ridx])
+            mu, hat = rf.gather_columns("mu", ridx), rf.gather_columns("hat", ridx)
+            # Cook's distances of the replaced genes (dds.py:1022-1036) from the resident mu / hat and the device's robust dispersions
+            a = np.asarray(r["robust_dispersions"])[ridx]
+            V = mu + a[None, :] * mu**2
+            ck = (sub - mu) ** 2 / V / p * (hat / (1 - hat) ** 2)
+            above = ck > cutoff
+            base = trimmed_mean_rows(sub / sf[:, None], 0.2)
+            repl = (base[None, :] * sf[:, None]).astype(int)   # truncation towards zero, like DataFrame.astype(int)
+            mask = replaceable[:, None] & above
+            new = sub.copy()
+            new[mask] = repl[mask]
+            zero_now = (new == 0).all(axis=0)
+            new_zero[ridx[zero_now]] = True
+            refitted[ridx[~zero_now]] = True
+            base_mean[new_zero] = 0.0
+            lfc[new_zero] = 0.0
+            if refitted.any():
+                q = rf.refit_subset(np.ascontiguousarray(new[:, ~zero_now]), r["trend"], r["prior_var"], contrast, lfc_null, alt_hypothesis)
+                base_mean[refitted], lfc[refitted] = q["normed_means"], q["lfc"]
+                genewise[refitted], fitted[refitted], disp[refitted] = q["genewise"], q["fitted"], q["disp"]
+                pv[refitted], stat[refitted], se[refitted] = q["pvalue"], q["stat"], q["se"]
+                # which refitted genes still lose their p-value (dds.py:1066-1110 on `replace_cooks`: distances of the replaceable
+                # samples are zeroed for refitted genes): samples in cells of 3..min_replicates-1 replicates can still flag them
+                use_for_max = n_or_more_replicates(X, 3)
+                keep = ~zero_now
+                ck_r = ck[:, keep].copy()
+                ck_r[replaceable] = 0.0
+                out_r = (ck_r[use_for_max] > cutoff).any(axis=0)
+                if out_r.any():
+                    pos = ck[:, keep][:, out_r].argmax(0)
+                    top = sub[:, keep][:, out_r][pos, np.arange(len(pos))]
+                    out_r[out_r] = (sub[:, keep][:, out_r] > top).sum(0) < 3
+                outlier[ridx[keep]] = out_r
+            if new_zero.any():
+                se[new_zero], stat[new_zero], pv[new_zero] = 0.0, 0.0, 1.0   # ds.py:355-360
+    if cooks_filter:
+        pv[outlier] = np.nan
+    nz = np.ones(G, bool)
+    if non_zero is not None:
+        nz = np.asarray(non_zero, dtype=bool)
+        assert int(nz.sum()) == G, "non_zero must select exactly the uploaded genes"
+
+        def full(v, fill):
+            out = np.full((len(nz),) + v.shape[1:], fill, dtype=v.dtype if v.dtype != bool else bool)
+            out[nz] = v
+            return out
+
+        base_mean, lfc = full(base_mean, 0.0), full(lfc, np.nan)
+        disp, genewise, fitted = full(disp, np.nan), full(genewise, np.nan), full(fitted, np.nan)
+        pv, stat, se = full(pv, np.nan), full(stat, np.nan), full(se, np.nan)
+        replaced, refitted, outlier = full(replaced, False), full(refitted, False), full(outlier, False)
+    # adjust=False stops where deseq2() + run_wald_test() + the Cook's filter stop (no independent filtering / BH: `padj` is NaN)
+    padj = _adjust(base_mean, pv, independent_filter, alpha, None) if adjust else np.full(len(pv), np.nan)
+    return Deseq2Results(base_mean, lfc @ contrast / LN2, se / LN2, stat, pv, padj, lfc, disp, genewise, fitted, sf, nz, replaced, refitted,
+                         outlier, None, None)
 
 
 def _full(v, nz, G):

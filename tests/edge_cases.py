@@ -182,7 +182,7 @@ def check_shrink_arguments(inf):
 def check_size_factors(inf):
     """Median-of-ratios on the device: same values as the reference (golden `final_size_factors` of the reference's
     shipped datasets and seeded inputs), and -- the north star's criterion -- bit-identical RANKS across samples."""
-    from pydeseq2_b200.pipeline import median_of_ratios
+    from oracle import nbglm  # the checker: restatement of preprocessing.py:5-102, pinned against the reference's goldens
 
     for name in ("tape_single_factor", "tape_continuous", "tape_wide"):
         t = load_golden(name)
@@ -191,11 +191,15 @@ def check_size_factors(inf):
         np.testing.assert_array_equal(np.argsort(np.argsort(sf)), np.argsort(np.argsort(t["final_size_factors"])))
     for N, G, seed in ((200, 3000, 0), (37, 501, 1), (8, 64, 2)):
         counts, _, _ = make_counts(N, G, "two_level", seed)
-        want_normed, want = median_of_ratios(counts)  # numpy restatement of preprocessing.py (== oracle)
-        normed, sf = inf.size_factors(counts)
+        want_normed, want = nbglm.deseq2_norm(counts)
+        normed, sf, logmeans = inf.size_factors(counts, return_logmeans=True)
         np.testing.assert_allclose(sf, want, rtol=1e-12)
         np.testing.assert_array_equal(np.argsort(np.argsort(sf)), np.argsort(np.argsort(want)))
         np.testing.assert_allclose(normed, want_normed, rtol=1e-12)
+        with np.errstate(divide="ignore"):  # deseq2_norm_fit's first output (preprocessing.py:31-59), -inf for genes holding a zero
+            want_lm = np.log(counts).mean(0)
+        np.testing.assert_array_equal(np.isinf(logmeans), np.isinf(want_lm))
+        np.testing.assert_allclose(logmeans[~np.isinf(want_lm)], want_lm[~np.isinf(want_lm)], rtol=1e-12)
     # every gene holds a zero -> ValueError, like dds.fit_size_factors' fallback trigger
     bad = np.array([[0, 3, 5], [2, 0, 1], [4, 1, 0]], dtype=np.int64)
     with pytest.raises(ValueError, match="at least one zero"):

@@ -109,8 +109,11 @@ class EmuOps:
         self.last_status = status
         return int((status != 0).sum())
 
-    def size_factors(self, counts, ld, N, G, sf):
+    def size_factors(self, counts, ld, N, G, sf, logmeans=None):
         assert self.lib.emu_size_factors(_p(counts, i64p), C.c_int64(ld), N, G, _p(sf, f64p)) == 0
+        if logmeans is not None:  # per-gene mean log count: the emulator entry returns the size factors only
+            with np.errstate(divide="ignore"):
+                logmeans[:] = np.log(np.asarray(counts)[:, :G]).mean(0)
 
     def cooks(self, counts, ld, N, G, sf, X, p, mu, hat, ld2, cutoff, cooks, disp, outlier, replaced):
         assert self.lib.emu_cooks(_p(counts, i64p), C.c_int64(ld), N, G, _p(sf, f64p), _p(X, f64p), p, _p(mu, f64p), _p(hat, f64p),

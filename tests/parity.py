@@ -177,7 +177,7 @@ def assert_mostly_close(got, want, rtol, what, atol=0.0, max_frac=0.0, slack=100
     assert_close(got, want, slack * rtol, what + " (outside the mismatch budget)", atol=slack * atol)
 
 
-def check_e2e(inf, g, rtol, name="", max_frac=0.0):
+def check_e2e(inf, g, rtol, name="", max_frac=0.0, resident=False):
     """`workflow.deseq2_results` (deseq2() + summary(): refit of Cook's outliers, Cook's / independent filtering, BH) against the
     final tables of the real orchestrator (oracle/make_golden.py `gen_e2e`, `gen_tape`)."""
     from pydeseq2_b200.workflow import deseq2_results
@@ -189,7 +189,21 @@ def check_e2e(inf, g, rtol, name="", max_frac=0.0):
         kw.update(alt_hypothesis=str(g["alt_hypothesis"]) or None, lfc_null=float(g["lfc_null"]))
     if "fit_type" in g:
         kw.update(fit_type=str(g["fit_type"]), refit_cooks=bool(g["refit_cooks"]))
-    r = deseq2_results(g["counts"], g["design"], inf, g["contrast"], **kw)
+    if resident:  # counts in HBM, one resident pass + resident refit of the replaced genes (workflow.deseq2_results_resident)
+        from pydeseq2_b200.pipeline import ResidentFit
+        from pydeseq2_b200.workflow import deseq2_results_resident
+
+        counts = np.ascontiguousarray(g["counts"], dtype=np.int64)
+        nz = ~(counts == 0).all(0)
+        rf = ResidentFit(inf._ops.ctx, g["design"], None)  # size factors by median of ratios on the device
+        rf.upload(np.ascontiguousarray(counts[:, nz]))
+        try:
+            r = deseq2_results_resident(rf, g["contrast"], non_zero=nz, **kw)
+        finally:
+            rf.close()
+        name = name + " [resident]"
+    else:
+        r = deseq2_results(g["counts"], g["design"], inf, g["contrast"], **kw)
     # decisions first: they are discrete, so they must agree exactly
     np.testing.assert_array_equal(r.replaced, g["final_replaced"] == 1, err_msg="replaced genes")
     if "final_refitted" in g:

@@ -213,3 +213,14 @@ def test_end_to_end_tables_match_the_real_orchestrator(inf, name):
     """deseq2() + summary() through `workflow.deseq2_results` on the GPU backend -- outlier refit, Cook's filtering, independent
     filtering / BH included -- against the final tables the real reference produced (tests/golden/tape_*, e2e_*)."""
     check_e2e(inf, load_golden(name), RTOL, name, max_frac=0.005)
+
+
+@pytest.mark.parametrize("name", TAPES_E2E + E2E)
+def test_end_to_end_tables_resident_workflow(inf, name):
+    """The same final tables from the RESIDENT workflow: counts uploaded once, one resident pass (hot path + Cook's distances and
+    their per-gene decisions), the outlier refit of the few replaced genes resident on a compact matrix, only per-gene vectors and
+    the replaced genes' mu / hat columns crossing PCIe (workflow.deseq2_results_resident)."""
+    g = load_golden(name)
+    if len(np.unique(g["design"], axis=0)) == 0:
+        pytest.skip("degenerate design")
+    check_e2e(inf, g, RTOL, name, max_frac=0.005, resident=True)

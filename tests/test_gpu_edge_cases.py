@@ -162,3 +162,22 @@ def test_many_samples_design_read_from_global_memory(inf):
     for g, w in zip(got, want):
         np.testing.assert_allclose(g, w, rtol=1e-8, atol=1e-300)
     np.testing.assert_allclose(inf.lin_reg_mu(counts, sf, X, 0.5), ora.lin_reg_mu(counts, sf, X, 0.5), rtol=1e-9)
+
+
+def test_csv_ingestion_into_pinned_memory(inf, tmp_path):
+    """pydeseq2_b200.io: a genes-x-samples CSV parsed by native host threads into a page-locked (samples, genes) matrix that the
+    plugin calls consume as it is."""
+    import numpy as np
+    import pandas as pd
+
+    from pydeseq2_b200.io import read_counts_csv
+    from pydeseq2_b200.synth import make_counts
+
+    counts, X, _ = make_counts(24, 300, "two_level", seed=5)
+    p = tmp_path / "counts.csv"
+    pd.DataFrame(counts.T, index=[f"g{i}" for i in range(300)], columns=[f"s{j}" for j in range(24)]).to_csv(p)
+    tab = read_counts_csv(p, ctx=inf._ops.ctx)
+    np.testing.assert_array_equal(tab.counts, counts)
+    assert tab.samples[0] == "s0" and tab.genes[-1] == "g299"
+    sf = np.ones(24)
+    np.testing.assert_array_equal(inf.lin_reg_mu(tab.counts, sf, X, 0.5), inf.lin_reg_mu(counts, sf, X, 0.5))
