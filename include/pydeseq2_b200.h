@@ -231,6 +231,17 @@ int pdq_alpha_mle_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* cou
                       double max_disp, double prior_disp_var,
                       const double* prior_var_dev /* device double overriding prior_disp_var, may be NULL */,
                       int cr_reg, int prior_reg, double* alpha_out, double* converged_out);
+/* pdq_alpha_mle_dev with a carried-over search state.  `hint_out` (device, [G][2], may be NULL) receives per gene the optimum
+ * x* = log(alpha) this search found and the curvature h* of its loss there; `hint_in` (may be NULL) takes such a record from an
+ * earlier search on the SAME counts and means WITHOUT the prior -- the genewise fit, dds.py:778 -- so that the MAP search
+ * (dds.py:901; objective = that loss + (x - log alpha_hat)^2 / (2 var)) opens with a Newton step of the MAP objective from x*
+ * instead of walking in from log(alpha_hat): ~2.2 evaluations per gene instead of ~3.5, same optimum (the start point is still
+ * evaluated first: the reference's rules that keep a gene at its start value are applied unchanged). */
+int pdq_alpha_mle_hint_dev(pdq_ctx* ctx, const pdq_design* design, const int64_t* counts, int64_t ld, int G,
+                           const double* mu, int64_t ld_mu, const double* alpha_hat, double min_disp,
+                           double max_disp, double prior_disp_var, const double* prior_var_dev, int cr_reg,
+                           int prior_reg, double* alpha_out, double* converged_out, const double* hint_in,
+                           double* hint_out);
 int pdq_wald_test_dev(pdq_ctx* ctx, const pdq_design* design, const double* disp, const double* lfc,
                       const double* mu, int64_t ld_mu, int G, const double* ridge_host,
                       const double* contrast_host, double lfc_null, int alt, double* pvalue_out,

@@ -82,6 +82,8 @@ _SIGNATURES = {
                                     C.c_double, C.c_int, c_dptr, c_dptr, c_dptr]),
     "pdq_alpha_mle_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, c_dptr, C.c_int64, c_dptr, C.c_double,
                                     C.c_double, C.c_double, c_dptr, C.c_int, C.c_int, c_dptr, c_dptr]),
+    "pdq_alpha_mle_hint_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, c_dptr, C.c_int64, c_dptr, C.c_double,
+                                         C.c_double, C.c_double, c_dptr, C.c_int, C.c_int, c_dptr, c_dptr, c_dptr, c_dptr]),
     "pdq_wald_test_dev": (C.c_int, [c_ctx, c_design, c_dptr, c_dptr, c_dptr, C.c_int64, C.c_int, f64p, f64p, C.c_double,
                                     C.c_int, c_dptr, c_dptr, c_dptr]),
     "pdq_mom_dispersions_dev": (C.c_int, [c_ctx, c_design, c_dptr, C.c_int64, C.c_int, C.c_double, C.c_double, c_dptr,

@@ -621,9 +621,10 @@ extern "C" int pdq_irls_wald_dev(pdq_ctx* c, const pdq_design* d, const int64_t*
                 "irls+wald");
 }
 
-extern "C" int pdq_alpha_mle_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, const double* mu,
+static int alpha_mle_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, const double* mu,
                                  int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp, double prior_disp_var,
-                                 const double* prior_var_dev, int cr_reg, int prior_reg, double* alpha, double* conv) {
+                                 const double* prior_var_dev, int cr_reg, int prior_reg, double* alpha, double* conv,
+                         const double* hint_in, double* hint_out) {
     CHECK_CTX(c);
     if (!d || !counts || !mu || !alpha_hat || !alpha || !conv || G <= 0 || ld < G || ld_mu < G)
         return fail(c, PDQ_ERR_INVALID, "pdq_alpha_mle_dev: bad arguments");
@@ -631,7 +632,22 @@ extern "C" int pdq_alpha_mle_dev(pdq_ctx* c, const pdq_design* d, const int64_t*
     void* status;
     if (int e = ensure(c, kBufStatus, (size_t)G * sizeof(int), &status)) return e;
     return done(c, launch_alpha_mle(cfg(c, G, d->d.N), d->d, counts, ld, G, mu, ld_mu, alpha_hat, min_disp, max_disp, prior_disp_var,
-                                    prior_var_dev, cr_reg, prior_reg, alpha, conv, (int*)status), "alpha_mle");
+                                    prior_var_dev, cr_reg, prior_reg, alpha, conv, (int*)status, hint_in, hint_out), "alpha_mle");
+}
+
+extern "C" int pdq_alpha_mle_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, const double* mu,
+                                 int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp, double prior_disp_var,
+                                 const double* prior_var_dev, int cr_reg, int prior_reg, double* alpha, double* conv) {
+    return alpha_mle_dev(c, d, counts, ld, G, mu, ld_mu, alpha_hat, min_disp, max_disp, prior_disp_var, prior_var_dev, cr_reg, prior_reg, alpha,
+                         conv, nullptr, nullptr);
+}
+
+extern "C" int pdq_alpha_mle_hint_dev(pdq_ctx* c, const pdq_design* d, const int64_t* counts, int64_t ld, int G, const double* mu,
+                                      int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp, double prior_disp_var,
+                                      const double* prior_var_dev, int cr_reg, int prior_reg, double* alpha, double* conv,
+                                      const double* hint_in, double* hint_out) {
+    return alpha_mle_dev(c, d, counts, ld, G, mu, ld_mu, alpha_hat, min_disp, max_disp, prior_disp_var, prior_var_dev, cr_reg, prior_reg, alpha,
+                         conv, hint_in, hint_out);
 }
 
 extern "C" int pdq_wald_test_dev(pdq_ctx* c, const pdq_design* d, const double* disp, const double* lfc, const double* mu,

@@ -42,13 +42,13 @@ int launch_irls(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, i
 
 #define DECL_ALPHA(sfx)                                                                                                          \
     int launch_alpha_mle##sfx(const LaunchCfg&, const DesignDev&, const int64_t*, int64_t, int, const double*, int64_t, const double*, \
-                              double, double, double, const double*, int, int, double*, double*, int*);
+                              double, double, double, const double*, int, int, double*, double*, int*, const double*, double*);
 PDQ_UNITS(DECL_ALPHA)
 int launch_alpha_mle(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G, const double* mu, int64_t ld_mu,
                      const double* alpha_hat, double min_disp, double max_disp, double prior_var, const double* prior_var_dev, int cr_reg,
-                     int prior_reg, double* alpha, double* conv, int* status) {
+                     int prior_reg, double* alpha, double* conv, int* status, const double* hint_in, double* hint_out) {
     PDQ_ROUTE(launch_alpha_mle, d.p, c, d, counts, ld, G, mu, ld_mu, alpha_hat, min_disp, max_disp, prior_var, prior_var_dev, cr_reg,
-              prior_reg, alpha, conv, status)
+              prior_reg, alpha, conv, status, hint_in, hint_out)
 }
 
 #define DECL_WALD(sfx)                                                                                                          \

@@ -1100,7 +1100,13 @@ constexpr int kAlphaNeedsGrid = 1;  // the reference's `res.success == False` br
 template <int P>
 PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& prm, const int64_t* y, int64_t ld,
                        const double* mu, int64_t ld_mu, double alpha_hat, double* alpha_out, double* conv_out,
-                       int* status_out, bool valid, double* psi_tab) {
+                       int* status_out, bool valid, double* psi_tab, const double* hint_in = nullptr, double* hint_out = nullptr) {
+    // hint_in = [x*, h*] of an EARLIER search on the same counts and means without the prior (the genewise fit, whose optimum x*
+    // = log alpha and curvature h* of its loss there carry over): the MAP objective is that loss plus (x - xhat)^2 / (2 var), so
+    // one Newton step of it from x* lands within ~1e-3 of the MAP optimum, and a second one, with the curvature h* + 1/var,
+    // usually ends the search: ~2.2 evaluations instead of 3.5.  The start point x0 = log(alpha_hat) is still evaluated first:
+    // the rules that keep a gene AT its start (flat tail, bounds; see below) are the reference's and do not depend on the hint.
+    // hint_out receives [x, h] of this search (h = slope of dloss between its last two evaluations, NaN when unavailable).
     const double xhat = log(alpha_hat);
     const double tolx = 1e-5;   // last secant step is taken unevaluated: final error << tolx
     // scipy's L-BFGS-B declares convergence as soon as the projected gradient is <= pgtol = 1e-5 (checked at the
@@ -1115,6 +1121,8 @@ PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& pr
     bool have_br = false, active = true, fail = false;
     double xres = xb, xt = xb;
     int stall = 0;
+    bool use_hint = false;
+    double hint_h = 0.0;
     // decide the first trial point
     if (!(gb == gb)) {
         fail = true;
@@ -1135,6 +1143,14 @@ PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& pr
             if (fabs(s) < 1.0) step = s;
         }
         xt = fmin(fmax(xb + step, prm.lo), prm.hi);
+        if (hint_in != nullptr) {
+            const double hx = hint_in[0];
+            hint_h = hint_in[1] + (prm.prior_reg ? 1.0 / prm.prior_var : 0.0);
+            const double xp = hx - (prm.prior_reg ? (hx - xhat) / prm.prior_var : 0.0) / hint_h;
+            // usable: finite, positive curvature, inside the box, and on the downhill side of the start point
+            use_hint = (hint_h > 0.0) && (hint_h < 1e300) && (xp > prm.lo) && (xp < prm.hi) && ((xp - xb) * gb < 0.0);
+            if (use_hint) xt = xp;
+        }
         if (fabs(xt - xb) <= tolx) {  // already there: take the step unevaluated, like the last secant step
             xres = xt;
             active = false;
@@ -1176,7 +1192,12 @@ PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& pr
         // next point
         const double dx = xb - xa, dg = gb - ga;
         double xn;
-        if (have_br) {
+        if (use_hint && ev == 0) {
+            // the hinted point has just been evaluated: Newton step with the carried-over curvature (the secant through the far
+            // start point would be a poor slope); inside a bracket it must stay inside, else bisect like below
+            xn = fmin(fmax(xb - gb / hint_h, prm.lo), prm.hi);
+            if (have_br && !((xn > bl) && (xn < br))) xn = 0.5 * (bl + br);
+        } else if (have_br) {
             xn = xb - gb * dx / dg;
             // Brent-style safeguard: fall back to bisection when the secant point leaves the bracket or
             // the steps have not been shrinking for two evaluations in a row
@@ -1209,6 +1230,10 @@ PDQ_HD void alpha_gene(const Group& grp, const DesignS& d, const AlphaParams& pr
         xt = xn;
     }
     if (active) fail = true;  // evaluation budget exhausted
+    if (hint_out != nullptr && valid && grp.si == 0) {
+        hint_out[0] = xres;
+        hint_out[1] = (xb != xa) ? (gb - ga) / (xb - xa) : __builtin_nan("");
+    }
     if (valid && grp.si == 0) {
         *alpha_out = exp(xres);
         *conv_out = fail ? 0.0 : 1.0;

@@ -54,7 +54,8 @@ int launch_irls(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64
                 int* n_fallback, const WaldHost* wald = nullptr);
 int launch_alpha_mle(const LaunchCfg&, const DesignDev&, const int64_t* counts, int64_t ld, int G, const double* mu,
                      int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp, double prior_var,
-                     const double* prior_var_dev, int cr_reg, int prior_reg, double* alpha, double* conv, int* status);
+                     const double* prior_var_dev, int cr_reg, int prior_reg, double* alpha, double* conv, int* status,
+                     const double* hint_in = nullptr, double* hint_out = nullptr);
 int launch_wald(const LaunchCfg&, const DesignDev&, const double* disp, const double* lfc, const double* mu,
                 int64_t ld_mu, int G, const double* ridge, const double* contrast, double lfc_null, int alt,
                 double* pv, double* stat, double* se);

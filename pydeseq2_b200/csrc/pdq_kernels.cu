@@ -281,6 +281,8 @@ struct AlphaArgs {
     const double* prior_var_dev;  // when set, overrides prm.prior_var (written by k_trend_prior on the same stream)
     int* ticket;                  // [0] tile counter of the persistent scheduler, [1] genes flagged for the grid (zeroed before)
     int force;                    // test hook: flag every gene for the grid fallback
+    const double* hint_in;        // [G][2] (x*, h*) of the prior-free search on the same counts / means, or nullptr (alpha_gene)
+    double* hint_out;             // [G][2] written by this search, or nullptr
 };
 
 template <int P, bool STAGED>
@@ -300,7 +302,8 @@ __global__ void __launch_bounds__(kBlock, PDQ_ALPHA_MINB) k_alpha_mle(const __gr
     int ahead = draw_ticket(a.ticket);
     while (next_tile(a.ticket, a.lgT, a.G, grp, g, valid, ahead)) {
         alpha_gene<P>(grp, d, prm, a.counts + g, a.ld, a.mu + g, a.ld_mu, a.alpha_hat[g], a.alpha + g, a.conv + g,
-                      a.status + g, valid, psi);
+                      a.status + g, valid, psi, a.hint_in ? a.hint_in + 2 * (int64_t)g : nullptr,
+                      a.hint_out ? a.hint_out + 2 * (int64_t)g : nullptr);
         if (valid && grp.si == 0) {
             if (a.force) {
                 a.status[g] = kAlphaNeedsGrid;
@@ -955,11 +958,11 @@ int PDQ_TUFN(launch_irls)(const LaunchCfg& c, const DesignDev& d, const int64_t*
 int PDQ_TUFN(launch_alpha_mle)(const LaunchCfg& c, const DesignDev& d, const int64_t* counts, int64_t ld, int G,
                      const double* mu, int64_t ld_mu, const double* alpha_hat, double min_disp, double max_disp,
                      double prior_var, const double* prior_var_dev, int cr_reg, int prior_reg, double* alpha, double* conv,
-                     int* status) {
+                     int* status, const double* hint_in, double* hint_out) {
     PDQ_DISPATCH_P(d.p, {
         AlphaArgs<P> a{{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0}, AlphaParams{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg},
                        counts, ld, G, c.lgT, mu, ld_mu, alpha_hat, alpha, conv, status, prior_var_dev, c.tickets + 2,
-                       (c.debug & PDQ_DEBUG_FORCE_ALPHA_GRID) ? 1 : 0};
+                       (c.debug & PDQ_DEBUG_FORCE_ALPHA_GRID) ? 1 : 0, hint_in, hint_out};
         const size_t smem_alpha = d.smem_bytes + kMathTabBytes + (size_t)kWarps * (32 >> c.lgT) * 2 * kPsiK * sizeof(double);
         if (int e = prep(k_alpha_grid<P>, d.smem_bytes)) return e;
         if (cudaMemsetAsync(c.tickets + 2, 0, 2 * sizeof(int), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;

@@ -314,6 +314,7 @@ class ResidentFit:
         self.use_graph = True         # replay the pass as one CUDA graph after the first eager pass
         self.fuse_wald = True         # Wald test inside the LFC-fit launch (False: the two plugin-shaped calls in sequence)
         self.gather = comm is not None  # end the pass with the all-gather of the result tables of all gene shards
+        self.use_hint = True          # MAP dispersion search opened from the genewise optimum + curvature (pdq_alpha_mle_hint_dev)
         self._graph, self._graph_key, self._eager_key, self._graph_epoch = None, None, None, -1
         self.design = None
         self.sf = None
@@ -398,7 +399,7 @@ class ResidentFit:
         self.d_t16, self._h["t16"] = self.d_slab + off * 8, self._h_slab[off:off + 16]
         self._h_slab[off:off + 16] = 0.0
         self.ctx.h2d(self.d_slab, self._h_slab)  # NaN pads (and zeros) land on the device once
-        for name, n in (("fitted", G), ("beta0", G * p)):
+        for name, n in (("fitted", G), ("beta0", G * p), ("hint", 2 * G)):
             setattr(self, "d_" + name, self._dev(name, n * 8))
         self.d_nfb = self._dev("nfb", 64)
         self._h_counts = counts  # the outlier refit (refit_subset) replaces counts of a few genes on the host
@@ -482,8 +483,10 @@ class ResidentFit:
                                      c_d(self.d_nfb)))
             # 3. genewise dispersions (dds.py:778-797)
             begin("alpha_mle_genewise")
-            check(L.pdq_alpha_mle_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(self.d_mom), self.min_disp,
-                                      self.max_disp, 1.0, None, 1, 0, c_d(self.d_gw), c_d(self.d_gw_conv)))
+            #    (its optimum and curvature per gene are kept on the device: the MAP search of step 5 opens from them)
+            check(L.pdq_alpha_mle_hint_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(self.d_mom), self.min_disp,
+                                           self.max_disp, 1.0, None, 1, 0, c_d(self.d_gw), c_d(self.d_gw_conv), None,
+                                           c_d(self.d_hint) if self.use_hint else None))
             # 4. trend + prior: global over ALL genes of ALL shards (dds.py:799-884).  With gene shards the per-gene
             #    vectors are all-gathered over NCCL first, device to device; the fit itself is one cluster launch.
             if self.comm is not None:
@@ -507,7 +510,7 @@ class ResidentFit:
 
         # The pass is ~20 launches + copies with no host synchronisation in between: after one eager pass (which allocates
         # every buffer) the identical sequence is captured into a CUDA graph and replayed with a single call.
-        key = (fit_type, contrast.tobytes(), float(lfc_null), alt_hypothesis, G, self.with_cooks, n_all, self.fuse_wald)
+        key = (fit_type, contrast.tobytes(), float(lfc_null), alt_hypothesis, G, self.with_cooks, n_all, self.fuse_wald, self.use_hint)
         # a captured pass holds pointers into context-owned scratch (per-gene status words, trend scratch); host-buffer calls on the
         # same context may have re-allocated it since: the context counts re-allocations, a stale graph is dropped and re-captured
         if events:
@@ -661,16 +664,17 @@ class ResidentFit:
         if not self.lin_branch:
             check(L.pdq_irls_dev(h, d, c_d(d_c), R, R, c_d(dptr["mom"]), self.min_mu, self.beta_tol, -30.0, 30.0, 250, c_d(d_beta0),
                                  c_d(d_muhat), c_d(d_hat), R, c_d(dptr["conv"]), c_d(self.d_nfb)))
-        check(L.pdq_alpha_mle_dev(h, d, c_d(d_c), R, R, c_d(d_muhat), R, c_d(dptr["mom"]), self.min_disp, self.max_disp, 1.0, None, 1, 0,
-                                  c_d(dptr["gw"]), c_d(dptr["gw_conv"])))
+        d_hint = dv("hint", 2 * R * 8)
+        check(L.pdq_alpha_mle_hint_dev(h, d, c_d(d_c), R, R, c_d(d_muhat), R, c_d(dptr["mom"]), self.min_disp, self.max_disp, 1.0, None, 1, 0,
+                                       c_d(dptr["gw"]), c_d(dptr["gw_conv"]), None, c_d(d_hint)))
         means = np.empty(R)
         ctx.d2h(means, dptr["means"])
         ctx.sync()
         with np.errstate(divide="ignore"):
             fitted = (trend.coeffs[0] + trend.coeffs[1] / means) if trend.kind == "parametric" else np.full(R, trend.coeffs[0])
         ctx.h2d(dptr["fitted"], np.ascontiguousarray(fitted))
-        check(L.pdq_alpha_mle_dev(h, d, c_d(d_c), R, R, c_d(d_muhat), R, c_d(dptr["fitted"]), self.min_disp, self.max_disp, float(prior_var),
-                                  None, 1, 1, c_d(dptr["map"]), c_d(dptr["map_conv"])))
+        check(L.pdq_alpha_mle_hint_dev(h, d, c_d(d_c), R, R, c_d(d_muhat), R, c_d(dptr["fitted"]), self.min_disp, self.max_disp,
+                                       float(prior_var), None, 1, 1, c_d(dptr["map"]), c_d(dptr["map_conv"]), c_d(d_hint), None))
         check(L.pdq_select_dispersions_dev(h, c_d(dptr["gw"]), c_d(dptr["map"]), c_d(dptr["fitted"]), c_d(self.d_t16), R, self.min_disp,
                                            self.max_disp, c_d(dptr["disp"]), c_d(dptr["outl"])))
         check(L.pdq_irls_wald_dev(h, d, c_d(d_c), R, R, c_d(dptr["disp"]), self.min_mu, self.beta_tol, -30.0, 30.0, 250, c_d(d_beta),
@@ -724,9 +728,10 @@ class ResidentFit:
         H = self._h
         # 5. MAP dispersions (dds.py:886-935); the prior variance is read from device memory (written by the trend kernel)
         begin("alpha_mle_map")
-        check(L.pdq_alpha_mle_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(d_fitted), self.min_disp,
-                                  self.max_disp, prior_var if d_prior_var is None else 1.0,
-                                  c_d(d_prior_var) if d_prior_var is not None else None, 1, 1, c_d(self.d_map), c_d(self.d_map_conv)))
+        check(L.pdq_alpha_mle_hint_dev(h, d, c_d(self.d_counts), G, G, c_d(self.d_mu_hat), G, c_d(d_fitted), self.min_disp,
+                                       self.max_disp, prior_var if d_prior_var is None else 1.0,
+                                       c_d(d_prior_var) if d_prior_var is not None else None, 1, 1, c_d(self.d_map), c_d(self.d_map_conv),
+                                       c_d(self.d_hint) if self.use_hint else None, None))
         # final dispersions: clip(MAP), outlier genes keep the genewise value (dds.py:918-932)
         begin("select_dispersions")
         check(L.pdq_select_dispersions_dev(h, c_d(self.d_gw), c_d(self.d_map), c_d(d_fitted), c_d(d_t16), G, self.min_disp,

@@ -237,16 +237,29 @@ int emu_irls(const int64_t* counts, int64_t ld, int N, int G, const double* sf, 
     return 0;
 }
 
+int emu_alpha_mle_hint(const int64_t* counts, int64_t ld, int N, int G, const double* X, int p, const double* mu, int64_t ld_mu,
+                       const double* alpha_hat, double min_disp, double max_disp, double prior_var, int cr_reg, int prior_reg,
+                       double* alpha, double* conv, int* status, int force_grid, const double* hint_in, double* hint_out);
+
 int emu_alpha_mle(const int64_t* counts, int64_t ld, int N, int G, const double* X, int p, const double* mu, int64_t ld_mu,
                   const double* alpha_hat, double min_disp, double max_disp, double prior_var, int cr_reg, int prior_reg,
                   double* alpha, double* conv, int* status, int force_grid) {
+    return emu_alpha_mle_hint(counts, ld, N, G, X, p, mu, ld_mu, alpha_hat, min_disp, max_disp, prior_var, cr_reg, prior_reg, alpha, conv,
+                              status, force_grid, nullptr, nullptr);
+}
+
+// hint_in / hint_out: [G][2], see alpha_gene
+int emu_alpha_mle_hint(const int64_t* counts, int64_t ld, int N, int G, const double* X, int p, const double* mu, int64_t ld_mu,
+                       const double* alpha_hat, double min_disp, double max_disp, double prior_var, int cr_reg, int prior_reg,
+                       double* alpha, double* conv, int* status, int force_grid, const double* hint_in, double* hint_out) {
     Pack k = make_pack(X, nullptr, N, p);
     EMU_DISPATCH(p, {
         const AlphaParams prm{log(min_disp), log(max_disp), prior_var, cr_reg, prior_reg};
         double psi[2 * kPsiK];
         for (int g = 0; g < G; ++g) {
             with_lanes([&](const Group& grp) {
-                alpha_gene<P>(grp, k.d, prm, counts + g, ld, mu + g, ld_mu, alpha_hat[g], alpha + g, conv + g, status + g, true, psi);
+                alpha_gene<P>(grp, k.d, prm, counts + g, ld, mu + g, ld_mu, alpha_hat[g], alpha + g, conv + g, status + g, true, psi,
+                              hint_in ? hint_in + 2 * g : nullptr, hint_out ? hint_out + 2 * g : nullptr);
             });
             if (force_grid) {
                 status[g] = kAlphaNeedsGrid;
