@@ -282,6 +282,13 @@ int pdq_size_factors_dev(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N,
  * array -- what the Cook's outlier refit (dds.py:1301-1458) needs from the device for the few replaced genes. */
 int pdq_gather_columns_dev(pdq_ctx* ctx, const double* in, int64_t ld_in, int N, const int* idx_dev, int R, double* out,
                            int64_t ld_out);
+/* Gene order of a resident shard.  pdq_column_sums_dev: per-gene total count (device, G doubles).  pdq_scatter_rows_dev:
+ * out[v][perm[j]][k] = in[v][j][k] for `nvec` blocks of `stride` rows of `width` doubles -- per-gene results computed in a
+ * device-friendly gene order (ResidentFit sorts the columns by total count at upload: the four genes a warp iterates in lock
+ * step then need similar iteration counts) returned to the caller's order. */
+int pdq_column_sums_dev(pdq_ctx* ctx, const int64_t* counts, int64_t ld, int N, int G, double* sums_out);
+int pdq_scatter_rows_dev(pdq_ctx* ctx, const double* in, double* out, const int* perm_dev, int n, int nvec, int64_t stride,
+                         int width);
 int pdq_select_dispersions_dev(pdq_ctx* ctx, const double* genewise, const double* map, const double* fitted,
                                const double* trend_out16, size_t n, double min_disp, double max_disp,
                                double* disp_out, double* outlier_out);

@@ -755,6 +755,18 @@ extern "C" int pdq_gather_columns_dev(pdq_ctx* c, const double* in, int64_t ld_i
     return done(c, rc, "gather_columns");
 }
 
+extern "C" int pdq_column_sums_dev(pdq_ctx* c, const int64_t* counts, int64_t ld, int N, int G, double* sums_out) {
+    CHECK_CTX(c);
+    if (!counts || !sums_out || N <= 0 || G <= 0 || ld < G) return fail(c, PDQ_ERR_INVALID, "pdq_column_sums_dev: bad arguments");
+    return done(c, launch_column_sums(c->stream, counts, ld, N, G, sums_out), "column_sums");
+}
+
+extern "C" int pdq_scatter_rows_dev(pdq_ctx* c, const double* in, double* out, const int* perm_dev, int n, int nvec, int64_t stride, int width) {
+    CHECK_CTX(c);
+    if (!in || !out || !perm_dev || n < 0 || nvec < 1 || width < 1 || stride < n) return fail(c, PDQ_ERR_INVALID, "pdq_scatter_rows_dev: bad arguments");
+    return done(c, launch_scatter_rows(c->stream, in, out, perm_dev, n, nvec, stride, width), "scatter_rows");
+}
+
 extern "C" int pdq_select_dispersions_dev(pdq_ctx* c, const double* genewise, const double* map, const double* fitted,
                                           const double* trend_out16, size_t n, double min_disp, double max_disp, double* disp_out,
                                           double* outlier_out) {

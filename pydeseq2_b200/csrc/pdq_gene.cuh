@@ -432,6 +432,9 @@ template <int P>
 PDQ_HD void irls_sweep(const Group& grp, const DesignS& d, const int64_t* y, int64_t ld, const double (&beta)[P],
                        double alpha, double r, double min_mu, double log_min_mu, Sym<P>& A, double (&b)[P],
                        double& S, bool few_rows) {
+#if defined(PDQ_EMU_COUNT_EVALS) && !defined(__CUDA_ARCH__)
+    if (grp.si == 0) ++g_emu_irls_sweeps;  // host emulator instrumentation only
+#endif
     // the branch-free cores need r = 1/alpha positive finite, a positive clamp and |x'beta| < 300 for every sample; the last
     // is checked once per sweep through |x'beta| <= sum_j |beta_j| max_n |x_nj| (the column maxima close the design pack)
     bool odd = !(alpha > 0.0 && r > 0.0 && r < 1e300 && min_mu > 0.0);

@@ -856,6 +856,32 @@ __global__ void k_gather_cols(const double* __restrict__ in, int64_t ld_in, int 
     if (j < R && n < N) out[(int64_t)n * ld_out + j] = in[(int64_t)n * ld_in + idx[j]];
 }
 
+// ---- gene order of the resident pipeline.  IRLS iteration counts follow a gene's expression level, and the four genes of a warp
+// run in lock step until the slowest stops: in the caller's gene order 22-24 % of the IRLS sweeps are repeats of finished genes,
+// with the genes sorted by their total count 4-5 % (measured with the emulator on the synthetic cohorts).  ResidentFit therefore
+// stores the shard's counts with the columns sorted by column sum (once, at upload) and returns every per-gene result to the
+// caller's order with one scatter at the end of a pass.  Per-gene arithmetic does not depend on a gene's position: results are
+// bit-identical to the unsorted pass.
+__global__ void k_column_sums(const int64_t* __restrict__ counts, int64_t ld, int N, int G, double* __restrict__ sums) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    long long s = 0;
+    for (int n = 0; n < N; ++n) s += counts[(int64_t)n * ld + g];
+    sums[g] = (double)s;
+}
+
+// out[v][perm[j]][k] = in[v][j][k], v < nvec blocks of `stride` rows of `width` doubles (rows j < n)
+__global__ void k_scatter_rows(const double* __restrict__ in, double* __restrict__ out, const int* __restrict__ perm, int n, int nvec,
+                               int64_t stride, int width) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)n * width;
+    if (t >= per * nvec) return;
+    const int v = (int)(t / per);
+    const int64_t r = t - (int64_t)v * per;
+    const int j = (int)(r / width), k = (int)(r - (int64_t)j * width);
+    out[((int64_t)v * stride + perm[j]) * width + k] = in[((int64_t)v * stride + j) * width + k];
+}
+
 // ---- content checksum of a device buffer: the device half of the residency cache of pdq_api.cu (host_hash there computes the
 // same two wrapping sums with host threads).  HBM-bound: 32 MB in ~10 us.
 __global__ void __launch_bounds__(256) k_hash(const uint64_t* __restrict__ w, size_t n, unsigned long long* out) {
@@ -1150,6 +1176,20 @@ int PDQ_TUFN(launch_lfc_shrink)(const LaunchCfg& c, const DesignDev& d, const in
 int launch_gather_cols(cudaStream_t stream, const double* in, int64_t ld_in, int N, const int* idx, int R, double* out, int64_t ld_out) {
     if (R <= 0 || N <= 0) return 0;
     k_gather_cols<<<dim3((unsigned)((R + 127) / 128), (unsigned)N), 128, 0, stream>>>(in, ld_in, N, idx, R, out, ld_out);
+    if (int e = check_launch()) return e;
+    return 1;
+}
+
+int launch_column_sums(cudaStream_t stream, const int64_t* counts, int64_t ld, int N, int G, double* sums) {
+    k_column_sums<<<(unsigned)((G + 127) / 128), 128, 0, stream>>>(counts, ld, N, G, sums);
+    if (int e = check_launch()) return e;
+    return 1;
+}
+
+int launch_scatter_rows(cudaStream_t stream, const double* in, double* out, const int* perm, int n, int nvec, int64_t stride, int width) {
+    const int64_t total = (int64_t)n * width * nvec;
+    if (total <= 0) return 0;
+    k_scatter_rows<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out, perm, n, nvec, stride, width);
     if (int e = check_launch()) return e;
     return 1;
 }

@@ -19,6 +19,7 @@
 #include <vector>
 
 extern long g_emu_alpha_evals;
+extern long g_emu_irls_sweeps;
 #define PDQ_EMU_COUNT_EVALS 1
 #define PDQ_EMU_LANES 1
 #include "../../pydeseq2_b200/csrc/pdq_gene.cuh"
@@ -27,6 +28,7 @@ extern long g_emu_alpha_evals;
 #include "../../pydeseq2_b200/csrc/pdq_shrink.cuh"
 
 long g_emu_alpha_evals = 0;
+long g_emu_irls_sweeps = 0;
 using namespace pdq;
 
 // ---- lane team: what a warp's shuffles and votes become on the host ------------------------------------------------------
@@ -416,6 +418,11 @@ int emu_set_lanes(int lanes) {
     return 0;
 }
 
+long emu_sweep_count(int reset) {
+    long v = g_emu_irls_sweeps;
+    if (reset) g_emu_irls_sweeps = 0;
+    return v;
+}
 long emu_eval_count(int reset) {
     long v = g_emu_alpha_evals;
     if (reset) g_emu_alpha_evals = 0;
