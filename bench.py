@@ -323,7 +323,13 @@ class Bench:
         if self.fp64_peak is None:
             self.fp64_peak = self.ctx.fp64_peak_tflops()
         fp64 = {"peak_tflops": self.fp64_peak, "peak_source": "measured in this run (pdq_fp64_peak_tflops: DFMA chains on every SM)"}
-        per_pair = prof.get("fp64_flop_per_gene_sample", {}).get(kname)
+        by_n = prof.get("fp64_flop_per_gene_sample_by_samples", {})
+        if by_n:  # counters exist for the captured sample counts (200, 500): take the nearest
+            key = min(by_n, key=lambda k: abs(int(k) - N))
+            per_pair = by_n[key].get(kname)
+            fp64["flop_counted_at_samples"] = int(key)
+        else:
+            per_pair = prof.get("fp64_flop_per_gene_sample", {}).get(kname)
         if per_pair:
             flop = per_pair * N * G
             fp64.update({"achieved_tflops": flop / (kern[top] * 1e-3) / 1e12, "flop_per_launch": flop,
