@@ -150,6 +150,7 @@ struct pdq_ctx {
     bool stage_busy[2] = {false, false};
     int staging = 1;  // PDQ_STAGING=0 disables (plain cudaMemcpyAsync from pageable memory)
     int* tickets = nullptr;  // device ints for the persistent kernels' tile counters (4 per stream slot)
+    void* grid_scratch = nullptr;  // accumulators of the grid-wide trend fit
     cudaStream_t pstream[2] = {nullptr, nullptr};  // gene-block pipeline of the host-buffer entry points
     cudaEvent_t pfork = nullptr, pjoin[2] = {nullptr, nullptr};
     int pipeline = 4;        // gene blocks per pipelined call; PDQ_PIPELINE=0 disables
@@ -283,7 +284,7 @@ extern "C" int pdq_ctx_create(int device, pdq_ctx** out) {
     c->res_cap = c->prop.totalGlobalMem / 4;
     if (c->res_cap > ((size_t)16 << 30)) c->res_cap = (size_t)16 << 30;
     if (const char* s = getenv("PDQ_RESIDENCY_BYTES")) c->res_cap = (size_t)atoll(s);
-    if (cudaMalloc((void**)&c->tickets, 64) != cudaSuccess || cudaStreamCreateWithFlags(&c->pstream[0], cudaStreamNonBlocking) != cudaSuccess ||
+    if (cudaMalloc((void**)&c->tickets, 64) != cudaSuccess || cudaMalloc(&c->grid_scratch, 4096) != cudaSuccess || cudaStreamCreateWithFlags(&c->pstream[0], cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->pstream[1], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->pfork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->pjoin[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -310,6 +311,7 @@ extern "C" void pdq_ctx_destroy(pdq_ctx* c) {
     if (c->hash_dev) cudaFree(c->hash_dev);
     if (c->hash_host) cudaFreeHost(c->hash_host);
     if (c->tickets) cudaFree(c->tickets);
+    if (c->grid_scratch) cudaFree(c->grid_scratch);
     for (auto& st : c->pstream)
         if (st) cudaStreamDestroy(st);
     if (c->pfork) cudaEventDestroy(c->pfork);
@@ -718,7 +720,7 @@ extern "C" int pdq_trend_fit_dev(pdq_ctx* c, const double* means, const double* 
     if (!means || !genewise || !out16 || n == 0) return fail(c, PDQ_ERR_INVALID, "pdq_trend_fit_dev: bad arguments");
     void* scratch;
     if (int e = ensure(c, kBufRes, 3 * n * 8, &scratch)) return e;
-    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets, c->debug};
+    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets, c->debug, c->grid_scratch};
     if (int e = done(c, launch_trend_fit(lc, means, genewise, (double*)scratch, n, 1, min_disp, max_disp, 1, min_disp, trigamma_c, 1, out16),
                      "trend_fit"))
         return e;
@@ -773,7 +775,7 @@ extern "C" int pdq_select_dispersions_dev(pdq_ctx* c, const double* genewise, co
     CHECK_CTX(c);
     if (!genewise || !map || !fitted || !trend_out16 || !disp_out || n == 0)
         return fail(c, PDQ_ERR_INVALID, "pdq_select_dispersions_dev: bad arguments");
-    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets, c->debug};
+    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets, c->debug, c->grid_scratch};
     return done(c, launch_select_disp(lc, genewise, map, fitted, trend_out16, n, min_disp, max_disp, disp_out, outlier_out), "select_dispersions");
 }
 
@@ -1459,7 +1461,7 @@ extern "C" int pdq_dispersion_trend_gamma_glm(pdq_ctx* c, const double* cov, con
     if (int e = ensure(c, kBufMisc, 256, &dout)) return e;
     CU(c, cudaMemcpyAsync(dx, cov, n * 8, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(dt, targets, n * 8, cudaMemcpyHostToDevice, c->stream));
-    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets, c->debug};
+    LaunchCfg lc{c->stream, 0, c->prop.multiProcessorCount, c->tickets, c->debug, c->grid_scratch};
     const double inf = 1.0 / 0.0;
     if (int e = done(c, launch_trend_fit(lc, (const double*)dx, (const double*)dt, (double*)scratch, n, 0, -inf, inf, 0, 0.0, 0.0, 0, (double*)dout),
                      "dispersion_trend_gamma_glm"))

@@ -30,6 +30,7 @@ struct LaunchCfg {
     int sm_count;
     int* tickets;  // device ints: tile counters of the persistent kernels
     int debug;     // PDQ_DEBUG_* test hooks
+    void* grid_scratch = nullptr;  // device scratch of the grid-wide trend fit (launch_trend_fit), 4 KB
 };
 
 struct IrlsHost {

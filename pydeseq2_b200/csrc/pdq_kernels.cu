@@ -688,6 +688,98 @@ __global__ void __launch_bounds__(1024) k_trend_prior(const double* __restrict__
     cluster.sync();  // no block may exit while peers can still address its shared memory
 }
 
+// ---- the same fit on the whole GPU (vectors of >= 64 k genes: the gathered vectors of many gene shards, one large shard).  One
+// cooperative launch of one block per SM; the per-pass reductions go through a few hundred bytes of global memory (atomics) and a
+// grid-wide barrier instead of DSMEM and a cluster barrier.  The accumulators rotate over three slots so that none is zeroed while
+// another block may still read or add to it: pass p adds into slot p % 3, reads it behind the barrier, and block 0 then clears slot
+// (p + 2) % 3, last read in pass p - 1 and next used in pass p + 1.
+struct GridScratch {
+    double acc[3][kTrendK];
+    unsigned long long maxkey[3];
+    unsigned hist[3][256];
+};
+
+struct GridReducer {
+    double* warp_part;  // [32][kTrendK] shared
+    double* totals;     // [kTrendK] shared
+    GridScratch* gs;    // global, zeroed before the launch
+    int p_sum, p_max, p_hist;
+    __device__ int tid() const { return blockIdx.x * blockDim.x + threadIdx.x; }
+    __device__ int nthreads() const { return gridDim.x * blockDim.x; }
+    __device__ int local_tid() const { return threadIdx.x; }
+    __device__ int local_nthreads() const { return blockDim.x; }
+    __device__ void local_sync() { __syncthreads(); }
+    __device__ void sync() { cooperative_groups::this_grid().sync(); }
+    __device__ void sum_many(double* v, int k) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, slot = p_sum % 3;
+        for (int j = 0; j < k; ++j) {
+            double w = v[j];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
+            if (lane == 0) warp_part[warp * kTrendK + j] = w;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < k) {
+            double tot = 0.0;
+            const int nw = blockDim.x >> 5;
+            for (int w = 0; w < nw; ++w) tot += warp_part[w * kTrendK + threadIdx.x];
+            atomicAdd(&gs->acc[slot][threadIdx.x], tot);
+        }
+        cooperative_groups::this_grid().sync();
+        if ((int)threadIdx.x < k) totals[threadIdx.x] = *reinterpret_cast<volatile double*>(&gs->acc[slot][threadIdx.x]);
+        if (blockIdx.x == 0 && (int)threadIdx.x < kTrendK) gs->acc[(p_sum + 2) % 3][threadIdx.x] = 0.0;
+        __syncthreads();
+        for (int j = 0; j < k; ++j) v[j] = totals[j];
+        __syncthreads();  // totals is overwritten by the next reduction
+        ++p_sum;
+    }
+    __device__ double max_one(double v) {
+        const int lane = threadIdx.x & 31, slot = p_max % 3;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+        if (lane == 0) atomicMax(&gs->maxkey[slot], (unsigned long long)f64_key(v));
+        cooperative_groups::this_grid().sync();
+        const double m = f64_from_key(*reinterpret_cast<volatile unsigned long long*>(&gs->maxkey[slot]));
+        if (blockIdx.x == 0 && threadIdx.x == 0) gs->maxkey[(p_max + 2) % 3] = 0ull;
+        ++p_max;
+        return m;
+    }
+    __device__ void hist_begin() { __syncthreads(); }
+    __device__ unsigned* hist_merge(unsigned* hist) {
+        const int slot = p_hist % 3;
+        __syncthreads();  // local bins complete
+        if (threadIdx.x < 256) {
+            const unsigned c = hist[threadIdx.x];
+            if (c) atomicAdd(&gs->hist[slot][threadIdx.x], c);
+        }
+        cooperative_groups::this_grid().sync();
+        if (threadIdx.x < 256) hist[256 + threadIdx.x] = *reinterpret_cast<volatile unsigned*>(&gs->hist[slot][threadIdx.x]);
+        if (blockIdx.x == 0 && threadIdx.x < 256) gs->hist[(p_hist + 2) % 3][threadIdx.x] = 0u;
+        __syncthreads();
+        ++p_hist;
+        return hist + 256;
+    }
+    __device__ void find_bin(const unsigned* hist, unsigned* out, size_t k, int& d, size_t& cum) {
+        ClusterReducer tmp{nullptr, nullptr, nullptr, 0u, 1u, 0};  // the single-block scan of the 256 merged bins
+        tmp.find_bin(hist, out, k, d, cum);
+    }
+};
+
+__global__ void __launch_bounds__(1024) k_trend_prior_grid(const double* __restrict__ x, const double* __restrict__ t,
+                                                           double* scratch /* 3 n doubles: xs | ts | res */, size_t n, int x_is_mean,
+                                                           double lo, double hi, int outer, double min_disp, double trigamma_c,
+                                                           int with_prior, TrendOut* out, GridScratch* gs) {
+    __shared__ double warp_part[32 * kTrendK];
+    __shared__ double totals[kTrendK];
+    __shared__ unsigned hist[514];
+    GridReducer red{warp_part, totals, gs, 0, 0, 0};
+    double *xs = scratch, *ts = scratch + n, *res = scratch + 2 * n;
+    trend_prepare(red, x, t, n, x_is_mean != 0, lo, hi, xs, ts);
+    TrendOut o = trend_fit_outer(red, xs, ts, n, outer != 0);
+    if (with_prior && o.status == 0.0) trend_prior(red, x, t, n, lo, hi, min_disp, trigamma_c, res, hist, o);
+    if (red.tid() == 0) *out = o;
+}
+
 // ---- median-of-ratios size factors (preprocessing.py:31-102), SURVEY.md §8 f-2 -------------------------------------
 // 1. per-gene mean of log counts (-inf when the gene holds a zero: such genes are filtered out, preprocessing.py:52-54)
 __global__ void __launch_bounds__(kBlock) k_log_means(const int64_t* __restrict__ counts, int64_t ld, int N, int G, int lgT,
@@ -1088,6 +1180,27 @@ int PDQ_TUFN(launch_mu_from_lfc)(const LaunchCfg& c, const DesignDev& d, const d
 #if PDQ_TU_P == 0
 int launch_trend_fit(const LaunchCfg& c, const double* x, const double* t, double* scratch3n, size_t n, int x_is_mean,
                      double lo, double hi, int outer, double min_disp, double trigamma_c, int with_prior, double* out16) {
+    // large vectors: one block per SM, cooperative launch (k_trend_prior_grid); PDQ_TREND_GRID=0/1 forces the choice
+    {
+        const char* e = getenv("PDQ_TREND_GRID");
+        const int force = e ? atoi(e) : -1;
+        const bool use_grid = force >= 0 ? force != 0 : n >= 65536;
+        if (use_grid && c.grid_scratch) {
+            if (cudaMemsetAsync(c.grid_scratch, 0, sizeof(GridScratch), c.stream) != cudaSuccess) return PDQ_ERR_CUDA;
+            int blocks = (int)((n + 2047) / 2048);
+            if (blocks > c.sm_count) blocks = c.sm_count;
+            if (blocks < 1) blocks = 1;
+            TrendOut* o16 = reinterpret_cast<TrendOut*>(out16);
+            GridScratch* gs = reinterpret_cast<GridScratch*>(c.grid_scratch);
+            void* args[] = {(void*)&x, (void*)&t, (void*)&scratch3n, (void*)&n, (void*)&x_is_mean, (void*)&lo, (void*)&hi, (void*)&outer,
+                            (void*)&min_disp, (void*)&trigamma_c, (void*)&with_prior, (void*)&o16, (void*)&gs};
+            if (cudaLaunchCooperativeKernel((const void*)k_trend_prior_grid, dim3(blocks), dim3(1024), args, 0, c.stream) == cudaSuccess) {
+                if (int e = check_launch()) return e;
+                return 1;
+            }
+            cudaGetLastError();  // cooperative launch not possible here: the cluster version below
+        }
+    }
     // cluster size: enough blocks for ~4 elements per thread; 8 is the portable maximum, 16 needs the opt-in attribute
     static int max_cluster = 0;
     if (!max_cluster) {

@@ -181,3 +181,51 @@ def test_csv_ingestion_into_pinned_memory(inf, tmp_path):
     assert tab.samples[0] == "s0" and tab.genes[-1] == "g299"
     sf = np.ones(24)
     np.testing.assert_array_equal(inf.lin_reg_mu(tab.counts, sf, X, 0.5), inf.lin_reg_mu(counts, sf, X, 0.5))
+
+
+def test_trend_prior_grid_wide_equals_cluster_version(inf):
+    """Vectors of >= 64 k genes run the trend + prior fit as one cooperative launch over all SMs (global-memory reductions, grid
+    barrier); it must reproduce the one-cluster kernel (same algorithm, other reduction tree) -- also inside a replayed CUDA graph."""
+    import os
+
+    import numpy as np
+
+    from pydeseq2_b200.pipeline import ResidentFit, median_of_ratios
+    from pydeseq2_b200.synth import make_counts
+
+    rng = np.random.default_rng(5)
+    n = 150_001
+    means = np.exp(rng.normal(4.0, 2.0, n))
+    gw = np.clip((4.0 / means + 0.1) * np.exp(rng.normal(0, 0.6, n)), 1e-8, 60.0)
+    gw[rng.choice(n, 300, replace=False)] = 1e-8     # flat-tail genes (excluded from the prior by the 100 * min_disp rule)
+    means[rng.choice(n, 50, replace=False)] = np.nan  # padding of short shards
+    out = {}
+    for mode in ("0", "1"):
+        os.environ["PDQ_TREND_GRID"] = mode
+        try:
+            out[mode] = inf.trend_and_prior(means, gw, 1e-8, 60.0, 60, 3)
+        finally:
+            del os.environ["PDQ_TREND_GRID"]
+    a, b = out["0"], out["1"]
+    assert a is not None and b is not None
+    np.testing.assert_allclose(b[0], a[0], rtol=1e-10)          # coefficients
+    np.testing.assert_allclose(b[1], a[1], rtol=1e-10, equal_nan=True)
+    assert b[2] == a[2] and b[3] == a[3] and b[4] == a[4]        # exact medians: squared log residual, prior variance; rounds
+    # inside the resident pass (70 000 genes > 64 k: grid version by default), eager then captured + replayed
+    counts, X, _ = make_counts(24, 70_000, "two_level", seed=2)
+    counts = np.ascontiguousarray(counts[:, ~(counts == 0).all(0)])
+    rf = ResidentFit(inf._ops.ctx, X, median_of_ratios(counts[:, :20000])[1])
+    rf.upload(counts)
+    r1, r2, r3 = rf.run(), rf.run(), rf.run()
+    np.testing.assert_array_equal(r1["dispersions"], r3["dispersions"])
+    np.testing.assert_array_equal(r1["trend"].coeffs, r3["trend"].coeffs)
+    os.environ["PDQ_TREND_GRID"] = "0"
+    try:
+        rf._drop_graph()
+        rf._eager_key = None
+        rc = rf.run()
+    finally:
+        del os.environ["PDQ_TREND_GRID"]
+    np.testing.assert_allclose(r3["trend"].coeffs, rc["trend"].coeffs, rtol=1e-10)
+    np.testing.assert_allclose(r3["dispersions"], rc["dispersions"], rtol=1e-8)
+    rf.close()
