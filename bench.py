@@ -9,8 +9,8 @@ One "step" = one pass of the hot path over one batch of synthetic counts: method
 initial mu (lin_reg_mu or IRLS), genewise dispersion MLE, dispersion trend + prior, MAP dispersions, the
 log-fold-change IRLS and the Wald test -- the Inference calls `DeseqDataSet.deseq2()` +
 `DeseqStats.run_wald_test()` make (reference dds.py:516-562, ds.py:303-360) -- and, with gene shards (N > 1), the two
-exchanges of the path: the grouped NCCL all-gather of the per-gene vectors before the trend step and the end-of-call
-all-gather of the result tables.  Size factors are computed once outside the timed region for both arms.
+exchanges of the path: the per-gene vectors before the trend step and the result tables at the end of the call (one peer-memory
+push kernel each, or grouped NCCL all-gathers).  Size factors are computed once outside the timed region for both arms.
 
 Headline workload (`value`, `e2e`, `roofline`, `cpu_baseline`) = BASELINE.json configs[1]: 20 000 genes x 200 samples, one
 2-level factor, per GPU (weak scaling).  The `configs` block of the same JSON line carries BASELINE's larger shapes, timed the
@@ -183,8 +183,9 @@ def config(args, note=None):
                      if (args.genes, args.samples, args.design) == (20000, 200, "two_level")
                      else f"{args.genes} genes x {args.samples} samples per GPU, {args.design} design (p={p})",
          "genes_per_gpu": args.genes, "samples": args.samples, "p": p,
-         "parallelism": f"gene shards x{args.gpus}; per step one grouped NCCL all-gather of the per-gene vectors before the trend fit "
-                        f"and one all-gather of the result tables at the end",
+         "parallelism": f"gene shards x{args.gpus}; per step one exchange of the per-gene vectors before the trend fit and one of the "
+                        f"result tables at the end (one push kernel each over peer memory / NVLink; grouped NCCL all-gathers when the "
+                        f"ranks cannot map each other's memory -- see `exchange`)",
          "size_factors": "median of ratios, precomputed outside the timed region (both arms)",
          "l2": "flushed between timed steps (256 MiB device memset)"}
     if note:
@@ -275,12 +276,14 @@ class Bench:
         self.ctx.sync()
 
     # -- measurements -----------------------------------------------------------------------------------------
-    def resident(self, counts, X, sf, G_in, steps, warmup):
+    def resident(self, counts, X, sf, G_in, steps, warmup, exchange=None):
         """Device-resident steps (CUDA events on the library's stream, L2 flushed, max over ranks) + per-stage timings."""
         from pydeseq2_b200.pipeline import ResidentFit
 
         N, G = counts.shape
         rf = ResidentFit(self.ctx, X, sf, comm=self.comm_for(G))
+        if exchange:
+            rf.exchange = exchange
         rf.upload(counts)
         for _ in range(max(warmup, 3)):
             rf.run()
@@ -300,6 +303,8 @@ class Bench:
         stages = dict(rf.stage_ms)
         rec = {"ms_per_step": ms, "genes_per_s": G_in * self.world / (ms * 1e-3), "gpu_launches": int(launches),
                "stages_ms": {k: round(v, 4) for k, v in stages.items()}}
+        if self.world > 1:  # how the shards exchanged: peer-memory push kernel (NVLink stores) or grouped NCCL all-gathers
+            rec["exchange"] = "peer" if rf._win is not None else "nccl"
         rec.update(self.rooflines(stages, N, G, X.shape[1], ms))
         return rf, rec
 
@@ -447,6 +452,12 @@ def main():
     rf, head = B.resident(counts, X, sf, G_in, args.steps, args.warmup)
     stages = dict(head["stages_ms"])
     shard_check = B.check_shards(rf) if world > 1 else None
+    exchange_ab = None
+    if world > 1 and head.get("exchange") == "peer":  # the same steps with the NCCL exchange, for comparison
+        rf_n, rec_n = B.resident(counts, X, sf, G_in, args.steps, args.warmup, exchange="nccl")
+        rf_n.close()
+        exchange_ab = {"peer_ms_per_step": head["ms_per_step"], "nccl_ms_per_step": rec_n["ms_per_step"],
+                       "nccl_stages_ms": {k: rec_n["stages_ms"][k] for k in ("allgather", "gather_results") if k in rec_n["stages_ms"]}}
 
     # untimed extras (reported for information, NOT part of the timed step): Cook's distances, apeGLM shrinkage, device size factors
     from pydeseq2_b200.pipeline import fit_shrink_prior_var
@@ -516,7 +527,8 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(args), "e2e": e2e,
                 "gpu_launches": head["gpu_launches"], "clocks": clk.summary(), "roofline": head["roofline"], "cpu_baseline": cpu,
-                "stages_ms": stages, "full_deseq2": full, "configs": configs, "shard_check": shard_check, "device": ctx.info()["name"]}
+                "stages_ms": stages, "full_deseq2": full, "configs": configs, "shard_check": shard_check, "exchange": head.get("exchange"), "exchange_ab": exchange_ab,
+                "device": ctx.info()["name"]}
         print(json.dumps(line), flush=True)
     if B.dist is not None:
         B.dist.barrier()

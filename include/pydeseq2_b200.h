@@ -310,6 +310,25 @@ int pdq_allgather_f64_dev(pdq_ctx* ctx, const double* send, double* recv, size_t
 int pdq_allgather_multi_f64_dev(pdq_ctx* ctx, int k, const double* const* send, double* const* recv, size_t count);
 int pdq_comm_destroy(pdq_ctx* ctx);
 
+/* Peer-memory flavour of the same two exchanges (ranks of ONE node; CUDA IPC + NVLink peer stores, no NCCL on the data path).
+ * Every rank allocates a window (`data_bytes` of payload, identical on all ranks), ships the 64-byte handle to its peers through any
+ * out-of-band channel, and opens the group with the `world` handles in rank order.  `pdq_peer_push_dev` is ONE kernel on the
+ * context's stream: it stores segment i (`count` doubles) of this rank at payload offset recv_off_bytes[i] + rank * count * 8 of
+ * EVERY rank's window and completes once all ranks' segments have arrived in the own window (copy + barrier; k = 0: barrier
+ * only); capturable into a CUDA graph.  A peer that never arrives is reported through `pdq_peer_status` (1 + its rank) after
+ * PDQ_PEER_TIMEOUT_MS (default 10 000) instead of hanging the device.  Every rank must close its group before any rank frees
+ * its window.  Replaces, like the NCCL calls above, the host-side concatenation of per-shard results a multi-process caller of the
+ * reference would do (the reference itself is single-process: `default_inference.py:18-41` fans genes out over joblib workers). */
+#define PDQ_PEER_HANDLE_BYTES 64
+typedef struct pdq_peer_group pdq_peer_group;
+int pdq_peer_window_alloc(pdq_ctx* ctx, size_t data_bytes, void** window_out, void** data_out, void* handle_out);
+int pdq_peer_window_free(pdq_ctx* ctx, void* window);
+int pdq_peer_group_open(pdq_ctx* ctx, void* own_window, int world_size, int rank, const void* handles, pdq_peer_group** group_out);
+int pdq_peer_push_dev(pdq_ctx* ctx, pdq_peer_group* group, int k, const double* const* send, const unsigned long long* recv_off_bytes,
+                      size_t count);
+int pdq_peer_status(pdq_ctx* ctx, pdq_peer_group* group, unsigned long long* status_out);
+int pdq_peer_group_close(pdq_ctx* ctx, pdq_peer_group* group);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ i64p = C.POINTER(C.c_int64)
 PDQ_MAX_P = 16
 ALT_CODES = {None: 0, "greaterAbs": 1, "lessAbs": 2, "greater": 3, "less": 4}
 UNIQUE_ID_BYTES = 128
+PEER_HANDLE_BYTES = 64
 
 STATUS = {0: "ok", -1: "cuda error", -2: "invalid argument", -3: "unsupported", -4: "nccl error", -5: "no sm_100 device"}
 
@@ -113,6 +114,12 @@ _SIGNATURES = {
     "pdq_allgather_f64_dev": (C.c_int, [c_ctx, c_dptr, c_dptr, C.c_size_t]),
     "pdq_allgather_multi_f64_dev": (C.c_int, [c_ctx, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t]),
     "pdq_comm_destroy": (C.c_int, [c_ctx]),
+    "pdq_peer_window_alloc": (C.c_int, [c_ctx, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
+    "pdq_peer_window_free": (C.c_int, [c_ctx, c_dptr]),
+    "pdq_peer_group_open": (C.c_int, [c_ctx, c_dptr, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pdq_peer_push_dev": (C.c_int, [c_ctx, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_size_t]),
+    "pdq_peer_status": (C.c_int, [c_ctx, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "pdq_peer_group_close": (C.c_int, [c_ctx, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1588,6 +1588,205 @@ extern "C" int pdq_allgather_multi_f64_dev(pdq_ctx* c, int k, const double* cons
     return PDQ_OK;
 }
 
+// --------------------------------------------------------------------------------------------- peer-memory gene-shard exchange
+// The same two exchanges without NCCL: every rank owns one "window" (a cudaMalloc block exported with CUDA IPC and mapped by all
+// peers of the node).  ONE kernel per exchange reads the rank's segment once and stores it into the same place of EVERY rank's
+// window over NVLink / NVSwitch (plain peer stores), then signals the peers and waits for theirs: copy + barrier in one launch,
+// capturable in the pass's CUDA graph.  Window layout: 4096 bytes of control words, data behind.
+//   control: word 0 = number of exchanges this rank has completed (local), byte 128 * (1 + r) = arrival counter of rank r:
+//   every block of r's push kernel adds 1 after its stores are fenced system-wide.
+static constexpr int kPeerMaxWorld = 16, kPeerBlocks = 64, kPeerThreads = 512;
+static constexpr size_t kPeerCtrlBytes = 4096;
+
+struct pdq_peer_group {
+    int world = 1, rank = 0;
+    void* base[kPeerMaxWorld] = {};      // every rank's window as mapped in THIS process (base[rank] = the own allocation)
+    unsigned long long* err_host = nullptr;  // mapped page-locked word: non-zero after a push kernel gave up waiting
+    unsigned long long* err_dev = nullptr;
+};
+
+struct PeerPushArgs {
+    char* base[kPeerMaxWorld];
+    int world, rank, k;
+    const double* send[4];
+    unsigned long long recv_off[4];  // byte offset of the gathered vector in the window (behind the control words)
+    unsigned long long count;        // doubles per rank and segment
+    unsigned long long* err;
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(kPeerThreads) k_peer_push(const PeerPushArgs a) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    for (int s = 0; s < a.k; ++s) {
+        const double* src = a.send[s];
+        const size_t dst_off = kPeerCtrlBytes + a.recv_off[s] + (size_t)a.rank * a.count * 8;
+        const bool vec = (a.count % 2 == 0) && (((uintptr_t)src | dst_off) % 16 == 0);
+        if (vec) {
+            const double2* src2 = reinterpret_cast<const double2*>(src);
+            for (size_t i = tid; i < a.count / 2; i += nth) {
+                const double2 v = src2[i];
+                for (int q = 0; q < a.world; ++q) {  // own window last: the remote stores leave first
+                    const int r = (a.rank + 1 + q) % a.world;
+                    reinterpret_cast<double2*>(a.base[r] + dst_off)[i] = v;
+                }
+            }
+        } else {
+            for (size_t i = tid; i < a.count; i += nth) {
+                const double v = src[i];
+                for (int q = 0; q < a.world; ++q) {
+                    const int r = (a.rank + 1 + q) % a.world;
+                    reinterpret_cast<double*>(a.base[r] + dst_off)[i] = v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int q = 1; q < a.world; ++q) {
+            const int r = (a.rank + q) % a.world;
+            atomicAdd_system(reinterpret_cast<unsigned long long*>(a.base[r] + 128 * (1 + a.rank)), 1ULL);
+        }
+    }
+    if (blockIdx.x != 0) return;
+    // block 0: wait until every peer's blocks of the same exchange have arrived here
+    unsigned long long* ctrl = reinterpret_cast<unsigned long long*>(a.base[a.rank]);
+    const unsigned long long target = (ctrl[0] + 1) * (unsigned long long)gridDim.x;
+    if ((int)threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(a.base[a.rank] + 128 * (1 + threadIdx.x));
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(flag) < target) {
+            if (global_timer_ns() - t0 > a.timeout_ns) {  // a peer never arrived: report instead of hanging the GPU
+                *a.err = 1ULL + threadIdx.x;
+                __threadfence_system();
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) ctrl[0] += 1;
+}
+
+extern "C" int pdq_peer_window_alloc(pdq_ctx* c, size_t data_bytes, void** window_out, void** data_out, void* handle_out) {
+    CHECK_CTX(c);
+    if (!window_out || !data_out || !handle_out) return fail(c, PDQ_ERR_INVALID, "pdq_peer_window_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PDQ_PEER_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    void* w = nullptr;
+    CU(c, cudaMalloc(&w, kPeerCtrlBytes + data_bytes));
+    CU(c, cudaMemsetAsync(w, 0, kPeerCtrlBytes, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, w);
+    if (e != cudaSuccess) {
+        cudaFree(w);
+        return fail(c, PDQ_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &hd, sizeof hd);
+    *window_out = w;
+    *data_out = (char*)w + kPeerCtrlBytes;
+    return PDQ_OK;
+}
+
+extern "C" int pdq_peer_window_free(pdq_ctx* c, void* window) {
+    CHECK_CTX(c);
+    if (window) CU(c, cudaFree(window));
+    return PDQ_OK;
+}
+
+extern "C" int pdq_peer_group_open(pdq_ctx* c, void* own_window, int world, int rank, const void* handles, pdq_peer_group** out) {
+    CHECK_CTX(c);
+    if (!own_window || !handles || !out || world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world)
+        return fail(c, PDQ_ERR_INVALID, "pdq_peer_group_open: bad arguments (world <= %d)", kPeerMaxWorld);
+    pdq_peer_group* g = new pdq_peer_group;
+    g->world = world;
+    g->rank = rank;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            g->base[r] = own_window;
+            continue;
+        }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char*)handles + (size_t)r * sizeof hd, sizeof hd);
+        cudaError_t e = cudaIpcOpenMemHandle(&g->base[r], hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; ++q)
+                if (q != rank) cudaIpcCloseMemHandle(g->base[q]);
+            delete g;
+            cudaGetLastError();
+            return fail(c, PDQ_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+        }
+    }
+    cudaError_t e = cudaHostAlloc((void**)&g->err_host, 8, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&g->err_dev, g->err_host, 0);
+    if (e != cudaSuccess) {
+        for (int q = 0; q < world; ++q)
+            if (q != rank) cudaIpcCloseMemHandle(g->base[q]);
+        delete g;
+        return fail(c, PDQ_ERR_CUDA, "cudaHostAlloc(peer status) failed: %s", cudaGetErrorString(e));
+    }
+    *g->err_host = 0;
+    *out = g;
+    return PDQ_OK;
+}
+
+// k (<= 4) segments of `count` doubles each: segment i of this rank lands at data offset recv_off_bytes[i] + rank * count * 8 of
+// EVERY rank's window; returns (on the stream) once all ranks' segments have landed here.  k = 0: barrier only.
+extern "C" int pdq_peer_push_dev(pdq_ctx* c, pdq_peer_group* g, int k, const double* const* send, const unsigned long long* recv_off_bytes,
+                                 size_t count) {
+    CHECK_CTX(c);
+    if (!g || k < 0 || k > 4 || (k > 0 && (!send || !recv_off_bytes))) return fail(c, PDQ_ERR_INVALID, "pdq_peer_push_dev: bad arguments");
+    PeerPushArgs a{};
+    for (int r = 0; r < g->world; ++r) a.base[r] = (char*)g->base[r];
+    a.world = g->world;
+    a.rank = g->rank;
+    a.k = k;
+    for (int i = 0; i < k; ++i) {
+        if (!send[i] || recv_off_bytes[i] % 8) return fail(c, PDQ_ERR_INVALID, "pdq_peer_push_dev: bad segment");
+        a.send[i] = send[i];
+        a.recv_off[i] = recv_off_bytes[i];
+    }
+    a.count = count;
+    a.err = g->err_dev;
+    static const unsigned long long timeout_ms = getenv("PDQ_PEER_TIMEOUT_MS") ? strtoull(getenv("PDQ_PEER_TIMEOUT_MS"), nullptr, 10) : 10000ULL;
+    a.timeout_ns = timeout_ms * 1000000ULL;
+    k_peer_push<<<kPeerBlocks, kPeerThreads, 0, c->stream>>>(a);
+    CU(c, cudaGetLastError());
+    c->launches += 1;
+    return PDQ_OK;
+}
+
+// 0 while every exchange completed; 1 + r when a push kernel gave up waiting for rank r (valid after a stream synchronisation)
+extern "C" int pdq_peer_status(pdq_ctx* c, pdq_peer_group* g, unsigned long long* status_out) {
+    CHECK_CTX(c);
+    if (!g || !status_out) return fail(c, PDQ_ERR_INVALID, "pdq_peer_status: bad arguments");
+    *status_out = *(volatile unsigned long long*)g->err_host;
+    return PDQ_OK;
+}
+
+// unmaps the peers' windows (every rank must do so BEFORE any rank frees its own window)
+extern "C" int pdq_peer_group_close(pdq_ctx* c, pdq_peer_group* g) {
+    CHECK_CTX(c);
+    if (!g) return PDQ_OK;
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < g->world; ++r)
+        if (r != g->rank && g->base[r]) cudaIpcCloseMemHandle(g->base[r]);
+    if (g->err_host) cudaFreeHost(g->err_host);
+    delete g;
+    return PDQ_OK;
+}
+
 extern "C" int pdq_comm_destroy(pdq_ctx* c) {
     CHECK_CTX(c);
     if (c->comm) {

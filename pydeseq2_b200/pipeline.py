@@ -14,6 +14,7 @@ Two drivers share the host glue (size factors, trend loop, dispersion prior -- g
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 import warnings
 from dataclasses import dataclass, field
@@ -315,6 +316,10 @@ class ResidentFit:
         self.fuse_wald = True         # Wald test inside the LFC-fit launch (False: the two plugin-shaped calls in sequence)
         self.gather = comm is not None  # end the pass with the all-gather of the result tables of all gene shards
         self.use_hint = True          # MAP dispersion search opened from the genewise optimum + curvature (pdq_alpha_mle_hint_dev)
+        # how gene shards exchange: "peer" = one kernel per exchange storing into every peer's HBM over NVLink (sharding.PeerWindow),
+        # "nccl" = grouped NCCL all-gathers, "auto" = peer when the ranks can map each other's memory (one node), else NCCL
+        self.exchange = os.environ.get("PDQ_EXCHANGE", "auto")
+        self._win, self._win_key = None, None
         # Device-side gene order: columns sorted by total count at upload.  IRLS iteration counts follow the expression level and
         # the four genes of a warp iterate in lock step, so neighbours of similar expression waste fewer repeated sweeps (22 % ->
         # 4 % of the IRLS sweeps on the synthetic cohorts).  Per-gene arithmetic is position-independent: results are bit-identical
@@ -452,6 +457,29 @@ class ResidentFit:
                                               c_d(self.d_perm), self.G, 1, self.Gs, self.p))
         self.ctx.check(L.pdq_memcpy_d2d(h, c_d(self.d_slab_out + self._off_t16 * 8), c_d(self.d_t16), 16 * 8))
 
+    def _window(self, n_all):
+        """The peer-memory receive window of this fit (collective on first use; None = exchange through NCCL)."""
+        if self.exchange == "nccl" or not hasattr(self.comm, "open_window"):
+            return None
+        key = (n_all, self._slab_len)
+        if self._win_key == key:
+            return self._win
+        from .sharding import PeerUnavailable
+
+        if self._win is not None:
+            self._drop_graph()
+            self._win.close()
+            self._win = None
+        vec = -(-n_all * 8 // 128) * 128
+        try:
+            self._win = self.comm.open_window(2 * vec + self.comm.world * self._slab_len * 8)
+        except PeerUnavailable:
+            if self.exchange == "peer":
+                raise
+            self._win = None
+        self._win_key = key
+        return self._win
+
     def _drop_graph(self):
         if self._graph is not None:
             self.lib.pdq_graph_destroy(self.ctx.h, self._graph)
@@ -459,6 +487,9 @@ class ResidentFit:
 
     def close(self):
         self._drop_graph()
+        if self._win is not None:  # collective, like the construction
+            self._win.close()
+            self._win, self._win_key = None, None
         for ptr, _ in self._bufs.values():
             self.ctx.free(ptr)
         self._bufs = {}
@@ -503,11 +534,31 @@ class ResidentFit:
         rank = self.comm.rank if self.comm is not None else 0
         m = self.comm.max_size if self.comm is not None else G
         n_all = W * m
-        if self.comm is not None:
+        win = self._window(n_all) if self.comm is not None else None
+        if win is not None:  # the gathered vectors live in the window every peer stores into
+            vec = -(-n_all * 8 // 128) * 128
+            off_gw, off_means, off_table = 0, vec, 2 * vec
+            d_gw_all, d_means_all = win.data + off_gw, win.data + off_means
+            d_table_all = win.data + off_table if self.gather else None
+        elif self.comm is not None:
             d_gw_all, d_means_all = self._dev("gw_all", n_all * 8), self._dev("means_all", n_all * 8)
             d_table_all = self._dev("table_all", W * self._slab_len * 8) if self.gather else None
         else:
             d_gw_all, d_means_all, d_table_all = self.d_gw, self.d_means, None
+        self._d_table_all = d_table_all
+
+        def exchange_vectors():
+            if win is not None:
+                win.push([(self.d_gw, off_gw), (self.d_means, off_means)], m)
+            else:
+                self.comm.allgather_dev([(self.d_gw, d_gw_all), (self.d_means, d_means_all)], m)
+
+        def exchange_tables():
+            if win is not None:  # without a table exchange the pass still ends with the barrier: a fast rank must not store the
+                # next pass' vectors into a window whose owner is still reading this pass'
+                win.push([(self.d_slab_out, off_table)] if self.gather else [], self._slab_len)
+            elif d_table_all is not None:
+                self.comm.allgather_dev([(self.d_slab_out, d_table_all)], self._slab_len)
         d_fit_all = self._dev("fitted_all", n_all * 8)
         d_t16 = self.d_t16
         d_fitted = d_fit_all + rank * m * 8  # this shard's slice of the fitted curve
@@ -534,7 +585,7 @@ class ResidentFit:
             #    vectors are all-gathered over NCCL first, device to device; the fit itself is one cluster launch.
             if self.comm is not None:
                 begin("allgather")
-                self.comm.allgather_dev([(self.d_gw, d_gw_all), (self.d_means, d_means_all)], m)
+                exchange_vectors()
                 if profile:
                     check(0)
             if fit_type == "parametric":
@@ -547,18 +598,19 @@ class ResidentFit:
                     self._to_caller_order()
                     if profile:
                         check(0)
-                if d_table_all is not None:
-                    # end-of-call exchange (SURVEY.md §8e / north star): ONE all-gather of the whole result slab -- dispersions,
+                if d_table_all is not None or win is not None:
+                    # end-of-call exchange (SURVEY.md §8e / north star): ONE exchange of the whole result slab -- dispersions,
                     # coefficients, flags, Wald statistics of every shard -- after which each rank holds the full tables in HBM
                     begin("gather_results")
-                    self.comm.allgather_dev([(self.d_slab_out, d_table_all)], self._slab_len)
+                    exchange_tables()
                     if profile:
                         check(0)
             ctx.d2h(self._h_slab, self.d_slab_out)  # every per-gene result of THIS shard + the trend record, one copy
 
         # The pass is ~20 launches + copies with no host synchronisation in between: after one eager pass (which allocates
         # every buffer) the identical sequence is captured into a CUDA graph and replayed with a single call.
-        key = (fit_type, contrast.tobytes(), float(lfc_null), alt_hypothesis, G, self.with_cooks, n_all, self.fuse_wald, self.use_hint)
+        key = (fit_type, contrast.tobytes(), float(lfc_null), alt_hypothesis, G, self.with_cooks, n_all, self.fuse_wald, self.use_hint,
+               self.gather, win is not None)
         # a captured pass holds pointers into context-owned scratch (per-gene status words, trend scratch); host-buffer calls on the
         # same context may have re-allocated it since: the context counts re-allocations, a stale graph is dropped and re-captured
         if events:
@@ -584,6 +636,8 @@ class ResidentFit:
         if events:
             ctx.record(events[1])
         ctx.sync()  # the only host synchronisation of the pass
+        if win is not None:
+            win.check()
         t16 = H["t16"]
         if fit_type == "parametric" and t16[2] == 0.0:
             trend = TrendFit("parametric", np.array([t16[0], t16[1]]), None, int(t16[3]))
@@ -610,8 +664,8 @@ class ResidentFit:
             ctx.h2d(d_fit_all, fit_all)
             self._tail(d_fitted, d_t16, None, prior_var, contrast, ridge, lfc_null, alt_hypothesis, begin, check)
             self._to_caller_order()
-            if d_table_all is not None:
-                self.comm.allgather_dev([(self.d_slab_out, d_table_all)], self._slab_len)
+            if self.comm is not None:
+                exchange_tables()
             ctx.d2h(self._h_slab, self.d_slab_out)
             ctx.sync()
         gw = np.clip(H["gw"], self.min_disp, self.max_disp)
@@ -639,7 +693,7 @@ class ResidentFit:
             raise RuntimeError("run() was told not to gather (ResidentFit.gather = False)")
         W, L = self.comm.world, self._slab_len
         tab = self.ctx.pinned_empty((W, L))
-        self.ctx.d2h(tab, self._dev("table_all", W * L * 8))
+        self.ctx.d2h(tab, self._d_table_all)
         self.ctx.sync()
         sizes = self.comm.sizes
         names = {"mom": "mom", "genewise": "gw", "genewise_converged": "gw_conv", "map": "map", "map_converged": "map_conv",

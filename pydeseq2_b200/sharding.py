@@ -4,6 +4,8 @@ the path is the dispersion trend + prior (``dds.py:799-884``), which need the ge
 normalised means of all genes -- one small all-gather of two float64 vectors.
 
 ``NcclComm`` runs that all-gather with NCCL on device buffers through the C ABI (``pdq_allgather_f64_dev``);
+``PeerWindow`` is the single-node fast path on top of it: one kernel per exchange that stores the shard's vectors straight into
+every peer's HBM over NVLink and waits for the peers' stores (copy + barrier, no NCCL on the data path);
 ``TorchDistComm`` does the same through ``torch.distributed`` (used with the ``gloo`` backend by the CPU tests
 of the multi-rank host logic).
 """
@@ -139,12 +141,13 @@ class NcclComm(_PaddedGather):
             self._cap = n
             self._hs = self.ctx.pinned_empty((n,))
             self._hr = self.ctx.pinned_empty((n * world,))
-        self._hs[:] = send
-        self.ctx.h2d(self._send, self._hs)
+        hs, hr = self._hs[:n], self._hr[: n * world]  # the staging blocks keep the largest size seen
+        hs[:] = send
+        self.ctx.h2d(self._send, hs)
         self.ctx.check(self.ctx.lib.pdq_allgather_f64_dev(self.ctx.h, self._c_dptr(self._send), self._c_dptr(self._recv), n))
-        self.ctx.d2h(self._hr, self._recv)
+        self.ctx.d2h(hr, self._recv)
         self.ctx.sync()
-        return self._hr.copy()
+        return hr.copy()
 
     def allgather_dev(self, pairs, count):
         """Device-to-device all-gather of several equal-length vectors as ONE NCCL group (a single fused launch on the context's
@@ -156,5 +159,80 @@ class NcclComm(_PaddedGather):
         recv = (C.c_void_p * k)(*[p[1] for p in pairs])
         self.ctx.check(self.ctx.lib.pdq_allgather_multi_f64_dev(self.ctx.h, k, send, recv, int(count)))
 
+    def barrier(self):
+        self._gather_equal(np.zeros(1))
+
+    def open_window(self, data_bytes: int) -> "PeerWindow":
+        """Collective: every rank allocates a receive window of ``data_bytes`` and maps its peers' (``PeerWindow``)."""
+        return PeerWindow(self, data_bytes)
+
     def close(self):
         self.ctx.check(self.ctx.lib.pdq_comm_destroy(self.ctx.h))
+
+
+class PeerUnavailable(RuntimeError):
+    """The ranks cannot map each other's device memory (no CUDA IPC / peer access): callers keep the NCCL exchange."""
+
+
+class PeerWindow:
+    """Peer-memory exchange of the gene shards of ONE node (``pdq_peer_*`` in ``include/pydeseq2_b200.h``): every rank owns a
+    device window that all peers map through CUDA IPC; :meth:`push` is one kernel that stores this rank's segments into every
+    rank's window over NVLink and returns -- on the stream -- when all ranks' segments have arrived here.  Construction and
+    :meth:`close` are collective over ``comm`` (the IPC handles travel through its host-staged all-gather); either every rank
+    gets a window or every rank raises :class:`PeerUnavailable`."""
+
+    def __init__(self, comm: NcclComm, data_bytes: int):
+        from . import _lib
+
+        ctx = self.ctx = comm.ctx
+        self.comm = comm
+        self.data_bytes = int(data_bytes)
+        self._group = None
+        w, d = C.c_void_p(), C.c_void_p()
+        hbuf = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        err = None
+        try:
+            ctx.check(ctx.lib.pdq_peer_window_alloc(ctx.h, self.data_bytes, C.byref(w), C.byref(d), hbuf))
+        except RuntimeError as e:  # keep the collective sequence alive: the other ranks are waiting in the all-gather
+            err = e
+        self.window, self.data = w.value, d.value
+        # one double per handle byte: the bits of an IPC handle are not a float64 anybody should normalise
+        mine = np.frombuffer(hbuf.raw, dtype=np.uint8).astype(np.float64)
+        handles = comm._gather_equal(mine).astype(np.uint8).tobytes()
+        if err is None:
+            g = C.c_void_p()
+            hb = C.create_string_buffer(handles, len(handles))
+            try:
+                ctx.check(ctx.lib.pdq_peer_group_open(ctx.h, C.c_void_p(self.window), comm.world, comm.rank, hb, C.byref(g)))
+                self._group = g
+            except RuntimeError as e:
+                err = e
+        ok = comm._gather_equal(np.array([0.0 if err is not None else 1.0]))
+        if not bool(np.all(ok == 1.0)):
+            self.close()
+            raise PeerUnavailable(str(err) if err is not None else "a peer rank could not map the windows")
+
+    def push(self, segments, count: int):
+        """``segments`` = [(send_ptr, byte offset of the gathered vector in the window's payload), ...] (at most 4), ``count``
+        doubles per rank each; segment of rank r lands at ``offset + r * count * 8`` in every window.  No segments: barrier."""
+        k = len(segments)
+        send = (C.c_void_p * max(k, 1))(*[s[0] for s in segments])
+        offs = (C.c_uint64 * max(k, 1))(*[int(s[1]) for s in segments])
+        self.ctx.check(self.ctx.lib.pdq_peer_push_dev(self.ctx.h, self._group, k, send, offs, int(count)))
+
+    def check(self):
+        """After a stream synchronisation: raise when a push gave up waiting for a peer."""
+        st = C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.pdq_peer_status(self.ctx.h, self._group, C.byref(st)))
+        if st.value:
+            raise RuntimeError(f"peer exchange timed out waiting for rank {st.value - 1}")
+
+    def close(self):
+        """Collective: unmap the peers' windows, wait until every rank has done so, free the own window."""
+        if self._group is not None:
+            self.ctx.check(self.ctx.lib.pdq_peer_group_close(self.ctx.h, self._group))
+            self._group = None
+        self.comm.barrier()
+        if self.window:
+            self.ctx.check(self.ctx.lib.pdq_peer_window_free(self.ctx.h, C.c_void_p(self.window)))
+            self.window = self.data = None

@@ -1,7 +1,7 @@
 """Worker of tests/test_gpu_multi.py: one process per GPU (torchrun), gene shards over NCCL through the C ABI.
 
-Every rank fits its contiguous gene shard with `ResidentFit(comm=NcclComm)`; the pass ends with the all-gather of the result
-tables.  Checks (rank 0 holds the single-GPU fit of the WHOLE matrix as the reference):
+Every rank fits its contiguous gene shard with `ResidentFit(comm=NcclComm)`; the pass ends with the exchange of the result
+tables -- grouped NCCL all-gathers or the peer-memory push kernel (PDQ_MG_EXCHANGE = nccl | peer).  Checks (rank 0 holds the single-GPU fit of the WHOLE matrix as the reference):
   * trend coefficients / prior variance of the sharded pass == single-GPU pass (same kernel on the gathered vectors; the NaN
     pads of short shards only change the summation order),
   * every per-gene table gathered on EVERY rank == the single-GPU tables,
@@ -45,6 +45,7 @@ def main():
     comm = NcclComm(ctx, sizes, rank, uid.cpu().numpy().tobytes())
     lo, hi = shard_bounds(G, world, rank)
     rf = ResidentFit(ctx, X, sf, comm=comm, with_cooks=True)
+    rf.exchange = os.environ.get("PDQ_MG_EXCHANGE", "nccl")  # "peer": must map the peers' windows or fail
     rf.upload(counts[:, lo:hi])
     errs = {}
     ok = True
@@ -54,6 +55,7 @@ def main():
         rf1 = ResidentFit(inf1._ops.ctx, X, sf, with_cooks=True)
         rf1.upload(counts)
         ref = rf1.run()
+    dist.barrier()
     for tag in ("eager", "eager2", "graph", "graph2"):  # third pass captures, fourth replays
         full = rf.gather_results(rf.run())
         # every rank must hold identical tables: compare a digest across ranks
@@ -79,10 +81,20 @@ def main():
             # IRLS stopping rule pass on attenuated; p-values of ~1e-300 amplify relative differences
             ok = ok and e["trend"] < 1e-9 and e["prior_var"] < 1e-9 and e["genewise"] < 1e-12 and e["dispersions"] < 1e-6 and \
                 e["lfc"] < 1e-6 and e["stat"] < 1e-6 and e["se"] < 1e-6 and e["cooks_outlier_equal"] and e["flags_equal"]
+    # a pass without the table exchange (peer flavour: ends with the bare barrier) returns the same shard results
+    last = rf.run()
+    rf.gather = False
+    for _ in range(3):
+        again = rf.run()
+        ok = ok and all(np.array_equal(np.asarray(again[k]), np.asarray(last[k]), equal_nan=True) for k in ("dispersions", "lfc", "pvalue"))
+    rf.gather = True
+    used_peer = rf._win is not None
+    ok = ok and (used_peer == (rf.exchange == "peer"))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({"world": world, "sizes": sizes, "N": N, "G": G, "design": kind, "ok": bool(flag.item()), "errors": errs}), flush=True)
+        print(json.dumps({"world": world, "sizes": sizes, "N": N, "G": G, "design": kind, "exchange": "peer" if used_peer else "nccl", "ok": bool(flag.item()),
+                          "errors": errs}), flush=True)
     rf.close()
     dist.barrier()
     dist.destroy_process_group()
