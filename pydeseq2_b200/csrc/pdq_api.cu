@@ -1593,9 +1593,10 @@ extern "C" int pdq_allgather_multi_f64_dev(pdq_ctx* c, int k, const double* cons
 // peers of the node).  ONE kernel per exchange reads the rank's segment once and stores it into the same place of EVERY rank's
 // window over NVLink / NVSwitch (plain peer stores), then signals the peers and waits for theirs: copy + barrier in one launch,
 // capturable in the pass's CUDA graph.  Window layout: 4096 bytes of control words, data behind.
-//   control: word 0 = number of exchanges this rank has completed (local), byte 128 * (1 + r) = arrival counter of rank r:
-//   every block of r's push kernel adds 1 after its stores are fenced system-wide.
-static constexpr int kPeerMaxWorld = 16, kPeerBlocks = 64, kPeerThreads = 512;
+//   control: word 0 = number of exchanges this rank has completed, word 1 = finished blocks of the running push (both local);
+//   byte 128 * (1 + r) = arrival counter of rank r: the last block of r's push kernel adds 1 after all of r's stores are fenced
+//   system-wide.
+static constexpr int kPeerMaxWorld = 16, kPeerThreads = 512;
 static constexpr size_t kPeerCtrlBytes = 4096;
 
 struct pdq_peer_group {
@@ -1651,18 +1652,27 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_push(const PeerPushArgs a
             }
         }
     }
+    // the LAST block of this rank to finish its stores signals the peers (one arrival per rank and exchange, whatever the grid)
+    __shared__ int last;
+    unsigned long long* ctrl = reinterpret_cast<unsigned long long*>(a.base[a.rank]);
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
-        for (int q = 1; q < a.world; ++q) {
-            const int r = (a.rank + q) % a.world;
-            atomicAdd_system(reinterpret_cast<unsigned long long*>(a.base[r] + 128 * (1 + a.rank)), 1ULL);
+        const unsigned long long done = atomicAdd(&ctrl[1], 1ULL);
+        last = (done == gridDim.x - 1);
+        if (last) {
+            ctrl[1] = 0;
+            __threadfence_system();
+            for (int q = 1; q < a.world; ++q) {
+                const int r = (a.rank + q) % a.world;
+                atomicAdd_system(reinterpret_cast<unsigned long long*>(a.base[r] + 128 * (1 + a.rank)), 1ULL);
+            }
         }
     }
-    if (blockIdx.x != 0) return;
-    // block 0: wait until every peer's blocks of the same exchange have arrived here
-    unsigned long long* ctrl = reinterpret_cast<unsigned long long*>(a.base[a.rank]);
-    const unsigned long long target = (ctrl[0] + 1) * (unsigned long long)gridDim.x;
+    __syncthreads();
+    if (!last) return;
+    // ... and waits until every peer's segments of the same exchange have arrived here
+    const unsigned long long target = ctrl[0] + 1;
     if ((int)threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
         const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(a.base[a.rank] + 128 * (1 + threadIdx.x));
         const unsigned long long t0 = global_timer_ns();
@@ -1676,7 +1686,7 @@ __global__ void __launch_bounds__(kPeerThreads) k_peer_push(const PeerPushArgs a
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) ctrl[0] += 1;
+    if (threadIdx.x == 0) ctrl[0] = target;
 }
 
 extern "C" int pdq_peer_window_alloc(pdq_ctx* c, size_t data_bytes, void** window_out, void** data_out, void* handle_out) {
@@ -1761,7 +1771,11 @@ extern "C" int pdq_peer_push_dev(pdq_ctx* c, pdq_peer_group* g, int k, const dou
     a.err = g->err_dev;
     static const unsigned long long timeout_ms = getenv("PDQ_PEER_TIMEOUT_MS") ? strtoull(getenv("PDQ_PEER_TIMEOUT_MS"), nullptr, 10) : 10000ULL;
     a.timeout_ns = timeout_ms * 1000000ULL;
-    k_peer_push<<<kPeerBlocks, kPeerThreads, 0, c->stream>>>(a);
+    // 64 blocks of 512 threads keep the NVLink store path busy (measured on 2 GPUs: 32 MB leave in 36 us with 64, 148 or 296
+    // blocks alike -- profiles/r2s_peer_probe_n2.txt) and leave a short tail before the signal; PDQ_PEER_BLOCKS overrides
+    static const int forced = getenv("PDQ_PEER_BLOCKS") ? atoi(getenv("PDQ_PEER_BLOCKS")) : 0;
+    const int blocks = forced > 0 ? forced : 64;
+    k_peer_push<<<blocks, kPeerThreads, 0, c->stream>>>(a);
     CU(c, cudaGetLastError());
     c->launches += 1;
     return PDQ_OK;
