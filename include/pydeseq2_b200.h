@@ -67,6 +67,9 @@ int pdq_set_lanes_per_gene(pdq_ctx* ctx, int lanes);
 /* ... and PDQ_DEBUG_FORCE_SHRINK_GRID every gene of pdq_lfc_shrink_nbinom_glm (two-column designs) through
  * grid_fit_shrink_beta (grid_search.py:224-318). */
 #define PDQ_DEBUG_FORCE_SHRINK_GRID 4
+/* PDQ_DEBUG_FAIL_IRLS_OPTIMIZER: the optimiser branch of pdq_irls behaves as if its minimiser had reported failure
+ * (`res.success == False`, utils.py:402): two-column designs then take the reference's grid_fit_beta (grid_search.py:145-221). */
+#define PDQ_DEBUG_FAIL_IRLS_OPTIMIZER 8
 int pdq_set_debug_flags(pdq_ctx* ctx, int flags);
 /* Measured FP64 FMA throughput of the context's device in TFLOP/s (dependent-free DFMA chains on every SM, CUDA-event timed):
  * the arithmetic roofline bench.py reports next to the HBM one -- the per-gene kernels are FP64-pipe bound. */

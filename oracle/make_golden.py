@@ -488,8 +488,32 @@ def main_e2e():
     gen_e2e("continuous_n30", 30, 300, "continuous", 14, 8)
 
 
+def main_grid_beta():
+    """``grid_beta_*.npz``: the reference's ``grid_fit_beta`` (grid_search.py:145-221) -- the last resort of ``irls_solver`` on
+    two-column designs (utils.py:402-409) -- on genes of the per-call fixtures, incl. genes that are all zero in one group (the
+    minimum then sits on a flat, ridge-only stretch of the grid)."""
+    import pydeseq2.utils  # noqa: F401  (utils and grid_search import each other: utils first)
+    from pydeseq2.grid_search import grid_fit_beta
+
+    for source, n_genes in (("two_level_n24", 12), ("large_counts_n12", 6)):
+        z = np.load(os.path.join(OUT, f"calls_{source}.npz"))
+        counts, X, sf, disp = z["counts"], z["X"], z["sf"], z["disp"]
+        if X.shape[1] != 2:
+            continue
+        counts = np.ascontiguousarray(counts[:, :n_genes])
+        # two more genes: expressed in one group only / nowhere (every sample at the min_mu clamp for very negative coefficients)
+        one_group = np.where(X[:, 1] > 0, counts[:, 0], 0)
+        counts = np.column_stack([counts, one_group, np.zeros_like(one_group)])
+        disp = np.concatenate([disp[:n_genes], [disp[0], 0.5]])
+        beta = np.array([grid_fit_beta(counts[:, i], sf, X, disp[i]) for i in range(counts.shape[1])])
+        np.savez_compressed(os.path.join(OUT, f"grid_beta_{source}.npz"), counts=counts, X=X, sf=sf, disp=disp, beta=beta)
+        print("wrote grid_beta_" + source, beta.shape)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "e2e":  # end-to-end fixtures only
+    if len(sys.argv) > 1 and sys.argv[1] == "grid_beta":
+        main_grid_beta()
+    elif len(sys.argv) > 1 and sys.argv[1] == "e2e":  # end-to-end fixtures only
         main_e2e()
         main_e2e_edge()
         main_e2e_alt()
@@ -505,3 +529,4 @@ if __name__ == "__main__":
         main_e2e()
         main_e2e_edge()
         main_e2e_alt()
+        main_grid_beta()

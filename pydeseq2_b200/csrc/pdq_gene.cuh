@@ -325,6 +325,7 @@ struct IrlsParams {
     int maxiter;
     int full_rank;
     int few_rows;  // the design has few distinct rows (categorical factors): reuse exp(x'beta) while the row repeats
+    int fail_optimizer;  // test hook (PDQ_DEBUG_FAIL_IRLS_OPTIMIZER): the optimiser branch reports `success = False`
 };
 
 // one fused sweep over the gene's samples at coefficient vector `beta`:
@@ -677,6 +678,69 @@ PDQ_UNROLL_P
     }
 }
 
+// numpy.linspace node i of n: arange(n) * step + start with step = (stop - start) / (n - 1), two roundings (no FMA contraction,
+// so the nodes are the reference's bit for bit); the last node is `stop` exactly
+PDQ_HD double linspace_at(double lo, double hi, int n, int i) {
+    if (i == n - 1) return hi;
+    const double step = (hi - lo) / (double)(n - 1);
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(__dmul_rn((double)i, step), lo);
+#else
+    volatile double prod = (double)i * step;
+    return prod + lo;
+#endif
+}
+
+// grid_fit_beta (grid_search.py:145-221), the reference's last resort for two-column designs when its optimiser reports failure
+// (utils.py:402-409): 60 x 60 nodes on [-30, 30]^2, then 60 x 60 on one coarse cell either side of the best node; loss =
+// nb_nll(y, max(sf exp(X b), 0.5), alpha) + 0.5e-6 |b|^2 -- the CALLER's min_mu and bounds are not passed on (`grid_fit_beta(counts,
+// size_factors, X, disp)`) --, np.argmin's first minimum in row-major order (a NaN node counts as the minimum, like np.argmin).
+// Only the part of the likelihood that depends on b is summed; the rest is the same number at every node.
+PDQ_HD void irls_grid_gene(const Group& grp, const DesignS& d, const int64_t* y, int64_t ld, double r, double (&out)[2]) {
+    constexpr int K = 60;
+    const double min_mu = 0.5, log_min_mu = log(0.5);
+    double lo0 = -30.0, hi0 = 30.0, lo1 = -30.0, hi1 = 30.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        double best = 0.0;
+        int bi = 0, bj = 0;
+        bool best_nan = false;
+        for (int i = 0; i < K; ++i) {
+            const double b0 = linspace_at(lo0, hi0, K, i);
+            for (int j = 0; j < K; ++j) {
+                const double b1 = linspace_at(lo1, hi1, K, j);
+                double f = 0.0;
+                for (int n = grp.si; n < d.N; n += grp.T) {
+                    const double* row = d.X + (size_t)n * d.RS;
+                    const double yv = (double)y[n * ld];
+                    const double eta = fma(row[1], b1, row[0] * b0);
+                    const double mu_raw = d.sf[n * d.RS] * exp(eta);
+                    const bool cl = mu_raw < min_mu;
+                    const double mu = cl ? min_mu : mu_raw;
+                    const double lmu = cl ? log_min_mu : log(mu);
+                    f += fma(yv + r, log(r + mu), -yv * lmu);
+                }
+                f = grp.sum(f);
+                f = fma(0.5 * kRidge, fma(b0, b0, b1 * b1), f);
+                const bool first = (i == 0 && j == 0);
+                const bool is_nan = !(f == f);
+                if (first || (!best_nan && (is_nan || f < best))) {
+                    best = f;
+                    best_nan = is_nan;
+                    bi = i;
+                    bj = j;
+                }
+            }
+        }
+        out[0] = linspace_at(lo0, hi0, K, bi);
+        out[1] = linspace_at(lo1, hi1, K, bj);
+        if (pass == 0) {
+            const double delta = linspace_at(-30.0, 30.0, K, 1) - (-30.0);
+            lo0 = out[0] - delta; hi0 = out[0] + delta;
+            lo1 = out[1] - delta; hi1 = out[1] + delta;
+        }
+    }
+}
+
 template <int P>
 PDQ_HD void irls_optimizer_gene(const Group& grp, const DesignS& d, const SmallMat<P>& pinv, const IrlsParams& prm,
                                 const int64_t* y, int64_t ld, double alpha, double* beta_out, double* mu_out,
@@ -805,6 +869,20 @@ PDQ_UNROLL_P
                     active = false;
                     ok = true;
                 }
+            }
+        }
+    }
+    if (prm.fail_optimizer) ok = false;
+    if constexpr (P == 2) {
+        // utils.py:402-409: `not res.success and num_vars <= 2` -> grid_fit_beta; `converged` stays False.  (With one column the
+        // reference's grid_fit_beta raises on the shape of `beta.T`; nothing to mirror.)
+        const bool need = valid && !ok;
+        if (grp.any(need)) {
+            double gb[2];
+            irls_grid_gene(grp, d, y, ld, r, gb);
+            if (need) {
+                beta[0] = gb[0];
+                beta[1] = gb[1];
             }
         }
     }

@@ -1058,7 +1058,8 @@ int PDQ_TUFN(launch_irls)(const LaunchCfg& c, const DesignDev& d, const int64_t*
         IrlsArgs<P> a;
         a.dv = DesignView{d.pack, d.N, d.staged ? (int)(d.smem_bytes - 16) : 0};
         a.pinv = pinv_of<P>(d);
-        a.prm = IrlsParams{h.min_mu, h.beta_tol, h.min_beta, h.max_beta, h.maxiter, d.full_rank, d.few_rows};
+        a.prm = IrlsParams{h.min_mu, h.beta_tol, h.min_beta, h.max_beta, h.maxiter, d.full_rank, d.few_rows,
+                           (c.debug & PDQ_DEBUG_FAIL_IRLS_OPTIMIZER) ? 1 : 0};
         a.counts = counts; a.ld = ld; a.G = G; a.lgT = c.lgT; a.disp = disp;
         a.beta = beta; a.mu = mu; a.hat = hat; a.conv = conv; a.ld_out = ld_out;
         a.status = status; a.n_fallback = n_fallback; a.ticket = c.tickets;

@@ -456,19 +456,6 @@ PDQ_UNROLL_P
 // grid fallback for two-column designs (grid_search.py:224-318): 60 x 60 nodes on [-30, 30]^2, then 60 x 60 on one coarse cell
 // either side of the best node; np.argmin's first minimum in row-major order.  The reference calls nbinomFn with its default
 // shrink_index = 1 here whatever the caller asked for.
-PDQ_HD double linspace_at(double lo, double hi, int n, int i) {
-    // numpy.linspace: arange(n) * step + start with step = (stop - start) / (n - 1), two roundings (no FMA contraction, so
-    // the nodes are the reference's bit for bit); the last node is `stop` exactly
-    if (i == n - 1) return hi;
-    const double step = (hi - lo) / (double)(n - 1);
-#if defined(__CUDA_ARCH__)
-    return __dadd_rn(__dmul_rn((double)i, step), lo);
-#else
-    volatile double prod = (double)i * step;
-    return prod + lo;
-#endif
-}
-
 PDQ_HD void shrink_grid_gene(const Group& grp, const DesignS& d, ShrinkParams prm, const int64_t* y, int64_t ld, double size,
                              double* beta_out, double* ih_out, bool valid) {
     constexpr int K = 60;

@@ -118,6 +118,34 @@ def check_irls_bounded_optimizer(inf, force):
         assert f(b2[i], i) <= f(rb, i) + 1e-7 * abs(f(rb, i)), i
 
 
+GRID_BETA = ["two_level_n24", "large_counts_n12"]
+
+
+def check_irls_grid_fallback(inf, force, name):
+    """utils.py:402-409: the optimiser reports failure on a two-column design -> `grid_fit_beta` (grid_search.py:145-221).
+    `force(True)` sends every gene through the optimiser branch AND makes it report failure; the fixtures hold the REAL
+    reference's grid answer (oracle/make_golden.py: main_grid_beta).  The coefficients are grid nodes: equal to the last bit,
+    unless two nodes tie within rounding; mu / hat follow from them like the tail of irls_solver; converged = False."""
+    g = load_golden("grid_beta_" + name)
+    c, X, sf, disp, want = g["counts"], g["X"], g["sf"], g["disp"], g["beta"]
+    force(True)
+    try:
+        b, m, h, cv = inf.irls(c, sf, X, disp, 0.5, 1e-8)
+    finally:
+        force(False)
+    assert inf.last_irls_fallbacks == c.shape[1]
+    assert (np.asarray(cv) == 0).all()
+    np.testing.assert_allclose(b, want, rtol=0, atol=1e-12)
+    for i in range(c.shape[1]):  # tail of irls_solver at the grid's coefficients (utils.py:423-438)
+        mu = sf * np.exp(X @ want[i])
+        muc = np.maximum(mu, 0.5)
+        W = muc / (1.0 + muc * disp[i])
+        Hinv = np.linalg.inv((X.T * W) @ X + 1e-6 * np.eye(2))
+        hat = W * np.einsum("ij,jk,ik->i", X, Hinv, X)
+        np.testing.assert_allclose(np.asarray(m)[:, i], mu, rtol=1e-10)
+        np.testing.assert_allclose(np.asarray(h)[:, i], hat, rtol=1e-8, atol=1e-14)
+
+
 def check_alpha_grid(inf, force):
     """Grid fallback (grid_search.py:54-142): forced for every gene, compared with the reference's grid search."""
     g = load_golden("calls_two_level_n24")

@@ -221,14 +221,16 @@ int emu_irls(const int64_t* counts, int64_t ld, int N, int G, const double* sf, 
     Pack k = make_pack(X, sf, N, p);
     EMU_DISPATCH(p, {
         const SmallMat<P> pi = pinv_of<P>(k);
-        const IrlsParams prm{min_mu, beta_tol, min_beta, max_beta, maxiter, k.full_rank, design_distinct_rows(X, N, p, 16) <= 16};
+        // force_optimizer: bit 0 = every gene takes the optimiser branch, bit 1 = that branch reports failure (grid_fit_beta at p = 2)
+        const IrlsParams prm{min_mu, beta_tol, min_beta, max_beta, maxiter, k.full_rank, design_distinct_rows(X, N, p, 16) <= 16,
+                             (force_optimizer >> 1) & 1};
         double lg_tab[kPsiK];
         for (int g = 0; g < G; ++g) {
             with_lanes([&](const Group& grp) {
                 irls_gene<P>(grp, k.d, pi, prm, counts + g, ld, disp[g], beta + (size_t)g * P, mu + g, hat + g, G, conv + g,
                              status + g, true, lg_tab, kLogFact);
             });
-            if (force_optimizer) status[g] = kIrlsNeedsOptimizer;
+            if (force_optimizer & 1) status[g] = kIrlsNeedsOptimizer;
             if (status[g] == kIrlsNeedsOptimizer)
                 with_lanes([&](const Group& grp) {
                     irls_optimizer_gene<P>(grp, k.d, pi, prm, counts + g, ld, disp[g], beta + (size_t)g * P, mu + g, hat + g, G,

@@ -37,6 +37,12 @@ def test_irls_optimizer_branch(backend):
     ec.check_irls_bounded_optimizer(inf, lambda on: setattr(ops, "force_optimizer", int(on)))
 
 
+@pytest.mark.parametrize("name", ec.GRID_BETA)
+def test_irls_grid_fallback(backend, name):
+    inf, ops = backend
+    ec.check_irls_grid_fallback(inf, lambda on: setattr(ops, "force_optimizer", 3 if on else 0), name)
+
+
 def test_alpha_grid_fallback(backend):
     inf, ops = backend
     ec.check_alpha_grid(inf, lambda on: setattr(ops, "force_grid", int(on)))

@@ -44,6 +44,11 @@ def test_irls_optimizer_branch(inf):
     ec.check_irls_bounded_optimizer(inf, _force(inf, 1))
 
 
+@pytest.mark.parametrize("name", ec.GRID_BETA)
+def test_irls_grid_fallback(inf, name):
+    ec.check_irls_grid_fallback(inf, _force(inf, 1 | 8), name)  # PDQ_DEBUG_FORCE_IRLS_OPTIMIZER | PDQ_DEBUG_FAIL_IRLS_OPTIMIZER
+
+
 def test_alpha_grid_fallback(inf):
     ec.check_alpha_grid(inf, _force(inf, 2))
 

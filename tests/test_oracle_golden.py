@@ -63,6 +63,15 @@ def test_oracle_replays_reference_tape(name):
     assert {"irls", "alpha_mle", "wald_test", "fit_rough_dispersions", "fit_moments_dispersions"} <= seen
 
 
+@pytest.mark.parametrize("name", ["two_level_n24", "large_counts_n12"])
+def test_oracle_grid_fit_beta(name):
+    """The restated `grid_fit_beta` (grid_search.py:145-221) lands on the real reference's grid node."""
+    g = load_golden("grid_beta_" + name)
+    for i in range(g["counts"].shape[1]):
+        got = nbglm.grid_fit_beta(g["counts"][:, i], g["sf"], g["X"], g["disp"][i])
+        np.testing.assert_allclose(got, g["beta"][i], rtol=0, atol=1e-12)
+
+
 def test_nb_nll_is_a_normalised_pmf():
     """Same property the reference's only hot-path unit test checks (tests/test_utils.py:11-33)."""
     for mu, alpha in ((3.0, 0.5), (40.0, 0.05), (0.7, 2.0)):
