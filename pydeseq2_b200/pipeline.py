@@ -386,8 +386,8 @@ class ResidentFit:
         self.d_hat = self._dev("hat", ng)
         # every per-gene result lives in ONE device slab mirrored by one page-locked host block: a pass ends with a single
         # device-to-host copy instead of a dozen small ones.  With gene shards every vector is laid out with the LARGEST shard's
-        # length `Gs` and NaN behind this shard's last gene (written here, once): the slab then is directly the send buffer of the
-        # equal-count NCCL all-gathers -- no per-step padding, no staging.
+        # length `Gs` and NaN behind this shard's last gene (written here, once): the slab then is directly the send
+        # segment of the exchanges (peer-memory push kernel or equal-count NCCL all-gathers) -- no per-step padding, no staging.
         per_gene = ("mom", "means", "gw", "gw_conv", "map", "map_conv", "disp", "conv", "pv", "stat", "se", "outlier",
                     "robust_disp", "cooks_outlier", "cooks_replaced")
         Gs = self.Gs = self.comm.max_size if self.comm is not None else G
@@ -582,7 +582,8 @@ class ResidentFit:
                                            self.max_disp, 1.0, None, 1, 0, c_d(self.d_gw), c_d(self.d_gw_conv), None,
                                            c_d(self.d_hint) if self.use_hint else None))
             # 4. trend + prior: global over ALL genes of ALL shards (dds.py:799-884).  With gene shards the per-gene
-            #    vectors are all-gathered over NCCL first, device to device; the fit itself is one cluster launch.
+            #    vectors are exchanged first, device to device (peer-memory push kernel or grouped NCCL all-gathers); the fit itself
+            #    is one launch (a thread-block cluster, or a cooperative grid from 65 536 genes).
             if self.comm is not None:
                 begin("allgather")
                 exchange_vectors()
