@@ -319,7 +319,7 @@ int pdq_comm_destroy(pdq_ctx* ctx);
  * context's stream: it stores segment i (`count` doubles) of this rank at payload offset recv_off_bytes[i] + rank * count * 8 of
  * EVERY rank's window and completes once all ranks' segments have arrived in the own window (copy + barrier; k = 0: barrier
  * only); capturable into a CUDA graph.  A peer that never arrives is reported through `pdq_peer_status` (1 + its rank) after
- * PDQ_PEER_TIMEOUT_MS (default 10 000) instead of hanging the device.  Every rank must close its group before any rank frees
+ * PDQ_PEER_TIMEOUT_MS (default 30 000) instead of hanging the device.  Every rank must close its group before any rank frees
  * its window.  Replaces, like the NCCL calls above, the host-side concatenation of per-shard results a multi-process caller of the
  * reference would do (the reference itself is single-process: `default_inference.py:18-41` fans genes out over joblib workers). */
 #define PDQ_PEER_HANDLE_BYTES 64

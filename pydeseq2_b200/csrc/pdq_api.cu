@@ -1769,7 +1769,7 @@ extern "C" int pdq_peer_push_dev(pdq_ctx* c, pdq_peer_group* g, int k, const dou
     }
     a.count = count;
     a.err = g->err_dev;
-    static const unsigned long long timeout_ms = getenv("PDQ_PEER_TIMEOUT_MS") ? strtoull(getenv("PDQ_PEER_TIMEOUT_MS"), nullptr, 10) : 10000ULL;
+    static const unsigned long long timeout_ms = getenv("PDQ_PEER_TIMEOUT_MS") ? strtoull(getenv("PDQ_PEER_TIMEOUT_MS"), nullptr, 10) : 30000ULL;
     a.timeout_ns = timeout_ms * 1000000ULL;
     // 64 blocks of 512 threads keep the NVLink store path busy (measured on 2 GPUs: 32 MB leave in 36 us with 64, 148 or 296
     // blocks alike -- profiles/r2s_peer_probe_n2.txt) and leave a short tail before the signal; PDQ_PEER_BLOCKS overrides
