@@ -55,7 +55,23 @@ def main(fixture, out, subclass=False):
         shrunk = backend.lfc_shrink_nbinom_glm(design_matrix=X, counts=dds.X[:, nz], size=size[nz], offset=offset,
                                               prior_no_shrink_scale=15, prior_scale=float(np.minimum(np.sqrt(prior_var), 1)),
                                               optimizer="L-BFGS-B", shrink_index=k)
-    np.savez(out, baseMean=res["baseMean"].values, log2FoldChange=res["log2FoldChange"].values, lfcSE=res["lfcSE"].values,
+    # the variance-stabilising transformation, another caller of the same plugin methods (dds.py:349-515: intercept-only design,
+    # `fit_genewise_dispersions(vst=True)` + trend fit, then a closed-form transform): through the backend under test and through
+    # the reference's own CPU backend, in this process
+    from oracle.make_golden import ref_inference
+
+    vst = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for tag, inf in (("b200", backend), ("ref", ref_inference())):
+            cls = DeseqDataSet if tag == "b200" else __import__("pydeseq2.dds", fromlist=["DeseqDataSet"]).DeseqDataSet
+            for fit_type in ("parametric", "mean"):
+                d2 = cls(counts=counts_df, metadata=meta, design=design_df, inference=inf, quiet=True)
+                d2.vst(fit_type=fit_type)
+                vst[f"vst_{fit_type}_{tag}"] = np.asarray(d2.layers["vst_counts"], dtype=float)
+            # transform of held-out counts with the FITTED log means (the override must have stored them: dds.py:438-480)
+            vst[f"vst_new_{tag}"] = np.asarray(d2.vst_transform(counts[: N // 2] + 1), dtype=float)
+    np.savez(out, **vst, baseMean=res["baseMean"].values, log2FoldChange=res["log2FoldChange"].values, lfcSE=res["lfcSE"].values,
              stat=res["stat"].values, pvalue=res["pvalue"].values, padj=res["padj"].values, LFC=dds.varm["LFC"].values,
              dispersions=dds.var["dispersions"].values, replaced=np.asarray(dds.var["replaced"], dtype=float),
              cooks_outlier=np.asarray(dds.cooks_outlier(), dtype=float), shrunk_lfc=shrunk[0], shrink_converged=shrunk[2],

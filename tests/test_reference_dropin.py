@@ -48,6 +48,10 @@ def test_real_orchestrator_with_b200_backend(name, mode, tmp_path):
     mostly(got["pvalue"][big], ref["final_pvalue"][big], 1e-3)
     ok = ~np.isnan(ref["final_padj"]) & big
     mostly(got["padj"][ok], ref["final_padj"][ok], 1e-3)
+    # vst(): same transformed counts as with the reference's CPU backend (the trend coefficients come from two different
+    # minimisers of the same objective, ~4e-6 apart: SURVEY App. B)
+    for key in ("vst_parametric", "vst_mean", "vst_new"):
+        np.testing.assert_allclose(got[key + "_b200"], got[key + "_ref"], rtol=2e-5, atol=1e-6)
     # the shrinkage plugin call made by the orchestrator's own lfc_shrink() went through the backend
     assert got["shrink_flag_set"] == 1.0 and got["shrink_converged"].mean() > 0.99
     assert np.isfinite(got["shrunk_lfc"]).all()
