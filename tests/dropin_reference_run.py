@@ -78,5 +78,49 @@ def main(fixture, out, subclass=False):
              shrink_flag_set=np.float64(ds.shrunk_LFCs), n_cpus=np.float64(backend.n_cpus or 0))
 
 
+def variants(fixture, out):
+    """Two more ways the reference's orchestrator drives the same plugin calls, each through the backend under test and through
+    the reference's own CPU backend: (a) the iterative size-factor estimator it switches to when every gene holds a zero
+    (dds.py:682-690, 1460-1545: rounds of genewise / MAP dispersion fits on an intercept-only design around a Powell search) --
+    reached here through the subclass, whose device median-of-ratios raises the same ValueError first; (b) `low_memory=True`
+    (dds.py:934, 1032, 1103: (N, G) intermediates are dropped as soon as they are used)."""
+    from pydeseq2.dds import DeseqDataSet
+    from pydeseq2.ds import DeseqStats
+
+    from emu.emu_ops import EmuOps
+    from oracle.make_golden import ref_inference
+    from pydeseq2_b200.inference import B200Inference
+    from pydeseq2_b200.integration import b200_dataset_class
+
+    g = np.load(fixture)
+    counts, X, contrast = g["counts"][:, :120], g["design"], g["contrast"]
+    N, G = counts.shape
+    idx = [f"s{i}" for i in range(N)]
+    design_df = pd.DataFrame(X, index=idx, columns=[f"x{j}" for j in range(X.shape[1])])
+    meta = pd.DataFrame({"dummy": np.arange(N)}, index=idx)
+    with_zero = counts.copy()
+    with_zero[np.random.default_rng(3).integers(0, N, G), np.arange(G)] = 0  # a zero in every gene
+    res = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for tag, cls, inf in (("b200", b200_dataset_class(), B200Inference(_ops=EmuOps())), ("ref", DeseqDataSet, ref_inference())):
+            df = pd.DataFrame(with_zero, index=idx, columns=[f"g{i}" for i in range(G)])
+            d = cls(counts=df, metadata=meta, design=design_df, inference=inf, quiet=True)
+            d.fit_size_factors()
+            res["iterative_sf_" + tag] = np.asarray(d.obs["size_factors"], dtype=float)
+            df = pd.DataFrame(counts, index=idx, columns=[f"g{i}" for i in range(G)])
+            d = cls(counts=df, metadata=meta, design=design_df, inference=inf, quiet=True, low_memory=True)
+            d.deseq2()
+            st = DeseqStats(d, contrast=contrast, inference=inf, quiet=True)
+            st.summary()
+            for col in ("log2FoldChange", "lfcSE", "pvalue", "padj"):
+                res[f"lowmem_{col}_{tag}"] = st.results_df[col].values.astype(float)
+            res["lowmem_kept_" + tag] = np.float64(sum(k.startswith("_") for k in list(d.layers.keys()) + list(d.obsm.keys())))
+    np.savez(out, **res)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], subclass=len(sys.argv) > 3 and sys.argv[3] == "subclass")
+    if len(sys.argv) > 3 and sys.argv[3] == "variants":
+        variants(sys.argv[1], sys.argv[2])
+    else:
+        main(sys.argv[1], sys.argv[2], subclass=len(sys.argv) > 3 and sys.argv[3] == "subclass")

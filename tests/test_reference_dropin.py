@@ -56,3 +56,22 @@ def test_real_orchestrator_with_b200_backend(name, mode, tmp_path):
     assert got["shrink_flag_set"] == 1.0 and got["shrink_converged"].mean() > 0.99
     assert np.isfinite(got["shrunk_lfc"]).all()
     assert got["n_cpus"] > 0   # the orchestrator set the attribute it expects on a backend (dds.py:323-333)
+
+
+def test_real_orchestrator_variants_with_b200_backend(tmp_path):
+    """Iterative size factors (every gene holds a zero) and `low_memory=True`: the orchestrator's other routes through the same
+    plugin calls give the reference CPU backend's numbers with the B200 backend."""
+    out = str(tmp_path / "variants.npz")
+    env = dict(os.environ)
+    env.pop("PYTHONPATH", None)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "dropin_reference_run.py"), os.path.join(GOLDEN, "e2e_two_level_n24.npz"), out,
+                        "variants"], capture_output=True, text=True, timeout=1500, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = np.load(out)
+    np.testing.assert_allclose(got["iterative_sf_b200"], got["iterative_sf_ref"], rtol=1e-5)
+    assert got["lowmem_kept_b200"] == got["lowmem_kept_ref"] == 0  # the (N, G) intermediates were dropped on both sides
+    np.testing.assert_array_equal(np.isnan(got["lowmem_padj_b200"]), np.isnan(got["lowmem_padj_ref"]))
+    np.testing.assert_allclose(got["lowmem_log2FoldChange_b200"], got["lowmem_log2FoldChange_ref"], rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(got["lowmem_lfcSE_b200"], got["lowmem_lfcSE_ref"], rtol=1e-4)
+    np.testing.assert_allclose(got["lowmem_pvalue_b200"], got["lowmem_pvalue_ref"], rtol=1e-3)
+    np.testing.assert_allclose(got["lowmem_padj_b200"], got["lowmem_padj_ref"], rtol=1e-3)
